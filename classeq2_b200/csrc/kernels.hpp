@@ -1,0 +1,41 @@
+// Launch interface of the sm_100a kernels (kernels.cu), used by the C-ABI layer (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/classeq_b200.h"
+#include "device_types.hpp"
+
+namespace cls {
+
+// device-side status values are the ABI's cls_status values
+constexpr uint32_t CLS_DEV_UNCL_NO_MATCH = CLS_STATUS_UNCL_NO_MATCH;
+constexpr uint32_t CLS_DEV_UNCL_NO_ROOT = CLS_STATUS_UNCL_NO_ROOT;
+constexpr uint32_t CLS_DEV_UNCL_COVERAGE = CLS_STATUS_UNCL_COVERAGE;
+constexpr uint32_t CLS_DEV_UNCL_NO_INTROSPECTION = CLS_STATUS_UNCL_NO_INTROSPECTION;
+constexpr uint32_t CLS_DEV_MAX_RESOLUTION = CLS_STATUS_MAX_RESOLUTION;
+constexpr uint32_t CLS_DEV_IDENTITY_FOUND = CLS_STATUS_IDENTITY_FOUND;
+constexpr uint32_t CLS_DEV_INCONCLUSIVE = CLS_STATUS_INCONCLUSIVE;
+constexpr uint32_t CLS_DEV_ERR_MAX_ITERATIONS = CLS_STATUS_ERR_MAX_ITERATIONS;
+constexpr uint32_t CLS_DEV_ERR_ROOT_NO_CHILDREN = CLS_STATUS_ERR_ROOT_NO_CHILDREN;
+
+// Per-warp shared-memory geometry of one launch (all reads of a launch share it; the host
+// groups reads into length classes so that short reads do not pay for long ones).
+struct PlaceGeom {
+    uint32_t str_words;       // 32-bit words per decoded strand string
+    uint32_t t1_size, t1_log2;  // hit de-duplication set (u32 slots), power of two >= 2 * max hits
+    uint32_t t2_size, t2_log2;  // node-set histogram (keys + counts), power of two > max hits
+    uint32_t fan_cap;         // vote counters per warp (max non-leaf fan-out of the tree)
+    uint32_t words_per_warp;
+};
+
+PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout);
+
+cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
+                         const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
+                         const PlaceGeom &g, int sm_count, cudaStream_t stream);
+
+cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, uint64_t *out, cudaStream_t stream);
+
+}  // namespace cls

@@ -1,0 +1,200 @@
+"""Thin object layer over the C ABI: a model resident on one GPU and batched placement calls.
+
+All compute happens in ``libclasseq_b200.so`` (hand-written sm_100a kernels); this module only
+marshals numpy buffers.  Reference call being replaced for a whole batch at once:
+``place_sequence`` (core/src/use_cases/place_sequences/place_sequence.rs:42-602) as invoked by the
+``par_bridge`` closure of ``place_sequences`` (place_sequences/mod.rs:123-159).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from .model import FlatModel, Tree, _ptr
+
+RESULT_DTYPES = (("status", np.uint8), ("node_id", np.uint64), ("one", np.int32), ("rest", np.int32),
+                 ("n_query_kmers", np.uint32), ("n_matched", np.uint32), ("n_root_matched", np.uint32),
+                 ("iterations", np.uint32))
+
+
+@dataclass
+class PlaceParams:
+    """place_sequence.rs:46-48 - ``None`` means the reference's default (:64-75)."""
+    max_iterations: Optional[int] = None
+    min_match_coverage: Optional[float] = None
+    remove_intersection: Optional[bool] = None
+
+    def to_c(self) -> _lib.Params:
+        p = _lib.Params()
+        _lib.lib.cls_params_default(C.byref(p))
+        if self.max_iterations is not None:
+            p.max_iterations = int(self.max_iterations)
+        if self.min_match_coverage is not None:
+            p.min_match_coverage = float(self.min_match_coverage)
+        if self.remove_intersection is not None:
+            p.remove_intersection = 1 if self.remove_intersection else 0
+        return p
+
+
+class BatchResult:
+    """Struct-of-arrays result of a batch (one element per query, caller order)."""
+
+    def __init__(self, n: int):
+        self.n = n
+        for name, dt in RESULT_DTYPES:
+            setattr(self, name, np.zeros(n, dtype=dt))
+
+    def to_c(self) -> _lib.Result:
+        r = _lib.Result()
+        r.status = _ptr(self.status, _lib.u8p)
+        r.node_id = _ptr(self.node_id, _lib.u64p)
+        r.one = _ptr(self.one, _lib.i32p)
+        r.rest = _ptr(self.rest, _lib.i32p)
+        r.n_query_kmers = _ptr(self.n_query_kmers, _lib.u32p)
+        r.n_matched = _ptr(self.n_matched, _lib.u32p)
+        r.n_root_matched = _ptr(self.n_root_matched, _lib.u32p)
+        r.iterations = _ptr(self.iterations, _lib.u32p)
+        return r
+
+    def row(self, i: int) -> dict:
+        return {name: getattr(self, name)[i].item() for name, _ in RESULT_DTYPES}
+
+
+def make_batch(seqs: Union[Sequence[Union[str, bytes]], Tuple[np.ndarray, np.ndarray]]):
+    """(bases uint8[], offsets uint64[n+1]) from a list of strings, or pass such a pair through."""
+    if isinstance(seqs, tuple) and len(seqs) == 2 and isinstance(seqs[0], np.ndarray):
+        bases = np.ascontiguousarray(seqs[0], dtype=np.uint8)
+        offsets = np.ascontiguousarray(seqs[1], dtype=np.uint64)
+        return bases, offsets
+    bs = [s.encode("utf-8") if isinstance(s, str) else bytes(s) for s in seqs]
+    offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offsets[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    return bases, offsets
+
+
+def _c_batch(bases: np.ndarray, offsets: np.ndarray) -> _lib.Batch:
+    b = _lib.Batch()
+    b.n_queries = len(offsets) - 1
+    b.bases = _ptr(bases, _lib.u8p)
+    b.offsets = _ptr(offsets, _lib.u64p)
+    return b
+
+
+class Index:
+    """A model serialised to one GPU (``cls_index_create``): upload once per model."""
+
+    def __init__(self, model: Union[FlatModel, Tree, "_lib.ModelView"], device: int = 0, keepalive=None):
+        if isinstance(model, Tree):
+            model = FlatModel.from_tree(model)
+        view = model.view if hasattr(model, "view") else model
+        self._keep = (model, keepalive)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib.cls_index_create(C.byref(view), int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def info(self) -> dict:
+        inf = _lib.IndexInfo()
+        _lib.check(_lib.lib.cls_index_get_info(self._h, C.byref(inf)))
+        return {f: getattr(inf, f) for f, _ in inf._fields_}
+
+    def place_batch(self, seqs, params: Optional[PlaceParams] = None) -> BatchResult:
+        """Host buffers in, host buffers out (``cls_place_batch``)."""
+        bases, offsets = make_batch(seqs)
+        res = BatchResult(len(offsets) - 1)
+        cb, cp, cr = _c_batch(bases, offsets), (params or PlaceParams()).to_c(), res.to_c()
+        _lib.check(_lib.lib.cls_place_batch(self._h, C.byref(cb), C.byref(cp), C.byref(cr)))
+        return res
+
+    def place_batch_into(self, bases: np.ndarray, offsets: np.ndarray, res: BatchResult,
+                         params: Optional[PlaceParams] = None) -> None:
+        """Same as :meth:`place_batch` without any allocation on the Python side (benchmarks)."""
+        cb, cp, cr = _c_batch(bases, offsets), (params or PlaceParams()).to_c(), res.to_c()
+        _lib.check(_lib.lib.cls_place_batch(self._h, C.byref(cb), C.byref(cp), C.byref(cr)))
+
+    def upload(self, seqs) -> "ResidentBatch":
+        return ResidentBatch(self, seqs)
+
+    def timing(self) -> dict:
+        t = _lib.Timing()
+        _lib.check(_lib.lib.cls_get_timing(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in t._fields_}
+
+    def close(self):
+        if self._h:
+            _lib.lib.cls_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ResidentBatch:
+    """A packed query batch resident in HBM (``cls_batch_upload``): upload once, place many times."""
+
+    def __init__(self, index: Index, seqs):
+        self.index = index
+        bases, offsets = make_batch(seqs)
+        self.n = len(offsets) - 1
+        self._h = C.c_void_p()
+        cb = _c_batch(bases, offsets)
+        _lib.check(_lib.lib.cls_batch_upload(index._h, C.byref(cb), C.byref(self._h)))
+
+    def place(self, params: Optional[PlaceParams] = None, stream: int = 0) -> None:
+        """Enqueue the placement kernels on ``stream`` (a ``cudaStream_t`` as int); asynchronous."""
+        cp = (params or PlaceParams()).to_c()
+        _lib.check(_lib.lib.cls_place_resident(self.index._h, self._h, C.byref(cp), C.c_void_p(stream)))
+
+    def fetch(self, stream: int = 0) -> BatchResult:
+        res = BatchResult(self.n)
+        cr = res.to_c()
+        _lib.check(_lib.lib.cls_resident_fetch(self.index._h, self._h, C.c_void_p(stream), C.byref(cr)))
+        return res
+
+    def nbytes(self) -> int:
+        return int(_lib.lib.cls_resident_bytes(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lib.cls_resident_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def debug_kmer_hashes(seq: Union[str, bytes], k_size: int, device: int = 0) -> np.ndarray:
+    """All window hashes of one query in the reference's order (``cls_debug_kmer_hashes``)."""
+    b = seq.encode() if isinstance(seq, str) else bytes(seq)
+    arr = np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(0, np.uint8)
+    cap = max(0, 2 * (len(b) - k_size + 1))
+    out = np.zeros(max(cap, 1), dtype=np.uint64)
+    n = C.c_uint64()
+    _lib.check(_lib.lib.cls_debug_kmer_hashes(int(device), int(k_size), _ptr(arr, _lib.u8p), len(b),
+                                              _ptr(out, _lib.u64p), cap, C.byref(n)))
+    return out[: n.value]
+
+
+def host_murmur3_h1(data: bytes, seed: int = 0) -> int:
+    arr = np.frombuffer(data, dtype=np.uint8).copy() if data else np.zeros(1, np.uint8)
+    return int(_lib.lib.cls_debug_host_murmur3_x64_128_h1(_ptr(arr, _lib.u8p), len(data), seed))
+
+
+def filter_sequence(line: Union[str, bytes]) -> str:
+    """``SequenceBody::remove_non_iupac_from_sequence`` (sequence.rs:47-56) via the C ABI."""
+    b = line.encode("utf-8") if isinstance(line, str) else bytes(line)
+    arr = np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(1, np.uint8)
+    out = np.zeros(max(len(b), 1), dtype=np.uint8)
+    n = _lib.lib.cls_filter_sequence(_ptr(arr, _lib.u8p), len(b), _ptr(out, _lib.u8p), len(out))
+    return out[:n].tobytes().decode("ascii")

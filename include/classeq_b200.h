@@ -1,0 +1,270 @@
+/*
+ * classeq_b200.h - C ABI of the B200-native placement path of classeq.
+ *
+ * This is the drop-in boundary for ONE path of the reference
+ * (LepistaBioinformatics/classeq2, v0.10.0): everything that happens inside
+ *   core/src/use_cases/place_sequences/place_sequence.rs:42-602   (place_sequence)
+ * for every query of a batch, i.e. what the closure at
+ *   core/src/use_cases/place_sequences/mod.rs:151-159
+ * computes.  The reference has no FFI layer of its own (pure safe Rust); the
+ * entry points below are what a Rust `extern "C"` block would bind (see
+ * INTEGRATION.md for the binding and for the call-site patch).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer, the
+ *     library owns device memory behind the opaque handles;
+ *   - every function returns 0 (CLS_OK) or a negative cls_error code and never
+ *     throws/aborts across the ABI; the text of the last error of the calling
+ *     thread is available from cls_last_error();
+ *   - per-query failures (reference: `Err(MappedErrors)` -> a line in
+ *     `<out>.error`, mod.rs:160-169) are per-query STATUS values, not call errors;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with CLS_ERR_CUDA.
+ */
+#ifndef CLASSEQ_B200_H
+#define CLASSEQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLS_ABI_VERSION 1
+
+typedef enum cls_error {
+    CLS_OK = 0,
+    CLS_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, inconsistent sizes, malformed view            */
+    CLS_ERR_CUDA = -2,             /* CUDA runtime/driver failure (incl. "no device")              */
+    CLS_ERR_UNSUPPORTED = -3,      /* model outside the supported envelope (see cls_index_create) */
+    CLS_ERR_OUT_OF_MEMORY = -4,
+    CLS_ERR_NCCL = -5
+} cls_error;
+
+/* Node kinds: clade.rs:5-16 (serde UPPERCASE "ROOT" | "NODE" | "LEAF"). */
+enum { CLS_KIND_ROOT = 0, CLS_KIND_NODE = 1, CLS_KIND_LEAF = 2 };
+
+/* cls_model_view.flags */
+enum {
+    /* tree.root.children is `None` (place_sequence.rs:199-206 -> Err for every query
+     * that survives the coverage gate).  `Some(vec![])` is expressed by an empty
+     * child range instead. */
+    CLS_MODEL_ROOT_CHILDREN_NONE = 1u
+};
+
+/*
+ * Borrowed, flat view of the reference's model types, built by the caller right
+ * after `load_database` (ports/cli/src/cmds/place_sequences.rs:135,
+ * ports/watcher/src/cmds/watch_dir/mod.rs:355):
+ *
+ *   Tree.root / Clade      core/src/domain/dtos/tree.rs:9-52, clade.rs:18-38
+ *   Tree.kmers_map         core/src/domain/dtos/kmers_map.rs:77-87
+ *                          map: MinimizerKey(u64) -> MinimizerValue(HashMap<u64 hash, HashSet<u64 node id>>)
+ *
+ * Nodes are listed in any order with node 0 == tree.root; `child_idx` holds node
+ * INDICES (not ids) in the order of `Clade.children`.  Each (bucket key, hash)
+ * pair of the two-level map is one entry; its node set is `set_node_ids[set_off[s]
+ * .. set_off[s+1])` with s = entry_set[i] (several entries may share one set; a
+ * caller that does not de-duplicate passes entry_set[i] = i).  Node sets hold the
+ * reference's sparse u64 node IDS; ids that do not occur in the tree are legal
+ * and ignored, exactly as the reference never consults them.
+ */
+typedef struct cls_model_view {
+    uint32_t k_size;                /* KmersMap.k_size  (kmers_map.rs:79)                */
+    uint32_t m_size;                /* KmersMap.m_size  (kmers_map.rs:83)                */
+    uint32_t flags;
+    uint32_t reserved;
+    uint64_t n_nodes;
+    const uint64_t *node_id;        /* [n_nodes]   Clade.id                              */
+    const uint8_t *node_kind;       /* [n_nodes]   CLS_KIND_*  (Clade.kind; is_leaf() is by kind, clade.rs:166-172) */
+    const uint64_t *child_off;      /* [n_nodes+1] CSR over child_idx                    */
+    const uint64_t *child_idx;      /* [child_off[n_nodes]] node indices                 */
+    uint64_t n_entries;
+    const uint64_t *entry_bucket;   /* [n_entries] MinimizerKey.0                        */
+    const uint64_t *entry_hash;     /* [n_entries] k-mer hash (murmur3_x64_128(.., 0).0) */
+    const uint64_t *entry_set;      /* [n_entries] index into set_off                    */
+    uint64_t n_sets;
+    const uint64_t *set_off;        /* [n_sets+1]                                        */
+    const uint64_t *set_node_ids;   /* [set_off[n_sets]] node ids                        */
+} cls_model_view;
+
+/*
+ * A batch of queries as the reference's FASTA reader hands them to
+ * place_sequence (file_or_stdin.rs:76-116 after sequence.rs:47-56): bodies are
+ * ASCII, already filtered to A/C/G/T.  Lower-case a/c/g/t is accepted and
+ * upper-cased (kmers_map.rs:410, :431-443).  Any other byte makes that one query
+ * CLS_STATUS_ERR_INVALID_BASE (the reference would panic, kmers_map.rs:440).
+ * Query i is bases[offsets[i] .. offsets[i+1]).
+ */
+typedef struct cls_batch {
+    uint64_t n_queries;
+    const uint8_t *bases;
+    const uint64_t *offsets;        /* [n_queries+1], non-decreasing */
+} cls_batch;
+
+/* Knobs of place_sequence (place_sequence.rs:46-48, :64-75); same meaning as the
+ * CLI's -i / -m / -r (ports/cli/src/cmds/place_sequences.rs:18-82).  The Option<>
+ * defaults are applied by cls_params_default(). */
+typedef struct cls_params {
+    int32_t max_iterations;         /* default 1000                                    */
+    uint32_t remove_intersection;   /* default 0 (false)                               */
+    double min_match_coverage;      /* default 0.7; clamped to [0,1] by the library    */
+} cls_params;
+
+/*
+ * Per-query outcome.  Strings of the reference are reconstructed by the host
+ * from (status, node_id, n_root_matched) - see INTEGRATION.md.
+ */
+typedef enum cls_status {
+    CLS_STATUS_ERR_TOO_SHORT = 0,      /* Err("The sequence does not contain enough kmers.")  place_sequence.rs:98-102 */
+    CLS_STATUS_UNCL_NO_MATCH = 1,      /* Unclassifiable("Query sequence {header:?} may not be related to the phylogeny") :130-139 */
+    CLS_STATUS_UNCL_NO_ROOT = 2,       /* Unclassifiable("Query sequence has no overlapping kmers with the reference tree") :156-166 */
+    CLS_STATUS_UNCL_COVERAGE = 3,      /* Unclassifiable("Insufficient kmers coverage: {n_root_matched}") :241-254 */
+    CLS_STATUS_UNCL_NO_INTROSPECTION = 4, /* Unclassifiable("Tree introspection not possible. ...") :446-454 */
+    CLS_STATUS_MAX_RESOLUTION = 5,     /* MaxResolutionReached(node_id, "LCA Accepted") :456-465 */
+    CLS_STATUS_IDENTITY_FOUND = 6,     /* IdentityFound(AdherenceTest{clade: node_id, one, rest}) update_introspection_node.rs:32-87 */
+    CLS_STATUS_INCONCLUSIVE = 7,       /* Inconclusive(.., "Multiple proposals") :584-598 (provably unreachable; node_id = parent) */
+    CLS_STATUS_ERR_MAX_ITERATIONS = 8, /* Err("The maximum number of iterations has been reached.") :295-301 */
+    CLS_STATUS_ERR_ROOT_NO_CHILDREN = 9, /* Err("The root node does not have children. This is unexpected.") :199-206 */
+    CLS_STATUS_ERR_INVALID_BASE = 10   /* non-ACGT byte in the body (reference: panic) */
+} cls_status;
+
+/* Caller-allocated result arrays, each of length n_queries.  `one`/`rest` are the
+ * AdherenceTest fields (adherence_test.rs:6-17, i32); the three counters are the
+ * values the reference records on its tracing span (place_sequence.rs:90-182). */
+typedef struct cls_result {
+    uint8_t *status;          /* cls_status                                               */
+    uint64_t *node_id;        /* Clade.id of the placement (IDENTITY_FOUND, MAX_RESOLUTION, INCONCLUSIVE), else 0 */
+    int32_t *one;             /* IDENTITY_FOUND only, else 0                              */
+    int32_t *rest;            /* IDENTITY_FOUND only, else 0                              */
+    uint32_t *n_query_kmers;  /* query.kmers.count        = 2*(L-k+1), 0 if L < k         */
+    uint32_t *n_matched;      /* query.kmers.treeMatches  = |M|                           */
+    uint32_t *n_root_matched; /* subject.kmers.queryMatches = |M_r|                       */
+    uint32_t *iterations;     /* descent levels entered                                   */
+} cls_result;
+
+/* Device-side timing of the last cls_place_batch / cls_place_resident call on a
+ * handle (CUDA events on the library's stream); the analogue of the reference's
+ * PlacementTime (place_sequences/mod.rs:30-34) at batch granularity. */
+typedef struct cls_timing {
+    double pack_ms;    /* host 2-bit packing + length ordering   */
+    double h2d_ms;     /* pinned host -> device copies            */
+    double kernel_ms;  /* placement kernel(s)                     */
+    double d2h_ms;     /* result records device -> host           */
+    double total_ms;   /* wall clock of the call                  */
+    uint64_t kernel_launches;
+} cls_timing;
+
+typedef struct cls_index cls_index;                 /* a model resident on one GPU            */
+typedef struct cls_resident_batch cls_resident_batch; /* a packed query batch resident in HBM  */
+
+int cls_abi_version(void);
+const char *cls_last_error(void);                   /* thread-local, never NULL               */
+void cls_params_default(cls_params *p);
+
+/* Number of CUDA devices visible (>= 0) or a negative cls_error. */
+int cls_device_count(void);
+
+/*
+ * Serialise the model to the GPU (once per model; the hook is right after
+ * `load_database`).  Builds the open-addressed k-mer table, the de-duplicated
+ * node-set records and the flattened tree, and uploads them to `device`.
+ * CLS_ERR_UNSUPPORTED is returned - never a silently different answer - for:
+ *   m_size > 12; k_size == 0; duplicated Clade ids; the same k-mer hash stored
+ *   under two different bucket keys (a cross-bucket 64-bit collision,
+ *   p ~ n^2 / 2^65); more than 2^24 nodes.
+ */
+int cls_index_create(const cls_model_view *model, int device, cls_index **out);
+void cls_index_destroy(cls_index *index);
+
+/* Introspection of a created index (all sizes in elements unless stated). */
+typedef struct cls_index_info {
+    uint32_t k_size, m_size;
+    uint64_t n_entries;        /* entries uploaded (entries in unreachable buckets are dropped) */
+    uint64_t n_buckets;        /* 32-byte buckets of two 16-byte slots                           */
+    uint64_t table_bytes;
+    uint64_t n_distinct_sets;
+    uint64_t set_arena_bytes;
+    uint64_t n_nonleaf_nodes;
+    uint32_t max_nonleaf_fanout;
+    int32_t device;
+} cls_index_info;
+int cls_index_get_info(const cls_index *index, cls_index_info *info);
+
+/*
+ * The hot path, host buffers in / host buffers out: pack to 2 bit, order by
+ * length, copy to the device, place, copy the result records back.  Callable
+ * concurrently from several host threads on the same handle (each call takes a
+ * private stream + workspace).  Replaces the body of the `par_bridge` closure's
+ * call to place_sequence (mod.rs:123-159) for the whole batch.
+ */
+int cls_place_batch(cls_index *index, const cls_batch *batch, const cls_params *params,
+                    cls_result *result);
+
+/*
+ * The same path split at the PCIe boundary, for callers (and benchmarks) that
+ * keep the packed batch resident in HBM: upload once, place many times.
+ * `stream` is a cudaStream_t (or NULL for the library's own stream);
+ * cls_place_resident only enqueues work, cls_resident_fetch synchronises the
+ * stream and scatters the result records into `result`.
+ */
+int cls_batch_upload(cls_index *index, const cls_batch *batch, cls_resident_batch **out);
+int cls_place_resident(cls_index *index, cls_resident_batch *rb, const cls_params *params,
+                       void *stream);
+int cls_resident_fetch(cls_index *index, cls_resident_batch *rb, void *stream, cls_result *result);
+void cls_resident_destroy(cls_resident_batch *rb);
+/* Bytes the resident batch occupies in HBM (packed bases + descriptors + result records). */
+uint64_t cls_resident_bytes(const cls_resident_batch *rb);
+
+int cls_get_timing(const cls_index *index, cls_timing *out);
+
+/*
+ * Parity/debug exports.
+ *
+ * cls_debug_kmer_hashes: run the extraction + hashing kernel alone on one query
+ * and return, in the reference's order (all forward windows, then all windows of
+ * the reverse complement: kmers_map.rs:387-395), the 2*(L-k+1) values
+ * murmurhash3_x64_128(window, 0).0.  `*n_out` receives the count; at most `cap`
+ * values are written.  Does not need an index.
+ *
+ * cls_debug_host_murmur3_x64_128_h1: the host-side hash used while building the
+ * index (bucket keys of all 4^m prefixes); exported so tests can pin it to the
+ * reference's known answers without a GPU.
+ */
+int cls_debug_kmer_hashes(int device, uint32_t k_size, const uint8_t *bases, uint64_t len,
+                          uint64_t *out_hashes, uint64_t cap, uint64_t *n_out);
+uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, uint64_t seed);
+
+/*
+ * Host helpers mirroring the reference's input side (no GPU needed).
+ *
+ * cls_filter_sequence: SequenceBody::remove_non_iupac_from_sequence
+ * (sequence.rs:47-56) for one line of UTF-8 text: upper-case, keep A/C/G/T.
+ * Writes at most `cap` bytes to `out`, returns the filtered length.
+ */
+uint64_t cls_filter_sequence(const uint8_t *line, uint64_t len, uint8_t *out, uint64_t cap);
+
+/*
+ * Host-side model builder (no GPU needed): the k-mer -> node-set map that the reference's
+ * `map_kmers_to_tree` (core/src/use_cases/build_database/mod.rs:26-181) produces for a tree and
+ * one sequence per tip, with every tip paired with ITS OWN sequence (the reference pairs header i
+ * with sequence i-1, mod.rs:93-116 - a build-side defect outside the placement path).
+ * For every tip, every window of the sequence and of its reverse complement
+ * (kmers_map.rs:375-398) is hashed; the node set of a (bucket key, hash) entry is the union of
+ * the root->tip id paths (both ends included, clade.rs:127-156) of the tips containing it.
+ * Only the tree part of `tree` is read (k_size/m_size/nodes/children); `tip_node[i]` is the node
+ * index of the tip whose sequence is bases[offsets[i] .. offsets[i+1]) (ASCII, A/C/G/T only).
+ * cls_built_model_view fills `out` with the tree pointers of `tree` (borrowed from the caller)
+ * plus entry/set arrays owned by the handle; it stays valid until cls_built_model_destroy.
+ */
+typedef struct cls_built_model cls_built_model;
+int cls_model_build(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node,
+                    const uint8_t *bases, const uint64_t *offsets, cls_built_model **out);
+int cls_built_model_view(const cls_built_model *bm, const cls_model_view *tree, cls_model_view *out);
+void cls_built_model_destroy(cls_built_model *bm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLASSEQ_B200_H */
