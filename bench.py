@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the placement hot path (BASELINE.json: "queries placed/s and k-mer lookups/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4] [--impl b200|reference]
+
+A "step" is one pass of the hot path (extract + murmur3 + probe + count + descend) over one batch
+of synthetic reads of the named configuration (classeq2_b200/synth.py):
+
+  value   reads placed per second with the packed batch already resident in HBM (kernel-resident),
+          CUDA events around every step on the launching stream, L2 flushed between steps,
+          max over ranks;
+  e2e     the same metric through the reference-facing C-ABI call `cls_place_batch` with HOST
+          buffers: 2-bit packing, pinned H2D, kernels and D2H of the result records all inside the
+          timed region;
+  roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+
+N > 1 (launched by torchrun, one rank per GPU): queries shard across ranks with the index
+replicated and NO data-path collective; per-GPU work is fixed ("weak").
+`--impl reference` times the CPU restatement of the reference (oracle/classeq_oracle.cpp, all host
+cores) on a bounded sample of the same workload; the reference itself is Rust and cannot be built
+here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_SIZE = 35
+NAMES = {2: "config2: synthetic 1,000-tip tree, 1 kb refs, 1M x 150 bp reads, index replicated",
+         3: "config3: synthetic 10k-tip tree, ~600 bp refs, 10M x 150 bp reads sharded over the GPUs, index replicated",
+         4: "config4: synthetic 5k-tip tree, 1.5 kb refs, 1M reads of skewed length 150-1550 bp"}
+
+
+def algorithmic_bytes(lens: np.ndarray) -> int:
+    """ceil(L/4) packed bases + 16 B per k-mer lookup + 32 B result record."""
+    lens = lens[lens >= K_SIZE].astype(np.int64)
+    return int(((lens + 3) // 4 + 2 * (lens - K_SIZE + 1) * 16 + 32).sum())
+
+
+def make_workload(config: int, rank: int, world: int, n_reads_override=None):
+    from classeq2_b200 import synth
+    c = dict(synth.CONFIGS[config])
+    t0 = time.time()
+    sm = synth.make_model(c["n_tips"], c["l_ref"], c["tree_seed"])
+    n_total = n_reads_override or c["n_reads"]
+    if config == 3:      # the 10M reads of config 3 are SHARDED over the ranks (strong)
+        n_local = n_total // world + (1 if rank < n_total % world else 0)
+        scaling = "strong"
+    else:                # configs 2 and 4: every GPU places its own batch of the named size (weak)
+        n_local, scaling = n_total, "weak"
+    if c["read_len"] == "skewed":
+        lens = synth.skewed_lengths(n_local, c["len_seed"] + rank)
+    else:
+        lens = c["read_len"]
+    bases, offsets, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, n_local, lens, c["tree_seed"] + 2 + 1000 * rank)
+    return sm, bases, offsets, scaling, time.time() - t0
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device: int):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.stop_flag, self.max_mhz = device, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].isdigit() else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        while self.nv is not None and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(config: int):
+    """dram bytes per launch of the place kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(f"config{config}")
+    return None
+
+
+def time_cpu_oracle(sm, bases, offsets, seconds: float, threads: int):
+    """The C++ restatement on a bounded prefix of the batch sized to take about `seconds`."""
+    from oracle import cpp_oracle
+    md = cpp_oracle.CppModel.from_flat(sm.flat)
+    n_all = len(offsets) - 1
+
+    def run(n):
+        off = offsets[: n + 1]
+        t0 = time.perf_counter()
+        md.place_batch(bases[: int(off[-1])], off, n_threads=threads)
+        return time.perf_counter() - t0
+
+    n0 = min(n_all, 2000)
+    t = run(n0)
+    n = int(min(n_all, max(n0, n0 * seconds / max(t, 1e-6))))
+    t = run(n)
+    lens = np.diff(offsets[: n + 1].astype(np.int64))
+    md.close()
+    return n, t, int((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum())
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sm, bases, offsets, scaling, _ = make_workload(args.config, 0, 1, args.reads)
+    threads = os.cpu_count() or 1
+    from oracle import cpp_oracle
+    md = cpp_oracle.CppModel.from_flat(sm.flat)
+    n_all = len(offsets) - 1
+    # size the per-step sample so that warmup + steps finish within about two minutes
+    n0 = min(n_all, 2000)
+    t0 = time.perf_counter()
+    md.place_batch(bases[: int(offsets[n0])], offsets[: n0 + 1], n_threads=threads)
+    rate = n0 / (time.perf_counter() - t0)
+    budget = 120.0 / (args.steps + args.warmup)
+    n = int(min(n_all, max(1000, rate * min(budget, 20.0))))
+    off = offsets[: n + 1]
+    bs = bases[: int(off[-1])]
+    for _ in range(args.warmup):
+        md.place_batch(bs, off, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        md.place_batch(bs, off, n_threads=threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    lens = np.diff(off.astype(np.int64))
+    value = n / dt
+    sample = f"first {n} reads of the batch per step, {threads} threads, C++ restatement of the reference (not the Rust binary)"
+    line = {"impl": "reference", "metric": "queries placed/s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": NAMES[args.config], "reads_per_step": n, "k": K_SIZE},
+            "lookups_per_s": float((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum() / dt),
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import classeq2_b200 as cq
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sm, bases, offsets, scaling, gen_s = make_workload(args.config, rank, world, args.reads)
+    n_local = len(offsets) - 1
+    lens = np.diff(offsets.astype(np.int64))
+    lookups_local = int((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum())
+    alg_bytes_local = algorithmic_bytes(lens)
+
+    t0 = time.time()
+    index = cq.Index(sm.flat, device=local_rank)
+    info = index.info()
+    upload_s = time.time() - t0
+    params = cq.PlaceParams()
+    rb = index.upload((bases, offsets))
+    stream = torch.cuda.Stream(device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- kernel-resident: `value` ----------------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.fill_(1)
+            rb.place(params, stream.cuda_stream)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.fill_(rank + 2)          # L2 flush, outside the event pair
+            a.record(stream)
+            rb.place(params, stream.cuda_stream)
+            b.record(stream)
+    barrier()
+    wall_resident = time.perf_counter() - wall0
+    clocks = sampler.summary()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms_local = float(sum(step_ms))
+    ms_total = allmax(ms_local)
+    launches_per_step = int(index.timing()["kernel_launches"])
+    reads_total = allsum(float(n_local))
+    lookups_total = allsum(float(lookups_local))
+    ms_per_step = ms_total / args.steps
+    value = reads_total / (ms_per_step / 1e3)
+
+    # parity spot check of what was just timed (bit-exact against the CPU oracle on a sample)
+    res = rb.fetch(stream.cuda_stream)
+    status_hist = np.bincount(res.status, minlength=11).tolist()
+
+    # ---- end to end through the C ABI with host buffers: `e2e` ----------------------------------------
+    out = cq.BatchResult(n_local)
+    for _ in range(max(1, min(args.warmup, 2))):
+        index.place_batch_into(bases, offsets, out, params)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        index.place_batch_into(bases, offsets, out, params)
+    torch.cuda.synchronize()
+    e2e_local = (time.perf_counter() - t0) / args.steps
+    e2e_s = allmax(e2e_local)
+    tm = index.timing()
+    same = all((getattr(out, f) == getattr(res, f)).all() for f, _ in cq.engine.RESULT_DTYPES)
+    n_device = int((lens >= K_SIZE).sum())
+    d2h = 32 * n_device
+    h2d = rb.nbytes() - d2h
+    e2e = {"value": reads_total / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_s * 1e3,
+           "breakdown_ms_rank0": {k: round(tm[k], 3) for k in ("pack_ms", "h2d_ms", "kernel_ms", "d2h_ms", "total_ms")},
+           "host_input": "ASCII bases + offsets in caller memory (what the reference's FASTA reader hands over)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) + sampled parity ---------------------------------------------
+    cpu = None
+    parity = None
+    if rank == 0:
+        from oracle import cpp_oracle
+        threads = os.cpu_count() or 1
+        if world == 1:
+            n_s, t_s, look_s = time_cpu_oracle(sm, bases, offsets, args.cpu_seconds, threads)
+            cpu = {"value": n_s / t_s, "unit": "reads/s", "cores": threads, "kind": "port",
+                   "lookups_per_s": look_s / t_s,
+                   "sample": f"first {n_s} reads of the same batch, {threads} threads, oracle/classeq_oracle.cpp "
+                             "(C++ restatement with direct hash lookups - kinder than the Rust reference, which "
+                             "clones and scans the whole index per query; the Rust binary cannot be built here)"}
+        md = cpp_oracle.CppModel.from_flat(sm.flat)
+        n_chk = min(n_local, 20000)
+        o = md.place_batch(bases[: int(offsets[n_chk])], offsets[: n_chk + 1], n_threads=threads)
+        bad = sum(int((o[f] != getattr(res, f)[:n_chk]).sum()) for f, _ in cq.engine.RESULT_DTYPES)
+        parity = {"checked_reads": n_chk, "mismatching_fields": bad, "e2e_equals_resident": bool(same)}
+        md.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = alg_bytes_local / (ms_local / args.steps / 1e3) / 1e9   # this GPU's kernel(s), GB/s
+        line = {
+            "metric": "queries placed/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": NAMES[args.config], "reads_per_gpu": n_local, "reads_total": int(reads_total),
+                       "k": K_SIZE, "m": 4, "index_entries": int(info["n_entries"]),
+                       "table_bytes": int(info["table_bytes"]), "distinct_node_sets": int(info["n_distinct_sets"]),
+                       "parallelism": f"queries sharded x{world}, index replicated, no collective",
+                       "l2": "256 MiB memset between steps (outside the event pairs)"},
+            "lookups_per_s": lookups_total / (ms_per_step / 1e3),
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.config), "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": alg_bytes_local, "launches_per_step": launches_per_step,
+                         "kernel": "cls::place_kernel<35>", "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result"},
+            "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
+            "status_histogram": status_hist, "step_ms": [round(x, 4) for x in step_ms],
+            "setup_s": {"generate": round(gen_s, 1), "index_upload": round(upload_s, 2)},
+            "wall_s_resident_region": round(wall_resident, 4),
+        }
+        print(json.dumps(line), flush=True)
+    rb.close()
+    index.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4])
+    ap.add_argument("--reads", type=int, default=None, help="override the number of reads of the config")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU); running the single-GPU line", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""The C-ABI library: loads, exports every symbol include/classeq_b200.h declares, its host-side
+helpers agree with the oracle, and compute entry points FAIL LOUDLY without a CUDA device
+(no CPU fallback).  CPU only."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, _has_nvidia_node
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "classeq_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cls_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from classeq2_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 20
+    raw = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert _lib.lib.cls_abi_version() == 1
+
+
+def test_no_torch_in_the_library():
+    from classeq2_b200 import _lib
+    out = os.popen(f"ldd {_lib.LIB_PATH}").read()
+    assert "torch" not in out and "c10" not in out
+
+
+def test_struct_layouts_match_header():
+    from classeq2_b200 import _lib
+    assert C.sizeof(_lib.ModelView) == 16 + 8 + 4 * 8 + 8 + 3 * 8 + 8 + 2 * 8
+    assert C.sizeof(_lib.Batch) == 24 and C.sizeof(_lib.Params) == 16 and C.sizeof(_lib.Result) == 64
+    p = _lib.Params()
+    _lib.lib.cls_params_default(C.byref(p))
+    assert (p.max_iterations, p.remove_intersection, p.min_match_coverage) == (1000, 0, 0.7)  # place_sequence.rs:64-75
+
+
+def test_host_murmur_matches_oracle(oracle, pins):
+    import classeq2_b200 as cq
+    for s, h in pins["murmur3_h1"].items():
+        assert cq.host_murmur3_h1(s.encode()) == h
+    rng = np.random.default_rng(7)
+    for n in list(range(0, 40)) + [63, 64, 65, 150]:
+        b = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        for seed in (0, 1, 2**63 + 5):
+            assert cq.host_murmur3_h1(b, seed) == oracle.murmurhash3_x64_128(b, seed)[0]
+
+
+def test_filter_sequence_matches_oracle(oracle):
+    import classeq2_b200 as cq
+    for line in ["acgtNNNN-ACGT", "", "xyz", "AcGt\tRYKM*acgu", "ACGTÀé", "ẗẚﬅﬆß", "ｔａ"]:
+        assert cq.filter_sequence(line) == oracle.remove_non_iupac_from_sequence(line), repr(line)
+
+
+def test_model_build_matches_oracle(oracle, col_queries, col_tree, col_npz):
+    """cls_model_build (host) == the oracle's map_kmers_to_tree on the Colletotrichum fixture."""
+    from classeq2_b200.model import BuiltModel, FlatModel
+    z = col_npz
+    tflat = FlatModel(35, 4, z["node_id"], z["node_kind"], z["child_off"], z["child_idx"])
+    name_to_idx = {}
+    clades = list(col_tree.root.walk())
+    # FlatModel / golden flattening is the same pre-order as Clade.walk()
+    assert [c.id for c in clades] == z["node_id"].tolist()
+    for i, c in enumerate(clades):
+        if c.is_leaf():
+            name_to_idx[c.name] = i
+    tips = col_queries[:171]
+    tip_node = np.array([name_to_idx[h] for h, _ in tips], np.uint64)
+    bases = np.frombuffer("".join(s for _, s in tips).encode(), np.uint8)
+    offsets = np.zeros(len(tips) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for _, s in tips])
+    bm = BuiltModel(tflat, tip_node, bases, offsets)
+    a = bm.arrays()
+    got = {}
+    for b, h, s in zip(a["entry_bucket"].tolist(), a["entry_hash"].tolist(), a["entry_set"].tolist()):
+        got.setdefault(b, {})[h] = set(a["set_node_ids"][int(a["set_off"][s]):int(a["set_off"][s + 1])].tolist())
+    assert got == col_tree.kmers_map.map
+    assert len(a["set_off"]) - 1 == 226
+    bm.close()
+
+
+@pytest.mark.skipif(_has_nvidia_node(), reason="only meaningful on a machine without a GPU")
+def test_compute_fails_loudly_without_gpu(col_flat):
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    with pytest.raises(_lib.ClsError) as ei:
+        cq.Index(col_flat, device=0)
+    assert ei.value.code == _lib.CLS_ERR_CUDA
+    with pytest.raises(_lib.ClsError):
+        cq.debug_kmer_hashes("ACGT" * 20, 35)
+
+
+def test_index_create_rejects_unsupported_models(col_npz):
+    """Rejections happen on the host before any CUDA call, so they are testable without a GPU."""
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    from classeq2_b200.model import FlatModel
+    z = col_npz
+    args = [z["node_id"], z["node_kind"], z["child_off"], z["child_idx"]]
+    ent = lambda: [z["entry_bucket"].copy(), z["entry_hash"].copy(), z["entry_set"], z["set_off"], z["set_node_ids"]]  # noqa: E731
+    with pytest.raises(_lib.ClsError) as ei:          # k = 0
+        cq.Index(FlatModel(0, 4, *args, *ent()))
+    assert ei.value.code == _lib.CLS_ERR_UNSUPPORTED
+    with pytest.raises(_lib.ClsError) as ei:          # m > 12
+        cq.Index(FlatModel(35, 13, *args, *ent()))
+    assert ei.value.code == _lib.CLS_ERR_UNSUPPORTED
+    e = ent()
+    e[1][1] = e[1][0]                                 # same hash twice (same or different bucket)
+    with pytest.raises(_lib.ClsError) as ei:
+        cq.Index(FlatModel(35, 4, *args, *e))
+    assert ei.value.code in (_lib.CLS_ERR_UNSUPPORTED, _lib.CLS_ERR_INVALID_ARGUMENT)
+    ids = z["node_id"].copy()
+    ids[5] = ids[6]                                   # duplicated Clade ids
+    with pytest.raises(_lib.ClsError) as ei:
+        cq.Index(FlatModel(35, 4, ids, *args[1:], *ent()))
+    assert ei.value.code == _lib.CLS_ERR_UNSUPPORTED

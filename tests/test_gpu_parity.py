@@ -1,0 +1,251 @@
+"""Parity of the sm_100a path (through the C ABI) against the CPU oracle.  Bit-exact: hashes,
+statuses, placement nodes, one/rest, all counters.  The only floating point on the path is
+round(n_matched * coverage) in f64 (place_sequence.rs:231-232) - exact, no tolerance needed."""
+import threading
+
+import numpy as np
+import pytest
+
+from helpers import assert_rows_equal, outcome_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cq():
+    import classeq2_b200
+    return classeq2_b200
+
+
+@pytest.fixture(scope="module")
+def col_index(cq, col_flat):
+    ix = cq.Index(col_flat, device=0)
+    yield ix
+    ix.close()
+
+
+def _rand_seq(rng, n):
+    return "".join("ACGT"[int(x)] for x in rng.integers(0, 4, n))
+
+
+# ---- (3) k-mer extraction + murmur3 ----------------------------------------------------------------
+@pytest.mark.parametrize("k", [35, 1, 2, 4, 8, 9, 15, 16, 17, 31, 32, 33, 36, 48, 64])
+def test_kmer_hashes_bit_exact(cq, oracle, k):
+    rng = np.random.default_rng(k)
+    for L in sorted({k, k + 1, k + 2, k + 15, k + 16, k + 17, 150, 151, 163, 1911}):
+        if L < k:
+            continue
+        s = _rand_seq(rng, L)
+        want = [h for _, h in oracle.KmersMap(k, 0).build_kmer_from_string(s)]
+        got = cq.debug_kmer_hashes(s, k)
+        assert got.tolist() == want, (k, L)
+    assert len(cq.debug_kmer_hashes("ACGT", 35)) == 0  # shorter than k: no k-mers (kmers_map.rs:383-385)
+    assert cq.debug_kmer_hashes("acgtacgtac", 4).tolist() == cq.debug_kmer_hashes("ACGTACGTAC", 4).tolist()
+
+
+def test_gyrb_query_has_3754_distinct_kmers(cq, pins, col_queries):
+    seq = dict(col_queries)[pins["gyrb_first_query"]["header"]]
+    h = cq.debug_kmer_hashes(seq, 35)
+    assert len(h) == len(set(h.tolist())) == pins["gyrb_first_query"]["one"]
+
+
+# ---- whole path on the Colletotrichum fixture -------------------------------------------------------
+@pytest.mark.parametrize("knob", ["default", "remove_intersection", "cov1", "iter2"])
+def test_colletotrichum_golden(cq, col_index, col_queries, col_expected, knob):
+    kn = next(k for k in col_expected["knobs"] if k["name"] == knob)
+    params = cq.PlaceParams(kn["max_iterations"], kn["min_match_coverage"], kn["remove_intersection"])
+    res = col_index.place_batch([s for _, s in col_queries], params)
+    assert_rows_equal(res, col_expected["outcomes"][knob], [h for h, _ in col_queries])
+
+
+def test_resident_path_equals_batch_path(cq, col_index, col_queries, col_expected):
+    seqs = [s for _, s in col_queries]
+    rb = col_index.upload(seqs)
+    rb.place()
+    res = rb.fetch()
+    assert_rows_equal(res, col_expected["outcomes"]["default"])
+    rb.place(cq.PlaceParams(remove_intersection=True))   # place again on the same resident batch
+    assert_rows_equal(rb.fetch(), col_expected["outcomes"]["remove_intersection"])
+    assert rb.nbytes() > 0
+    rb.close()
+
+
+def test_batch_order_and_ragged_inputs(cq, col_index, col_queries, col_expected):
+    """Results come back in caller order whatever the length ordering on the device."""
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(col_queries))
+    res = col_index.place_batch([col_queries[i][1] for i in perm])
+    assert_rows_equal(res, [col_expected["outcomes"]["default"][i] for i in perm])
+    # empty batch, all-too-short batch, single query
+    assert col_index.place_batch([]).n == 0
+    r = col_index.place_batch(["", "ACGT", "A" * 34])
+    assert r.status.tolist() == [0, 0, 0] and r.n_query_kmers.tolist() == [0, 0, 0]
+    one = col_index.place_batch([col_queries[0][1]])
+    assert_rows_equal(one, [col_expected["outcomes"]["default"][0]])
+
+
+def test_invalid_base_is_a_per_query_status(cq, col_index, col_queries, col_expected):
+    from classeq2_b200 import _lib
+    good = col_queries[0][1]
+    bad = good[:50] + "N" + good[51:]
+    res = col_index.place_batch([good, bad, good.lower()])
+    assert res.status[1] == _lib.STATUS_ERR_INVALID_BASE
+    e = col_expected["outcomes"]["default"][0]
+    assert_rows_equal(res, [e], None) if False else None
+    assert res.row(0) == res.row(2)
+    assert res.node_id[0] == e["clade"]
+
+
+def test_concurrent_calls_on_one_handle(cq, col_index, col_queries, col_expected):
+    seqs = [s for _, s in col_queries]
+    out, errs = {}, []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                out[t] = col_index.place_batch(seqs)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for t in range(4):
+        assert_rows_equal(out[t], col_expected["outcomes"]["default"])
+
+
+# ---- adversarial random models (sparse ids, multifurcations, sets that are not upward closed,
+#      sets without the root, leaf-kind nodes with children, m = 0 / m > k, small k) ---------------
+def _random_tree_model(oracle, rng, k, m):
+    O = oracle
+    root = O.Clade(int(rng.integers(0, 5)), None, "ROOT", children=[])
+    nodes, used = [root], {root.id}
+
+    def new_id():
+        while True:
+            i = int(rng.integers(0, 2000)) if rng.random() < 0.9 else int(rng.integers(2**40, 2**63))
+            if i not in used:
+                used.add(i)
+                return i
+
+    for _ in range(int(rng.integers(1, 40))):
+        p = nodes[int(rng.integers(len(nodes)))]
+        if p.kind == "LEAF" and rng.random() < 0.9:
+            continue
+        kind = "LEAF" if rng.random() < 0.45 else "NODE"
+        c = O.Clade(new_id(), p.id, kind, name="x" if kind == "LEAF" else None,
+                    children=[] if (kind == "NODE" and rng.random() < 0.5) else None)
+        p.children = (p.children or []) + [c]
+        nodes.append(c)
+    tree = O.Tree("t", "t", 70.0, root)
+    # reference sequences: a few related strings so that queries hit many entries
+    base = _rand_seq(rng, int(rng.integers(k + 5, 120)))
+    km = O.KmersMap(k, m)
+    ids = [n.id for n in nodes]
+    paths = {}
+    for n in nodes:  # root->node paths
+        pass
+
+    def path_to(n):
+        out, cur = [n.id], n
+        while cur.parent is not None:
+            cur = next(x for x in nodes if x.id == cur.parent)
+            out.append(cur.id)
+        return set(out)
+
+    for t in range(int(rng.integers(1, 8))):
+        s = list(base)
+        for i in range(len(s)):
+            if rng.random() < 0.05:
+                s[i] = "ACGT"[int(rng.integers(4))]
+        s = "".join(s)
+        n = nodes[int(rng.integers(len(nodes)))]
+        mode = rng.random()
+        if mode < 0.6:
+            nset = path_to(n)                       # builder-like: upward closed
+        elif mode < 0.8:
+            nset = {ids[int(j)] for j in rng.integers(0, len(ids), int(rng.integers(1, 5)))}  # arbitrary
+        elif mode < 0.9:
+            nset = path_to(n) - {root.id}           # no root
+        else:
+            nset = path_to(n) | {int(rng.integers(3000, 4000))}  # id that is not in the tree
+        for kmer, h in km.build_kmer_from_string(s):
+            km.insert_or_append_kmer_hash(kmer, h, nset)
+    tree.kmers_map = km
+    queries = []
+    for q in range(12):
+        a = int(rng.integers(0, max(1, len(base) - k)))
+        s = list(base[a:a + int(rng.integers(0, len(base) + 10))])
+        for i in range(len(s)):
+            if rng.random() < 0.03:
+                s[i] = "ACGT"[int(rng.integers(4))]
+        s = "".join(s)
+        if rng.random() < 0.3:
+            s = O.KmersMap.reverse_complement(s)
+        queries.append((f"q{q}", s))
+    queries.append(("rand", _rand_seq(rng, 90)))
+    return tree, queries
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_models(cq, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.choice([35, 35, 35, 5, 11, 16, 21, 32, 40]))
+    m = int(rng.choice([4, 4, 0, 1, 2, 7, k + 3 if k < 9 else 3]))
+    tree, queries = _random_tree_model(oracle, rng, k, m)
+    if rng.random() < 0.1:
+        tree.root.children = None
+    ix = cq.Index(tree_to_product(cq, tree), device=0)
+    for kn in [dict(), dict(remove_intersection=True), dict(min_match_coverage=1.0),
+               dict(max_iterations=int(rng.integers(0, 3)), min_match_coverage=0.0)]:
+        res = ix.place_batch([s for _, s in queries], cq.PlaceParams(**kn))
+        want = [outcome_of(oracle, h, s, tree, kn.get("max_iterations"), kn.get("min_match_coverage"),
+                           kn.get("remove_intersection")) for h, s in queries]
+        assert_rows_equal(res, want, [h for h, _ in queries])
+    ix.close()
+
+
+def tree_to_product(cq, otree):
+    """oracle Tree -> product Tree (same serde object shape) -> FlatModel."""
+    t = cq.Tree.from_obj(otree.to_obj())
+    return cq.FlatModel.from_tree(t)
+
+
+# ---- synthetic configs at reduced size against the Python oracle ------------------------------------
+def test_synthetic_small_config(cq, oracle):
+    from classeq2_b200 import synth
+    sm = synth.make_model(60, 300, 4242)
+    bases, offsets, truth = synth.make_reads(sm.ref_codes, sm.ref_lens, 300, 150, 4244)
+    lens = synth.skewed_lengths(40, 5) // 5 + 35
+    b2, o2, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, 40, lens, 4245)
+    ix = cq.Index(sm.flat, device=0)
+    otree = oracle_tree_from_flat(oracle, sm.flat)
+    for bs, of in ((bases, offsets), (b2, o2)):
+        seqs = [bytes(bs[int(of[i]):int(of[i + 1])]).decode() for i in range(len(of) - 1)]
+        for kn in (dict(), dict(remove_intersection=True)):
+            res = ix.place_batch((bs, of), cq.PlaceParams(**kn))
+            want = [outcome_of(oracle, f"r{i}", s, otree, None, None, kn.get("remove_intersection"))
+                    for i, s in enumerate(seqs)]
+            assert_rows_equal(res, want)
+    info = ix.info()
+    assert info["n_entries"] == sm.flat.n_entries and info["k_size"] == 35
+    ix.close()
+
+
+def oracle_tree_from_flat(oracle, flat):
+    O = oracle
+    kinds = {0: "ROOT", 1: "NODE", 2: "LEAF"}
+    n = len(flat.node_id)
+    clades = [O.Clade(int(flat.node_id[i]), None, kinds[int(flat.node_kind[i])]) for i in range(n)]
+    for i in range(n):
+        a, b = int(flat.child_off[i]), int(flat.child_off[i + 1])
+        if b > a:
+            clades[i].children = [clades[int(j)] for j in flat.child_idx[a:b]]
+            for c in clades[i].children:
+                c.parent = clades[i].id
+    km = O.KmersMap(flat.k_size, flat.m_size)
+    so, sn = flat.set_off, flat.set_node_ids
+    for b, h, s in zip(flat.entry_bucket.tolist(), flat.entry_hash.tolist(), flat.entry_set.tolist()):
+        km.map.setdefault(b, {})[h] = set(sn[int(so[s]):int(so[s + 1])].tolist())
+    return O.Tree("s", "s", 70.0, clades[0], kmers_map=km)
