@@ -22,6 +22,7 @@ CLS_ERR_NCCL = -5
 
 KIND_ROOT, KIND_NODE, KIND_LEAF = 0, 1, 2
 MODEL_ROOT_CHILDREN_NONE = 1
+MODEL_FORCE_GENERAL_SETS = 2
 
 (STATUS_ERR_TOO_SHORT, STATUS_UNCL_NO_MATCH, STATUS_UNCL_NO_ROOT, STATUS_UNCL_COVERAGE,
  STATUS_UNCL_NO_INTROSPECTION, STATUS_MAX_RESOLUTION, STATUS_IDENTITY_FOUND, STATUS_INCONCLUSIVE,
@@ -65,7 +66,8 @@ class IndexInfo(C.Structure):
     _fields_ = [("k_size", C.c_uint32), ("m_size", C.c_uint32), ("n_entries", C.c_uint64),
                 ("n_buckets", C.c_uint64), ("table_bytes", C.c_uint64), ("n_distinct_sets", C.c_uint64),
                 ("set_arena_bytes", C.c_uint64), ("n_nonleaf_nodes", C.c_uint64),
-                ("max_nonleaf_fanout", C.c_uint32), ("device", C.c_int32)]
+                ("max_nonleaf_fanout", C.c_uint32), ("device", C.c_int32),
+                ("closed_sets", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class ClsError(RuntimeError):

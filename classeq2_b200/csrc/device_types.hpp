@@ -10,7 +10,8 @@ namespace cls {
 // probe).  bucket = hash & bucket_mask; linear probing over buckets on overflow.
 struct Slot {
     uint64_t hash;     // murmur3_x64_128(kmer, 0).0  (kmers_map.rs:157-159)
-    uint32_t set_off;  // offset (in 8-byte units) of the node-set record in the arena; kEmpty = free
+    uint32_t set_off;  // offset of the node-set record (SetWord units in `arena`, or u32 units in
+                       // `terms`, depending on the descent mode); kEmpty = free slot
     uint32_t code;     // bits 0..23: 2-bit prefix code of the entry's bucket (MinimizerKey);
                        // bit 31 (slot 0 of a bucket only): bucket overflowed at build time
 };
@@ -19,9 +20,9 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kOverflowBit = 0x80000000u;
 constexpr uint32_t kCodeMask = 0x00FFFFFFu;
 
-// ---- node-set arena ----------------------------------------------------------------
-// One record per DISTINCT node set, as a "mini-tree": the set restricted to the
-// non-leaf nodes of the model tree, closed under ancestors, in DFS pre-order.
+// ---- node-set records, GENERAL mode ("mini-trees") -----------------------------------
+// One record per DISTINCT node set: the set restricted to the non-leaf nodes of the model
+// tree, closed under ancestors, in DFS pre-order.
 //   arena[off]      header  {x: flags (bit0 = set contains tree.root.id), y: n_entries}
 //   arena[off+1+i]  entry i {x: ordinal among the parent's NON-LEAF children | present<<31,
 //                            y: size of this entry's subtree in entries (>= 1)}
@@ -34,7 +35,19 @@ struct SetWord {
 constexpr uint32_t kPresentBit = 0x80000000u;
 constexpr uint32_t kSetHasRoot = 1u;
 
-// ---- flattened tree over non-leaf nodes (dense ids q, root = 0) ------------------
+// ---- node-set records, CLOSED mode ("terminal lists") ---------------------------------
+// Used when every root-containing set of the model is upward closed over the non-leaf tree
+// (always true for models made by the reference's builder: node sets are unions of root->tip
+// paths, build_database/mod.rs:139-168).  Such a set is determined by its TERMINALS - the
+// members none of whose non-leaf children are members - and with non-leaf nodes numbered in
+// DFS pre-order (q ids; subtree(q) = [q, q_end[q])) membership of a node x is
+// "some terminal lies in [x, q_end[x])".
+//   terms[off]          header: n_terminals | (contains root) << 31
+//   terms[off+1 .. +n]  terminal q ids, ascending
+// Sets that do not contain the root carry n = 0: they only count towards |M|.
+constexpr uint32_t kTermHasRoot = 0x80000000u;
+
+// ---- flattened tree over non-leaf nodes (dense ids q in DFS pre-order, root = 0) ------
 struct QNode {
     uint32_t child_first;  // into q_child_list
     uint32_t child_count;  // number of NON-LEAF children (Clade.kind != LEAF)
@@ -60,14 +73,21 @@ static_assert(sizeof(ResultRec) == 32, "result record must be 32 bytes");
 struct DeviceIndex {
     const Slot *table;
     uint64_t bucket_mask;
-    const SetWord *arena;
+    const SetWord *arena;         // general mode
+    const uint32_t *terms;        // closed mode
     const QNode *qnodes;
     const uint32_t *q_child_list;
     const uint64_t *q_node_id;
+    const uint32_t *q_end;        // closed mode: one past the last q of the subtree
+    const uint32_t *q_depth;      // closed mode
+    const uint32_t *q_up;         // closed mode: binary lifting, q_up[j * n_q + q] = 2^j-th ancestor
+    uint32_t n_q;
+    uint32_t n_lift;
     uint32_t k_size;
     uint32_t m_eff;         // min(m, k): number of prefix bases in the bucket code
     uint32_t max_fanout;    // max child_count over qnodes
     uint32_t root_children_none;
+    uint32_t closed;        // 1 = terminal-list records, 0 = mini-tree records
 };
 
 struct PlaceParams {
@@ -79,6 +99,5 @@ struct PlaceParams {
 // 2-bit base code used everywhere: (ascii >> 1) & 3  ->  A=0 C=1 T=2 G=3 (case-insensitive);
 // complement = code ^ 2.
 constexpr uint32_t kAsciiLut = 0x47544341u;    // byte[code] = "ACTG"[code]
-constexpr uint32_t kAsciiRcLut = 0x43414754u;  // byte[code] = complement: "TGAC"[code]
 
 }  // namespace cls

@@ -126,6 +126,22 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
         }
         out.q_node_id.resize(nq);
         for (uint32_t q = 0; q < nq; ++q) out.q_node_id[q] = mv->node_id[q_node[q]];
+        // closed-mode tree arrays: subtree intervals, depths, binary-lifting ancestors
+        out.q_end = q_end;
+        out.q_depth.assign(nq, 0);
+        uint32_t max_depth = 0;
+        for (uint32_t q = 1; q < nq; ++q) {  // pre-order: parents first
+            out.q_depth[q] = out.q_depth[q_parent[q]] + 1;
+            max_depth = std::max(max_depth, out.q_depth[q]);
+        }
+        uint32_t n_lift = 1;
+        while ((1u << n_lift) <= max_depth) ++n_lift;
+        out.n_lift = n_lift;
+        out.q_up.assign((size_t)n_lift * nq, 0);
+        for (uint32_t q = 1; q < nq; ++q) out.q_up[q] = q_parent[q];
+        for (uint32_t j = 1; j < n_lift; ++j)
+            for (uint32_t q = 0; q < nq; ++q)
+                out.q_up[(size_t)j * nq + q] = out.q_up[(size_t)(j - 1) * nq + out.q_up[(size_t)(j - 1) * nq + q]];
     }
     const uint32_t nq = (uint32_t)q_node.size();
 
@@ -151,10 +167,77 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
     // ---- node sets -> de-duplicated mini-tree records ------------------------------------------
     const uint64_t n_sets = mv->n_sets;
     std::vector<uint32_t> set_arena_off(n_sets, kEmpty);
+    if (n_sets && (!mv->set_off || (mv->set_off[n_sets] && !mv->set_node_ids))) {
+        err = "set arrays are NULL"; return CLS_ERR_INVALID_ARGUMENT;
+    }
+    for (uint64_t s = 0; s < n_sets; ++s)
+        if (mv->set_off[s] > mv->set_off[s + 1]) { err = "set_off is not non-decreasing"; return CLS_ERR_INVALID_ARGUMENT; }
+
+    // ---- descent mode: CLOSED iff every root-containing set is upward closed over the non-leaf tree
+    bool closed = (mv->flags & CLS_MODEL_FORCE_GENERAL_SETS) == 0;
     {
-        if (n_sets && (!mv->set_off || (mv->set_off[n_sets] && !mv->set_node_ids))) {
-            err = "set arrays are NULL"; return CLS_ERR_INVALID_ARGUMENT;
+        std::vector<uint64_t> stamp(nq, 0);
+        std::vector<uint32_t> members;
+        for (uint64_t s = 0; s < n_sets && closed; ++s) {
+            const uint64_t tag = s + 1;
+            members.clear();
+            for (uint64_t j = mv->set_off[s]; j < mv->set_off[s + 1]; ++j) {
+                uint32_t q = id_to_q(mv->set_node_ids[j]);
+                if (q == kNoQ || stamp[q] == tag) continue;
+                stamp[q] = tag;
+                members.push_back(q);
+            }
+            if (stamp[0] != tag) continue;  // no root: never consulted by the descent
+            for (uint32_t q : members)
+                if (q != 0 && stamp[q_parent[q]] != tag) { closed = false; break; }
         }
+    }
+    out.closed = closed;
+
+    if (closed) {
+        // terminal-list records (device_types.hpp), de-duplicated by content
+        std::unordered_map<uint64_t, std::vector<uint32_t>> dedup;
+        dedup.reserve(n_sets / 4 + 16);
+        std::vector<uint64_t> stamp(nq, 0), has_child(nq, 0);
+        std::vector<uint32_t> members, rec;
+        for (uint64_t s = 0; s < n_sets; ++s) {
+            const uint64_t tag = s + 1;
+            members.clear();
+            for (uint64_t j = mv->set_off[s]; j < mv->set_off[s + 1]; ++j) {
+                uint32_t q = id_to_q(mv->set_node_ids[j]);
+                if (q == kNoQ || stamp[q] == tag) continue;
+                stamp[q] = tag;
+                members.push_back(q);
+            }
+            rec.clear();
+            if (stamp[0] != tag) {
+                rec.push_back(0u);
+            } else {
+                for (uint32_t q : members) if (q != 0) has_child[q_parent[q]] = tag;
+                rec.push_back(0u);
+                for (uint32_t q : members) if (has_child[q] != tag) rec.push_back(q);
+                std::sort(rec.begin() + 1, rec.end());
+                rec[0] = (uint32_t)(rec.size() - 1) | kTermHasRoot;
+            }
+            uint64_t h = 0x243f6a8885a308d3ULL;
+            for (uint32_t w : rec) h = mix64(h ^ w);
+            auto &cands = dedup[h];
+            uint32_t found = kEmpty;
+            for (uint32_t off : cands) {
+                if ((out.terms[off] & ~kTermHasRoot) + 1 == rec.size() &&
+                    std::memcmp(&out.terms[off], rec.data(), rec.size() * sizeof(uint32_t)) == 0) { found = off; break; }
+            }
+            if (found == kEmpty) {
+                if (out.terms.size() + rec.size() >= 0xFFFFFFF0ull) { err = "node-set arena exceeds 2^32 words"; return CLS_ERR_UNSUPPORTED; }
+                found = (uint32_t)out.terms.size();
+                out.terms.insert(out.terms.end(), rec.begin(), rec.end());
+                cands.push_back(found);
+                out.n_distinct_sets++;
+            }
+            set_arena_off[s] = found;
+        }
+        out.terms.push_back(0u);  // padding: records are read one word past a range end at most
+    } else {
         std::unordered_map<uint64_t, std::vector<uint32_t>> dedup;  // content hash -> arena offsets
         dedup.reserve(n_sets / 4 + 16);
         std::vector<uint32_t> stamp(nq, 0), present(nq, 0);
@@ -162,7 +245,6 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
         std::vector<SetWord> rec;
         std::vector<uint32_t> open;
         for (uint64_t s = 0; s < n_sets; ++s) {
-            if (mv->set_off[s] > mv->set_off[s + 1]) { err = "set_off is not non-decreasing"; return CLS_ERR_INVALID_ARGUMENT; }
             const uint32_t tag = (uint32_t)(s + 1);
             if (tag == 0) { std::fill(stamp.begin(), stamp.end(), 0); std::fill(present.begin(), present.end(), 0); }
             members.clear();
@@ -212,6 +294,7 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
         }
     }
     if (out.arena.empty()) out.arena.push_back(SetWord{0, 0});  // never dereferenced; keeps uploads non-empty
+    if (out.terms.empty()) out.terms.push_back(0u);
 
     // ---- bucket key -> prefix code -------------------------------------------------------------
     std::unordered_map<uint64_t, uint32_t> key_code;

@@ -17,7 +17,11 @@ struct HostIndex {
     std::vector<Slot> table;  // 2 * n_buckets slots
     uint64_t n_buckets = 0;
     uint64_t n_entries_kept = 0;
+    bool closed = false;            // terminal-list records (`terms`) instead of mini-trees (`arena`)
     std::vector<SetWord> arena;
+    std::vector<uint32_t> terms;
+    std::vector<uint32_t> q_end, q_depth, q_up;  // q_up: n_lift x n_q
+    uint32_t n_lift = 0;
     uint64_t n_distinct_sets = 0;
     std::vector<QNode> qnodes;
     std::vector<uint32_t> q_child_list;

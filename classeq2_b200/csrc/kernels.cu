@@ -1,22 +1,29 @@
 // sm_100a kernels of the placement path.  One warp places one query end to end:
 //
-//   decode   2-bit packed bases -> forward + reverse-complement ASCII strings in shared memory
+//   decode   2-bit packed bases -> forward + reverse-complement ASCII strings (and the packed
+//            reverse complement) in shared memory
 //            (reference: kmers_map.rs:375-398 build_kmer_from_string, :431-443 reverse_complement)
 //   hash     murmur3_x64_128(window).0 for every window of both strands, one window per lane
-//            (kmers_map.rs:405-424, :157-159)
+//            (kmers_map.rs:405-424, :157-159).  k = 35: the two per-word pre-mixes of every
+//            8-byte word are computed ONCE per byte offset and shared between the four windows
+//            that use them through a shared-memory ring; the 3-byte tail mix is a 64-entry table.
 //   probe    one 32-byte bucket (a single DRAM sector, one 256-bit load) of the open-addressed
 //            table per window; bucket-key gating by 2-bit prefix code (kmers_map.rs:273-311, :55-70)
 //   dedup    distinct-hash semantics of the reference's HashSets: hits de-duplicated by table
 //            slot in a per-warp shared-memory set, then histogrammed by node-set record
 //   descend  one-vs-rest walk from the root (place_sequence.rs:279-601,
-//            update_introspection_node.rs:13-91) with per-warp shared-memory vote counters:
+//            update_introspection_node.rs:13-91):
 //            cnt(c)  = #hits whose node set contains child c
 //            excl(c) = #hits whose node set contains c and no other non-leaf sibling
 //            U       = #hits whose node set contains any non-leaf child of the current node
 //            default mode: one = cnt(c), rest = U - excl(c); remove_intersection: one = excl(c),
 //            rest = U - cnt(c); a single candidate -> (cnt(c), 0)   (place_sequence.rs:353-418)
+//            CLOSED models (every set upward closed - the builder's invariant): sets are sorted
+//            terminal lists over pre-order ids; all levels between the current node and the LCA of
+//            the live terminals are unanimous (one candidate, rest = 0) and are skipped in one jump.
+//            GENERAL models: sets are mini-trees walked level by level with shared-memory counters.
 //
-// Integer/byte work bound by HBM sector rate and the integer pipes - no tensor cores.
+// Integer/byte work bound by instruction issue (murmur3) and the HBM/L2 sector rate - no tensor cores.
 #include <cuda_runtime.h>
 
 #include <climits>
@@ -31,6 +38,8 @@ namespace cls {
 namespace {
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr uint32_t kUndecided = 0xFFFFFFFFu;
+constexpr uint32_t kRing = 64;  // pre-mix ring entries per warp (two 32-offset chunks)
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
@@ -47,22 +56,37 @@ __device__ __forceinline__ uint32_t revcomp16(uint32_t w) {
     return r ^ 0xAAAAAAAAu;
 }
 
-// Decode one read into two 4-byte aligned ASCII strings (forward, reverse complement).
-__device__ __forceinline__ void decode_read(const uint32_t *__restrict__ packed, uint32_t len,
-                                            uint32_t *str_f, uint32_t *str_r) {
+// Per-warp shared-memory view.
+struct WarpMem {
+    uint32_t *str_f, *str_r;  // ASCII strands, 4-byte aligned, zero padded
+    uint32_t *pk_f, *pk_r;    // 2-bit packed strands (16 bases / word), zero padded
+    uint64_t *ring_a, *ring_b;  // pre-mix ring (k = 35 path)
+};
+
+// Decode one read into the two ASCII strands and the two packed strands.
+__device__ __forceinline__ void decode_read(const uint32_t *__restrict__ packed, uint32_t len, const WarpMem &m,
+                                            uint32_t pk_words) {
     const uint32_t nw = (len + 15u) >> 4;
     const uint32_t pad = nw * 16u - len;  // unused base slots at the top of the last word
-    for (uint32_t t = lane_id(); t < nw; t += 32) {
-        uint32_t f = __ldg(packed + t);
-        // reverse-complement word t = bases [16t, 16t+16) of the reversed string
-        uint32_t a = revcomp16(__ldg(packed + (nw - 1 - t)));
-        uint32_t b = (t + 1 < nw) ? revcomp16(__ldg(packed + (nw - 2 - t))) : 0u;
-        uint32_t r = __funnelshift_r(a, b, 2u * pad);
+    for (uint32_t t = lane_id(); t < pk_words; t += 32) {
+        uint32_t f = 0, r = 0;
+        if (t < nw) {
+            f = __ldg(packed + t);
+            // reverse-complement word t = bases [16t, 16t+16) of the reversed string
+            uint32_t a = revcomp16(__ldg(packed + (nw - 1 - t)));
+            uint32_t b = (t + 1 < nw) ? revcomp16(__ldg(packed + (nw - 2 - t))) : 0u;
+            r = __funnelshift_r(a, b, 2u * pad);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            str_f[4 * t + q] = decode4((f >> (8 * q)) & 0xFFu);
-            str_r[4 * t + q] = decode4((r >> (8 * q)) & 0xFFu);
+            for (int q = 0; q < 4; ++q) {
+                m.str_f[4 * t + q] = decode4((f >> (8 * q)) & 0xFFu);
+                m.str_r[4 * t + q] = decode4((r >> (8 * q)) & 0xFFu);
+            }
+        } else if (t == nw) {  // over-read pad of the strings
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { m.str_f[4 * t + q] = 0; m.str_r[4 * t + q] = 0; }
         }
+        m.pk_f[t] = f;
+        m.pk_r[t] = r;
     }
 }
 
@@ -73,161 +97,298 @@ __device__ __forceinline__ void ld_bucket(const Slot *table, uint64_t bucket, ui
                  : "l"(table + 2 * bucket));
 }
 
-// 2-bit prefix code of the m_eff leading bases of a window (bucket gating).
-__device__ __forceinline__ uint32_t prefix_code(const uint8_t *s, uint32_t pos, uint32_t m_eff) {
-    uint32_t code = 0;
-    for (uint32_t j = 0; j < m_eff; ++j) code |= ((uint32_t)(s[pos + j] >> 1) & 3u) << (2 * j);
-    return code;
+// `nbits` (<= 24) bits of a packed strand starting at base `pos`.
+__device__ __forceinline__ uint32_t packed_bits(const uint32_t *pk, uint32_t pos, uint32_t mask) {
+    const uint32_t j = pos >> 4;
+    return __funnelshift_r(pk[j], pk[j + 1], (2u * pos) & 31u) & mask;
 }
 
-template <int K>
-__device__ __forceinline__ uint64_t hash_window(const uint32_t *s32, uint32_t pos, uint32_t k) {
-    if constexpr (K > 0) {
-        return murmur_window_smem<K>(s32, pos);
-    } else {
-        return murmur_window_generic(reinterpret_cast<const uint8_t *>(s32), pos, k);
+// 64-bit x * 5 + c
+__device__ __forceinline__ uint64_t mul5add(uint64_t x, uint64_t c) { return x * 5ull + c; }
+
+// Pre-mixes of the 8-byte little-endian word at byte offset q of an ASCII strand:
+//   a = rotl(w * c1, 31) * c2   (the k1 lane of a murmur block), b = rotl(w * c2, 33) * c1 (the k2 lane)
+__device__ __forceinline__ void premix_word(const uint32_t *s32, uint32_t q, uint64_t &a, uint64_t &b) {
+    const uint32_t *w = s32 + (q >> 2);
+    const uint32_t sh = (q & 3u) * 8u;
+    const uint32_t r0 = w[0], r1 = w[1], r2 = w[2];
+    const uint64_t x = (uint64_t)__funnelshift_r(r0, r1, sh) | ((uint64_t)__funnelshift_r(r1, r2, sh) << 32);
+    a = rotl64_d(x * kC1, 31) * kC2;
+    b = rotl64_d(x * kC2, 33) * kC1;
+}
+
+// Calls f(rc, pos, hash) for every window of both strands (reference order: forward windows,
+// then reverse-complement windows), one window per lane.  Must be called by all 32 lanes.
+//   K == 35: ring-shared pre-mixes (see the header comment);  K == 0: generic byte-wise hash.
+template <int K, class F>
+__device__ __forceinline__ uint32_t for_each_window(const WarpMem &m, uint32_t len, uint32_t k, const uint64_t *tail_lut,
+                                                F &&f) {
+    const uint32_t lane = lane_id();
+    const uint32_t W = len - k + 1;
+    const uint32_t n_chunks = (W + 31u) >> 5;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (uint32_t strand = 0; strand < 2; ++strand) {
+        const uint32_t *s32 = strand ? m.str_r : m.str_f;
+        if constexpr (K == 35) {
+            const uint32_t *pk = strand ? m.pk_r : m.pk_f;
+            const uint32_t n_off = W + 24u;  // offsets 0 .. W+23 carry a pre-mix some window needs
+            {
+                uint64_t a, b;
+                if (lane < n_off) { premix_word(s32, lane, a, b); m.ring_a[lane] = a; m.ring_b[lane] = b; }
+            }
+#pragma unroll 1
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                const uint32_t q = 32u * (c + 1) + lane;
+                if (q < n_off) {
+                    uint64_t a, b;
+                    premix_word(s32, q, a, b);
+                    m.ring_a[q & (kRing - 1)] = a;
+                    m.ring_b[q & (kRing - 1)] = b;
+                }
+                __syncwarp();
+                const uint32_t p = 32u * c + lane;
+                if (p < W) {
+                    const uint64_t a0 = m.ring_a[p & (kRing - 1)], b1 = m.ring_b[(p + 8) & (kRing - 1)];
+                    const uint64_t a2 = m.ring_a[(p + 16) & (kRing - 1)], b3 = m.ring_b[(p + 24) & (kRing - 1)];
+                    // block 0 (h1 = h2 = 0 on entry), block 1, 3-byte tail, finalisation
+                    uint64_t h1 = mul5add(rotl64_d(a0, 27), 0x52dce729ull);
+                    uint64_t h2 = mul5add(rotl64_d(b1, 31) + h1, 0x38495ab5ull);
+                    h1 = mul5add(rotl64_d(h1 ^ a2, 27) + h2, 0x52dce729ull);
+                    h2 = mul5add(rotl64_d(h2 ^ b3, 31) + h1, 0x38495ab5ull);
+                    h1 ^= tail_lut[packed_bits(pk, p + 32u, 63u)];
+                    acc += f(strand != 0, p, mm_finish(h1, h2, 35ull));
+                }
+                __syncwarp();
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+                const uint32_t p = 32u * c + lane;
+                if (p < W) acc += f(strand != 0, p, murmur_window_generic(reinterpret_cast<const uint8_t *>(s32), p, k));
+            }
+        }
     }
+    return acc;
+}
+
+// tail_lut[c0 | c1 << 2 | c2 << 4] = k1 pre-mix of the 3-byte tail "XYZ" (codes A=0 C=1 T=2 G=3).
+__device__ __forceinline__ void init_tail_lut(uint64_t *tail_lut) {
+    if (threadIdx.x < 64) {
+        const uint32_t i = threadIdx.x;
+        const uint64_t t = (uint64_t)((kAsciiLut >> (8 * (i & 3))) & 0xFF) | ((uint64_t)((kAsciiLut >> (8 * ((i >> 2) & 3))) & 0xFF) << 8) |
+                           ((uint64_t)((kAsciiLut >> (8 * ((i >> 4) & 3))) & 0xFF) << 16);
+        tail_lut[i] = rotl64_d(t * kC1, 31) * kC2;
+    }
+}
+
+// First index in [lo, hi) whose terminal is >= key.
+__device__ __forceinline__ uint32_t lower_bound_terms(const uint32_t *__restrict__ terms, uint32_t lo, uint32_t hi, uint32_t key) {
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(terms + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Lowest common ancestor of pre-order ids u <= v (binary lifting; uniform across the warp).
+__device__ __forceinline__ uint32_t lca(const DeviceIndex &ix, uint32_t u, uint32_t v) {
+    if (v < __ldg(ix.q_end + u)) return u;
+    uint32_t a = u;
+    for (int j = (int)ix.n_lift - 1; j >= 0; --j) {
+        const uint32_t b = __ldg(ix.q_up + (size_t)j * ix.n_q + a);
+        if (__ldg(ix.q_end + b) <= v) a = b;  // b does not contain v yet
+    }
+    return __ldg(ix.q_up + a);  // parent of the highest ancestor that does not contain v
+}
+
+// One-vs-rest decision over `m` children whose vote counters sit in shared memory
+// (place_sequence.rs:353-418 proposals, :436-600 decision).  Uniform results in all lanes.
+struct Decision {
+    uint32_t nprop, n_best, best_ord;
+    int32_t best_one, best_rest;
+};
+__device__ __forceinline__ Decision decide_smem(const uint32_t *cnt, const uint32_t *excl, uint32_t m, uint32_t U, bool ri) {
+    const uint32_t lane = lane_id();
+    uint32_t ncand = 0;
+    for (uint32_t o0 = 0; o0 < m; o0 += 32) {
+        const uint32_t o = o0 + lane;
+        ncand += __popc(__ballot_sync(kFull, o < m && cnt[o] > 0));
+    }
+    Decision d{0, 0, 0, 0, 0};
+    int32_t best_diff = INT_MIN;
+    for (uint32_t o0 = 0; o0 < m; o0 += 32) {
+        const uint32_t o = o0 + lane;
+        const uint32_t c = o < m ? cnt[o] : 0u, x = o < m ? excl[o] : 0u;
+        const int32_t one = (int32_t)((ri && ncand > 1) ? x : c);
+        const int32_t rest = ncand > 1 ? (int32_t)(ri ? U - c : U - x) : 0;
+        const bool prop = c > 0 && one > rest;
+        const uint32_t pm = __ballot_sync(kFull, prop);
+        if (pm) {
+            d.nprop += __popc(pm);
+            const int32_t diff = prop ? one - rest : INT_MIN;
+            const int32_t dmax = __reduce_max_sync(kFull, diff);
+            const uint32_t eq = __ballot_sync(kFull, prop && diff == dmax);
+            if (dmax > best_diff) {
+                const int src = __ffs(eq) - 1;
+                best_diff = dmax; d.n_best = __popc(eq);
+                d.best_ord = __shfl_sync(kFull, o, src);
+                d.best_one = __shfl_sync(kFull, one, src);
+                d.best_rest = __shfl_sync(kFull, rest, src);
+            } else if (dmax == best_diff) {
+                d.n_best += __popc(eq);
+            }
+        }
+    }
+    return d;
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
 // Debug/parity kernel: all window hashes of one read, reference order (forward then revcomp).
+// One warp; runs the very same decode + hashing code as the placement kernel.
 // ------------------------------------------------------------------------------------------
 template <int K>
 __global__ void hash_only_kernel(const uint32_t *__restrict__ packed, uint32_t len, uint32_t k,
-                                 uint64_t *__restrict__ out, uint32_t str_words) {
-    extern __shared__ uint32_t smem[];
-    uint32_t *str_f = smem;
-    uint32_t *str_r = smem + str_words;
-    for (uint32_t i = threadIdx.x; i < 2 * str_words; i += blockDim.x) smem[i] = 0;
+                                 uint64_t *__restrict__ out, uint32_t str_words, uint32_t pk_words) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint64_t tail_lut[64];
+    init_tail_lut(tail_lut);
+    WarpMem m;
+    m.ring_a = reinterpret_cast<uint64_t *>(smem);
+    m.ring_b = m.ring_a + kRing;
+    m.str_f = smem + 4 * kRing;
+    m.str_r = m.str_f + str_words;
+    m.pk_f = m.str_r + str_words;
+    m.pk_r = m.pk_f + pk_words;
     __syncthreads();
-    if (threadIdx.x < 32) decode_read(packed, len, str_f, str_r);
-    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    decode_read(packed, len, m, pk_words);
+    __syncwarp();
     const uint32_t W = len - k + 1;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * W; idx += gridDim.x * blockDim.x) {
-        const bool rc = idx >= W;
-        out[idx] = hash_window<K>(rc ? str_r : str_f, rc ? idx - W : idx, k);
-    }
+    for_each_window<K>(m, len, k, tail_lut, [=](bool rc, uint32_t pos, uint64_t h) -> uint32_t { out[(rc ? W : 0u) + pos] = h; return 0u; });
 }
 
 // ------------------------------------------------------------------------------------------
 // The placement kernel: one warp per query, persistent CTAs striding over the query range.
 // ------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(256) place_kernel(DeviceIndex ix, PlaceParams pp,
+template <int K, bool CLOSED>
+__global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlaceParams pp,
                                                     const uint32_t *__restrict__ packed,
                                                     const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                     uint32_t n_reads, ResultRec *__restrict__ results,
                                                     PlaceGeom g) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint64_t tail_lut[64];
+    init_tail_lut(tail_lut);
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t warps_per_cta = blockDim.x >> 5;
     uint32_t *wbase = smem + (size_t)warp * g.words_per_warp;
-    uint32_t *str_f = wbase;
-    uint32_t *str_r = str_f + g.str_words;
-    uint32_t *t1 = str_r + g.str_words;  // dedup set keyed by table slot; later the (entry, weight) list
+    WarpMem wm;
+    wm.ring_a = reinterpret_cast<uint64_t *>(wbase);
+    wm.ring_b = wm.ring_a + kRing;
+    uint32_t *t1 = wbase + 4 * kRing;    // dedup set keyed by table slot; later the live-set list
     uint32_t *t2k = t1 + g.t1_size;      // histogram keys: node-set record offsets
     uint32_t *t2c = t2k + g.t2_size;     // histogram counts
-    uint32_t *cnt = t2c + g.t2_size;     // vote counters, one per non-leaf child ordinal
+    uint32_t *lst = t2c + g.t2_size;     // histogram positions of the distinct sets, in arrival order
+    wm.str_f = lst + g.t2_size;
+    wm.str_r = wm.str_f + g.str_words;
+    wm.pk_f = wm.str_r + g.str_words;
+    wm.pk_r = wm.pk_f + g.pk_words;
+    uint32_t *cnt = wm.pk_r + g.pk_words;  // vote counters, one per non-leaf child ordinal
     uint32_t *excl = cnt + g.fan_cap;
-    const uint32_t t1_shift = 32u - g.t1_log2, t2_shift = 32u - g.t2_log2;
+    uint32_t *n_sets_smem = excl + g.fan_cap;
     const uint32_t t1_mask = g.t1_size - 1u, t2_mask = g.t2_size - 1u;
+    const uint32_t t2_shift = 32u - g.t2_log2;
     const uint32_t k = ix.k_size;
+    const uint32_t code_mask = ix.m_eff >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ix.m_eff)) - 1u);
     const bool ri = pp.remove_intersection != 0;
 
     for (uint32_t o = lane; o < g.fan_cap; o += 32) { cnt[o] = 0; excl[o] = 0; }
+    __syncthreads();
 
     const uint32_t gwarp = blockIdx.x * warps_per_cta + warp;
     const uint32_t gstride = gridDim.x * warps_per_cta;
+#pragma unroll 1
     for (uint32_t r = gwarp; r < n_reads; r += gstride) {
         const ReadDesc rd = reads[first_read + r];
         const uint32_t L = rd.len;
         const uint32_t W = L - k + 1;  // host guarantees L >= k
-        const uint32_t nwin = 2 * W;
 
         // ---- reset per-read tables, decode ------------------------------------------------
-        for (uint32_t i = lane; i < g.t1_size; i += 32) t1[i] = kEmpty;
-        for (uint32_t i = lane; i < g.t2_size; i += 32) { t2k[i] = kEmpty; t2c[i] = 0; }
-        decode_read(packed + rd.word_off, L, str_f, str_r);
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(t1);
+            const uint32_t n4 = (g.t1_size + g.t2_size) >> 2;  // t1 and t2k are contiguous: all kEmpty
+            for (uint32_t i = lane; i < n4; i += 32) z[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            uint4 *zc = reinterpret_cast<uint4 *>(t2c);
+            for (uint32_t i = lane; i < (g.t2_size >> 2); i += 32) zc[i] = make_uint4(0, 0, 0, 0);
+            if (lane == 0) *n_sets_smem = 0;
+        }
+        decode_read(packed + rd.word_off, L, wm, g.pk_words);
         __syncwarp();
 
         // ---- hash + probe + dedup + histogram -------------------------------------------
-        uint32_t n_matched = 0;
-        for (uint32_t base = 0; base < nwin; base += 32) {
-            const uint32_t idx = base + lane;
-            bool fresh = false;
-            if (idx < nwin) {
-                const bool rc = idx >= W;
-                const uint32_t pos = rc ? idx - W : idx;
-                const uint32_t *s32 = rc ? str_r : str_f;
-                const uint64_t h = hash_window<K>(s32, pos, k);
-                uint64_t b = h & ix.bucket_mask;
-                uint32_t slot_id = kEmpty, set_off = 0, code = 0;
-                for (;;) {
-                    uint64_t h0, m0, h1, m1;
-                    ld_bucket(ix.table, b, h0, m0, h1, m1);
-                    if (h0 == h && (uint32_t)m0 != kEmpty) { slot_id = (uint32_t)(2 * b); set_off = (uint32_t)m0; code = (uint32_t)(m0 >> 32); break; }
-                    if (h1 == h && (uint32_t)m1 != kEmpty) { slot_id = (uint32_t)(2 * b + 1); set_off = (uint32_t)m1; code = (uint32_t)(m1 >> 32); break; }
-                    if (!((uint32_t)(m0 >> 32) & kOverflowBit)) break;
-                    b = (b + 1) & ix.bucket_mask;
-                }
-                if (slot_id != kEmpty) {
-                    // bucket gating: the entry's bucket key must be among the query's prefix keys
-                    const uint8_t *s8 = reinterpret_cast<const uint8_t *>(s32);
-                    const uint32_t want = code & kCodeMask;
-                    bool pass = prefix_code(s8, pos, ix.m_eff) == want;
-                    if (!pass) {  // only possible for models whose bucket keys disagree with their k-mers
-                        const uint8_t *f8 = reinterpret_cast<const uint8_t *>(str_f);
-                        const uint8_t *r8 = reinterpret_cast<const uint8_t *>(str_r);
-                        for (uint32_t p = 0; p < W && !pass; ++p)
-                            pass = prefix_code(f8, p, ix.m_eff) == want || prefix_code(r8, p, ix.m_eff) == want;
-                    }
-                    if (pass) {
-                        uint32_t p1 = (slot_id * 0x9E3779B1u) >> t1_shift;
-                        for (;;) {
-                            uint32_t old = atomicCAS(&t1[p1], kEmpty, slot_id);
-                            if (old == kEmpty) { fresh = true; break; }
-                            if (old == slot_id) break;
-                            p1 = (p1 + 1) & t1_mask;
-                        }
-                        if (fresh) {
-                            uint32_t p2 = (set_off * 0x9E3779B1u) >> t2_shift;
-                            for (;;) {
-                                uint32_t old = atomicCAS(&t2k[p2], kEmpty, set_off);
-                                if (old == kEmpty || old == set_off) { atomicAdd(&t2c[p2], 1u); break; }
-                                p2 = (p2 + 1) & t2_mask;
-                            }
-                        }
-                    }
-                }
+        const uint32_t n_fresh = for_each_window<K>(wm, L, k, tail_lut, [=](bool rc, uint32_t pos, uint64_t h) -> uint32_t {
+            uint64_t b = h & ix.bucket_mask;
+            uint32_t slot_id = kEmpty, set_off = 0, code = 0;
+            for (;;) {
+                uint64_t h0, m0, h1, m1;
+                ld_bucket(ix.table, b, h0, m0, h1, m1);
+                if (h0 == h && (uint32_t)m0 != kEmpty) { slot_id = (uint32_t)(2 * b); set_off = (uint32_t)m0; code = (uint32_t)(m0 >> 32); break; }
+                if (h1 == h && (uint32_t)m1 != kEmpty) { slot_id = (uint32_t)(2 * b + 1); set_off = (uint32_t)m1; code = (uint32_t)(m1 >> 32); break; }
+                if (!((uint32_t)(m0 >> 32) & kOverflowBit)) break;
+                b = (b + 1) & ix.bucket_mask;
             }
-            n_matched += __popc(__ballot_sync(kFull, fresh));
-        }
+            if (slot_id == kEmpty) return 0u;
+            // bucket gating: the entry's bucket key must be among the query's prefix keys
+            const uint32_t want = code & kCodeMask;
+            bool pass = packed_bits(rc ? wm.pk_r : wm.pk_f, pos, code_mask) == want;
+            if (!pass) {  // only possible for models whose bucket keys disagree with their k-mers
+                for (uint32_t p = 0; p < W && !pass; ++p)
+                    pass = packed_bits(wm.pk_f, p, code_mask) == want || packed_bits(wm.pk_r, p, code_mask) == want;
+                if (!pass) return 0u;
+            }
+            uint32_t p1 = slot_id & t1_mask;
+            for (;;) {
+                const uint32_t old = atomicCAS(&t1[p1], kEmpty, slot_id);
+                if (old == slot_id) return 0u;  // the same k-mer hash was already counted
+                if (old == kEmpty) break;
+                p1 = (p1 + 1) & t1_mask;
+            }
+            uint32_t p2 = (set_off * 0x9E3779B1u) >> t2_shift;
+            for (;;) {
+                const uint32_t old = atomicCAS(&t2k[p2], kEmpty, set_off);
+                if (old == kEmpty) { lst[atomicAdd(n_sets_smem, 1u)] = p2; }
+                if (old == kEmpty || old == set_off) { atomicAdd(&t2c[p2], 1u); break; }
+                p2 = (p2 + 1) & t2_mask;
+            }
+            return 1u;
+        });
+        const uint32_t n_matched = __reduce_add_sync(kFull, n_fresh);
         __syncwarp();
+        const uint32_t D = *n_sets_smem;
 
-        // ---- compact the histogram into a list of (current entry, weight) in t1 ---------
-        uint32_t D = 0;
-        for (uint32_t base = 0; base < g.t2_size; base += 32) {
-            const uint32_t key = t2k[base + lane], c = t2c[base + lane];
-            const bool occ = key != kEmpty;
-            const uint32_t m = __ballot_sync(kFull, occ);
-            if (occ) {
-                const uint32_t j = D + __popc(m & ((1u << lane) - 1u));
-                t1[2 * j] = key;
-                t1[2 * j + 1] = c;
-            }
-            D += __popc(m);
-        }
-        __syncwarp();
-        // restrict to sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
+        // ---- live-set list: restrict to sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
+        //      CLOSED : t1[2j] = lo, t1[2j+1] = weight, lst[j] = hi   (terminal range [lo, hi))
+        //      GENERAL: t1[2j] = current mini-tree entry, t1[2j+1] = weight
         uint32_t n_root = 0;
         for (uint32_t j = lane; j < D; j += 32) {
-            const uint32_t off = t1[2 * j];
-            const SetWord hdr = ix.arena[off];
-            if (hdr.x & kSetHasRoot) { n_root += t1[2 * j + 1]; t1[2 * j] = off + 1; }
-            else t1[2 * j + 1] = 0;
+            const uint32_t p2 = lst[j];
+            const uint32_t off = t2k[p2];
+            uint32_t w = t2c[p2];
+            if constexpr (CLOSED) {
+                const uint32_t hdr = __ldg(ix.terms + off);
+                if (hdr & kTermHasRoot) n_root += w; else w = 0;
+                t1[2 * j] = off + 1;
+                lst[j] = off + 1 + (hdr & ~kTermHasRoot);
+            } else {
+                const SetWord hdr = ix.arena[off];
+                if (hdr.x & kSetHasRoot) n_root += w; else w = 0;
+                t1[2 * j] = off + 1;
+            }
+            t1[2 * j + 1] = w;
         }
         n_root = __reduce_add_sync(kFull, n_root);
         __syncwarp();
@@ -236,110 +397,203 @@ __global__ void __launch_bounds__(256) place_kernel(DeviceIndex ix, PlaceParams 
         ResultRec res;
         res.node_id = 0; res.one = 0; res.rest = 0;
         res.n_matched = n_matched; res.n_root_matched = n_root; res.iterations = 0;
-        res.status = 0xFFFFFFFFu;
+        res.status = kUndecided;
         if (n_matched == 0) res.status = CLS_DEV_UNCL_NO_MATCH;
         else if (n_root == 0) res.status = CLS_DEV_UNCL_NO_ROOT;
         else if (ix.root_children_none) res.status = CLS_DEV_ERR_ROOT_NO_CHILDREN;
         else {
-            const double expected = round((double)n_matched * pp.min_match_coverage);
+            // f64::round (half away from zero) of a non-negative product, without a libdevice call
+            const double x = (double)n_matched * pp.min_match_coverage;
+            double expected = floor(x);
+            if (x - expected >= 0.5) expected += 1.0;
             if ((double)n_root < expected) res.status = CLS_DEV_UNCL_COVERAGE;
         }
 
         // ---- descent ---------------------------------------------------------------------------
         uint32_t p = 0;  // current parent (dense non-leaf id), root = 0
-        uint32_t iteration = 0;
-        while (res.status == 0xFFFFFFFFu) {
-            iteration++;
-            res.iterations = iteration;
-            if ((int64_t)iteration > (int64_t)pp.max_iterations) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
-            const QNode qn = ix.qnodes[p];
-            const uint32_t m = qn.child_count;
-
-            // votes
-            uint32_t u_local = 0;
-            for (uint32_t j = lane; j < D; j += 32) {
-                const uint32_t w = t1[2 * j + 1];
-                if (w == 0) continue;
-                const uint32_t cur = t1[2 * j];
-                const uint32_t end = cur + ix.arena[cur].y;
-                uint32_t npres = 0, last = 0;
-                for (uint32_t c = cur + 1; c < end;) {
-                    const SetWord e = ix.arena[c];
-                    if (e.x & kPresentBit) { last = e.x & ~kPresentBit; atomicAdd(&cnt[last], w); npres++; }
-                    c += e.y;
+        int64_t iteration = 0;
+        const int64_t max_iter = pp.max_iterations;
+        if constexpr (CLOSED) {
+            while (res.status == kUndecided) {
+                // pooled extremes of the live terminals -> every level down to their LCA is unanimous
+                uint32_t umin = 0xFFFFFFFFu, vmax = 0, wl = 0;
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const uint32_t w = t1[2 * j + 1];
+                    if (w == 0) continue;
+                    umin = min(umin, __ldg(ix.terms + t1[2 * j]));
+                    vmax = max(vmax, __ldg(ix.terms + lst[j] - 1));
+                    wl += w;
                 }
-                if (npres) u_local += w;
-                if (npres == 1) atomicAdd(&excl[last], w);
-            }
-            const uint32_t U = __reduce_add_sync(kFull, u_local);
-            __syncwarp();
-
-            // one-vs-rest test over the candidates (children with a non-empty K(c))
-            uint32_t ncand = 0;
-            for (uint32_t o0 = 0; o0 < m; o0 += 32) {
-                const uint32_t o = o0 + lane;
-                ncand += __popc(__ballot_sync(kFull, o < m && cnt[o] > 0));
-            }
-            uint32_t nprop = 0, n_best = 0, best_ord = 0;
-            int32_t best_diff = INT_MIN, best_one = 0, best_rest = 0;
-            for (uint32_t o0 = 0; o0 < m; o0 += 32) {
-                const uint32_t o = o0 + lane;
-                const uint32_t c = o < m ? cnt[o] : 0u, x = o < m ? excl[o] : 0u;
-                const int32_t one = (int32_t)((ri && ncand > 1) ? x : c);
-                const int32_t rest = ncand > 1 ? (int32_t)(ri ? U - c : U - x) : 0;
-                const bool prop = c > 0 && one > rest;
-                const uint32_t pm = __ballot_sync(kFull, prop);
-                if (pm) {
-                    nprop += __popc(pm);
-                    const int32_t diff = prop ? one - rest : INT_MIN;
-                    const int32_t dmax = __reduce_max_sync(kFull, diff);
-                    const uint32_t eq = __ballot_sync(kFull, prop && diff == dmax);
-                    if (dmax > best_diff) {
-                        const int src = __ffs(eq) - 1;
-                        best_diff = dmax; n_best = __popc(eq);
-                        best_ord = __shfl_sync(kFull, o, src);
-                        best_one = __shfl_sync(kFull, one, src);
-                        best_rest = __shfl_sync(kFull, rest, src);
-                    } else if (dmax == best_diff) {
-                        n_best += __popc(eq);
+                umin = __reduce_min_sync(kFull, umin);
+                vmax = __reduce_max_sync(kFull, vmax);
+                const uint32_t Wlive = __reduce_add_sync(kFull, wl);
+                const uint32_t A = lca(ix, umin, vmax);
+                const uint32_t d = __ldg(ix.q_depth + A) - __ldg(ix.q_depth + p);
+                if (d > 0) {
+                    if (iteration + (int64_t)d > max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+                    iteration += d;
+                    if (ix.qnodes[A].child_count == 0) {  // update_introspection_node.rs:32-87
+                        res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[A];
+                        res.one = (int32_t)Wlive; res.rest = 0;
+                        break;
                     }
+                    p = A;
                 }
-            }
-            __syncwarp();
-            for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
-            __syncwarp();
-
-            if (nprop == 0) {
-                if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
-                else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
-                break;
-            }
-            if (n_best != 1) {  // several proposals tie on (one - rest): provably unreachable
-                res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p];
-                break;
-            }
-            const uint32_t cq = ix.q_child_list[qn.child_first + best_ord];
-            if (ix.qnodes[cq].child_count == 0) {  // update_introspection_node.rs:32-87
-                res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[cq];
-                res.one = best_one; res.rest = best_rest;
-                break;
-            }
-            p = cq;
-            // every live set follows the winner (or drops out)
-            for (uint32_t j = lane; j < D; j += 32) {
-                if (t1[2 * j + 1] == 0) continue;
-                const uint32_t cur = t1[2 * j];
-                const uint32_t end = cur + ix.arena[cur].y;
-                uint32_t next = 0;
-                for (uint32_t c = cur + 1; c < end;) {
-                    const SetWord e = ix.arena[c];
-                    if ((e.x & ~kPresentBit) == best_ord) { next = c; break; }
-                    c += e.y;
+                // ---- evaluate the children of p -------------------------------------------------
+                iteration++;
+                if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+                const uint32_t m = ix.qnodes[p].child_count;
+                const uint32_t p_end = __ldg(ix.q_end + p);
+                uint32_t win_q = 0, win_end = 0, nprop = 0, n_best = 0;
+                int32_t win_one = 0, win_rest = 0;
+                if (m <= 2) {
+                    // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
+                    const uint32_t bnd = m ? __ldg(ix.q_end + p + 1) : p_end;
+                    uint32_t c1 = 0, c2 = 0, both = 0;
+                    for (uint32_t j = lane; j < D; j += 32) {
+                        const uint32_t w = t1[2 * j + 1];
+                        if (w == 0) continue;
+                        uint32_t lo = t1[2 * j];
+                        const uint32_t hi = lst[j];
+                        uint32_t first = __ldg(ix.terms + lo);
+                        if (first == p) { ++lo; first = lo < hi ? __ldg(ix.terms + lo) : 0u; }
+                        if (lo < hi) {
+                            const bool in1 = first < bnd, in2 = __ldg(ix.terms + hi - 1) >= bnd;
+                            c1 += in1 ? w : 0u; c2 += in2 ? w : 0u; both += (in1 && in2) ? w : 0u;
+                        }
+                    }
+                    c1 = __reduce_add_sync(kFull, c1);
+                    c2 = __reduce_add_sync(kFull, c2);
+                    both = __reduce_add_sync(kFull, both);
+                    const uint32_t U = c1 + c2 - both, x1 = c1 - both, x2 = c2 - both;
+                    const uint32_t ncand = (c1 > 0) + (c2 > 0);
+                    const int32_t one1 = (int32_t)((ri && ncand > 1) ? x1 : c1), rest1 = ncand > 1 ? (int32_t)(ri ? U - c1 : U - x1) : 0;
+                    const int32_t one2 = (int32_t)((ri && ncand > 1) ? x2 : c2), rest2 = ncand > 1 ? (int32_t)(ri ? U - c2 : U - x2) : 0;
+                    const bool pr1 = c1 > 0 && one1 > rest1, pr2 = c2 > 0 && one2 > rest2;
+                    nprop = (uint32_t)pr1 + (uint32_t)pr2;
+                    bool pick2 = pr2 && !pr1;
+                    n_best = nprop ? 1u : 0u;
+                    if (pr1 && pr2) {  // provably unreachable; kept for fidelity (:519-599)
+                        const int32_t d1 = one1 - rest1, d2 = one2 - rest2;
+                        if (d1 == d2) n_best = 2; else pick2 = d2 > d1;
+                    }
+                    if (pick2) { win_q = bnd; win_end = p_end; win_one = one2; win_rest = rest2; }
+                    else { win_q = p + 1; win_end = bnd; win_one = one1; win_rest = rest1; }
+                } else {
+                    // general fan-out: per-set merge walk of the terminal range against the child
+                    // intervals, votes in shared-memory counters
+                    uint32_t u_local = 0;
+                    for (uint32_t j = lane; j < D; j += 32) {
+                        const uint32_t w = t1[2 * j + 1];
+                        if (w == 0) continue;
+                        uint32_t pos = t1[2 * j];
+                        const uint32_t hi = lst[j];
+                        if (__ldg(ix.terms + pos) == p) ++pos;
+                        uint32_t npres = 0, last = 0, ord = 0, cend = __ldg(ix.q_end + p + 1);
+                        while (pos < hi) {
+                            const uint32_t t = __ldg(ix.terms + pos);
+                            while (t >= cend) { cend = __ldg(ix.q_end + cend); ++ord; }
+                            atomicAdd(&cnt[ord], w); ++npres; last = ord;
+                            ++pos;
+                            if (pos < hi && __ldg(ix.terms + pos) < cend) pos = lower_bound_terms(ix.terms, pos, hi, cend);
+                        }
+                        if (npres) u_local += w;
+                        if (npres == 1) atomicAdd(&excl[last], w);
+                    }
+                    const uint32_t U = __reduce_add_sync(kFull, u_local);
+                    __syncwarp();
+                    const Decision dc = decide_smem(cnt, excl, m, U, ri);
+                    __syncwarp();
+                    for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
+                    __syncwarp();
+                    nprop = dc.nprop; n_best = dc.n_best; win_one = dc.best_one; win_rest = dc.best_rest;
+                    win_q = p + 1;
+                    for (uint32_t o = 0; o < dc.best_ord; ++o) win_q = __ldg(ix.q_end + win_q);
+                    win_end = __ldg(ix.q_end + win_q);
                 }
-                if (next) t1[2 * j] = next; else t1[2 * j + 1] = 0;
+                if (nprop == 0) {
+                    if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
+                    else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
+                    break;
+                }
+                if (n_best != 1) { res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p]; break; }
+                if (ix.qnodes[win_q].child_count == 0) {  // update_introspection_node.rs:32-87
+                    res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[win_q];
+                    res.one = win_one; res.rest = win_rest;
+                    break;
+                }
+                p = win_q;
+                // every live set keeps its terminals inside the winner's interval (or drops out)
+                for (uint32_t j = lane; j < D; j += 32) {
+                    if (t1[2 * j + 1] == 0) continue;
+                    uint32_t lo = t1[2 * j], hi = lst[j];
+                    if (__ldg(ix.terms + lo) < win_q) lo = lower_bound_terms(ix.terms, lo + 1, hi, win_q);
+                    if (lo < hi && __ldg(ix.terms + hi - 1) >= win_end) hi = lower_bound_terms(ix.terms, lo, hi - 1, win_end);
+                    if (lo < hi) { t1[2 * j] = lo; lst[j] = hi; } else t1[2 * j + 1] = 0;
+                }
+                __syncwarp();
             }
-            __syncwarp();
+        } else {
+            while (res.status == kUndecided) {
+                iteration++;
+                if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+                const QNode qn = ix.qnodes[p];
+                const uint32_t m = qn.child_count;
+                // votes
+                uint32_t u_local = 0;
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const uint32_t w = t1[2 * j + 1];
+                    if (w == 0) continue;
+                    const uint32_t cur = t1[2 * j];
+                    const uint32_t end = cur + ix.arena[cur].y;
+                    uint32_t npres = 0, last = 0;
+                    for (uint32_t c = cur + 1; c < end;) {
+                        const SetWord e = ix.arena[c];
+                        if (e.x & kPresentBit) { last = e.x & ~kPresentBit; atomicAdd(&cnt[last], w); npres++; }
+                        c += e.y;
+                    }
+                    if (npres) u_local += w;
+                    if (npres == 1) atomicAdd(&excl[last], w);
+                }
+                const uint32_t U = __reduce_add_sync(kFull, u_local);
+                __syncwarp();
+                const Decision dc = decide_smem(cnt, excl, m, U, ri);
+                __syncwarp();
+                for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
+                __syncwarp();
+                if (dc.nprop == 0) {
+                    if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
+                    else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
+                    break;
+                }
+                if (dc.n_best != 1) {  // several proposals tie on (one - rest): provably unreachable
+                    res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p];
+                    break;
+                }
+                const uint32_t cq = ix.q_child_list[qn.child_first + dc.best_ord];
+                if (ix.qnodes[cq].child_count == 0) {  // update_introspection_node.rs:32-87
+                    res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[cq];
+                    res.one = dc.best_one; res.rest = dc.best_rest;
+                    break;
+                }
+                p = cq;
+                // every live set follows the winner (or drops out)
+                for (uint32_t j = lane; j < D; j += 32) {
+                    if (t1[2 * j + 1] == 0) continue;
+                    const uint32_t cur = t1[2 * j];
+                    const uint32_t end = cur + ix.arena[cur].y;
+                    uint32_t next = 0;
+                    for (uint32_t c = cur + 1; c < end;) {
+                        const SetWord e = ix.arena[c];
+                        if ((e.x & ~kPresentBit) == dc.best_ord) { next = c; break; }
+                        c += e.y;
+                    }
+                    if (next) t1[2 * j] = next; else t1[2 * j + 1] = 0;
+                }
+                __syncwarp();
+            }
         }
+        res.iterations = (uint32_t)iteration;
         if (lane == 0) results[first_read + r] = res;
         __syncwarp();
     }
@@ -358,59 +612,65 @@ PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout) {
     PlaceGeom g{};
     const uint32_t H = max_len >= k ? 2 * (max_len - k + 1) : 2;
     g.str_words = ((max_len + 15u) / 16u) * 4u + 4u;  // decoded in 16-base groups, + over-read pad
+    g.pk_words = (((max_len + 15u) / 16u) + 4u + 3u) & ~3u;
     g.t1_log2 = ceil_log2(H * 2 < 64 ? 64 : H * 2);
     g.t2_log2 = ceil_log2(H + 1 < 32 ? 32 : H + 1);
     g.t1_size = 1u << g.t1_log2;
     g.t2_size = 1u << g.t2_log2;
     g.fan_cap = max_fanout < 1 ? 1 : max_fanout;
-    g.words_per_warp = 2 * g.str_words + g.t1_size + 2 * g.t2_size + 2 * g.fan_cap;
+    g.words_per_warp = 4 * kRing + g.t1_size + 3 * g.t2_size + 2 * g.str_words + 2 * g.pk_words + 2 * g.fan_cap + 1;
     g.words_per_warp = (g.words_per_warp + 3u) & ~3u;
     return g;
 }
 
-template <int K>
+template <int K, bool CLOSED>
 static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                                   const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
                                   ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream) {
     const size_t per_warp = (size_t)g.words_per_warp * 4;
     int warps = 8;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-    if (per_warp * warps > 227 * 1024) return cudaErrorInvalidConfiguration;
+    if (per_warp * warps > 226 * 1024) return cudaErrorInvalidConfiguration;
     const size_t smem = per_warp * warps;
-    cudaError_t e = cudaFuncSetAttribute(place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(place_kernel<K, CLOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, place_kernel<K>, warps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, place_kernel<K, CLOSED>, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid == 0) return cudaSuccess;
-    place_kernel<K><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g);
+    place_kernel<K, CLOSED><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g);
     return cudaGetLastError();
 }
 
 cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                          const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
                          const PlaceGeom &g, int sm_count, cudaStream_t stream) {
-    if (ix.k_size == 35) return launch_place_t<35>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
-    return launch_place_t<0>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+    if (ix.k_size == 35) {
+        return ix.closed ? launch_place_t<35, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
+                         : launch_place_t<35, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+    }
+    return ix.closed ? launch_place_t<0, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
+                     : launch_place_t<0, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
 }
 
 cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, uint64_t *out, cudaStream_t stream) {
     const uint32_t str_words = ((len + 15u) / 16u) * 4u + 4u + (k + 3) / 4;
-    const size_t smem = (size_t)2 * str_words * 4;
+    const uint32_t pk_words = (((len + 15u) / 16u) + 4u + 3u) & ~3u;
+    const size_t smem = (size_t)(4 * kRing + 2 * str_words + 2 * pk_words) * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e;
     if (k == 35) {
         e = cudaFuncSetAttribute(hash_only_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hash_only_kernel<35><<<1, 256, smem, stream>>>(packed, len, k, out, str_words);
+        hash_only_kernel<35><<<1, 64, smem, stream>>>(packed, len, k, out, str_words, pk_words);
     } else {
         e = cudaFuncSetAttribute(hash_only_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hash_only_kernel<0><<<1, 256, smem, stream>>>(packed, len, k, out, str_words);
+        hash_only_kernel<0><<<1, 64, smem, stream>>>(packed, len, k, out, str_words, pk_words);
     }
     return cudaGetLastError();
 }

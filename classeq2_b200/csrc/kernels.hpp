@@ -24,6 +24,7 @@ constexpr uint32_t CLS_DEV_ERR_ROOT_NO_CHILDREN = CLS_STATUS_ERR_ROOT_NO_CHILDRE
 // groups reads into length classes so that short reads do not pay for long ones).
 struct PlaceGeom {
     uint32_t str_words;       // 32-bit words per decoded strand string
+    uint32_t pk_words;        // 32-bit words per 2-bit packed strand (zero padded)
     uint32_t t1_size, t1_log2;  // hit de-duplication set (u32 slots), power of two >= 2 * max hits
     uint32_t t2_size, t2_log2;  // node-set histogram (keys + counts), power of two > max hits
     uint32_t fan_cap;         // vote counters per warp (max non-leaf fan-out of the tree)

@@ -137,7 +137,7 @@ class FlatModel:
 
     def __init__(self, k_size: int, m_size: int, node_id, node_kind, child_off, child_idx,
                  entry_bucket=None, entry_hash=None, entry_set=None, set_off=None, set_node_ids=None,
-                 root_children_none: bool = False, keepalive=None):
+                 root_children_none: bool = False, keepalive=None, force_general_sets: bool = False):
         u64 = lambda a: np.ascontiguousarray(a if a is not None else [], dtype=np.uint64)  # noqa: E731
         self.k_size, self.m_size = int(k_size), int(m_size)
         self.node_id = u64(node_id)
@@ -148,13 +148,15 @@ class FlatModel:
         self.set_off = u64(set_off if set_off is not None else [0])
         self.set_node_ids = u64(set_node_ids)
         self.root_children_none = bool(root_children_none)
+        self.force_general_sets = bool(force_general_sets)
         self._keepalive = keepalive
         self.view = self._make_view()
 
     def _make_view(self) -> _lib.ModelView:
         v = _lib.ModelView()
         v.k_size, v.m_size = self.k_size, self.m_size
-        v.flags = _lib.MODEL_ROOT_CHILDREN_NONE if self.root_children_none else 0
+        v.flags = ((_lib.MODEL_ROOT_CHILDREN_NONE if self.root_children_none else 0)
+                   | (_lib.MODEL_FORCE_GENERAL_SETS if self.force_general_sets else 0))
         v.n_nodes = len(self.node_id)
         v.node_id = _ptr(self.node_id, _lib.u64p)
         v.node_kind = _ptr(self.node_kind, _lib.u8p)
@@ -172,6 +174,12 @@ class FlatModel:
     @property
     def n_entries(self) -> int:
         return len(self.entry_hash)
+
+    def with_general_sets(self) -> "FlatModel":
+        """The same model, forced onto the general mini-tree node-set records (testing knob)."""
+        return FlatModel(self.k_size, self.m_size, self.node_id, self.node_kind, self.child_off, self.child_idx,
+                         self.entry_bucket, self.entry_hash, self.entry_set, self.set_off, self.set_node_ids,
+                         self.root_children_none, self._keepalive, force_general_sets=True)
 
     # ---- constructors -------------------------------------------------------------------------
     @staticmethod

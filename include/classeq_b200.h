@@ -50,7 +50,11 @@ enum {
     /* tree.root.children is `None` (place_sequence.rs:199-206 -> Err for every query
      * that survives the coverage gate).  `Some(vec![])` is expressed by an empty
      * child range instead. */
-    CLS_MODEL_ROOT_CHILDREN_NONE = 1u
+    CLS_MODEL_ROOT_CHILDREN_NONE = 1u,
+    /* Testing knob: serialise node sets as general "mini-tree" records even when every set is
+     * upward closed (the library picks the faster terminal-list records for such models; both
+     * give identical results - see DESIGN.md "node-set records"). */
+    CLS_MODEL_FORCE_GENERAL_SETS = 2u
 };
 
 /*
@@ -189,6 +193,8 @@ typedef struct cls_index_info {
     uint64_t n_nonleaf_nodes;
     uint32_t max_nonleaf_fanout;
     int32_t device;
+    uint32_t closed_sets;      /* 1: terminal-list records + LCA jumps; 0: general mini-tree records */
+    uint32_t reserved;
 } cls_index_info;
 int cls_index_get_info(const cls_index *index, cls_index_info *info);
 

@@ -17,9 +17,13 @@ def cq():
     return classeq2_b200
 
 
-@pytest.fixture(scope="module")
-def col_index(cq, col_flat):
-    ix = cq.Index(col_flat, device=0)
+@pytest.fixture(scope="module", params=["closed", "general"])
+def col_index(request, cq, col_flat):
+    """The Colletotrichum model on the GPU in both node-set record formats: terminal lists + LCA
+    jumps (picked automatically: the builder's sets are upward closed) and general mini-trees."""
+    flat = col_flat if request.param == "closed" else col_flat.with_general_sets()
+    ix = cq.Index(flat, device=0)
+    assert ix.info()["closed_sets"] == (1 if request.param == "closed" else 0)
     yield ix
     ix.close()
 
@@ -196,14 +200,17 @@ def test_random_models(cq, oracle, seed):
     tree, queries = _random_tree_model(oracle, rng, k, m)
     if rng.random() < 0.1:
         tree.root.children = None
-    ix = cq.Index(tree_to_product(cq, tree), device=0)
-    for kn in [dict(), dict(remove_intersection=True), dict(min_match_coverage=1.0),
-               dict(max_iterations=int(rng.integers(0, 3)), min_match_coverage=0.0)]:
-        res = ix.place_batch([s for _, s in queries], cq.PlaceParams(**kn))
-        want = [outcome_of(oracle, h, s, tree, kn.get("max_iterations"), kn.get("min_match_coverage"),
-                           kn.get("remove_intersection")) for h, s in queries]
-        assert_rows_equal(res, want, [h for h, _ in queries])
-    ix.close()
+    flat = tree_to_product(cq, tree)
+    knobs = [dict(), dict(remove_intersection=True), dict(min_match_coverage=1.0),
+             dict(max_iterations=int(rng.integers(0, 3)), min_match_coverage=0.0)]
+    wants = [[outcome_of(oracle, h, s, tree, kn.get("max_iterations"), kn.get("min_match_coverage"),
+                         kn.get("remove_intersection")) for h, s in queries] for kn in knobs]
+    for f in (flat, flat.with_general_sets()):
+        ix = cq.Index(f, device=0)
+        for kn, want in zip(knobs, wants):
+            res = ix.place_batch([s for _, s in queries], cq.PlaceParams(**kn))
+            assert_rows_equal(res, want, [h for h, _ in queries])
+        ix.close()
 
 
 def tree_to_product(cq, otree):
@@ -220,17 +227,114 @@ def test_synthetic_small_config(cq, oracle):
     lens = synth.skewed_lengths(40, 5) // 5 + 35
     b2, o2, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, 40, lens, 4245)
     ix = cq.Index(sm.flat, device=0)
+    ixg = cq.Index(sm.flat.with_general_sets(), device=0)
     otree = oracle_tree_from_flat(oracle, sm.flat)
     for bs, of in ((bases, offsets), (b2, o2)):
         seqs = [bytes(bs[int(of[i]):int(of[i + 1])]).decode() for i in range(len(of) - 1)]
         for kn in (dict(), dict(remove_intersection=True)):
-            res = ix.place_batch((bs, of), cq.PlaceParams(**kn))
             want = [outcome_of(oracle, f"r{i}", s, otree, None, None, kn.get("remove_intersection"))
                     for i, s in enumerate(seqs)]
-            assert_rows_equal(res, want)
+            assert_rows_equal(ix.place_batch((bs, of), cq.PlaceParams(**kn)), want)
+            assert_rows_equal(ixg.place_batch((bs, of), cq.PlaceParams(**kn)), want)
     info = ix.info()
     assert info["n_entries"] == sm.flat.n_entries and info["k_size"] == 35
+    assert info["closed_sets"] == 1 and ixg.info()["closed_sets"] == 0
     ix.close()
+    ixg.close()
+
+
+# ---- builder-like (upward closed) random models: multifurcations, deep trees, big shared sets,
+#      every knob; checked against the C++ oracle (itself held equal to the Python one on CPU) ----------
+def _closed_model(rng, n_internal, max_kids, n_tips_per, k, m, ref_len):
+    """Random rooted tree with multifurcations; refs evolved down the tree; node sets = unions of
+    root->tip paths (the reference builder's invariant)."""
+    from classeq2_b200 import _lib
+    from classeq2_b200.model import BuiltModel, FlatModel
+    parent, kind = [-1], [_lib.KIND_ROOT]
+    internal = [0]
+    for _ in range(n_internal):
+        p = internal[int(rng.integers(len(internal)))] if rng.random() < 0.7 else internal[-1]
+        parent.append(p), kind.append(_lib.KIND_NODE)
+        internal.append(len(parent) - 1)
+    tips = []
+    for p in internal:
+        for _ in range(int(rng.integers(0, n_tips_per + 1))):
+            parent.append(p), kind.append(_lib.KIND_LEAF)
+            tips.append(len(parent) - 1)
+    n = len(parent)
+    kids = [[] for _ in range(n)]
+    for c in range(1, n):
+        kids[parent[c]].append(c)
+    child_off = np.zeros(n + 1, np.uint64)
+    child_idx = []
+    for i in range(n):
+        rng.shuffle(kids[i])
+        child_idx += kids[i]
+        child_off[i + 1] = len(child_idx)
+    node_id = (rng.permutation(4 * n)[:n] + 1).astype(np.uint64)   # sparse, shuffled ids
+    if rng.random() < 0.5:
+        node_id[0] = 0
+    seqs = [None] * n
+    seqs[0] = rng.integers(0, 4, ref_len, dtype=np.uint8)
+    order = [0]
+    for v in order:
+        for c in kids[v]:
+            s = seqs[v].copy()
+            mut = np.flatnonzero(rng.random(ref_len) < 0.03)
+            s[mut] = (s[mut] + rng.integers(1, 4, len(mut), dtype=np.uint8)) & 3
+            seqs[c] = s
+            order.append(c)
+    ascii_ = np.frombuffer(b"ACGT", np.uint8)
+    tflat = FlatModel(k, m, node_id, np.array(kind, np.uint8), child_off, np.array(child_idx, np.uint64))
+    tip_bases = np.concatenate([ascii_[seqs[t]] for t in tips]) if tips else np.zeros(0, np.uint8)
+    tip_off = np.arange(len(tips) + 1, dtype=np.uint64) * ref_len
+    bm = BuiltModel(tflat, np.array(tips, np.uint64), tip_bases, tip_off)
+    a = bm.arrays()
+    bm.close()
+    flat = FlatModel(k, m, node_id, np.array(kind, np.uint8), child_off, np.array(child_idx, np.uint64),
+                     a["entry_bucket"], a["entry_hash"], a["entry_set"], a["set_off"], a["set_node_ids"])
+    # queries: fragments of tip and internal sequences, both strands, some chimeric / random
+    qs = []
+    for _ in range(200):
+        src = seqs[int(rng.integers(n))]
+        ln = int(rng.integers(k - 2, ref_len + 1))
+        st = int(rng.integers(0, ref_len - ln + 1))
+        s = src[st:st + ln].copy()
+        if rng.random() < 0.3:
+            other = seqs[int(rng.integers(n))]
+            cut = int(rng.integers(0, ln + 1))
+            s[cut:] = other[st + cut:st + ln]
+        if rng.random() < 0.5:
+            s = (3 - s)[::-1]
+        if rng.random() < 0.05:
+            s = rng.integers(0, 4, ln, dtype=np.uint8)
+        qs.append(ascii_[s].tobytes().decode())
+    return flat, qs
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_closed_models(cq, seed):
+    from oracle import cpp_oracle
+    rng = np.random.default_rng(7000 + seed)
+    k = int(rng.choice([35, 35, 35, 21, 9]))
+    m = int(rng.choice([4, 4, 0, 2]))
+    flat, qs = _closed_model(rng, n_internal=int(rng.integers(1, 80)), max_kids=0,
+                             n_tips_per=int(rng.integers(1, 4)), k=k, m=m, ref_len=int(rng.integers(60, 260)))
+    md = cpp_oracle.CppModel.from_flat(flat)
+    bases, offsets = cq.make_batch(qs)
+    ix, ixg = cq.Index(flat, device=0), cq.Index(flat.with_general_sets(), device=0)
+    assert ix.info()["closed_sets"] == 1
+    for kn in [dict(), dict(remove_intersection=True), dict(min_match_coverage=0.0, max_iterations=3),
+               dict(min_match_coverage=1.0, max_iterations=1)]:
+        want = md.place_batch(bases, offsets, kn.get("max_iterations"), kn.get("min_match_coverage"), kn.get("remove_intersection"))
+        for index in (ix, ixg):
+            got = index.place_batch((bases, offsets), cq.PlaceParams(**kn))
+            for f in ("status", "node_id", "one", "rest", "n_query_kmers", "n_matched", "n_root_matched"):
+                bad = np.flatnonzero(getattr(got, f) != want[f])
+                assert bad.size == 0, (f, kn, bad[:5], getattr(got, f)[bad[:5]], want[f][bad[:5]])
+            ok_it = (got.iterations == want["iterations"]) | (want["status"] == 8)
+            assert ok_it.all()
+    ix.close(), ixg.close(), md.close()
 
 
 def oracle_tree_from_flat(oracle, flat):
