@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclasseq_b200.so")
+# CLASSEQ_B200_LIB selects another build of the same library (kernel A/B experiments only)
+LIB_PATH = os.environ.get("CLASSEQ_B200_LIB") or os.path.join(_HERE, "libclasseq_b200.so")
 
 CLS_OK = 0
 CLS_ERR_INVALID_ARGUMENT = -1

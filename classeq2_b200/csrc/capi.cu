@@ -108,7 +108,7 @@ struct Workspace {
 struct cls_index {
     int device = 0;
     int sm_count = 0;
-    DevBuf d_table, d_arena, d_terms, d_qnodes, d_qchild, d_qid, d_qend, d_qdepth, d_qup;
+    DevBuf d_table, d_arena, d_terms, d_qnodes, d_qchild, d_qid, d_qinfo, d_lca;
     DeviceIndex dix{};
     cls_index_info info{};
     std::mutex mu;
@@ -387,9 +387,8 @@ int cls_index_create(const cls_model_view *model, int device, cls_index **out) {
     CU_TRY(up(ix->d_qchild, h.q_child_list.data(), h.q_child_list.size() * sizeof(uint32_t)));
     CU_TRY(up(ix->d_qid, h.q_node_id.data(), h.q_node_id.size() * sizeof(uint64_t)));
     CU_TRY(up(ix->d_terms, h.terms.data(), h.terms.size() * sizeof(uint32_t)));
-    CU_TRY(up(ix->d_qend, h.q_end.data(), h.q_end.size() * sizeof(uint32_t)));
-    CU_TRY(up(ix->d_qdepth, h.q_depth.data(), h.q_depth.size() * sizeof(uint32_t)));
-    CU_TRY(up(ix->d_qup, h.q_up.data(), h.q_up.size() * sizeof(uint32_t)));
+    CU_TRY(up(ix->d_qinfo, h.qinfo.data(), h.qinfo.size() * sizeof(QInfo)));
+    CU_TRY(up(ix->d_lca, h.lca_table.data(), h.lca_table.size() * sizeof(uint64_t)));
     ix->dix.table = (const Slot *)ix->d_table.p;
     ix->dix.bucket_mask = h.n_buckets - 1;
     ix->dix.arena = (const SetWord *)ix->d_arena.p;
@@ -397,11 +396,10 @@ int cls_index_create(const cls_model_view *model, int device, cls_index **out) {
     ix->dix.q_child_list = (const uint32_t *)ix->d_qchild.p;
     ix->dix.q_node_id = (const uint64_t *)ix->d_qid.p;
     ix->dix.terms = (const uint32_t *)ix->d_terms.p;
-    ix->dix.q_end = (const uint32_t *)ix->d_qend.p;
-    ix->dix.q_depth = (const uint32_t *)ix->d_qdepth.p;
-    ix->dix.q_up = (const uint32_t *)ix->d_qup.p;
+    ix->dix.qinfo = (const QInfo *)ix->d_qinfo.p;
+    ix->dix.lca_table = (const uint64_t *)ix->d_lca.p;
     ix->dix.n_q = (uint32_t)h.qnodes.size();
-    ix->dix.n_lift = h.n_lift;
+    ix->dix.euler_len = h.euler_len;
     ix->dix.closed = h.closed ? 1u : 0u;
     ix->dix.k_size = h.k_size;
     ix->dix.m_eff = h.m_eff;
@@ -432,7 +430,7 @@ void cls_index_destroy(cls_index *ix) {
         w->d_words.release(); w->d_descs.release(); w->d_results.release();
     }
     ix->d_table.release(); ix->d_arena.release(); ix->d_qnodes.release(); ix->d_qchild.release(); ix->d_qid.release();
-    ix->d_terms.release(); ix->d_qend.release(); ix->d_qdepth.release(); ix->d_qup.release();
+    ix->d_terms.release(); ix->d_qinfo.release(); ix->d_lca.release();
     delete ix;
 }
 

@@ -43,9 +43,20 @@ constexpr uint32_t kSetHasRoot = 1u;
 // DFS pre-order (q ids; subtree(q) = [q, q_end[q])) membership of a node x is
 // "some terminal lies in [x, q_end[x])".
 //   terms[off]          header: n_terminals | (contains root) << 31
-//   terms[off+1 .. +n]  terminal q ids, ascending
+//   terms[off+1]        copy of the LAST terminal (so first and last arrive in one round trip)
+//   terms[off+2 .. +n]  terminal q ids, ascending
 // Sets that do not contain the root carry n = 0: they only count towards |M|.
 constexpr uint32_t kTermHasRoot = 0x80000000u;
+
+// Per non-leaf node, closed mode.  LCA queries go through an Euler tour of the non-leaf tree and
+// a sparse table of (depth << 32 | q) minima: two dependent round trips, whatever the depth.
+struct QInfo {
+    uint32_t q_end;        // one past the last q of the subtree
+    uint32_t child_count;  // non-leaf children; they tile [q+1, q_end): c1 = q+1, c2 = q_end[c1], ...
+    uint32_t euler_first;  // first occurrence in the Euler tour
+    uint32_t depth;
+};
+static_assert(sizeof(QInfo) == 16, "QInfo must be 16 bytes");
 
 // ---- flattened tree over non-leaf nodes (dense ids q in DFS pre-order, root = 0) ------
 struct QNode {
@@ -78,11 +89,10 @@ struct DeviceIndex {
     const QNode *qnodes;
     const uint32_t *q_child_list;
     const uint64_t *q_node_id;
-    const uint32_t *q_end;        // closed mode: one past the last q of the subtree
-    const uint32_t *q_depth;      // closed mode
-    const uint32_t *q_up;         // closed mode: binary lifting, q_up[j * n_q + q] = 2^j-th ancestor
+    const QInfo *qinfo;           // closed mode
+    const uint64_t *lca_table;    // closed mode: sparse table, level j at lca_table + j * euler_len
     uint32_t n_q;
-    uint32_t n_lift;
+    uint32_t euler_len;
     uint32_t k_size;
     uint32_t m_eff;         // min(m, k): number of prefix bases in the bucket code
     uint32_t max_fanout;    // max child_count over qnodes

@@ -83,6 +83,8 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
     std::vector<uint32_t> q_parent;  // q -> parent q
     std::vector<uint32_t> q_ord;     // q -> ordinal among the parent's non-leaf children
     std::vector<uint32_t> q_end;     // q -> one past the last q of its subtree (pre-order interval)
+    std::vector<uint32_t> lca_tour;  // Euler tour of the non-leaf tree
+    uint32_t lca_levels = 0;
     {
         node_q[0] = 0; q_node.push_back(0); q_parent.push_back(kNoQ); q_ord.push_back(0);
         out.qnodes.push_back(QNode{0, 0});
@@ -126,22 +128,38 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
         }
         out.q_node_id.resize(nq);
         for (uint32_t q = 0; q < nq; ++q) out.q_node_id[q] = mv->node_id[q_node[q]];
-        // closed-mode tree arrays: subtree intervals, depths, binary-lifting ancestors
-        out.q_end = q_end;
-        out.q_depth.assign(nq, 0);
-        uint32_t max_depth = 0;
-        for (uint32_t q = 1; q < nq; ++q) {  // pre-order: parents first
-            out.q_depth[q] = out.q_depth[q_parent[q]] + 1;
-            max_depth = std::max(max_depth, out.q_depth[q]);
+        // closed-mode tree arrays: subtree intervals, depths, Euler tour + sparse table for LCA
+        out.qinfo.assign(nq, QInfo{0, 0, 0, 0});
+        for (uint32_t q = 0; q < nq; ++q) {
+            out.qinfo[q].q_end = q_end[q];
+            out.qinfo[q].child_count = out.qnodes[q].child_count;
+            if (q) out.qinfo[q].depth = out.qinfo[q_parent[q]].depth + 1;  // pre-order: parents first
         }
-        uint32_t n_lift = 1;
-        while ((1u << n_lift) <= max_depth) ++n_lift;
-        out.n_lift = n_lift;
-        out.q_up.assign((size_t)n_lift * nq, 0);
-        for (uint32_t q = 1; q < nq; ++q) out.q_up[q] = q_parent[q];
-        for (uint32_t j = 1; j < n_lift; ++j)
-            for (uint32_t q = 0; q < nq; ++q)
-                out.q_up[(size_t)j * nq + q] = out.q_up[(size_t)(j - 1) * nq + out.q_up[(size_t)(j - 1) * nq + q]];
+        std::vector<uint32_t> tour;
+        tour.reserve(2 * (size_t)nq);
+        {
+            std::vector<uint32_t> stack{0}, cur(nq, 0);
+            out.qinfo[0].euler_first = 0;
+            tour.push_back(0);
+            while (!stack.empty()) {
+                const uint32_t q = stack.back();
+                const QNode qn = out.qnodes[q];
+                if (cur[q] == qn.child_count) {
+                    stack.pop_back();
+                    if (!stack.empty()) tour.push_back(stack.back());
+                    continue;
+                }
+                const uint32_t c = out.q_child_list[qn.child_first + cur[q]++];
+                out.qinfo[c].euler_first = (uint32_t)tour.size();
+                tour.push_back(c);
+                stack.push_back(c);
+            }
+        }
+        out.euler_len = (uint32_t)tour.size();
+        uint32_t levels = 1;
+        while ((2u << (levels - 1)) <= out.euler_len) ++levels;
+        lca_levels = levels;
+        lca_tour.swap(tour);
     }
     const uint32_t nq = (uint32_t)q_node.size();
 
@@ -194,7 +212,18 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
     }
     out.closed = closed;
 
+    if (closed && (uint64_t)lca_levels * out.euler_len > (1ull << 27)) closed = out.closed = false;  // LCA table > 1 GiB
     if (closed) {
+        // sparse table over the Euler tour: level j holds minima of (depth << 32 | q) over [i, i + 2^j)
+        const size_t len = out.euler_len;
+        out.lca_table.assign((size_t)lca_levels * len, ~0ull);
+        for (size_t i = 0; i < len; ++i) out.lca_table[i] = ((uint64_t)out.qinfo[lca_tour[i]].depth << 32) | lca_tour[i];
+        for (uint32_t j = 1; j < lca_levels; ++j) {
+            const size_t half = (size_t)1 << (j - 1);
+            const uint64_t *prev = &out.lca_table[(size_t)(j - 1) * len];
+            uint64_t *cur = &out.lca_table[(size_t)j * len];
+            for (size_t i = 0; i + 2 * half <= len; ++i) cur[i] = std::min(prev[i], prev[i + half]);
+        }
         // terminal-list records (device_types.hpp), de-duplicated by content
         std::unordered_map<uint64_t, std::vector<uint32_t>> dedup;
         dedup.reserve(n_sets / 4 + 16);
@@ -212,19 +241,22 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
             rec.clear();
             if (stamp[0] != tag) {
                 rec.push_back(0u);
+                rec.push_back(0u);
             } else {
                 for (uint32_t q : members) if (q != 0) has_child[q_parent[q]] = tag;
                 rec.push_back(0u);
+                rec.push_back(0u);
                 for (uint32_t q : members) if (has_child[q] != tag) rec.push_back(q);
-                std::sort(rec.begin() + 1, rec.end());
-                rec[0] = (uint32_t)(rec.size() - 1) | kTermHasRoot;
+                std::sort(rec.begin() + 2, rec.end());
+                rec[0] = (uint32_t)(rec.size() - 2) | kTermHasRoot;
+                rec[1] = rec.back();
             }
             uint64_t h = 0x243f6a8885a308d3ULL;
             for (uint32_t w : rec) h = mix64(h ^ w);
             auto &cands = dedup[h];
             uint32_t found = kEmpty;
             for (uint32_t off : cands) {
-                if ((out.terms[off] & ~kTermHasRoot) + 1 == rec.size() &&
+                if ((out.terms[off] & ~kTermHasRoot) + 2 == rec.size() &&
                     std::memcmp(&out.terms[off], rec.data(), rec.size() * sizeof(uint32_t)) == 0) { found = off; break; }
             }
             if (found == kEmpty) {
@@ -236,7 +268,7 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
             }
             set_arena_off[s] = found;
         }
-        out.terms.push_back(0u);  // padding: records are read one word past a range end at most
+        for (int pad = 0; pad < 4; ++pad) out.terms.push_back(0u);  // records may be read a little past their end
     } else {
         std::unordered_map<uint64_t, std::vector<uint32_t>> dedup;  // content hash -> arena offsets
         dedup.reserve(n_sets / 4 + 16);

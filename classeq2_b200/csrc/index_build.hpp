@@ -20,8 +20,9 @@ struct HostIndex {
     bool closed = false;            // terminal-list records (`terms`) instead of mini-trees (`arena`)
     std::vector<SetWord> arena;
     std::vector<uint32_t> terms;
-    std::vector<uint32_t> q_end, q_depth, q_up;  // q_up: n_lift x n_q
-    uint32_t n_lift = 0;
+    std::vector<QInfo> qinfo;             // closed mode
+    std::vector<uint64_t> lca_table;      // closed mode: n_levels x euler_len
+    uint32_t euler_len = 0;
     uint64_t n_distinct_sets = 0;
     std::vector<QNode> qnodes;
     std::vector<uint32_t> q_child_list;

@@ -37,6 +37,9 @@ namespace cls {
 
 namespace {
 
+#ifndef CLS_PIPELINE
+#define CLS_PIPELINE 0  // probe software pipelining: 0 = none (fastest measured: 7.21 ms), 1 = rotate registers (7.24), 2 = ping-pong (8.43; code bloat)
+#endif
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kUndecided = 0xFFFFFFFFu;
 constexpr uint32_t kRing = 64;  // pre-mix ring entries per warp (two 32-offset chunks)
@@ -97,88 +100,79 @@ __device__ __forceinline__ void ld_bucket(const Slot *table, uint64_t bucket, ui
                  : "l"(table + 2 * bucket));
 }
 
-// `nbits` (<= 24) bits of a packed strand starting at base `pos`.
+// `mask`-selected low bits (<= 24 of them) of a packed strand starting at base `pos`.
 __device__ __forceinline__ uint32_t packed_bits(const uint32_t *pk, uint32_t pos, uint32_t mask) {
     const uint32_t j = pos >> 4;
     return __funnelshift_r(pk[j], pk[j + 1], (2u * pos) & 31u) & mask;
 }
 
-// 64-bit x * 5 + c
-__device__ __forceinline__ uint64_t mul5add(uint64_t x, uint64_t c) { return x * 5ull + c; }
-
-// Pre-mixes of the 8-byte little-endian word at byte offset q of an ASCII strand:
-//   a = rotl(w * c1, 31) * c2   (the k1 lane of a murmur block), b = rotl(w * c2, 33) * c1 (the k2 lane)
-__device__ __forceinline__ void premix_word(const uint32_t *s32, uint32_t q, uint64_t &a, uint64_t &b) {
+// Pre-mixes of the 8-byte little-endian word at byte offset q of an ASCII strand, into the ring.
+__device__ __forceinline__ void premix_to_ring(const WarpMem &m, const uint32_t *s32, uint32_t q) {
     const uint32_t *w = s32 + (q >> 2);
     const uint32_t sh = (q & 3u) * 8u;
     const uint32_t r0 = w[0], r1 = w[1], r2 = w[2];
-    const uint64_t x = (uint64_t)__funnelshift_r(r0, r1, sh) | ((uint64_t)__funnelshift_r(r1, r2, sh) << 32);
-    a = rotl64_d(x * kC1, 31) * kC2;
-    b = rotl64_d(x * kC2, 33) * kC1;
+    const uint64_t x = pack64(__funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh));
+    m.ring_a[q & (kRing - 1)] = premix_k1(x);
+    m.ring_b[q & (kRing - 1)] = premix_k2(x);
 }
 
-// Calls f(rc, pos, hash) for every window of both strands (reference order: forward windows,
-// then reverse-complement windows), one window per lane.  Must be called by all 32 lanes.
-//   K == 35: ring-shared pre-mixes (see the header comment);  K == 0: generic byte-wise hash.
-template <int K, class F>
-__device__ __forceinline__ uint32_t for_each_window(const WarpMem &m, uint32_t len, uint32_t k, const uint64_t *tail_lut,
-                                                F &&f) {
-    const uint32_t lane = lane_id();
-    const uint32_t W = len - k + 1;
-    const uint32_t n_chunks = (W + 31u) >> 5;
-    uint32_t acc = 0;
-#pragma unroll 1
-    for (uint32_t strand = 0; strand < 2; ++strand) {
-        const uint32_t *s32 = strand ? m.str_r : m.str_f;
+// Window hashing, one window per lane and pass.  Usage, by all 32 lanes:
+//     for strand in {0, 1}: begin_strand(strand); for c in [0, n_chunks): valid = pass(c, pos, h)
+//   K == 35: every 8-byte word of the strand is pre-mixed once (both murmur lanes) into a 64-entry
+//            shared-memory ring and reused by the four windows that contain it at block offsets
+//            0 / 8 / 16 / 24; block 0 starts from h1 = h2 = 0; the 3-byte tail mix is a table.
+//   K == 0 : generic byte-wise hash for any runtime k.
+template <int K>
+struct WindowHasher {
+    const WarpMem &m;
+    const uint64_t *tail_lut;
+    uint32_t W, k, lane;
+    const uint32_t *s32, *pk;
+
+    __device__ __forceinline__ WindowHasher(const WarpMem &m_, const uint64_t *lut, uint32_t len, uint32_t k_)
+        : m(m_), tail_lut(lut), W(len - k_ + 1), k(k_), lane(threadIdx.x & 31u), s32(nullptr), pk(nullptr) {}
+
+    __device__ __forceinline__ uint32_t n_chunks() const { return (W + 31u) >> 5; }
+
+    __device__ __forceinline__ void begin_strand(uint32_t strand) {
+        s32 = strand ? m.str_r : m.str_f;
+        pk = strand ? m.pk_r : m.pk_f;
         if constexpr (K == 35) {
-            const uint32_t *pk = strand ? m.pk_r : m.pk_f;
-            const uint32_t n_off = W + 24u;  // offsets 0 .. W+23 carry a pre-mix some window needs
-            {
-                uint64_t a, b;
-                if (lane < n_off) { premix_word(s32, lane, a, b); m.ring_a[lane] = a; m.ring_b[lane] = b; }
-            }
-#pragma unroll 1
-            for (uint32_t c = 0; c < n_chunks; ++c) {
-                const uint32_t q = 32u * (c + 1) + lane;
-                if (q < n_off) {
-                    uint64_t a, b;
-                    premix_word(s32, q, a, b);
-                    m.ring_a[q & (kRing - 1)] = a;
-                    m.ring_b[q & (kRing - 1)] = b;
-                }
-                __syncwarp();
-                const uint32_t p = 32u * c + lane;
-                if (p < W) {
-                    const uint64_t a0 = m.ring_a[p & (kRing - 1)], b1 = m.ring_b[(p + 8) & (kRing - 1)];
-                    const uint64_t a2 = m.ring_a[(p + 16) & (kRing - 1)], b3 = m.ring_b[(p + 24) & (kRing - 1)];
-                    // block 0 (h1 = h2 = 0 on entry), block 1, 3-byte tail, finalisation
-                    uint64_t h1 = mul5add(rotl64_d(a0, 27), 0x52dce729ull);
-                    uint64_t h2 = mul5add(rotl64_d(b1, 31) + h1, 0x38495ab5ull);
-                    h1 = mul5add(rotl64_d(h1 ^ a2, 27) + h2, 0x52dce729ull);
-                    h2 = mul5add(rotl64_d(h2 ^ b3, 31) + h1, 0x38495ab5ull);
-                    h1 ^= tail_lut[packed_bits(pk, p + 32u, 63u)];
-                    acc += f(strand != 0, p, mm_finish(h1, h2, 35ull));
-                }
-                __syncwarp();
-            }
-        } else {
-#pragma unroll 1
-            for (uint32_t c = 0; c < n_chunks; ++c) {
-                const uint32_t p = 32u * c + lane;
-                if (p < W) acc += f(strand != 0, p, murmur_window_generic(reinterpret_cast<const uint8_t *>(s32), p, k));
-            }
+            if (lane < W + 24u) premix_to_ring(m, s32, lane);  // offsets 0 .. W+23 carry a needed pre-mix
         }
     }
-    return acc;
-}
+
+    __device__ __forceinline__ bool pass(uint32_t c, uint32_t &pos, uint64_t &h) {
+        pos = 32u * c + lane;
+        const bool valid = pos < W;
+        if constexpr (K == 35) {
+            const uint32_t q = pos + 32u;
+            if (q < W + 24u) premix_to_ring(m, s32, q);
+            __syncwarp();
+            if (valid) {
+                const uint64_t a0 = m.ring_a[pos & (kRing - 1)], b1 = m.ring_b[(pos + 8) & (kRing - 1)];
+                const uint64_t a2 = m.ring_a[(pos + 16) & (kRing - 1)], b3 = m.ring_b[(pos + 24) & (kRing - 1)];
+                uint64_t h1 = mul5add(rotlc<27>(a0), 0x52dce729u);
+                uint64_t h2 = mul5add(rotlc<31>(b1) + h1, 0x38495ab5u);
+                h1 = mul5add(rotlc<27>(h1 ^ a2) + h2, 0x52dce729u);
+                h2 = mul5add(rotlc<31>(h2 ^ b3) + h1, 0x38495ab5u);
+                h1 ^= tail_lut[packed_bits(pk, pos + 32u, 63u)];
+                h = mm_finish(h1, h2, 35ull);
+            }
+            __syncwarp();
+        } else {
+            if (valid) h = murmur_window_generic(reinterpret_cast<const uint8_t *>(s32), pos, k);
+        }
+        return valid;
+    }
+};
 
 // tail_lut[c0 | c1 << 2 | c2 << 4] = k1 pre-mix of the 3-byte tail "XYZ" (codes A=0 C=1 T=2 G=3).
 __device__ __forceinline__ void init_tail_lut(uint64_t *tail_lut) {
-    if (threadIdx.x < 64) {
-        const uint32_t i = threadIdx.x;
+    for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) {
         const uint64_t t = (uint64_t)((kAsciiLut >> (8 * (i & 3))) & 0xFF) | ((uint64_t)((kAsciiLut >> (8 * ((i >> 2) & 3))) & 0xFF) << 8) |
                            ((uint64_t)((kAsciiLut >> (8 * ((i >> 4) & 3))) & 0xFF) << 16);
-        tail_lut[i] = rotl64_d(t * kC1, 31) * kC2;
+        tail_lut[i] = premix_k1(t);
     }
 }
 
@@ -191,15 +185,19 @@ __device__ __forceinline__ uint32_t lower_bound_terms(const uint32_t *__restrict
     return lo;
 }
 
-// Lowest common ancestor of pre-order ids u <= v (binary lifting; uniform across the warp).
-__device__ __forceinline__ uint32_t lca(const DeviceIndex &ix, uint32_t u, uint32_t v) {
-    if (v < __ldg(ix.q_end + u)) return u;
-    uint32_t a = u;
-    for (int j = (int)ix.n_lift - 1; j >= 0; --j) {
-        const uint32_t b = __ldg(ix.q_up + (size_t)j * ix.n_q + a);
-        if (__ldg(ix.q_end + b) <= v) a = b;  // b does not contain v yet
-    }
-    return __ldg(ix.q_up + a);  // parent of the highest ancestor that does not contain v
+__device__ __forceinline__ QInfo ld_qinfo(const QInfo *qi, uint32_t q) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(qi + q));
+    return QInfo{v.x, v.y, v.z, v.w};
+}
+
+// Lowest common ancestor of pre-order ids u <= v: minimum of (depth << 32 | q) over the Euler-tour
+// range between their first occurrences, from the sparse table.  Two dependent round trips.
+__device__ __forceinline__ uint64_t lca_depth_node(const DeviceIndex &ix, uint32_t u, uint32_t v) {
+    const uint32_t fu = __ldg(&ix.qinfo[u].euler_first), fv = __ldg(&ix.qinfo[v].euler_first);
+    const uint32_t j = 31u - __clz(fv - fu + 1u);
+    const uint64_t *lvl = ix.lca_table + (size_t)j * ix.euler_len;
+    const uint64_t a = __ldg(lvl + fu), b = __ldg(lvl + fv + 1u - (1u << j));
+    return a < b ? a : b;
 }
 
 // One-vs-rest decision over `m` children whose vote counters sit in shared memory
@@ -266,8 +264,15 @@ __global__ void hash_only_kernel(const uint32_t *__restrict__ packed, uint32_t l
     if (threadIdx.x >= 32) return;
     decode_read(packed, len, m, pk_words);
     __syncwarp();
-    const uint32_t W = len - k + 1;
-    for_each_window<K>(m, len, k, tail_lut, [=](bool rc, uint32_t pos, uint64_t h) -> uint32_t { out[(rc ? W : 0u) + pos] = h; return 0u; });
+    WindowHasher<K> wh(m, tail_lut, len, k);
+    for (uint32_t strand = 0; strand < 2; ++strand) {
+        wh.begin_strand(strand);
+        for (uint32_t c = 0; c < wh.n_chunks(); ++c) {
+            uint32_t pos;
+            uint64_t h;
+            if (wh.pass(c, pos, h)) out[(strand ? wh.W : 0u) + pos] = h;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -275,10 +280,10 @@ __global__ void hash_only_kernel(const uint32_t *__restrict__ packed, uint32_t l
 // ------------------------------------------------------------------------------------------
 template <int K, bool CLOSED>
 __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlaceParams pp,
-                                                    const uint32_t *__restrict__ packed,
-                                                    const ReadDesc *__restrict__ reads, uint32_t first_read,
-                                                    uint32_t n_reads, ResultRec *__restrict__ results,
-                                                    PlaceGeom g) {
+                                                       const uint32_t *__restrict__ packed,
+                                                       const ReadDesc *__restrict__ reads, uint32_t first_read,
+                                                       uint32_t n_reads, ResultRec *__restrict__ results,
+                                                       PlaceGeom g) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t tail_lut[64];
     init_tail_lut(tail_lut);
@@ -290,9 +295,9 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
     wm.ring_a = reinterpret_cast<uint64_t *>(wbase);
     wm.ring_b = wm.ring_a + kRing;
     uint32_t *t1 = wbase + 4 * kRing;    // dedup set keyed by table slot; later the live-set list
-    uint32_t *t2k = t1 + g.t1_size;      // histogram keys: node-set record offsets
-    uint32_t *t2c = t2k + g.t2_size;     // histogram counts
-    uint32_t *lst = t2c + g.t2_size;     // histogram positions of the distinct sets, in arrival order
+    uint32_t *t2k = t1 + g.t1_size;      // histogram keys: node-set record offsets; later `first`
+    uint32_t *t2c = t2k + g.t2_size;     // histogram counts; later `last`
+    uint32_t *lst = t2c + g.t2_size;     // histogram positions of the distinct sets; later `hi`
     wm.str_f = lst + g.t2_size;
     wm.str_r = wm.str_f + g.str_words;
     wm.pk_f = wm.str_r + g.str_words;
@@ -329,60 +334,127 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
         decode_read(packed + rd.word_off, L, wm, g.pk_words);
         __syncwarp();
 
-        // ---- hash + probe + dedup + histogram -------------------------------------------
-        const uint32_t n_fresh = for_each_window<K>(wm, L, k, tail_lut, [=](bool rc, uint32_t pos, uint64_t h) -> uint32_t {
-            uint64_t b = h & ix.bucket_mask;
+        // ---- hash + probe + dedup + histogram, software pipelined: the bucket of pass i is in
+        //      flight while pass i+1 is hashed and pass i-1 is consumed ---------------------------
+        // consume(): match the loaded bucket, gate by bucket key, de-duplicate by table slot, and add
+        // the distinct hits to the node-set histogram (one shared-memory atomic per group of lanes
+        // that hit the same node set, found with match.any).  Called by all 32 lanes.
+        auto consume = [=](bool valid, bool rc, uint32_t pos, uint64_t h, uint64_t h0, uint64_t m0, uint64_t h1,
+                           uint64_t m1) -> uint32_t {
             uint32_t slot_id = kEmpty, set_off = 0, code = 0;
-            for (;;) {
-                uint64_t h0, m0, h1, m1;
-                ld_bucket(ix.table, b, h0, m0, h1, m1);
-                if (h0 == h && (uint32_t)m0 != kEmpty) { slot_id = (uint32_t)(2 * b); set_off = (uint32_t)m0; code = (uint32_t)(m0 >> 32); break; }
-                if (h1 == h && (uint32_t)m1 != kEmpty) { slot_id = (uint32_t)(2 * b + 1); set_off = (uint32_t)m1; code = (uint32_t)(m1 >> 32); break; }
-                if (!((uint32_t)(m0 >> 32) & kOverflowBit)) break;
-                b = (b + 1) & ix.bucket_mask;
+            if (valid) {
+                uint64_t b = h & ix.bucket_mask;
+                for (;;) {
+                    if (h0 == h && (uint32_t)m0 != kEmpty) { slot_id = (uint32_t)(2 * b); set_off = (uint32_t)m0; code = (uint32_t)(m0 >> 32); break; }
+                    if (h1 == h && (uint32_t)m1 != kEmpty) { slot_id = (uint32_t)(2 * b + 1); set_off = (uint32_t)m1; code = (uint32_t)(m1 >> 32); break; }
+                    if (!((uint32_t)(m0 >> 32) & kOverflowBit)) break;
+                    b = (b + 1) & ix.bucket_mask;
+                    ld_bucket(ix.table, b, h0, m0, h1, m1);
+                }
             }
-            if (slot_id == kEmpty) return 0u;
-            // bucket gating: the entry's bucket key must be among the query's prefix keys
-            const uint32_t want = code & kCodeMask;
-            bool pass = packed_bits(rc ? wm.pk_r : wm.pk_f, pos, code_mask) == want;
-            if (!pass) {  // only possible for models whose bucket keys disagree with their k-mers
-                for (uint32_t p = 0; p < W && !pass; ++p)
-                    pass = packed_bits(wm.pk_f, p, code_mask) == want || packed_bits(wm.pk_r, p, code_mask) == want;
-                if (!pass) return 0u;
+            bool fresh = false;
+            if (slot_id != kEmpty) {
+                // bucket gating: the entry's bucket key must be among the query's prefix keys
+                const uint32_t want = code & kCodeMask;
+                bool pass = packed_bits(rc ? wm.pk_r : wm.pk_f, pos, code_mask) == want;
+                if (!pass) {  // only possible for models whose bucket keys disagree with their k-mers
+                    for (uint32_t p = 0; p < W && !pass; ++p)
+                        pass = packed_bits(wm.pk_f, p, code_mask) == want || packed_bits(wm.pk_r, p, code_mask) == want;
+                }
+                if (pass) {
+                    uint32_t p1 = slot_id & t1_mask;
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&t1[p1], kEmpty, slot_id);
+                        if (old == kEmpty) { fresh = true; break; }
+                        if (old == slot_id) break;  // the same k-mer hash was already counted
+                        p1 = (p1 + 1) & t1_mask;
+                    }
+                }
             }
-            uint32_t p1 = slot_id & t1_mask;
-            for (;;) {
-                const uint32_t old = atomicCAS(&t1[p1], kEmpty, slot_id);
-                if (old == slot_id) return 0u;  // the same k-mer hash was already counted
-                if (old == kEmpty) break;
-                p1 = (p1 + 1) & t1_mask;
+            const uint32_t fm = __ballot_sync(kFull, fresh);
+            if (fresh) {
+                const uint32_t peers = __match_any_sync(fm, set_off);
+                if ((uint32_t)(__ffs(peers) - 1) == lane) {
+                    uint32_t p2 = (set_off * 0x9E3779B1u) >> t2_shift;
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&t2k[p2], kEmpty, set_off);
+                        if (old == kEmpty) lst[atomicAdd(n_sets_smem, 1u)] = p2;
+                        if (old == kEmpty || old == set_off) { atomicAdd(&t2c[p2], (uint32_t)__popc(peers)); break; }
+                        p2 = (p2 + 1) & t2_mask;
+                    }
+                }
             }
-            uint32_t p2 = (set_off * 0x9E3779B1u) >> t2_shift;
-            for (;;) {
-                const uint32_t old = atomicCAS(&t2k[p2], kEmpty, set_off);
-                if (old == kEmpty) { lst[atomicAdd(n_sets_smem, 1u)] = p2; }
-                if (old == kEmpty || old == set_off) { atomicAdd(&t2c[p2], 1u); break; }
-                p2 = (p2 + 1) & t2_mask;
+            return (uint32_t)__popc(fm);
+        };
+
+        uint32_t n_matched = 0;
+        {
+            WindowHasher<K> wh(wm, tail_lut, L, k);
+            const uint32_t n_chunks = wh.n_chunks();
+            // passes t = 0 .. 2 * n_chunks - 1 (forward chunks, then reverse-complement chunks), taken two
+            // at a time with ping-pong register sets A / B so that no loaded value is copied (a copy
+            // would wait for the load and undo the pipelining)
+            auto hash_and_issue = [&](uint32_t t, bool &valid, bool &rc, uint32_t &pos, uint64_t &h, uint64_t &q0,
+                                      uint64_t &qm0, uint64_t &q1, uint64_t &qm1) {
+                rc = t >= n_chunks;
+                const uint32_t c = rc ? t - n_chunks : t;
+                if (c == 0) wh.begin_strand(rc ? 1u : 0u);
+                valid = wh.pass(c, pos, h);
+                if (valid) ld_bucket(ix.table, h & ix.bucket_mask, q0, qm0, q1, qm1);
+            };
+            [[maybe_unused]] bool av = false, arc = false, bv = false, brc = false;
+            [[maybe_unused]] uint32_t apos = 0, bpos = 0;
+            [[maybe_unused]] uint64_t ah = 0, a0 = 0, am0 = 0, a1 = 0, am1 = 0, bh = 0, b0 = 0, bm0 = 0, b1 = 0, bm1 = 0;
+#if CLS_PIPELINE == 2
+#pragma unroll 1
+            for (uint32_t t = 0; t < 2 * n_chunks; t += 2) {
+                hash_and_issue(t, av, arc, apos, ah, a0, am0, a1, am1);
+                n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
+                hash_and_issue(t + 1, bv, brc, bpos, bh, b0, bm0, b1, bm1);
+                n_matched += consume(av, arc, apos, ah, a0, am0, a1, am1);
             }
-            return 1u;
-        });
-        const uint32_t n_matched = __reduce_add_sync(kFull, n_fresh);
+            n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
+#elif CLS_PIPELINE == 1
+#pragma unroll 1
+            for (uint32_t t = 0; t < 2 * n_chunks; ++t) {
+                hash_and_issue(t, av, arc, apos, ah, a0, am0, a1, am1);
+                n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
+                bv = av; brc = arc; bpos = apos; bh = ah; b0 = a0; bm0 = am0; b1 = a1; bm1 = am1;
+            }
+            n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
+#else
+#pragma unroll 1
+            for (uint32_t t = 0; t < 2 * n_chunks; ++t) {
+                hash_and_issue(t, av, arc, apos, ah, a0, am0, a1, am1);
+                n_matched += consume(av, arc, apos, ah, a0, am0, a1, am1);
+            }
+#endif
+        }
         __syncwarp();
         const uint32_t D = *n_sets_smem;
 
         // ---- live-set list: restrict to sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
-        //      CLOSED : t1[2j] = lo, t1[2j+1] = weight, lst[j] = hi   (terminal range [lo, hi))
+        //      CLOSED : t1[2j] = lo, t1[2j+1] = weight, lst[j] = hi (terminal range [lo, hi)),
+        //               t2k[j] = terms[lo] ("first"), t2c[j] = terms[hi-1] ("last")
         //      GENERAL: t1[2j] = current mini-tree entry, t1[2j+1] = weight
-        uint32_t n_root = 0;
         for (uint32_t j = lane; j < D; j += 32) {
             const uint32_t p2 = lst[j];
-            const uint32_t off = t2k[p2];
-            uint32_t w = t2c[p2];
+            const uint32_t off = t2k[p2], w = t2c[p2];
+            t1[2 * j] = off;
+            t1[2 * j + 1] = w;
+        }
+        __syncwarp();
+        uint32_t n_root = 0;
+        for (uint32_t j = lane; j < D; j += 32) {
+            const uint32_t off = t1[2 * j];
+            uint32_t w = t1[2 * j + 1];
             if constexpr (CLOSED) {
-                const uint32_t hdr = __ldg(ix.terms + off);
+                const uint32_t hdr = __ldg(ix.terms + off), last = __ldg(ix.terms + off + 1), first = __ldg(ix.terms + off + 2);
                 if (hdr & kTermHasRoot) n_root += w; else w = 0;
-                t1[2 * j] = off + 1;
-                lst[j] = off + 1 + (hdr & ~kTermHasRoot);
+                t1[2 * j] = off + 2;
+                lst[j] = off + 2 + (hdr & ~kTermHasRoot);
+                t2k[j] = first;
+                t2c[j] = last;
             } else {
                 const SetWord hdr = ix.arena[off];
                 if (hdr.x & kSetHasRoot) n_root += w; else w = 0;
@@ -414,51 +486,60 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
         int64_t iteration = 0;
         const int64_t max_iter = pp.max_iterations;
         if constexpr (CLOSED) {
+            uint32_t depth_p = 0;
+            QInfo ip = res.status == kUndecided ? ld_qinfo(ix.qinfo, 0) : QInfo{0, 0, 0, 0};
             while (res.status == kUndecided) {
                 // pooled extremes of the live terminals -> every level down to their LCA is unanimous
                 uint32_t umin = 0xFFFFFFFFu, vmax = 0, wl = 0;
                 for (uint32_t j = lane; j < D; j += 32) {
                     const uint32_t w = t1[2 * j + 1];
                     if (w == 0) continue;
-                    umin = min(umin, __ldg(ix.terms + t1[2 * j]));
-                    vmax = max(vmax, __ldg(ix.terms + lst[j] - 1));
+                    umin = min(umin, t2k[j]);
+                    vmax = max(vmax, t2c[j]);
                     wl += w;
                 }
                 umin = __reduce_min_sync(kFull, umin);
                 vmax = __reduce_max_sync(kFull, vmax);
                 const uint32_t Wlive = __reduce_add_sync(kFull, wl);
-                const uint32_t A = lca(ix, umin, vmax);
-                const uint32_t d = __ldg(ix.q_depth + A) - __ldg(ix.q_depth + p);
-                if (d > 0) {
+                const uint64_t dn = lca_depth_node(ix, umin, vmax);
+                const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
+                if (depth_a > depth_p) {
+                    const uint32_t d = depth_a - depth_p;
                     if (iteration + (int64_t)d > max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
                     iteration += d;
-                    if (ix.qnodes[A].child_count == 0) {  // update_introspection_node.rs:32-87
+                    ip = ld_qinfo(ix.qinfo, A);
+                    if (ip.child_count == 0) {  // update_introspection_node.rs:32-87
                         res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[A];
                         res.one = (int32_t)Wlive; res.rest = 0;
                         break;
                     }
-                    p = A;
+                    p = A; depth_p = depth_a;
                 }
                 // ---- evaluate the children of p -------------------------------------------------
                 iteration++;
                 if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
-                const uint32_t m = ix.qnodes[p].child_count;
-                const uint32_t p_end = __ldg(ix.q_end + p);
-                uint32_t win_q = 0, win_end = 0, nprop = 0, n_best = 0;
+                const uint32_t m = ip.child_count;
+                const uint32_t p_end = ip.q_end;
+                uint32_t win_q = 0, nprop = 0, n_best = 0;
                 int32_t win_one = 0, win_rest = 0;
+                QInfo iw{0, 0, 0, 0};
                 if (m <= 2) {
                     // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
-                    const uint32_t bnd = m ? __ldg(ix.q_end + p + 1) : p_end;
+                    const QInfo i1 = m ? ld_qinfo(ix.qinfo, p + 1) : QInfo{p_end, 0, 0, 0};
+                    const uint32_t bnd = i1.q_end;
                     uint32_t c1 = 0, c2 = 0, both = 0;
                     for (uint32_t j = lane; j < D; j += 32) {
                         const uint32_t w = t1[2 * j + 1];
                         if (w == 0) continue;
-                        uint32_t lo = t1[2 * j];
+                        uint32_t lo = t1[2 * j], first = t2k[j];
                         const uint32_t hi = lst[j];
-                        uint32_t first = __ldg(ix.terms + lo);
-                        if (first == p) { ++lo; first = lo < hi ? __ldg(ix.terms + lo) : 0u; }
+                        if (first == p) {  // the set ends at p itself for some tip: not a vote for any child
+                            ++lo;
+                            first = lo < hi ? __ldg(ix.terms + lo) : 0xFFFFFFFFu;
+                            t1[2 * j] = lo; t2k[j] = first;
+                        }
                         if (lo < hi) {
-                            const bool in1 = first < bnd, in2 = __ldg(ix.terms + hi - 1) >= bnd;
+                            const bool in1 = first < bnd, in2 = t2c[j] >= bnd;
                             c1 += in1 ? w : 0u; c2 += in2 ? w : 0u; both += (in1 && in2) ? w : 0u;
                         }
                     }
@@ -477,8 +558,8 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
                         const int32_t d1 = one1 - rest1, d2 = one2 - rest2;
                         if (d1 == d2) n_best = 2; else pick2 = d2 > d1;
                     }
-                    if (pick2) { win_q = bnd; win_end = p_end; win_one = one2; win_rest = rest2; }
-                    else { win_q = p + 1; win_end = bnd; win_one = one1; win_rest = rest1; }
+                    if (pick2) { win_q = bnd; win_one = one2; win_rest = rest2; if (nprop) iw = ld_qinfo(ix.qinfo, bnd); }
+                    else { win_q = p + 1; win_one = one1; win_rest = rest1; iw = i1; }
                 } else {
                     // general fan-out: per-set merge walk of the terminal range against the child
                     // intervals, votes in shared-memory counters
@@ -488,11 +569,11 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
                         if (w == 0) continue;
                         uint32_t pos = t1[2 * j];
                         const uint32_t hi = lst[j];
-                        if (__ldg(ix.terms + pos) == p) ++pos;
-                        uint32_t npres = 0, last = 0, ord = 0, cend = __ldg(ix.q_end + p + 1);
+                        if (t2k[j] == p) ++pos;
+                        uint32_t npres = 0, last = 0, ord = 0, cend = __ldg(&ix.qinfo[p + 1].q_end);
                         while (pos < hi) {
                             const uint32_t t = __ldg(ix.terms + pos);
-                            while (t >= cend) { cend = __ldg(ix.q_end + cend); ++ord; }
+                            while (t >= cend) { cend = __ldg(&ix.qinfo[cend].q_end); ++ord; }
                             atomicAdd(&cnt[ord], w); ++npres; last = ord;
                             ++pos;
                             if (pos < hi && __ldg(ix.terms + pos) < cend) pos = lower_bound_terms(ix.terms, pos, hi, cend);
@@ -508,8 +589,8 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
                     __syncwarp();
                     nprop = dc.nprop; n_best = dc.n_best; win_one = dc.best_one; win_rest = dc.best_rest;
                     win_q = p + 1;
-                    for (uint32_t o = 0; o < dc.best_ord; ++o) win_q = __ldg(ix.q_end + win_q);
-                    win_end = __ldg(ix.q_end + win_q);
+                    for (uint32_t o = 0; o < dc.best_ord; ++o) win_q = __ldg(&ix.qinfo[win_q].q_end);
+                    iw = ld_qinfo(ix.qinfo, win_q);
                 }
                 if (nprop == 0) {
                     if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
@@ -517,19 +598,29 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
                     break;
                 }
                 if (n_best != 1) { res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p]; break; }
-                if (ix.qnodes[win_q].child_count == 0) {  // update_introspection_node.rs:32-87
+                if (iw.child_count == 0) {  // update_introspection_node.rs:32-87
                     res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[win_q];
                     res.one = win_one; res.rest = win_rest;
                     break;
                 }
-                p = win_q;
+                p = win_q; ip = iw; depth_p++;
+                const uint32_t win_end = iw.q_end;
                 // every live set keeps its terminals inside the winner's interval (or drops out)
                 for (uint32_t j = lane; j < D; j += 32) {
                     if (t1[2 * j + 1] == 0) continue;
-                    uint32_t lo = t1[2 * j], hi = lst[j];
-                    if (__ldg(ix.terms + lo) < win_q) lo = lower_bound_terms(ix.terms, lo + 1, hi, win_q);
-                    if (lo < hi && __ldg(ix.terms + hi - 1) >= win_end) hi = lower_bound_terms(ix.terms, lo, hi - 1, win_end);
-                    if (lo < hi) { t1[2 * j] = lo; lst[j] = hi; } else t1[2 * j + 1] = 0;
+                    uint32_t lo = t1[2 * j], hi = lst[j], first = t2k[j], last = t2c[j];
+                    bool live = lo < hi && last >= win_q && first < win_end;
+                    if (live && first < win_q) {
+                        lo = lower_bound_terms(ix.terms, lo + 1, hi, win_q);
+                        first = __ldg(ix.terms + lo);  // lo < hi because last >= win_q
+                        live = first < win_end;
+                        t1[2 * j] = lo; t2k[j] = first;
+                    }
+                    if (live && last >= win_end) {
+                        hi = lower_bound_terms(ix.terms, lo + 1, hi - 1, win_end);  // terms[lo] < win_end
+                        lst[j] = hi; t2c[j] = __ldg(ix.terms + hi - 1);
+                    }
+                    if (!live) t1[2 * j + 1] = 0;
                 }
                 __syncwarp();
             }
@@ -632,7 +723,9 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
     if (per_warp * warps > 226 * 1024) return cudaErrorInvalidConfiguration;
     const size_t smem = per_warp * warps;
-    cudaError_t e = cudaFuncSetAttribute(place_kernel<K, CLOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // always the same (maximal) opt-in size: concurrent callers with different geometries must not
+    // lower each other's limit between this call and the launch
+    cudaError_t e = cudaFuncSetAttribute(place_kernel<K, CLOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, place_kernel<K, CLOSED>, warps * 32, smem);
@@ -664,11 +757,11 @@ cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, u
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e;
     if (k == 35) {
-        e = cudaFuncSetAttribute(hash_only_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(hash_only_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         hash_only_kernel<35><<<1, 64, smem, stream>>>(packed, len, k, out, str_words, pk_words);
     } else {
-        e = cudaFuncSetAttribute(hash_only_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(hash_only_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         hash_only_kernel<0><<<1, 64, smem, stream>>>(packed, len, k, out, str_words, pk_words);
     }

@@ -1,33 +1,67 @@
 // Device-side MurmurHash3_x64_128 (first 64-bit half, seed 0) over the ASCII bytes of one k-mer
 // window: the function the reference calls for every window through
 // `mur3::murmurhash3_x64_128(kmer.as_bytes(), 0).0` (core/src/domain/dtos/kmers_map.rs:157-159,
-// :414-421).  The hash is NOT a rolling hash: every window is hashed independently, so the
-// work per k-mer is 2 sixteen-byte blocks + a 3-byte tail + two fmix64 at k = 35
-// (14 64-bit multiplies).  Integer-only; no tensor cores apply.
+// :414-421).  The hash is NOT a rolling hash: every window is hashed independently.
+// Integer-only; no tensor cores apply.  64-bit values live in register pairs; multiplies by the
+// murmur constants are spelled out as one IMAD.WIDE + two IMAD, rotates as two funnel shifts.
 #pragma once
 #include <cstdint>
 
 namespace cls {
 
-__device__ __forceinline__ uint64_t rotl64_d(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
-
-__device__ __forceinline__ uint64_t fmix64_d(uint64_t k) {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdULL;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ULL;
-    k ^= k >> 33;
-    return k;
-}
-
 constexpr uint64_t kC1 = 0x87c37b91114253d5ULL;
 constexpr uint64_t kC2 = 0x4cf5ad432745937fULL;
 
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// x * C (mod 2^64) for a compile-time constant C
+template <uint64_t C>
+__device__ __forceinline__ uint64_t mulc(uint64_t x) {
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    const uint64_t r = (uint64_t)lo * (uint32_t)C;
+    const uint32_t rh = (uint32_t)(r >> 32) + lo * (uint32_t)(C >> 32) + hi * (uint32_t)C;
+    return pack64((uint32_t)r, rh);
+}
+
+// rotate left by a compile-time amount
+template <int R>
+__device__ __forceinline__ uint64_t rotlc(uint64_t x) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if constexpr (R >= 32) { const uint32_t t = lo; lo = hi; hi = t; }
+    constexpr int S = R & 31;
+    if constexpr (S == 0) return pack64(lo, hi);
+    return pack64(__funnelshift_l(hi, lo, S), __funnelshift_l(lo, hi, S));
+}
+
+// x * 5 + c
+__device__ __forceinline__ uint64_t mul5add(uint64_t x, uint32_t c) {
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    const uint64_t r = (uint64_t)lo * 5u + c;
+    return pack64((uint32_t)r, (uint32_t)(r >> 32) + hi * 5u);
+}
+
+__device__ __forceinline__ uint64_t xorshift33(uint64_t k) {
+    const uint32_t hi = (uint32_t)(k >> 32);
+    return pack64((uint32_t)k ^ (hi >> 1), hi);
+}
+
+__device__ __forceinline__ uint64_t fmix64_d(uint64_t k) {
+    k = xorshift33(k);
+    k = mulc<0xff51afd7ed558ccdULL>(k);
+    k = xorshift33(k);
+    k = mulc<0xc4ceb9fe1a85ec53ULL>(k);
+    return xorshift33(k);
+}
+
+// pre-mix of one 8-byte word in the k1 / k2 lane of a block
+__device__ __forceinline__ uint64_t premix_k1(uint64_t w) { return mulc<kC2>(rotlc<31>(mulc<kC1>(w))); }
+__device__ __forceinline__ uint64_t premix_k2(uint64_t w) { return mulc<kC1>(rotlc<33>(mulc<kC2>(w))); }
+
 __device__ __forceinline__ void mm_block(uint64_t &h1, uint64_t &h2, uint64_t k1, uint64_t k2) {
-    k1 *= kC1; k1 = rotl64_d(k1, 31); k1 *= kC2; h1 ^= k1;
-    h1 = rotl64_d(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-    k2 *= kC2; k2 = rotl64_d(k2, 33); k2 *= kC1; h2 ^= k2;
-    h2 = rotl64_d(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    h1 ^= premix_k1(k1);
+    h1 = mul5add(rotlc<27>(h1) + h2, 0x52dce729u);
+    h2 ^= premix_k2(k2);
+    h2 = mul5add(rotlc<31>(h2) + h1, 0x38495ab5u);
 }
 
 __device__ __forceinline__ uint64_t mm_finish(uint64_t h1, uint64_t h2, uint64_t len) {
@@ -37,47 +71,7 @@ __device__ __forceinline__ uint64_t mm_finish(uint64_t h1, uint64_t h2, uint64_t
     return h1 + h2;
 }
 
-// Hash the K bytes that start at byte `pos` of a 4-byte aligned ASCII string held in shared
-// memory.  The string must be readable up to 4*((pos>>2) + (K+6)/4 + 1) bytes (padding is
-// never mixed into the hash).  K is a compile-time constant: all block/tail indexing unrolls.
-template <int K>
-__device__ __forceinline__ uint64_t murmur_window_smem(const uint32_t *s32, uint32_t pos) {
-    constexpr int NW = (K + 3) / 4;  // 32-bit words of window data
-    const uint32_t *p = s32 + (pos >> 2);
-    const uint32_t sh = (pos & 3u) * 8u;
-    uint32_t raw[NW + 1];
-#pragma unroll
-    for (int i = 0; i <= NW; ++i) raw[i] = p[i];
-    uint32_t w[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
-    uint64_t h1 = 0, h2 = 0;
-    constexpr int NB = K / 16;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        uint64_t k1 = (uint64_t)w[4 * b] | ((uint64_t)w[4 * b + 1] << 32);
-        uint64_t k2 = (uint64_t)w[4 * b + 2] | ((uint64_t)w[4 * b + 3] << 32);
-        mm_block(h1, h2, k1, k2);
-    }
-    constexpr int T = K & 15;
-    if constexpr (T > 8) {
-        constexpr int nb = T - 8;  // bytes of k2 (1..7)
-        uint64_t k2 = (uint64_t)w[4 * NB + 2];
-        if (nb > 4) k2 |= (uint64_t)w[(4 * NB + 3 < NW) ? 4 * NB + 3 : NW - 1] << 32;
-        k2 &= (nb >= 8) ? ~0ULL : ((1ULL << (8 * nb)) - 1);
-        k2 *= kC2; k2 = rotl64_d(k2, 33); k2 *= kC1; h2 ^= k2;
-    }
-    if constexpr (T > 0) {
-        constexpr int nb = T > 8 ? 8 : T;  // bytes of k1 (1..8)
-        uint64_t k1 = (uint64_t)w[4 * NB];
-        if (nb > 4) k1 |= (uint64_t)w[(4 * NB + 1 < NW) ? 4 * NB + 1 : NW - 1] << 32;
-        k1 &= (nb >= 8) ? ~0ULL : ((1ULL << (8 * nb)) - 1);
-        k1 *= kC1; k1 = rotl64_d(k1, 31); k1 *= kC2; h1 ^= k1;
-    }
-    return mm_finish(h1, h2, (uint64_t)K);
-}
-
-// Runtime-k variant (any k >= 1): byte-wise reads, slow but exact; used for k != 35.
+// Runtime-k variant (any k >= 1): byte-wise reads from a shared-memory ASCII string; used for k != 35.
 __device__ __forceinline__ uint64_t load_le_smem(const uint8_t *p, int n) {
     uint64_t v = 0;
     for (int i = 0; i < n; ++i) v |= (uint64_t)p[i] << (8 * i);
@@ -92,14 +86,8 @@ __device__ inline uint64_t murmur_window_generic(const uint8_t *s, uint32_t pos,
         mm_block(h1, h2, load_le_smem(d + 16 * b, 8), load_le_smem(d + 16 * b + 8, 8));
     const uint8_t *tail = d + 16 * nblocks;
     const int t = (int)(k & 15u);
-    if (t > 8) {
-        uint64_t k2 = load_le_smem(tail + 8, t - 8);
-        k2 *= kC2; k2 = rotl64_d(k2, 33); k2 *= kC1; h2 ^= k2;
-    }
-    if (t > 0) {
-        uint64_t k1 = load_le_smem(tail, t > 8 ? 8 : t);
-        k1 *= kC1; k1 = rotl64_d(k1, 31); k1 *= kC2; h1 ^= k1;
-    }
+    if (t > 8) h2 ^= premix_k2(load_le_smem(tail + 8, t - 8));
+    if (t > 0) h1 ^= premix_k1(load_le_smem(tail, t > 8 ? 8 : t));
     return mm_finish(h1, h2, (uint64_t)k);
 }
 
