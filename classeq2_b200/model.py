@@ -66,8 +66,11 @@ class Clade:
     @staticmethod
     def from_obj(o: dict) -> "Clade":
         ch = o.get("children")
+        # support / length are Option<f64> (clade.rs:27-34); YAML 1.1 loaders hand "1e-6" over as a string
+        f64 = lambda v: None if v is None else float(v)  # noqa: E731
         return Clade(id=int(o["id"]), parent=None if o.get("parent") is None else int(o["parent"]),
-                     kind=str(o["kind"]), name=o.get("name"), support=o.get("support"), length=o.get("length"),
+                     kind=str(o["kind"]), name=None if o.get("name") is None else str(o["name"]),
+                     support=f64(o.get("support")), length=f64(o.get("length")),
                      children=None if ch is None else [Clade.from_obj(c) for c in ch])
 
 
