@@ -68,10 +68,10 @@ struct WarpMem {
 
 // Decode one read into the two ASCII strands and the two packed strands.
 __device__ __forceinline__ void decode_read(const uint32_t *__restrict__ packed, uint32_t len, const WarpMem &m,
-                                            uint32_t pk_words) {
+                                            uint32_t pk_words, uint32_t tid = threadIdx.x & 31u, uint32_t nthreads = 32u) {
     const uint32_t nw = (len + 15u) >> 4;
     const uint32_t pad = nw * 16u - len;  // unused base slots at the top of the last word
-    for (uint32_t t = lane_id(); t < pk_words; t += 32) {
+    for (uint32_t t = tid; t < pk_words; t += nthreads) {
         uint32_t f = 0, r = 0;
         if (t < nw) {
             f = __ldg(packed + t);
@@ -134,11 +134,14 @@ struct WindowHasher {
 
     __device__ __forceinline__ uint32_t n_chunks() const { return (W + 31u) >> 5; }
 
-    __device__ __forceinline__ void begin_strand(uint32_t strand) {
+    // start hashing a strand at chunk `first_chunk` (chunks are then taken consecutively)
+    __device__ __forceinline__ void begin_strand(uint32_t strand, uint32_t first_chunk = 0) {
         s32 = strand ? m.str_r : m.str_f;
         pk = strand ? m.pk_r : m.pk_f;
         if constexpr (K == 35) {
-            if (lane < W + 24u) premix_to_ring(m, s32, lane);  // offsets 0 .. W+23 carry a needed pre-mix
+            __syncwarp();
+            const uint32_t q = 32u * first_chunk + lane;
+            if (q < W + 24u) premix_to_ring(m, s32, q);  // offsets 0 .. W+23 carry a needed pre-mix
         }
     }
 
@@ -276,10 +279,13 @@ __global__ void hash_only_kernel(const uint32_t *__restrict__ packed, uint32_t l
 }
 
 // ------------------------------------------------------------------------------------------
-// The placement kernel: one warp per query, persistent CTAs striding over the query range.
+// The placement kernel, persistent CTAs striding over the query range.
+//   CTA == false: one WARP per query (short reads: the per-query tables are a few KB)
+//   CTA == true : one CTA per query (kb-scale reads): all warps hash / probe / de-duplicate
+//                 contiguous chunk ranges of the read into one set of shared tables, warp 0 walks the tree
 // ------------------------------------------------------------------------------------------
-template <int K, bool CLOSED>
-__global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlaceParams pp,
+template <int K, bool CLOSED, bool CTA>
+__global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix, PlaceParams pp,
                                                        const uint32_t *__restrict__ packed,
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                        uint32_t n_reads, ResultRec *__restrict__ results,
@@ -290,11 +296,15 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t warps_per_cta = blockDim.x >> 5;
-    uint32_t *wbase = smem + (size_t)warp * g.words_per_warp;
+    // layout: [rings of all warps][tables + strings of group 0][... of group 1] ...; a group is one
+    // warp (CTA == false) or the whole CTA (CTA == true)
+    uint32_t *gbase = smem + 4 * kRing * warps_per_cta + (CTA ? (size_t)0 : (size_t)warp * g.words_per_warp);
     WarpMem wm;
-    wm.ring_a = reinterpret_cast<uint64_t *>(wbase);
+    wm.ring_a = reinterpret_cast<uint64_t *>(smem + 4 * kRing * warp);
     wm.ring_b = wm.ring_a + kRing;
-    uint32_t *t1 = wbase + 4 * kRing;    // dedup set keyed by table slot; later the live-set list
+    const uint32_t gtid = CTA ? threadIdx.x : lane, gthreads = CTA ? blockDim.x : 32u;
+    auto group_sync = [] { if constexpr (CTA) __syncthreads(); else __syncwarp(); };
+    uint32_t *t1 = gbase;                // dedup set keyed by table slot; later the live-set list
     uint32_t *t2k = t1 + g.t1_size;      // histogram keys: node-set record offsets; later `first`
     uint32_t *t2c = t2k + g.t2_size;     // histogram counts; later `last`
     uint32_t *lst = t2c + g.t2_size;     // histogram positions of the distinct sets; later `hi`
@@ -305,17 +315,18 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
     uint32_t *cnt = wm.pk_r + g.pk_words;  // vote counters, one per non-leaf child ordinal
     uint32_t *excl = cnt + g.fan_cap;
     uint32_t *n_sets_smem = excl + g.fan_cap;
+    uint32_t *n_matched_smem = n_sets_smem + 1;
     const uint32_t t1_mask = g.t1_size - 1u, t2_mask = g.t2_size - 1u;
     const uint32_t t2_shift = 32u - g.t2_log2;
     const uint32_t k = ix.k_size;
     const uint32_t code_mask = ix.m_eff >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ix.m_eff)) - 1u);
     const bool ri = pp.remove_intersection != 0;
 
-    for (uint32_t o = lane; o < g.fan_cap; o += 32) { cnt[o] = 0; excl[o] = 0; }
+    for (uint32_t o = gtid; o < g.fan_cap; o += gthreads) { cnt[o] = 0; excl[o] = 0; }
     __syncthreads();
 
-    const uint32_t gwarp = blockIdx.x * warps_per_cta + warp;
-    const uint32_t gstride = gridDim.x * warps_per_cta;
+    const uint32_t gwarp = CTA ? blockIdx.x : blockIdx.x * warps_per_cta + warp;
+    const uint32_t gstride = CTA ? gridDim.x : gridDim.x * warps_per_cta;
 #pragma unroll 1
     for (uint32_t r = gwarp; r < n_reads; r += gstride) {
         const ReadDesc rd = reads[first_read + r];
@@ -326,13 +337,13 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
         {
             uint4 *z = reinterpret_cast<uint4 *>(t1);
             const uint32_t n4 = (g.t1_size + g.t2_size) >> 2;  // t1 and t2k are contiguous: all kEmpty
-            for (uint32_t i = lane; i < n4; i += 32) z[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            for (uint32_t i = gtid; i < n4; i += gthreads) z[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
             uint4 *zc = reinterpret_cast<uint4 *>(t2c);
-            for (uint32_t i = lane; i < (g.t2_size >> 2); i += 32) zc[i] = make_uint4(0, 0, 0, 0);
-            if (lane == 0) *n_sets_smem = 0;
+            for (uint32_t i = gtid; i < (g.t2_size >> 2); i += gthreads) zc[i] = make_uint4(0, 0, 0, 0);
+            if (gtid == 0) { *n_sets_smem = 0; *n_matched_smem = 0; }
         }
-        decode_read(packed + rd.word_off, L, wm, g.pk_words);
-        __syncwarp();
+        decode_read(packed + rd.word_off, L, wm, g.pk_words, gtid, gthreads);
+        group_sync();
 
         // ---- hash + probe + dedup + histogram, software pipelined: the bucket of pass i is in
         //      flight while pass i+1 is hashed and pass i-1 is consumed ---------------------------
@@ -391,44 +402,28 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
         {
             WindowHasher<K> wh(wm, tail_lut, L, k);
             const uint32_t n_chunks = wh.n_chunks();
-            // passes t = 0 .. 2 * n_chunks - 1 (forward chunks, then reverse-complement chunks), taken two
-            // at a time with ping-pong register sets A / B so that no loaded value is copied (a copy
-            // would wait for the load and undo the pipelining)
-            auto hash_and_issue = [&](uint32_t t, bool &valid, bool &rc, uint32_t &pos, uint64_t &h, uint64_t &q0,
-                                      uint64_t &qm0, uint64_t &q1, uint64_t &qm1) {
-                rc = t >= n_chunks;
-                const uint32_t c = rc ? t - n_chunks : t;
-                if (c == 0) wh.begin_strand(rc ? 1u : 0u);
-                valid = wh.pass(c, pos, h);
-                if (valid) ld_bucket(ix.table, h & ix.bucket_mask, q0, qm0, q1, qm1);
-            };
-            [[maybe_unused]] bool av = false, arc = false, bv = false, brc = false;
-            [[maybe_unused]] uint32_t apos = 0, bpos = 0;
-            [[maybe_unused]] uint64_t ah = 0, a0 = 0, am0 = 0, a1 = 0, am1 = 0, bh = 0, b0 = 0, bm0 = 0, b1 = 0, bm1 = 0;
-#if CLS_PIPELINE == 2
+            // this warp's contiguous chunk range [c_lo, c_hi) of each strand (the whole strand when a
+            // warp owns the read)
+            const uint32_t per = CTA ? (n_chunks + warps_per_cta - 1) / warps_per_cta : n_chunks;
+            const uint32_t c_lo = CTA ? min(warp * per, n_chunks) : 0u, c_hi = CTA ? min(c_lo + per, n_chunks) : n_chunks;
 #pragma unroll 1
-            for (uint32_t t = 0; t < 2 * n_chunks; t += 2) {
-                hash_and_issue(t, av, arc, apos, ah, a0, am0, a1, am1);
-                n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
-                hash_and_issue(t + 1, bv, brc, bpos, bh, b0, bm0, b1, bm1);
-                n_matched += consume(av, arc, apos, ah, a0, am0, a1, am1);
-            }
-            n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
-#elif CLS_PIPELINE == 1
+            for (uint32_t strand = 0; strand < 2 && c_lo < c_hi; ++strand) {
+                wh.begin_strand(strand, c_lo);
 #pragma unroll 1
-            for (uint32_t t = 0; t < 2 * n_chunks; ++t) {
-                hash_and_issue(t, av, arc, apos, ah, a0, am0, a1, am1);
-                n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
-                bv = av; brc = arc; bpos = apos; bh = ah; b0 = a0; bm0 = am0; b1 = a1; bm1 = am1;
+                for (uint32_t c = c_lo; c < c_hi; ++c) {
+                    uint32_t pos;
+                    uint64_t h = 0, q0 = 0, qm0 = 0, q1 = 0, qm1 = 0;
+                    const bool valid = wh.pass(c, pos, h);
+                    if (valid) ld_bucket(ix.table, h & ix.bucket_mask, q0, qm0, q1, qm1);
+                    n_matched += consume(valid, strand != 0, pos, h, q0, qm0, q1, qm1);
+                }
             }
-            n_matched += consume(bv, brc, bpos, bh, b0, bm0, b1, bm1);
-#else
-#pragma unroll 1
-            for (uint32_t t = 0; t < 2 * n_chunks; ++t) {
-                hash_and_issue(t, av, arc, apos, ah, a0, am0, a1, am1);
-                n_matched += consume(av, arc, apos, ah, a0, am0, a1, am1);
-            }
-#endif
+        }
+        if constexpr (CTA) {
+            if (lane == 0 && n_matched) atomicAdd(n_matched_smem, n_matched);
+            __syncthreads();
+            n_matched = *n_matched_smem;
+            if (warp != 0) { __syncthreads(); continue; }   // warp 0 finishes the read; see the barrier at the end
         }
         __syncwarp();
         const uint32_t D = *n_sets_smem;
@@ -687,6 +682,7 @@ __global__ void __launch_bounds__(256, 4) place_kernel(DeviceIndex ix, PlacePara
         res.iterations = (uint32_t)iteration;
         if (lane == 0) results[first_read + r] = res;
         __syncwarp();
+        if constexpr (CTA) __syncthreads();   // the tables are free again for the next read
     }
 }
 
@@ -709,45 +705,60 @@ PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout) {
     g.t1_size = 1u << g.t1_log2;
     g.t2_size = 1u << g.t2_log2;
     g.fan_cap = max_fanout < 1 ? 1 : max_fanout;
-    g.words_per_warp = 4 * kRing + g.t1_size + 3 * g.t2_size + 2 * g.str_words + 2 * g.pk_words + 2 * g.fan_cap + 1;
+    // tables + strings of one group (a warp or a CTA); the pre-mix rings (4 * kRing words per warp) come on top
+    g.words_per_warp = g.t1_size + 3 * g.t2_size + 2 * g.str_words + 2 * g.pk_words + 2 * g.fan_cap + 2;
     g.words_per_warp = (g.words_per_warp + 3u) & ~3u;
+    g.cta_per_read = (size_t)(g.words_per_warp + 4 * kRing) * 4 > 12 * 1024 ? 1u : 0u;  // reads beyond ~300 bp
     return g;
 }
 
-template <int K, bool CLOSED>
+template <int K, bool CLOSED, bool CTA>
 static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                                   const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
                                   ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream) {
-    const size_t per_warp = (size_t)g.words_per_warp * 4;
+    const size_t ring = (size_t)4 * kRing * 4, group = (size_t)g.words_per_warp * 4;
     int warps = 8;
-    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-    if (per_warp * warps > 226 * 1024) return cudaErrorInvalidConfiguration;
-    const size_t smem = per_warp * warps;
+    size_t smem;
+    if (CTA) {
+        smem = group + ring * warps;
+    } else {
+        while (warps > 1 && (group + ring) * warps > 200 * 1024) warps >>= 1;
+        smem = (group + ring) * warps;
+    }
+    if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
     // always the same (maximal) opt-in size: concurrent callers with different geometries must not
     // lower each other's limit between this call and the launch
-    cudaError_t e = cudaFuncSetAttribute(place_kernel<K, CLOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(place_kernel<K, CLOSED, CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, place_kernel<K, CLOSED>, warps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, place_kernel<K, CLOSED, CTA>, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)(sm_count * occ);
-    const uint32_t need = (n_reads + warps - 1) / warps;
+    const uint32_t need = CTA ? n_reads : (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid == 0) return cudaSuccess;
-    place_kernel<K, CLOSED><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g);
+    place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g);
     return cudaGetLastError();
+}
+
+template <int K, bool CLOSED>
+static cudaError_t launch_place_m(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
+                                  const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
+                                  ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream) {
+    return g.cta_per_read ? launch_place_t<K, CLOSED, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
+                          : launch_place_t<K, CLOSED, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
 }
 
 cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                          const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
                          const PlaceGeom &g, int sm_count, cudaStream_t stream) {
     if (ix.k_size == 35) {
-        return ix.closed ? launch_place_t<35, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
-                         : launch_place_t<35, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+        return ix.closed ? launch_place_m<35, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
+                         : launch_place_m<35, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
     }
-    return ix.closed ? launch_place_t<0, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
-                     : launch_place_t<0, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+    return ix.closed ? launch_place_m<0, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
+                     : launch_place_m<0, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
 }
 
 cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, uint64_t *out, cudaStream_t stream) {

@@ -28,7 +28,8 @@ struct PlaceGeom {
     uint32_t t1_size, t1_log2;  // hit de-duplication set (u32 slots), power of two >= 2 * max hits
     uint32_t t2_size, t2_log2;  // node-set histogram (keys + counts), power of two > max hits
     uint32_t fan_cap;         // vote counters per warp (max non-leaf fan-out of the tree)
-    uint32_t words_per_warp;
+    uint32_t words_per_warp;  // tables + strings of one group (warp or CTA), without the pre-mix rings
+    uint32_t cta_per_read;    // 1: one CTA per read (long reads), 0: one warp per read
 };
 
 PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout);

@@ -353,3 +353,28 @@ def oracle_tree_from_flat(oracle, flat):
     for b, h, s in zip(flat.entry_bucket.tolist(), flat.entry_hash.tolist(), flat.entry_set.tolist()):
         km.map.setdefault(b, {})[h] = set(sn[int(so[s]):int(so[s + 1])].tolist())
     return O.Tree("s", "s", 70.0, clades[0], kmers_map=km)
+
+
+# ---- kb-scale reads: one CTA per read (all warps share one set of tables) --------------------------
+@pytest.mark.parametrize("general", [False, True])
+def test_long_reads_cta_mode(cq, general):
+    from classeq2_b200 import synth
+    from oracle import cpp_oracle
+    sm = synth.make_model(48, 1600, 9090)
+    lens = np.concatenate([synth.skewed_lengths(300, 77), np.array([35, 36, 299, 300, 301, 512, 1024, 1600, 1600])])
+    bases, offsets, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, len(lens), lens, 9092)
+    md = cpp_oracle.CppModel.from_flat(sm.flat)
+    ix = cq.Index(sm.flat.with_general_sets() if general else sm.flat, device=0)
+    for kn in (dict(), dict(remove_intersection=True), dict(min_match_coverage=0.0, max_iterations=2)):
+        want = md.place_batch(bases, offsets, kn.get("max_iterations"), kn.get("min_match_coverage"), kn.get("remove_intersection"))
+        got = ix.place_batch((bases, offsets), cq.PlaceParams(**kn))
+        for f in ("status", "node_id", "one", "rest", "n_query_kmers", "n_matched", "n_root_matched"):
+            bad = np.flatnonzero(getattr(got, f) != want[f])
+            assert bad.size == 0, (f, kn, bad[:5], getattr(got, f)[bad[:5]], want[f][bad[:5]], lens[bad[:5]])
+    # low-complexity reads: every window repeats (distinct-hash semantics across warps of the CTA)
+    rep = ["ACGT" * 400, "A" * 1200, ("ACGTTGCA" * 200)[:1550]]
+    b2, o2 = cq.make_batch(rep)
+    want = md.place_batch(b2, o2)
+    got = ix.place_batch((b2, o2))
+    assert got.status.tolist() == want["status"].tolist() and got.n_matched.tolist() == want["n_matched"].tolist()
+    ix.close(), md.close()
