@@ -96,6 +96,7 @@ PROTOTYPES = {
     "cls_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "cls_debug_kmer_hashes": (C.c_int, [C.c_int, C.c_uint32, u8p, C.c_uint64, u64p, C.c_uint64, u64p]),
     "cls_debug_host_murmur3_x64_128_h1": (C.c_uint64, [u8p, C.c_uint64, C.c_uint64]),
+    "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),
     "cls_filter_sequence": (C.c_uint64, [u8p, C.c_uint64, u8p, C.c_uint64]),
     "cls_model_build": (C.c_int, [C.POINTER(ModelView), C.c_uint64, u64p, u8p, u64p, C.POINTER(C.c_void_p)]),
     "cls_built_model_view": (C.c_int, [C.c_void_p, C.POINTER(ModelView), C.POINTER(ModelView)]),

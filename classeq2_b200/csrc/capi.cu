@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -17,6 +18,8 @@
 #include "../../include/classeq_b200.h"
 #include "device_types.hpp"
 #include "index_build.hpp"
+#include "host_pack.hpp"
+#include "host_pool.hpp"
 #include "kernels.hpp"
 #include "murmur3_host.hpp"
 
@@ -92,14 +95,18 @@ struct PackedLayout {
     std::vector<uint32_t> perm;  // device order -> caller index
     std::vector<uint8_t> pre_status;  // caller index -> status decided on the host, or 0xFF
     std::vector<uint32_t> lens;       // caller index -> query length (for n_query_kmers)
+    std::vector<uint8_t> cls_id;      // caller index -> length class (scratch of plan_batch)
+    std::vector<uint32_t> word_off;   // device order -> first packed word (+ one past the end)
     std::vector<LengthClass> classes;
 };
 
 struct Workspace {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> chunk_ev;  // 4 per chunk: start, kernel start, kernel end, done
     PinBuf h_words, h_descs, h_results;
     DevBuf d_words, d_descs, d_results;
+    PackedLayout lay;                   // reused across calls
     bool in_use = false;
 };
 
@@ -125,129 +132,83 @@ struct cls_resident_batch {
 
 namespace {
 
-// ---- 2-bit packing ---------------------------------------------------------------------------
-// code = (ascii >> 1) & 3 -> A=0 C=1 T=2 G=3, case-insensitive.  Returns false on a non-ACGT byte.
-inline bool pack8(uint64_t x, uint32_t &out16) {
-    const uint64_t ones = 0x0101010101010101ULL, low7 = 0x7F7F7F7F7F7F7F7FULL;
-    const uint64_t y = x & 0xDFDFDFDFDFDFDFDFULL;  // upper-case
-    auto nonzero = [&](uint64_t z) { return (((z & low7) + low7) | z) & 0x8080808080808080ULL; };
-    const uint64_t bad = nonzero(y ^ (ones * 0x41)) & nonzero(y ^ (ones * 0x43)) &
-                         nonzero(y ^ (ones * 0x47)) & nonzero(y ^ (ones * 0x54));
-    uint64_t c = (x >> 1) & 0x0303030303030303ULL;
-    c = (c | (c >> 6)) & 0x000F000F000F000FULL;
-    c = (c | (c >> 12)) & 0x000000FF000000FFULL;
-    c = (c | (c >> 24)) & 0xFFFFULL;
-    out16 = (uint32_t)c;
-    return bad == 0;
-}
-
-inline bool pack_read(const uint8_t *s, uint32_t len, uint32_t *dst) {
-    bool ok = true;
-    uint32_t i = 0, w = 0;
-    for (; i + 16 <= len; i += 16, ++w) {
-        uint64_t a, b;
-        std::memcpy(&a, s + i, 8);
-        std::memcpy(&b, s + i + 8, 8);
-        uint32_t lo, hi;
-        ok &= pack8(a, lo);
-        ok &= pack8(b, hi);
-        dst[w] = lo | (hi << 16);
-    }
-    if (i < len) {
-        uint32_t v = 0;
-        for (uint32_t j = 0; i + j < len; ++j) {
-            const uint8_t ch = s[i + j], u = ch & 0xDF;
-            ok &= (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
-            v |= ((uint32_t)(ch >> 1) & 3u) << (2 * j);
-        }
-        dst[w] = v;
-    }
-    return ok;
-}
-
-int host_threads() {
-    unsigned hc = std::thread::hardware_concurrency();
-    if (hc == 0) hc = 4;
-    return (int)std::min(hc, 32u);
-}
-
-template <class F>
-void parallel_for(uint64_t n, uint64_t grain, F f) {
-    int nt = (int)std::min<uint64_t>((uint64_t)host_threads(), (n + grain - 1) / std::max<uint64_t>(grain, 1));
-    if (nt <= 1) { f(0, n); return; }
-    std::vector<std::thread> th;
-    const uint64_t chunk = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t) {
-        uint64_t a = t * chunk, b = std::min(n, a + chunk);
-        if (a >= b) break;
-        th.emplace_back([=] { f(a, b); });
-    }
-    for (auto &x : th) x.join();
-}
-
-// Decide host-side statuses, order the surviving queries by decreasing length (so that every
-// launch works on one length class and long reads start first), and compute the packed layout.
+// Decide host-side statuses, group the surviving queries into LENGTH CLASSES (all reads of a class
+// share one per-read table geometry; longest class first so that long reads start first; input
+// order is kept inside a class), and compute the packed layout.
 int plan_batch(const cls_batch *batch, uint32_t k, uint32_t max_fanout, PackedLayout &lay,
                std::vector<uint32_t> &word_off) {
     const uint64_t n = batch->n_queries;
     if (n >= 0xFFFFFFFFull) return fail(CLS_ERR_INVALID_ARGUMENT, "more than 2^32-1 queries in one batch");
     if (n && (!batch->offsets || (batch->offsets[n] && !batch->bases)))
         return fail(CLS_ERR_INVALID_ARGUMENT, "batch arrays are NULL");
-    lay = PackedLayout();
+    lay.classes.clear();               // buffers are reused from call to call (no fresh pages)
     lay.n_queries = n;
+    lay.n_device = 0;
+    lay.n_words = 0;
     lay.pre_status.assign(n, 0xFF);
     lay.lens.resize(n);
-    uint64_t max_len = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        if (batch->offsets[i] > batch->offsets[i + 1])
-            return fail(CLS_ERR_INVALID_ARGUMENT, "batch offsets are not non-decreasing");
-        const uint64_t len = batch->offsets[i + 1] - batch->offsets[i];
-        if (len >= (1ull << 31)) return fail(CLS_ERR_INVALID_ARGUMENT, "query longer than 2^31 bases");
-        lay.lens[i] = (uint32_t)len;
-        if (len < k) lay.pre_status[i] = CLS_STATUS_ERR_TOO_SHORT;  // kmers_map.rs:383-385, place_sequence.rs:98-102
-        else max_len = std::max(max_len, len);
-    }
-    // counting sort by length, longest first
-    std::vector<uint32_t> count(max_len + 2, 0);
-    for (uint64_t i = 0; i < n; ++i)
-        if (lay.pre_status[i] == 0xFF) count[batch->offsets[i + 1] - batch->offsets[i]]++;
-    std::vector<uint32_t> start(max_len + 2, 0);
-    uint32_t acc = 0;
-    for (uint64_t len = max_len + 1; len-- > 0;) { start[len] = acc; acc += count[len]; }
-    lay.n_device = acc;
-    lay.perm.resize(acc);
-    for (uint64_t i = 0; i < n; ++i)
-        if (lay.pre_status[i] == 0xFF) lay.perm[start[batch->offsets[i + 1] - batch->offsets[i]]++] = (uint32_t)i;
-    // word offsets + classes
-    word_off.resize((size_t)acc + 1);
-    uint64_t w = 0;
-    PlaceGeom cur{};
-    for (uint32_t j = 0; j < acc; ++j) {
-        const uint64_t i = lay.perm[j];
-        const uint32_t len = (uint32_t)(batch->offsets[i + 1] - batch->offsets[i]);
-        if (w >= 0xFFFFFFFFull) return fail(CLS_ERR_INVALID_ARGUMENT, "batch exceeds 2^32 packed words; split it");
-        word_off[j] = (uint32_t)w;
-        w += (len + 15) / 16;
-        PlaceGeom g = make_place_geom(len, k, max_fanout);
-        if (lay.classes.empty() || g.t1_size != cur.t1_size) {
-            // lengths are non-increasing: a new class starts when the table size drops; the class
-            // geometry is that of its first (longest) read
-            lay.classes.push_back(LengthClass{j, 0, len});
-            cur = g;
+    // class id = log2 of the de-duplication table size for that length (make_place_geom)
+    constexpr int kMaxClass = 40;
+    auto class_of = [k](uint64_t len) {
+        const uint64_t h2 = 4 * (len - k + 1);
+        int c = 6;
+        while ((1ull << c) < h2) ++c;
+        return c;
+    };
+    uint64_t count[kMaxClass] = {0}, words[kMaxClass] = {0}, maxlen[kMaxClass] = {0};
+    std::vector<uint8_t> &cls_id = lay.cls_id;
+    cls_id.resize(n);
+    std::atomic<bool> bad_offsets{false}, too_long{false};
+    parallel_for(n, 1 << 16, [&](uint64_t a, uint64_t b) {  // per-read lengths, statuses, classes
+        for (uint64_t i = a; i < b; ++i) {
+            if (batch->offsets[i] > batch->offsets[i + 1]) { bad_offsets = true; continue; }
+            const uint64_t len = batch->offsets[i + 1] - batch->offsets[i];
+            if (len >= (1ull << 31)) { too_long = true; continue; }
+            lay.lens[i] = (uint32_t)len;
+            if (len < k) { lay.pre_status[i] = CLS_STATUS_ERR_TOO_SHORT; cls_id[i] = 0xFF; }  // kmers_map.rs:383-385
+            else cls_id[i] = (uint8_t)class_of(len);
         }
-        lay.classes.back().count++;
+    });
+    if (bad_offsets) return fail(CLS_ERR_INVALID_ARGUMENT, "batch offsets are not non-decreasing");
+    if (too_long) return fail(CLS_ERR_INVALID_ARGUMENT, "query longer than 2^31 bases");
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t c = cls_id[i];
+        if (c == 0xFF) continue;
+        count[c]++;
+        words[c] += (lay.lens[i] + 15u) / 16u;
+        maxlen[c] = std::max<uint64_t>(maxlen[c], lay.lens[i]);
     }
-    word_off[acc] = (uint32_t)std::min<uint64_t>(w, 0xFFFFFFFFull);
+    uint64_t start[kMaxClass], wstart[kMaxClass], acc = 0, w = 0;
+    for (int c = kMaxClass - 1; c >= 0; --c) {
+        start[c] = acc; wstart[c] = w;
+        if (count[c]) lay.classes.push_back(LengthClass{(uint32_t)acc, (uint32_t)count[c], (uint32_t)maxlen[c]});
+        acc += count[c]; w += words[c];
+    }
+    if (w >= 0xFFFFFFFFull) return fail(CLS_ERR_INVALID_ARGUMENT, "batch exceeds 2^32 packed words; split it");
+    lay.n_device = (uint32_t)acc;
     lay.n_words = w;
+    lay.perm.resize(acc);
+    word_off.resize((size_t)acc + 1);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t c = cls_id[i];
+        if (c == 0xFF) continue;
+        const uint64_t j = start[c]++;
+        lay.perm[j] = (uint32_t)i;
+        word_off[j] = (uint32_t)wstart[c];
+        wstart[c] += (lay.lens[i] + 15u) / 16u;
+    }
+    word_off[acc] = (uint32_t)w;
+    (void)max_fanout;
     return CLS_OK;
 }
 
 // Pack the planned batch into `words`/`descs` (pinned).  Invalid bases demote the query to
 // CLS_STATUS_ERR_INVALID_BASE; it still occupies its device slot (the device result is ignored).
 void pack_batch(const cls_batch *batch, PackedLayout &lay, const std::vector<uint32_t> &word_off,
-                uint32_t *words, ReadDesc *descs) {
-    parallel_for(lay.n_device, 4096, [&](uint64_t a, uint64_t b) {
-        for (uint64_t j = a; j < b; ++j) {
+                uint32_t *words, ReadDesc *descs, uint64_t first = 0, uint64_t count = ~0ull) {
+    if (count == ~0ull) count = lay.n_device;
+    parallel_for(count, 4096, [&](uint64_t a0, uint64_t b0) {
+        for (uint64_t j = first + a0; j < first + b0; ++j) {
             const uint64_t i = lay.perm[j];
             const uint32_t len = (uint32_t)(batch->offsets[i + 1] - batch->offsets[i]);
             descs[j] = ReadDesc{word_off[j], len};
@@ -257,8 +218,7 @@ void pack_batch(const cls_batch *batch, PackedLayout &lay, const std::vector<uin
     });
 }
 
-int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *params, const uint32_t *d_words,
-                   const ReadDesc *d_descs, ResultRec *d_results, cudaStream_t stream, uint64_t *launches) {
+PlaceParams make_place_params(const cls_params *params) {
     PlaceParams pp;
     pp.max_iterations = params->max_iterations;
     pp.remove_intersection = params->remove_intersection ? 1u : 0u;
@@ -267,6 +227,12 @@ int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *par
     else if (cov > 1.0) cov = 1.0;
     else if (cov < 0.0) cov = 0.0;
     pp.min_match_coverage = cov;
+    return pp;
+}
+
+int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *params, const uint32_t *d_words,
+                   const ReadDesc *d_descs, ResultRec *d_results, cudaStream_t stream, uint64_t *launches) {
+    const PlaceParams pp = make_place_params(params);
     for (const LengthClass &c : lay.classes) {
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_results, g, ix->sm_count, stream);
@@ -278,9 +244,10 @@ int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *par
     return CLS_OK;
 }
 
-void scatter_results(const PackedLayout &lay, uint32_t k, const ResultRec *recs, cls_result *out) {
+// Fields decided on the host (n_query_kmers of every query; everything for queries that never
+// reach the device).
+void scatter_host_decided(const PackedLayout &lay, uint32_t k, cls_result *out) {
     const uint64_t n = lay.n_queries;
-    // host-decided statuses first
     parallel_for(n, 65536, [&](uint64_t a, uint64_t b) {
         for (uint64_t i = a; i < b; ++i) {
             const uint64_t len = lay.lens[i];
@@ -297,11 +264,25 @@ void scatter_results(const PackedLayout &lay, uint32_t k, const ResultRec *recs,
             }
         }
     });
-    parallel_for(lay.n_device, 65536, [&](uint64_t a, uint64_t b) {
-        for (uint64_t j = a; j < b; ++j) {
+}
+
+// Device result records [first, first + count) (device order) -> the caller's arrays (caller order).
+// Queries demoted on the host while packing (invalid base) keep their host status.
+void scatter_device_range(const PackedLayout &lay, const ResultRec *recs, cls_result *out, uint64_t first, uint64_t count) {
+    parallel_for(count, 65536, [&](uint64_t a, uint64_t b) {
+        for (uint64_t j = first + a; j < first + b; ++j) {
             const uint64_t i = lay.perm[j];
-            if (lay.pre_status[i] != 0xFF) continue;
             const ResultRec &r = recs[j];
+            if (lay.pre_status[i] != 0xFF) {
+                if (out->status) out->status[i] = lay.pre_status[i];
+                if (out->node_id) out->node_id[i] = 0;
+                if (out->one) out->one[i] = 0;
+                if (out->rest) out->rest[i] = 0;
+                if (out->n_matched) out->n_matched[i] = 0;
+                if (out->n_root_matched) out->n_root_matched[i] = 0;
+                if (out->iterations) out->iterations[i] = 0;
+                continue;
+            }
             if (out->status) out->status[i] = (uint8_t)r.status;
             if (out->node_id) out->node_id[i] = r.node_id;
             if (out->one) out->one[i] = r.one;
@@ -313,12 +294,18 @@ void scatter_results(const PackedLayout &lay, uint32_t k, const ResultRec *recs,
     });
 }
 
+void scatter_results(const PackedLayout &lay, uint32_t k, const ResultRec *recs, cls_result *out) {
+    scatter_host_decided(lay, k, out);
+    scatter_device_range(lay, recs, out, 0, lay.n_device);
+}
+
 Workspace *acquire_ws(cls_index *ix) {
     std::lock_guard<std::mutex> lk(ix->mu);
     for (auto &w : ix->pool)
         if (!w->in_use) { w->in_use = true; return w.get(); }
     auto w = std::make_unique<Workspace>();
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     for (auto &e : w->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
     w->in_use = true;
@@ -425,6 +412,8 @@ void cls_index_destroy(cls_index *ix) {
     cudaSetDevice(ix->device);
     for (auto &w : ix->pool) {
         if (w->stream) { cudaStreamSynchronize(w->stream); cudaStreamDestroy(w->stream); }
+        if (w->stream2) { cudaStreamSynchronize(w->stream2); cudaStreamDestroy(w->stream2); }
+        for (auto &e : w->chunk_ev) if (e) cudaEventDestroy(e);
         for (auto &e : w->ev) if (e) cudaEventDestroy(e);
         w->h_words.release(); w->h_descs.release(); w->h_results.release();
         w->d_words.release(); w->d_descs.release(); w->d_results.release();
@@ -444,38 +433,85 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
     if (!ix || !batch || !params || !result) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     const double t0 = now_ms();
     CU_TRY(cudaSetDevice(ix->device));
-    PackedLayout lay;
-    std::vector<uint32_t> word_off;
-    int rc = plan_batch(batch, ix->dix.k_size, ix->dix.max_fanout, lay, word_off);
-    if (rc != CLS_OK) return rc;
     Workspace *w = acquire_ws(ix);
     if (!w) return fail(CLS_ERR_CUDA, "could not create a stream/workspace");
     WsGuard guard{ix, w};
+    PackedLayout &lay = w->lay;
+    std::vector<uint32_t> &word_off = lay.word_off;
+    int rc = plan_batch(batch, ix->dix.k_size, ix->dix.max_fanout, lay, word_off);
+    if (rc != CLS_OK) return rc;
     cls_timing tm{};
+    tm.pack_ms = now_ms() - t0;  // planning counts as packing
     const size_t words_b = (size_t)lay.n_words * 4, descs_b = (size_t)lay.n_device * sizeof(ReadDesc),
                  res_b = (size_t)lay.n_device * sizeof(ResultRec);
+    PlaceParams pp = make_place_params(params);
     if (lay.n_device) {
         CU_TRY(w->h_words.reserve(words_b + 16)); CU_TRY(w->h_descs.reserve(descs_b)); CU_TRY(w->h_results.reserve(res_b));
         CU_TRY(w->d_words.reserve(words_b + 16)); CU_TRY(w->d_descs.reserve(descs_b)); CU_TRY(w->d_results.reserve(res_b));
-        pack_batch(batch, lay, word_off, (uint32_t *)w->h_words.p, (ReadDesc *)w->h_descs.p);
-        tm.pack_ms = now_ms() - t0;
-        CU_TRY(cudaEventRecord(w->ev[0], w->stream));
-        CU_TRY(cudaMemcpyAsync(w->d_words.p, w->h_words.p, words_b, cudaMemcpyHostToDevice, w->stream));
-        CU_TRY(cudaMemcpyAsync(w->d_descs.p, w->h_descs.p, descs_b, cudaMemcpyHostToDevice, w->stream));
-        CU_TRY(cudaEventRecord(w->ev[1], w->stream));
-        rc = launch_classes(ix, lay, params, (const uint32_t *)w->d_words.p, (const ReadDesc *)w->d_descs.p,
-                            (ResultRec *)w->d_results.p, w->stream, &tm.kernel_launches);
-        if (rc != CLS_OK) { cudaStreamSynchronize(w->stream); return rc; }
-        CU_TRY(cudaEventRecord(w->ev[2], w->stream));
-        CU_TRY(cudaMemcpyAsync(w->h_results.p, w->d_results.p, res_b, cudaMemcpyDeviceToHost, w->stream));
-        CU_TRY(cudaEventRecord(w->ev[3], w->stream));
-        CU_TRY(cudaStreamSynchronize(w->stream));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, w->ev[0], w->ev[1]); tm.h2d_ms = ms;
-        cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]); tm.kernel_ms = ms;
-        cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]); tm.d2h_ms = ms;
     }
-    scatter_results(lay, ix->dix.k_size, (const ResultRec *)w->h_results.p, result);
+    scatter_host_decided(lay, ix->dix.k_size, result);
+    // Chunks of every length class go through pack (host threads) -> H2D -> kernel -> D2H on two
+    // alternating streams: chunk c+1 is packed and copied while chunk c is on the SMs, and the
+    // results of finished chunks are scattered to the caller's arrays while later chunks run.
+    struct Chunk { uint32_t first, count, max_len; };
+    std::vector<Chunk> chunks;
+    constexpr uint64_t kChunkBases = 24ull << 20;  // about 24 M bases (6 MiB packed) per chunk
+    for (const LengthClass &c : lay.classes) {
+        const uint64_t per = std::max<uint64_t>(4096, kChunkBases / std::max<uint32_t>(c.max_len, 1));
+        for (uint64_t a = 0; a < c.count; a += per)
+            chunks.push_back(Chunk{(uint32_t)(c.first + a), (uint32_t)std::min<uint64_t>(per, c.count - a), c.max_len});
+    }
+    while (w->chunk_ev.size() < 4 * chunks.size()) {
+        cudaEvent_t e = nullptr;
+        CU_TRY(cudaEventCreate(&e));
+        w->chunk_ev.push_back(e);
+    }
+    uint32_t *h_words = (uint32_t *)w->h_words.p, *d_words = (uint32_t *)w->d_words.p;
+    ReadDesc *h_descs = (ReadDesc *)w->h_descs.p, *d_descs = (ReadDesc *)w->d_descs.p;
+    ResultRec *h_res = (ResultRec *)w->h_results.p, *d_res = (ResultRec *)w->d_results.p;
+    size_t scattered = 0;
+    auto drain = [&](size_t upto) -> int {  // scatter the chunks whose D2H has completed (blocking up to `upto`)
+        for (; scattered < upto; ++scattered) {
+            CU_TRY(cudaEventSynchronize(w->chunk_ev[4 * scattered + 3]));
+            scatter_device_range(lay, h_res, result, chunks[scattered].first, chunks[scattered].count);
+        }
+        return CLS_OK;
+    };
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk &c = chunks[ci];
+        cudaStream_t st = (ci & 1) ? w->stream2 : w->stream;
+        cudaEvent_t *ev = &w->chunk_ev[4 * ci];
+        const double tp = now_ms();
+        pack_batch(batch, lay, word_off, h_words, h_descs, c.first, c.count);
+        tm.pack_ms += now_ms() - tp;
+        const size_t w0 = word_off[c.first], w1 = word_off[c.first + c.count];
+        CU_TRY(cudaEventRecord(ev[0], st));
+        CU_TRY(cudaMemcpyAsync(d_words + w0, h_words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_descs + c.first, h_descs + c.first, (size_t)c.count * sizeof(ReadDesc), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaEventRecord(ev[1], st));
+        PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
+        cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_res, g, ix->sm_count, st);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(w->stream); cudaStreamSynchronize(w->stream2);
+            if (e == cudaErrorInvalidConfiguration)
+                return fail(CLS_ERR_UNSUPPORTED, "query too long (or tree fan-out too large) for the per-read shared-memory tables");
+            return fail(CLS_ERR_CUDA, std::string("place kernel launch: ") + cudaGetErrorString(e));
+        }
+        tm.kernel_launches++;
+        CU_TRY(cudaEventRecord(ev[2], st));
+        CU_TRY(cudaMemcpyAsync(h_res + c.first, d_res + c.first, (size_t)c.count * sizeof(ResultRec), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaEventRecord(ev[3], st));
+        if (ci >= 2) { rc = drain(ci - 1); if (rc != CLS_OK) return rc; }  // chunks older than the two in flight
+    }
+    rc = drain(chunks.size());
+    if (rc != CLS_OK) return rc;
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        float ms = 0;
+        cudaEvent_t *ev = &w->chunk_ev[4 * ci];
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); tm.h2d_ms += ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); tm.kernel_ms += ms;
+        cudaEventElapsedTime(&ms, ev[2], ev[3]); tm.d2h_ms += ms;
+    }
     tm.total_ms = now_ms() - t0;
     { std::lock_guard<std::mutex> lk(ix->mu); ix->timing = tm; }
     return CLS_OK;
@@ -569,6 +605,13 @@ int cls_debug_kmer_hashes(int device, uint32_t k_size, const uint8_t *bases, uin
     *n_out = n;
     if (out_hashes) std::memcpy(out_hashes, h.data(), std::min<uint64_t>(n, cap) * 8);
     return CLS_OK;
+}
+
+int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable) {
+    if ((len && !bases) || !words_out || len >= (1ull << 31) || cap_words < (len + 15) / 16)
+        return fail(CLS_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (len == 0) return 1;
+    return (portable ? pack_read_portable(bases, (uint32_t)len, words_out) : pack_read(bases, (uint32_t)len, words_out)) ? 1 : 0;
 }
 
 uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, uint64_t seed) {

@@ -122,3 +122,28 @@ def test_index_create_rejects_unsupported_models(col_npz):
     with pytest.raises(_lib.ClsError) as ei:
         cq.Index(FlatModel(35, 4, ids, *args[1:], *ent()))
     assert ei.value.code == _lib.CLS_ERR_UNSUPPORTED
+
+
+def test_host_packer_variants_agree_with_numpy():
+    """cls_debug_pack_read: the run-time dispatched (AVX2+BMI2) and the portable packer both equal a
+    numpy restatement of the layout, and both flag non-ACGT bytes."""
+    from classeq2_b200 import _lib
+    rng = np.random.default_rng(5)
+    for L in list(range(0, 70)) + [127, 128, 129, 150, 151, 1000, 1911]:
+        codes = rng.integers(0, 4, L)
+        s = np.frombuffer(b"ACTG", np.uint8)[codes].copy()          # code order A=0 C=1 T=2 G=3
+        lower = rng.random(L) < 0.3
+        s[lower] |= 0x20
+        want = np.zeros((L + 15) // 16 + 1, np.uint32)
+        for j, c in enumerate(codes):
+            want[j // 16] |= np.uint32(int(c) << (2 * (j % 16)))
+        for portable in (0, 1):
+            out = np.zeros(len(want), np.uint32)
+            buf = s if L else np.zeros(1, np.uint8)
+            rc = _lib.lib.cls_debug_pack_read(buf.ctypes.data_as(_lib.u8p), L, out.ctypes.data_as(_lib.u32p), len(out), portable)
+            assert rc == 1 and (out == want).all(), (L, portable)
+            if L:
+                bad = s.copy()
+                bad[int(rng.integers(L))] = ord("N")
+                rc = _lib.lib.cls_debug_pack_read(bad.ctypes.data_as(_lib.u8p), L, out.ctypes.data_as(_lib.u32p), len(out), portable)
+                assert rc == 0, (L, portable)
