@@ -244,6 +244,311 @@ __device__ __forceinline__ Decision decide_smem(const uint32_t *cnt, const uint3
     return d;
 }
 
+// Per-read shared-memory tables (one set per warp, or per CTA for kb-scale reads).
+struct ReadTables {
+    uint32_t *t1;    // de-duplication set keyed by table slot; later the live-set list (lo / entry, weight)
+    uint32_t *t2k;   // histogram keys: node-set record offsets; later `first`
+    uint32_t *t2c;   // histogram counts; later `last`
+    uint32_t *lst;   // histogram positions of the distinct sets in arrival order; later `hi`
+    uint32_t *cnt, *excl;   // vote counters, one per non-leaf child ordinal
+    uint32_t *n_sets;       // number of distinct node sets seen
+    uint32_t t1_mask, t2_mask, t2_shift;
+};
+
+// Adds this pass's hits to the read's tables: de-duplicate by `slot_key` (distinct-hash semantics of
+// the reference's HashSets), then add the distinct ones to the node-set histogram with ONE
+// shared-memory atomic per group of lanes that hit the same node set (match.any).  Called by all
+// 32 lanes; returns the number of distinct new hits of the pass (uniform).
+__device__ __forceinline__ uint32_t insert_hits(const ReadTables &tb, bool hit, uint32_t slot_key, uint32_t set_off) {
+    bool fresh = false;
+    if (hit) {
+        uint32_t p1 = slot_key & tb.t1_mask;
+        for (;;) {
+            const uint32_t old = atomicCAS(&tb.t1[p1], kEmpty, slot_key);
+            if (old == kEmpty) { fresh = true; break; }
+            if (old == slot_key) break;  // the same k-mer hash was already counted
+            p1 = (p1 + 1) & tb.t1_mask;
+        }
+    }
+    const uint32_t fm = __ballot_sync(kFull, fresh);
+    if (fresh) {
+        const uint32_t peers = __match_any_sync(fm, set_off);
+        if ((uint32_t)(__ffs(peers) - 1) == lane_id()) {
+            uint32_t p2 = (set_off * 0x9E3779B1u) >> tb.t2_shift;
+            for (;;) {
+                const uint32_t old = atomicCAS(&tb.t2k[p2], kEmpty, set_off);
+                if (old == kEmpty) tb.lst[atomicAdd(tb.n_sets, 1u)] = p2;
+                if (old == kEmpty || old == set_off) { atomicAdd(&tb.t2c[p2], (uint32_t)__popc(peers)); break; }
+                p2 = (p2 + 1) & tb.t2_mask;
+            }
+        }
+    }
+    return (uint32_t)__popc(fm);
+}
+
+// Everything after the hits of a read are in its tables: restriction to the root, gates, descent,
+// and the result record.  One warp; `D` distinct node sets, `n_matched` distinct hits (|M|).
+template <bool CLOSED>
+__device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlaceParams &pp, const ReadTables &tb,
+                                            uint32_t D, uint32_t n_matched, ResultRec *__restrict__ out) {
+    const uint32_t lane = lane_id();
+    uint32_t *t1 = tb.t1, *t2k = tb.t2k, *t2c = tb.t2c, *lst = tb.lst, *cnt = tb.cnt, *excl = tb.excl;
+    const bool ri = pp.remove_intersection != 0;
+    // ---- live-set list: restrict to sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
+    //      CLOSED : t1[2j] = lo, t1[2j+1] = weight, lst[j] = hi (terminal range [lo, hi)),
+    //               t2k[j] = terms[lo] ("first"), t2c[j] = terms[hi-1] ("last")
+    //      GENERAL: t1[2j] = current mini-tree entry, t1[2j+1] = weight
+    for (uint32_t j = lane; j < D; j += 32) {
+        const uint32_t p2 = lst[j];
+        const uint32_t off = t2k[p2], w = t2c[p2];
+        t1[2 * j] = off;
+        t1[2 * j + 1] = w;
+    }
+    __syncwarp();
+    uint32_t n_root = 0;
+    for (uint32_t j = lane; j < D; j += 32) {
+        const uint32_t off = t1[2 * j];
+        uint32_t w = t1[2 * j + 1];
+        if constexpr (CLOSED) {
+            const uint32_t hdr = __ldg(ix.terms + off), last = __ldg(ix.terms + off + 1), first = __ldg(ix.terms + off + 2);
+            if (hdr & kTermHasRoot) n_root += w; else w = 0;
+            t1[2 * j] = off + 2;
+            lst[j] = off + 2 + (hdr & ~kTermHasRoot);
+            t2k[j] = first;
+            t2c[j] = last;
+        } else {
+            const SetWord hdr = ix.arena[off];
+            if (hdr.x & kSetHasRoot) n_root += w; else w = 0;
+            t1[2 * j] = off + 1;
+        }
+        t1[2 * j + 1] = w;
+    }
+    n_root = __reduce_add_sync(kFull, n_root);
+    __syncwarp();
+
+    // ---- gates (place_sequence.rs:120-139, :156-166, :199-206, :231-254) ---------------
+    ResultRec res;
+    res.node_id = 0; res.one = 0; res.rest = 0;
+    res.n_matched = n_matched; res.n_root_matched = n_root; res.iterations = 0;
+    res.status = kUndecided;
+    if (n_matched == 0) res.status = CLS_DEV_UNCL_NO_MATCH;
+    else if (n_root == 0) res.status = CLS_DEV_UNCL_NO_ROOT;
+    else if (ix.root_children_none) res.status = CLS_DEV_ERR_ROOT_NO_CHILDREN;
+    else {
+        // f64::round (half away from zero) of a non-negative product, without a libdevice call
+        const double x = (double)n_matched * pp.min_match_coverage;
+        double expected = floor(x);
+        if (x - expected >= 0.5) expected += 1.0;
+        if ((double)n_root < expected) res.status = CLS_DEV_UNCL_COVERAGE;
+    }
+
+    // ---- descent ---------------------------------------------------------------------------
+    uint32_t p = 0;  // current parent (dense non-leaf id), root = 0
+    int64_t iteration = 0;
+    const int64_t max_iter = pp.max_iterations;
+    if constexpr (CLOSED) {
+        uint32_t depth_p = 0;
+        QInfo ip = res.status == kUndecided ? ld_qinfo(ix.qinfo, 0) : QInfo{0, 0, 0, 0};
+        while (res.status == kUndecided) {
+            // pooled extremes of the live terminals -> every level down to their LCA is unanimous
+            uint32_t umin = 0xFFFFFFFFu, vmax = 0, wl = 0;
+            for (uint32_t j = lane; j < D; j += 32) {
+                const uint32_t w = t1[2 * j + 1];
+                if (w == 0) continue;
+                umin = min(umin, t2k[j]);
+                vmax = max(vmax, t2c[j]);
+                wl += w;
+            }
+            umin = __reduce_min_sync(kFull, umin);
+            vmax = __reduce_max_sync(kFull, vmax);
+            const uint32_t Wlive = __reduce_add_sync(kFull, wl);
+            const uint64_t dn = lca_depth_node(ix, umin, vmax);
+            const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
+            if (depth_a > depth_p) {
+                const uint32_t d = depth_a - depth_p;
+                if (iteration + (int64_t)d > max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+                iteration += d;
+                ip = ld_qinfo(ix.qinfo, A);
+                if (ip.child_count == 0) {  // update_introspection_node.rs:32-87
+                    res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[A];
+                    res.one = (int32_t)Wlive; res.rest = 0;
+                    break;
+                }
+                p = A; depth_p = depth_a;
+            }
+            // ---- evaluate the children of p -------------------------------------------------
+            iteration++;
+            if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+            const uint32_t m = ip.child_count;
+            const uint32_t p_end = ip.q_end;
+            uint32_t win_q = 0, nprop = 0, n_best = 0;
+            int32_t win_one = 0, win_rest = 0;
+            QInfo iw{0, 0, 0, 0};
+            if (m <= 2) {
+                // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
+                const QInfo i1 = m ? ld_qinfo(ix.qinfo, p + 1) : QInfo{p_end, 0, 0, 0};
+                const uint32_t bnd = i1.q_end;
+                uint32_t c1 = 0, c2 = 0, both = 0;
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const uint32_t w = t1[2 * j + 1];
+                    if (w == 0) continue;
+                    uint32_t lo = t1[2 * j], first = t2k[j];
+                    const uint32_t hi = lst[j];
+                    if (first == p) {  // the set ends at p itself for some tip: not a vote for any child
+                        ++lo;
+                        first = lo < hi ? __ldg(ix.terms + lo) : 0xFFFFFFFFu;
+                        t1[2 * j] = lo; t2k[j] = first;
+                    }
+                    if (lo < hi) {
+                        const bool in1 = first < bnd, in2 = t2c[j] >= bnd;
+                        c1 += in1 ? w : 0u; c2 += in2 ? w : 0u; both += (in1 && in2) ? w : 0u;
+                    }
+                }
+                c1 = __reduce_add_sync(kFull, c1);
+                c2 = __reduce_add_sync(kFull, c2);
+                both = __reduce_add_sync(kFull, both);
+                const uint32_t U = c1 + c2 - both, x1 = c1 - both, x2 = c2 - both;
+                const uint32_t ncand = (c1 > 0) + (c2 > 0);
+                const int32_t one1 = (int32_t)((ri && ncand > 1) ? x1 : c1), rest1 = ncand > 1 ? (int32_t)(ri ? U - c1 : U - x1) : 0;
+                const int32_t one2 = (int32_t)((ri && ncand > 1) ? x2 : c2), rest2 = ncand > 1 ? (int32_t)(ri ? U - c2 : U - x2) : 0;
+                const bool pr1 = c1 > 0 && one1 > rest1, pr2 = c2 > 0 && one2 > rest2;
+                nprop = (uint32_t)pr1 + (uint32_t)pr2;
+                bool pick2 = pr2 && !pr1;
+                n_best = nprop ? 1u : 0u;
+                if (pr1 && pr2) {  // provably unreachable; kept for fidelity (:519-599)
+                    const int32_t d1 = one1 - rest1, d2 = one2 - rest2;
+                    if (d1 == d2) n_best = 2; else pick2 = d2 > d1;
+                }
+                if (pick2) { win_q = bnd; win_one = one2; win_rest = rest2; if (nprop) iw = ld_qinfo(ix.qinfo, bnd); }
+                else { win_q = p + 1; win_one = one1; win_rest = rest1; iw = i1; }
+            } else {
+                // general fan-out: per-set merge walk of the terminal range against the child
+                // intervals, votes in shared-memory counters
+                uint32_t u_local = 0;
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const uint32_t w = t1[2 * j + 1];
+                    if (w == 0) continue;
+                    uint32_t pos = t1[2 * j];
+                    const uint32_t hi = lst[j];
+                    if (t2k[j] == p) ++pos;
+                    uint32_t npres = 0, last = 0, ord = 0, cend = __ldg(&ix.qinfo[p + 1].q_end);
+                    while (pos < hi) {
+                        const uint32_t t = __ldg(ix.terms + pos);
+                        while (t >= cend) { cend = __ldg(&ix.qinfo[cend].q_end); ++ord; }
+                        atomicAdd(&cnt[ord], w); ++npres; last = ord;
+                        ++pos;
+                        if (pos < hi && __ldg(ix.terms + pos) < cend) pos = lower_bound_terms(ix.terms, pos, hi, cend);
+                    }
+                    if (npres) u_local += w;
+                    if (npres == 1) atomicAdd(&excl[last], w);
+                }
+                const uint32_t U = __reduce_add_sync(kFull, u_local);
+                __syncwarp();
+                const Decision dc = decide_smem(cnt, excl, m, U, ri);
+                __syncwarp();
+                for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
+                __syncwarp();
+                nprop = dc.nprop; n_best = dc.n_best; win_one = dc.best_one; win_rest = dc.best_rest;
+                win_q = p + 1;
+                for (uint32_t o = 0; o < dc.best_ord; ++o) win_q = __ldg(&ix.qinfo[win_q].q_end);
+                iw = ld_qinfo(ix.qinfo, win_q);
+            }
+            if (nprop == 0) {
+                if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
+                else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
+                break;
+            }
+            if (n_best != 1) { res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p]; break; }
+            if (iw.child_count == 0) {  // update_introspection_node.rs:32-87
+                res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[win_q];
+                res.one = win_one; res.rest = win_rest;
+                break;
+            }
+            p = win_q; ip = iw; depth_p++;
+            const uint32_t win_end = iw.q_end;
+            // every live set keeps its terminals inside the winner's interval (or drops out)
+            for (uint32_t j = lane; j < D; j += 32) {
+                if (t1[2 * j + 1] == 0) continue;
+                uint32_t lo = t1[2 * j], hi = lst[j], first = t2k[j], last = t2c[j];
+                bool live = lo < hi && last >= win_q && first < win_end;
+                if (live && first < win_q) {
+                    lo = lower_bound_terms(ix.terms, lo + 1, hi, win_q);
+                    first = __ldg(ix.terms + lo);  // lo < hi because last >= win_q
+                    live = first < win_end;
+                    t1[2 * j] = lo; t2k[j] = first;
+                }
+                if (live && last >= win_end) {
+                    hi = lower_bound_terms(ix.terms, lo + 1, hi - 1, win_end);  // terms[lo] < win_end
+                    lst[j] = hi; t2c[j] = __ldg(ix.terms + hi - 1);
+                }
+                if (!live) t1[2 * j + 1] = 0;
+            }
+            __syncwarp();
+        }
+    } else {
+        while (res.status == kUndecided) {
+            iteration++;
+            if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+            const QNode qn = ix.qnodes[p];
+            const uint32_t m = qn.child_count;
+            // votes
+            uint32_t u_local = 0;
+            for (uint32_t j = lane; j < D; j += 32) {
+                const uint32_t w = t1[2 * j + 1];
+                if (w == 0) continue;
+                const uint32_t cur = t1[2 * j];
+                const uint32_t end = cur + ix.arena[cur].y;
+                uint32_t npres = 0, last = 0;
+                for (uint32_t c = cur + 1; c < end;) {
+                    const SetWord e = ix.arena[c];
+                    if (e.x & kPresentBit) { last = e.x & ~kPresentBit; atomicAdd(&cnt[last], w); npres++; }
+                    c += e.y;
+                }
+                if (npres) u_local += w;
+                if (npres == 1) atomicAdd(&excl[last], w);
+            }
+            const uint32_t U = __reduce_add_sync(kFull, u_local);
+            __syncwarp();
+            const Decision dc = decide_smem(cnt, excl, m, U, ri);
+            __syncwarp();
+            for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
+            __syncwarp();
+            if (dc.nprop == 0) {
+                if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
+                else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
+                break;
+            }
+            if (dc.n_best != 1) {  // several proposals tie on (one - rest): provably unreachable
+                res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p];
+                break;
+            }
+            const uint32_t cq = ix.q_child_list[qn.child_first + dc.best_ord];
+            if (ix.qnodes[cq].child_count == 0) {  // update_introspection_node.rs:32-87
+                res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[cq];
+                res.one = dc.best_one; res.rest = dc.best_rest;
+                break;
+            }
+            p = cq;
+            // every live set follows the winner (or drops out)
+            for (uint32_t j = lane; j < D; j += 32) {
+                if (t1[2 * j + 1] == 0) continue;
+                const uint32_t cur = t1[2 * j];
+                const uint32_t end = cur + ix.arena[cur].y;
+                uint32_t next = 0;
+                for (uint32_t c = cur + 1; c < end;) {
+                    const SetWord e = ix.arena[c];
+                    if ((e.x & ~kPresentBit) == dc.best_ord) { next = c; break; }
+                    c += e.y;
+                }
+                if (next) t1[2 * j] = next; else t1[2 * j + 1] = 0;
+            }
+            __syncwarp();
+        }
+    }
+    res.iterations = (uint32_t)iteration;
+    if (lane == 0) *out = res;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -316,11 +621,9 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
     uint32_t *excl = cnt + g.fan_cap;
     uint32_t *n_sets_smem = excl + g.fan_cap;
     uint32_t *n_matched_smem = n_sets_smem + 1;
-    const uint32_t t1_mask = g.t1_size - 1u, t2_mask = g.t2_size - 1u;
-    const uint32_t t2_shift = 32u - g.t2_log2;
+    const ReadTables tb{t1, t2k, t2c, lst, cnt, excl, n_sets_smem, g.t1_size - 1u, g.t2_size - 1u, 32u - g.t2_log2};
     const uint32_t k = ix.k_size;
     const uint32_t code_mask = ix.m_eff >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ix.m_eff)) - 1u);
-    const bool ri = pp.remove_intersection != 0;
 
     for (uint32_t o = gtid; o < g.fan_cap; o += gthreads) { cnt[o] = 0; excl[o] = 0; }
     __syncthreads();
@@ -363,39 +666,17 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
                     ld_bucket(ix.table, b, h0, m0, h1, m1);
                 }
             }
-            bool fresh = false;
-            if (slot_id != kEmpty) {
+            bool hit = slot_id != kEmpty;
+            if (hit) {
                 // bucket gating: the entry's bucket key must be among the query's prefix keys
                 const uint32_t want = code & kCodeMask;
-                bool pass = packed_bits(rc ? wm.pk_r : wm.pk_f, pos, code_mask) == want;
-                if (!pass) {  // only possible for models whose bucket keys disagree with their k-mers
-                    for (uint32_t p = 0; p < W && !pass; ++p)
-                        pass = packed_bits(wm.pk_f, p, code_mask) == want || packed_bits(wm.pk_r, p, code_mask) == want;
-                }
-                if (pass) {
-                    uint32_t p1 = slot_id & t1_mask;
-                    for (;;) {
-                        const uint32_t old = atomicCAS(&t1[p1], kEmpty, slot_id);
-                        if (old == kEmpty) { fresh = true; break; }
-                        if (old == slot_id) break;  // the same k-mer hash was already counted
-                        p1 = (p1 + 1) & t1_mask;
-                    }
+                hit = packed_bits(rc ? wm.pk_r : wm.pk_f, pos, code_mask) == want;
+                if (!hit) {  // only possible for models whose bucket keys disagree with their k-mers
+                    for (uint32_t p = 0; p < W && !hit; ++p)
+                        hit = packed_bits(wm.pk_f, p, code_mask) == want || packed_bits(wm.pk_r, p, code_mask) == want;
                 }
             }
-            const uint32_t fm = __ballot_sync(kFull, fresh);
-            if (fresh) {
-                const uint32_t peers = __match_any_sync(fm, set_off);
-                if ((uint32_t)(__ffs(peers) - 1) == lane) {
-                    uint32_t p2 = (set_off * 0x9E3779B1u) >> t2_shift;
-                    for (;;) {
-                        const uint32_t old = atomicCAS(&t2k[p2], kEmpty, set_off);
-                        if (old == kEmpty) lst[atomicAdd(n_sets_smem, 1u)] = p2;
-                        if (old == kEmpty || old == set_off) { atomicAdd(&t2c[p2], (uint32_t)__popc(peers)); break; }
-                        p2 = (p2 + 1) & t2_mask;
-                    }
-                }
-            }
-            return (uint32_t)__popc(fm);
+            return insert_hits(tb, hit, slot_id, set_off);
         };
 
         uint32_t n_matched = 0;
@@ -428,259 +709,7 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
         __syncwarp();
         const uint32_t D = *n_sets_smem;
 
-        // ---- live-set list: restrict to sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
-        //      CLOSED : t1[2j] = lo, t1[2j+1] = weight, lst[j] = hi (terminal range [lo, hi)),
-        //               t2k[j] = terms[lo] ("first"), t2c[j] = terms[hi-1] ("last")
-        //      GENERAL: t1[2j] = current mini-tree entry, t1[2j+1] = weight
-        for (uint32_t j = lane; j < D; j += 32) {
-            const uint32_t p2 = lst[j];
-            const uint32_t off = t2k[p2], w = t2c[p2];
-            t1[2 * j] = off;
-            t1[2 * j + 1] = w;
-        }
-        __syncwarp();
-        uint32_t n_root = 0;
-        for (uint32_t j = lane; j < D; j += 32) {
-            const uint32_t off = t1[2 * j];
-            uint32_t w = t1[2 * j + 1];
-            if constexpr (CLOSED) {
-                const uint32_t hdr = __ldg(ix.terms + off), last = __ldg(ix.terms + off + 1), first = __ldg(ix.terms + off + 2);
-                if (hdr & kTermHasRoot) n_root += w; else w = 0;
-                t1[2 * j] = off + 2;
-                lst[j] = off + 2 + (hdr & ~kTermHasRoot);
-                t2k[j] = first;
-                t2c[j] = last;
-            } else {
-                const SetWord hdr = ix.arena[off];
-                if (hdr.x & kSetHasRoot) n_root += w; else w = 0;
-                t1[2 * j] = off + 1;
-            }
-            t1[2 * j + 1] = w;
-        }
-        n_root = __reduce_add_sync(kFull, n_root);
-        __syncwarp();
-
-        // ---- gates (place_sequence.rs:120-139, :156-166, :199-206, :231-254) ---------------
-        ResultRec res;
-        res.node_id = 0; res.one = 0; res.rest = 0;
-        res.n_matched = n_matched; res.n_root_matched = n_root; res.iterations = 0;
-        res.status = kUndecided;
-        if (n_matched == 0) res.status = CLS_DEV_UNCL_NO_MATCH;
-        else if (n_root == 0) res.status = CLS_DEV_UNCL_NO_ROOT;
-        else if (ix.root_children_none) res.status = CLS_DEV_ERR_ROOT_NO_CHILDREN;
-        else {
-            // f64::round (half away from zero) of a non-negative product, without a libdevice call
-            const double x = (double)n_matched * pp.min_match_coverage;
-            double expected = floor(x);
-            if (x - expected >= 0.5) expected += 1.0;
-            if ((double)n_root < expected) res.status = CLS_DEV_UNCL_COVERAGE;
-        }
-
-        // ---- descent ---------------------------------------------------------------------------
-        uint32_t p = 0;  // current parent (dense non-leaf id), root = 0
-        int64_t iteration = 0;
-        const int64_t max_iter = pp.max_iterations;
-        if constexpr (CLOSED) {
-            uint32_t depth_p = 0;
-            QInfo ip = res.status == kUndecided ? ld_qinfo(ix.qinfo, 0) : QInfo{0, 0, 0, 0};
-            while (res.status == kUndecided) {
-                // pooled extremes of the live terminals -> every level down to their LCA is unanimous
-                uint32_t umin = 0xFFFFFFFFu, vmax = 0, wl = 0;
-                for (uint32_t j = lane; j < D; j += 32) {
-                    const uint32_t w = t1[2 * j + 1];
-                    if (w == 0) continue;
-                    umin = min(umin, t2k[j]);
-                    vmax = max(vmax, t2c[j]);
-                    wl += w;
-                }
-                umin = __reduce_min_sync(kFull, umin);
-                vmax = __reduce_max_sync(kFull, vmax);
-                const uint32_t Wlive = __reduce_add_sync(kFull, wl);
-                const uint64_t dn = lca_depth_node(ix, umin, vmax);
-                const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
-                if (depth_a > depth_p) {
-                    const uint32_t d = depth_a - depth_p;
-                    if (iteration + (int64_t)d > max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
-                    iteration += d;
-                    ip = ld_qinfo(ix.qinfo, A);
-                    if (ip.child_count == 0) {  // update_introspection_node.rs:32-87
-                        res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[A];
-                        res.one = (int32_t)Wlive; res.rest = 0;
-                        break;
-                    }
-                    p = A; depth_p = depth_a;
-                }
-                // ---- evaluate the children of p -------------------------------------------------
-                iteration++;
-                if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
-                const uint32_t m = ip.child_count;
-                const uint32_t p_end = ip.q_end;
-                uint32_t win_q = 0, nprop = 0, n_best = 0;
-                int32_t win_one = 0, win_rest = 0;
-                QInfo iw{0, 0, 0, 0};
-                if (m <= 2) {
-                    // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
-                    const QInfo i1 = m ? ld_qinfo(ix.qinfo, p + 1) : QInfo{p_end, 0, 0, 0};
-                    const uint32_t bnd = i1.q_end;
-                    uint32_t c1 = 0, c2 = 0, both = 0;
-                    for (uint32_t j = lane; j < D; j += 32) {
-                        const uint32_t w = t1[2 * j + 1];
-                        if (w == 0) continue;
-                        uint32_t lo = t1[2 * j], first = t2k[j];
-                        const uint32_t hi = lst[j];
-                        if (first == p) {  // the set ends at p itself for some tip: not a vote for any child
-                            ++lo;
-                            first = lo < hi ? __ldg(ix.terms + lo) : 0xFFFFFFFFu;
-                            t1[2 * j] = lo; t2k[j] = first;
-                        }
-                        if (lo < hi) {
-                            const bool in1 = first < bnd, in2 = t2c[j] >= bnd;
-                            c1 += in1 ? w : 0u; c2 += in2 ? w : 0u; both += (in1 && in2) ? w : 0u;
-                        }
-                    }
-                    c1 = __reduce_add_sync(kFull, c1);
-                    c2 = __reduce_add_sync(kFull, c2);
-                    both = __reduce_add_sync(kFull, both);
-                    const uint32_t U = c1 + c2 - both, x1 = c1 - both, x2 = c2 - both;
-                    const uint32_t ncand = (c1 > 0) + (c2 > 0);
-                    const int32_t one1 = (int32_t)((ri && ncand > 1) ? x1 : c1), rest1 = ncand > 1 ? (int32_t)(ri ? U - c1 : U - x1) : 0;
-                    const int32_t one2 = (int32_t)((ri && ncand > 1) ? x2 : c2), rest2 = ncand > 1 ? (int32_t)(ri ? U - c2 : U - x2) : 0;
-                    const bool pr1 = c1 > 0 && one1 > rest1, pr2 = c2 > 0 && one2 > rest2;
-                    nprop = (uint32_t)pr1 + (uint32_t)pr2;
-                    bool pick2 = pr2 && !pr1;
-                    n_best = nprop ? 1u : 0u;
-                    if (pr1 && pr2) {  // provably unreachable; kept for fidelity (:519-599)
-                        const int32_t d1 = one1 - rest1, d2 = one2 - rest2;
-                        if (d1 == d2) n_best = 2; else pick2 = d2 > d1;
-                    }
-                    if (pick2) { win_q = bnd; win_one = one2; win_rest = rest2; if (nprop) iw = ld_qinfo(ix.qinfo, bnd); }
-                    else { win_q = p + 1; win_one = one1; win_rest = rest1; iw = i1; }
-                } else {
-                    // general fan-out: per-set merge walk of the terminal range against the child
-                    // intervals, votes in shared-memory counters
-                    uint32_t u_local = 0;
-                    for (uint32_t j = lane; j < D; j += 32) {
-                        const uint32_t w = t1[2 * j + 1];
-                        if (w == 0) continue;
-                        uint32_t pos = t1[2 * j];
-                        const uint32_t hi = lst[j];
-                        if (t2k[j] == p) ++pos;
-                        uint32_t npres = 0, last = 0, ord = 0, cend = __ldg(&ix.qinfo[p + 1].q_end);
-                        while (pos < hi) {
-                            const uint32_t t = __ldg(ix.terms + pos);
-                            while (t >= cend) { cend = __ldg(&ix.qinfo[cend].q_end); ++ord; }
-                            atomicAdd(&cnt[ord], w); ++npres; last = ord;
-                            ++pos;
-                            if (pos < hi && __ldg(ix.terms + pos) < cend) pos = lower_bound_terms(ix.terms, pos, hi, cend);
-                        }
-                        if (npres) u_local += w;
-                        if (npres == 1) atomicAdd(&excl[last], w);
-                    }
-                    const uint32_t U = __reduce_add_sync(kFull, u_local);
-                    __syncwarp();
-                    const Decision dc = decide_smem(cnt, excl, m, U, ri);
-                    __syncwarp();
-                    for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
-                    __syncwarp();
-                    nprop = dc.nprop; n_best = dc.n_best; win_one = dc.best_one; win_rest = dc.best_rest;
-                    win_q = p + 1;
-                    for (uint32_t o = 0; o < dc.best_ord; ++o) win_q = __ldg(&ix.qinfo[win_q].q_end);
-                    iw = ld_qinfo(ix.qinfo, win_q);
-                }
-                if (nprop == 0) {
-                    if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
-                    else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
-                    break;
-                }
-                if (n_best != 1) { res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p]; break; }
-                if (iw.child_count == 0) {  // update_introspection_node.rs:32-87
-                    res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[win_q];
-                    res.one = win_one; res.rest = win_rest;
-                    break;
-                }
-                p = win_q; ip = iw; depth_p++;
-                const uint32_t win_end = iw.q_end;
-                // every live set keeps its terminals inside the winner's interval (or drops out)
-                for (uint32_t j = lane; j < D; j += 32) {
-                    if (t1[2 * j + 1] == 0) continue;
-                    uint32_t lo = t1[2 * j], hi = lst[j], first = t2k[j], last = t2c[j];
-                    bool live = lo < hi && last >= win_q && first < win_end;
-                    if (live && first < win_q) {
-                        lo = lower_bound_terms(ix.terms, lo + 1, hi, win_q);
-                        first = __ldg(ix.terms + lo);  // lo < hi because last >= win_q
-                        live = first < win_end;
-                        t1[2 * j] = lo; t2k[j] = first;
-                    }
-                    if (live && last >= win_end) {
-                        hi = lower_bound_terms(ix.terms, lo + 1, hi - 1, win_end);  // terms[lo] < win_end
-                        lst[j] = hi; t2c[j] = __ldg(ix.terms + hi - 1);
-                    }
-                    if (!live) t1[2 * j + 1] = 0;
-                }
-                __syncwarp();
-            }
-        } else {
-            while (res.status == kUndecided) {
-                iteration++;
-                if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
-                const QNode qn = ix.qnodes[p];
-                const uint32_t m = qn.child_count;
-                // votes
-                uint32_t u_local = 0;
-                for (uint32_t j = lane; j < D; j += 32) {
-                    const uint32_t w = t1[2 * j + 1];
-                    if (w == 0) continue;
-                    const uint32_t cur = t1[2 * j];
-                    const uint32_t end = cur + ix.arena[cur].y;
-                    uint32_t npres = 0, last = 0;
-                    for (uint32_t c = cur + 1; c < end;) {
-                        const SetWord e = ix.arena[c];
-                        if (e.x & kPresentBit) { last = e.x & ~kPresentBit; atomicAdd(&cnt[last], w); npres++; }
-                        c += e.y;
-                    }
-                    if (npres) u_local += w;
-                    if (npres == 1) atomicAdd(&excl[last], w);
-                }
-                const uint32_t U = __reduce_add_sync(kFull, u_local);
-                __syncwarp();
-                const Decision dc = decide_smem(cnt, excl, m, U, ri);
-                __syncwarp();
-                for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
-                __syncwarp();
-                if (dc.nprop == 0) {
-                    if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
-                    else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
-                    break;
-                }
-                if (dc.n_best != 1) {  // several proposals tie on (one - rest): provably unreachable
-                    res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p];
-                    break;
-                }
-                const uint32_t cq = ix.q_child_list[qn.child_first + dc.best_ord];
-                if (ix.qnodes[cq].child_count == 0) {  // update_introspection_node.rs:32-87
-                    res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[cq];
-                    res.one = dc.best_one; res.rest = dc.best_rest;
-                    break;
-                }
-                p = cq;
-                // every live set follows the winner (or drops out)
-                for (uint32_t j = lane; j < D; j += 32) {
-                    if (t1[2 * j + 1] == 0) continue;
-                    const uint32_t cur = t1[2 * j];
-                    const uint32_t end = cur + ix.arena[cur].y;
-                    uint32_t next = 0;
-                    for (uint32_t c = cur + 1; c < end;) {
-                        const SetWord e = ix.arena[c];
-                        if ((e.x & ~kPresentBit) == dc.best_ord) { next = c; break; }
-                        c += e.y;
-                    }
-                    if (next) t1[2 * j] = next; else t1[2 * j + 1] = 0;
-                }
-                __syncwarp();
-            }
-        }
-        res.iterations = (uint32_t)iteration;
-        if (lane == 0) results[first_read + r] = res;
+        finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
         __syncwarp();
         if constexpr (CTA) __syncthreads();   // the tables are free again for the next read
     }
