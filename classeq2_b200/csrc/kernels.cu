@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <climits>
+#include <cstdlib>
 #include <cstdint>
 
 #include "device_types.hpp"
@@ -549,6 +550,157 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
     if (lane == 0) *out = res;
 }
 
+// ------------------------------------------------------------------------------------------
+// finish_read for CLOSED models when the read has at most 32 distinct node sets (97 % of 150 bp
+// reads): lane j keeps set j - its live terminal range [lo, hi), its smallest and largest live
+// terminal and its weight - in registers, every vote is one warp reduction, and no loop runs over
+// the sets.  Same algorithm and same outcomes as finish_read<true>.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const PlaceParams &pp, const ReadTables &tb,
+                                                uint32_t D, uint32_t n_matched, ResultRec *__restrict__ out) {
+    const uint32_t lane = lane_id();
+    const uint32_t *__restrict__ terms = ix.terms;
+    const bool ri = pp.remove_intersection != 0;
+    // ---- restriction to the sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
+    uint32_t lo = 0, hi = 0, first = 0xFFFFFFFFu, last = 0, w = 0;
+    if (lane < D) {
+        const uint32_t p2 = tb.lst[lane];
+        const uint32_t off = tb.t2k[p2];
+        const uint32_t hdr = __ldg(terms + off);
+        if (hdr & kTermHasRoot) {
+            last = __ldg(terms + off + 1); first = __ldg(terms + off + 2);
+            w = tb.t2c[p2];
+            lo = off + 2; hi = lo + (hdr & ~kTermHasRoot);
+        }
+    }
+    const uint32_t n_root = __reduce_add_sync(kFull, w);
+    // ---- gates (place_sequence.rs:120-139, :156-166, :199-206, :231-254)
+    ResultRec res;
+    res.node_id = 0; res.one = 0; res.rest = 0;
+    res.n_matched = n_matched; res.n_root_matched = n_root; res.iterations = 0;
+    res.status = kUndecided;
+    if (n_matched == 0) res.status = CLS_DEV_UNCL_NO_MATCH;
+    else if (n_root == 0) res.status = CLS_DEV_UNCL_NO_ROOT;
+    else if (ix.root_children_none) res.status = CLS_DEV_ERR_ROOT_NO_CHILDREN;
+    else {
+        const double x = (double)n_matched * pp.min_match_coverage;  // f64::round, half away from zero
+        double expected = floor(x);
+        if (x - expected >= 0.5) expected += 1.0;
+        if ((double)n_root < expected) res.status = CLS_DEV_UNCL_COVERAGE;
+    }
+    // ---- descent
+    uint32_t p = 0, depth_p = 0;
+    int64_t iteration = 0;
+    const int64_t max_iter = pp.max_iterations;
+    QInfo ip = res.status == kUndecided ? ld_qinfo(ix.qinfo, 0) : QInfo{0, 0, 0, 0};
+    while (res.status == kUndecided) {
+        // pooled extremes of the live terminals -> every level down to their LCA is unanimous
+        const uint32_t umin = __reduce_min_sync(kFull, w ? first : 0xFFFFFFFFu);
+        const uint32_t vmax = __reduce_max_sync(kFull, w ? last : 0u);
+        const uint64_t dn = lca_depth_node(ix, umin, vmax);
+        const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
+        if (depth_a > depth_p) {
+            const uint32_t d = depth_a - depth_p;
+            if (iteration + (int64_t)d > max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+            iteration += d;
+            ip = ld_qinfo(ix.qinfo, A);
+            if (ip.child_count == 0) {  // update_introspection_node.rs:32-87
+                res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[A];
+                res.one = (int32_t)__reduce_add_sync(kFull, w); res.rest = 0;
+                break;
+            }
+            p = A; depth_p = depth_a;
+        }
+        // ---- evaluate the children of p
+        iteration++;
+        if (iteration > max_iter) { res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+        const uint32_t m = ip.child_count, p_end = ip.q_end;
+        uint32_t win_q = 0, nprop = 0, n_best = 0;
+        int32_t win_one = 0, win_rest = 0;
+        QInfo iw{0, 0, 0, 0};
+        if (w && first == p) {  // the set ends at p itself for some tip: that is no vote for any child
+            ++lo;
+            first = lo < hi ? __ldg(terms + lo) : 0xFFFFFFFFu;
+        }
+        const bool has = w && lo < hi;
+        if (m <= 2) {
+            // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
+            const QInfo i1 = m ? ld_qinfo(ix.qinfo, p + 1) : QInfo{p_end, 0, 0, 0};
+            const uint32_t bnd = i1.q_end;
+            const bool in1 = has && first < bnd, in2 = has && last >= bnd;
+            const uint32_t c1 = __reduce_add_sync(kFull, in1 ? w : 0u), c2 = __reduce_add_sync(kFull, in2 ? w : 0u);
+            const uint32_t both = __reduce_add_sync(kFull, (in1 && in2) ? w : 0u);
+            const uint32_t U = c1 + c2 - both, x1 = c1 - both, x2 = c2 - both;
+            const uint32_t ncand = (c1 > 0) + (c2 > 0);
+            const int32_t one1 = (int32_t)((ri && ncand > 1) ? x1 : c1), rest1 = ncand > 1 ? (int32_t)(ri ? U - c1 : U - x1) : 0;
+            const int32_t one2 = (int32_t)((ri && ncand > 1) ? x2 : c2), rest2 = ncand > 1 ? (int32_t)(ri ? U - c2 : U - x2) : 0;
+            const bool pr1 = c1 > 0 && one1 > rest1, pr2 = c2 > 0 && one2 > rest2;
+            nprop = (uint32_t)pr1 + (uint32_t)pr2;
+            bool pick2 = pr2 && !pr1;
+            n_best = nprop ? 1u : 0u;
+            if (pr1 && pr2) {  // provably unreachable; kept for fidelity (:519-599)
+                const int32_t d1 = one1 - rest1, d2 = one2 - rest2;
+                if (d1 == d2) n_best = 2; else pick2 = d2 > d1;
+            }
+            if (pick2) { win_q = bnd; win_one = one2; win_rest = rest2; if (nprop) iw = ld_qinfo(ix.qinfo, bnd); }
+            else { win_q = p + 1; win_one = one1; win_rest = rest1; iw = i1; }
+        } else {
+            // general fan-out: every lane merges its terminal range against the child intervals,
+            // votes in the shared-memory counters
+            uint32_t u_local = 0;
+            if (has) {
+                uint32_t pos = lo, npres = 0, lastc = 0, ord = 0, cend = __ldg(&ix.qinfo[p + 1].q_end);
+                while (pos < hi) {
+                    const uint32_t t = __ldg(terms + pos);
+                    while (t >= cend) { cend = __ldg(&ix.qinfo[cend].q_end); ++ord; }
+                    atomicAdd(&tb.cnt[ord], w); ++npres; lastc = ord;
+                    ++pos;
+                    if (pos < hi && __ldg(terms + pos) < cend) pos = lower_bound_terms(terms, pos, hi, cend);
+                }
+                u_local = w;
+                if (npres == 1) atomicAdd(&tb.excl[lastc], w);
+            }
+            const uint32_t U = __reduce_add_sync(kFull, u_local);
+            __syncwarp();
+            const Decision dc = decide_smem(tb.cnt, tb.excl, m, U, ri);
+            __syncwarp();
+            for (uint32_t o = lane; o < m; o += 32) { tb.cnt[o] = 0; tb.excl[o] = 0; }
+            __syncwarp();
+            nprop = dc.nprop; n_best = dc.n_best; win_one = dc.best_one; win_rest = dc.best_rest;
+            win_q = p + 1;
+            for (uint32_t o = 0; o < dc.best_ord; ++o) win_q = __ldg(&ix.qinfo[win_q].q_end);
+            iw = ld_qinfo(ix.qinfo, win_q);
+        }
+        if (nprop == 0) {
+            if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
+            else { res.status = CLS_DEV_MAX_RESOLUTION; res.node_id = ix.q_node_id[p]; }
+            break;
+        }
+        if (n_best != 1) { res.status = CLS_DEV_INCONCLUSIVE; res.node_id = ix.q_node_id[p]; break; }
+        if (iw.child_count == 0) {  // update_introspection_node.rs:32-87
+            res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[win_q];
+            res.one = win_one; res.rest = win_rest;
+            break;
+        }
+        p = win_q; ip = iw; depth_p++;
+        const uint32_t win_end = iw.q_end;
+        // every live set keeps its terminals inside the winner's interval (or drops out)
+        bool live = has && last >= win_q && first < win_end;
+        if (live && first < win_q) {
+            lo = lower_bound_terms(terms, lo + 1, hi, win_q);
+            first = __ldg(terms + lo);  // lo < hi because last >= win_q
+            live = first < win_end;
+        }
+        if (live && last >= win_end) {
+            hi = lower_bound_terms(terms, lo + 1, hi - 1, win_end);  // terms[lo] < win_end
+            last = __ldg(terms + hi - 1);
+        }
+        if (!live) w = 0;
+    }
+    res.iterations = (uint32_t)iteration;
+    if (lane == 0) *out = res;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -716,6 +868,146 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
 }
 
 // ------------------------------------------------------------------------------------------
+// Short reads, k = 35: the scan kernel (one warp per read: decode, hash, probe, de-duplicate,
+// histogram by node set) and the descent kernel (one thread per read).  The scan loop is unrolled
+// over the two halves of the pre-mix ring so that every shared-memory address of a pass is a
+// per-lane constant: pass c hashes windows 32c + lane from the pre-mixes at offsets pos, pos + 8,
+// pos + 16, pos + 24 and meanwhile pre-mixes offsets 32(c + 1) + lane into the other half.
+// Reads with more distinct node sets than the scratch holds per read (or any read of a model that
+// is not closed) are finished by their scan warp with finish_read.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void premix_store(const uint32_t *w, uint32_t sh8, uint64_t *ra, uint64_t *rb) {
+    const uint32_t r0 = w[0], r1 = w[1], r2 = w[2];
+    const uint64_t x = pack64(__funnelshift_r(r0, r1, sh8), __funnelshift_r(r1, r2, sh8));
+    *ra = premix_k1(x);
+    *rb = premix_k2(x);
+}
+
+__device__ __forceinline__ uint64_t window_hash35(uint64_t a0, uint64_t b1, uint64_t a2, uint64_t b3, uint64_t tail) {
+    uint64_t h1 = mul5add(rotlc<27>(a0), 0x52dce729u);
+    uint64_t h2 = mul5add(rotlc<31>(b1) + h1, 0x38495ab5u);
+    h1 = mul5add(rotlc<27>(h1 ^ a2) + h2, 0x52dce729u);
+    h2 = mul5add(rotlc<31>(h2 ^ b3) + h1, 0x38495ab5u);
+    return mm_finish(h1 ^ tail, h2, 35ull);
+}
+
+#ifndef CLS_SCAN_MINB
+#define CLS_SCAN_MINB 4
+#endif
+template <bool CLOSED>
+__global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix, PlaceParams pp, const uint32_t *__restrict__ packed,
+                                                      const ReadDesc *__restrict__ reads, uint32_t first_read,
+                                                      uint32_t n_reads, ResultRec *__restrict__ results, PlaceGeom g) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint64_t tail_lut[64];
+    init_tail_lut(tail_lut);
+    const uint32_t lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t warps_per_cta = blockDim.x >> 5;
+    uint32_t *gbase = smem + 4 * kRing * warps_per_cta + (size_t)warp * g.words_per_warp;
+    uint64_t *ring_a = reinterpret_cast<uint64_t *>(smem + 4 * kRing * warp), *ring_b = ring_a + kRing;
+    WarpMem wm;
+    wm.ring_a = ring_a; wm.ring_b = ring_b;
+    uint32_t *t1 = gbase, *t2k = t1 + g.t1_size, *t2c = t2k + g.t2_size, *lst = t2c + g.t2_size;
+    wm.str_f = lst + g.t2_size;
+    wm.str_r = wm.str_f + g.str_words;
+    wm.pk_f = wm.str_r + g.str_words;
+    wm.pk_r = wm.pk_f + g.pk_words;
+    uint32_t *cnt = wm.pk_r + g.pk_words, *excl = cnt + g.fan_cap, *n_sets_smem = excl + g.fan_cap;
+    const ReadTables tb{t1, t2k, t2c, lst, cnt, excl, n_sets_smem, g.t1_size - 1u, g.t2_size - 1u, 32u - g.t2_log2};
+    const uint32_t code_mask = ix.m_eff >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ix.m_eff)) - 1u);
+    const uint32_t bmask = (uint32_t)ix.bucket_mask;  // at most 2^30 buckets (cls_index_create)
+    // per-lane constants of the hashing loop
+    const uint32_t sh8 = (lane & 3u) * 8u, sh2 = (lane & 15u) * 2u;
+    uint64_t *const ra0 = ring_a + lane, *const rb0 = ring_b + lane;
+    const uint64_t *const rb_o1 = ring_b + ((lane + 40u) & 63u), *const ra_o2 = ring_a + ((lane + 48u) & 63u),
+                   *const rb_o3 = ring_b + ((lane + 56u) & 63u);
+
+    for (uint32_t o = lane; o < g.fan_cap; o += 32) { cnt[o] = 0; excl[o] = 0; }
+    __syncthreads();
+
+    const uint32_t gwarp = blockIdx.x * warps_per_cta + warp, gstride = gridDim.x * warps_per_cta;
+#pragma unroll 1
+    for (uint32_t r = gwarp; r < n_reads; r += gstride) {
+        const ReadDesc rd = reads[first_read + r];
+        const uint32_t L = rd.len;
+        const uint32_t W = L - 34u;  // host guarantees L >= k = 35
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(t1);
+            const uint32_t n4 = (g.t1_size + g.t2_size) >> 2;  // t1 and t2k are contiguous: all kEmpty
+            for (uint32_t i = lane; i < n4; i += 32) z[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+            uint4 *zc = reinterpret_cast<uint4 *>(t2c);
+            for (uint32_t i = lane; i < (g.t2_size >> 2); i += 32) zc[i] = make_uint4(0, 0, 0, 0);
+            if (lane == 0) *n_sets_smem = 0;
+        }
+        decode_read(packed + rd.word_off, L, wm, g.pk_words);
+        const uint32_t n_chunks = (W + 31u) >> 5;
+        uint32_t n_matched = 0;
+#pragma unroll 1
+        for (uint32_t strand = 0; strand < 2; ++strand) {
+            const uint32_t *pk = strand ? wm.pk_r : wm.pk_f;
+            const uint32_t *wsrc = (strand ? wm.str_r : wm.str_f) + (lane >> 2);  // + 8 words per 32 offsets
+            const uint32_t *pkl = pk + (lane >> 4);                               // + 2 words per 32 bases
+            // probe the table with the hash of window `pos`, gate, and add the hit to the read's tables
+            auto process = [&](uint32_t pos, uint64_t h) {
+                const bool valid = pos < W;
+                uint64_t h0, m0, h1, m1;
+                uint32_t b = valid ? (uint32_t)h & bmask : 0u;  // lanes past the last window load bucket 0 and ignore it
+                ld_bucket(ix.table, b, h0, m0, h1, m1);
+                bool e0 = h0 == h && (uint32_t)m0 != kEmpty, e1 = h1 == h && (uint32_t)m1 != kEmpty;
+                if (valid && !(e0 || e1) && ((uint32_t)(m0 >> 32) & kOverflowBit)) {  // the bucket overflowed at build time
+                    do {
+                        b = (b + 1) & bmask;
+                        ld_bucket(ix.table, b, h0, m0, h1, m1);
+                        e0 = h0 == h && (uint32_t)m0 != kEmpty; e1 = h1 == h && (uint32_t)m1 != kEmpty;
+                    } while (!(e0 || e1) && ((uint32_t)(m0 >> 32) & kOverflowBit));
+                }
+                const uint64_t mm = e0 ? m0 : m1;
+                bool hit = valid && (e0 || e1);
+                if (hit) {
+                    // bucket gating: the entry's bucket key must be among the query's prefix keys
+                    const uint32_t want = (uint32_t)(mm >> 32) & kCodeMask;
+                    hit = packed_bits(pk, pos, code_mask) == want;
+                    if (!hit) {  // only possible for models whose bucket keys disagree with their k-mers
+                        for (uint32_t q = 0; q < W && !hit; ++q)
+                            hit = packed_bits(wm.pk_f, q, code_mask) == want || packed_bits(wm.pk_r, q, code_mask) == want;
+                    }
+                }
+                n_matched += insert_hits(tb, hit, 2u * b + (e0 ? 0u : 1u), (uint32_t)mm);
+            };
+            __syncwarp();
+            premix_store(wsrc, sh8, ra0, rb0);  // offsets 0..31 -> ring half 0
+#pragma unroll 1
+            for (uint32_t c = 0; c < n_chunks; c += 2) {
+                {   // even pass: windows 32c + lane; offsets 32(c+1) + lane -> ring half 1
+                    premix_store(wsrc + 8 * (c + 1), sh8, ra0 + 32, rb0 + 32);
+                    __syncwarp();
+                    const uint64_t a0 = ra0[0], b1 = rb0[8], a2 = ra0[16], b3 = rb0[24];
+                    const uint32_t ti = __funnelshift_r(pkl[2 * c + 2], pkl[2 * c + 3], sh2) & 63u;
+                    const uint64_t h = window_hash35(a0, b1, a2, b3, tail_lut[ti]);
+                    __syncwarp();
+                    process(32u * c + lane, h);
+                }
+                if (c + 1 < n_chunks) {  // odd pass: windows 32(c+1) + lane; offsets 32(c+2) + lane -> ring half 0
+                    premix_store(wsrc + 8 * (c + 2), sh8, ra0, rb0);
+                    __syncwarp();
+                    const uint64_t a0 = ra0[32], b1 = *rb_o1, a2 = *ra_o2, b3 = *rb_o3;
+                    const uint32_t ti = __funnelshift_r(pkl[2 * c + 4], pkl[2 * c + 5], sh2) & 63u;
+                    const uint64_t h = window_hash35(a0, b1, a2, b3, tail_lut[ti]);
+                    __syncwarp();
+                    process(32u * (c + 1) + lane, h);
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t D = *n_sets_smem;
+        if (CLOSED && D <= 32) finish_read_reg(ix, pp, tb, D, n_matched, results + first_read + r);
+        else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host launchers
 // ------------------------------------------------------------------------------------------
 static inline uint32_t ceil_log2(uint32_t x) {
@@ -779,12 +1071,40 @@ static cudaError_t launch_place_m(const DeviceIndex &ix, const PlaceParams &pp, 
                           : launch_place_t<K, CLOSED, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
 }
 
+// ---- short reads, k = 35: the scan kernel ---------------------------------------------------
+template <bool CLOSED>
+static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
+                                 const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
+                                 const PlaceGeom &g, int sm_count, cudaStream_t stream) {
+    const size_t ring = (size_t)4 * kRing * 4, group = (size_t)g.words_per_warp * 4;
+    int warps = 8;
+    while (warps > 1 && (group + ring) * warps > 200 * 1024) warps >>= 1;
+    const size_t smem = (group + ring) * warps;
+    if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<CLOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<CLOSED>, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    uint32_t grid = (uint32_t)(sm_count * occ);
+    const uint32_t need = (n_reads + warps - 1) / warps;
+    if (grid > need) grid = need;
+    scan_kernel<CLOSED><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                          const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
                          const PlaceGeom &g, int sm_count, cudaStream_t stream) {
+    if (n_reads == 0) return cudaSuccess;
+    if (ix.k_size == 35 && !g.cta_per_read) {
+        return ix.closed ? launch_scan_t<true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
+                         : launch_scan_t<false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+    }
     if (ix.k_size == 35) {
-        return ix.closed ? launch_place_m<35, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
-                         : launch_place_m<35, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+        return ix.closed ? launch_place_t<35, true, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
+                         : launch_place_t<35, false, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
     }
     return ix.closed ? launch_place_m<0, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
                      : launch_place_m<0, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
