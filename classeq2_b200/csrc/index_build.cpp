@@ -373,7 +373,10 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
 
     // ---- open-addressed table: 32-byte buckets of two slots, load factor in (0.25, 0.5] ----------
     uint64_t nb = 1;
-    while (nb < kept.size()) nb <<= 1;
+    {
+        static const int shift = [] { const char *e = getenv("CLS_TABLE_SHIFT"); return e ? atoi(e) : 0; }();
+        while (nb < (kept.size() << shift)) nb <<= 1;
+    }
     out.n_buckets = nb;
     out.table.assign(2 * nb, Slot{0, kEmpty, 0});
     const uint64_t mask = nb - 1;

@@ -948,12 +948,9 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
             const uint32_t *pk = strand ? wm.pk_r : wm.pk_f;
             const uint32_t *wsrc = (strand ? wm.str_r : wm.str_f) + (lane >> 2);  // + 8 words per 32 offsets
             const uint32_t *pkl = pk + (lane >> 4);                               // + 2 words per 32 bases
-            // probe the table with the hash of window `pos`, gate, and add the hit to the read's tables
-            auto process = [&](uint32_t pos, uint64_t h) {
+            // match the bucket loaded for window `pos` against its hash, gate, and add the hit to the read's tables
+            auto consume = [&](uint32_t pos, uint64_t h, uint32_t b, uint64_t h0, uint64_t m0, uint64_t h1, uint64_t m1) {
                 const bool valid = pos < W;
-                uint64_t h0, m0, h1, m1;
-                uint32_t b = valid ? (uint32_t)h & bmask : 0u;  // lanes past the last window load bucket 0 and ignore it
-                ld_bucket(ix.table, b, h0, m0, h1, m1);
                 bool e0 = h0 == h && (uint32_t)m0 != kEmpty, e1 = h1 == h && (uint32_t)m1 != kEmpty;
                 if (valid && !(e0 || e1) && ((uint32_t)(m0 >> 32) & kOverflowBit)) {  // the bucket overflowed at build time
                     do {
@@ -977,26 +974,36 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
             };
             __syncwarp();
             premix_store(wsrc, sh8, ra0, rb0);  // offsets 0..31 -> ring half 0
+            // two passes per iteration: the ring loads of both are done first, then the two hash chains
+            // run interleaved (independent instruction streams), their two probes are in flight together,
+            // and the two results are consumed one after the other
 #pragma unroll 1
             for (uint32_t c = 0; c < n_chunks; c += 2) {
-                {   // even pass: windows 32c + lane; offsets 32(c+1) + lane -> ring half 1
-                    premix_store(wsrc + 8 * (c + 1), sh8, ra0 + 32, rb0 + 32);
+                const bool two = c + 1 < n_chunks;  // warp-uniform
+                const uint32_t posA = 32u * c + lane, posB = posA + 32u;
+                premix_store(wsrc + 8 * (c + 1), sh8, ra0 + 32, rb0 + 32);  // offsets 32(c+1) + lane -> ring half 1
+                __syncwarp();
+                const uint64_t a0 = ra0[0], b1 = rb0[8], a2 = ra0[16], b3 = rb0[24];
+                const uint32_t tiA = __funnelshift_r(pkl[2 * c + 2], pkl[2 * c + 3], sh2) & 63u;
+                __syncwarp();
+                uint64_t e0 = 0, f1 = 0, e2 = 0, f3 = 0;
+                uint32_t tiB = 0;
+                if (two) {
+                    premix_store(wsrc + 8 * (c + 2), sh8, ra0, rb0);        // offsets 32(c+2) + lane -> ring half 0
                     __syncwarp();
-                    const uint64_t a0 = ra0[0], b1 = rb0[8], a2 = ra0[16], b3 = rb0[24];
-                    const uint32_t ti = __funnelshift_r(pkl[2 * c + 2], pkl[2 * c + 3], sh2) & 63u;
-                    const uint64_t h = window_hash35(a0, b1, a2, b3, tail_lut[ti]);
+                    e0 = ra0[32]; f1 = *rb_o1; e2 = *ra_o2; f3 = *rb_o3;
+                    tiB = __funnelshift_r(pkl[2 * c + 4], pkl[2 * c + 5], sh2) & 63u;
                     __syncwarp();
-                    process(32u * c + lane, h);
                 }
-                if (c + 1 < n_chunks) {  // odd pass: windows 32(c+1) + lane; offsets 32(c+2) + lane -> ring half 0
-                    premix_store(wsrc + 8 * (c + 2), sh8, ra0, rb0);
-                    __syncwarp();
-                    const uint64_t a0 = ra0[32], b1 = *rb_o1, a2 = *ra_o2, b3 = *rb_o3;
-                    const uint32_t ti = __funnelshift_r(pkl[2 * c + 4], pkl[2 * c + 5], sh2) & 63u;
-                    const uint64_t h = window_hash35(a0, b1, a2, b3, tail_lut[ti]);
-                    __syncwarp();
-                    process(32u * (c + 1) + lane, h);
-                }
+                const uint64_t hA = window_hash35(a0, b1, a2, b3, tail_lut[tiA]);
+                const uint64_t hB = window_hash35(e0, f1, e2, f3, tail_lut[tiB]);
+                // lanes past the last window load bucket 0 and ignore it
+                const uint32_t bA = posA < W ? (uint32_t)hA & bmask : 0u, bB = (two && posB < W) ? (uint32_t)hB & bmask : 0u;
+                uint64_t A0, A1, A2, A3, B0, B1, B2, B3;
+                ld_bucket(ix.table, bA, A0, A1, A2, A3);
+                ld_bucket(ix.table, bB, B0, B1, B2, B3);
+                consume(posA, hA, bA, A0, A1, A2, A3);
+                if (two) consume(posB, hB, bB, B0, B1, B2, B3);
             }
         }
         __syncwarp();
