@@ -94,6 +94,11 @@ PROTOTYPES = {
     "cls_resident_destroy": (None, [C.c_void_p]),
     "cls_resident_bytes": (C.c_uint64, [C.c_void_p]),
     "cls_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "cls_index_create_shard": (C.c_int, [C.POINTER(ModelView), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "cls_routed_windows": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
+    "cls_route_hashes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, u64p, C.c_void_p]),
+    "cls_shard_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "cls_place_routed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p]),
     "cls_debug_kmer_hashes": (C.c_int, [C.c_int, C.c_uint32, u8p, C.c_uint64, u64p, C.c_uint64, u64p]),
     "cls_debug_host_murmur3_x64_128_h1": (C.c_uint64, [u8p, C.c_uint64, C.c_uint64]),
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),

@@ -115,6 +115,7 @@ struct Workspace {
 struct cls_index {
     int device = 0;
     int sm_count = 0;
+    uint32_t shard = 0, n_shards = 1;  // hash-sharded index: this handle holds the table entries of one shard
     DevBuf d_table, d_arena, d_terms, d_qnodes, d_qchild, d_qid, d_qinfo, d_lca;
     DeviceIndex dix{};
     cls_index_info info{};
@@ -127,6 +128,8 @@ struct cls_resident_batch {
     int device = 0;
     PackedLayout lay;
     DevBuf d_words, d_descs, d_results;
+    DevBuf d_win_base, d_route_state;  // routed path: first window of every read; per-owner cursors + overflow flag
+    uint64_t n_windows = 0;
     PinBuf h_results;
 };
 
@@ -347,13 +350,19 @@ int cls_device_count(void) {
 }
 
 int cls_index_create(const cls_model_view *model, int device, cls_index **out) {
+    return cls_index_create_shard(model, device, 0, 1, out);
+}
+
+int cls_index_create_shard(const cls_model_view *model, int device, uint32_t shard, uint32_t n_shards, cls_index **out) {
     if (!out) return fail(CLS_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
+    if (n_shards == 0 || n_shards > kMaxShards || shard >= n_shards)
+        return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8 and shard < n_shards");
     HostIndex h;
     std::string err;
-    int rc = build_host_index(model, h, err);
+    int rc = build_host_index(model, h, err, shard, n_shards);
     if (rc != CLS_OK) return fail(rc, err);
-    if (h.n_buckets > (1ull << 30)) return fail(CLS_ERR_UNSUPPORTED, "k-mer table larger than 2^30 buckets");
+    if (h.n_buckets > (1ull << (n_shards > 1 ? 28 : 30))) return fail(CLS_ERR_UNSUPPORTED, "k-mer table too large (2^30 buckets, 2^28 per shard)");
 
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -363,6 +372,8 @@ int cls_index_create(const cls_model_view *model, int device, cls_index **out) {
     auto ix = std::make_unique<cls_index>();
     ix->device = device;
     ix->sm_count = prop.multiProcessorCount;
+    ix->shard = shard;
+    ix->n_shards = n_shards;
     auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = b.reserve(std::max<size_t>(bytes, 16));
         if (e != cudaSuccess) return e;
@@ -431,6 +442,7 @@ int cls_index_get_info(const cls_index *ix, cls_index_info *info) {
 
 int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) {
     if (!ix || !batch || !params || !result) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
     const double t0 = now_ms();
     CU_TRY(cudaSetDevice(ix->device));
     Workspace *w = acquire_ws(ix);
@@ -544,6 +556,7 @@ int cls_batch_upload(cls_index *ix, const cls_batch *batch, cls_resident_batch *
 int cls_place_resident(cls_index *ix, cls_resident_batch *rb, const cls_params *params, void *stream) {
     if (!ix || !rb || !params) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (rb->device != ix->device) return fail(CLS_ERR_INVALID_ARGUMENT, "resident batch lives on another device");
+    if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
     CU_TRY(cudaSetDevice(ix->device));
     uint64_t launches = 0;
     int rc = launch_classes(ix, rb->lay, params, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p,
@@ -568,12 +581,91 @@ void cls_resident_destroy(cls_resident_batch *rb) {
     if (!rb) return;
     cudaSetDevice(rb->device);
     rb->d_words.release(); rb->d_descs.release(); rb->d_results.release(); rb->h_results.release();
+    rb->d_win_base.release(); rb->d_route_state.release();
     delete rb;
 }
 
 uint64_t cls_resident_bytes(const cls_resident_batch *rb) {
     if (!rb) return 0;
     return (uint64_t)rb->lay.n_words * 4 + (uint64_t)rb->lay.n_device * (sizeof(ReadDesc) + sizeof(ResultRec));
+}
+
+// ---- hash-sharded index: route -> (all-to-all) -> probe -> (all-to-all) -> place --------------------
+int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_windows) {
+    if (!ix || !rb || !n_windows) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU_TRY(cudaSetDevice(ix->device));
+    if (!rb->d_win_base.p) {
+        const PackedLayout &lay = rb->lay;
+        const uint32_t k = ix->dix.k_size;
+        std::vector<uint64_t> base((size_t)lay.n_device + 1);
+        uint64_t acc = 0;
+        for (uint32_t j = 0; j < lay.n_device; ++j) {
+            base[j] = acc;
+            acc += 2ull * (lay.lens[lay.perm[j]] - k + 1);
+        }
+        base[lay.n_device] = acc;
+        CU_TRY(rb->d_win_base.reserve(base.size() * 8));
+        CU_TRY(cudaMemcpy(rb->d_win_base.p, base.data(), base.size() * 8, cudaMemcpyHostToDevice));
+        CU_TRY(rb->d_route_state.reserve(256));
+        rb->n_windows = acc;
+    }
+    *n_windows = rb->n_windows;
+    return CLS_OK;
+}
+
+int cls_route_hashes(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *d_send,
+                     void *d_win_slot, uint64_t *counts_out, void *stream) {
+    if (!ix || !rb || !d_send || !d_win_slot || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
+    if ((uint64_t)n_shards * seg_cap >= 0xFFFFFFFFull) return fail(CLS_ERR_UNSUPPORTED, "send buffer beyond 2^32 entries: split the batch");
+    uint64_t nw = 0;
+    int rc = cls_routed_windows(ix, rb, &nw);
+    if (rc != CLS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *cursor = (unsigned long long *)rb->d_route_state.p;
+    uint32_t *overflow = (uint32_t *)((char *)rb->d_route_state.p + 64);
+    CU_TRY(cudaMemsetAsync(rb->d_route_state.p, 0, 128, st));
+    for (const LengthClass &c : rb->lay.classes) {
+        PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
+        cudaError_t e = launch_route(ix->dix.k_size, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p, c.first, c.count, g,
+                                     (const uint64_t *)rb->d_win_base.p, n_shards, seg_cap, (uint64_t *)d_send, (uint32_t *)d_win_slot,
+                                     cursor, overflow, ix->sm_count, st);
+        if (e == cudaErrorInvalidConfiguration)
+            return fail(CLS_ERR_UNSUPPORTED, "the routed path places reads of up to 161 bases (the one-warp-per-read geometry)");
+        if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("route kernel launch: ") + cudaGetErrorString(e));
+    }
+    uint64_t state[16];
+    CU_TRY(cudaMemcpyAsync(state, rb->d_route_state.p, 128, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if ((uint32_t)state[8]) return fail(CLS_ERR_OUT_OF_MEMORY, "a shard's segment of the send buffer is too small (seg_cap)");
+    for (uint32_t o = 0; o < n_shards; ++o) counts_out[o] = state[o];
+    return CLS_OK;
+}
+
+int cls_shard_probe(cls_index *ix, const void *d_hashes, uint64_t n, void *d_replies, void *stream) {
+    if (!ix || (n && (!d_hashes || !d_replies))) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaError_t e = launch_shard_probe(ix->dix, ix->shard, (const uint64_t *)d_hashes, n, d_replies, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("probe kernel launch: ") + cudaGetErrorString(e));
+    return CLS_OK;
+}
+
+int cls_place_routed(cls_index *ix, cls_resident_batch *rb, const void *d_replies, const void *d_win_slot,
+                     const cls_params *params, void *stream) {
+    if (!ix || !rb || !params || !d_replies || !d_win_slot) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!rb->d_win_base.p) return fail(CLS_ERR_INVALID_ARGUMENT, "cls_route_hashes has not run on this batch");
+    CU_TRY(cudaSetDevice(ix->device));
+    const PlaceParams pp = make_place_params(params);
+    for (const LengthClass &c : rb->lay.classes) {
+        PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
+        cudaError_t e = launch_place_routed(ix->dix, pp, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p, c.first, c.count,
+                                            (ResultRec *)rb->d_results.p, g, (const uint64_t *)rb->d_win_base.p,
+                                            (const uint32_t *)d_win_slot, d_replies, ix->sm_count, (cudaStream_t)stream);
+        if (e == cudaErrorInvalidConfiguration)
+            return fail(CLS_ERR_UNSUPPORTED, "the routed path places reads of up to 161 bases (the one-warp-per-read geometry)");
+        if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("routed place kernel launch: ") + cudaGetErrorString(e));
+    }
+    return CLS_OK;
 }
 
 int cls_get_timing(const cls_index *ix, cls_timing *out) {

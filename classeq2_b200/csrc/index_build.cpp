@@ -35,7 +35,7 @@ inline uint64_t mix64(uint64_t x) { return fmix64_h(x + 0x9e3779b97f4a7c15ULL); 
 
 }  // namespace
 
-int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err) {
+int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err, uint32_t shard, uint32_t n_shards) {
     if (!mv) { err = "model view is NULL"; return CLS_ERR_INVALID_ARGUMENT; }
     if (mv->k_size == 0) { err = "k_size == 0 is not supported"; return CLS_ERR_UNSUPPORTED; }
     if (mv->m_size > 12) { err = "m_size > 12 is not supported (prefix code table would exceed 4^12)"; return CLS_ERR_UNSUPPORTED; }
@@ -351,6 +351,7 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
     for (uint64_t i = 0; i < mv->n_entries; ++i) {
         auto it = key_code.find(mv->entry_bucket[i]);
         if (it == key_code.end()) continue;  // unreachable bucket: no ACGT query can produce this key
+        if (n_shards > 1 && (uint32_t)(mv->entry_hash[i] >> 61) % n_shards != shard) continue;  // another GPU owns it
         uint64_t s = mv->entry_set[i];
         if (s >= n_sets) { err = "entry_set out of range"; return CLS_ERR_INVALID_ARGUMENT; }
         kept.push_back(KeptEntry{mv->entry_hash[i], mv->entry_bucket[i], set_arena_off[s], it->second});
@@ -373,10 +374,7 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err)
 
     // ---- open-addressed table: 32-byte buckets of two slots, load factor in (0.25, 0.5] ----------
     uint64_t nb = 1;
-    {
-        static const int shift = [] { const char *e = getenv("CLS_TABLE_SHIFT"); return e ? atoi(e) : 0; }();
-        while (nb < (kept.size() << shift)) nb <<= 1;
-    }
+    while (nb < kept.size()) nb <<= 1;
     out.n_buckets = nb;
     out.table.assign(2 * nb, Slot{0, kEmpty, 0});
     const uint64_t mask = nb - 1;

@@ -31,6 +31,8 @@ struct HostIndex {
 };
 
 // Returns CLS_OK or a negative cls_error; `err` receives the message.
-int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err);
+// Only the entries with (hash >> 61) % n_shards == shard go into the table (hash-sharded index);
+// node-set records and the tree are always complete.
+int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err, uint32_t shard = 0, uint32_t n_shards = 1);
 
 }  // namespace cls

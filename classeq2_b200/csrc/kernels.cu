@@ -1135,4 +1135,6 @@ cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, u
     return cudaGetLastError();
 }
 
+#include "routed_kernels.cuh"
+
 }  // namespace cls

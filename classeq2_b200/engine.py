@@ -89,14 +89,19 @@ def _c_batch(bases: np.ndarray, offsets: np.ndarray) -> _lib.Batch:
 class Index:
     """A model serialised to one GPU (``cls_index_create``): upload once per model."""
 
-    def __init__(self, model: Union[FlatModel, Tree, "_lib.ModelView"], device: int = 0, keepalive=None):
+    def __init__(self, model: Union[FlatModel, Tree, "_lib.ModelView"], device: int = 0, keepalive=None,
+                 shard: int = 0, n_shards: int = 1):
+        """``n_shards > 1``: this handle holds the k-mer table entries with ``(hash >> 61) % n_shards ==
+        shard`` only (``cls_index_create_shard``); such a handle serves the routed calls of
+        :mod:`classeq2_b200.parallel` and refuses ``place_batch``."""
         if isinstance(model, Tree):
             model = FlatModel.from_tree(model)
         view = model.view if hasattr(model, "view") else model
         self._keep = (model, keepalive)
         self._h = C.c_void_p()
-        _lib.check(_lib.lib.cls_index_create(C.byref(view), int(device), C.byref(self._h)))
+        _lib.check(_lib.lib.cls_index_create_shard(C.byref(view), int(device), int(shard), int(n_shards), C.byref(self._h)))
         self.device = int(device)
+        self.shard, self.n_shards = int(shard), int(n_shards)
 
     def info(self) -> dict:
         inf = _lib.IndexInfo()
@@ -119,6 +124,10 @@ class Index:
 
     def upload(self, seqs) -> "ResidentBatch":
         return ResidentBatch(self, seqs)
+
+    def shard_probe(self, d_hashes: int, n: int, d_replies: int, stream: int = 0) -> None:
+        """``cls_shard_probe``: answer ``n`` received hashes (device pointers) from this shard of the table."""
+        _lib.check(_lib.lib.cls_shard_probe(self._h, C.c_void_p(d_hashes), int(n), C.c_void_p(d_replies), C.c_void_p(stream)))
 
     def timing(self) -> dict:
         t = _lib.Timing()
@@ -161,6 +170,26 @@ class ResidentBatch:
 
     def nbytes(self) -> int:
         return int(_lib.lib.cls_resident_bytes(self._h))
+
+    # ---- hash-sharded index: the three device stages around the two all-to-alls --------------------
+    def routed_windows(self) -> int:
+        """Number of k-mer windows (2 * (L - k + 1) summed over the reads on the device)."""
+        n = C.c_uint64()
+        _lib.check(_lib.lib.cls_routed_windows(self.index._h, self._h, C.byref(n)))
+        return int(n.value)
+
+    def route_hashes(self, n_shards: int, seg_cap: int, d_send: int, d_win_slot: int, stream: int = 0) -> np.ndarray:
+        """``cls_route_hashes``: fills the caller's device buffers (raw pointers) and returns the number
+        of hashes routed to every owner."""
+        counts = np.zeros(8, dtype=np.uint64)
+        _lib.check(_lib.lib.cls_route_hashes(self.index._h, self._h, int(n_shards), int(seg_cap), C.c_void_p(d_send),
+                                             C.c_void_p(d_win_slot), _ptr(counts, _lib.u64p), C.c_void_p(stream)))
+        return counts[:n_shards].copy()
+
+    def place_routed(self, d_replies: int, d_win_slot: int, params: Optional[PlaceParams] = None, stream: int = 0) -> None:
+        cp = (params or PlaceParams()).to_c()
+        _lib.check(_lib.lib.cls_place_routed(self.index._h, self._h, C.c_void_p(d_replies), C.c_void_p(d_win_slot),
+                                             C.byref(cp), C.c_void_p(stream)))
 
     def close(self):
         if self._h:

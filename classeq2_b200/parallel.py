@@ -57,3 +57,158 @@ def gather_results(local: BatchResult, n_total: int, group=None, dst: int = 0) -
             full = torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)]).cpu().numpy().view(arr.dtype)
             getattr(out, name)[:] = full
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Hash-sharded index (config 5 of BASELINE.json): the k-mer table is split over
+# the GPUs by ``owner = (hash >> 61) % world`` and the query k-mers are routed to their owner with an
+# all-to-all over NVLink (NCCL).  One process per GPU; every rank is "home" for its own reads and
+# "owner" of one shard of the table.
+# --------------------------------------------------------------------------------------------------
+REPLY_BYTES = 12   # cls_probe_reply
+
+
+def owner_of(hashes: np.ndarray, n_shards: int) -> np.ndarray:
+    """Owner shard of every 64-bit k-mer hash: the top three bits modulo the number of shards."""
+    return ((hashes.astype(np.uint64) >> np.uint64(61)) % np.uint64(n_shards)).astype(np.int64)
+
+
+def exchange_plan(counts_to: np.ndarray, group=None) -> np.ndarray:
+    """All-to-all of the per-owner request counts: returns ``counts_from[s]`` = how many hashes rank
+    ``s`` sends to this rank.  Works on nccl (device tensors) and gloo (CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t_in = torch.from_numpy(counts_to.astype(np.int64)).to(dev)
+    t_out = torch.empty_like(t_in)
+    dist.all_to_all_single(t_out, t_in, group=group)
+    return t_out.cpu().numpy().astype(np.int64)
+
+
+def exchange_segments(send_views, recv_views, group=None) -> None:
+    """One all-to-all of ragged per-peer segments (lists of 1-D tensors, one per rank).  NCCL takes
+    the views as they are (grouped send/recv over NVLink, no staging copy); gloo has no list
+    all-to-all, so on CPU the segments are packed, exchanged with ``all_to_all_single`` and unpacked."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv_views, send_views, group=group)
+        return
+    packed_in = torch.cat(send_views) if send_views else None
+    packed_out = torch.empty(sum(v.numel() for v in recv_views), dtype=packed_in.dtype)
+    dist.all_to_all_single(packed_out, packed_in, [v.numel() for v in recv_views], [v.numel() for v in send_views], group=group)
+    at = 0
+    for v in recv_views:
+        v.copy_(packed_out[at: at + v.numel()])
+        at += v.numel()
+
+
+def segment_views(buf, counts: np.ndarray, seg_cap: int = 0, item: int = 1):
+    """Per-peer 1-D views of ``buf``: peer ``o`` owns ``counts[o] * item`` elements starting at
+    ``o * seg_cap * item`` (fixed-capacity segments) or, with ``seg_cap == 0``, packed back to back."""
+    if seg_cap:
+        return [buf[o * seg_cap * item: (o * seg_cap + int(c)) * item] for o, c in enumerate(counts)]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return [buf[int(off[o]) * item: int(off[o + 1]) * item] for o in range(len(counts))]
+
+
+class ShardedPlacer:
+    """Placement against a hash-sharded index, one instance per rank.
+
+    ``place(seqs)``: route_hashes -> all-to-all (hashes, 8 B each) -> shard_probe -> all-to-all back
+    (replies, 12 B each) -> place_routed.  The three compute stages are the library's CUDA kernels
+    (``cls_route_hashes`` / ``cls_shard_probe`` / ``cls_place_routed``); the exchanges are
+    ``torch.distributed`` collectives on the same device buffers.  With ``world == 1`` no process
+    group is needed (everything is local)."""
+
+    def __init__(self, model, device: int, rank: int, world: int, group=None, slack: float = 1.15):
+        from .engine import Index
+
+        self.rank, self.world, self.group, self.slack = rank, world, group, slack
+        self.index = Index(model, device=device, shard=rank, n_shards=world)
+        self.device = device
+        self.timing = {}
+
+    def place(self, seqs, params=None) -> BatchResult:
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        rb = self.index.upload(seqs)
+        st = torch.cuda.current_stream(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        nw = rb.routed_windows()
+        world = self.world
+        seg_cap = int(nw / world * self.slack) + 65536
+        send = torch.empty(world * seg_cap, dtype=torch.int64, device=dev)
+        win_slot = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
+        ev[0].record(st)
+        counts_to = rb.route_hashes(world, seg_cap, send.data_ptr(), win_slot.data_ptr(), st.cuda_stream).astype(np.int64)
+        ev[1].record(st)
+        counts_from = exchange_plan(counts_to, self.group) if world > 1 else counts_to.copy()
+        n_recv = int(counts_from.sum())
+        recv = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
+        send_views, recv_views = segment_views(send, counts_to, seg_cap), segment_views(recv, counts_from)
+        if world > 1:
+            exchange_segments(send_views, recv_views, self.group)
+        else:
+            recv_views[0].copy_(send_views[0])
+        ev[2].record(st)
+        # owner side: answer everything received, in the order received
+        rep_out = torch.empty(max(n_recv, 1) * REPLY_BYTES, dtype=torch.uint8, device=dev)
+        self.index.shard_probe(recv.data_ptr(), n_recv, rep_out.data_ptr(), st.cuda_stream)
+        ev[3].record(st)
+        # replies travel back into a buffer laid out exactly like `send`
+        rep_in = torch.empty(world * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev)
+        back_send = segment_views(rep_out, counts_from, 0, REPLY_BYTES)
+        back_recv = segment_views(rep_in, counts_to, seg_cap, REPLY_BYTES)
+        if world > 1:
+            exchange_segments(back_send, back_recv, self.group)
+        else:
+            back_recv[0].copy_(back_send[0])
+        ev[4].record(st)
+        rb.place_routed(rep_in.data_ptr(), win_slot.data_ptr(), params, st.cuda_stream)
+        ev[5].record(st)
+        res = rb.fetch(st.cuda_stream)
+        names = ["route_ms", "send_ms", "probe_ms", "reply_ms", "place_ms"]
+        self.timing = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
+        remote_out = int(counts_to.sum() - counts_to[self.rank]), int(counts_from.sum() - counts_from[self.rank])
+        self.timing.update(n_windows=nw, routed_out=remote_out[0],
+                           wire_bytes_out=remote_out[0] * 8 + remote_out[1] * REPLY_BYTES)
+        rb.close()
+        return res
+
+
+class LocalShardedPlacer:
+    """The routed pipeline with ``n_shards`` table shards on ONE GPU and the two exchanges done as
+    local copies: the same kernels and buffer layouts as :class:`ShardedPlacer`, no process group.
+    Used by the parity tests (any ``n_shards`` on a single device)."""
+
+    def __init__(self, model, device: int, n_shards: int, slack: float = 1.15):
+        from .engine import Index
+
+        self.n_shards, self.device, self.slack = n_shards, device, slack
+        self.shards = [Index(model, device=device, shard=s, n_shards=n_shards) for s in range(n_shards)]
+
+    def place(self, seqs, params=None) -> BatchResult:
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        rb = self.shards[0].upload(seqs)
+        st = torch.cuda.current_stream(dev)
+        nw = rb.routed_windows()
+        seg_cap = int(nw / self.n_shards * self.slack) + 65536
+        send = torch.empty(self.n_shards * seg_cap, dtype=torch.int64, device=dev)
+        win_slot = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
+        counts = rb.route_hashes(self.n_shards, seg_cap, send.data_ptr(), win_slot.data_ptr(), st.cuda_stream)
+        assert int(counts.sum()) == nw
+        rep = torch.empty(self.n_shards * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev)
+        for o, ix in enumerate(self.shards):
+            ix.shard_probe(send.data_ptr() + o * seg_cap * 8, int(counts[o]), rep.data_ptr() + o * seg_cap * REPLY_BYTES,
+                           st.cuda_stream)
+        rb.place_routed(rep.data_ptr(), win_slot.data_ptr(), params, st.cuda_stream)
+        res = rb.fetch(st.cuda_stream)
+        self.last_counts, self.last_send = counts, (send, seg_cap)
+        rb.close()
+        return res

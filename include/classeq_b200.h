@@ -226,6 +226,40 @@ uint64_t cls_resident_bytes(const cls_resident_batch *rb);
 int cls_get_timing(const cls_index *index, cls_timing *out);
 
 /*
+ * Hash-sharded index (config 5 of BASELINE.json).  The k-mer table is split over up
+ * to 8 GPUs by `owner = (hash >> 61) % n_shards`; node-set records and the tree are replicated.
+ * The reference has no counterpart (its index is one in-memory HashMap, kmers_map.rs:77-87): these
+ * calls split cls_place_resident at the two points where query k-mers cross NVLink, so that the
+ * caller's collective (NCCL all-to-all on the device buffers) sits between them:
+ *
+ *   home  GPU  cls_route_hashes   hash every window, append it to its owner's segment
+ *                                 d_send[o * seg_cap .. + counts_out[o])  (uint64 hashes);
+ *                                 d_win_slot[window] = index into d_send  (uint32, n_windows entries)
+ *   all-to-all of the segments (hashes travel to their owners)
+ *   owner GPU  cls_shard_probe    one cls_probe_reply (12 bytes) per received hash, same order
+ *   all-to-all back, into a reply buffer laid out exactly like d_send
+ *   home  GPU  cls_place_routed   gating, distinct-hash counting, descent; results as cls_place_resident
+ *
+ * All d_* pointers are device memory owned by the caller.  cls_route_hashes synchronises `stream`
+ * (the counts are needed on the host for the exchange); the other two only enqueue.
+ * CLS_ERR_OUT_OF_MEMORY from cls_route_hashes means seg_cap was too small for some owner.
+ * Reads longer than 161 bases (beyond the one-warp-per-read geometry) are CLS_ERR_UNSUPPORTED on this path.
+ */
+typedef struct cls_probe_reply {
+    uint32_t set_off;   /* node-set record of the hit, 0xFFFFFFFF = not in the index       */
+    uint32_t slot;      /* globally unique id of the table slot (distinct-hash counting)   */
+    uint32_t code;      /* 2-bit prefix code of the entry's bucket key (gated at home)     */
+} cls_probe_reply;
+int cls_index_create_shard(const cls_model_view *model, int device, uint32_t shard, uint32_t n_shards,
+                           cls_index **out);
+int cls_routed_windows(cls_index *index, cls_resident_batch *rb, uint64_t *n_windows);
+int cls_route_hashes(cls_index *index, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap,
+                     void *d_send, void *d_win_slot, uint64_t *counts_out, void *stream);
+int cls_shard_probe(cls_index *index, const void *d_hashes, uint64_t n, void *d_replies, void *stream);
+int cls_place_routed(cls_index *index, cls_resident_batch *rb, const void *d_replies, const void *d_win_slot,
+                     const cls_params *params, void *stream);
+
+/*
  * Parity/debug exports.
  *
  * cls_debug_kmer_hashes: run the extraction + hashing kernel alone on one query
