@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the placement hot path (BASELINE.json: "queries placed/s and k-mer lookups/s").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl b200|reference]
 
 A "step" is one pass of the hot path (extract + murmur3 + probe + count + descend) over one batch
 of synthetic reads of the named configuration (classeq2_b200/synth.py):
@@ -37,7 +37,9 @@ sys.path.insert(0, ROOT)
 K_SIZE = 35
 NAMES = {2: "config2: synthetic 1,000-tip tree, 1 kb refs, 1M x 150 bp reads, index replicated",
          3: "config3: synthetic 10k-tip tree, ~600 bp refs, 10M x 150 bp reads sharded over the GPUs, index replicated",
-         4: "config4: synthetic 5k-tip tree, 1.5 kb refs, 1M reads of skewed length 150-1550 bp"}
+         4: "config4: synthetic 5k-tip tree, 1.5 kb refs, 1M reads of skewed length 150-1550 bp",
+         5: "config5: synthetic 100k-tip tree, ~600 bp refs, 10M x 150 bp reads sharded over the GPUs, index HASH-SHARDED "
+            "(owner = hash >> 61 mod N), query k-mers routed by NCCL all-to-all over NVLink"}
 
 
 def algorithmic_bytes(lens: np.ndarray) -> int:
@@ -52,7 +54,7 @@ def make_workload(config: int, rank: int, world: int, n_reads_override=None):
     t0 = time.time()
     sm = synth.make_model(c["n_tips"], c["l_ref"], c["tree_seed"])
     n_total = n_reads_override or c["n_reads"]
-    if config == 3:      # the 10M reads of config 3 are SHARDED over the ranks (strong)
+    if config in (3, 5):  # the 10M reads of configs 3 and 5 are SHARDED over the ranks (strong)
         n_local = n_total // world + (1 if rank < n_total % world else 0)
         scaling = "strong"
     else:                # configs 2 and 4: every GPU places its own batch of the named size (weak)
@@ -310,7 +312,7 @@ def run_b200(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes_local, "launches_per_step": launches_per_step,
-                         "kernel": "cls::place_kernel<35>", "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result"},
+                         "kernel": "cls::scan_kernel<1> (config 4: + cls::place_kernel<35,1,1>)", "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result"},
             "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
             "status_histogram": status_hist, "step_ms": [round(x, 4) for x in step_ms],
             "setup_s": {"generate": round(gen_s, 1), "index_upload": round(upload_s, 2)},
@@ -324,13 +326,155 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_sharded(args, rank, world, local_rank):
+    """Config 5: every rank owns one shard of the k-mer table and is home to its share of the reads."""
+    import torch
+    import torch.distributed as dist
+
+    import classeq2_b200 as cq
+    from classeq2_b200.parallel import ShardedPlacer
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sm, bases, offsets, scaling, gen_s = make_workload(5, rank, world, args.reads)
+    n_local = len(offsets) - 1
+    lens = np.diff(offsets.astype(np.int64))
+    lookups_local = int((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum())
+    t0 = time.time()
+    sp = ShardedPlacer(sm.flat, local_rank, rank, world)
+    info = sp.index.info()
+    upload_s = time.time() - t0
+    params = cq.PlaceParams()
+    dev = f"cuda:{local_rank}"
+    # sub-batches bound the exchange buffers (about 20 bytes of wire + 24 bytes of buffers per k-mer)
+    sub = 1_250_000
+    cuts = list(range(0, n_local, sub)) + [n_local]
+    parts = [(bases[int(offsets[a]):int(offsets[b])], (offsets[a:b + 1] - offsets[a]).astype(np.uint64)) for a, b in zip(cuts[:-1], cuts[1:])]
+    rbs = [sp.index.upload(p) for p in parts]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allred(x: float, op) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    st = torch.cuda.current_stream()
+    stage = {}
+
+    def step():
+        for rb in rbs:
+            sp.place_resident(rb, params)
+            for k, v in sp.timing.items():
+                stage[k] = stage.get(k, 0.0) + float(v)
+
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    barrier()
+    stage.clear()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_local = 0.0
+    step_ms = []
+    for i in range(args.steps):
+        flush.fill_(i + 2)
+        if world > 1:
+            dist.barrier()       # the all-to-alls couple the ranks: start every step together
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        step()
+        b.record(st)
+        b.synchronize()
+        step_ms.append(a.elapsed_time(b))
+        ms_local += step_ms[-1]
+    barrier()
+    clocks = sampler.summary()
+    ms_per_step = allred(ms_local, dist.ReduceOp.MAX) / args.steps
+    reads_total = allred(float(n_local), dist.ReduceOp.SUM)
+    lookups_total = allred(float(lookups_local), dist.ReduceOp.SUM)
+    value = reads_total / (ms_per_step / 1e3)
+    res = [rb.fetch(st.cuda_stream) for rb in rbs]
+
+    # end to end: host ASCII in, host arrays out, every sub-batch uploaded and fetched inside the timed region
+    e2e_res = [sp.place(p, params) for p in parts]   # warm-up (first-use registration of the exchange buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        e2e_res = [sp.place(p, params) for p in parts]
+    torch.cuda.synchronize()
+    e2e_s = allred((time.perf_counter() - t0) / max(1, args.steps // 2), dist.ReduceOp.MAX)
+
+    # parity: the replicated index on this GPU must give the very same arrays for a sample of the reads
+    n_chk = min(len(parts[0][1]) - 1, 20000)
+    rep_ix = cq.Index(sm.flat, device=local_rank)
+    want = rep_ix.place_batch((parts[0][0][: int(parts[0][1][n_chk])], parts[0][1][: n_chk + 1]), params)
+    bad = sum(int((getattr(want, f) != getattr(res[0], f)[:n_chk]).sum()) for f, _ in cq.engine.RESULT_DTYPES)
+    bad_e2e = sum(int((getattr(e2e_res[0], f) != getattr(res[0], f)).sum()) for f, _ in cq.engine.RESULT_DTYPES)
+    rep_info = rep_ix.info()
+    rep_ix.close()
+    bad = int(allred(float(bad + bad_e2e), dist.ReduceOp.SUM))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per = {k: v / args.steps for k, v in stage.items()}
+        n_device = int((lens >= K_SIZE).sum())
+        kern_ms = per.get("route_ms", 0) + per.get("probe_ms", 0) + per.get("place_ms", 0)
+        alg = algorithmic_bytes(lens)
+        wire_ms = per.get("send_ms", 0) + per.get("reply_ms", 0)
+        line = {
+            "metric": "queries placed/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": NAMES[5], "reads_per_gpu": n_local, "reads_total": int(reads_total), "k": K_SIZE, "m": 4,
+                       "index_entries_this_shard": int(info["n_entries"]), "index_entries_total": int(rep_info["n_entries"]),
+                       "table_bytes_this_shard": int(info["table_bytes"]), "distinct_node_sets": int(info["n_distinct_sets"]),
+                       "parallelism": f"queries sharded x{world}, k-mer table hash-sharded x{world}, 2 NCCL all-to-alls per sub-batch",
+                       "sub_batch_reads": sub, "l2": "256 MiB memset between steps (outside the event pairs)"},
+            "lookups_per_s": lookups_total / (ms_per_step / 1e3),
+            "e2e": {"value": reads_total / e2e_s, "unit": "reads/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(sum(rb.nbytes() for rb in rbs) - 32 * n_device), "d2h_bytes_per_step": 32 * n_device,
+                    "host_input": "ASCII bases + offsets in caller memory"},
+            "gpu_launches": 3 * len(rbs) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": alg / (kern_ms / 1e3) / 1e9 if kern_ms else None, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (kern_ms / 1e3) / 1e9 / peak if kern_ms else None, "traffic": ncu_traffic(5),
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                         "kernel": "cls::route_kernel<35> + cls::shard_probe_kernel + cls::place_routed_kernel<1> (rank 0, summed)",
+                         "note": "the exchange is NVLink-bound: see `nvlink`"},
+            "nvlink": {"wire_ms_per_step_rank0": wire_ms, "bytes_out_per_step_rank0": per.get("wire_bytes_out", 0),
+                       "achieved_gbs_out_rank0": per.get("wire_bytes_out", 0) / (wire_ms / 1e3) / 1e9 if wire_ms else None,
+                       "peak_gbs_per_direction": 900.0, "bytes_per_routed_kmer": 20},
+            "stage_ms_per_step_rank0": {k: round(v, 3) for k, v in per.items() if k.endswith("_ms")},
+            "cpu_baseline": None, "clocks": clocks,
+            "parity": {"checked_reads": n_chk, "mismatching_fields": bad,
+                       "against": "the replicated index on the same GPU (itself pinned to the CPU oracle by configs 2-4 and the tests)"},
+            "status_histogram": np.bincount(np.concatenate([r.status for r in res]), minlength=11).tolist(),
+            "step_ms": [round(x, 3) for x in step_ms],
+            "setup_s": {"generate": round(gen_s, 1), "index_upload": round(upload_s, 2)},
+        }
+        print(json.dumps(line), flush=True)
+    for rb in rbs:
+        rb.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--reads", type=int, default=None, help="override the number of reads of the config")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
     args = ap.parse_args()
@@ -341,6 +485,8 @@ def main():
         print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU); running the single-GPU line", file=sys.stderr)
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config == 5:
+        run_sharded(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 

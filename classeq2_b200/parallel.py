@@ -129,26 +129,40 @@ class ShardedPlacer:
         self.rank, self.world, self.group, self.slack = rank, world, group, slack
         self.index = Index(model, device=device, shard=rank, n_shards=world)
         self.device = device
-        self.timing = {}
 
     def place(self, seqs, params=None) -> BatchResult:
+        """Host buffers in, host arrays out: upload, the routed pipeline, fetch."""
+        import torch
+
+        rb = self.index.upload(seqs)
+        self.place_resident(rb, params)
+        res = rb.fetch(torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream)
+        rb.close()
+        return res
+
+    def place_resident(self, rb, params=None) -> None:
+        """The routed pipeline over a batch already resident in HBM, enqueued on torch's current
+        stream (the host only waits for the per-owner counts, which size the exchange).  Results stay
+        on the device (``rb.fetch``).  ``self.timing`` holds the CUDA-event time of every stage."""
         import torch
 
         dev = torch.device("cuda", self.device)
-        rb = self.index.upload(seqs)
         st = torch.cuda.current_stream(dev)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         nw = rb.routed_windows()
         world = self.world
         seg_cap = int(nw / world * self.slack) + 65536
-        send = torch.empty(world * seg_cap, dtype=torch.int64, device=dev)
-        win_slot = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
+        buf = self._buffers(nw, seg_cap, dev)
+        send, win_slot, rep_in = buf["send"], buf["win_slot"], buf["rep_in"]
         ev[0].record(st)
         counts_to = rb.route_hashes(world, seg_cap, send.data_ptr(), win_slot.data_ptr(), st.cuda_stream).astype(np.int64)
         ev[1].record(st)
         counts_from = exchange_plan(counts_to, self.group) if world > 1 else counts_to.copy()
         n_recv = int(counts_from.sum())
-        recv = torch.empty(max(n_recv, 1), dtype=torch.int64, device=dev)
+        if buf["recv"].numel() < max(n_recv, 1):
+            buf["recv"] = torch.empty(int(n_recv * 1.05) + 1, dtype=torch.int64, device=dev)
+            buf["rep_out"] = torch.empty(buf["recv"].numel() * REPLY_BYTES, dtype=torch.uint8, device=dev)
+        recv, rep_out = buf["recv"], buf["rep_out"]
         send_views, recv_views = segment_views(send, counts_to, seg_cap), segment_views(recv, counts_from)
         if world > 1:
             exchange_segments(send_views, recv_views, self.group)
@@ -156,11 +170,9 @@ class ShardedPlacer:
             recv_views[0].copy_(send_views[0])
         ev[2].record(st)
         # owner side: answer everything received, in the order received
-        rep_out = torch.empty(max(n_recv, 1) * REPLY_BYTES, dtype=torch.uint8, device=dev)
         self.index.shard_probe(recv.data_ptr(), n_recv, rep_out.data_ptr(), st.cuda_stream)
         ev[3].record(st)
         # replies travel back into a buffer laid out exactly like `send`
-        rep_in = torch.empty(world * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev)
         back_send = segment_views(rep_out, counts_from, 0, REPLY_BYTES)
         back_recv = segment_views(rep_in, counts_to, seg_cap, REPLY_BYTES)
         if world > 1:
@@ -170,14 +182,38 @@ class ShardedPlacer:
         ev[4].record(st)
         rb.place_routed(rep_in.data_ptr(), win_slot.data_ptr(), params, st.cuda_stream)
         ev[5].record(st)
-        res = rb.fetch(st.cuda_stream)
+        self._events = ev
+        remote = int(counts_to.sum() - counts_to[self.rank]), int(counts_from.sum() - counts_from[self.rank])
+        self._stats = dict(n_windows=nw, routed_out=remote[0], routed_in=remote[1],
+                           wire_bytes_out=remote[0] * 8 + remote[1] * REPLY_BYTES,
+                           wire_bytes_in=remote[1] * 8 + remote[0] * REPLY_BYTES)
+
+    def _buffers(self, nw: int, seg_cap: int, dev):
+        import torch
+
+        b = getattr(self, "_buf", None)
+        if b is None or b["seg_cap"] < seg_cap or b["win_slot"].numel() < max(nw, 1):
+            b = dict(seg_cap=seg_cap,
+                     send=torch.empty(self.world * seg_cap, dtype=torch.int64, device=dev),
+                     win_slot=torch.empty(max(nw, 1), dtype=torch.int32, device=dev),
+                     rep_in=torch.empty(self.world * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev),
+                     recv=torch.empty(1, dtype=torch.int64, device=dev),
+                     rep_out=torch.empty(REPLY_BYTES, dtype=torch.uint8, device=dev))
+            self._buf = b
+        return b
+
+    @property
+    def timing(self) -> dict:
+        """Stage times (ms, CUDA events) and wire volume of the last ``place_resident``; synchronises."""
+        ev = getattr(self, "_events", None)
+        if ev is None:
+            return {}
+        ev[-1].synchronize()
         names = ["route_ms", "send_ms", "probe_ms", "reply_ms", "place_ms"]
-        self.timing = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
-        remote_out = int(counts_to.sum() - counts_to[self.rank]), int(counts_from.sum() - counts_from[self.rank])
-        self.timing.update(n_windows=nw, routed_out=remote_out[0],
-                           wire_bytes_out=remote_out[0] * 8 + remote_out[1] * REPLY_BYTES)
-        rb.close()
-        return res
+        t = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
+        t["total_ms"] = ev[0].elapsed_time(ev[5])
+        t.update(self._stats)
+        return t
 
 
 class LocalShardedPlacer:
