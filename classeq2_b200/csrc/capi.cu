@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -148,7 +149,7 @@ int plan_batch(const cls_batch *batch, uint32_t k, uint32_t max_fanout, PackedLa
     lay.n_queries = n;
     lay.n_device = 0;
     lay.n_words = 0;
-    lay.pre_status.assign(n, 0xFF);
+    lay.pre_status.resize(n);
     lay.lens.resize(n);
     // class id = log2 of the de-duplication table size for that length (make_place_geom)
     constexpr int kMaxClass = 40;
@@ -158,48 +159,68 @@ int plan_batch(const cls_batch *batch, uint32_t k, uint32_t max_fanout, PackedLa
         while ((1ull << c) < h2) ++c;
         return c;
     };
-    uint64_t count[kMaxClass] = {0}, words[kMaxClass] = {0}, maxlen[kMaxClass] = {0};
+    // Everything below runs over fixed blocks of reads on the host pool: per-block class histograms,
+    // a short serial scan over (class, block), then every block fills its own slice of the permutation
+    // (input order is kept inside a class, exactly as a serial pass would).
+    constexpr uint64_t kBlock = 1 << 15;
+    const uint64_t nblk = (n + kBlock - 1) / kBlock;
+    std::vector<uint64_t> bcount(nblk * kMaxClass, 0), bwords(nblk * kMaxClass, 0), bmax(nblk * kMaxClass, 0);
     std::vector<uint8_t> &cls_id = lay.cls_id;
     cls_id.resize(n);
     std::atomic<bool> bad_offsets{false}, too_long{false};
-    parallel_for(n, 1 << 16, [&](uint64_t a, uint64_t b) {  // per-read lengths, statuses, classes
-        for (uint64_t i = a; i < b; ++i) {
-            if (batch->offsets[i] > batch->offsets[i + 1]) { bad_offsets = true; continue; }
-            const uint64_t len = batch->offsets[i + 1] - batch->offsets[i];
-            if (len >= (1ull << 31)) { too_long = true; continue; }
-            lay.lens[i] = (uint32_t)len;
-            if (len < k) { lay.pre_status[i] = CLS_STATUS_ERR_TOO_SHORT; cls_id[i] = 0xFF; }  // kmers_map.rs:383-385
-            else cls_id[i] = (uint8_t)class_of(len);
+    parallel_for(nblk, 1, [&](uint64_t b0, uint64_t b1) {  // per-read lengths, statuses, classes
+        for (uint64_t blk = b0; blk < b1; ++blk) {
+            uint64_t *bc = &bcount[blk * kMaxClass], *bw = &bwords[blk * kMaxClass], *bm = &bmax[blk * kMaxClass];
+            const uint64_t hi = std::min(n, (blk + 1) * kBlock);
+            for (uint64_t i = blk * kBlock; i < hi; ++i) {
+                lay.pre_status[i] = 0xFF;
+                cls_id[i] = 0xFF;
+                if (batch->offsets[i] > batch->offsets[i + 1]) { bad_offsets = true; continue; }
+                const uint64_t len = batch->offsets[i + 1] - batch->offsets[i];
+                if (len >= (1ull << 31)) { too_long = true; continue; }
+                lay.lens[i] = (uint32_t)len;
+                if (len < k) { lay.pre_status[i] = CLS_STATUS_ERR_TOO_SHORT; continue; }  // kmers_map.rs:383-385
+                const int c = class_of(len);
+                cls_id[i] = (uint8_t)c;
+                bc[c]++;
+                bw[c] += (len + 15u) / 16u;
+                bm[c] = std::max<uint64_t>(bm[c], len);
+            }
         }
     });
     if (bad_offsets) return fail(CLS_ERR_INVALID_ARGUMENT, "batch offsets are not non-decreasing");
     if (too_long) return fail(CLS_ERR_INVALID_ARGUMENT, "query longer than 2^31 bases");
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint8_t c = cls_id[i];
-        if (c == 0xFF) continue;
-        count[c]++;
-        words[c] += (lay.lens[i] + 15u) / 16u;
-        maxlen[c] = std::max<uint64_t>(maxlen[c], lay.lens[i]);
-    }
-    uint64_t start[kMaxClass], wstart[kMaxClass], acc = 0, w = 0;
-    for (int c = kMaxClass - 1; c >= 0; --c) {
-        start[c] = acc; wstart[c] = w;
-        if (count[c]) lay.classes.push_back(LengthClass{(uint32_t)acc, (uint32_t)count[c], (uint32_t)maxlen[c]});
-        acc += count[c]; w += words[c];
+    uint64_t acc = 0, w = 0;
+    for (int c = kMaxClass - 1; c >= 0; --c) {  // longest class first; bcount / bwords become the blocks' start positions
+        uint64_t cnt = 0, mx = 0;
+        const uint64_t first = acc;
+        for (uint64_t blk = 0; blk < nblk; ++blk) {
+            const uint64_t bc = bcount[blk * kMaxClass + c], bw = bwords[blk * kMaxClass + c];
+            bcount[blk * kMaxClass + c] = acc; bwords[blk * kMaxClass + c] = w;
+            acc += bc; w += bw; cnt += bc;
+            mx = std::max(mx, bmax[blk * kMaxClass + c]);
+        }
+        if (cnt) lay.classes.push_back(LengthClass{(uint32_t)first, (uint32_t)cnt, (uint32_t)mx});
     }
     if (w >= 0xFFFFFFFFull) return fail(CLS_ERR_INVALID_ARGUMENT, "batch exceeds 2^32 packed words; split it");
     lay.n_device = (uint32_t)acc;
     lay.n_words = w;
     lay.perm.resize(acc);
     word_off.resize((size_t)acc + 1);
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint8_t c = cls_id[i];
-        if (c == 0xFF) continue;
-        const uint64_t j = start[c]++;
-        lay.perm[j] = (uint32_t)i;
-        word_off[j] = (uint32_t)wstart[c];
-        wstart[c] += (lay.lens[i] + 15u) / 16u;
-    }
+    parallel_for(nblk, 1, [&](uint64_t b0, uint64_t b1) {
+        for (uint64_t blk = b0; blk < b1; ++blk) {
+            uint64_t *start = &bcount[blk * kMaxClass], *wstart = &bwords[blk * kMaxClass];
+            const uint64_t hi = std::min(n, (blk + 1) * kBlock);
+            for (uint64_t i = blk * kBlock; i < hi; ++i) {
+                const uint8_t c = cls_id[i];
+                if (c == 0xFF) continue;
+                const uint64_t j = start[c]++;
+                lay.perm[j] = (uint32_t)i;
+                word_off[j] = (uint32_t)wstart[c];
+                wstart[c] += (lay.lens[i] + 15u) / 16u;
+            }
+        }
+    });
     word_off[acc] = (uint32_t)w;
     (void)max_fanout;
     return CLS_OK;
@@ -467,7 +488,7 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
     // results of finished chunks are scattered to the caller's arrays while later chunks run.
     struct Chunk { uint32_t first, count, max_len; };
     std::vector<Chunk> chunks;
-    constexpr uint64_t kChunkBases = 24ull << 20;  // about 24 M bases (6 MiB packed) per chunk
+    static const uint64_t kChunkBases = [] { const char *e = getenv("CLS_CHUNK_MBASES"); return (uint64_t)(e ? atoi(e) : 24) << 20; }();  // bases per chunk
     for (const LengthClass &c : lay.classes) {
         const uint64_t per = std::max<uint64_t>(4096, kChunkBases / std::max<uint32_t>(c.max_len, 1));
         for (uint64_t a = 0; a < c.count; a += per)

@@ -1002,8 +1002,12 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
                 uint64_t A0, A1, A2, A3, B0, B1, B2, B3;
                 ld_bucket(ix.table, bA, A0, A1, A2, A3);
                 ld_bucket(ix.table, bB, B0, B1, B2, B3);
-                consume(posA, hA, bA, A0, A1, A2, A3);
-                if (two) consume(posB, hB, bB, B0, B1, B2, B3);
+                // ONE copy of the consume code, run once per window of the pair (the hot loop has to stay
+                // small: instruction-cache misses showed up as the third largest stall with two copies)
+#pragma unroll 1
+                for (uint32_t u = 0; u < (two ? 2u : 1u); ++u) {
+                    consume(u ? posB : posA, u ? hB : hA, u ? bB : bA, u ? B0 : A0, u ? B1 : A1, u ? B2 : A2, u ? B3 : A3);
+                }
             }
         }
         __syncwarp();
