@@ -260,10 +260,14 @@ struct ReadTables {
 // the reference's HashSets), then add the distinct ones to the node-set histogram with ONE
 // shared-memory atomic per group of lanes that hit the same node set (match.any).  Called by all
 // 32 lanes; returns the number of distinct new hits of the pass (uniform).
+// SHARED == true: several warps fill the tables of one read (CTA-per-read mode): counts are atomic and
+// start from zeroed bins.  SHARED == false: the warp owns the tables; a bin's count has one writer per
+// pass (the leader of its node set), so plain stores do and the bins need no zeroing.
+template <bool SHARED>
 __device__ __forceinline__ uint32_t insert_hits(const ReadTables &tb, bool hit, uint32_t slot_key, uint32_t set_off) {
     bool fresh = false;
     if (hit) {
-        uint32_t p1 = slot_key & tb.t1_mask;
+        uint32_t p1 = (slot_key >> 1) & tb.t1_mask;  // bit 0 is the slot within the bucket (mostly 0): not a hash bit
         for (;;) {
             const uint32_t old = atomicCAS(&tb.t1[p1], kEmpty, slot_key);
             if (old == kEmpty) { fresh = true; break; }
@@ -278,12 +282,18 @@ __device__ __forceinline__ uint32_t insert_hits(const ReadTables &tb, bool hit, 
             uint32_t p2 = (set_off * 0x9E3779B1u) >> tb.t2_shift;
             for (;;) {
                 const uint32_t old = atomicCAS(&tb.t2k[p2], kEmpty, set_off);
-                if (old == kEmpty) tb.lst[atomicAdd(tb.n_sets, 1u)] = p2;
-                if (old == kEmpty || old == set_off) { atomicAdd(&tb.t2c[p2], (uint32_t)__popc(peers)); break; }
+                if constexpr (SHARED) {
+                    if (old == kEmpty) tb.lst[atomicAdd(tb.n_sets, 1u)] = p2;
+                    if (old == kEmpty || old == set_off) { atomicAdd(&tb.t2c[p2], (uint32_t)__popc(peers)); break; }
+                } else {
+                    if (old == kEmpty) { tb.lst[atomicAdd(tb.n_sets, 1u)] = p2; tb.t2c[p2] = (uint32_t)__popc(peers); break; }
+                    if (old == set_off) { tb.t2c[p2] += (uint32_t)__popc(peers); break; }
+                }
                 p2 = (p2 + 1) & tb.t2_mask;
             }
         }
     }
+    if constexpr (!SHARED) __syncwarp();  // the next pass may elect another lane as the leader of the same bin
     return (uint32_t)__popc(fm);
 }
 
@@ -551,29 +561,37 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
 }
 
 // ------------------------------------------------------------------------------------------
-// finish_read for CLOSED models when the read has at most 32 distinct node sets (97 % of 150 bp
-// reads): lane j keeps set j - its live terminal range [lo, hi), its smallest and largest live
+// finish_read for CLOSED models when the read has at most 32 * SLOTS distinct node sets (97 % of 150 bp
+// reads have at most 32, 99.9 % at most 64): lane j keeps sets j, j + 32, ... - its live terminal range [lo, hi), its smallest and largest live
 // terminal and its weight - in registers, every vote is one warp reduction, and no loop runs over
 // the sets.  Same algorithm and same outcomes as finish_read<true>.
 // ------------------------------------------------------------------------------------------
+template <int SLOTS>
 __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const PlaceParams &pp, const ReadTables &tb,
                                                 uint32_t D, uint32_t n_matched, ResultRec *__restrict__ out) {
     const uint32_t lane = lane_id();
     const uint32_t *__restrict__ terms = ix.terms;
     const bool ri = pp.remove_intersection != 0;
     // ---- restriction to the sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
-    uint32_t lo = 0, hi = 0, first = 0xFFFFFFFFu, last = 0, w = 0;
-    if (lane < D) {
-        const uint32_t p2 = tb.lst[lane];
-        const uint32_t off = tb.t2k[p2];
-        const uint32_t hdr = __ldg(terms + off);
-        if (hdr & kTermHasRoot) {
-            last = __ldg(terms + off + 1); first = __ldg(terms + off + 2);
-            w = tb.t2c[p2];
-            lo = off + 2; hi = lo + (hdr & ~kTermHasRoot);
+    uint32_t lo[SLOTS], hi[SLOTS], first[SLOTS], last[SLOTS], w[SLOTS];
+    uint32_t wsum = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        lo[s] = 0; hi[s] = 0; first[s] = 0xFFFFFFFFu; last[s] = 0; w[s] = 0;
+        const uint32_t j = lane + 32u * s;
+        if (j < D) {
+            const uint32_t p2 = tb.lst[j];
+            const uint32_t off = tb.t2k[p2];
+            const uint32_t hdr = __ldg(terms + off);
+            if (hdr & kTermHasRoot) {
+                last[s] = __ldg(terms + off + 1); first[s] = __ldg(terms + off + 2);
+                w[s] = tb.t2c[p2];
+                lo[s] = off + 2; hi[s] = lo[s] + (hdr & ~kTermHasRoot);
+            }
         }
+        wsum += w[s];
     }
-    const uint32_t n_root = __reduce_add_sync(kFull, w);
+    const uint32_t n_root = __reduce_add_sync(kFull, wsum);
     // ---- gates (place_sequence.rs:120-139, :156-166, :199-206, :231-254)
     ResultRec res;
     res.node_id = 0; res.one = 0; res.rest = 0;
@@ -595,8 +613,11 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
     QInfo ip = res.status == kUndecided ? ld_qinfo(ix.qinfo, 0) : QInfo{0, 0, 0, 0};
     while (res.status == kUndecided) {
         // pooled extremes of the live terminals -> every level down to their LCA is unanimous
-        const uint32_t umin = __reduce_min_sync(kFull, w ? first : 0xFFFFFFFFu);
-        const uint32_t vmax = __reduce_max_sync(kFull, w ? last : 0u);
+        uint32_t mn = 0xFFFFFFFFu, mx = 0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+            if (w[s]) { mn = min(mn, first[s]); mx = max(mx, last[s]); }
+        const uint32_t umin = __reduce_min_sync(kFull, mn), vmax = __reduce_max_sync(kFull, mx);
         const uint64_t dn = lca_depth_node(ix, umin, vmax);
         const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
         if (depth_a > depth_p) {
@@ -605,8 +626,11 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
             iteration += d;
             ip = ld_qinfo(ix.qinfo, A);
             if (ip.child_count == 0) {  // update_introspection_node.rs:32-87
+                uint32_t ws = 0;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) ws += w[s];
                 res.status = CLS_DEV_IDENTITY_FOUND; res.node_id = ix.q_node_id[A];
-                res.one = (int32_t)__reduce_add_sync(kFull, w); res.rest = 0;
+                res.one = (int32_t)__reduce_add_sync(kFull, ws); res.rest = 0;
                 break;
             }
             p = A; depth_p = depth_a;
@@ -618,18 +642,27 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
         uint32_t win_q = 0, nprop = 0, n_best = 0;
         int32_t win_one = 0, win_rest = 0;
         QInfo iw{0, 0, 0, 0};
-        if (w && first == p) {  // the set ends at p itself for some tip: that is no vote for any child
-            ++lo;
-            first = lo < hi ? __ldg(terms + lo) : 0xFFFFFFFFu;
+        bool has[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            if (w[s] && first[s] == p) {  // the set ends at p itself for some tip: that is no vote for any child
+                ++lo[s];
+                first[s] = lo[s] < hi[s] ? __ldg(terms + lo[s]) : 0xFFFFFFFFu;
+            }
+            has[s] = w[s] && lo[s] < hi[s];
         }
-        const bool has = w && lo < hi;
         if (m <= 2) {
             // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
             const QInfo i1 = m ? ld_qinfo(ix.qinfo, p + 1) : QInfo{p_end, 0, 0, 0};
             const uint32_t bnd = i1.q_end;
-            const bool in1 = has && first < bnd, in2 = has && last >= bnd;
-            const uint32_t c1 = __reduce_add_sync(kFull, in1 ? w : 0u), c2 = __reduce_add_sync(kFull, in2 ? w : 0u);
-            const uint32_t both = __reduce_add_sync(kFull, (in1 && in2) ? w : 0u);
+            uint32_t a1 = 0, a2 = 0, ab = 0;
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const bool in1 = has[s] && first[s] < bnd, in2 = has[s] && last[s] >= bnd;
+                a1 += in1 ? w[s] : 0u; a2 += in2 ? w[s] : 0u; ab += (in1 && in2) ? w[s] : 0u;
+            }
+            const uint32_t c1 = __reduce_add_sync(kFull, a1), c2 = __reduce_add_sync(kFull, a2);
+            const uint32_t both = __reduce_add_sync(kFull, ab);
             const uint32_t U = c1 + c2 - both, x1 = c1 - both, x2 = c2 - both;
             const uint32_t ncand = (c1 > 0) + (c2 > 0);
             const int32_t one1 = (int32_t)((ri && ncand > 1) ? x1 : c1), rest1 = ncand > 1 ? (int32_t)(ri ? U - c1 : U - x1) : 0;
@@ -645,20 +678,22 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
             if (pick2) { win_q = bnd; win_one = one2; win_rest = rest2; if (nprop) iw = ld_qinfo(ix.qinfo, bnd); }
             else { win_q = p + 1; win_one = one1; win_rest = rest1; iw = i1; }
         } else {
-            // general fan-out: every lane merges its terminal range against the child intervals,
+            // general fan-out: every lane merges its terminal ranges against the child intervals,
             // votes in the shared-memory counters
             uint32_t u_local = 0;
-            if (has) {
-                uint32_t pos = lo, npres = 0, lastc = 0, ord = 0, cend = __ldg(&ix.qinfo[p + 1].q_end);
-                while (pos < hi) {
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                if (!has[s]) continue;
+                uint32_t pos = lo[s], npres = 0, lastc = 0, ord = 0, cend = __ldg(&ix.qinfo[p + 1].q_end);
+                while (pos < hi[s]) {
                     const uint32_t t = __ldg(terms + pos);
                     while (t >= cend) { cend = __ldg(&ix.qinfo[cend].q_end); ++ord; }
-                    atomicAdd(&tb.cnt[ord], w); ++npres; lastc = ord;
+                    atomicAdd(&tb.cnt[ord], w[s]); ++npres; lastc = ord;
                     ++pos;
-                    if (pos < hi && __ldg(terms + pos) < cend) pos = lower_bound_terms(terms, pos, hi, cend);
+                    if (pos < hi[s] && __ldg(terms + pos) < cend) pos = lower_bound_terms(terms, pos, hi[s], cend);
                 }
-                u_local = w;
-                if (npres == 1) atomicAdd(&tb.excl[lastc], w);
+                u_local += w[s];
+                if (npres == 1) atomicAdd(&tb.excl[lastc], w[s]);
             }
             const uint32_t U = __reduce_add_sync(kFull, u_local);
             __syncwarp();
@@ -685,17 +720,20 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
         p = win_q; ip = iw; depth_p++;
         const uint32_t win_end = iw.q_end;
         // every live set keeps its terminals inside the winner's interval (or drops out)
-        bool live = has && last >= win_q && first < win_end;
-        if (live && first < win_q) {
-            lo = lower_bound_terms(terms, lo + 1, hi, win_q);
-            first = __ldg(terms + lo);  // lo < hi because last >= win_q
-            live = first < win_end;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            bool live = has[s] && last[s] >= win_q && first[s] < win_end;
+            if (live && first[s] < win_q) {
+                lo[s] = lower_bound_terms(terms, lo[s] + 1, hi[s], win_q);
+                first[s] = __ldg(terms + lo[s]);  // lo < hi because last >= win_q
+                live = first[s] < win_end;
+            }
+            if (live && last[s] >= win_end) {
+                hi[s] = lower_bound_terms(terms, lo[s] + 1, hi[s] - 1, win_end);  // terms[lo] < win_end
+                last[s] = __ldg(terms + hi[s] - 1);
+            }
+            if (!live) w[s] = 0;
         }
-        if (live && last >= win_end) {
-            hi = lower_bound_terms(terms, lo + 1, hi - 1, win_end);  // terms[lo] < win_end
-            last = __ldg(terms + hi - 1);
-        }
-        if (!live) w = 0;
     }
     res.iterations = (uint32_t)iteration;
     if (lane == 0) *out = res;
@@ -793,8 +831,10 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
             uint4 *z = reinterpret_cast<uint4 *>(t1);
             const uint32_t n4 = (g.t1_size + g.t2_size) >> 2;  // t1 and t2k are contiguous: all kEmpty
             for (uint32_t i = gtid; i < n4; i += gthreads) z[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            uint4 *zc = reinterpret_cast<uint4 *>(t2c);
-            for (uint32_t i = gtid; i < (g.t2_size >> 2); i += gthreads) zc[i] = make_uint4(0, 0, 0, 0);
+            if constexpr (CTA) {  // counts are accumulated atomically by all warps: start from zero
+                uint4 *zc = reinterpret_cast<uint4 *>(t2c);
+                for (uint32_t i = gtid; i < (g.t2_size >> 2); i += gthreads) zc[i] = make_uint4(0, 0, 0, 0);
+            }
             if (gtid == 0) { *n_sets_smem = 0; *n_matched_smem = 0; }
         }
         decode_read(packed + rd.word_off, L, wm, g.pk_words, gtid, gthreads);
@@ -828,7 +868,7 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
                         hit = packed_bits(wm.pk_f, p, code_mask) == want || packed_bits(wm.pk_r, p, code_mask) == want;
                 }
             }
-            return insert_hits(tb, hit, slot_id, set_off);
+            return insert_hits<CTA>(tb, hit, slot_id, set_off);
         };
 
         uint32_t n_matched = 0;
@@ -894,6 +934,12 @@ __device__ __forceinline__ uint64_t window_hash35(uint64_t a0, uint64_t b1, uint
 #ifndef CLS_SCAN_MINB
 #define CLS_SCAN_MINB 4
 #endif
+#ifndef CLS_ONE_CONSUME
+#define CLS_ONE_CONSUME 0  // 1: a single copy of the consume code looped over the pair (118 more instructions per read: 5.59 vs 5.46 ms)
+#endif
+#ifndef CLS_REG_SLOTS2
+#define CLS_REG_SLOTS2 1
+#endif
 template <bool CLOSED>
 __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix, PlaceParams pp, const uint32_t *__restrict__ packed,
                                                       const ReadDesc *__restrict__ reads, uint32_t first_read,
@@ -936,9 +982,7 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
             uint4 *z = reinterpret_cast<uint4 *>(t1);
             const uint32_t n4 = (g.t1_size + g.t2_size) >> 2;  // t1 and t2k are contiguous: all kEmpty
             for (uint32_t i = lane; i < n4; i += 32) z[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            uint4 *zc = reinterpret_cast<uint4 *>(t2c);
-            for (uint32_t i = lane; i < (g.t2_size >> 2); i += 32) zc[i] = make_uint4(0, 0, 0, 0);
-            if (lane == 0) *n_sets_smem = 0;
+            if (lane == 0) *n_sets_smem = 0;  // the histogram counts (t2c) are written before they are read
         }
         decode_read(packed + rd.word_off, L, wm, g.pk_words);
         const uint32_t n_chunks = (W + 31u) >> 5;
@@ -970,7 +1014,7 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
                             hit = packed_bits(wm.pk_f, q, code_mask) == want || packed_bits(wm.pk_r, q, code_mask) == want;
                     }
                 }
-                n_matched += insert_hits(tb, hit, 2u * b + (e0 ? 0u : 1u), (uint32_t)mm);
+                n_matched += insert_hits<false>(tb, hit, 2u * b + (e0 ? 0u : 1u), (uint32_t)mm);
             };
             __syncwarp();
             premix_store(wsrc, sh8, ra0, rb0);  // offsets 0..31 -> ring half 0
@@ -1002,17 +1046,24 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
                 uint64_t A0, A1, A2, A3, B0, B1, B2, B3;
                 ld_bucket(ix.table, bA, A0, A1, A2, A3);
                 ld_bucket(ix.table, bB, B0, B1, B2, B3);
-                // ONE copy of the consume code, run once per window of the pair (the hot loop has to stay
-                // small: instruction-cache misses showed up as the third largest stall with two copies)
+#if CLS_ONE_CONSUME
+                // ONE copy of the consume code, run once per window of the pair
 #pragma unroll 1
                 for (uint32_t u = 0; u < (two ? 2u : 1u); ++u) {
                     consume(u ? posB : posA, u ? hB : hA, u ? bB : bA, u ? B0 : A0, u ? B1 : A1, u ? B2 : A2, u ? B3 : A3);
                 }
+#else
+                consume(posA, hA, bA, A0, A1, A2, A3);
+                if (two) consume(posB, hB, bB, B0, B1, B2, B3);
+#endif
             }
         }
         __syncwarp();
         const uint32_t D = *n_sets_smem;
-        if (CLOSED && D <= 32) finish_read_reg(ix, pp, tb, D, n_matched, results + first_read + r);
+        if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
+#if CLS_REG_SLOTS2
+        else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
+#endif
         else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
         __syncwarp();
     }

@@ -174,8 +174,6 @@ __global__ void __launch_bounds__(256, 4) place_routed_kernel(DeviceIndex ix, Pl
             uint4 *z = reinterpret_cast<uint4 *>(wl.t1);
             const uint32_t n4 = (g.t1_size + g.t2_size) >> 2;
             for (uint32_t i = lane; i < n4; i += 32) z[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            uint4 *zc = reinterpret_cast<uint4 *>(wl.t2c);
-            for (uint32_t i = lane; i < (g.t2_size >> 2); i += 32) zc[i] = make_uint4(0, 0, 0, 0);
             if (lane == 0) *wl.n_sets = 0;
         }
         decode_read(packed + rd.word_off, L, wl.wm, g.pk_words);  // the packed strands gate the hits
@@ -198,11 +196,12 @@ __global__ void __launch_bounds__(256, 4) place_routed_kernel(DeviceIndex ix, Pl
                         hit = packed_bits(wl.wm.pk_f, q, code_mask) == rep.code || packed_bits(wl.wm.pk_r, q, code_mask) == rep.code;
                 }
             }
-            n_matched += insert_hits(tb, hit, rep.slot, rep.set_off);
+            n_matched += insert_hits<false>(tb, hit, rep.slot, rep.set_off);
         }
         __syncwarp();
         const uint32_t D = *wl.n_sets;
-        if (CLOSED && D <= 32) finish_read_reg(ix, pp, tb, D, n_matched, results + first_read + r);
+        if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
+        else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
         else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
         __syncwarp();
     }
