@@ -107,6 +107,7 @@ struct Workspace {
     std::vector<cudaEvent_t> chunk_ev;  // 4 per chunk: start, kernel start, kernel end, done
     PinBuf h_words, h_descs, h_results;
     DevBuf d_words, d_descs, d_results;
+    DevBuf d_scratch[2];                // scan -> descent hand-over of the chunk in flight on each stream
     PackedLayout lay;                   // reused across calls
     bool in_use = false;
 };
@@ -129,6 +130,7 @@ struct cls_resident_batch {
     int device = 0;
     PackedLayout lay;
     DevBuf d_words, d_descs, d_results;
+    DevBuf d_scratch;  // scan -> descent hand-over (one placement of this batch in flight at a time)
     DevBuf d_win_base, d_route_state;  // routed path: first window of every read; per-owner cursors + overflow flag
     uint64_t n_windows = 0;
     PinBuf h_results;
@@ -255,15 +257,26 @@ PlaceParams make_place_params(const cls_params *params) {
 }
 
 int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *params, const uint32_t *d_words,
-                   const ReadDesc *d_descs, ResultRec *d_results, cudaStream_t stream, uint64_t *launches) {
+                   const ReadDesc *d_descs, ResultRec *d_results, cudaStream_t stream, DevBuf &scratch, uint64_t *launches) {
     const PlaceParams pp = make_place_params(params);
+    size_t want = 0;
     for (const LengthClass &c : lay.classes) {
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
-        cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_results, g, ix->sm_count, stream);
+        if (!g.cta_per_read) want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size));
+    }
+    if (want > scratch.cap) {
+        if (scratch.p) CU_TRY(cudaStreamSynchronize(stream));  // an earlier placement on this stream may still use it
+        CU_TRY(scratch.reserve(want));
+    }
+    for (const LengthClass &c : lay.classes) {
+        PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
+        uint32_t nl = 0;
+        cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_results, g, ix->sm_count, stream,
+                                     scratch.p, scratch.cap, &nl);
+        if (launches) *launches += nl;
         if (e == cudaErrorInvalidConfiguration)
             return fail(CLS_ERR_UNSUPPORTED, "query too long (or tree fan-out too large) for the per-warp shared-memory tables");
         if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("place kernel launch: ") + cudaGetErrorString(e));
-        if (launches) (*launches)++;
     }
     return CLS_OK;
 }
@@ -449,6 +462,7 @@ void cls_index_destroy(cls_index *ix) {
         for (auto &e : w->ev) if (e) cudaEventDestroy(e);
         w->h_words.release(); w->h_descs.release(); w->h_results.release();
         w->d_words.release(); w->d_descs.release(); w->d_results.release();
+        w->d_scratch[0].release(); w->d_scratch[1].release();
     }
     ix->d_table.release(); ix->d_arena.release(); ix->d_qnodes.release(); ix->d_qchild.release(); ix->d_qid.release();
     ix->d_terms.release(); ix->d_qinfo.release(); ix->d_lca.release();
@@ -523,14 +537,18 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
         CU_TRY(cudaMemcpyAsync(d_descs + c.first, h_descs + c.first, (size_t)c.count * sizeof(ReadDesc), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaEventRecord(ev[1], st));
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
-        cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_res, g, ix->sm_count, st);
+        DevBuf &scratch = w->d_scratch[ci & 1];  // stream order protects its reuse by the chunk after next
+        if (!g.cta_per_read) CU_TRY(scratch.reserve(place_scratch_bytes(c.count, c.max_len, ix->dix.k_size)));
+        uint32_t nl = 0;
+        cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_res, g, ix->sm_count, st,
+                                     scratch.p, scratch.cap, &nl);
         if (e != cudaSuccess) {
             cudaStreamSynchronize(w->stream); cudaStreamSynchronize(w->stream2);
             if (e == cudaErrorInvalidConfiguration)
                 return fail(CLS_ERR_UNSUPPORTED, "query too long (or tree fan-out too large) for the per-read shared-memory tables");
             return fail(CLS_ERR_CUDA, std::string("place kernel launch: ") + cudaGetErrorString(e));
         }
-        tm.kernel_launches++;
+        tm.kernel_launches += nl;
         CU_TRY(cudaEventRecord(ev[2], st));
         CU_TRY(cudaMemcpyAsync(h_res + c.first, d_res + c.first, (size_t)c.count * sizeof(ResultRec), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaEventRecord(ev[3], st));
@@ -581,7 +599,7 @@ int cls_place_resident(cls_index *ix, cls_resident_batch *rb, const cls_params *
     CU_TRY(cudaSetDevice(ix->device));
     uint64_t launches = 0;
     int rc = launch_classes(ix, rb->lay, params, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p,
-                            (ResultRec *)rb->d_results.p, (cudaStream_t)stream, &launches);
+                            (ResultRec *)rb->d_results.p, (cudaStream_t)stream, rb->d_scratch, &launches);
     if (rc == CLS_OK) { std::lock_guard<std::mutex> lk(ix->mu); ix->timing.kernel_launches = launches; }
     return rc;
 }
@@ -602,7 +620,7 @@ void cls_resident_destroy(cls_resident_batch *rb) {
     if (!rb) return;
     cudaSetDevice(rb->device);
     rb->d_words.release(); rb->d_descs.release(); rb->d_results.release(); rb->h_results.release();
-    rb->d_win_base.release(); rb->d_route_state.release();
+    rb->d_win_base.release(); rb->d_route_state.release(); rb->d_scratch.release();
     delete rb;
 }
 

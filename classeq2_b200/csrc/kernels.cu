@@ -566,9 +566,12 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
 // terminal and its weight - in registers, every vote is one warp reduction, and no loop runs over
 // the sets.  Same algorithm and same outcomes as finish_read<true>.
 // ------------------------------------------------------------------------------------------
+// `set_off[s]` / `weight[s]`: node-set record and number of distinct hits of set lane + 32 s (weight 0 = none);
+// `cnt` / `excl`: zeroed shared-memory vote counters of the warp (fan-out beyond two children only).
 template <int SLOTS>
-__device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const PlaceParams &pp, const ReadTables &tb,
-                                                uint32_t D, uint32_t n_matched, ResultRec *__restrict__ out) {
+__device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const PlaceParams &pp, uint32_t *cnt, uint32_t *excl,
+                                                const uint32_t (&set_off)[SLOTS], const uint32_t (&weight)[SLOTS],
+                                                uint32_t n_matched, ResultRec *__restrict__ out) {
     const uint32_t lane = lane_id();
     const uint32_t *__restrict__ terms = ix.terms;
     const bool ri = pp.remove_intersection != 0;
@@ -578,14 +581,12 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         lo[s] = 0; hi[s] = 0; first[s] = 0xFFFFFFFFu; last[s] = 0; w[s] = 0;
-        const uint32_t j = lane + 32u * s;
-        if (j < D) {
-            const uint32_t p2 = tb.lst[j];
-            const uint32_t off = tb.t2k[p2];
+        if (weight[s]) {
+            const uint32_t off = set_off[s];
             const uint32_t hdr = __ldg(terms + off);
             if (hdr & kTermHasRoot) {
                 last[s] = __ldg(terms + off + 1); first[s] = __ldg(terms + off + 2);
-                w[s] = tb.t2c[p2];
+                w[s] = weight[s];
                 lo[s] = off + 2; hi[s] = lo[s] + (hdr & ~kTermHasRoot);
             }
         }
@@ -688,18 +689,18 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
                 while (pos < hi[s]) {
                     const uint32_t t = __ldg(terms + pos);
                     while (t >= cend) { cend = __ldg(&ix.qinfo[cend].q_end); ++ord; }
-                    atomicAdd(&tb.cnt[ord], w[s]); ++npres; lastc = ord;
+                    atomicAdd(&cnt[ord], w[s]); ++npres; lastc = ord;
                     ++pos;
                     if (pos < hi[s] && __ldg(terms + pos) < cend) pos = lower_bound_terms(terms, pos, hi[s], cend);
                 }
                 u_local += w[s];
-                if (npres == 1) atomicAdd(&tb.excl[lastc], w[s]);
+                if (npres == 1) atomicAdd(&excl[lastc], w[s]);
             }
             const uint32_t U = __reduce_add_sync(kFull, u_local);
             __syncwarp();
-            const Decision dc = decide_smem(tb.cnt, tb.excl, m, U, ri);
+            const Decision dc = decide_smem(cnt, excl, m, U, ri);
             __syncwarp();
-            for (uint32_t o = lane; o < m; o += 32) { tb.cnt[o] = 0; tb.excl[o] = 0; }
+            for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
             __syncwarp();
             nprop = dc.nprop; n_best = dc.n_best; win_one = dc.best_one; win_rest = dc.best_rest;
             win_q = p + 1;
@@ -737,6 +738,20 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
     }
     res.iterations = (uint32_t)iteration;
     if (lane == 0) *out = res;
+}
+
+// The same, fed from the read's shared-memory histogram.
+template <int SLOTS>
+__device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const PlaceParams &pp, const ReadTables &tb,
+                                                uint32_t D, uint32_t n_matched, ResultRec *__restrict__ out) {
+    uint32_t off[SLOTS], wt[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const uint32_t j = lane_id() + 32u * s;
+        off[s] = 0; wt[s] = 0;
+        if (j < D) { const uint32_t p2 = tb.lst[j]; off[s] = tb.t2k[p2]; wt[s] = tb.t2c[p2]; }
+    }
+    finish_read_reg<SLOTS>(ix, pp, tb.cnt, tb.excl, off, wt, n_matched, out);
 }
 
 }  // namespace
@@ -916,6 +931,15 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
 // Reads with more distinct node sets than the scratch holds per read (or any read of a model that
 // is not closed) are finished by their scan warp with finish_read.
 // ------------------------------------------------------------------------------------------
+// Hand-over from the scan kernel to the descent kernel (SPLIT mode): per read of the launch
+//     pairs[r * kPairCap + j] = {node-set record offset, distinct hits with that node set}, j < D
+//     meta[r] = {n_matched, D};  D = kDone: the scan warp finished the read itself (D > kPairCap)
+constexpr uint32_t kPairCap = 64, kDone = 0xFFFFFFFFu;
+struct ScanOut {
+    uint2 *pairs;
+    uint2 *meta;
+};
+
 __device__ __forceinline__ void premix_store(const uint32_t *w, uint32_t sh8, uint64_t *ra, uint64_t *rb) {
     const uint32_t r0 = w[0], r1 = w[1], r2 = w[2];
     const uint64_t x = pack64(__funnelshift_r(r0, r1, sh8), __funnelshift_r(r1, r2, sh8));
@@ -940,10 +964,10 @@ __device__ __forceinline__ uint64_t window_hash35(uint64_t a0, uint64_t b1, uint
 #ifndef CLS_REG_SLOTS2
 #define CLS_REG_SLOTS2 1
 #endif
-template <bool CLOSED>
+template <bool CLOSED, bool SPLIT>
 __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix, PlaceParams pp, const uint32_t *__restrict__ packed,
                                                       const ReadDesc *__restrict__ reads, uint32_t first_read,
-                                                      uint32_t n_reads, ResultRec *__restrict__ results, PlaceGeom g) {
+                                                      uint32_t n_reads, ResultRec *__restrict__ results, PlaceGeom g, ScanOut so) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t tail_lut[64];
     init_tail_lut(tail_lut);
@@ -1060,12 +1084,51 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
         }
         __syncwarp();
         const uint32_t D = *n_sets_smem;
-        if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
-#if CLS_REG_SLOTS2
-        else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
-#endif
-        else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+        if constexpr (SPLIT) {
+            // hand the read over to the descent kernel (its own launch: 64 warps per SM and the whole L1)
+            if (D <= kPairCap) {
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const uint32_t p2 = lst[j];
+                    so.pairs[(size_t)r * kPairCap + j] = make_uint2(t2k[p2], t2c[p2]);
+                }
+                if (lane == 0) so.meta[r] = make_uint2(n_matched, D);
+            } else {
+                finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+                if (lane == 0) so.meta[r] = make_uint2(n_matched, kDone);
+            }
+        } else {
+            if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
+            else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
+            else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+        }
         __syncwarp();
+    }
+}
+
+// One warp per read: gates and descent over the {node set, weight} pairs the scan kernel left.
+__global__ void __launch_bounds__(256) descend_kernel(DeviceIndex ix, PlaceParams pp, ScanOut so, uint32_t first_read,
+                                                      uint32_t n_reads, ResultRec *__restrict__ results, uint32_t fan_cap) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+    uint32_t *cnt = smem + (size_t)warp * 2 * fan_cap, *excl = cnt + fan_cap;
+    for (uint32_t o = lane; o < fan_cap; o += 32) { cnt[o] = 0; excl[o] = 0; }
+    __syncwarp();
+    const uint32_t gwarp = blockIdx.x * warps_per_cta + warp, gstride = gridDim.x * warps_per_cta;
+#pragma unroll 1
+    for (uint32_t r = gwarp; r < n_reads; r += gstride) {
+        const uint2 me = so.meta[r];
+        if (me.y == kDone) continue;
+        const uint2 *pr = so.pairs + (size_t)r * kPairCap;
+        if (me.y <= 32) {
+            uint32_t off[1] = {0}, wt[1] = {0};
+            if (lane < me.y) { const uint2 v = pr[lane]; off[0] = v.x; wt[0] = v.y; }
+            finish_read_reg<1>(ix, pp, cnt, excl, off, wt, me.x, results + first_read + r);
+        } else {
+            uint32_t off[2] = {0, 0}, wt[2] = {0, 0};
+            { const uint2 v = pr[lane]; off[0] = v.x; wt[0] = v.y; }
+            if (lane + 32 < me.y) { const uint2 v = pr[lane + 32]; off[1] = v.x; wt[1] = v.y; }
+            finish_read_reg<2>(ix, pp, cnt, excl, off, wt, me.x, results + first_read + r);
+        }
     }
 }
 
@@ -1133,37 +1196,65 @@ static cudaError_t launch_place_m(const DeviceIndex &ix, const PlaceParams &pp, 
                           : launch_place_t<K, CLOSED, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
 }
 
-// ---- short reads, k = 35: the scan kernel ---------------------------------------------------
+// ---- short reads, k = 35: scan kernel (+ descent kernel when the caller provides the hand-over scratch) ----
+size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k) {
+    static const bool off = getenv("CLS_NO_SPLIT") != nullptr;
+    if (off || k != 35 || max_len < 35 || n_reads == 0) return 0;
+    return (size_t)n_reads * ((size_t)kPairCap * 8 + 8) + 256;
+}
+
 template <bool CLOSED>
 static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                                  const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
-                                 const PlaceGeom &g, int sm_count, cudaStream_t stream) {
+                                 const PlaceGeom &g, int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes,
+                                 uint32_t *n_launches) {
     const size_t ring = (size_t)4 * kRing * 4, group = (size_t)g.words_per_warp * 4;
     int warps = 8;
     while (warps > 1 && (group + ring) * warps > 200 * 1024) warps >>= 1;
     const size_t smem = (group + ring) * warps;
     if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel<CLOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    const bool split = CLOSED && scratch && scratch_bytes >= place_scratch_bytes(n_reads, 35, 35) && place_scratch_bytes(n_reads, 35, 35) &&
+                       (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
+    auto kern = split ? scan_kernel<CLOSED, true> : scan_kernel<CLOSED, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<CLOSED>, warps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
-    scan_kernel<CLOSED><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g);
-    return cudaGetLastError();
+    ScanOut so{nullptr, nullptr};
+    if (split) {
+        char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+        so.pairs = reinterpret_cast<uint2 *>(base);
+        so.meta = so.pairs + (size_t)n_reads * kPairCap;
+    }
+    kern<<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (n_launches) ++*n_launches;
+    if (split) {
+        const size_t dsmem = (size_t)2 * g.fan_cap * 4 * 8;
+        uint32_t dgrid = (uint32_t)(sm_count * 8);
+        if (dgrid > need) dgrid = need;
+        descend_kernel<<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, g.fan_cap);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (n_launches) ++*n_launches;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                          const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
-                         const PlaceGeom &g, int sm_count, cudaStream_t stream) {
+                         const PlaceGeom &g, int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes,
+                         uint32_t *n_launches) {
     if (n_reads == 0) return cudaSuccess;
     if (ix.k_size == 35 && !g.cta_per_read) {
-        return ix.closed ? launch_scan_t<true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
-                         : launch_scan_t<false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+        return ix.closed ? launch_scan_t<true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
+                         : launch_scan_t<false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);
     }
+    if (n_launches) ++*n_launches;
     if (ix.k_size == 35) {
         return ix.closed ? launch_place_t<35, true, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
                          : launch_place_t<35, false, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);

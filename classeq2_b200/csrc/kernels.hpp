@@ -34,9 +34,17 @@ struct PlaceGeom {
 
 PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout);
 
+// Scratch the short-read path (k = 35, closed models) wants for a launch over `n_reads` reads: the scan
+// kernel hands every read's {node set, weight} pairs to a separate descent kernel through it.  0 when that
+// path does not apply.  Without (enough) scratch the scan warps run the descent themselves.
+size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k);
+
+// Places reads [first_read, first_read + n_reads) of a length class.  `n_launches` (optional) is
+// incremented once per kernel launched.
 cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                          const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
-                         const PlaceGeom &g, int sm_count, cudaStream_t stream);
+                         const PlaceGeom &g, int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes,
+                         uint32_t *n_launches);
 
 // ---- hash-sharded index (routed_kernels.cuh) ------------------------------------------------------
 constexpr uint32_t kMaxShards = 8;
