@@ -652,10 +652,8 @@ int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_window
     return CLS_OK;
 }
 
-int cls_route_hashes(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *d_send,
-                     void *d_win_slot, uint64_t *counts_out, void *stream) {
-    if (!ix || !rb || !d_send || !d_win_slot || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
+static int route_hashes_impl(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
+                             void *d_win_slot, uint64_t *counts_out, void *stream) {
     if ((uint64_t)n_shards * seg_cap >= 0xFFFFFFFFull) return fail(CLS_ERR_UNSUPPORTED, "send buffer beyond 2^32 entries: split the batch");
     uint64_t nw = 0;
     int rc = cls_routed_windows(ix, rb, &nw);
@@ -667,7 +665,7 @@ int cls_route_hashes(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, u
     for (const LengthClass &c : rb->lay.classes) {
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         cudaError_t e = launch_route(ix->dix.k_size, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p, c.first, c.count, g,
-                                     (const uint64_t *)rb->d_win_base.p, n_shards, seg_cap, (uint64_t *)d_send, (uint32_t *)d_win_slot,
+                                     (const uint64_t *)rb->d_win_base.p, n_shards, seg_cap, seg_ptrs, (uint32_t *)d_win_slot,
                                      cursor, overflow, ix->sm_count, st);
         if (e == cudaErrorInvalidConfiguration)
             return fail(CLS_ERR_UNSUPPORTED, "the routed path places reads of up to 161 bases (the one-warp-per-read geometry)");
@@ -678,6 +676,68 @@ int cls_route_hashes(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, u
     CU_TRY(cudaStreamSynchronize(st));
     if ((uint32_t)state[8]) return fail(CLS_ERR_OUT_OF_MEMORY, "a shard's segment of the send buffer is too small (seg_cap)");
     for (uint32_t o = 0; o < n_shards; ++o) counts_out[o] = state[o];
+    return CLS_OK;
+}
+
+int cls_route_hashes(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *d_send,
+                     void *d_win_slot, uint64_t *counts_out, void *stream) {
+    if (!ix || !rb || !d_send || !d_win_slot || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
+    uint64_t *seg[kMaxShards] = {nullptr};
+    for (uint32_t o = 0; o < n_shards; ++o) seg[o] = (uint64_t *)d_send + (uint64_t)o * seg_cap;
+    return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_win_slot, counts_out, stream);
+}
+
+int cls_route_hashes_p2p(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *const *d_segments,
+                         void *d_win_slot, uint64_t *counts_out, void *stream) {
+    if (!ix || !rb || !d_segments || !d_win_slot || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
+    uint64_t *seg[kMaxShards] = {nullptr};
+    for (uint32_t o = 0; o < n_shards; ++o) {
+        if (!d_segments[o]) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL segment pointer");
+        seg[o] = (uint64_t *)d_segments[o];
+    }
+    return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_win_slot, counts_out, stream);
+}
+
+// ---- buffers other processes of the box can map (CUDA IPC): the inbox / reply box of the fused exchange ----
+int cls_peer_alloc(int device, uint64_t bytes, void **d_ptr, uint8_t ipc_handle[64]) {
+    if (!d_ptr || !ipc_handle || bytes == 0) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument or zero size");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU_TRY(cudaSetDevice(device));
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return fail(CLS_ERR_OUT_OF_MEMORY, "cudaMalloc of a peer buffer failed"); }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(CLS_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    std::memcpy(ipc_handle, &h, 64);
+    *d_ptr = p;
+    return CLS_OK;
+}
+
+int cls_peer_open(int device, const uint8_t ipc_handle[64], void **d_ptr) {
+    if (!d_ptr || !ipc_handle) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    *d_ptr = p;
+    return CLS_OK;
+}
+
+int cls_peer_close(int device, void *d_ptr) {
+    if (!d_ptr) return CLS_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return CLS_OK;
+}
+
+int cls_peer_free(int device, void *d_ptr) {
+    if (!d_ptr) return CLS_OK;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaFree(d_ptr));
     return CLS_OK;
 }
 

@@ -49,14 +49,20 @@ __device__ __forceinline__ WarpLayout carve_warp(uint32_t *smem, const PlaceGeom
 }
 
 // ---- stage 1 + 2: hash and route ---------------------------------------------------------------
-// send[o * seg_cap + i], i < cursor[o]: the hashes owned by shard o, in no particular order.
-// win_slot[win_base[r] + strand * W + pos] = index into `send` (and later into the reply buffer).
+// seg.p[o][i], i < cursor[o]: the hashes owned by shard o, in no particular order.  seg.p[o] is either
+// this GPU's send buffer + o * seg_cap (the exchange is then an NCCL all-to-all) or a PEER pointer into
+// owner o's inbox (CUDA IPC over NVLink): the stores of this kernel then ARE the exchange, overlapped with
+// the hashing of the next reads, and no collective moves the payload.
+// win_slot[win_base[r] + strand * W + pos] = o * seg_cap + i (where the reply will be found).
 // *overflow is set when a segment would exceed seg_cap (the caller retries with a larger one).
+struct SegPtrs {
+    uint64_t *p[8];
+};
 template <int K>
 __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_t *__restrict__ packed,
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                        uint32_t n_reads, PlaceGeom g, const uint64_t *__restrict__ win_base,
-                                                       uint32_t n_shards, uint64_t seg_cap, uint64_t *__restrict__ send,
+                                                       uint32_t n_shards, uint64_t seg_cap, SegPtrs seg,
                                                        uint32_t *__restrict__ win_slot, unsigned long long *__restrict__ cursor,
                                                        uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -118,9 +124,8 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
                     own_cnt[8 + o] = (uint32_t)(nxt >> 32);
                 }
                 if (at < seg_cap) {
-                    const uint64_t idx = (uint64_t)o * seg_cap + at;
-                    send[idx] = h;
-                    win_slot[wb + w] = (uint32_t)idx;
+                    seg.p[o][at] = h;
+                    win_slot[wb + w] = (uint32_t)((uint64_t)o * seg_cap + at);
                 }
             }
             __syncwarp();
@@ -217,8 +222,10 @@ static inline cudaError_t routed_smem(const PlaceGeom &g, int &warps, size_t &sm
 }
 
 cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
-                         const PlaceGeom &g, const uint64_t *win_base, uint32_t n_shards, uint64_t seg_cap, uint64_t *send,
+                         const PlaceGeom &g, const uint64_t *win_base, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
                          uint32_t *win_slot, unsigned long long *cursor, uint32_t *overflow, int sm_count, cudaStream_t stream) {
+    SegPtrs seg{};
+    for (uint32_t o = 0; o < n_shards && o < 8; ++o) seg.p[o] = seg_ptrs[o];
     if (n_reads == 0) return cudaSuccess;
     if (g.cta_per_read || n_shards == 0 || n_shards > 8) return cudaErrorInvalidConfiguration;
     int warps;
@@ -230,11 +237,11 @@ cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *rea
     if (grid > need) grid = need;
     if (k == 35) {
         if ((e = cudaFuncSetAttribute(route_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
-        route_kernel<35><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, send,
+        route_kernel<35><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, seg,
                                                              win_slot, cursor, overflow);
     } else {
         if ((e = cudaFuncSetAttribute(route_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
-        route_kernel<0><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, send,
+        route_kernel<0><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, seg,
                                                             win_slot, cursor, overflow);
     }
     return cudaGetLastError();

@@ -114,21 +114,79 @@ def segment_views(buf, counts: np.ndarray, seg_cap: int = 0, item: int = 1):
     return [buf[int(off[o]) * item: int(off[o + 1]) * item] for o in range(len(counts))]
 
 
+class PeerBuffers:
+    """Inbox (hashes other ranks route to this one) and reply box (answers to this rank's own hashes) of
+    one rank, allocated by the library and mapped into every peer process of the box through CUDA IPC.
+    ``inbox[r]`` / ``reply[r]`` are the device pointers, valid in THIS process, of rank r's buffers."""
+
+    def __init__(self, device: int, rank: int, world: int, seg_cap: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.device, self.rank, self.world, self.seg_cap = device, rank, world, seg_cap
+        self._own, self._opened = [], []
+
+        def alloc(nbytes):
+            ptr, h = C.c_void_p(), (C.c_uint8 * 64)()
+            _lib.check(_lib.lib.cls_peer_alloc(device, int(nbytes), C.byref(ptr), h))
+            self._own.append(ptr.value)
+            return ptr.value, bytes(h)
+
+        my_in, h_in = alloc(world * seg_cap * 8)
+        my_rep, h_rep = alloc(world * seg_cap * REPLY_BYTES)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, (h_in, h_rep), group=group)
+        self.inbox, self.reply = [0] * world, [0] * world
+        for r in range(world):
+            if r == rank:
+                self.inbox[r], self.reply[r] = my_in, my_rep
+                continue
+            for name, hb in (("inbox", handles[r][0]), ("reply", handles[r][1])):
+                ptr = C.c_void_p()
+                hbuf = (C.c_uint8 * 64).from_buffer_copy(hb)
+                _lib.check(_lib.lib.cls_peer_open(device, hbuf, C.byref(ptr)))
+                self._opened.append(ptr.value)
+                getattr(self, name)[r] = ptr.value
+
+    def close(self):
+        from . import _lib
+
+        for p in self._opened:
+            _lib.lib.cls_peer_close(self.device, p)
+        for p in self._own:
+            _lib.lib.cls_peer_free(self.device, p)
+        self._opened, self._own = [], []
+
+
 class ShardedPlacer:
     """Placement against a hash-sharded index, one instance per rank.
 
-    ``place(seqs)``: route_hashes -> all-to-all (hashes, 8 B each) -> shard_probe -> all-to-all back
-    (replies, 12 B each) -> place_routed.  The three compute stages are the library's CUDA kernels
-    (``cls_route_hashes`` / ``cls_shard_probe`` / ``cls_place_routed``); the exchanges are
-    ``torch.distributed`` collectives on the same device buffers.  With ``world == 1`` no process
-    group is needed (everything is local)."""
+    ``transport="nccl"``: route_hashes -> all-to-all (hashes, 8 B each) -> shard_probe -> all-to-all back
+    (replies, 12 B each) -> place_routed; the exchanges are ``torch.distributed`` collectives on the device
+    buffers.  ``transport="p2p"``: the exchanges are FUSED into the kernels - the route kernel stores every
+    hash straight into its owner's inbox and the probe kernel stores every reply straight into the asking
+    GPU's reply box, both through NVLink peer pointers (CUDA IPC, :class:`PeerBuffers`); NCCL only carries
+    the eight per-owner counts and one barrier per batch.  The compute stages are the library's CUDA kernels
+    in both cases.  With ``world == 1`` no process group is needed."""
 
-    def __init__(self, model, device: int, rank: int, world: int, group=None, slack: float = 1.15):
+    def __init__(self, model, device: int, rank: int, world: int, group=None, slack: float = 1.15,
+                 transport: str = "nccl", max_windows: int = 0):
         from .engine import Index
 
         self.rank, self.world, self.group, self.slack = rank, world, group, slack
         self.index = Index(model, device=device, shard=rank, n_shards=world)
         self.device = device
+        self.transport = transport
+        self.peers = None
+        if transport == "p2p":
+            if max_windows <= 0:
+                raise ValueError("transport='p2p' needs max_windows (k-mer windows of the largest batch)")
+            self.peers = PeerBuffers(device, rank, world, int(max_windows / world * slack) + 65536, group)
+        elif transport != "nccl":
+            raise ValueError("transport must be 'nccl' or 'p2p'")
 
     def place(self, seqs, params=None) -> BatchResult:
         """Host buffers in, host arrays out: upload, the routed pipeline, fetch."""
@@ -144,6 +202,8 @@ class ShardedPlacer:
         """The routed pipeline over a batch already resident in HBM, enqueued on torch's current
         stream (the host only waits for the per-owner counts, which size the exchange).  Results stay
         on the device (``rb.fetch``).  ``self.timing`` holds the CUDA-event time of every stage."""
+        if self.transport == "p2p":
+            return self._place_resident_p2p(rb, params)
         import torch
 
         dev = torch.device("cuda", self.device)
@@ -183,7 +243,49 @@ class ShardedPlacer:
         rb.place_routed(rep_in.data_ptr(), win_slot.data_ptr(), params, st.cuda_stream)
         ev[5].record(st)
         self._events = ev
+        self._stage_names = ["route_ms", "send_ms", "probe_ms", "reply_ms", "place_ms"]
         remote = int(counts_to.sum() - counts_to[self.rank]), int(counts_from.sum() - counts_from[self.rank])
+        self._stats = dict(n_windows=nw, routed_out=remote[0], routed_in=remote[1],
+                           wire_bytes_out=remote[0] * 8 + remote[1] * REPLY_BYTES,
+                           wire_bytes_in=remote[1] * 8 + remote[0] * REPLY_BYTES)
+
+    def _place_resident_p2p(self, rb, params=None) -> None:
+        import torch
+        import torch.distributed as dist
+
+        dev = torch.device("cuda", self.device)
+        st = torch.cuda.current_stream(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        pb, world, me = self.peers, self.world, self.rank
+        nw = rb.routed_windows()
+        if int(nw / world * self.slack) + 65536 > pb.seg_cap:
+            raise ValueError("batch has more k-mer windows than the peer buffers were sized for (max_windows)")
+        seg_cap = pb.seg_cap
+        b = getattr(self, "_buf", None)
+        if b is None or b["win_slot"].numel() < max(nw, 1):
+            b = dict(win_slot=torch.empty(max(nw, 1), dtype=torch.int32, device=dev),
+                     token=torch.zeros(1, dtype=torch.int32, device=dev))
+            self._buf = b
+        ev[0].record(st)
+        # stage 1+2+3: hash, group by owner, and store into the owners' inboxes (my segment of each)
+        seg_ptrs = [pb.inbox[o] + me * seg_cap * 8 for o in range(world)]
+        counts_to = rb.route_hashes_p2p(world, seg_cap, seg_ptrs, b["win_slot"].data_ptr(), st.cuda_stream).astype(np.int64)
+        ev[1].record(st)
+        # the counts all-to-all doubles as "every rank's route kernel has completed": my inbox is whole
+        counts_from = exchange_plan(counts_to, self.group) if world > 1 else counts_to.copy()
+        ev[2].record(st)
+        # stage 4+5: answer every sender's segment straight into that sender's reply box (my segment of it)
+        for s_rank in range(world):
+            self.index.shard_probe(pb.inbox[me] + s_rank * seg_cap * 8, int(counts_from[s_rank]),
+                                   pb.reply[s_rank] + me * seg_cap * REPLY_BYTES, st.cuda_stream)
+        if world > 1:
+            dist.all_reduce(b["token"], group=self.group)  # barrier on the stream: every probe kernel has completed
+        ev[3].record(st)
+        rb.place_routed(pb.reply[me], b["win_slot"].data_ptr(), params, st.cuda_stream)
+        ev[4].record(st)
+        self._events = ev
+        self._stage_names = ["route_ms", "counts_ms", "probe_ms", "place_ms"]
+        remote = int(counts_to.sum() - counts_to[me]), int(counts_from.sum() - counts_from[me])
         self._stats = dict(n_windows=nw, routed_out=remote[0], routed_in=remote[1],
                            wire_bytes_out=remote[0] * 8 + remote[1] * REPLY_BYTES,
                            wire_bytes_in=remote[1] * 8 + remote[0] * REPLY_BYTES)
@@ -209,11 +311,15 @@ class ShardedPlacer:
         if ev is None:
             return {}
         ev[-1].synchronize()
-        names = ["route_ms", "send_ms", "probe_ms", "reply_ms", "place_ms"]
-        t = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
-        t["total_ms"] = ev[0].elapsed_time(ev[5])
+        t = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(self._stage_names)}
+        t["total_ms"] = ev[0].elapsed_time(ev[-1])
         t.update(self._stats)
         return t
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
 
 
 class LocalShardedPlacer:

@@ -256,6 +256,26 @@ int cls_routed_windows(cls_index *index, cls_resident_batch *rb, uint64_t *n_win
 int cls_route_hashes(cls_index *index, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap,
                      void *d_send, void *d_win_slot, uint64_t *counts_out, void *stream);
 int cls_shard_probe(cls_index *index, const void *d_hashes, uint64_t n, void *d_replies, void *stream);
+
+/*
+ * The same pipeline with the exchange FUSED into the kernels over NVLink peer memory (no collective
+ * moves the payload).  Every rank owns an inbox (n_shards segments of seg_cap hashes) and a reply box
+ * (n_shards segments of seg_cap replies) allocated with cls_peer_alloc, publishes their CUDA IPC
+ * handles, and maps its peers' with cls_peer_open.  Then
+ *   cls_route_hashes_p2p   d_segments[o] = owner o's inbox + my_rank * seg_cap (a peer pointer):
+ *                          the route kernel stores every hash straight into its owner's memory;
+ *   (counts all-to-all, 8 integers - also the point after which the inboxes are complete)
+ *   cls_shard_probe        once per sender s: hashes = my inbox + s * seg_cap, replies = sender s's
+ *                          reply box + my_rank * seg_cap (a peer pointer): the probe kernel stores
+ *                          every reply straight into the memory of the GPU that asked;
+ *   (barrier)  cls_place_routed on the local reply box.
+ */
+int cls_route_hashes_p2p(cls_index *index, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap,
+                         void *const *d_segments, void *d_win_slot, uint64_t *counts_out, void *stream);
+int cls_peer_alloc(int device, uint64_t bytes, void **d_ptr, uint8_t ipc_handle[64]);
+int cls_peer_open(int device, const uint8_t ipc_handle[64], void **d_ptr);
+int cls_peer_close(int device, void *d_ptr);
+int cls_peer_free(int device, void *d_ptr);
 int cls_place_routed(cls_index *index, cls_resident_batch *rb, const void *d_replies, const void *d_win_slot,
                      const cls_params *params, void *stream);
 

@@ -192,6 +192,14 @@ want = cq.Index(sm.flat, device=local).place_batch((bases, offsets))
 sp = ShardedPlacer(sm.flat, local, rank, world)
 got = sp.place((bases, offsets))
 bad = {n: int((getattr(got, n) != getattr(want, n)).sum()) for n, _ in RESULT_DTYPES}
+# the same with the exchange fused into the kernels (peer stores over NVLink instead of NCCL all-to-alls), twice
+# in a row so that the reuse of the inboxes / reply boxes is exercised
+sp2 = ShardedPlacer(sm.flat, local, rank, world, transport="p2p", max_windows=2 * 116 * 6000)
+for _ in range(2):
+    got2 = sp2.place((bases, offsets))
+    for n, _ in RESULT_DTYPES:
+        bad[n] += int((getattr(got2, n) != getattr(want, n)).sum())
+sp2.close()
 flags = [None] * world
 dist.all_gather_object(flags, (bad, sp.timing["routed_out"], sp.index.info()["n_entries"]))
 if rank == 0:
