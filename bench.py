@@ -342,7 +342,9 @@ def run_sharded(args, rank, world, local_rank):
     lens = np.diff(offsets.astype(np.int64))
     lookups_local = int((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum())
     t0 = time.time()
-    sp = ShardedPlacer(sm.flat, local_rank, rank, world)
+    max_w = int(2 * (lens[lens >= K_SIZE] - K_SIZE + 1)[:1_250_000].sum()) if n_local else 0
+    max_w = max(max_w, 2 * 116 * min(n_local, 1_250_000))
+    sp = ShardedPlacer(sm.flat, local_rank, rank, world, transport=args.transport, max_windows=max_w)
     info = sp.index.info()
     upload_s = time.time() - t0
     params = cq.PlaceParams()
@@ -429,7 +431,7 @@ def run_sharded(args, rank, world, local_rank):
         n_device = int((lens >= K_SIZE).sum())
         kern_ms = per.get("route_ms", 0) + per.get("probe_ms", 0) + per.get("place_ms", 0)
         alg = algorithmic_bytes(lens)
-        wire_ms = per.get("send_ms", 0) + per.get("reply_ms", 0)
+        wire_ms = (per.get("send_ms", 0) + per.get("reply_ms", 0)) if args.transport == "nccl" else (per.get("route_ms", 0) + per.get("probe_ms", 0))
         line = {
             "metric": "queries placed/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
@@ -437,7 +439,11 @@ def run_sharded(args, rank, world, local_rank):
             "config": {"workload": NAMES[5], "reads_per_gpu": n_local, "reads_total": int(reads_total), "k": K_SIZE, "m": 4,
                        "index_entries_this_shard": int(info["n_entries"]), "index_entries_total": int(rep_info["n_entries"]),
                        "table_bytes_this_shard": int(info["table_bytes"]), "distinct_node_sets": int(info["n_distinct_sets"]),
-                       "parallelism": f"queries sharded x{world}, k-mer table hash-sharded x{world}, 2 NCCL all-to-alls per sub-batch",
+                       "parallelism": (f"queries sharded x{world}, k-mer table hash-sharded x{world}, exchange fused into the route / probe "
+                                       "kernels over NVLink peer memory (CUDA IPC); NCCL carries 8 counts + 1 barrier per sub-batch")
+                       if args.transport == "p2p" else
+                       f"queries sharded x{world}, k-mer table hash-sharded x{world}, 2 NCCL all-to-alls per sub-batch",
+                       "transport": args.transport,
                        "sub_batch_reads": sub, "l2": "256 MiB memset between steps (outside the event pairs)"},
             "lookups_per_s": lookups_total / (ms_per_step / 1e3),
             "e2e": {"value": reads_total / e2e_s, "unit": "reads/s", "ms_per_step": e2e_s * 1e3,
@@ -451,7 +457,8 @@ def run_sharded(args, rank, world, local_rank):
                          "note": "the exchange is NVLink-bound: see `nvlink`"},
             "nvlink": {"wire_ms_per_step_rank0": wire_ms, "bytes_out_per_step_rank0": per.get("wire_bytes_out", 0),
                        "achieved_gbs_out_rank0": per.get("wire_bytes_out", 0) / (wire_ms / 1e3) / 1e9 if wire_ms else None,
-                       "peak_gbs_per_direction": 900.0, "bytes_per_routed_kmer": 20},
+                       "peak_gbs_per_direction": 900.0, "bytes_per_routed_kmer": 20,
+                       "note": "p2p: the wire time IS the route + probe kernels (stores into peer memory)" if args.transport == "p2p" else "nccl: send + reply all-to-alls"},
             "stage_ms_per_step_rank0": {k: round(v, 3) for k, v in per.items() if k.endswith("_ms")},
             "cpu_baseline": None, "clocks": clocks,
             "parity": {"checked_reads": n_chk, "mismatching_fields": bad,
@@ -465,6 +472,8 @@ def run_sharded(args, rank, world, local_rank):
         rb.close()
     if world > 1:
         dist.barrier()
+    sp.close()
+    if world > 1:
         dist.destroy_process_group()
 
 
@@ -476,6 +485,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--reads", type=int, default=None, help="override the number of reads of the config")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="config 5: how routed k-mers cross NVLink")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
