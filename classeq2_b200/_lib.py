@@ -103,7 +103,7 @@ PROTOTYPES = {
     "cls_peer_open": (C.c_int, [C.c_int, u8p, C.POINTER(C.c_void_p)]),
     "cls_peer_close": (C.c_int, [C.c_int, C.c_void_p]),
     "cls_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
-    "cls_place_routed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p]),
+    "cls_place_routed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(Params), C.c_void_p]),
     "cls_debug_kmer_hashes": (C.c_int, [C.c_int, C.c_uint32, u8p, C.c_uint64, u64p, C.c_uint64, u64p]),
     "cls_debug_host_murmur3_x64_128_h1": (C.c_uint64, [u8p, C.c_uint64, C.c_uint64]),
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),

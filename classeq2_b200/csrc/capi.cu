@@ -131,7 +131,7 @@ struct cls_resident_batch {
     PackedLayout lay;
     DevBuf d_words, d_descs, d_results;
     DevBuf d_scratch;  // scan -> descent hand-over (one placement of this batch in flight at a time)
-    DevBuf d_win_base, d_route_state;  // routed path: first window of every read; per-owner cursors + overflow flag
+    DevBuf d_win_base, d_route_state, d_runs;  // routed path: first window of every read; per-owner cursors + overflow flag
     uint64_t n_windows = 0;
     PinBuf h_results;
 };
@@ -620,7 +620,7 @@ void cls_resident_destroy(cls_resident_batch *rb) {
     if (!rb) return;
     cudaSetDevice(rb->device);
     rb->d_words.release(); rb->d_descs.release(); rb->d_results.release(); rb->h_results.release();
-    rb->d_win_base.release(); rb->d_route_state.release(); rb->d_scratch.release();
+    rb->d_win_base.release(); rb->d_route_state.release(); rb->d_runs.release(); rb->d_scratch.release();
     delete rb;
 }
 
@@ -646,6 +646,7 @@ int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_window
         CU_TRY(rb->d_win_base.reserve(base.size() * 8));
         CU_TRY(cudaMemcpy(rb->d_win_base.p, base.data(), base.size() * 8, cudaMemcpyHostToDevice));
         CU_TRY(rb->d_route_state.reserve(256));
+        CU_TRY(rb->d_runs.reserve((size_t)lay.n_device * 8 * sizeof(uint2) + 64));
         rb->n_windows = acc;
     }
     *n_windows = rb->n_windows;
@@ -653,7 +654,7 @@ int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_window
 }
 
 static int route_hashes_impl(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
-                             void *d_win_slot, uint64_t *counts_out, void *stream) {
+                             void *d_slot_win, uint64_t *counts_out, void *stream) {
     if ((uint64_t)n_shards * seg_cap >= 0xFFFFFFFFull) return fail(CLS_ERR_UNSUPPORTED, "send buffer beyond 2^32 entries: split the batch");
     uint64_t nw = 0;
     int rc = cls_routed_windows(ix, rb, &nw);
@@ -665,8 +666,8 @@ static int route_hashes_impl(cls_index *ix, cls_resident_batch *rb, uint32_t n_s
     for (const LengthClass &c : rb->lay.classes) {
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         cudaError_t e = launch_route(ix->dix.k_size, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p, c.first, c.count, g,
-                                     (const uint64_t *)rb->d_win_base.p, n_shards, seg_cap, seg_ptrs, (uint32_t *)d_win_slot,
-                                     cursor, overflow, ix->sm_count, st);
+                                     (const uint64_t *)rb->d_win_base.p, n_shards, seg_cap, seg_ptrs, (uint16_t *)d_slot_win,
+                                     (uint2 *)rb->d_runs.p, cursor, overflow, ix->sm_count, st);
         if (e == cudaErrorInvalidConfiguration)
             return fail(CLS_ERR_UNSUPPORTED, "the routed path places reads of up to 161 bases (the one-warp-per-read geometry)");
         if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("route kernel launch: ") + cudaGetErrorString(e));
@@ -680,24 +681,24 @@ static int route_hashes_impl(cls_index *ix, cls_resident_batch *rb, uint32_t n_s
 }
 
 int cls_route_hashes(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *d_send,
-                     void *d_win_slot, uint64_t *counts_out, void *stream) {
-    if (!ix || !rb || !d_send || !d_win_slot || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+                     void *d_slot_win, uint64_t *counts_out, void *stream) {
+    if (!ix || !rb || !d_send || !d_slot_win || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
     uint64_t *seg[kMaxShards] = {nullptr};
     for (uint32_t o = 0; o < n_shards; ++o) seg[o] = (uint64_t *)d_send + (uint64_t)o * seg_cap;
-    return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_win_slot, counts_out, stream);
+    return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_slot_win, counts_out, stream);
 }
 
 int cls_route_hashes_p2p(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *const *d_segments,
-                         void *d_win_slot, uint64_t *counts_out, void *stream) {
-    if (!ix || !rb || !d_segments || !d_win_slot || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+                         void *d_slot_win, uint64_t *counts_out, void *stream) {
+    if (!ix || !rb || !d_segments || !d_slot_win || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
     uint64_t *seg[kMaxShards] = {nullptr};
     for (uint32_t o = 0; o < n_shards; ++o) {
         if (!d_segments[o]) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL segment pointer");
         seg[o] = (uint64_t *)d_segments[o];
     }
-    return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_win_slot, counts_out, stream);
+    return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_slot_win, counts_out, stream);
 }
 
 // ---- buffers other processes of the box can map (CUDA IPC): the inbox / reply box of the fused exchange ----
@@ -749,17 +750,25 @@ int cls_shard_probe(cls_index *ix, const void *d_hashes, uint64_t n, void *d_rep
     return CLS_OK;
 }
 
-int cls_place_routed(cls_index *ix, cls_resident_batch *rb, const void *d_replies, const void *d_win_slot,
-                     const cls_params *params, void *stream) {
-    if (!ix || !rb || !params || !d_replies || !d_win_slot) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+int cls_place_routed(cls_index *ix, cls_resident_batch *rb, const void *d_replies, const void *d_slot_win,
+                     uint32_t n_shards, uint64_t seg_cap, const cls_params *params, void *stream) {
+    if (!ix || !rb || !params || !d_replies || !d_slot_win) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
     if (!rb->d_win_base.p) return fail(CLS_ERR_INVALID_ARGUMENT, "cls_route_hashes has not run on this batch");
     CU_TRY(cudaSetDevice(ix->device));
     const PlaceParams pp = make_place_params(params);
+    size_t want = 0;
+    for (const LengthClass &c : rb->lay.classes) want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size));
+    if (want > rb->d_scratch.cap) {
+        if (rb->d_scratch.p) CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        CU_TRY(rb->d_scratch.reserve(want));
+    }
     for (const LengthClass &c : rb->lay.classes) {
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         cudaError_t e = launch_place_routed(ix->dix, pp, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p, c.first, c.count,
-                                            (ResultRec *)rb->d_results.p, g, (const uint64_t *)rb->d_win_base.p,
-                                            (const uint32_t *)d_win_slot, d_replies, ix->sm_count, (cudaStream_t)stream);
+                                            (ResultRec *)rb->d_results.p, g, n_shards, seg_cap, (const uint2 *)rb->d_runs.p,
+                                            (const uint16_t *)d_slot_win, d_replies, ix->sm_count, (cudaStream_t)stream,
+                                            rb->d_scratch.p, rb->d_scratch.cap);
         if (e == cudaErrorInvalidConfiguration)
             return fail(CLS_ERR_UNSUPPORTED, "the routed path places reads of up to 161 bases (the one-warp-per-read geometry)");
         if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("routed place kernel launch: ") + cudaGetErrorString(e));

@@ -51,13 +51,13 @@ constexpr uint32_t kMaxShards = 8;
 constexpr uint32_t kProbeReplyBytes = 12;
 cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
                          const PlaceGeom &g, const uint64_t *win_base, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
-                         uint32_t *win_slot, unsigned long long *cursor, uint32_t *overflow, int sm_count, cudaStream_t stream);
+                         uint16_t *slot_win, uint2 *runs, unsigned long long *cursor, uint32_t *overflow, int sm_count, cudaStream_t stream);
 cudaError_t launch_shard_probe(const DeviceIndex &ix, uint32_t shard, const uint64_t *hashes, uint64_t n, void *replies,
                                cudaStream_t stream);
 cudaError_t launch_place_routed(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed, const ReadDesc *reads,
                                 uint32_t first_read, uint32_t n_reads, ResultRec *results, const PlaceGeom &g,
-                                const uint64_t *win_base, const uint32_t *win_slot, const void *replies, int sm_count,
-                                cudaStream_t stream);
+                                uint32_t n_shards, uint64_t seg_cap, const uint2 *runs, const uint16_t *slot_win, const void *replies,
+                                int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes);
 
 cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, uint64_t *out, cudaStream_t stream);
 

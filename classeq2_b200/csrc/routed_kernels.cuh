@@ -5,11 +5,12 @@
 //
 //   route_kernel         home GPU, one warp per read: decode + hash every window (the same code as the
 //                        placement kernel), group the hashes by owner and append each group to that
-//                        owner's segment of the send buffer; win_slot[window] = where it went
+//                        owner's segment of the send buffer; the read's run in every segment and the window
+//                        of every slot are kept at home
 //   shard_probe_kernel   owner GPU, one thread per received hash: probe the local table shard, answer
 //                        {node-set record offset | kEmpty, globally unique slot id, bucket prefix code}
 //   place_routed_kernel  home GPU, one warp per read: the placement kernel with the table probe replaced
-//                        by a read of the reply at win_slot[window]; gating, de-duplication, histogram
+//                        by coalesced reads of the read's runs of replies; gating, de-duplication, histogram
 //                        and descent are the shared code (insert_hits, finish_read_reg, finish_read)
 //
 // Included at the end of kernels.cu (inside namespace cls): it shares that file's device helpers.
@@ -53,7 +54,8 @@ __device__ __forceinline__ WarpLayout carve_warp(uint32_t *smem, const PlaceGeom
 // this GPU's send buffer + o * seg_cap (the exchange is then an NCCL all-to-all) or a PEER pointer into
 // owner o's inbox (CUDA IPC over NVLink): the stores of this kernel then ARE the exchange, overlapped with
 // the hashing of the next reads, and no collective moves the payload.
-// win_slot[win_base[r] + strand * W + pos] = o * seg_cap + i (where the reply will be found).
+// The hashes of one read occupy one contiguous RUN per owner: runs[r * 8 + o] = {first slot, count}, and
+// slot_win[o * seg_cap + i] = strand * W + pos of the window behind slot i (the reply comes back at the same index).
 // *overflow is set when a segment would exceed seg_cap (the caller retries with a larger one).
 struct SegPtrs {
     uint64_t *p[8];
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                        uint32_t n_reads, PlaceGeom g, const uint64_t *__restrict__ win_base,
                                                        uint32_t n_shards, uint64_t seg_cap, SegPtrs seg,
-                                                       uint32_t *__restrict__ win_slot, unsigned long long *__restrict__ cursor,
-                                                       uint32_t *__restrict__ overflow) {
+                                                       uint16_t *__restrict__ slot_win, uint2 *__restrict__ runs,
+                                                       unsigned long long *__restrict__ cursor, uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t tail_lut[64];
     init_tail_lut(tail_lut);
@@ -102,9 +104,9 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
             if (base + c > seg_cap) *overflow = 1u;
             own_cnt[lane] = (uint32_t)base;
             own_cnt[8 + lane] = (uint32_t)(base >> 32);
+            runs[(size_t)(first_read + r) * 8 + lane] = make_uint2((uint32_t)base, base + c > seg_cap ? 0u : c);
         }
         __syncwarp();
-        const uint64_t wb = win_base[first_read + r];
         for (uint32_t w0 = 0; w0 < 2 * W; w0 += 32) {
             const uint32_t w = w0 + lane;
             const bool valid = w < 2 * W;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
                 }
                 if (at < seg_cap) {
                     seg.p[o][at] = h;
-                    win_slot[wb + w] = (uint32_t)((uint64_t)o * seg_cap + at);
+                    slot_win[(uint64_t)o * seg_cap + at] = (uint16_t)w;
                 }
             }
             __syncwarp();
@@ -155,13 +157,13 @@ __global__ void __launch_bounds__(256) shard_probe_kernel(DeviceIndex ix, uint32
 }
 
 // ---- stage 6: count and descend at home -------------------------------------------------------
-template <bool CLOSED>
+template <bool CLOSED, bool SPLIT>
 __global__ void __launch_bounds__(256, 4) place_routed_kernel(DeviceIndex ix, PlaceParams pp, const uint32_t *__restrict__ packed,
                                                               const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                               uint32_t n_reads, ResultRec *__restrict__ results, PlaceGeom g,
-                                                              const uint64_t *__restrict__ win_base,
-                                                              const uint32_t *__restrict__ win_slot,
-                                                              const ProbeReply *__restrict__ replies) {
+                                                              uint32_t n_shards, uint64_t seg_cap, const uint2 *__restrict__ runs,
+                                                              const uint16_t *__restrict__ slot_win,
+                                                              const ProbeReply *__restrict__ replies, ScanOut so) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
     WarpLayout wl = carve_warp(smem, g, warp, warps_per_cta);
@@ -182,32 +184,54 @@ __global__ void __launch_bounds__(256, 4) place_routed_kernel(DeviceIndex ix, Pl
             if (lane == 0) *wl.n_sets = 0;
         }
         decode_read(packed + rd.word_off, L, wl.wm, g.pk_words);  // the packed strands gate the hits
+        const uint2 my_run = lane < n_shards ? runs[(size_t)(first_read + r) * 8 + lane] : make_uint2(0u, 0u);
         __syncwarp();
-        const uint64_t wb = win_base[first_read + r];
         uint32_t n_matched = 0;
-        for (uint32_t w0 = 0; w0 < 2 * W; w0 += 32) {
-            const uint32_t w = w0 + lane;
-            const bool valid = w < 2 * W;
-            ProbeReply rep{kEmpty, 0u, 0u};
-            if (valid) rep = replies[win_slot[wb + w]];
-            bool hit = valid && rep.set_off != kEmpty;
-            if (hit) {
-                // bucket gating: the entry's bucket key must be among the query's prefix keys
-                const bool rc = w >= W;
-                const uint32_t pos = rc ? w - W : w;
-                hit = packed_bits(rc ? wl.wm.pk_r : wl.wm.pk_f, pos, code_mask) == rep.code;
-                if (!hit) {
-                    for (uint32_t q = 0; q < W && !hit; ++q)
-                        hit = packed_bits(wl.wm.pk_f, q, code_mask) == rep.code || packed_bits(wl.wm.pk_r, q, code_mask) == rep.code;
+        // the replies of this read come back as one contiguous run per owner: coalesced loads
+        for (uint32_t o = 0; o < n_shards; ++o) {
+            const uint32_t base = __shfl_sync(kFull, my_run.x, o), cnt = __shfl_sync(kFull, my_run.y, o);
+            for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool valid = i < cnt;
+                ProbeReply rep{kEmpty, 0u, 0u};
+                uint32_t w = 0;
+                if (valid) {
+                    const uint64_t idx = (uint64_t)o * seg_cap + base + i;
+                    rep = replies[idx];
+                    w = slot_win[idx];
                 }
+                bool hit = valid && rep.set_off != kEmpty;
+                if (hit) {
+                    // bucket gating: the entry's bucket key must be among the query's prefix keys
+                    const bool rc = w >= W;
+                    const uint32_t pos = rc ? w - W : w;
+                    hit = packed_bits(rc ? wl.wm.pk_r : wl.wm.pk_f, pos, code_mask) == rep.code;
+                    if (!hit) {
+                        for (uint32_t q = 0; q < W && !hit; ++q)
+                            hit = packed_bits(wl.wm.pk_f, q, code_mask) == rep.code || packed_bits(wl.wm.pk_r, q, code_mask) == rep.code;
+                    }
+                }
+                n_matched += insert_hits<false>(tb, hit, rep.slot, rep.set_off);
             }
-            n_matched += insert_hits<false>(tb, hit, rep.slot, rep.set_off);
         }
         __syncwarp();
         const uint32_t D = *wl.n_sets;
-        if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
-        else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
-        else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+        if constexpr (SPLIT) {  // hand the read over to descend_kernel, like scan_kernel does
+            if (D <= kPairCap) {
+                for (uint32_t j = lane; j < D; j += 32) {
+                    const uint32_t p2 = wl.lst[j];
+                    so.pairs[(size_t)r * kPairCap + j] = make_uint2(wl.t2k[p2], wl.t2c[p2]);
+                }
+                if (lane == 0) so.meta[r] = make_uint2(n_matched, D);
+            } else {
+                finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+                if (lane == 0) so.meta[r] = make_uint2(n_matched, kDone);
+            }
+        } else {
+            if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
+            else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
+            else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+        }
         __syncwarp();
     }
 }
@@ -223,7 +247,7 @@ static inline cudaError_t routed_smem(const PlaceGeom &g, int &warps, size_t &sm
 
 cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
                          const PlaceGeom &g, const uint64_t *win_base, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
-                         uint32_t *win_slot, unsigned long long *cursor, uint32_t *overflow, int sm_count, cudaStream_t stream) {
+                         uint16_t *slot_win, uint2 *runs, unsigned long long *cursor, uint32_t *overflow, int sm_count, cudaStream_t stream) {
     SegPtrs seg{};
     for (uint32_t o = 0; o < n_shards && o < 8; ++o) seg.p[o] = seg_ptrs[o];
     if (n_reads == 0) return cudaSuccess;
@@ -238,11 +262,11 @@ cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *rea
     if (k == 35) {
         if ((e = cudaFuncSetAttribute(route_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
         route_kernel<35><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, seg,
-                                                             win_slot, cursor, overflow);
+                                                             slot_win, runs, cursor, overflow);
     } else {
         if ((e = cudaFuncSetAttribute(route_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
         route_kernel<0><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, seg,
-                                                            win_slot, cursor, overflow);
+                                                            slot_win, runs, cursor, overflow);
     }
     return cudaGetLastError();
 }
@@ -258,8 +282,8 @@ cudaError_t launch_shard_probe(const DeviceIndex &ix, uint32_t shard, const uint
 
 cudaError_t launch_place_routed(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed, const ReadDesc *reads,
                                 uint32_t first_read, uint32_t n_reads, ResultRec *results, const PlaceGeom &g,
-                                const uint64_t *win_base, const uint32_t *win_slot, const void *replies, int sm_count,
-                                cudaStream_t stream) {
+                                uint32_t n_shards, uint64_t seg_cap, const uint2 *runs, const uint16_t *slot_win, const void *replies,
+                                int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes) {
     if (n_reads == 0) return cudaSuccess;
     if (g.cta_per_read) return cudaErrorInvalidConfiguration;
     int warps;
@@ -270,12 +294,23 @@ cudaError_t launch_place_routed(const DeviceIndex &ix, const PlaceParams &pp, co
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
     const ProbeReply *rp = reinterpret_cast<const ProbeReply *>(replies);
-    if (ix.closed) {
-        if ((e = cudaFuncSetAttribute(place_routed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
-        place_routed_kernel<true><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, win_base, win_slot, rp);
-    } else {
-        if ((e = cudaFuncSetAttribute(place_routed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
-        place_routed_kernel<false><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, win_base, win_slot, rp);
+    const size_t want = place_scratch_bytes(n_reads, 35, 35);
+    const bool split = ix.closed && scratch && want && scratch_bytes >= want && (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
+    ScanOut so{nullptr, nullptr};
+    if (split) {
+        char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+        so.pairs = reinterpret_cast<uint2 *>(base);
+        so.meta = so.pairs + (size_t)n_reads * kPairCap;
     }
-    return cudaGetLastError();
+    auto kern = split ? place_routed_kernel<true, true> : (ix.closed ? place_routed_kernel<true, false> : place_routed_kernel<false, false>);
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
+    kern<<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, n_shards, seg_cap, runs, slot_win, rp, so);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (split) {
+        uint32_t dgrid = (uint32_t)(sm_count * 8);
+        if (dgrid > need) dgrid = need;
+        descend_kernel<<<dgrid, 256, (size_t)2 * g.fan_cap * 4 * 8, stream>>>(ix, pp, so, first_read, n_reads, results, g.fan_cap);
+        e = cudaGetLastError();
+    }
+    return e;
 }

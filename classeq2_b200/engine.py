@@ -178,27 +178,28 @@ class ResidentBatch:
         _lib.check(_lib.lib.cls_routed_windows(self.index._h, self._h, C.byref(n)))
         return int(n.value)
 
-    def route_hashes(self, n_shards: int, seg_cap: int, d_send: int, d_win_slot: int, stream: int = 0) -> np.ndarray:
+    def route_hashes(self, n_shards: int, seg_cap: int, d_send: int, d_slot_win: int, stream: int = 0) -> np.ndarray:
         """``cls_route_hashes``: fills the caller's device buffers (raw pointers) and returns the number
         of hashes routed to every owner."""
         counts = np.zeros(8, dtype=np.uint64)
         _lib.check(_lib.lib.cls_route_hashes(self.index._h, self._h, int(n_shards), int(seg_cap), C.c_void_p(d_send),
-                                             C.c_void_p(d_win_slot), _ptr(counts, _lib.u64p), C.c_void_p(stream)))
+                                             C.c_void_p(d_slot_win), _ptr(counts, _lib.u64p), C.c_void_p(stream)))
         return counts[:n_shards].copy()
 
-    def route_hashes_p2p(self, n_shards: int, seg_cap: int, seg_ptrs, d_win_slot: int, stream: int = 0) -> np.ndarray:
+    def route_hashes_p2p(self, n_shards: int, seg_cap: int, seg_ptrs, d_slot_win: int, stream: int = 0) -> np.ndarray:
         """``cls_route_hashes_p2p``: ``seg_ptrs[o]`` is where owner ``o`` keeps the hashes of THIS rank (a
         peer pointer into its inbox); the route kernel stores there directly over NVLink."""
         counts = np.zeros(8, dtype=np.uint64)
         arr = (C.c_void_p * 8)(*[C.c_void_p(int(p)) for p in seg_ptrs] + [None] * (8 - len(seg_ptrs)))
         _lib.check(_lib.lib.cls_route_hashes_p2p(self.index._h, self._h, int(n_shards), int(seg_cap), arr,
-                                                 C.c_void_p(d_win_slot), _ptr(counts, _lib.u64p), C.c_void_p(stream)))
+                                                 C.c_void_p(d_slot_win), _ptr(counts, _lib.u64p), C.c_void_p(stream)))
         return counts[:n_shards].copy()
 
-    def place_routed(self, d_replies: int, d_win_slot: int, params: Optional[PlaceParams] = None, stream: int = 0) -> None:
+    def place_routed(self, d_replies: int, d_slot_win: int, n_shards: int, seg_cap: int,
+                     params: Optional[PlaceParams] = None, stream: int = 0) -> None:
         cp = (params or PlaceParams()).to_c()
-        _lib.check(_lib.lib.cls_place_routed(self.index._h, self._h, C.c_void_p(d_replies), C.c_void_p(d_win_slot),
-                                             C.byref(cp), C.c_void_p(stream)))
+        _lib.check(_lib.lib.cls_place_routed(self.index._h, self._h, C.c_void_p(d_replies), C.c_void_p(d_slot_win),
+                                             int(n_shards), int(seg_cap), C.byref(cp), C.c_void_p(stream)))
 
     def close(self):
         if self._h:

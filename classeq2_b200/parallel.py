@@ -240,7 +240,7 @@ class ShardedPlacer:
         else:
             back_recv[0].copy_(back_send[0])
         ev[4].record(st)
-        rb.place_routed(rep_in.data_ptr(), win_slot.data_ptr(), params, st.cuda_stream)
+        rb.place_routed(rep_in.data_ptr(), win_slot.data_ptr(), world, seg_cap, params, st.cuda_stream)
         ev[5].record(st)
         self._events = ev
         self._stage_names = ["route_ms", "send_ms", "probe_ms", "reply_ms", "place_ms"]
@@ -262,8 +262,8 @@ class ShardedPlacer:
             raise ValueError("batch has more k-mer windows than the peer buffers were sized for (max_windows)")
         seg_cap = pb.seg_cap
         b = getattr(self, "_buf", None)
-        if b is None or b["win_slot"].numel() < max(nw, 1):
-            b = dict(win_slot=torch.empty(max(nw, 1), dtype=torch.int32, device=dev),
+        if b is None:
+            b = dict(win_slot=torch.empty(world * seg_cap, dtype=torch.int16, device=dev),
                      token=torch.zeros(1, dtype=torch.int32, device=dev))
             self._buf = b
         ev[0].record(st)
@@ -281,7 +281,7 @@ class ShardedPlacer:
         if world > 1:
             dist.all_reduce(b["token"], group=self.group)  # barrier on the stream: every probe kernel has completed
         ev[3].record(st)
-        rb.place_routed(pb.reply[me], b["win_slot"].data_ptr(), params, st.cuda_stream)
+        rb.place_routed(pb.reply[me], b["win_slot"].data_ptr(), world, seg_cap, params, st.cuda_stream)
         ev[4].record(st)
         self._events = ev
         self._stage_names = ["route_ms", "counts_ms", "probe_ms", "place_ms"]
@@ -294,10 +294,10 @@ class ShardedPlacer:
         import torch
 
         b = getattr(self, "_buf", None)
-        if b is None or b["seg_cap"] < seg_cap or b["win_slot"].numel() < max(nw, 1):
+        if b is None or b["seg_cap"] != seg_cap:
             b = dict(seg_cap=seg_cap,
                      send=torch.empty(self.world * seg_cap, dtype=torch.int64, device=dev),
-                     win_slot=torch.empty(max(nw, 1), dtype=torch.int32, device=dev),
+                     win_slot=torch.empty(self.world * seg_cap, dtype=torch.int16, device=dev),
                      rep_in=torch.empty(self.world * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev),
                      recv=torch.empty(1, dtype=torch.int64, device=dev),
                      rep_out=torch.empty(REPLY_BYTES, dtype=torch.uint8, device=dev))
@@ -342,14 +342,14 @@ class LocalShardedPlacer:
         nw = rb.routed_windows()
         seg_cap = int(nw / self.n_shards * self.slack) + 65536
         send = torch.empty(self.n_shards * seg_cap, dtype=torch.int64, device=dev)
-        win_slot = torch.empty(max(nw, 1), dtype=torch.int32, device=dev)
+        win_slot = torch.empty(self.n_shards * seg_cap, dtype=torch.int16, device=dev)
         counts = rb.route_hashes(self.n_shards, seg_cap, send.data_ptr(), win_slot.data_ptr(), st.cuda_stream)
         assert int(counts.sum()) == nw
         rep = torch.empty(self.n_shards * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev)
         for o, ix in enumerate(self.shards):
             ix.shard_probe(send.data_ptr() + o * seg_cap * 8, int(counts[o]), rep.data_ptr() + o * seg_cap * REPLY_BYTES,
                            st.cuda_stream)
-        rb.place_routed(rep.data_ptr(), win_slot.data_ptr(), params, st.cuda_stream)
+        rb.place_routed(rep.data_ptr(), win_slot.data_ptr(), self.n_shards, seg_cap, params, st.cuda_stream)
         res = rb.fetch(st.cuda_stream)
         self.last_counts, self.last_send = counts, (send, seg_cap)
         rb.close()

@@ -234,7 +234,9 @@ int cls_get_timing(const cls_index *index, cls_timing *out);
  *
  *   home  GPU  cls_route_hashes   hash every window, append it to its owner's segment
  *                                 d_send[o * seg_cap .. + counts_out[o])  (uint64 hashes);
- *                                 d_win_slot[window] = index into d_send  (uint32, n_windows entries)
+ *                                 d_slot_win[slot] = window (strand * W + pos) behind that slot of d_send
+ *                                 (uint16, n_shards * seg_cap entries); the hashes of one read form one
+ *                                 contiguous run per owner (the run table stays inside `rb`)
  *   all-to-all of the segments (hashes travel to their owners)
  *   owner GPU  cls_shard_probe    one cls_probe_reply (12 bytes) per received hash, same order
  *   all-to-all back, into a reply buffer laid out exactly like d_send
@@ -254,7 +256,7 @@ int cls_index_create_shard(const cls_model_view *model, int device, uint32_t sha
                            cls_index **out);
 int cls_routed_windows(cls_index *index, cls_resident_batch *rb, uint64_t *n_windows);
 int cls_route_hashes(cls_index *index, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap,
-                     void *d_send, void *d_win_slot, uint64_t *counts_out, void *stream);
+                     void *d_send, void *d_slot_win, uint64_t *counts_out, void *stream);
 int cls_shard_probe(cls_index *index, const void *d_hashes, uint64_t n, void *d_replies, void *stream);
 
 /*
@@ -271,13 +273,13 @@ int cls_shard_probe(cls_index *index, const void *d_hashes, uint64_t n, void *d_
  *   (barrier)  cls_place_routed on the local reply box.
  */
 int cls_route_hashes_p2p(cls_index *index, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap,
-                         void *const *d_segments, void *d_win_slot, uint64_t *counts_out, void *stream);
+                         void *const *d_segments, void *d_slot_win, uint64_t *counts_out, void *stream);
 int cls_peer_alloc(int device, uint64_t bytes, void **d_ptr, uint8_t ipc_handle[64]);
 int cls_peer_open(int device, const uint8_t ipc_handle[64], void **d_ptr);
 int cls_peer_close(int device, void *d_ptr);
 int cls_peer_free(int device, void *d_ptr);
-int cls_place_routed(cls_index *index, cls_resident_batch *rb, const void *d_replies, const void *d_win_slot,
-                     const cls_params *params, void *stream);
+int cls_place_routed(cls_index *index, cls_resident_batch *rb, const void *d_replies, const void *d_slot_win,
+                     uint32_t n_shards, uint64_t seg_cap, const cls_params *params, void *stream);
 
 /*
  * Parity/debug exports.
