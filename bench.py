@@ -312,7 +312,7 @@ def run_b200(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.config), "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes_local, "launches_per_step": launches_per_step,
-                         "kernel": "cls::scan_kernel<1> (config 4: + cls::place_kernel<35,1,1>)", "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result"},
+                         "kernel": "cls::scan_kernel<1,1> + cls::descend_kernel, timed together (config 4: + cls::place_kernel<35,1,1> for the kb-scale classes)", "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result; achieved = algorithmic bytes / CUDA-event time of the whole step (all launches of the step)"},
             "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
             "status_histogram": status_hist, "step_ms": [round(x, 4) for x in step_ms],
             "setup_s": {"generate": round(gen_s, 1), "index_upload": round(upload_s, 2)},
