@@ -378,3 +378,86 @@ def test_long_reads_cta_mode(cq, general):
     got = ix.place_batch((b2, o2))
     assert got.status.tolist() == want["status"].tolist() and got.n_matched.tolist() == want["n_matched"].tolist()
     ix.close(), md.close()
+
+
+# ---- reads with MANY distinct node sets: every hand-over / fallback of the short-read path ----------
+def _many_sets_model(cq, oracle, rng, n_tips, n_reads, pool):
+    """A model whose k-mer index holds exactly the windows of `n_reads` random 150-mers, every window
+    filed under a node set drawn from a pool of `pool` random upward-closed sets (None: one set per
+    window), so that a read sees up to 232 distinct node sets."""
+    from classeq2_b200 import synth
+    from classeq2_b200.model import FlatModel
+    tree = synth.make_tree(n_tips, int(rng.integers(1 << 30)))
+    n = len(tree.node_id)
+    parent = np.full(n, -1, np.int64)
+    for p in range(n):
+        for j in range(int(tree.child_off[p]), int(tree.child_off[p + 1])):
+            parent[int(tree.child_idx[j])] = p
+
+    def path_ids(tips):
+        nodes = set()
+        for t in tips:
+            v = int(tree.tip_node[t])
+            while v >= 0:
+                nodes.add(int(tree.node_id[v]))
+                v = int(parent[v])
+        return sorted(nodes)
+
+    def rand_set():
+        return path_ids(rng.choice(n_tips, size=int(rng.integers(1, 5)), replace=False))
+
+    sets = [rand_set() for _ in range(pool)] if pool else []
+    reads = [_rand_seq(rng, 150) for _ in range(n_reads)]
+    km = oracle.KmersMap(35, 4)
+    eb, eh, es = [], [], []
+    seen = set()
+    for s in reads:
+        for kmer, h in km.build_kmer_from_string(s):
+            if h in seen:
+                continue
+            seen.add(h)
+            if pool:
+                si = int(rng.integers(pool))
+            else:
+                sets.append(rand_set())
+                si = len(sets) - 1
+            eb.append(cq.host_murmur3_h1(kmer[:4].encode())), eh.append(h), es.append(si)
+    set_off = np.zeros(len(sets) + 1, np.uint64)
+    set_off[1:] = np.cumsum([len(x) for x in sets])
+    flat = FlatModel(35, 4, tree.node_id, tree.node_kind, tree.child_off, tree.child_idx,
+                     np.array(eb, np.uint64), np.array(eh, np.uint64), np.array(es, np.uint64), set_off,
+                     np.array([v for x in sets for v in x], np.uint64))
+    # queries: the reads themselves, mutated copies (fewer hits) and chimeras of two reads
+    qs = list(reads)
+    for s in reads:
+        b = bytearray(s.encode())
+        for i in rng.integers(0, 150, 3):
+            b[int(i)] = b"ACGT"[int(rng.integers(4))]
+        qs.append(b.decode())
+    for i in range(n_reads - 1):
+        qs.append(reads[i][:75] + reads[i + 1][75:])
+    return flat, qs
+
+
+@pytest.mark.parametrize("pool", [8, 30, 50, 64, 100, None])
+def test_many_distinct_node_sets_per_read(cq, oracle, pool):
+    from classeq2_b200.parallel import LocalShardedPlacer
+    from oracle import cpp_oracle
+    rng = np.random.default_rng(4242 + (pool or 0))
+    flat, qs = _many_sets_model(cq, oracle, rng, n_tips=90, n_reads=24, pool=pool)
+    md = cpp_oracle.CppModel.from_flat(flat)
+    bases, offsets = cq.make_batch(qs)
+    ix = cq.Index(flat, device=0)
+    assert ix.info()["closed_sets"] == 1
+    sharded = LocalShardedPlacer(flat, 0, 4)
+    for kn in [dict(), dict(remove_intersection=True), dict(min_match_coverage=0.1, max_iterations=4)]:
+        want = md.place_batch(bases, offsets, kn.get("max_iterations"), kn.get("min_match_coverage"), kn.get("remove_intersection"))
+        rb = ix.upload((bases, offsets))
+        rb.place(cq.PlaceParams(**kn))
+        for got in (ix.place_batch((bases, offsets), cq.PlaceParams(**kn)), rb.fetch(), sharded.place((bases, offsets), cq.PlaceParams(**kn))):
+            for f in ("status", "node_id", "one", "rest", "n_query_kmers", "n_matched", "n_root_matched"):
+                bad = np.flatnonzero(getattr(got, f) != want[f])
+                assert bad.size == 0, (f, kn, pool, bad[:5], getattr(got, f)[bad[:5]], want[f][bad[:5]])
+            assert ((got.iterations == want["iterations"]) | (want["status"] == 8)).all()
+        rb.close()
+    md.close(), ix.close()
