@@ -461,3 +461,45 @@ def test_many_distinct_node_sets_per_read(cq, oracle, pool):
             assert ((got.iterations == want["iterations"]) | (want["status"] == 8)).all()
         rb.close()
     md.close(), ix.close()
+
+
+def test_repeated_kmers_in_short_reads(cq, oracle):
+    """Distinct-hash semantics (the reference collects hashes in HashSets): tandem repeats put the same
+    k-mer at several positions of a strand, hairpins put it on both strands; every copy must count once."""
+    from classeq2_b200 import synth
+    from classeq2_b200.model import BuiltModel, FlatModel
+    from classeq2_b200.parallel import LocalShardedPlacer
+    from oracle import cpp_oracle
+    rng = np.random.default_rng(99)
+    tree = synth.make_tree(12, 5)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    rc = lambda s: "".join(comp[c] for c in reversed(s))
+    tips = []
+    for t in range(12):
+        unit, stem = _rand_seq(rng, 41 + t), _rand_seq(rng, 70)
+        tips.append(unit * 4 + stem + rc(stem))          # period-(41+t) repeat, then a perfect hairpin
+    bases = np.frombuffer("".join(tips).encode(), np.uint8).copy()
+    offs = np.zeros(13, np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in tips])
+    tflat = synth.tree_only_flat(tree)
+    bm = BuiltModel(tflat, tree.tip_node, bases, offs)
+    a = bm.arrays()
+    bm.close()
+    flat = FlatModel(35, 4, tree.node_id, tree.node_kind, tree.child_off, tree.child_idx,
+                     a["entry_bucket"], a["entry_hash"], a["entry_set"], a["set_off"], a["set_node_ids"])
+    qs = []
+    for s in tips:
+        for st in range(0, len(s) - 150, 13):
+            qs.append(s[st:st + 150])
+            qs.append(rc(s[st:st + 140]))
+        qs.append(s[-140:])                              # the hairpin: forward and reverse strand share their k-mers
+    md = cpp_oracle.CppModel.from_flat(flat)
+    b, o = cq.make_batch(qs)
+    want = md.place_batch(b, o)
+    assert (want["n_matched"] < want["n_query_kmers"]).sum() > len(qs) // 2   # the repeats really collapse
+    ix = cq.Index(flat, device=0)
+    for got in (ix.place_batch((b, o)), LocalShardedPlacer(flat, 0, 3).place((b, o))):
+        for f in ("status", "node_id", "one", "rest", "n_query_kmers", "n_matched", "n_root_matched", "iterations"):
+            bad = np.flatnonzero(getattr(got, f) != want[f])
+            assert bad.size == 0, (f, bad[:5], getattr(got, f)[bad[:5]], want[f][bad[:5]])
+    md.close(), ix.close()
