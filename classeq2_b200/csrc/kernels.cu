@@ -67,30 +67,32 @@ struct WarpMem {
     uint64_t *ring_a, *ring_b;  // pre-mix ring (k = 35 path)
 };
 
-// Decode one read into the two ASCII strands and the two packed strands.
+// Decode one read into the two ASCII strands and the two packed strands.  One (word, strand) item per
+// thread: a 150-base read is 10 words per strand, i.e. 20 items - all of a warp's lanes get work.
 __device__ __forceinline__ void decode_read(const uint32_t *__restrict__ packed, uint32_t len, const WarpMem &m,
                                             uint32_t pk_words, uint32_t tid = threadIdx.x & 31u, uint32_t nthreads = 32u) {
     const uint32_t nw = (len + 15u) >> 4;
     const uint32_t pad = nw * 16u - len;  // unused base slots at the top of the last word
-    for (uint32_t t = tid; t < pk_words; t += nthreads) {
-        uint32_t f = 0, r = 0;
+    for (uint32_t it = tid; it < 2 * pk_words; it += nthreads) {
+        const bool rc = it >= pk_words;
+        const uint32_t t = rc ? it - pk_words : it;
+        uint32_t v = 0;
         if (t < nw) {
-            f = __ldg(packed + t);
-            // reverse-complement word t = bases [16t, 16t+16) of the reversed string
-            uint32_t a = revcomp16(__ldg(packed + (nw - 1 - t)));
-            uint32_t b = (t + 1 < nw) ? revcomp16(__ldg(packed + (nw - 2 - t))) : 0u;
-            r = __funnelshift_r(a, b, 2u * pad);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                m.str_f[4 * t + q] = decode4((f >> (8 * q)) & 0xFFu);
-                m.str_r[4 * t + q] = decode4((r >> (8 * q)) & 0xFFu);
+            if (!rc) {
+                v = __ldg(packed + t);
+            } else {
+                // reverse-complement word t = bases [16t, 16t+16) of the reversed string
+                const uint32_t a = revcomp16(__ldg(packed + (nw - 1 - t)));
+                const uint32_t b = (t + 1 < nw) ? revcomp16(__ldg(packed + (nw - 2 - t))) : 0u;
+                v = __funnelshift_r(a, b, 2u * pad);
             }
-        } else if (t == nw) {  // over-read pad of the strings
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { m.str_f[4 * t + q] = 0; m.str_r[4 * t + q] = 0; }
         }
-        m.pk_f[t] = f;
-        m.pk_r[t] = r;
+        uint32_t *str = rc ? m.str_r : m.str_f;
+        if (t <= nw) {  // word nw is the over-read pad of the strings
+#pragma unroll
+            for (int q = 0; q < 4; ++q) str[4 * t + q] = t < nw ? decode4((v >> (8 * q)) & 0xFFu) : 0u;
+        }
+        (rc ? m.pk_r : m.pk_f)[t] = v;
     }
 }
 
@@ -199,8 +201,8 @@ __device__ __forceinline__ QInfo ld_qinfo(const QInfo *qi, uint32_t q) {
 __device__ __forceinline__ uint64_t lca_depth_node(const DeviceIndex &ix, uint32_t u, uint32_t v) {
     const uint32_t fu = __ldg(&ix.qinfo[u].euler_first), fv = __ldg(&ix.qinfo[v].euler_first);
     const uint32_t j = 31u - __clz(fv - fu + 1u);
-    const uint64_t *lvl = ix.lca_table + (size_t)j * ix.euler_len;
-    const uint64_t a = __ldg(lvl + fu), b = __ldg(lvl + fv + 1u - (1u << j));
+    const uint32_t row = j * ix.euler_len;  // the table holds at most 2^27 entries (build_host_index)
+    const uint64_t a = __ldg(ix.lca_table + (row + fu)), b = __ldg(ix.lca_table + (row + fv + 1u - (1u << j)));
     return a < b ? a : b;
 }
 
@@ -609,8 +611,8 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
     }
     // ---- descent
     uint32_t p = 0, depth_p = 0;
-    int64_t iteration = 0;
-    const int64_t max_iter = pp.max_iterations;
+    int32_t iteration = 0;  // never beyond max_iterations + 1
+    const int32_t max_iter = pp.max_iterations;
     QInfo ip = res.status == kUndecided ? ld_qinfo(ix.qinfo, 0) : QInfo{0, 0, 0, 0};
     while (res.status == kUndecided) {
         // pooled extremes of the live terminals -> every level down to their LCA is unanimous
@@ -623,8 +625,8 @@ __device__ __forceinline__ void finish_read_reg(const DeviceIndex &ix, const Pla
         const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
         if (depth_a > depth_p) {
             const uint32_t d = depth_a - depth_p;
-            if (iteration + (int64_t)d > max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
-            iteration += d;
+            if ((int64_t)iteration + (int64_t)d > (int64_t)max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
+            iteration += (int32_t)d;
             ip = ld_qinfo(ix.qinfo, A);
             if (ip.child_count == 0) {  // update_introspection_node.rs:32-87
                 uint32_t ws = 0;
