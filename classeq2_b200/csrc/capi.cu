@@ -261,8 +261,7 @@ int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *par
     const PlaceParams pp = make_place_params(params);
     size_t want = 0;
     for (const LengthClass &c : lay.classes) {
-        PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
-        if (!g.cta_per_read) want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size));
+        want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size));
     }
     if (want > scratch.cap) {
         if (scratch.p) CU_TRY(cudaStreamSynchronize(stream));  // an earlier placement on this stream may still use it
@@ -538,7 +537,7 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
         CU_TRY(cudaEventRecord(ev[1], st));
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         DevBuf &scratch = w->d_scratch[ci & 1];  // stream order protects its reuse by the chunk after next
-        if (!g.cta_per_read) CU_TRY(scratch.reserve(place_scratch_bytes(c.count, c.max_len, ix->dix.k_size)));
+        CU_TRY(scratch.reserve(place_scratch_bytes(c.count, c.max_len, ix->dix.k_size)));
         uint32_t nl = 0;
         cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_res, g, ix->sm_count, st,
                                      scratch.p, scratch.cap, &nl);

@@ -1,4 +1,5 @@
-// sm_100a kernels of the placement path.  One warp places one query end to end:
+// sm_100a kernels of the placement path.  The stages of one query (one warp per query for short reads -
+// scan_kernel then descend_kernel - or one CTA per query for kb-scale reads - place_kernel):
 //
 //   decode   2-bit packed bases -> forward + reverse-complement ASCII strings (and the packed
 //            reverse complement) in shared memory
@@ -38,9 +39,6 @@ namespace cls {
 
 namespace {
 
-#ifndef CLS_PIPELINE
-#define CLS_PIPELINE 0  // probe software pipelining: 0 = none (fastest measured: 7.21 ms), 1 = rotate registers (7.24), 2 = ping-pong (8.43; code bloat)
-#endif
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kUndecided = 0xFFFFFFFFu;
 constexpr uint32_t kRing = 64;  // pre-mix ring entries per warp (two 32-offset chunks)
@@ -790,6 +788,18 @@ __global__ void hash_only_kernel(const uint32_t *__restrict__ packed, uint32_t l
     }
 }
 
+// Hand-over to the descent kernels (their own launch, one warp per read): per read of the launch
+//     pairs[r * cap + j] = {node-set record offset, distinct hits with that node set}, j < D
+//     meta[r] = {n_matched, D};  D = kDone: the read was finished where its histogram was built (D > cap)
+// cap = kPairCap for one-warp-per-read launches, kPairCapWide for one-CTA-per-read launches (kb-scale reads
+// see a hundred or more distinct node sets).
+constexpr uint32_t kPairCap = 64, kPairCapWide = 256, kDone = 0xFFFFFFFFu;
+struct ScanOut {
+    uint2 *pairs;
+    uint2 *meta;
+    uint32_t cap;
+};
+
 // ------------------------------------------------------------------------------------------
 // The placement kernel, persistent CTAs striding over the query range.
 //   CTA == false: one WARP per query (short reads: the per-query tables are a few KB)
@@ -801,7 +811,7 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
                                                        const uint32_t *__restrict__ packed,
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                        uint32_t n_reads, ResultRec *__restrict__ results,
-                                                       PlaceGeom g) {
+                                                       PlaceGeom g, ScanOut so) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t tail_lut[64];
     init_tail_lut(tail_lut);
@@ -913,7 +923,20 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
             if (lane == 0 && n_matched) atomicAdd(n_matched_smem, n_matched);
             __syncthreads();
             n_matched = *n_matched_smem;
+            if (CLOSED && so.pairs && *n_sets_smem <= so.cap) {
+                // hand the read over to the descent kernel: one warp walking the tree while seven wait is
+                // what made kb-scale reads slow
+                const uint32_t D = *n_sets_smem;
+                for (uint32_t j = gtid; j < D; j += gthreads) {
+                    const uint32_t p2 = lst[j];
+                    so.pairs[(size_t)r * so.cap + j] = make_uint2(t2k[p2], t2c[p2]);
+                }
+                if (gtid == 0) so.meta[r] = make_uint2(n_matched, D);
+                __syncthreads();   // the tables are free again for the next read
+                continue;
+            }
             if (warp != 0) { __syncthreads(); continue; }   // warp 0 finishes the read; see the barrier at the end
+            if (so.pairs && lane == 0) so.meta[r] = make_uint2(n_matched, kDone);
         }
         __syncwarp();
         const uint32_t D = *n_sets_smem;
@@ -926,22 +949,11 @@ __global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix,
 
 // ------------------------------------------------------------------------------------------
 // Short reads, k = 35: the scan kernel (one warp per read: decode, hash, probe, de-duplicate,
-// histogram by node set) and the descent kernel (one thread per read).  The scan loop is unrolled
-// over the two halves of the pre-mix ring so that every shared-memory address of a pass is a
-// per-lane constant: pass c hashes windows 32c + lane from the pre-mixes at offsets pos, pos + 8,
-// pos + 16, pos + 24 and meanwhile pre-mixes offsets 32(c + 1) + lane into the other half.
-// Reads with more distinct node sets than the scratch holds per read (or any read of a model that
-// is not closed) are finished by their scan warp with finish_read.
+// histogram by node set) and the descent kernel (one warp per read as well, its own launch).  The scan
+// loop is unrolled over the two halves of the pre-mix ring so that every shared-memory address of a
+// pass is a per-lane constant: pass c hashes windows 32c + lane from the pre-mixes at offsets pos,
+// pos + 8, pos + 16, pos + 24 and meanwhile pre-mixes offsets 32(c + 1) + lane into the other half.
 // ------------------------------------------------------------------------------------------
-// Hand-over from the scan kernel to the descent kernel (SPLIT mode): per read of the launch
-//     pairs[r * kPairCap + j] = {node-set record offset, distinct hits with that node set}, j < D
-//     meta[r] = {n_matched, D};  D = kDone: the scan warp finished the read itself (D > kPairCap)
-constexpr uint32_t kPairCap = 64, kDone = 0xFFFFFFFFu;
-struct ScanOut {
-    uint2 *pairs;
-    uint2 *meta;
-};
-
 __device__ __forceinline__ void premix_store(const uint32_t *w, uint32_t sh8, uint64_t *ra, uint64_t *rb) {
     const uint32_t r0 = w[0], r1 = w[1], r2 = w[2];
     const uint64_t x = pack64(__funnelshift_r(r0, r1, sh8), __funnelshift_r(r1, r2, sh8));
@@ -959,12 +971,6 @@ __device__ __forceinline__ uint64_t window_hash35(uint64_t a0, uint64_t b1, uint
 
 #ifndef CLS_SCAN_MINB
 #define CLS_SCAN_MINB 4
-#endif
-#ifndef CLS_ONE_CONSUME
-#define CLS_ONE_CONSUME 0  // 1: a single copy of the consume code looped over the pair (118 more instructions per read: 5.59 vs 5.46 ms)
-#endif
-#ifndef CLS_REG_SLOTS2
-#define CLS_REG_SLOTS2 1
 #endif
 template <bool CLOSED, bool SPLIT>
 __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix, PlaceParams pp, const uint32_t *__restrict__ packed,
@@ -1072,26 +1078,18 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
                 uint64_t A0, A1, A2, A3, B0, B1, B2, B3;
                 ld_bucket(ix.table, bA, A0, A1, A2, A3);
                 ld_bucket(ix.table, bB, B0, B1, B2, B3);
-#if CLS_ONE_CONSUME
-                // ONE copy of the consume code, run once per window of the pair
-#pragma unroll 1
-                for (uint32_t u = 0; u < (two ? 2u : 1u); ++u) {
-                    consume(u ? posB : posA, u ? hB : hA, u ? bB : bA, u ? B0 : A0, u ? B1 : A1, u ? B2 : A2, u ? B3 : A3);
-                }
-#else
                 consume(posA, hA, bA, A0, A1, A2, A3);
                 if (two) consume(posB, hB, bB, B0, B1, B2, B3);
-#endif
             }
         }
         __syncwarp();
         const uint32_t D = *n_sets_smem;
         if constexpr (SPLIT) {
             // hand the read over to the descent kernel (its own launch: 64 warps per SM and the whole L1)
-            if (D <= kPairCap) {
+            if (D <= so.cap) {
                 for (uint32_t j = lane; j < D; j += 32) {
                     const uint32_t p2 = lst[j];
-                    so.pairs[(size_t)r * kPairCap + j] = make_uint2(t2k[p2], t2c[p2]);
+                    so.pairs[(size_t)r * so.cap + j] = make_uint2(t2k[p2], t2c[p2]);
                 }
                 if (lane == 0) so.meta[r] = make_uint2(n_matched, D);
             } else {
@@ -1108,6 +1106,22 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
 }
 
 // One warp per read: gates and descent over the {node set, weight} pairs the scan kernel left.
+// MAXSLOTS = 2 serves the short-read launches (at most 64 pairs), MAXSLOTS = 8 the kb-scale ones (at most 256).
+template <int SLOTS>
+__device__ __forceinline__ void descend_from_pairs(const DeviceIndex &ix, const PlaceParams &pp, uint32_t *cnt, uint32_t *excl,
+                                                   const uint2 *__restrict__ pr, uint32_t D, uint32_t n_matched,
+                                                   ResultRec *__restrict__ out) {
+    uint32_t off[SLOTS], wt[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const uint32_t j = lane_id() + 32u * s;
+        off[s] = 0; wt[s] = 0;
+        if (j < D) { const uint2 v = pr[j]; off[s] = v.x; wt[s] = v.y; }
+    }
+    finish_read_reg<SLOTS>(ix, pp, cnt, excl, off, wt, n_matched, out);
+}
+
+template <int MAXSLOTS>
 __global__ void __launch_bounds__(256) descend_kernel(DeviceIndex ix, PlaceParams pp, ScanOut so, uint32_t first_read,
                                                       uint32_t n_reads, ResultRec *__restrict__ results, uint32_t fan_cap) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -1120,16 +1134,13 @@ __global__ void __launch_bounds__(256) descend_kernel(DeviceIndex ix, PlaceParam
     for (uint32_t r = gwarp; r < n_reads; r += gstride) {
         const uint2 me = so.meta[r];
         if (me.y == kDone) continue;
-        const uint2 *pr = so.pairs + (size_t)r * kPairCap;
-        if (me.y <= 32) {
-            uint32_t off[1] = {0}, wt[1] = {0};
-            if (lane < me.y) { const uint2 v = pr[lane]; off[0] = v.x; wt[0] = v.y; }
-            finish_read_reg<1>(ix, pp, cnt, excl, off, wt, me.x, results + first_read + r);
-        } else {
-            uint32_t off[2] = {0, 0}, wt[2] = {0, 0};
-            { const uint2 v = pr[lane]; off[0] = v.x; wt[0] = v.y; }
-            if (lane + 32 < me.y) { const uint2 v = pr[lane + 32]; off[1] = v.x; wt[1] = v.y; }
-            finish_read_reg<2>(ix, pp, cnt, excl, off, wt, me.x, results + first_read + r);
+        const uint2 *pr = so.pairs + (size_t)r * so.cap;
+        ResultRec *out = results + first_read + r;
+        if (me.y <= 32) descend_from_pairs<1>(ix, pp, cnt, excl, pr, me.y, me.x, out);
+        else if (MAXSLOTS == 2 || me.y <= 64) descend_from_pairs<2>(ix, pp, cnt, excl, pr, me.y, me.x, out);
+        else if constexpr (MAXSLOTS > 2) {
+            if (me.y <= 128) descend_from_pairs<4>(ix, pp, cnt, excl, pr, me.y, me.x, out);
+            else descend_from_pairs<8>(ix, pp, cnt, excl, pr, me.y, me.x, out);
         }
     }
 }
@@ -1160,10 +1171,30 @@ PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout) {
     return g;
 }
 
+static inline size_t scratch_bytes_for(uint32_t n_reads, uint32_t cap) { return (size_t)n_reads * ((size_t)cap * 8 + 8) + 256; }
+static inline ScanOut carve_scratch(void *scratch, uint32_t n_reads, uint32_t cap) {
+    char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    ScanOut so;
+    so.pairs = reinterpret_cast<uint2 *>(base);
+    so.meta = so.pairs + (size_t)n_reads * cap;
+    so.cap = cap;
+    return so;
+}
+template <int MAXSLOTS>
+static cudaError_t launch_descend(const DeviceIndex &ix, const PlaceParams &pp, const ScanOut &so, uint32_t first_read,
+                                  uint32_t n_reads, ResultRec *results, uint32_t fan_cap, int sm_count, cudaStream_t stream) {
+    uint32_t dgrid = (uint32_t)(sm_count * 8);
+    const uint32_t need = (n_reads + 7) / 8;
+    if (dgrid > need) dgrid = need;
+    descend_kernel<MAXSLOTS><<<dgrid, 256, (size_t)2 * fan_cap * 4 * 8, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
+    return cudaGetLastError();
+}
+
 template <int K, bool CLOSED, bool CTA>
 static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                                   const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
-                                  ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream) {
+                                  ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream,
+                                  void *scratch = nullptr, size_t scratch_bytes = 0, uint32_t *n_launches = nullptr) {
     const size_t ring = (size_t)4 * kRing * 4, group = (size_t)g.words_per_warp * 4;
     int warps = 8;
     size_t smem;
@@ -1186,23 +1217,37 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
     const uint32_t need = CTA ? n_reads : (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid == 0) return cudaSuccess;
-    place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g);
-    return cudaGetLastError();
+    // kb-scale reads of closed models: the histogram goes to the wide descent kernel when the caller gave scratch
+    const bool split = CTA && CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCapWide) &&
+                       (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024 && getenv("CLS_NO_SPLIT") == nullptr;
+    ScanOut so{nullptr, nullptr, 0};
+    if (split) so = carve_scratch(scratch, n_reads, kPairCapWide);
+    place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (n_launches) ++*n_launches;
+    if (split) {
+        if ((e = launch_descend<8>(ix, pp, so, first_read, n_reads, results, g.fan_cap, sm_count, stream)) != cudaSuccess) return e;
+        if (n_launches) ++*n_launches;
+    }
+    return cudaSuccess;
 }
 
 template <int K, bool CLOSED>
 static cudaError_t launch_place_m(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                                   const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
-                                  ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream) {
-    return g.cta_per_read ? launch_place_t<K, CLOSED, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
-                          : launch_place_t<K, CLOSED, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+                                  ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream,
+                                  void *scratch, size_t scratch_bytes, uint32_t *n_launches) {
+    return g.cta_per_read ? launch_place_t<K, CLOSED, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
+                          : launch_place_t<K, CLOSED, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);
 }
 
 // ---- short reads, k = 35: scan kernel (+ descent kernel when the caller provides the hand-over scratch) ----
 size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k) {
     static const bool off = getenv("CLS_NO_SPLIT") != nullptr;
-    if (off || k != 35 || max_len < 35 || n_reads == 0) return 0;
-    return (size_t)n_reads * ((size_t)kPairCap * 8 + 8) + 256;
+    if (off || max_len < k || n_reads == 0) return 0;
+    const PlaceGeom g = make_place_geom(max_len, k, 1);
+    if (g.cta_per_read) return scratch_bytes_for(n_reads, kPairCapWide);
+    return k == 35 ? scratch_bytes_for(n_reads, kPairCap) : 0;
 }
 
 template <bool CLOSED>
@@ -1213,9 +1258,10 @@ static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, c
     const size_t ring = (size_t)4 * kRing * 4, group = (size_t)g.words_per_warp * 4;
     int warps = 8;
     while (warps > 1 && (group + ring) * warps > 200 * 1024) warps >>= 1;
-    const size_t smem = (group + ring) * warps;
+    static const size_t pad = [] { const char *e = getenv("CLS_SCAN_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
+    const size_t smem = (group + ring) * warps + pad;
     if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
-    const bool split = CLOSED && scratch && scratch_bytes >= place_scratch_bytes(n_reads, 35, 35) && place_scratch_bytes(n_reads, 35, 35) &&
+    const bool split = CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && getenv("CLS_NO_SPLIT") == nullptr &&
                        (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
     auto kern = split ? scan_kernel<CLOSED, true> : scan_kernel<CLOSED, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -1227,21 +1273,13 @@ static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, c
     uint32_t grid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
-    ScanOut so{nullptr, nullptr};
-    if (split) {
-        char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
-        so.pairs = reinterpret_cast<uint2 *>(base);
-        so.meta = so.pairs + (size_t)n_reads * kPairCap;
-    }
+    ScanOut so{nullptr, nullptr, 0};
+    if (split) so = carve_scratch(scratch, n_reads, kPairCap);
     kern<<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (n_launches) ++*n_launches;
     if (split) {
-        const size_t dsmem = (size_t)2 * g.fan_cap * 4 * 8;
-        uint32_t dgrid = (uint32_t)(sm_count * 8);
-        if (dgrid > need) dgrid = need;
-        descend_kernel<<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, g.fan_cap);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = launch_descend<2>(ix, pp, so, first_read, n_reads, results, g.fan_cap, sm_count, stream)) != cudaSuccess) return e;
         if (n_launches) ++*n_launches;
     }
     return cudaSuccess;
@@ -1256,13 +1294,12 @@ cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uin
         return ix.closed ? launch_scan_t<true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
                          : launch_scan_t<false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);
     }
-    if (n_launches) ++*n_launches;
     if (ix.k_size == 35) {
-        return ix.closed ? launch_place_t<35, true, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
-                         : launch_place_t<35, false, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+        return ix.closed ? launch_place_t<35, true, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
+                         : launch_place_t<35, false, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);
     }
-    return ix.closed ? launch_place_m<0, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream)
-                     : launch_place_m<0, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream);
+    return ix.closed ? launch_place_m<0, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
+                     : launch_place_m<0, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);
 }
 
 cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, uint64_t *out, cudaStream_t stream) {

@@ -217,10 +217,10 @@ __global__ void __launch_bounds__(256, 4) place_routed_kernel(DeviceIndex ix, Pl
         __syncwarp();
         const uint32_t D = *wl.n_sets;
         if constexpr (SPLIT) {  // hand the read over to descend_kernel, like scan_kernel does
-            if (D <= kPairCap) {
+            if (D <= so.cap) {
                 for (uint32_t j = lane; j < D; j += 32) {
                     const uint32_t p2 = wl.lst[j];
-                    so.pairs[(size_t)r * kPairCap + j] = make_uint2(wl.t2k[p2], wl.t2c[p2]);
+                    so.pairs[(size_t)r * so.cap + j] = make_uint2(wl.t2k[p2], wl.t2c[p2]);
                 }
                 if (lane == 0) so.meta[r] = make_uint2(n_matched, D);
             } else {
@@ -294,23 +294,14 @@ cudaError_t launch_place_routed(const DeviceIndex &ix, const PlaceParams &pp, co
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
     const ProbeReply *rp = reinterpret_cast<const ProbeReply *>(replies);
-    const size_t want = place_scratch_bytes(n_reads, 35, 35);
-    const bool split = ix.closed && scratch && want && scratch_bytes >= want && (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
-    ScanOut so{nullptr, nullptr};
-    if (split) {
-        char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
-        so.pairs = reinterpret_cast<uint2 *>(base);
-        so.meta = so.pairs + (size_t)n_reads * kPairCap;
-    }
+    const bool split = ix.closed && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && getenv("CLS_NO_SPLIT") == nullptr &&
+                       (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
+    ScanOut so{nullptr, nullptr, 0};
+    if (split) so = carve_scratch(scratch, n_reads, kPairCap);
     auto kern = split ? place_routed_kernel<true, true> : (ix.closed ? place_routed_kernel<true, false> : place_routed_kernel<false, false>);
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, n_shards, seg_cap, runs, slot_win, rp, so);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (split) {
-        uint32_t dgrid = (uint32_t)(sm_count * 8);
-        if (dgrid > need) dgrid = need;
-        descend_kernel<<<dgrid, 256, (size_t)2 * g.fan_cap * 4 * 8, stream>>>(ix, pp, so, first_read, n_reads, results, g.fan_cap);
-        e = cudaGetLastError();
-    }
+    if (split) e = launch_descend<2>(ix, pp, so, first_read, n_reads, results, g.fan_cap, sm_count, stream);
     return e;
 }
