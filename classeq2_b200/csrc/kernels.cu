@@ -807,7 +807,7 @@ struct ScanOut {
 //                 contiguous chunk ranges of the read into one set of shared tables, warp 0 walks the tree
 // ------------------------------------------------------------------------------------------
 template <int K, bool CLOSED, bool CTA>
-__global__ void __launch_bounds__(256, CTA ? 2 : 4) place_kernel(DeviceIndex ix, PlaceParams pp,
+__global__ void __launch_bounds__(CTA ? 512 : 256, CTA ? 2 : 4) place_kernel(DeviceIndex ix, PlaceParams pp,
                                                        const uint32_t *__restrict__ packed,
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                        uint32_t n_reads, ResultRec *__restrict__ results,
@@ -1199,6 +1199,10 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
     int warps = 8;
     size_t smem;
     if (CTA) {
+        // the tables of a kb-scale read leave room for two CTAs per SM: sixteen warps each keep the SM busy
+        static const int cta_warps = [] { const char *e = getenv("CLS_CTA_WARPS"); return e ? atoi(e) : 16; }();
+        warps = cta_warps;
+        if (group + ring * warps > 113 * 1024) warps = 8;
         smem = group + ring * warps;
     } else {
         while (warps > 1 && (group + ring) * warps > 200 * 1024) warps >>= 1;
