@@ -71,6 +71,11 @@ class IndexInfo(C.Structure):
                 ("closed_sets", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class LevelCount(C.Structure):
+    _fields_ = [("parent_id", C.c_uint64), ("child_id", C.c_uint64), ("level", C.c_uint32), ("cnt", C.c_uint32),
+                ("excl", C.c_uint32), ("u", C.c_uint32)]
+
+
 class ClsError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"classeq_b200 error {code}: {message}")
@@ -105,6 +110,8 @@ PROTOTYPES = {
     "cls_peer_free": (C.c_int, [C.c_int, C.c_void_p]),
     "cls_place_routed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(Params), C.c_void_p]),
     "cls_debug_kmer_hashes": (C.c_int, [C.c_int, C.c_uint32, u8p, C.c_uint64, u64p, C.c_uint64, u64p]),
+    "cls_debug_node_counts": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(Params), C.POINTER(LevelCount), C.c_uint64, u64p,
+                                        C.POINTER(Result)]),
     "cls_debug_host_murmur3_x64_128_h1": (C.c_uint64, [u8p, C.c_uint64, C.c_uint64]),
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),
     "cls_filter_sequence": (C.c_uint64, [u8p, C.c_uint64, u8p, C.c_uint64]),

@@ -806,6 +806,56 @@ int cls_debug_kmer_hashes(int device, uint32_t k_size, const uint8_t *bases, uin
     return CLS_OK;
 }
 
+int cls_debug_node_counts(cls_index *ix, const uint8_t *bases, uint64_t len, const cls_params *params, cls_level_count *rows,
+                          uint64_t cap, uint64_t *n_rows, cls_result *result) {
+    if (!ix || !params || !n_rows || (len && !bases) || (cap && !rows)) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *n_rows = 0;
+    if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index");
+    if (len < ix->dix.k_size || len >= (1ull << 20)) return fail(CLS_ERR_INVALID_ARGUMENT, "query shorter than k or longer than 2^20 bases");
+    static_assert(sizeof(cls_level_count) == sizeof(TraceRow), "trace row layout");
+    CU_TRY(cudaSetDevice(ix->device));
+    std::vector<uint32_t> words((len + 15) / 16 + 8, 0);
+    if (!pack_read(bases, (uint32_t)len, words.data())) return fail(CLS_ERR_INVALID_ARGUMENT, "non-ACGT byte in the sequence");
+    const uint32_t cap_dev = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cap, 1), 1u << 22);
+    DevBuf d_words, d_desc, d_res, d_rows, d_n;
+    struct Free { DevBuf *b[5]; ~Free() { for (auto *x : b) x->release(); } } guard{{&d_words, &d_desc, &d_res, &d_rows, &d_n}};
+    CU_TRY(d_words.reserve(words.size() * 4)); CU_TRY(d_desc.reserve(sizeof(ReadDesc))); CU_TRY(d_res.reserve(sizeof(ResultRec)));
+    CU_TRY(d_rows.reserve((size_t)cap_dev * sizeof(TraceRow))); CU_TRY(d_n.reserve(4));
+    const ReadDesc rd{0u, (uint32_t)len};
+    CU_TRY(cudaMemcpy(d_words.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_desc.p, &rd, sizeof rd, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemset(d_n.p, 0, 4));
+    const PlaceGeom g = make_place_geom((uint32_t)len, ix->dix.k_size, ix->dix.max_fanout);
+    cudaError_t e = launch_trace(ix->dix, make_place_params(params), (const uint32_t *)d_words.p, (const ReadDesc *)d_desc.p,
+                                 (ResultRec *)d_res.p, g, ix->sm_count, nullptr, TraceBuf{(TraceRow *)d_rows.p, (uint32_t *)d_n.p, cap_dev});
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidConfiguration ? CLS_ERR_UNSUPPORTED : CLS_ERR_CUDA, std::string("trace launch: ") + cudaGetErrorString(e));
+    CU_TRY(cudaDeviceSynchronize());
+    uint32_t n = 0;
+    ResultRec rr;
+    CU_TRY(cudaMemcpy(&n, d_n.p, 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&rr, d_res.p, sizeof rr, cudaMemcpyDeviceToHost));
+    *n_rows = n;
+    const uint32_t take = (uint32_t)std::min<uint64_t>(std::min<uint32_t>(n, cap_dev), cap);
+    if (take) {
+        CU_TRY(cudaMemcpy(rows, d_rows.p, (size_t)take * sizeof(TraceRow), cudaMemcpyDeviceToHost));
+        // rows arrive in no particular order within a level: sort by (level, child id) for the caller
+        std::sort(rows, rows + take, [](const cls_level_count &a, const cls_level_count &b) {
+            return a.level != b.level ? a.level < b.level : a.child_id < b.child_id;
+        });
+    }
+    if (result) {
+        if (result->status) result->status[0] = (uint8_t)rr.status;
+        if (result->node_id) result->node_id[0] = rr.node_id;
+        if (result->one) result->one[0] = rr.one;
+        if (result->rest) result->rest[0] = rr.rest;
+        if (result->n_query_kmers) result->n_query_kmers[0] = (uint32_t)(2 * (len - ix->dix.k_size + 1));
+        if (result->n_matched) result->n_matched[0] = rr.n_matched;
+        if (result->n_root_matched) result->n_root_matched[0] = rr.n_root_matched;
+        if (result->iterations) result->iterations[0] = rr.iterations;
+    }
+    return CLS_OK;
+}
+
 int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable) {
     if ((len && !bases) || !words_out || len >= (1ull << 31) || cap_words < (len + 15) / 16)
         return fail(CLS_ERR_INVALID_ARGUMENT, "bad arguments");

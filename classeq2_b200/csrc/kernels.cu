@@ -299,10 +299,25 @@ __device__ __forceinline__ uint32_t insert_hits(const ReadTables &tb, bool hit, 
 
 // Everything after the hits of a read are in its tables: restriction to the root, gates, descent,
 // and the result record.  One warp; `D` distinct node sets, `n_matched` distinct hits (|M|).
+// `trace` (debug export cls_debug_node_counts): every level is evaluated with the vote counters - no LCA
+// jump, no two-children shortcut; same outcome by construction - and one row per (level, child with votes)
+// is appended to the trace.
 template <bool CLOSED>
 __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlaceParams &pp, const ReadTables &tb,
-                                            uint32_t D, uint32_t n_matched, ResultRec *__restrict__ out) {
+                                            uint32_t D, uint32_t n_matched, ResultRec *__restrict__ out,
+                                            const TraceBuf *trace = nullptr) {
     const uint32_t lane = lane_id();
+    const bool tracing = trace != nullptr;
+    auto trace_level = [&](uint32_t p, uint32_t m, uint32_t U, int64_t level) {
+        const QNode qn = ix.qnodes[p];
+        for (uint32_t o = lane; o < m; o += 32) {
+            if (tb.cnt[o] == 0) continue;
+            const uint32_t at = atomicAdd(trace->n_rows, 1u);
+            if (at < trace->cap)
+                trace->rows[at] = TraceRow{ix.q_node_id[p], ix.q_node_id[ix.q_child_list[qn.child_first + o]], (uint32_t)level,
+                                           tb.cnt[o], tb.excl[o], U};
+        }
+    };
     uint32_t *t1 = tb.t1, *t2k = tb.t2k, *t2c = tb.t2c, *lst = tb.lst, *cnt = tb.cnt, *excl = tb.excl;
     const bool ri = pp.remove_intersection != 0;
     // ---- live-set list: restrict to sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
@@ -375,7 +390,7 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
             const uint32_t Wlive = __reduce_add_sync(kFull, wl);
             const uint64_t dn = lca_depth_node(ix, umin, vmax);
             const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
-            if (depth_a > depth_p) {
+            if (!tracing && depth_a > depth_p) {
                 const uint32_t d = depth_a - depth_p;
                 if (iteration + (int64_t)d > max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; res.status = CLS_DEV_ERR_MAX_ITERATIONS; break; }
                 iteration += d;
@@ -395,7 +410,7 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
             uint32_t win_q = 0, nprop = 0, n_best = 0;
             int32_t win_one = 0, win_rest = 0;
             QInfo iw{0, 0, 0, 0};
-            if (m <= 2) {
+            if (!tracing && m <= 2) {
                 // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
                 const QInfo i1 = m ? ld_qinfo(ix.qinfo, p + 1) : QInfo{p_end, 0, 0, 0};
                 const uint32_t bnd = i1.q_end;
@@ -442,8 +457,8 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
                     uint32_t pos = t1[2 * j];
                     const uint32_t hi = lst[j];
                     if (t2k[j] == p) ++pos;
-                    uint32_t npres = 0, last = 0, ord = 0, cend = __ldg(&ix.qinfo[p + 1].q_end);
-                    while (pos < hi) {
+                    uint32_t npres = 0, last = 0, ord = 0, cend = m ? __ldg(&ix.qinfo[p + 1].q_end) : 0u;
+                    while (m && pos < hi) {
                         const uint32_t t = __ldg(ix.terms + pos);
                         while (t >= cend) { cend = __ldg(&ix.qinfo[cend].q_end); ++ord; }
                         atomicAdd(&cnt[ord], w); ++npres; last = ord;
@@ -455,6 +470,7 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
                 }
                 const uint32_t U = __reduce_add_sync(kFull, u_local);
                 __syncwarp();
+                if (tracing) trace_level(p, m, U, iteration);
                 const Decision dc = decide_smem(cnt, excl, m, U, ri);
                 __syncwarp();
                 for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
@@ -462,7 +478,7 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
                 nprop = dc.nprop; n_best = dc.n_best; win_one = dc.best_one; win_rest = dc.best_rest;
                 win_q = p + 1;
                 for (uint32_t o = 0; o < dc.best_ord; ++o) win_q = __ldg(&ix.qinfo[win_q].q_end);
-                iw = ld_qinfo(ix.qinfo, win_q);
+                if (nprop) iw = ld_qinfo(ix.qinfo, win_q);
             }
             if (nprop == 0) {
                 if (iteration == 1) res.status = CLS_DEV_UNCL_NO_INTROSPECTION;
@@ -520,6 +536,7 @@ __device__ __forceinline__ void finish_read(const DeviceIndex &ix, const PlacePa
             }
             const uint32_t U = __reduce_add_sync(kFull, u_local);
             __syncwarp();
+            if (tracing) trace_level(p, m, U, iteration);
             const Decision dc = decide_smem(cnt, excl, m, U, ri);
             __syncwarp();
             for (uint32_t o = lane; o < m; o += 32) { cnt[o] = 0; excl[o] = 0; }
@@ -811,7 +828,7 @@ __global__ void __launch_bounds__(CTA ? 512 : 256, CTA ? 2 : 4) place_kernel(Dev
                                                        const uint32_t *__restrict__ packed,
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                        uint32_t n_reads, ResultRec *__restrict__ results,
-                                                       PlaceGeom g, ScanOut so) {
+                                                       PlaceGeom g, ScanOut so, TraceBuf trace) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t tail_lut[64];
     init_tail_lut(tail_lut);
@@ -941,7 +958,7 @@ __global__ void __launch_bounds__(CTA ? 512 : 256, CTA ? 2 : 4) place_kernel(Dev
         __syncwarp();
         const uint32_t D = *n_sets_smem;
 
-        finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
+        finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r, trace.rows ? &trace : nullptr);
         __syncwarp();
         if constexpr (CTA) __syncthreads();   // the tables are free again for the next read
     }
@@ -1194,7 +1211,8 @@ template <int K, bool CLOSED, bool CTA>
 static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                                   const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
                                   ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream,
-                                  void *scratch = nullptr, size_t scratch_bytes = 0, uint32_t *n_launches = nullptr) {
+                                  void *scratch = nullptr, size_t scratch_bytes = 0, uint32_t *n_launches = nullptr,
+                                  TraceBuf trace = TraceBuf{nullptr, nullptr, 0}) {
     const size_t ring = (size_t)4 * kRing * 4, group = (size_t)g.words_per_warp * 4;
     int warps = 8;
     size_t smem;
@@ -1226,7 +1244,7 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
                        (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024 && getenv("CLS_NO_SPLIT") == nullptr;
     ScanOut so{nullptr, nullptr, 0};
     if (split) so = carve_scratch(scratch, n_reads, kPairCapWide);
-    place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so);
+    place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so, trace);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (n_launches) ++*n_launches;
     if (split) {
@@ -1304,6 +1322,23 @@ cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uin
     }
     return ix.closed ? launch_place_m<0, true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
                      : launch_place_m<0, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);
+}
+
+// Debug export: place ONE read with the level-by-level walk and record the vote counters of every level.
+cudaError_t launch_trace(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed, const ReadDesc *reads,
+                         ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream, TraceBuf trace) {
+    if (ix.k_size == 35) {
+        if (g.cta_per_read)
+            return ix.closed ? launch_place_t<35, true, true>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace)
+                             : launch_place_t<35, false, true>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace);
+        return ix.closed ? launch_place_t<35, true, false>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace)
+                         : launch_place_t<35, false, false>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace);
+    }
+    if (g.cta_per_read)
+        return ix.closed ? launch_place_t<0, true, true>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace)
+                         : launch_place_t<0, false, true>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace);
+    return ix.closed ? launch_place_t<0, true, false>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace)
+                     : launch_place_t<0, false, false>(ix, pp, packed, reads, 0, 1, results, g, sm_count, stream, nullptr, 0, nullptr, trace);
 }
 
 cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, uint64_t *out, cudaStream_t stream) {

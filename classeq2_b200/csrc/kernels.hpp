@@ -34,6 +34,19 @@ struct PlaceGeom {
 
 PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout);
 
+// One row of the debug trace (cls_debug_node_counts): the vote counters of one child at one level.
+struct TraceRow {
+    uint64_t parent_id, child_id;
+    uint32_t level, cnt, excl, u;
+};
+struct TraceBuf {
+    TraceRow *rows;
+    uint32_t *n_rows;
+    uint32_t cap;
+};
+cudaError_t launch_trace(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed, const ReadDesc *reads,
+                         ResultRec *results, const PlaceGeom &g, int sm_count, cudaStream_t stream, TraceBuf trace);
+
 // Scratch the short-read path (k = 35, closed models) wants for a launch over `n_reads` reads: the scan
 // kernel hands every read's {node set, weight} pairs to a separate descent kernel through it.  0 when that
 // path does not apply.  Without (enough) scratch the scan warps run the descent themselves.

@@ -125,6 +125,21 @@ class Index:
     def upload(self, seqs) -> "ResidentBatch":
         return ResidentBatch(self, seqs)
 
+    def debug_node_counts(self, seq, params: Optional[PlaceParams] = None, cap: int = 1 << 16):
+        """``cls_debug_node_counts``: (rows, result) for one query; rows are dicts with parent_id, child_id, level,
+        cnt, excl, u, sorted by (level, child id)."""
+        b = seq.encode() if isinstance(seq, str) else bytes(seq)
+        arr = np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(1, np.uint8)
+        rows = (_lib.LevelCount * cap)()
+        n = C.c_uint64()
+        res = BatchResult(1)
+        cp, cr = (params or PlaceParams()).to_c(), res.to_c()
+        _lib.check(_lib.lib.cls_debug_node_counts(self._h, _ptr(arr, _lib.u8p), len(b), C.byref(cp), rows, cap, C.byref(n), C.byref(cr)))
+        if n.value > cap:
+            raise RuntimeError(f"trace has {n.value} rows, cap is {cap}")
+        out = [{f: getattr(rows[i], f) for f, _ in _lib.LevelCount._fields_} for i in range(n.value)]
+        return out, res
+
     def shard_probe(self, d_hashes: int, n: int, d_replies: int, stream: int = 0) -> None:
         """``cls_shard_probe``: answer ``n`` received hashes (device pointers) from this shard of the table."""
         _lib.check(_lib.lib.cls_shard_probe(self._h, C.c_void_p(d_hashes), int(n), C.c_void_p(d_replies), C.c_void_p(stream)))

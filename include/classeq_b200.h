@@ -296,6 +296,26 @@ int cls_place_routed(cls_index *index, cls_resident_batch *rb, const void *d_rep
  */
 int cls_debug_kmer_hashes(int device, uint32_t k_size, const uint8_t *bases, uint64_t len,
                           uint64_t *out_hashes, uint64_t cap, uint64_t *n_out);
+
+/*
+ * cls_debug_node_counts: per-node hit counts of ONE query, level by level.  The query
+ * is placed with a walk that evaluates every level with the vote counters (no shortcut of any kind; the
+ * outcome is the production path's - tests hold the two equal) and returns one row per evaluated level
+ * and non-leaf child c of the current node with at least one vote:
+ *   cnt  = |K(c)|, the matched distinct hashes whose node set contains c      (place_sequence.rs:319-333)
+ *   excl = hashes whose node set contains c and no other non-leaf child of the current node
+ *   u    = hashes whose node set contains any non-leaf child of the current node
+ * from which the reference's (one, rest) follow: default one = cnt, rest = u - excl; remove_intersection
+ * one = excl, rest = u - cnt; a single child with votes: (cnt, 0)              (place_sequence.rs:353-418)
+ * Rows are sorted by (level, child id); `*n_rows` receives the number of rows the walk produced (it may
+ * exceed `cap`).  `result` (optional, arrays of length 1) receives the placement.
+ */
+typedef struct cls_level_count {
+    uint64_t parent_id, child_id;
+    uint32_t level, cnt, excl, u;
+} cls_level_count;
+int cls_debug_node_counts(cls_index *index, const uint8_t *bases, uint64_t len, const cls_params *params,
+                          cls_level_count *rows, uint64_t cap, uint64_t *n_rows, cls_result *result);
 uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, uint64_t seed);
 
 /*

@@ -544,7 +544,10 @@ def rust_round(x: float) -> float:
 def place_sequence(header: str, sequence: str, tree: Tree,
                    max_iterations: Optional[int] = None,
                    min_match_coverage: Optional[float] = None,
-                   remove_intersection: Optional[bool] = None) -> Placement:
+                   remove_intersection: Optional[bool] = None, trace: Optional[list] = None) -> Placement:
+    """`trace` (test infrastructure for cls_debug_node_counts): receives one dict per evaluated level and
+    non-leaf child with K(c) != None: parent_id, child_id, level, cnt = |K(c)|, excl = |K(c) - union of the
+    siblings' K|, u = |union of all K|."""
     # :64-75
     remove_intersection = bool(remove_intersection) if remove_intersection is not None else False
     max_iterations = 1000 if max_iterations is None else max_iterations
@@ -610,6 +613,12 @@ def place_sequence(header: str, sequence: str, tree: Tree,
             if k is not None:
                 children_kmers.append((k, record))
         children_kmers.sort(key=lambda t: -len(t[0]))  # stable, descending (:335)
+        if trace is not None and children_kmers:
+            union_all = set().union(*[k for k, _ in children_kmers])
+            for kmers, clade in children_kmers:
+                others = set().union(*[k for k, c in children_kmers if c.id != clade.id]) if len(children_kmers) > 1 else set()
+                trace.append({"parent_id": parent.id, "child_id": clade.id, "level": iteration, "cnt": len(kmers),
+                              "excl": len(kmers - others), "u": len(union_all)})
 
         proposals = []  # (clade, one, rest)
         for kmers, clade in children_kmers:

@@ -503,3 +503,49 @@ def test_repeated_kmers_in_short_reads(cq, oracle):
             bad = np.flatnonzero(getattr(got, f) != want[f])
             assert bad.size == 0, (f, bad[:5], getattr(got, f)[bad[:5]], want[f][bad[:5]])
     md.close(), ix.close()
+
+
+# ---- per-node hit counts, level by level (cls_debug_node_counts) ------------------------------------
+@pytest.mark.parametrize("general", [False, True])
+@pytest.mark.parametrize("ri", [False, True])
+def test_node_counts_per_level_colletotrichum(cq, oracle, col_flat, col_tree, col_queries, general, ri):
+    """|K(c)|, exclusive and union counts of every non-leaf child with votes at every level of the walk,
+    against the oracle's sets (place_sequence.rs:311-428), on the reference's own data fixture
+    (multifurcating tree, 35 .. 1911 bp queries: both the one-warp and the one-CTA geometry)."""
+    flat = col_flat.with_general_sets() if general else col_flat
+    ix = cq.Index(flat, device=0)
+    params = cq.PlaceParams(remove_intersection=ri)
+    want_all = ix.place_batch([s for _, s in col_queries], params)
+    n_rows = 0
+    for qi, (h, s) in enumerate(col_queries):
+        if len(s) < 35 or (qi % 3 and len(s) > 400):
+            continue
+        trace = []
+        try:
+            oracle.place_sequence(h, s, col_tree, None, None, ri, trace=trace)
+        except oracle.PlacementError:
+            pass
+        trace.sort(key=lambda r: (r["level"], r["child_id"]))
+        rows, res = ix.debug_node_counts(s, params)
+        assert rows == trace, (h, rows[:3], trace[:3])
+        for f, _ in cq.engine.RESULT_DTYPES:   # the traced walk gives the production path's result
+            assert getattr(res, f)[0] == getattr(want_all, f)[qi], (h, f)
+        n_rows += len(rows)
+    assert n_rows > 500
+    ix.close()
+
+
+def test_node_counts_per_level_synthetic(cq, oracle):
+    from classeq2_b200 import synth
+    sm = synth.make_model(60, 300, 31)
+    bases, offsets, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, 40, 150, 33)
+    tree = oracle_tree_from_flat(oracle, sm.flat)
+    ix = cq.Index(sm.flat, device=0)
+    for i in range(40):
+        s = bases[int(offsets[i]):int(offsets[i + 1])].tobytes().decode()
+        trace = []
+        oracle.place_sequence("q", s, tree, trace=trace)
+        trace.sort(key=lambda r: (r["level"], r["child_id"]))
+        rows, _ = ix.debug_node_counts(s)
+        assert rows == trace, (i, rows[:3], trace[:3])
+    ix.close()
