@@ -71,6 +71,10 @@ class IndexInfo(C.Structure):
                 ("closed_sets", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class FastaRecords(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("header_begin", u64p), ("header_end", u64p), ("length", u32p)]
+
+
 class LevelCount(C.Structure):
     _fields_ = [("parent_id", C.c_uint64), ("child_id", C.c_uint64), ("level", C.c_uint32), ("cnt", C.c_uint32),
                 ("excl", C.c_uint32), ("u", C.c_uint32)]
@@ -99,6 +103,7 @@ PROTOTYPES = {
     "cls_resident_destroy": (None, [C.c_void_p]),
     "cls_resident_bytes": (C.c_uint64, [C.c_void_p]),
     "cls_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "cls_fasta_upload": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(FastaRecords)]),
     "cls_index_create_shard": (C.c_int, [C.POINTER(ModelView), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "cls_routed_windows": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
     "cls_route_hashes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, u64p, C.c_void_p]),

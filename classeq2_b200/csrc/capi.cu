@@ -20,6 +20,7 @@
 #include "device_types.hpp"
 #include "index_build.hpp"
 #include "host_pack.hpp"
+#include "fasta_kernels.hpp"
 #include "host_pool.hpp"
 #include "kernels.hpp"
 #include "murmur3_host.hpp"
@@ -131,7 +132,9 @@ struct cls_resident_batch {
     PackedLayout lay;
     DevBuf d_words, d_descs, d_results;
     DevBuf d_scratch;  // scan -> descent hand-over (one placement of this batch in flight at a time)
-    DevBuf d_win_base, d_route_state, d_runs;  // routed path: first window of every read; per-owner cursors + overflow flag
+    DevBuf d_win_base, d_route_state, d_runs;
+    std::vector<uint64_t> fa_header_begin, fa_header_end;  // cls_fasta_upload: the records the reader sent
+    std::vector<uint32_t> fa_length;  // routed path: first window of every read; per-owner cursors + overflow flag
     uint64_t n_windows = 0;
     PinBuf h_results;
 };
@@ -587,6 +590,123 @@ int cls_batch_upload(cls_index *ix, const cls_batch *batch, cls_resident_batch *
     CU_TRY(cudaMemcpy(rb->d_words.p, words.data(), words_b, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(rb->d_descs.p, descs.data(), descs_b, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemset(rb->d_results.p, 0xFF, res_b));
+    *out = rb.release();
+    return CLS_OK;
+}
+
+// ---- FASTA ingest on the device (file_or_stdin.rs:76-116, sequence.rs:47-56) -----------
+int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_resident_batch **out, cls_fasta_records *records) {
+    if (!ix || !out || !records || (n_bytes && !text)) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    std::memset(records, 0, sizeof *records);
+    if (n_bytes >= (1ull << 40)) return fail(CLS_ERR_UNSUPPORTED, "FASTA text beyond 2^40 bytes: split it");
+    CU_TRY(cudaSetDevice(ix->device));
+    auto rb = std::make_unique<cls_resident_batch>();
+    rb->device = ix->device;
+    cudaStream_t st = nullptr;
+    DevBuf d_text, d_tiles, d_bases, d_misc, d_codes, d_hpos, d_hkept, d_hflag, d_src, d_woff, d_len;
+    struct Free { std::vector<DevBuf *> b; ~Free() { for (auto *x : b) x->release(); } }
+        guard{{&d_text, &d_tiles, &d_bases, &d_misc, &d_codes, &d_hpos, &d_hkept, &d_hflag, &d_src, &d_woff, &d_len}};
+    const uint32_t nt = fasta_n_tiles(n_bytes);
+    TileBase totals{0, 0, 0, 0};
+    uint32_t non_ascii = 0;
+    if (n_bytes) {
+        CU_TRY(d_text.reserve(n_bytes + 16)); CU_TRY(d_tiles.reserve((size_t)nt * fasta_tile_bytes())); CU_TRY(d_bases.reserve((size_t)nt * sizeof(TileBase)));
+        CU_TRY(d_misc.reserve(256));
+        CU_TRY(cudaMemcpyAsync(d_text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemsetAsync(d_misc.p, 0, 256, st));
+        TileBase *d_totals = (TileBase *)d_misc.p;
+        uint32_t *d_non_ascii = (uint32_t *)((char *)d_misc.p + 128);
+        CU_TRY(launch_fasta_scan((const uint8_t *)d_text.p, n_bytes, d_tiles.p, (TileBase *)d_bases.p, d_totals, d_non_ascii, st));
+        CU_TRY(cudaMemcpyAsync(&totals, d_totals, sizeof totals, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&non_ascii, d_non_ascii, 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    if (non_ascii)
+        return fail(CLS_ERR_UNSUPPORTED, "non-ASCII byte in the FASTA text: Rust's to_uppercase() is Unicode-aware - use the host reader for this file");
+    const uint64_t n_hdr = totals.hdrs, n_kept = totals.kept;
+    if (n_hdr >= 0xFFFFFFFFull) return fail(CLS_ERR_UNSUPPORTED, "more than 2^32-1 header lines");
+    std::vector<uint64_t> hpos(n_hdr), hkept(n_hdr);
+    std::vector<uint32_t> hflag(n_hdr);
+    if (n_hdr || n_kept) {
+        CU_TRY(d_codes.reserve(n_kept + 16)); CU_TRY(d_hpos.reserve(n_hdr * 8 + 8)); CU_TRY(d_hkept.reserve(n_hdr * 8 + 8)); CU_TRY(d_hflag.reserve(n_hdr * 4 + 4));
+        CU_TRY(cudaMemsetAsync(d_hflag.p, 0, n_hdr * 4 + 4, st));
+        CU_TRY(launch_fasta_write((const uint8_t *)d_text.p, n_bytes, (const TileBase *)d_bases.p, (uint8_t *)d_codes.p, (uint64_t *)d_hpos.p,
+                                  (uint64_t *)d_hkept.p, (uint32_t *)d_hflag.p, st));
+        if (n_hdr) {
+            CU_TRY(cudaMemcpyAsync(hpos.data(), d_hpos.p, n_hdr * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(hkept.data(), d_hkept.p, n_hdr * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(hflag.data(), d_hflag.p, n_hdr * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    // ---- the record rules of the reader (file_or_stdin.rs:91-113) on the per-header-line facts -----------------
+    std::vector<uint64_t> src;      // first kept base of every record that is sent
+    auto &hb = rb->fa_header_begin;
+    auto &he = rb->fa_header_end;
+    auto &ln = rb->fa_length;
+    const bool orphan_sequence = n_hdr && hkept[0] > 0;   // bases before the first header: the reader errors out at that header (:96-100)
+    if (n_hdr && !orphan_sequence) {
+        for (uint64_t j = 0; j < n_hdr; ++j) {
+            const bool last = j + 1 == n_hdr;
+            const uint64_t kept = (last ? n_kept : hkept[j + 1]) - hkept[j];
+            if (kept >= (1ull << 31)) return fail(CLS_ERR_INVALID_ARGUMENT, "query longer than 2^31 bases");
+            if (!hflag[j]) {                    // header text empty after removing '>': the reader holds no header
+                if (kept && !last) break;       // ... and errors out at the next header line (:96-100)
+                continue;
+            }
+            if (last && kept == 0) continue;    // trailing record without sequence is dropped (:111-113)
+            hb.push_back(hpos[j]);
+            src.push_back(hkept[j]);
+            ln.push_back((uint32_t)kept);
+        }
+    }
+    const uint64_t n = hb.size();
+    he.resize(n);
+    parallel_for(n, 4096, [&](uint64_t a, uint64_t b) {   // end of the header line's content: "\n" or "\r\n" excluded
+        for (uint64_t i = a; i < b; ++i) {
+            const uint8_t *s = text + hb[i];
+            const void *nl = std::memchr(s, '\n', n_bytes - hb[i]);
+            uint64_t e = nl ? (uint64_t)((const uint8_t *)nl - text) : n_bytes;
+            if (nl && e > hb[i] && text[e - 1] == '\r') --e;
+            he[i] = e;
+        }
+    });
+    // ---- length classes, device order, packed layout: the same planner as cls_batch_upload ------------------------
+    std::vector<uint64_t> offsets(n + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + ln[i];
+    cls_batch fake{n, reinterpret_cast<const uint8_t *>(offsets.data()), offsets.data()};   // plan_batch never reads the bases
+    std::vector<uint32_t> word_off;
+    int rc = plan_batch(&fake, ix->dix.k_size, ix->dix.max_fanout, rb->lay, word_off);
+    if (rc != CLS_OK) return rc;
+    const PackedLayout &lay = rb->lay;
+    const size_t words_b = (size_t)lay.n_words * 4, descs_b = (size_t)lay.n_device * sizeof(ReadDesc), res_b = (size_t)lay.n_device * sizeof(ResultRec);
+    CU_TRY(rb->d_words.reserve(words_b + 16)); CU_TRY(rb->d_descs.reserve(descs_b + 16)); CU_TRY(rb->d_results.reserve(res_b + 32));
+    CU_TRY(rb->h_results.reserve(res_b + 32));
+    if (lay.n_device) {
+        std::vector<ReadDesc> descs(lay.n_device);
+        std::vector<uint64_t> src_dev(lay.n_device);
+        std::vector<uint32_t> len_dev(lay.n_device);
+        for (uint32_t j = 0; j < lay.n_device; ++j) {
+            const uint32_t i = lay.perm[j];
+            descs[j] = ReadDesc{word_off[j], ln[i]};
+            src_dev[j] = src[i];
+            len_dev[j] = ln[i];
+        }
+        CU_TRY(d_src.reserve(src_dev.size() * 8)); CU_TRY(d_woff.reserve(word_off.size() * 4)); CU_TRY(d_len.reserve(len_dev.size() * 4));
+        CU_TRY(cudaMemcpyAsync(d_src.p, src_dev.data(), src_dev.size() * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_woff.p, word_off.data(), (size_t)lay.n_device * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(d_len.p, len_dev.data(), len_dev.size() * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(rb->d_descs.p, descs.data(), descs_b, cudaMemcpyHostToDevice, st));
+        CU_TRY(launch_fasta_pack((const uint8_t *)d_codes.p, (const uint64_t *)d_src.p, (const uint32_t *)d_woff.p, (const uint32_t *)d_len.p,
+                                 lay.n_device, (uint32_t *)rb->d_words.p, ix->sm_count, st));
+        CU_TRY(cudaMemsetAsync(rb->d_results.p, 0xFF, res_b, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    records->n_records = n;
+    records->header_begin = hb.data();
+    records->header_end = he.data();
+    records->length = ln.data();
     *out = rb.release();
     return CLS_OK;
 }

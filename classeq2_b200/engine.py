@@ -125,6 +125,27 @@ class Index:
     def upload(self, seqs) -> "ResidentBatch":
         return ResidentBatch(self, seqs)
 
+    def upload_fasta(self, text: Union[bytes, bytearray, memoryview, np.ndarray]):
+        """``cls_fasta_upload``: parse, filter and pack a FASTA text ON THE DEVICE.  Returns ``(batch, headers,
+        lengths)``: a :class:`ResidentBatch` holding the records the reference's reader would send, their
+        headers (every '>' removed) and filtered lengths."""
+        arr = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, dtype=np.uint8)
+        if arr.size == 0:
+            arr = np.zeros(1, np.uint8)
+            n_bytes = 0
+        else:
+            n_bytes = arr.size
+        h = C.c_void_p()
+        rec = _lib.FastaRecords()
+        _lib.check(_lib.lib.cls_fasta_upload(self._h, arr.ctypes.data_as(_lib.u8p), n_bytes, C.byref(h), C.byref(rec)))
+        n = int(rec.n_records)
+        hb = np.ctypeslib.as_array(rec.header_begin, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        he = np.ctypeslib.as_array(rec.header_end, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+        ln = np.ctypeslib.as_array(rec.length, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        raw = arr.tobytes() if n else b""
+        headers = [raw[int(a):int(b)].replace(b">", b"").decode("utf-8", "replace") for a, b in zip(hb, he)]
+        return ResidentBatch._from_handle(self, h, n), headers, ln
+
     def debug_node_counts(self, seq, params: Optional[PlaceParams] = None, cap: int = 1 << 16):
         """``cls_debug_node_counts``: (rows, result) for one query; rows are dicts with parent_id, child_id, level,
         cnt, excl, u, sorted by (level, child id)."""
@@ -171,6 +192,12 @@ class ResidentBatch:
         self._h = C.c_void_p()
         cb = _c_batch(bases, offsets)
         _lib.check(_lib.lib.cls_batch_upload(index._h, C.byref(cb), C.byref(self._h)))
+
+    @classmethod
+    def _from_handle(cls, index: "Index", handle, n: int) -> "ResidentBatch":
+        rb = cls.__new__(cls)
+        rb.index, rb.n, rb._h = index, n, handle
+        return rb
 
     def place(self, params: Optional[PlaceParams] = None, stream: int = 0) -> None:
         """Enqueue the placement kernels on ``stream`` (a ``cudaStream_t`` as int); asynchronous."""

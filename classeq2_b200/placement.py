@@ -55,10 +55,12 @@ def read_fasta_text(text: str) -> List[Tuple[str, str]]:
     out: List[Tuple[str, str]] = []
     header, parts = "", []
     lines = text.split("\n")
+    terminated = [True] * len(lines)
+    terminated[-1] = False          # what follows the last "\n" (possibly nothing) has no terminator
     if lines and lines[-1] == "":
         lines.pop()
-    for line in lines:
-        if line.endswith("\r"):
+    for line, term in zip(lines, terminated):
+        if term and line.endswith("\r"):   # BufRead::lines strips "\n" and then one "\r": only "\r\n" is a terminator
             line = line[:-1]
         if line == "":
             continue
@@ -84,7 +86,7 @@ def read_fasta(query: Union[str, os.PathLike, io.TextIOBase]) -> List[Tuple[str,
         return read_fasta_text(query.read())
     if str(query) == "-":
         return read_fasta_text(sys.stdin.read())
-    with open(query, "r", encoding="utf-8") as f:
+    with open(query, "r", encoding="utf-8", newline="") as f:   # no newline translation: "\r" alone is not a line break
         return read_fasta_text(f.read())
 
 

@@ -226,6 +226,30 @@ uint64_t cls_resident_bytes(const cls_resident_batch *rb);
 int cls_get_timing(const cls_index *index, cls_timing *out);
 
 /*
+ * FASTA ingest on the device: the raw bytes of a (multi-)FASTA file go to the GPU, which classifies
+ * every byte (header line / sequence line), upper-cases, keeps A/C/G/T only - everything else is
+ * deleted and the flanks joined (sequence.rs:47-56) - and packs the records to 2 bit; the record rules
+ * of the reference's reader (file_or_stdin.rs:76-116: '>' lines start records and lose every '>',
+ * empty lines are skipped, "\n" and "\r\n" terminate lines, a trailing record without sequence is
+ * dropped while a mid-file one is kept, a record whose header text is empty is never sent and stops the
+ * reader at the next header line if it had sequence, sequence before the first header stops it at once)
+ * are applied to the per-line facts on the host.  The result is a resident batch exactly as
+ * cls_batch_upload would have built from the reader's records (use cls_place_resident /
+ * cls_resident_fetch; results come in record order), plus where every record's header sits in `text`:
+ * header = text[header_begin + .. header_end) minus every '>'.  The arrays live in the batch and are
+ * freed with it.  CLS_ERR_UNSUPPORTED: the text holds a byte >= 0x80 (Rust's to_uppercase() is
+ * Unicode-aware; use the host reader, cls_filter_sequence, for such files).
+ */
+typedef struct cls_fasta_records {
+    uint64_t n_records;
+    const uint64_t *header_begin;   /* byte offset of the header line (its '>')                       */
+    const uint64_t *header_end;     /* one past the header line's content ("\n" / "\r\n" excluded)   */
+    const uint32_t *length;         /* filtered sequence length in bases                              */
+} cls_fasta_records;
+int cls_fasta_upload(cls_index *index, const uint8_t *text, uint64_t n_bytes, cls_resident_batch **out,
+                     cls_fasta_records *records);
+
+/*
  * Hash-sharded index (config 5 of BASELINE.json).  The k-mer table is split over up
  * to 8 GPUs by `owner = (hash >> 61) % n_shards`; node-set records and the tree are replicated.
  * The reference has no counterpart (its index is one in-memory HashMap, kmers_map.rs:77-87): these

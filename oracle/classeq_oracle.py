@@ -133,10 +133,12 @@ def read_fasta_text(text: str) -> List[Tuple[str, str]]:
     header = ""
     sequence = ""
     lines = text.split("\n")
+    terminated = [True] * len(lines)
+    terminated[-1] = False  # BufRead::lines pops "\n" and then one "\r": a "\r" at end of file stays
     if lines and lines[-1] == "":
         lines.pop()
-    for line in lines:
-        if line.endswith("\r"):
+    for line, term in zip(lines, terminated):
+        if term and line.endswith("\r"):
             line = line[:-1]
         if line == "":
             continue
