@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -601,6 +602,9 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
     std::memset(records, 0, sizeof *records);
     if (n_bytes >= (1ull << 40)) return fail(CLS_ERR_UNSUPPORTED, "FASTA text beyond 2^40 bytes: split it");
     CU_TRY(cudaSetDevice(ix->device));
+    static const bool dbg = getenv("CLS_DEBUG_TIMING") != nullptr;
+    double tlast = now_ms();
+    auto lap = [&](const char *what) { if (dbg) { const double t = now_ms(); fprintf(stderr, "[fasta] %-22s %8.2f ms\n", what, t - tlast); tlast = t; } };
     auto rb = std::make_unique<cls_resident_batch>();
     rb->device = ix->device;
     cudaStream_t st = nullptr;
@@ -613,6 +617,7 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
     if (n_bytes) {
         CU_TRY(d_text.reserve(n_bytes + 16)); CU_TRY(d_tiles.reserve((size_t)nt * fasta_tile_bytes())); CU_TRY(d_bases.reserve((size_t)nt * sizeof(TileBase)));
         CU_TRY(d_misc.reserve(256));
+        lap("alloc");
         CU_TRY(cudaMemcpyAsync(d_text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemsetAsync(d_misc.p, 0, 256, st));
         TileBase *d_totals = (TileBase *)d_misc.p;
@@ -621,6 +626,7 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
         CU_TRY(cudaMemcpyAsync(&totals, d_totals, sizeof totals, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(&non_ascii, d_non_ascii, 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        lap("h2d + scan");
     }
     if (non_ascii)
         return fail(CLS_ERR_UNSUPPORTED, "non-ASCII byte in the FASTA text: Rust's to_uppercase() is Unicode-aware - use the host reader for this file");
@@ -639,12 +645,14 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
             CU_TRY(cudaMemcpyAsync(hflag.data(), d_hflag.p, n_hdr * 4, cudaMemcpyDeviceToHost, st));
         }
         CU_TRY(cudaStreamSynchronize(st));
+        lap("write + d2h");
     }
     // ---- the record rules of the reader (file_or_stdin.rs:91-113) on the per-header-line facts -----------------
     std::vector<uint64_t> src;      // first kept base of every record that is sent
     auto &hb = rb->fa_header_begin;
     auto &he = rb->fa_header_end;
     auto &ln = rb->fa_length;
+    hb.reserve(n_hdr); src.reserve(n_hdr); ln.reserve(n_hdr);
     const bool orphan_sequence = n_hdr && hkept[0] > 0;   // bases before the first header: the reader errors out at that header (:96-100)
     if (n_hdr && !orphan_sequence) {
         for (uint64_t j = 0; j < n_hdr; ++j) {
@@ -661,6 +669,7 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
             ln.push_back((uint32_t)kept);
         }
     }
+    lap("record rules");
     const uint64_t n = hb.size();
     he.resize(n);
     parallel_for(n, 4096, [&](uint64_t a, uint64_t b) {   // end of the header line's content: "\n" or "\r\n" excluded
@@ -672,6 +681,7 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
             he[i] = e;
         }
     });
+    lap("header ends");
     // ---- length classes, device order, packed layout: the same planner as cls_batch_upload ------------------------
     std::vector<uint64_t> offsets(n + 1, 0);
     for (uint64_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + ln[i];
@@ -679,20 +689,22 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
     std::vector<uint32_t> word_off;
     int rc = plan_batch(&fake, ix->dix.k_size, ix->dix.max_fanout, rb->lay, word_off);
     if (rc != CLS_OK) return rc;
+    lap("plan");
     const PackedLayout &lay = rb->lay;
     const size_t words_b = (size_t)lay.n_words * 4, descs_b = (size_t)lay.n_device * sizeof(ReadDesc), res_b = (size_t)lay.n_device * sizeof(ResultRec);
     CU_TRY(rb->d_words.reserve(words_b + 16)); CU_TRY(rb->d_descs.reserve(descs_b + 16)); CU_TRY(rb->d_results.reserve(res_b + 32));
-    CU_TRY(rb->h_results.reserve(res_b + 32));
-    if (lay.n_device) {
+    if (lay.n_device) {   // the pinned result buffer is allocated by the first cls_resident_fetch
         std::vector<ReadDesc> descs(lay.n_device);
         std::vector<uint64_t> src_dev(lay.n_device);
         std::vector<uint32_t> len_dev(lay.n_device);
-        for (uint32_t j = 0; j < lay.n_device; ++j) {
-            const uint32_t i = lay.perm[j];
-            descs[j] = ReadDesc{word_off[j], ln[i]};
-            src_dev[j] = src[i];
-            len_dev[j] = ln[i];
-        }
+        parallel_for(lay.n_device, 1 << 15, [&](uint64_t j0, uint64_t j1) {
+            for (uint64_t j = j0; j < j1; ++j) {
+                const uint32_t i = lay.perm[j];
+                descs[j] = ReadDesc{word_off[j], ln[i]};
+                src_dev[j] = src[i];
+                len_dev[j] = ln[i];
+            }
+        });
         CU_TRY(d_src.reserve(src_dev.size() * 8)); CU_TRY(d_woff.reserve(word_off.size() * 4)); CU_TRY(d_len.reserve(len_dev.size() * 4));
         CU_TRY(cudaMemcpyAsync(d_src.p, src_dev.data(), src_dev.size() * 8, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(d_woff.p, word_off.data(), (size_t)lay.n_device * 4, cudaMemcpyHostToDevice, st));
@@ -703,6 +715,7 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
         CU_TRY(cudaMemsetAsync(rb->d_results.p, 0xFF, res_b, st));
         CU_TRY(cudaStreamSynchronize(st));
     }
+    lap("pack");
     records->n_records = n;
     records->header_begin = hb.data();
     records->header_end = he.data();
@@ -728,6 +741,7 @@ int cls_resident_fetch(cls_index *ix, cls_resident_batch *rb, void *stream, cls_
     CU_TRY(cudaSetDevice(ix->device));
     const size_t res_b = (size_t)rb->lay.n_device * sizeof(ResultRec);
     if (res_b) {
+        CU_TRY(rb->h_results.reserve(res_b + 32));
         CU_TRY(cudaMemcpyAsync(rb->h_results.p, rb->d_results.p, res_b, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     }
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
