@@ -450,13 +450,17 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                     max_iterations: Optional[int] = None, min_match_coverage: Optional[float] = None,
                     overwrite: bool = False, output_format: str = "yaml",
                     remove_intersection: Optional[bool] = None, *, index: Optional[Index] = None,
-                    device: int = 0, batch_size: int = 1 << 20) -> List[PlacementTime]:
+                    device: int = 0, batch_size: int = 1 << 20, ingest: str = "host") -> List[PlacementTime]:
     """Place every sequence of a FASTA input on ``tree`` and append one record per query to
     ``<out_file>.yaml|.jsonl`` (errors to ``<out_file>.error``), as the reference does.
 
     ``index`` may carry an already uploaded model (``cls_index_create`` once per model - the hook is
     right after ``load_database``); otherwise the model is uploaded for this call.
+    ``ingest="device"`` parses, filters and packs the FASTA text on the GPU (``cls_fasta_upload``; file paths
+    only, ASCII only) instead of with the host reader; the records and results are identical.
     """
+    if ingest not in ("host", "device"):
+        raise ValueError("ingest must be 'host' or 'device'")
     if output_format not in ("yaml", "jsonl"):
         raise ValueError("output_format must be 'yaml' or 'jsonl'")           # output_format.rs
     base = os.fspath(out_file)
@@ -474,10 +478,20 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                                   "option is `false`.")                         # :96-101
         os.remove(out_path)
 
-    records = read_fasta(query_sequence)
     own_index = index is None
     if own_index:
         index = Index(tree, device=device)
+    device_batch = None
+    if ingest == "device":
+        if hasattr(query_sequence, "read") or str(query_sequence) == "-":
+            raise ValueError("ingest='device' reads a file path")
+        with open(query_sequence, "rb") as f:
+            raw = f.read()
+        device_batch, headers, _ = index.upload_fasta(raw)
+        records = [(h, None) for h in headers]
+        batch_size = max(len(records), 1)
+    else:
+        records = read_fasta(query_sequence)
     lookup = _TreeLookup(tree)
     params = PlaceParams(max_iterations, min_match_coverage, remove_intersection)
     times: List[PlacementTime] = []
@@ -486,7 +500,11 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
             for a in range(0, len(records), batch_size):
                 chunk = records[a:a + batch_size]
                 t0 = time.perf_counter()
-                res = index.place_batch([s for _, s in chunk], params)
+                if device_batch is not None:
+                    device_batch.place(params)
+                    res = device_batch.fetch()
+                else:
+                    res = index.place_batch([s for _, s in chunk], params)
                 per_seq_ms = (time.perf_counter() - t0) * 1e3 / max(len(chunk), 1)
                 buf_o, buf_e = [], []
                 for i, (header, _) in enumerate(chunk):
@@ -501,6 +519,8 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                 fo.write("".join(buf_o))
                 fe.write("".join(buf_e))
     finally:
+        if device_batch is not None:
+            device_batch.close()
         if own_index:
             index.close()
     return times

@@ -168,3 +168,18 @@ def test_place_sequences_end_to_end(ps, tmp_path, col_tree, col_expected, fmt):
     cq.place_sequences(os.path.join(GOLDEN, "colletotrichum_queries.fasta"), tree, out, output_format=fmt, overwrite=True,
                        remove_intersection=True)
     assert out_path.read_text() != "" and err_path.read_text().count("kmers.") == 2 * n_err   # error file is appended
+
+
+@pytest.mark.gpu
+def test_place_sequences_device_ingest_writes_the_same_files(ps, tmp_path, col_tree):
+    """FASTA parsed, filtered and packed on the GPU (cls_fasta_upload): result and error files byte-identical
+    to the host-reader run."""
+    import classeq2_b200 as cq
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    fa = os.path.join(GOLDEN, "colletotrichum_queries.fasta")
+    a, b = tmp_path / "host" / "r.yaml", tmp_path / "dev" / "r.yaml"
+    ta = cq.place_sequences(fa, tree, a)
+    tb = cq.place_sequences(fa, tree, b, ingest="device")
+    assert [t.sequence for t in ta] == [t.sequence for t in tb] and len(ta) > 300
+    assert a.read_bytes() == b.read_bytes() and len(a.read_bytes()) > 10000
+    assert (tmp_path / "host" / "r.error").read_bytes() == (tmp_path / "dev" / "r.error").read_bytes()
