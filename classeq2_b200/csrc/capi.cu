@@ -508,8 +508,15 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
     static const uint64_t kChunkBases = [] { const char *e = getenv("CLS_CHUNK_MBASES"); return (uint64_t)(e ? atoi(e) : 24) << 20; }();  // bases per chunk
     for (const LengthClass &c : lay.classes) {
         const uint64_t per = std::max<uint64_t>(4096, kChunkBases / std::max<uint32_t>(c.max_len, 1));
-        for (uint64_t a = 0; a < c.count; a += per)
-            chunks.push_back(Chunk{(uint32_t)(c.first + a), (uint32_t)std::min<uint64_t>(per, c.count - a), c.max_len});
+        // the very first chunks are small so that the GPU starts early; later ones grow (fewer launch tails)
+        static const int ramp = [] { const char *e = getenv("CLS_CHUNK_RAMP"); return e ? atoi(e) : 1; }();
+        uint64_t a = 0, step = (ramp && chunks.empty()) ? std::max<uint64_t>(4096, per / 4) : per;
+        while (a < c.count) {
+            const uint64_t n = std::min<uint64_t>(step, c.count - a);
+            chunks.push_back(Chunk{(uint32_t)(c.first + a), (uint32_t)n, c.max_len});
+            a += n;
+            if (ramp) step = std::min<uint64_t>(step * 2, per * (uint64_t)ramp);
+        }
     }
     while (w->chunk_ev.size() < 4 * chunks.size()) {
         cudaEvent_t e = nullptr;
