@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
     WarpLayout wl = carve_warp(smem, g, warp, warps_per_cta);
     uint64_t *hs = reinterpret_cast<uint64_t *>(wl.t1);  // 2W hashes: t1 holds 2H 32-bit words
-    uint32_t *own_cnt = wl.t2k;                          // per-owner counts, then segment bases (low / high words)
+    uint64_t *sorted_h = reinterpret_cast<uint64_t *>(wl.t2k);  // the same hashes grouped by owner (t2k + t2c: 2 x t2_size words)
+    uint16_t *sorted_w = reinterpret_cast<uint16_t *>(wl.lst);   // the window of every sorted hash
+    uint32_t *own_cnt = wl.lst + (g.t2_size >> 1);               // per-owner counts, then running positions
     __syncthreads();
     const uint32_t gwarp = blockIdx.x * warps_per_cta + warp, gstride = gridDim.x * warps_per_cta;
 #pragma unroll 1
@@ -97,16 +99,28 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
             }
         }
         __syncwarp();
-        // reserve this read's share of every owner's segment
+        // reserve this read's share of every owner's segment; own_loc = start of the owner's run in the sorted copy
+        uint32_t my_cnt = 0, my_loc = 0;
+        uint64_t my_base = 0;
+        if (lane < n_shards) my_cnt = own_cnt[lane];
+        {
+            uint32_t inc = my_cnt;
+            for (int d = 1; d < 8; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, inc, d);
+                if ((int)lane >= d) inc += t;
+            }
+            my_loc = inc - my_cnt;
+        }
         if (lane < n_shards) {
-            const uint32_t c = own_cnt[lane];
-            const unsigned long long base = c ? atomicAdd(&cursor[lane], (unsigned long long)c) : 0ull;
-            if (base + c > seg_cap) *overflow = 1u;
-            own_cnt[lane] = (uint32_t)base;
-            own_cnt[8 + lane] = (uint32_t)(base >> 32);
-            runs[(size_t)(first_read + r) * 8 + lane] = make_uint2((uint32_t)base, base + c > seg_cap ? 0u : c);
+            my_base = my_cnt ? atomicAdd(&cursor[lane], (unsigned long long)my_cnt) : 0ull;
+            const bool fits = my_base + my_cnt <= seg_cap;
+            if (!fits) *overflow = 1u;
+            runs[(size_t)(first_read + r) * 8 + lane] = make_uint2((uint32_t)my_base, fits ? my_cnt : 0u);
+            if (!fits) my_cnt = 0;
+            own_cnt[lane] = my_loc;   // running position of the owner inside the sorted copy
         }
         __syncwarp();
+        // counting sort by owner into shared memory (window order is kept inside an owner)
         for (uint32_t w0 = 0; w0 < 2 * W; w0 += 32) {
             const uint32_t w = w0 + lane;
             const bool valid = w < 2 * W;
@@ -114,23 +128,26 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
             const uint32_t o = valid ? owner_of(h, n_shards) : 0xFFu;
             const uint32_t peers = __match_any_sync(kFull, o);
             const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            // every lane of a group reads the group's cursor; then the group's leader advances it
-            uint64_t cur = 0;
-            if (valid) cur = ((uint64_t)own_cnt[8 + o] << 32) | own_cnt[o];
+            uint32_t cur = 0;
+            if (valid) cur = own_cnt[o];
             __syncwarp();
             if (valid) {
-                const uint64_t at = cur + rank;
-                if ((uint32_t)(__ffs(peers) - 1) == lane) {
-                    const uint64_t nxt = cur + __popc(peers);
-                    own_cnt[o] = (uint32_t)nxt;
-                    own_cnt[8 + o] = (uint32_t)(nxt >> 32);
-                }
-                if (at < seg_cap) {
-                    seg.p[o][at] = h;
-                    slot_win[(uint64_t)o * seg_cap + at] = (uint16_t)w;
-                }
+                sorted_h[cur + rank] = h;
+                sorted_w[cur + rank] = (uint16_t)w;
+                if ((uint32_t)(__ffs(peers) - 1) == lane) own_cnt[o] = cur + __popc(peers);
             }
             __syncwarp();
+        }
+        // one contiguous run per owner: coalesced stores, local or over NVLink
+        for (uint32_t o = 0; o < n_shards; ++o) {
+            const uint32_t c = __shfl_sync(kFull, my_cnt, o), loc = __shfl_sync(kFull, my_loc, o);
+            const uint64_t base = __shfl_sync(kFull, my_base, o);
+            uint64_t *dst = seg.p[o] + base;
+            uint16_t *dw = slot_win + (uint64_t)o * seg_cap + base;
+            for (uint32_t i = lane; i < c; i += 32) {
+                dst[i] = sorted_h[loc + i];
+                dw[i] = sorted_w[loc + i];
+            }
         }
         __syncwarp();
     }
@@ -139,21 +156,34 @@ __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_
 // ---- stage 4: the owner answers ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) shard_probe_kernel(DeviceIndex ix, uint32_t shard, const uint64_t *__restrict__ hashes,
                                                           uint64_t n, ProbeReply *__restrict__ replies) {
+    __shared__ __align__(16) uint32_t stage[8][96];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t h = hashes[i];
-    const uint32_t bmask = (uint32_t)ix.bucket_mask;
-    uint32_t b = (uint32_t)h & bmask;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     ProbeReply rep{kEmpty, 0u, 0u};
-    for (;;) {
-        uint64_t h0, m0, h1, m1;
-        ld_bucket(ix.table, b, h0, m0, h1, m1);
-        if (h0 == h && (uint32_t)m0 != kEmpty) { rep = ProbeReply{(uint32_t)m0, ((2u * b) << 3) | shard, (uint32_t)(m0 >> 32) & kCodeMask}; break; }
-        if (h1 == h && (uint32_t)m1 != kEmpty) { rep = ProbeReply{(uint32_t)m1, ((2u * b + 1u) << 3) | shard, (uint32_t)(m1 >> 32) & kCodeMask}; break; }
-        if (!((uint32_t)(m0 >> 32) & kOverflowBit)) break;
-        b = (b + 1) & bmask;
+    if (i < n) {
+        const uint64_t h = hashes[i];
+        const uint32_t bmask = (uint32_t)ix.bucket_mask;
+        uint32_t b = (uint32_t)h & bmask;
+        for (;;) {
+            uint64_t h0, m0, h1, m1;
+            ld_bucket(ix.table, b, h0, m0, h1, m1);
+            if (h0 == h && (uint32_t)m0 != kEmpty) { rep = ProbeReply{(uint32_t)m0, ((2u * b) << 3) | shard, (uint32_t)(m0 >> 32) & kCodeMask}; break; }
+            if (h1 == h && (uint32_t)m1 != kEmpty) { rep = ProbeReply{(uint32_t)m1, ((2u * b + 1u) << 3) | shard, (uint32_t)(m1 >> 32) & kCodeMask}; break; }
+            if (!((uint32_t)(m0 >> 32) & kOverflowBit)) break;
+            b = (b + 1) & bmask;
+        }
     }
-    replies[i] = rep;
+    // the 32 replies of a warp are 384 contiguous bytes: store them as 24 aligned 16-byte vectors (whole
+    // sectors - the destination may be a peer's memory across NVLink, where partial-sector stores cost a packet each)
+    const uint64_t i0 = i - lane;
+    const bool vector_ok = i0 + 32 <= n && ((reinterpret_cast<uintptr_t>(replies + i0) & 15u) == 0);
+    if (vector_ok) {
+        stage[warp][3 * lane] = rep.set_off; stage[warp][3 * lane + 1] = rep.slot; stage[warp][3 * lane + 2] = rep.code;
+        __syncwarp();
+        if (lane < 24) reinterpret_cast<uint4 *>(replies + i0)[lane] = reinterpret_cast<const uint4 *>(stage[warp])[lane];
+    } else if (i < n) {
+        replies[i] = rep;
+    }
 }
 
 // ---- stage 6: count and descend at home -------------------------------------------------------

@@ -184,7 +184,7 @@ class ShardedPlacer:
         if transport == "p2p":
             if max_windows <= 0:
                 raise ValueError("transport='p2p' needs max_windows (k-mer windows of the largest batch)")
-            self.peers = PeerBuffers(device, rank, world, int(max_windows / world * slack) + 65536, group)
+            self.peers = PeerBuffers(device, rank, world, (int(max_windows / world * slack) + 65536 + 3) & ~3, group)
         elif transport != "nccl":
             raise ValueError("transport must be 'nccl' or 'p2p'")
 
@@ -211,7 +211,7 @@ class ShardedPlacer:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         nw = rb.routed_windows()
         world = self.world
-        seg_cap = int(nw / world * self.slack) + 65536
+        seg_cap = (int(nw / world * self.slack) + 65536 + 3) & ~3   # multiple of 4: reply segments stay 16-byte aligned
         buf = self._buffers(nw, seg_cap, dev)
         send, win_slot, rep_in = buf["send"], buf["win_slot"], buf["rep_in"]
         ev[0].record(st)
@@ -258,7 +258,7 @@ class ShardedPlacer:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         pb, world, me = self.peers, self.world, self.rank
         nw = rb.routed_windows()
-        if int(nw / world * self.slack) + 65536 > pb.seg_cap:
+        if ((int(nw / world * self.slack) + 65536 + 3) & ~3) > pb.seg_cap:
             raise ValueError("batch has more k-mer windows than the peer buffers were sized for (max_windows)")
         seg_cap = pb.seg_cap
         b = getattr(self, "_buf", None)
@@ -340,7 +340,7 @@ class LocalShardedPlacer:
         rb = self.shards[0].upload(seqs)
         st = torch.cuda.current_stream(dev)
         nw = rb.routed_windows()
-        seg_cap = int(nw / self.n_shards * self.slack) + 65536
+        seg_cap = (int(nw / self.n_shards * self.slack) + 65536 + 3) & ~3
         send = torch.empty(self.n_shards * seg_cap, dtype=torch.int64, device=dev)
         win_slot = torch.empty(self.n_shards * seg_cap, dtype=torch.int16, device=dev)
         counts = rb.route_hashes(self.n_shards, seg_cap, send.data_ptr(), win_slot.data_ptr(), st.cuda_stream)

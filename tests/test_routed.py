@@ -194,7 +194,7 @@ got = sp.place((bases, offsets))
 bad = {n: int((getattr(got, n) != getattr(want, n)).sum()) for n, _ in RESULT_DTYPES}
 # the same with the exchange fused into the kernels (peer stores over NVLink instead of NCCL all-to-alls), twice
 # in a row so that the reuse of the inboxes / reply boxes is exercised
-sp2 = ShardedPlacer(sm.flat, local, rank, world, transport="p2p", max_windows=2 * 116 * 6000)
+sp2 = ShardedPlacer(sm.flat, local, rank, world, transport="p2p", max_windows=2 * 116 * (4000 + 500 * world))
 for _ in range(2):
     got2 = sp2.place((bases, offsets))
     for n, _ in RESULT_DTYPES:
