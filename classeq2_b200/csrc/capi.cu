@@ -509,7 +509,7 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
     for (const LengthClass &c : lay.classes) {
         const uint64_t per = std::max<uint64_t>(4096, kChunkBases / std::max<uint32_t>(c.max_len, 1));
         // the very first chunks are small so that the GPU starts early; later ones grow (fewer launch tails)
-        static const int ramp = [] { const char *e = getenv("CLS_CHUNK_RAMP"); return e ? atoi(e) : 1; }();
+        static const int ramp = [] { const char *e = getenv("CLS_CHUNK_RAMP"); return e ? atoi(e) : 2; }();
         uint64_t a = 0, step = (ramp && chunks.empty()) ? std::max<uint64_t>(4096, per / 4) : per;
         while (a < c.count) {
             const uint64_t n = std::min<uint64_t>(step, c.count - a);
