@@ -126,6 +126,23 @@ struct cls_index {
     std::mutex mu;
     std::vector<std::unique_ptr<Workspace>> pool;
     cls_timing timing{};
+    cls_index() = default;
+    cls_index(const cls_index &) = delete;
+    cls_index &operator=(const cls_index &) = delete;
+    ~cls_index() {   // also runs when cls_index_create fails half-way: nothing is leaked
+        cudaSetDevice(device);
+        for (auto &w : pool) {
+            if (w->stream) { cudaStreamSynchronize(w->stream); cudaStreamDestroy(w->stream); }
+            if (w->stream2) { cudaStreamSynchronize(w->stream2); cudaStreamDestroy(w->stream2); }
+            for (auto &e : w->chunk_ev) if (e) cudaEventDestroy(e);
+            for (auto &e : w->ev) if (e) cudaEventDestroy(e);
+            w->h_words.release(); w->h_descs.release(); w->h_results.release();
+            w->d_words.release(); w->d_descs.release(); w->d_results.release();
+            w->d_scratch[0].release(); w->d_scratch[1].release();
+        }
+        d_table.release(); d_arena.release(); d_qnodes.release(); d_qchild.release(); d_qid.release();
+        d_terms.release(); d_qinfo.release(); d_lca.release();
+    }
 };
 
 struct cls_resident_batch {
@@ -133,11 +150,19 @@ struct cls_resident_batch {
     PackedLayout lay;
     DevBuf d_words, d_descs, d_results;
     DevBuf d_scratch;  // scan -> descent hand-over (one placement of this batch in flight at a time)
-    DevBuf d_win_base, d_route_state, d_runs;
+    DevBuf d_win_base, d_route_state, d_runs;  // routed path: first window of every read; per-owner cursors + overflow flag; run table
     std::vector<uint64_t> fa_header_begin, fa_header_end;  // cls_fasta_upload: the records the reader sent
-    std::vector<uint32_t> fa_length;  // routed path: first window of every read; per-owner cursors + overflow flag
+    std::vector<uint32_t> fa_length;
     uint64_t n_windows = 0;
     PinBuf h_results;
+    cls_resident_batch() = default;
+    cls_resident_batch(const cls_resident_batch &) = delete;
+    cls_resident_batch &operator=(const cls_resident_batch &) = delete;
+    ~cls_resident_batch() {   // also runs on the error paths of the upload calls: nothing is leaked
+        cudaSetDevice(device);
+        d_words.release(); d_descs.release(); d_results.release(); d_scratch.release();
+        d_win_base.release(); d_route_state.release(); d_runs.release(); h_results.release();
+    }
 };
 
 namespace {
@@ -455,22 +480,7 @@ int cls_index_create_shard(const cls_model_view *model, int device, uint32_t sha
     return CLS_OK;
 }
 
-void cls_index_destroy(cls_index *ix) {
-    if (!ix) return;
-    cudaSetDevice(ix->device);
-    for (auto &w : ix->pool) {
-        if (w->stream) { cudaStreamSynchronize(w->stream); cudaStreamDestroy(w->stream); }
-        if (w->stream2) { cudaStreamSynchronize(w->stream2); cudaStreamDestroy(w->stream2); }
-        for (auto &e : w->chunk_ev) if (e) cudaEventDestroy(e);
-        for (auto &e : w->ev) if (e) cudaEventDestroy(e);
-        w->h_words.release(); w->h_descs.release(); w->h_results.release();
-        w->d_words.release(); w->d_descs.release(); w->d_results.release();
-        w->d_scratch[0].release(); w->d_scratch[1].release();
-    }
-    ix->d_table.release(); ix->d_arena.release(); ix->d_qnodes.release(); ix->d_qchild.release(); ix->d_qid.release();
-    ix->d_terms.release(); ix->d_qinfo.release(); ix->d_lca.release();
-    delete ix;
-}
+void cls_index_destroy(cls_index *ix) { delete ix; }
 
 int cls_index_get_info(const cls_index *ix, cls_index_info *info) {
     if (!ix || !info) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -756,13 +766,7 @@ int cls_resident_fetch(cls_index *ix, cls_resident_batch *rb, void *stream, cls_
     return CLS_OK;
 }
 
-void cls_resident_destroy(cls_resident_batch *rb) {
-    if (!rb) return;
-    cudaSetDevice(rb->device);
-    rb->d_words.release(); rb->d_descs.release(); rb->d_results.release(); rb->h_results.release();
-    rb->d_win_base.release(); rb->d_route_state.release(); rb->d_runs.release(); rb->d_scratch.release();
-    delete rb;
-}
+void cls_resident_destroy(cls_resident_batch *rb) { delete rb; }
 
 uint64_t cls_resident_bytes(const cls_resident_batch *rb) {
     if (!rb) return 0;

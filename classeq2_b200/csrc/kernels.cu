@@ -1188,6 +1188,11 @@ PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout) {
     return g;
 }
 
+// CLS_NO_SPLIT=1 (A/B experiments): every read is finished by the warp / CTA that built its histogram.
+static bool split_disabled() {
+    static const bool off = getenv("CLS_NO_SPLIT") != nullptr;
+    return off;
+}
 static inline size_t scratch_bytes_for(uint32_t n_reads, uint32_t cap) { return (size_t)n_reads * ((size_t)cap * 8 + 8) + 256; }
 static inline ScanOut carve_scratch(void *scratch, uint32_t n_reads, uint32_t cap) {
     char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
@@ -1241,7 +1246,7 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
     if (grid == 0) return cudaSuccess;
     // kb-scale reads of closed models: the histogram goes to the wide descent kernel when the caller gave scratch
     const bool split = CTA && CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCapWide) &&
-                       (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024 && getenv("CLS_NO_SPLIT") == nullptr;
+                       (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024 && !split_disabled();
     ScanOut so{nullptr, nullptr, 0};
     if (split) so = carve_scratch(scratch, n_reads, kPairCapWide);
     place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so, trace);
@@ -1265,8 +1270,7 @@ static cudaError_t launch_place_m(const DeviceIndex &ix, const PlaceParams &pp, 
 
 // ---- short reads, k = 35: scan kernel (+ descent kernel when the caller provides the hand-over scratch) ----
 size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k) {
-    static const bool off = getenv("CLS_NO_SPLIT") != nullptr;
-    if (off || max_len < k || n_reads == 0) return 0;
+    if (split_disabled() || max_len < k || n_reads == 0) return 0;
     const PlaceGeom g = make_place_geom(max_len, k, 1);
     if (g.cta_per_read) return scratch_bytes_for(n_reads, kPairCapWide);
     return k == 35 ? scratch_bytes_for(n_reads, kPairCap) : 0;
@@ -1283,7 +1287,7 @@ static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, c
     static const size_t pad = [] { const char *e = getenv("CLS_SCAN_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
     const size_t smem = (group + ring) * warps + pad;
     if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
-    const bool split = CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && getenv("CLS_NO_SPLIT") == nullptr &&
+    const bool split = CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && !split_disabled() &&
                        (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
     auto kern = split ? scan_kernel<CLOSED, true> : scan_kernel<CLOSED, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);

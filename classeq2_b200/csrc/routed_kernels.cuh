@@ -324,7 +324,7 @@ cudaError_t launch_place_routed(const DeviceIndex &ix, const PlaceParams &pp, co
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
     const ProbeReply *rp = reinterpret_cast<const ProbeReply *>(replies);
-    const bool split = ix.closed && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && getenv("CLS_NO_SPLIT") == nullptr &&
+    const bool split = ix.closed && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && !split_disabled() &&
                        (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
     ScanOut so{nullptr, nullptr, 0};
     if (split) so = carve_scratch(scratch, n_reads, kPairCap);
