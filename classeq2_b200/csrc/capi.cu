@@ -502,6 +502,8 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
     if (rc != CLS_OK) return rc;
     cls_timing tm{};
     tm.pack_ms = now_ms() - t0;  // planning counts as packing
+    static const bool dbg = getenv("CLS_DEBUG_TIMING") != nullptr;
+    if (dbg) fprintf(stderr, "[place_batch] plan %.2f ms\n", tm.pack_ms);
     const size_t words_b = (size_t)lay.n_words * 4, descs_b = (size_t)lay.n_device * sizeof(ReadDesc),
                  res_b = (size_t)lay.n_device * sizeof(ResultRec);
     PlaceParams pp = make_place_params(params);
@@ -509,7 +511,6 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
         CU_TRY(w->h_words.reserve(words_b + 16)); CU_TRY(w->h_descs.reserve(descs_b)); CU_TRY(w->h_results.reserve(res_b));
         CU_TRY(w->d_words.reserve(words_b + 16)); CU_TRY(w->d_descs.reserve(descs_b)); CU_TRY(w->d_results.reserve(res_b));
     }
-    scatter_host_decided(lay, ix->dix.k_size, result);
     // Chunks of every length class go through pack (host threads) -> H2D -> kernel -> D2H on two
     // alternating streams: chunk c+1 is packed and copied while chunk c is on the SMs, and the
     // results of finished chunks are scattered to the caller's arrays while later chunks run.
@@ -574,8 +575,14 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
         CU_TRY(cudaEventRecord(ev[3], st));
         if (ci >= 2) { rc = drain(ci - 1); if (rc != CLS_OK) return rc; }  // chunks older than the two in flight
     }
+    // fields decided on the host (n_query_kmers of every query; queries that never reach the device): written
+    // while the last chunks are still on the device
+    const double th = now_ms();
+    scatter_host_decided(lay, ix->dix.k_size, result);
+    if (dbg) fprintf(stderr, "[place_batch] enqueue done at %.2f ms, host-decided fields %.2f ms\n", th - t0, now_ms() - th);
     rc = drain(chunks.size());
     if (rc != CLS_OK) return rc;
+    if (dbg) fprintf(stderr, "[place_batch] drained at %.2f ms\n", now_ms() - t0);
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         float ms = 0;
         cudaEvent_t *ev = &w->chunk_ev[4 * ci];
