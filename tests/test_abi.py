@@ -38,6 +38,7 @@ def test_struct_layouts_match_header():
     from classeq2_b200 import _lib
     assert C.sizeof(_lib.ModelView) == 16 + 8 + 4 * 8 + 8 + 3 * 8 + 8 + 2 * 8
     assert C.sizeof(_lib.Batch) == 24 and C.sizeof(_lib.Params) == 16 and C.sizeof(_lib.Result) == 64
+    assert C.sizeof(_lib.LevelCount) == 32 and C.sizeof(_lib.FastaRecords) == 32   # cls_level_count, cls_fasta_records
     p = _lib.Params()
     _lib.lib.cls_params_default(C.byref(p))
     assert (p.max_iterations, p.remove_intersection, p.min_match_coverage) == (1000, 0, 0.7)  # place_sequence.rs:64-75
@@ -96,6 +97,22 @@ def test_compute_fails_loudly_without_gpu(col_flat):
     assert ei.value.code == _lib.CLS_ERR_CUDA
     with pytest.raises(_lib.ClsError):
         cq.debug_kmer_hashes("ACGT" * 20, 35)
+    # the sharded-index and peer-buffer entry points as well: no device, no answer
+    with pytest.raises(_lib.ClsError) as ei:
+        cq.Index(col_flat, device=0, shard=1, n_shards=2)
+    assert ei.value.code == _lib.CLS_ERR_CUDA
+    ptr, h = C.c_void_p(), (C.c_uint8 * 64)()
+    assert _lib.lib.cls_peer_alloc(0, 1 << 20, C.byref(ptr), h) == _lib.CLS_ERR_CUDA
+    assert _lib.lib.cls_peer_open(0, h, C.byref(ptr)) == _lib.CLS_ERR_CUDA
+
+
+def test_shard_arguments_are_checked_on_the_host(col_flat):
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    for shard, n in ((2, 2), (0, 0), (0, 9)):
+        with pytest.raises(_lib.ClsError) as ei:
+            cq.Index(col_flat, device=0, shard=shard, n_shards=n)
+        assert ei.value.code == _lib.CLS_ERR_INVALID_ARGUMENT
 
 
 def test_index_create_rejects_unsupported_models(col_npz):
