@@ -150,7 +150,7 @@ struct cls_resident_batch {
     PackedLayout lay;
     DevBuf d_words, d_descs, d_results;
     DevBuf d_scratch;  // scan -> descent hand-over (one placement of this batch in flight at a time)
-    DevBuf d_win_base, d_route_state, d_runs;  // routed path: first window of every read; per-owner cursors + overflow flag; run table
+    DevBuf d_route_state, d_runs;  // routed path: per-owner cursors + overflow flag; the run of every read in every owner's segment
     std::vector<uint64_t> fa_header_begin, fa_header_end;  // cls_fasta_upload: the records the reader sent
     std::vector<uint32_t> fa_length;
     uint64_t n_windows = 0;
@@ -161,7 +161,7 @@ struct cls_resident_batch {
     ~cls_resident_batch() {   // also runs on the error paths of the upload calls: nothing is leaked
         cudaSetDevice(device);
         d_words.release(); d_descs.release(); d_results.release(); d_scratch.release();
-        d_win_base.release(); d_route_state.release(); d_runs.release(); h_results.release();
+        d_route_state.release(); d_runs.release(); h_results.release();
     }
 };
 
@@ -784,18 +784,11 @@ uint64_t cls_resident_bytes(const cls_resident_batch *rb) {
 int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_windows) {
     if (!ix || !rb || !n_windows) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     CU_TRY(cudaSetDevice(ix->device));
-    if (!rb->d_win_base.p) {
+    if (!rb->d_runs.p) {
         const PackedLayout &lay = rb->lay;
         const uint32_t k = ix->dix.k_size;
-        std::vector<uint64_t> base((size_t)lay.n_device + 1);
         uint64_t acc = 0;
-        for (uint32_t j = 0; j < lay.n_device; ++j) {
-            base[j] = acc;
-            acc += 2ull * (lay.lens[lay.perm[j]] - k + 1);
-        }
-        base[lay.n_device] = acc;
-        CU_TRY(rb->d_win_base.reserve(base.size() * 8));
-        CU_TRY(cudaMemcpy(rb->d_win_base.p, base.data(), base.size() * 8, cudaMemcpyHostToDevice));
+        for (uint32_t j = 0; j < lay.n_device; ++j) acc += 2ull * (lay.lens[lay.perm[j]] - k + 1);
         CU_TRY(rb->d_route_state.reserve(256));
         CU_TRY(rb->d_runs.reserve((size_t)lay.n_device * 8 * sizeof(uint2) + 64));
         rb->n_windows = acc;
@@ -817,7 +810,7 @@ static int route_hashes_impl(cls_index *ix, cls_resident_batch *rb, uint32_t n_s
     for (const LengthClass &c : rb->lay.classes) {
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         cudaError_t e = launch_route(ix->dix.k_size, (const uint32_t *)rb->d_words.p, (const ReadDesc *)rb->d_descs.p, c.first, c.count, g,
-                                     (const uint64_t *)rb->d_win_base.p, n_shards, seg_cap, seg_ptrs, (uint16_t *)d_slot_win,
+                                     n_shards, seg_cap, seg_ptrs, (uint16_t *)d_slot_win,
                                      (uint2 *)rb->d_runs.p, cursor, overflow, ix->sm_count, st);
         if (e == cudaErrorInvalidConfiguration)
             return fail(CLS_ERR_UNSUPPORTED, "the routed path places reads of up to 161 bases (the one-warp-per-read geometry)");
@@ -905,7 +898,7 @@ int cls_place_routed(cls_index *ix, cls_resident_batch *rb, const void *d_replie
                      uint32_t n_shards, uint64_t seg_cap, const cls_params *params, void *stream) {
     if (!ix || !rb || !params || !d_replies || !d_slot_win) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
-    if (!rb->d_win_base.p) return fail(CLS_ERR_INVALID_ARGUMENT, "cls_route_hashes has not run on this batch");
+    if (!rb->d_runs.p) return fail(CLS_ERR_INVALID_ARGUMENT, "cls_route_hashes has not run on this batch");
     CU_TRY(cudaSetDevice(ix->device));
     const PlaceParams pp = make_place_params(params);
     size_t want = 0;

@@ -63,7 +63,7 @@ cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uin
 constexpr uint32_t kMaxShards = 8;
 constexpr uint32_t kProbeReplyBytes = 12;
 cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
-                         const PlaceGeom &g, const uint64_t *win_base, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
+                         const PlaceGeom &g, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
                          uint16_t *slot_win, uint2 *runs, unsigned long long *cursor, uint32_t *overflow, int sm_count, cudaStream_t stream);
 cudaError_t launch_shard_probe(const DeviceIndex &ix, uint32_t shard, const uint64_t *hashes, uint64_t n, void *replies,
                                cudaStream_t stream);

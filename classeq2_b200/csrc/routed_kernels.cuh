@@ -63,7 +63,7 @@ struct SegPtrs {
 template <int K>
 __global__ void __launch_bounds__(256, 4) route_kernel(uint32_t k, const uint32_t *__restrict__ packed,
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
-                                                       uint32_t n_reads, PlaceGeom g, const uint64_t *__restrict__ win_base,
+                                                       uint32_t n_reads, PlaceGeom g,
                                                        uint32_t n_shards, uint64_t seg_cap, SegPtrs seg,
                                                        uint16_t *__restrict__ slot_win, uint2 *__restrict__ runs,
                                                        unsigned long long *__restrict__ cursor, uint32_t *__restrict__ overflow) {
@@ -276,7 +276,7 @@ static inline cudaError_t routed_smem(const PlaceGeom &g, int &warps, size_t &sm
 }
 
 cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
-                         const PlaceGeom &g, const uint64_t *win_base, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
+                         const PlaceGeom &g, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
                          uint16_t *slot_win, uint2 *runs, unsigned long long *cursor, uint32_t *overflow, int sm_count, cudaStream_t stream) {
     SegPtrs seg{};
     for (uint32_t o = 0; o < n_shards && o < 8; ++o) seg.p[o] = seg_ptrs[o];
@@ -291,11 +291,11 @@ cudaError_t launch_route(uint32_t k, const uint32_t *packed, const ReadDesc *rea
     if (grid > need) grid = need;
     if (k == 35) {
         if ((e = cudaFuncSetAttribute(route_kernel<35>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
-        route_kernel<35><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, seg,
+        route_kernel<35><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, n_shards, seg_cap, seg,
                                                              slot_win, runs, cursor, overflow);
     } else {
         if ((e = cudaFuncSetAttribute(route_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
-        route_kernel<0><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, win_base, n_shards, seg_cap, seg,
+        route_kernel<0><<<grid, warps * 32, smem, stream>>>(k, packed, reads, first_read, n_reads, g, n_shards, seg_cap, seg,
                                                             slot_win, runs, cursor, overflow);
     }
     return cudaGetLastError();

@@ -213,9 +213,9 @@ class ShardedPlacer:
         world = self.world
         seg_cap = (int(nw / world * self.slack) + 65536 + 3) & ~3   # multiple of 4: reply segments stay 16-byte aligned
         buf = self._buffers(nw, seg_cap, dev)
-        send, win_slot, rep_in = buf["send"], buf["win_slot"], buf["rep_in"]
+        send, slot_win, rep_in = buf["send"], buf["slot_win"], buf["rep_in"]
         ev[0].record(st)
-        counts_to = rb.route_hashes(world, seg_cap, send.data_ptr(), win_slot.data_ptr(), st.cuda_stream).astype(np.int64)
+        counts_to = rb.route_hashes(world, seg_cap, send.data_ptr(), slot_win.data_ptr(), st.cuda_stream).astype(np.int64)
         ev[1].record(st)
         counts_from = exchange_plan(counts_to, self.group) if world > 1 else counts_to.copy()
         n_recv = int(counts_from.sum())
@@ -240,7 +240,7 @@ class ShardedPlacer:
         else:
             back_recv[0].copy_(back_send[0])
         ev[4].record(st)
-        rb.place_routed(rep_in.data_ptr(), win_slot.data_ptr(), world, seg_cap, params, st.cuda_stream)
+        rb.place_routed(rep_in.data_ptr(), slot_win.data_ptr(), world, seg_cap, params, st.cuda_stream)
         ev[5].record(st)
         self._events = ev
         self._stage_names = ["route_ms", "send_ms", "probe_ms", "reply_ms", "place_ms"]
@@ -263,13 +263,13 @@ class ShardedPlacer:
         seg_cap = pb.seg_cap
         b = getattr(self, "_buf", None)
         if b is None:
-            b = dict(win_slot=torch.empty(world * seg_cap, dtype=torch.int16, device=dev),
+            b = dict(slot_win=torch.empty(world * seg_cap, dtype=torch.int16, device=dev),
                      token=torch.zeros(1, dtype=torch.int32, device=dev))
             self._buf = b
         ev[0].record(st)
         # stage 1+2+3: hash, group by owner, and store into the owners' inboxes (my segment of each)
         seg_ptrs = [pb.inbox[o] + me * seg_cap * 8 for o in range(world)]
-        counts_to = rb.route_hashes_p2p(world, seg_cap, seg_ptrs, b["win_slot"].data_ptr(), st.cuda_stream).astype(np.int64)
+        counts_to = rb.route_hashes_p2p(world, seg_cap, seg_ptrs, b["slot_win"].data_ptr(), st.cuda_stream).astype(np.int64)
         ev[1].record(st)
         # the counts all-to-all doubles as "every rank's route kernel has completed": my inbox is whole
         counts_from = exchange_plan(counts_to, self.group) if world > 1 else counts_to.copy()
@@ -281,7 +281,7 @@ class ShardedPlacer:
         if world > 1:
             dist.all_reduce(b["token"], group=self.group)  # barrier on the stream: every probe kernel has completed
         ev[3].record(st)
-        rb.place_routed(pb.reply[me], b["win_slot"].data_ptr(), world, seg_cap, params, st.cuda_stream)
+        rb.place_routed(pb.reply[me], b["slot_win"].data_ptr(), world, seg_cap, params, st.cuda_stream)
         ev[4].record(st)
         self._events = ev
         self._stage_names = ["route_ms", "counts_ms", "probe_ms", "place_ms"]
@@ -297,7 +297,7 @@ class ShardedPlacer:
         if b is None or b["seg_cap"] != seg_cap:
             b = dict(seg_cap=seg_cap,
                      send=torch.empty(self.world * seg_cap, dtype=torch.int64, device=dev),
-                     win_slot=torch.empty(self.world * seg_cap, dtype=torch.int16, device=dev),
+                     slot_win=torch.empty(self.world * seg_cap, dtype=torch.int16, device=dev),
                      rep_in=torch.empty(self.world * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev),
                      recv=torch.empty(1, dtype=torch.int64, device=dev),
                      rep_out=torch.empty(REPLY_BYTES, dtype=torch.uint8, device=dev))
@@ -342,14 +342,14 @@ class LocalShardedPlacer:
         nw = rb.routed_windows()
         seg_cap = (int(nw / self.n_shards * self.slack) + 65536 + 3) & ~3
         send = torch.empty(self.n_shards * seg_cap, dtype=torch.int64, device=dev)
-        win_slot = torch.empty(self.n_shards * seg_cap, dtype=torch.int16, device=dev)
-        counts = rb.route_hashes(self.n_shards, seg_cap, send.data_ptr(), win_slot.data_ptr(), st.cuda_stream)
+        slot_win = torch.empty(self.n_shards * seg_cap, dtype=torch.int16, device=dev)
+        counts = rb.route_hashes(self.n_shards, seg_cap, send.data_ptr(), slot_win.data_ptr(), st.cuda_stream)
         assert int(counts.sum()) == nw
         rep = torch.empty(self.n_shards * seg_cap * REPLY_BYTES, dtype=torch.uint8, device=dev)
         for o, ix in enumerate(self.shards):
             ix.shard_probe(send.data_ptr() + o * seg_cap * 8, int(counts[o]), rep.data_ptr() + o * seg_cap * REPLY_BYTES,
                            st.cuda_stream)
-        rb.place_routed(rep.data_ptr(), win_slot.data_ptr(), self.n_shards, seg_cap, params, st.cuda_stream)
+        rb.place_routed(rep.data_ptr(), slot_win.data_ptr(), self.n_shards, seg_cap, params, st.cuda_stream)
         res = rb.fetch(st.cuda_stream)
         self.last_counts, self.last_send = counts, (send, seg_cap)
         rb.close()
