@@ -9,8 +9,8 @@ from .engine import (BatchResult, Index, PlaceParams, ResidentBatch, debug_kmer_
                      filter_sequence, host_murmur3_h1, make_batch)
 from .model import BuiltModel, Clade, FlatModel, KmersMap, Tree  # noqa: F401
 from .placement import (PlacementTime, load_annotations, load_database, place_sequences,  # noqa: F401
-                              read_fasta)
+                        read_fasta, save_database)
 
 __all__ = ["Index", "ResidentBatch", "PlaceParams", "BatchResult", "Clade", "KmersMap", "Tree",
            "FlatModel", "BuiltModel", "debug_kmer_hashes", "host_murmur3_h1", "filter_sequence", "make_batch", "place_sequences", "load_database",
-           "load_annotations", "read_fasta", "PlacementTime"]
+           "save_database", "load_annotations", "read_fasta", "PlacementTime"]

@@ -178,6 +178,23 @@ class FlatModel:
     def n_entries(self) -> int:
         return len(self.entry_hash)
 
+    # ---- flat binary cache: upload without parsing the YAML again ------------------
+    _ARRAYS = ("node_id", "node_kind", "child_off", "child_idx", "entry_bucket", "entry_hash", "entry_set", "set_off",
+               "set_node_ids")
+
+    def save(self, path) -> None:
+        """The arrays of the ``cls_model_view`` as one uncompressed ``.npz`` (the YAML of a 10 k-tip model is GBs;
+        these arrays are what ``cls_index_create`` consumes directly)."""
+        np.savez(path, k_size=np.uint32(self.k_size), m_size=np.uint32(self.m_size),
+                 root_children_none=np.uint8(self.root_children_none), force_general_sets=np.uint8(self.force_general_sets),
+                 **{n: getattr(self, n) for n in self._ARRAYS})
+
+    @staticmethod
+    def load(path) -> "FlatModel":
+        z = np.load(path)
+        return FlatModel(int(z["k_size"]), int(z["m_size"]), *[z[n] for n in FlatModel._ARRAYS],
+                         root_children_none=bool(z["root_children_none"]), force_general_sets=bool(z["force_general_sets"]))
+
     def with_general_sets(self) -> "FlatModel":
         """The same model, forced onto the general mini-tree node-set records (testing knob)."""
         return FlatModel(self.k_size, self.m_size, self.node_id, self.node_kind, self.child_off, self.child_idx,

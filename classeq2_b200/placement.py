@@ -443,6 +443,39 @@ def load_database(path: Union[str, os.PathLike]) -> Tree:
     return Tree.from_obj(obj)
 
 
+def _zstd_compress(data: bytes, level: int = 0) -> bytes:
+    name = ctypes.util.find_library("zstd") or "libzstd.so.1"
+    z = C.CDLL(name)
+    z.ZSTD_compressBound.restype = C.c_size_t
+    z.ZSTD_compressBound.argtypes = [C.c_size_t]
+    z.ZSTD_compress.restype = C.c_size_t
+    z.ZSTD_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+    z.ZSTD_isError.restype = C.c_uint
+    z.ZSTD_isError.argtypes = [C.c_size_t]
+    cap = z.ZSTD_compressBound(len(data))
+    buf = C.create_string_buffer(cap)
+    n = z.ZSTD_compress(buf, cap, data, len(data), level)
+    if z.ZSTD_isError(n):
+        raise OSError("ZSTD_compress failed")
+    return buf.raw[:n]
+
+
+def save_database(tree: Tree, path: Union[str, os.PathLike], compress: bool = True) -> str:
+    """What ``build-db`` writes (ports/cli/src/cmds/build_db.rs:67-75): the serde_yaml text of the ``Tree`` inside a
+    zstd frame (level 0), extension forced to ``.cls``; ``compress=False`` writes the plain YAML under the given name.
+    Returns the path written.  ``load_database`` reads both back."""
+    text = yaml_dump(tree.to_obj()).encode("utf-8")
+    if compress:
+        root, _ = os.path.splitext(os.fspath(path))     # PathBuf::set_extension("cls")
+        out = root + ".cls"
+        data = _zstd_compress(text, 0)
+    else:
+        out, data = os.fspath(path), text
+    with open(out, "wb") as f:
+        f.write(data)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # place_sequences (mod.rs:43-270)
 # --------------------------------------------------------------------------------------------------

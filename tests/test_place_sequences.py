@@ -183,3 +183,42 @@ def test_place_sequences_device_ingest_writes_the_same_files(ps, tmp_path, col_t
     assert [t.sequence for t in ta] == [t.sequence for t in tb] and len(ta) > 300
     assert a.read_bytes() == b.read_bytes() and len(a.read_bytes()) > 10000
     assert (tmp_path / "host" / "r.error").read_bytes() == (tmp_path / "dev" / "r.error").read_bytes()
+
+
+def test_save_database_round_trip_and_shape(ps, tmp_path, col_tree):
+    """build-db's output side (build_db.rs:67-75): serde_yaml text in a zstd frame, extension forced to .cls;
+    load_database reads it back; the text has the documented shape (docs/book/02-build-db.md:139-197)."""
+    import classeq2_b200 as cq
+    obj = col_tree.to_obj()
+    obj["kmersMap"]["map"] = {k: v for k, v in list(obj["kmersMap"]["map"].items())[:4]}
+    tree = cq.Tree.from_obj(obj)
+    try:
+        out = cq.save_database(tree, tmp_path / "db.anything")
+    except OSError:
+        pytest.skip("libzstd not available")
+    assert out.endswith("db.cls") and open(out, "rb").read(4) == b"\x28\xb5\x2f\xfd"      # zstd magic
+    back = cq.load_database(out)
+    assert back.to_obj() == tree.to_obj()
+    plain = cq.save_database(tree, tmp_path / "db.yaml", compress=False)
+    text = open(plain).read()
+    assert cq.load_database(plain).to_obj() == tree.to_obj()
+    lines = text.splitlines()
+    assert lines[0].startswith("id: ") and any(ln == "kmersMap:" for ln in lines) and "  kSize: 35" in lines and "  mSize: 4" in lines
+    assert "root:" in lines and "  kind: ROOT" in lines and "  children:" in lines and "  - id: 1" in lines
+    key = next(iter(obj["kmersMap"]["map"]))
+    assert f"    {key}:" in lines                  # u64 bucket keys are plain integers, hashes nest below them
+
+
+def test_flat_model_cache_round_trip(tmp_path, col_flat):
+    """The flat binary cache of a model: same arrays back, hence the same cls_model_view."""
+    import classeq2_b200 as cq
+    p = tmp_path / "model.npz"
+    col_flat.save(p)
+    back = cq.FlatModel.load(p)
+    for n in cq.FlatModel._ARRAYS:
+        assert (getattr(back, n) == getattr(col_flat, n)).all() and getattr(back, n).dtype == getattr(col_flat, n).dtype
+    assert (back.k_size, back.m_size, back.view.n_entries, back.view.n_sets, back.view.flags) == \
+           (col_flat.k_size, col_flat.m_size, col_flat.view.n_entries, col_flat.view.n_sets, col_flat.view.flags)
+    g = col_flat.with_general_sets()
+    g.save(p)
+    assert cq.FlatModel.load(p).view.flags == g.view.flags != col_flat.view.flags
