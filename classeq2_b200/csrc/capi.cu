@@ -624,7 +624,7 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
     if (!ix || !out || !records || (n_bytes && !text)) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = nullptr;
     std::memset(records, 0, sizeof *records);
-    if (n_bytes >= (1ull << 40)) return fail(CLS_ERR_UNSUPPORTED, "FASTA text beyond 2^40 bytes: split it");
+    if (n_bytes >= (1ull << 32)) return fail(CLS_ERR_UNSUPPORTED, "FASTA text of 4 GiB or more: split it (the tile summaries count in 32 bits)");
     CU_TRY(cudaSetDevice(ix->device));
     static const bool dbg = getenv("CLS_DEBUG_TIMING") != nullptr;
     double tlast = now_ms();
