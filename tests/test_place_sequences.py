@@ -222,3 +222,37 @@ def test_flat_model_cache_round_trip(tmp_path, col_flat):
     g = col_flat.with_general_sets()
     g.save(p)
     assert cq.FlatModel.load(p).view.flags == g.view.flags != col_flat.view.flags
+
+
+def test_build_database_mirror_equals_oracle(tmp_path, oracle, col_queries, col_tree):
+    """map_kmers_to_tree (build_database/mod.rs:26-181, tree.rs:164-364) on the reference's own newick + tip
+    sequences: same sanitized tree (ids, kinds, supports, lengths), same tree id, same k-mer map as the oracle's
+    restatement; the result goes through save_database / load_database unchanged."""
+    import shutil
+    import classeq2_b200 as cq
+    from classeq2_b200 import build
+    nwk = "Colletotrichum_acutatum_gapdh-PhyML.nwk"
+    shutil.copy(os.path.join(GOLDEN, nwk), tmp_path / nwk)
+    tips = col_queries[:171]
+    msa = tmp_path / "tips.fasta"
+    msa.write_text("".join(f">{h}\n{s}\n" for h, s in tips))
+    tree = build.map_kmers_to_tree(tmp_path / nwk, msa)
+    want = oracle.tree_from_newick(open(os.path.join(GOLDEN, nwk)).read(), nwk, 70.0)
+    oracle.map_kmers_to_tree(want, tips, 35, 4)
+    assert (tree.id, tree.name, tree.min_branch_support) == (want.id, want.name, want.min_branch_support)
+    assert tree.root.to_obj() == want.root.to_obj() == col_tree.root.to_obj()
+    assert tree.kmers_map.k_size == 35 and tree.kmers_map.m_size == 4
+    assert {k: {h: set(n) for h, n in v.items()} for k, v in tree.kmers_map.map.items()} == \
+           {k: {h: set(n) for h, n in v.items()} for k, v in want.kmers_map.map.items()}
+    for thr in (0.0, 95.0, 101.0):      # other collapse thresholds; a caterpillar deeper than the recursion limit
+        a = build.tree_from_newick(open(os.path.join(GOLDEN, nwk)).read(), nwk, thr)
+        b = oracle.tree_from_newick(open(os.path.join(GOLDEN, nwk)).read(), nwk, thr)
+        assert a.root.to_obj() == b.root.to_obj()
+    deep = "(" * 3000 + "t0:1" + "".join(f",t{i + 1}:1)90:0.5" for i in range(3000)) + ";"
+    t = build.tree_from_newick(deep, "deep.nwk", 70.0)
+    assert sum(1 for c in t.root.walk() if c.is_leaf()) == 3001
+    try:
+        out = cq.save_database(tree, tmp_path / "db")
+    except OSError:
+        pytest.skip("libzstd not available")
+    assert cq.load_database(out).to_obj() == tree.to_obj()
