@@ -1205,10 +1205,16 @@ static inline ScanOut carve_scratch(void *scratch, uint32_t n_reads, uint32_t ca
 template <int MAXSLOTS>
 static cudaError_t launch_descend(const DeviceIndex &ix, const PlaceParams &pp, const ScanOut &so, uint32_t first_read,
                                   uint32_t n_reads, ResultRec *results, uint32_t fan_cap, int sm_count, cudaStream_t stream) {
-    uint32_t dgrid = (uint32_t)(sm_count * 8);
+    // persistent CTAs: exactly as many as are resident at once (a larger grid would run a second, mostly empty wave)
+    const size_t dsmem = (size_t)2 * fan_cap * 4 * 8;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, descend_kernel<MAXSLOTS>, 256, dsmem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    uint32_t dgrid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + 7) / 8;
     if (dgrid > need) dgrid = need;
-    descend_kernel<MAXSLOTS><<<dgrid, 256, (size_t)2 * fan_cap * 4 * 8, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
+    descend_kernel<MAXSLOTS><<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
     return cudaGetLastError();
 }
 
