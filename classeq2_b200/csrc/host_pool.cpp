@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
+#include <cstdlib>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -10,9 +11,19 @@
 namespace cls {
 
 int host_threads() {
+    // CLS_HOST_THREADS overrides; under torchrun (one process per GPU) the cores are shared between the
+    // LOCAL_WORLD_SIZE ranks of the box instead of being oversubscribed by every rank
     static const int n = [] {
+        if (const char *e = std::getenv("CLS_HOST_THREADS")) {
+            const int v = std::atoi(e);
+            if (v >= 1) return std::min(v, 64);
+        }
         unsigned hc = std::thread::hardware_concurrency();
         if (hc == 0) hc = 4;
+        if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
+            const int w = std::atoi(e);
+            if (w > 1) hc = std::max(1u, hc / (unsigned)w);
+        }
         return (int)std::min(hc, 32u);
     }();
     return n;
