@@ -11,8 +11,8 @@
 namespace cls {
 
 int host_threads() {
-    // CLS_HOST_THREADS overrides; under torchrun (one process per GPU) the cores are shared between the
-    // LOCAL_WORLD_SIZE ranks of the box instead of being oversubscribed by every rank
+    // CLS_HOST_THREADS overrides the default (all cores, at most 32).  Under torchrun every rank keeps the full
+    // pool: the ranks pack at different times, and a static split of the cores measured no better
     static const int n = [] {
         if (const char *e = std::getenv("CLS_HOST_THREADS")) {
             const int v = std::atoi(e);
@@ -20,10 +20,6 @@ int host_threads() {
         }
         unsigned hc = std::thread::hardware_concurrency();
         if (hc == 0) hc = 4;
-        if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
-            const int w = std::atoi(e);
-            if (w > 1) hc = std::max(1u, hc / (unsigned)w);
-        }
         return (int)std::min(hc, 32u);
     }();
     return n;
