@@ -12,7 +12,7 @@ namespace cls {
 
 int host_threads() {
     // CLS_HOST_THREADS overrides the default (all cores, at most 32).  Under torchrun every rank keeps the full
-    // pool: the ranks pack at different times, and a static split of the cores measured no better
+    // pool: the ranks pack at different times, and a static split would idle cores while a rank waits for its GPU
     static const int n = [] {
         if (const char *e = std::getenv("CLS_HOST_THREADS")) {
             const int v = std::atoi(e);
