@@ -121,6 +121,7 @@ PROTOTYPES = {
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),
     "cls_filter_sequence": (C.c_uint64, [u8p, C.c_uint64, u8p, C.c_uint64]),
     "cls_model_build": (C.c_int, [C.POINTER(ModelView), C.c_uint64, u64p, u8p, u64p, C.POINTER(C.c_void_p)]),
+    "cls_model_build_device": (C.c_int, [C.POINTER(ModelView), C.c_uint64, u64p, u8p, u64p, C.c_int, C.POINTER(C.c_void_p)]),
     "cls_built_model_view": (C.c_int, [C.c_void_p, C.POINTER(ModelView), C.POINTER(ModelView)]),
     "cls_built_model_destroy": (None, [C.c_void_p]),
 }

@@ -3,10 +3,10 @@
 
 Reference: ``map_kmers_to_tree`` (core/src/use_cases/build_database/mod.rs:26-181), ``Tree::init_from_file``
 and ``sanitize`` (core/src/domain/dtos/tree.rs:164-364).  Offline, once per model - not part of the placement
-hot path; the k-mer -> node-set map itself is built by the library's multi-threaded
-host builder ``cls_model_build``.  One deliberate difference, as in ``cls_model_build``: every tip is indexed with
-ITS OWN sequence (the reference pairs header i with sequence i-1 and drops the last record,
-build_database/mod.rs:93-116).
+hot path; the k-mer -> node-set map itself is built by the library: on the host
+(``cls_model_build``) or, with ``device=``, on the GPU (``cls_model_build_device``).  One deliberate difference,
+in both builders: every tip is indexed with ITS OWN sequence (the reference pairs header i with sequence i-1
+and drops the last record, build_database/mod.rs:93-116).
 """
 from __future__ import annotations
 
@@ -127,9 +127,11 @@ def tree_from_newick(newick: str, file_name: str, min_branch_support: float) -> 
 
 def map_kmers_to_tree(tree_path: Union[str, os.PathLike], msa_path: Union[str, os.PathLike],
                       k_size: Optional[int] = None, m_size: Optional[int] = None,
-                      min_branch_support: Optional[float] = None) -> Tree:
+                      min_branch_support: Optional[float] = None, device: Optional[int] = None) -> Tree:
     """Same arguments and defaults as the reference (build_database/mod.rs:26-44: k = 35, m = 4, support >= 70).
-    Sequences whose header names no tip of the tree are ignored; tips without a sequence get no k-mers."""
+    Sequences whose header names no tip of the tree are ignored; tips without a sequence get no k-mers.
+    ``device``: build the k-mer map on that GPU (``cls_model_build_device``) instead of the host builder; the
+    result is the same map."""
     k_size = 35 if k_size is None else int(k_size)
     m_size = 4 if m_size is None else int(m_size)
     min_branch_support = 70.0 if min_branch_support is None else float(min_branch_support)
@@ -155,7 +157,7 @@ def map_kmers_to_tree(tree_path: Union[str, os.PathLike], msa_path: Union[str, o
         offsets[1:] = np.cumsum([len(s) for s in seqs])
     bases = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy() if seqs else np.zeros(1, np.uint8)
     tree_only = FlatModel(k_size, m_size, node_id, node_kind, child_off, child_idx)
-    bm = BuiltModel(tree_only, np.array(tip_node, dtype=np.uint64), bases, offsets)
+    bm = BuiltModel(tree_only, np.array(tip_node, dtype=np.uint64), bases, offsets, device=device)
     a = bm.arrays()
     bm.close()
     km = KmersMap(k_size, m_size)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/classeq_b200.h"
+#include "built_model.hpp"
 #include "murmur3_host.hpp"
 
 namespace {
@@ -24,11 +25,6 @@ struct Occ {
 inline uint64_t mix64(uint64_t x) { return cls::fmix64_h(x + 0x9e3779b97f4a7c15ULL); }
 
 }  // namespace
-
-struct cls_built_model {
-    uint32_t k_size = 0, m_size = 0;
-    std::vector<uint64_t> entry_bucket, entry_hash, entry_set, set_off, set_node_ids;
-};
 
 extern "C" {
 

@@ -247,16 +247,23 @@ class FlatModel:
 
 
 class BuiltModel:
-    """``cls_model_build``: k-mer map for one sequence per tip (host side, no GPU)."""
+    """k-mer map for one sequence per tip: ``cls_model_build`` (host side, no GPU) or, with ``device`` given,
+    ``cls_model_build_device`` (the same map built on that GPU; no CPU fallback)."""
 
-    def __init__(self, tree_only: FlatModel, tip_node: np.ndarray, bases: np.ndarray, offsets: np.ndarray):
+    def __init__(self, tree_only: FlatModel, tip_node: np.ndarray, bases: np.ndarray, offsets: np.ndarray,
+                 device: Optional[int] = None):
         self.tree_only = tree_only
         tip_node = np.ascontiguousarray(tip_node, dtype=np.uint64)
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         self._h = C.c_void_p()
-        _lib.check(_lib.lib.cls_model_build(C.byref(tree_only.view), len(tip_node), _ptr(tip_node, _lib.u64p),
-                                            _ptr(bases, _lib.u8p), _ptr(offsets, _lib.u64p), C.byref(self._h)))
+        if device is None:
+            _lib.check(_lib.lib.cls_model_build(C.byref(tree_only.view), len(tip_node), _ptr(tip_node, _lib.u64p),
+                                                _ptr(bases, _lib.u8p), _ptr(offsets, _lib.u64p), C.byref(self._h)))
+        else:
+            _lib.check(_lib.lib.cls_model_build_device(C.byref(tree_only.view), len(tip_node), _ptr(tip_node, _lib.u64p),
+                                                       _ptr(bases, _lib.u8p), _ptr(offsets, _lib.u64p), int(device),
+                                                       C.byref(self._h)))
         self.view = _lib.ModelView()
         _lib.check(_lib.lib.cls_built_model_view(self._h, C.byref(tree_only.view), C.byref(self.view)))
 

@@ -379,6 +379,19 @@ int cls_model_build(const cls_model_view *tree, uint64_t n_tips, const uint64_t 
 int cls_built_model_view(const cls_built_model *bm, const cls_model_view *tree, cls_model_view *out);
 void cls_built_model_destroy(cls_built_model *bm);
 
+/*
+ * The same builder on the GPU (`build-db`, map_kmers_to_tree,
+ * build_database/mod.rs:26-181).  Same arguments, same pairing of tips and sequences, and the same result
+ * as cls_model_build: entries in (hash, bucket key) order, node sets numbered in order of their first
+ * entry; only the order of the ids inside one node set differs (a set has no order: the reference keeps
+ * HashSets, kmers_map.rs:16-17).  Every window of both strands is hashed by one kernel, the occurrences are
+ * radix-sorted, entries / tip lists / node sets come from flag scans; the tree (parents, depths) is the only
+ * thing prepared on the host.  No CPU fallback: CLS_ERR_CUDA without a device.  CLS_ERR_UNSUPPORTED: more
+ * than 2^31 - 1 k-mer occurrences in one call, a sequence longer than 4 GiB, k_size beyond 100 KiB.
+ */
+int cls_model_build_device(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node,
+                           const uint8_t *bases, const uint64_t *offsets, int device, cls_built_model **out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,3 +59,84 @@ def assert_rows_equal(res, expected_outcomes, headers=None):
         if diff:
             bad.append((i, headers[i] if headers else None, diff))
     assert not bad, f"{len(bad)} of {len(expected_outcomes)} queries differ (got, want): {bad[:5]}"
+
+
+# ---- model-builder cases (host builder vs. device builder vs. the CPU walk through the device steps) ----
+def random_build_case(rng, n_internal, k, m, max_len=300, shuffle_nodes=True, letters=b"ACGT", dup_tips=0,
+                      internal_tips=0):
+    """A random tree (multifurcating, node indices in random order when ``shuffle_nodes``) and one sequence per
+    tip: related sequences (so that tips share k-mers), some shorter than k, ``dup_tips`` extra sequences mapped to
+    tips that already have one, ``internal_tips`` sequences mapped to internal nodes.  Returns
+    ``(FlatModel tree_only, tip_node, bases, offsets)``."""
+    import numpy as np
+    from classeq2_b200 import _lib
+    from classeq2_b200.model import FlatModel
+    children = {0: []}
+    n = 1
+    internal = [0]
+    for _ in range(n_internal):
+        p = internal[int(rng.integers(len(internal)))]
+        children[p].append(n)
+        children[n] = []
+        internal.append(n)
+        n += 1
+    for p in list(internal):                      # every internal node gets 1-3 leaves
+        for _ in range(int(rng.integers(1, 4))):
+            children[p].append(n)
+            children[n] = None
+            n += 1
+    perm = rng.permutation(n) if shuffle_nodes else np.arange(n)
+    perm = np.concatenate([[0], perm[perm != 0]])      # node 0 stays the root
+    new_of = np.empty(n, np.int64)
+    new_of[perm] = np.arange(n)
+    node_id = np.zeros(n, np.uint64)
+    kind = np.zeros(n, np.uint8)
+    lists = [[] for _ in range(n)]
+    for old in range(n):
+        i = int(new_of[old])
+        node_id[i] = 1000 + 7 * old                    # sparse ids
+        ch = children[old]
+        kind[i] = _lib.KIND_ROOT if old == 0 else (_lib.KIND_LEAF if ch is None else _lib.KIND_NODE)
+        lists[i] = [int(new_of[c]) for c in (ch or [])]
+    child_off = np.zeros(n + 1, np.uint64)
+    child_off[1:] = np.cumsum([len(c) for c in lists])
+    child_idx = np.array([c for cl in lists for c in cl], np.uint64)
+    tflat = FlatModel(k, m, node_id, kind, child_off, child_idx)
+    leaves = [int(new_of[o]) for o in range(n) if children[o] is None]
+    inner = [int(new_of[o]) for o in range(n) if children[o] is not None]
+    tip_nodes = list(leaves)
+    tip_nodes += [leaves[int(rng.integers(len(leaves)))] for _ in range(dup_tips)]
+    tip_nodes += [inner[int(rng.integers(len(inner)))] for _ in range(internal_tips)]
+    order = rng.permutation(len(tip_nodes))
+    tip_nodes = [tip_nodes[int(i)] for i in order]
+    lut = np.frombuffer(letters, np.uint8)
+    base = lut[rng.integers(0, len(lut), max_len)]
+    seqs = []
+    for _ in tip_nodes:
+        s = base.copy()
+        mut = rng.random(max_len) < 0.03
+        s[mut] = lut[rng.integers(0, len(lut), int(mut.sum()))]
+        ln = int(rng.integers(0, max_len + 1)) if rng.random() < 0.3 else max_len
+        start = int(rng.integers(0, max_len - ln + 1))
+        seqs.append(s[start:start + ln])
+    offsets = np.zeros(len(seqs) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    bases = np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)
+    if len(bases) == 0:
+        bases = np.zeros(1, np.uint8)
+    return tflat, np.array(tip_nodes, np.uint64), bases, offsets
+
+
+def assert_built_equal(a: dict, b: dict):
+    """Two ``BuiltModel.arrays()`` results describe the same map: same entries in the same order, same set
+    numbering, same ids in every set (the order inside a set is free)."""
+    import numpy as np
+    for key in ("entry_hash", "entry_bucket", "entry_set"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["set_off"], b["set_off"])
+    so = a["set_off"].astype(np.int64)
+    if len(so) > 1 and so[-1] > 0:
+        seg = np.repeat(np.arange(len(so) - 1), np.diff(so))
+        ka = np.lexsort((a["set_node_ids"], seg))
+        kb = np.lexsort((b["set_node_ids"], seg))
+        assert np.array_equal(a["set_node_ids"][ka], b["set_node_ids"][kb])

@@ -101,6 +101,16 @@ def test_compute_fails_loudly_without_gpu(col_flat):
     with pytest.raises(_lib.ClsError) as ei:
         cq.Index(col_flat, device=0, shard=1, n_shards=2)
     assert ei.value.code == _lib.CLS_ERR_CUDA
+    # the device model builder too (host-side argument checks come first, then "no device")
+    from classeq2_b200.model import BuiltModel, FlatModel
+    tflat = FlatModel(35, 4, col_flat.node_id, col_flat.node_kind, col_flat.child_off, col_flat.child_idx)
+    seq = np.frombuffer(b"ACGT" * 20, np.uint8).copy()
+    with pytest.raises(_lib.ClsError) as ei:
+        BuiltModel(tflat, np.array([1], np.uint64), seq, np.array([0, 80], np.uint64), device=0)
+    assert ei.value.code == _lib.CLS_ERR_CUDA
+    with pytest.raises(_lib.ClsError) as ei:
+        BuiltModel(tflat, np.array([1 << 40], np.uint64), seq, np.array([0, 80], np.uint64), device=0)
+    assert ei.value.code == _lib.CLS_ERR_INVALID_ARGUMENT
     ptr, h = C.c_void_p(), (C.c_uint8 * 64)()
     assert _lib.lib.cls_peer_alloc(0, 1 << 20, C.byref(ptr), h) == _lib.CLS_ERR_CUDA
     assert _lib.lib.cls_peer_open(0, h, C.byref(ptr)) == _lib.CLS_ERR_CUDA

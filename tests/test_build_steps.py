@@ -1,0 +1,97 @@
+"""The index arithmetic of the device model builder (classeq2_b200/csrc/build_steps.hpp, build_prep.hpp), walked
+element by element on the CPU by the test-only library tests/native/libbuild_steps_host.so, against the host
+builder ``cls_model_build``.  No GPU: the kernels themselves are held equal to the host builder in
+tests/test_gpu_build.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import assert_built_equal, random_build_case
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def walk():
+    from classeq2_b200 import _lib
+    subprocess.run(["make", "-C", os.path.join(HERE, "native")], check=True, capture_output=True)
+    lib = C.CDLL(os.path.join(HERE, "native", "libbuild_steps_host.so"))
+    lib.bsh_model_build.restype = C.c_int
+    lib.bsh_model_build.argtypes = [C.POINTER(_lib.ModelView), C.c_uint64, _lib.u64p, _lib.u8p, _lib.u64p, C.POINTER(C.c_void_p)]
+
+    def run(tflat, tip_node, bases, offsets):
+        from classeq2_b200.model import BuiltModel
+        h = C.c_void_p()
+        rc = lib.bsh_model_build(C.byref(tflat.view), len(tip_node), tip_node.ctypes.data_as(_lib.u64p),
+                                 bases.ctypes.data_as(_lib.u8p), offsets.ctypes.data_as(_lib.u64p), C.byref(h))
+        assert rc == 0, rc
+        bm = BuiltModel.__new__(BuiltModel)       # read the handle with the product's own view call
+        bm.tree_only, bm._h, bm.view = tflat, h, _lib.ModelView()
+        _lib.check(_lib.lib.cls_built_model_view(h, C.byref(tflat.view), C.byref(bm.view)))
+        a = bm.arrays()
+        bm.close()
+        return a
+    return run
+
+
+def _host(tflat, tip_node, bases, offsets):
+    from classeq2_b200.model import BuiltModel
+    bm = BuiltModel(tflat, tip_node, bases, offsets)
+    a = bm.arrays()
+    bm.close()
+    return a
+
+
+@pytest.mark.parametrize("k,m", [(35, 4), (21, 0), (5, 7), (16, 2), (33, 4)])
+def test_walk_equals_host_builder_random(walk, k, m):
+    rng = np.random.default_rng(100 * k + m)
+    for it in range(6):
+        case = random_build_case(rng, n_internal=int(rng.integers(0, 25)), k=k, m=m, max_len=int(rng.integers(k, 260)),
+                                 dup_tips=it % 3, internal_tips=it % 2,
+                                 letters=b"ACGT" if it % 2 == 0 else b"ACGTacgtN")
+        assert_built_equal(_host(*case), walk(*case))
+
+
+def test_walk_multi_tile_sequences(walk):
+    """Sequences longer than one tile of the hashing kernel (2048 windows), with a tile of one window."""
+    rng = np.random.default_rng(7)
+    for max_len in (2048 + 34, 2048 + 35, 5000):
+        case = random_build_case(rng, n_internal=3, k=35, m=4, max_len=max_len)
+        a = _host(*case)
+        assert len(a["entry_hash"]) > 2048
+        assert_built_equal(a, walk(*case))
+
+
+def test_walk_colletotrichum(walk, col_queries, col_tree, col_npz):
+    from classeq2_b200.model import FlatModel
+    z = col_npz
+    tflat = FlatModel(35, 4, z["node_id"], z["node_kind"], z["child_off"], z["child_idx"])
+    idx = {c.name: i for i, c in enumerate(col_tree.root.walk()) if c.is_leaf()}
+    tips = col_queries[:171]
+    tip_node = np.array([idx[h] for h, _ in tips], np.uint64)
+    bases = np.frombuffer("".join(s for _, s in tips).encode(), np.uint8).copy()
+    offsets = np.zeros(len(tips) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for _, s in tips])
+    a = walk(tflat, tip_node, bases, offsets)
+    assert_built_equal(_host(tflat, tip_node, bases, offsets), a)
+    assert len(a["set_off"]) - 1 == 226
+
+
+def test_walk_degenerate_inputs(walk):
+    from classeq2_b200 import _lib
+    from classeq2_b200.model import FlatModel
+    tflat = FlatModel(35, 4, np.array([5, 9], np.uint64), np.array([_lib.KIND_ROOT, _lib.KIND_LEAF], np.uint8),
+                      np.array([0, 1, 1], np.uint64), np.array([1], np.uint64))
+    # no tips; one tip shorter than k; one tip of exactly k bases
+    for seqs in ([], [b"ACGT"], [b"ACGTTGCATGCATGACTGACTGATCGATCGATGCA"]):
+        offsets = np.zeros(len(seqs) + 1, np.uint64)
+        if seqs:
+            offsets[1:] = np.cumsum([len(s) for s in seqs])
+        bases = np.frombuffer(b"".join(seqs) or b"\0", np.uint8).copy()
+        tip_node = np.ones(len(seqs), np.uint64)
+        a, b = _host(tflat, tip_node, bases, offsets), walk(tflat, tip_node, bases, offsets)
+        assert_built_equal(a, b)
+        assert len(b["entry_hash"]) == (2 if seqs and len(seqs[0]) == 35 else 0)
