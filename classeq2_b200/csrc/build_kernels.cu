@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <memory>
 #include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -203,8 +204,8 @@ inline uint32_t grid_for(uint64_t n, int sm_count) {
                                        std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
     } while (0)
 
-extern "C" int cls_model_build_device(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node, const uint8_t *bases,
-                                      const uint64_t *offsets, int device, cls_built_model **out) {
+static int build_device(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node, const uint8_t *bases,
+                        const uint64_t *offsets, int device, cls_built_model **out) {
     using cls::set_last_error;
     if (!tree || !out || (n_tips && (!tip_node || !offsets || !bases))) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = nullptr;
@@ -368,12 +369,8 @@ extern "C" int cls_model_build_device(const cls_model_view *tree, uint64_t n_tip
     set_fill_kernel<<<gS, 256, 0, st>>>(d_parent, d_depth, d_rank_node, d_node_id, d_set_rep, d_list_off, d_tips, d_set_off, d_set_nodes, S);
     BK_TRY(cudaGetLastError());
     // ---- results ------------------------------------------------------------------------------------------------
-    try {
-        bm->entry_hash.resize(E); bm->entry_bucket.resize(E); bm->entry_set.resize(E);
-        bm->set_off.resize((size_t)S + 1); bm->set_node_ids.resize(total_nodes);
-    } catch (const std::bad_alloc &) {
-        return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation of the built model failed");
-    }
+    bm->entry_hash.resize(E); bm->entry_bucket.resize(E); bm->entry_set.resize(E);
+    bm->set_off.resize((size_t)S + 1); bm->set_node_ids.resize(total_nodes);
     BK_TRY(cudaMemcpyAsync(bm->entry_hash.data(), d_entry_hash, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
     BK_TRY(cudaMemcpyAsync(bm->entry_bucket.data(), d_entry_bucket, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
     BK_TRY(cudaMemcpyAsync(bm->entry_set.data(), d_entry_set, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
@@ -383,4 +380,18 @@ extern "C" int cls_model_build_device(const cls_model_view *tree, uint64_t n_tip
     bm->set_off[S] = total_nodes;
     *out = guard.release();
     return CLS_OK;
+}
+
+// Nothing is thrown across the ABI: host allocation failures become CLS_ERR_OUT_OF_MEMORY.
+extern "C" int cls_model_build_device(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node, const uint8_t *bases,
+                                      const uint64_t *offsets, int device, cls_built_model **out) {
+    try {
+        return build_device(tree, n_tips, tip_node, bases, offsets, device, out);
+    } catch (const std::bad_alloc &) {
+        if (out) *out = nullptr;
+        return cls::set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while building the model");
+    } catch (const std::exception &e) {
+        if (out) *out = nullptr;
+        return cls::set_last_error(CLS_ERR_INVALID_ARGUMENT, std::string("cls_model_build_device: ") + e.what());
+    }
 }

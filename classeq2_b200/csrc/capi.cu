@@ -13,6 +13,8 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -41,6 +43,24 @@ int fail(int code, const std::string &msg) {
 namespace cls {
 int set_last_error(int code, const std::string &msg) { return fail(code, msg); }  // for host_api.cpp
 }
+namespace {
+
+// Nothing is thrown across the C ABI (include/classeq_b200.h, "Conventions"): every entry point with a body that
+// can allocate is a function-try-block ending in CLS_ABI_CATCH.
+int translate_exception() {
+    try {
+        throw;
+    } catch (const std::bad_alloc &) {
+        return fail(CLS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    } catch (const std::exception &e) {
+        return fail(CLS_ERR_INVALID_ARGUMENT, std::string("unexpected exception: ") + e.what());
+    } catch (...) {
+        return fail(CLS_ERR_INVALID_ARGUMENT, "unexpected exception");
+    }
+}
+#define CLS_ABI_CATCH catch (...) { return translate_exception(); }
+
+}  // namespace
 namespace {
 
 #define CU_TRY(expr)                                                                          \
@@ -404,18 +424,18 @@ void cls_params_default(cls_params *p) {
     p->min_match_coverage = 0.7;   // place_sequence.rs:74
 }
 
-int cls_device_count(void) {
+int cls_device_count(void) try {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
     return n;
-}
+} CLS_ABI_CATCH
 
-int cls_index_create(const cls_model_view *model, int device, cls_index **out) {
+int cls_index_create(const cls_model_view *model, int device, cls_index **out) try {
     return cls_index_create_shard(model, device, 0, 1, out);
-}
+} CLS_ABI_CATCH
 
-int cls_index_create_shard(const cls_model_view *model, int device, uint32_t shard, uint32_t n_shards, cls_index **out) {
+int cls_index_create_shard(const cls_model_view *model, int device, uint32_t shard, uint32_t n_shards, cls_index **out) try {
     if (!out) return fail(CLS_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = nullptr;
     if (n_shards == 0 || n_shards > kMaxShards || shard >= n_shards)
@@ -478,17 +498,17 @@ int cls_index_create_shard(const cls_model_view *model, int device, uint32_t sha
     ix->info.device = device;
     *out = ix.release();
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
 void cls_index_destroy(cls_index *ix) { delete ix; }
 
-int cls_index_get_info(const cls_index *ix, cls_index_info *info) {
+int cls_index_get_info(const cls_index *ix, cls_index_info *info) try {
     if (!ix || !info) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     *info = ix->info;
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) {
+int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) try {
     if (!ix || !batch || !params || !result) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
     const double t0 = now_ms();
@@ -593,9 +613,9 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
     tm.total_ms = now_ms() - t0;
     { std::lock_guard<std::mutex> lk(ix->mu); ix->timing = tm; }
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_batch_upload(cls_index *ix, const cls_batch *batch, cls_resident_batch **out) {
+int cls_batch_upload(cls_index *ix, const cls_batch *batch, cls_resident_batch **out) try {
     if (!ix || !batch || !out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = nullptr;
     CU_TRY(cudaSetDevice(ix->device));
@@ -617,10 +637,10 @@ int cls_batch_upload(cls_index *ix, const cls_batch *batch, cls_resident_batch *
     CU_TRY(cudaMemset(rb->d_results.p, 0xFF, res_b));
     *out = rb.release();
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
 // ---- FASTA ingest on the device (file_or_stdin.rs:76-116, sequence.rs:47-56) -----------
-int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_resident_batch **out, cls_fasta_records *records) {
+int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_resident_batch **out, cls_fasta_records *records) try {
     if (!ix || !out || !records || (n_bytes && !text)) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = nullptr;
     std::memset(records, 0, sizeof *records);
@@ -746,9 +766,9 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
     records->length = ln.data();
     *out = rb.release();
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_place_resident(cls_index *ix, cls_resident_batch *rb, const cls_params *params, void *stream) {
+int cls_place_resident(cls_index *ix, cls_resident_batch *rb, const cls_params *params, void *stream) try {
     if (!ix || !rb || !params) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (rb->device != ix->device) return fail(CLS_ERR_INVALID_ARGUMENT, "resident batch lives on another device");
     if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
@@ -758,9 +778,9 @@ int cls_place_resident(cls_index *ix, cls_resident_batch *rb, const cls_params *
                             (ResultRec *)rb->d_results.p, (cudaStream_t)stream, rb->d_scratch, &launches);
     if (rc == CLS_OK) { std::lock_guard<std::mutex> lk(ix->mu); ix->timing.kernel_launches = launches; }
     return rc;
-}
+} CLS_ABI_CATCH
 
-int cls_resident_fetch(cls_index *ix, cls_resident_batch *rb, void *stream, cls_result *result) {
+int cls_resident_fetch(cls_index *ix, cls_resident_batch *rb, void *stream, cls_result *result) try {
     if (!ix || !rb || !result) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     CU_TRY(cudaSetDevice(ix->device));
     const size_t res_b = (size_t)rb->lay.n_device * sizeof(ResultRec);
@@ -771,7 +791,7 @@ int cls_resident_fetch(cls_index *ix, cls_resident_batch *rb, void *stream, cls_
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     scatter_results(rb->lay, ix->dix.k_size, (const ResultRec *)rb->h_results.p, result);
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
 void cls_resident_destroy(cls_resident_batch *rb) { delete rb; }
 
@@ -781,7 +801,7 @@ uint64_t cls_resident_bytes(const cls_resident_batch *rb) {
 }
 
 // ---- hash-sharded index: route -> (all-to-all) -> probe -> (all-to-all) -> place --------------------
-int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_windows) {
+int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_windows) try {
     if (!ix || !rb || !n_windows) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     CU_TRY(cudaSetDevice(ix->device));
     if (!rb->d_runs.p) {
@@ -795,7 +815,7 @@ int cls_routed_windows(cls_index *ix, cls_resident_batch *rb, uint64_t *n_window
     }
     *n_windows = rb->n_windows;
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
 static int route_hashes_impl(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, uint64_t *const *seg_ptrs,
                              void *d_slot_win, uint64_t *counts_out, void *stream) {
@@ -825,16 +845,16 @@ static int route_hashes_impl(cls_index *ix, cls_resident_batch *rb, uint32_t n_s
 }
 
 int cls_route_hashes(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *d_send,
-                     void *d_slot_win, uint64_t *counts_out, void *stream) {
+                     void *d_slot_win, uint64_t *counts_out, void *stream) try {
     if (!ix || !rb || !d_send || !d_slot_win || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
     uint64_t *seg[kMaxShards] = {nullptr};
     for (uint32_t o = 0; o < n_shards; ++o) seg[o] = (uint64_t *)d_send + (uint64_t)o * seg_cap;
     return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_slot_win, counts_out, stream);
-}
+} CLS_ABI_CATCH
 
 int cls_route_hashes_p2p(cls_index *ix, cls_resident_batch *rb, uint32_t n_shards, uint64_t seg_cap, void *const *d_segments,
-                         void *d_slot_win, uint64_t *counts_out, void *stream) {
+                         void *d_slot_win, uint64_t *counts_out, void *stream) try {
     if (!ix || !rb || !d_segments || !d_slot_win || !counts_out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
     uint64_t *seg[kMaxShards] = {nullptr};
@@ -843,10 +863,10 @@ int cls_route_hashes_p2p(cls_index *ix, cls_resident_batch *rb, uint32_t n_shard
         seg[o] = (uint64_t *)d_segments[o];
     }
     return route_hashes_impl(ix, rb, n_shards, seg_cap, seg, d_slot_win, counts_out, stream);
-}
+} CLS_ABI_CATCH
 
 // ---- buffers other processes of the box can map (CUDA IPC): the inbox / reply box of the fused exchange ----
-int cls_peer_alloc(int device, uint64_t bytes, void **d_ptr, uint8_t ipc_handle[64]) {
+int cls_peer_alloc(int device, uint64_t bytes, void **d_ptr, uint8_t ipc_handle[64]) try {
     if (!d_ptr || !ipc_handle || bytes == 0) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument or zero size");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     CU_TRY(cudaSetDevice(device));
@@ -858,9 +878,9 @@ int cls_peer_alloc(int device, uint64_t bytes, void **d_ptr, uint8_t ipc_handle[
     std::memcpy(ipc_handle, &h, 64);
     *d_ptr = p;
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_peer_open(int device, const uint8_t ipc_handle[64], void **d_ptr) {
+int cls_peer_open(int device, const uint8_t ipc_handle[64], void **d_ptr) try {
     if (!d_ptr || !ipc_handle) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     CU_TRY(cudaSetDevice(device));
     cudaIpcMemHandle_t h;
@@ -870,32 +890,32 @@ int cls_peer_open(int device, const uint8_t ipc_handle[64], void **d_ptr) {
     if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
     *d_ptr = p;
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_peer_close(int device, void *d_ptr) {
+int cls_peer_close(int device, void *d_ptr) try {
     if (!d_ptr) return CLS_OK;
     CU_TRY(cudaSetDevice(device));
     CU_TRY(cudaIpcCloseMemHandle(d_ptr));
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_peer_free(int device, void *d_ptr) {
+int cls_peer_free(int device, void *d_ptr) try {
     if (!d_ptr) return CLS_OK;
     CU_TRY(cudaSetDevice(device));
     CU_TRY(cudaFree(d_ptr));
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_shard_probe(cls_index *ix, const void *d_hashes, uint64_t n, void *d_replies, void *stream) {
+int cls_shard_probe(cls_index *ix, const void *d_hashes, uint64_t n, void *d_replies, void *stream) try {
     if (!ix || (n && (!d_hashes || !d_replies))) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     CU_TRY(cudaSetDevice(ix->device));
     cudaError_t e = launch_shard_probe(ix->dix, ix->shard, (const uint64_t *)d_hashes, n, d_replies, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("probe kernel launch: ") + cudaGetErrorString(e));
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
 int cls_place_routed(cls_index *ix, cls_resident_batch *rb, const void *d_replies, const void *d_slot_win,
-                     uint32_t n_shards, uint64_t seg_cap, const cls_params *params, void *stream) {
+                     uint32_t n_shards, uint64_t seg_cap, const cls_params *params, void *stream) try {
     if (!ix || !rb || !params || !d_replies || !d_slot_win) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n_shards == 0 || n_shards > kMaxShards) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8");
     if (!rb->d_runs.p) return fail(CLS_ERR_INVALID_ARGUMENT, "cls_route_hashes has not run on this batch");
@@ -918,17 +938,17 @@ int cls_place_routed(cls_index *ix, cls_resident_batch *rb, const void *d_replie
         if (e != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("routed place kernel launch: ") + cudaGetErrorString(e));
     }
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_get_timing(const cls_index *ix, cls_timing *out) {
+int cls_get_timing(const cls_index *ix, cls_timing *out) try {
     if (!ix || !out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     std::lock_guard<std::mutex> lk(const_cast<cls_index *>(ix)->mu);
     *out = ix->timing;
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
 int cls_debug_kmer_hashes(int device, uint32_t k_size, const uint8_t *bases, uint64_t len, uint64_t *out_hashes,
-                          uint64_t cap, uint64_t *n_out) {
+                          uint64_t cap, uint64_t *n_out) try {
     if (!n_out || (len && !bases) || k_size == 0) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument or k == 0");
     *n_out = 0;
     if (len < k_size) return CLS_OK;  // kmers_map.rs:383-385
@@ -949,10 +969,10 @@ int cls_debug_kmer_hashes(int device, uint32_t k_size, const uint8_t *bases, uin
     *n_out = n;
     if (out_hashes) std::memcpy(out_hashes, h.data(), std::min<uint64_t>(n, cap) * 8);
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
 int cls_debug_node_counts(cls_index *ix, const uint8_t *bases, uint64_t len, const cls_params *params, cls_level_count *rows,
-                          uint64_t cap, uint64_t *n_rows, cls_result *result) {
+                          uint64_t cap, uint64_t *n_rows, cls_result *result) try {
     if (!ix || !params || !n_rows || (len && !bases) || (cap && !rows)) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     *n_rows = 0;
     if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index");
@@ -999,14 +1019,14 @@ int cls_debug_node_counts(cls_index *ix, const uint8_t *bases, uint64_t len, con
         if (result->iterations) result->iterations[0] = rr.iterations;
     }
     return CLS_OK;
-}
+} CLS_ABI_CATCH
 
-int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable) {
+int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable) try {
     if ((len && !bases) || !words_out || len >= (1ull << 31) || cap_words < (len + 15) / 16)
         return fail(CLS_ERR_INVALID_ARGUMENT, "bad arguments");
     if (len == 0) return 1;
     return (portable ? pack_read_portable(bases, (uint32_t)len, words_out) : pack_read(bases, (uint32_t)len, words_out)) ? 1 : 0;
-}
+} CLS_ABI_CATCH
 
 uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, uint64_t seed) {
     return murmur3_x64_128_h1(data, len, seed);

@@ -5,6 +5,9 @@
 // the synthetic models of BASELINE.json's configs without going through multi-GB YAML.
 #include <algorithm>
 #include <cstring>
+#include <memory>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -36,8 +39,8 @@ namespace cls {
 int set_last_error(int code, const std::string &msg);  // capi.cu
 }
 
-extern "C" int cls_model_build(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node,
-                               const uint8_t *bases, const uint64_t *offsets, cls_built_model **out) {
+static int build_host(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node,
+                      const uint8_t *bases, const uint64_t *offsets, cls_built_model **out) {
     using cls::set_last_error;
     if (!tree || !out || (n_tips && (!tip_node || !offsets || !bases)))
         return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -103,7 +106,8 @@ extern "C" int cls_model_build(const cls_model_view *tree, uint64_t n_tips, cons
     });
 
     // ---- group by (bucket, hash); de-duplicate tip lists; node set = union of root->tip paths ----
-    auto bm = new cls_built_model();
+    std::unique_ptr<cls_built_model> guard(new cls_built_model());
+    cls_built_model *bm = guard.get();
     bm->k_size = k; bm->m_size = m;
     bm->set_off.push_back(0);
     std::unordered_map<uint64_t, std::vector<uint64_t>> set_by_hash;  // tip-list hash -> set indices
@@ -145,8 +149,22 @@ extern "C" int cls_model_build(const cls_model_view *tree, uint64_t n_tips, cons
         bm->entry_set.push_back(sid);
         i = j;
     }
-    *out = bm;
+    *out = guard.release();
     return CLS_OK;
+}
+
+// Nothing is thrown across the ABI: host allocation failures become CLS_ERR_OUT_OF_MEMORY.
+extern "C" int cls_model_build(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node,
+                               const uint8_t *bases, const uint64_t *offsets, cls_built_model **out) {
+    try {
+        return build_host(tree, n_tips, tip_node, bases, offsets, out);
+    } catch (const std::bad_alloc &) {
+        if (out) *out = nullptr;
+        return cls::set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while building the model");
+    } catch (const std::exception &e) {
+        if (out) *out = nullptr;
+        return cls::set_last_error(CLS_ERR_INVALID_ARGUMENT, std::string("cls_model_build: ") + e.what());
+    }
 }
 
 extern "C" int cls_built_model_view(const cls_built_model *bm, const cls_model_view *tree, cls_model_view *out) {
