@@ -127,11 +127,18 @@ def tree_from_newick(newick: str, file_name: str, min_branch_support: float) -> 
 
 def map_kmers_to_tree(tree_path: Union[str, os.PathLike], msa_path: Union[str, os.PathLike],
                       k_size: Optional[int] = None, m_size: Optional[int] = None,
-                      min_branch_support: Optional[float] = None, device: Optional[int] = None) -> Tree:
+                      min_branch_support: Optional[float] = None, device: Optional[int] = None,
+                      pairing: str = "own") -> Tree:
     """Same arguments and defaults as the reference (build_database/mod.rs:26-44: k = 35, m = 4, support >= 70).
     Sequences whose header names no tip of the tree are ignored; tips without a sequence get no k-mers.
     ``device``: build the k-mer map on that GPU (``cls_model_build_device``) instead of the host builder; the
-    result is the same map."""
+    result is the same map.
+    ``pairing``: ``"own"`` (default) indexes every tip with its own sequence; ``"reference"`` reproduces the
+    reference's MSA loop bit for bit - header i is indexed with sequence i-1, the first header gets no k-mers and
+    the last sequence is dropped (build_database/mod.rs:93-116; pinned by the reference's own build output,
+    tests/golden/reference_built_model_k12.json.gz)."""
+    if pairing not in ("own", "reference"):
+        raise ValueError("pairing must be 'own' or 'reference'")
     k_size = 35 if k_size is None else int(k_size)
     m_size = 4 if m_size is None else int(m_size)
     min_branch_support = 70.0 if min_branch_support is None else float(min_branch_support)
@@ -147,7 +154,10 @@ def map_kmers_to_tree(tree_path: Union[str, os.PathLike], msa_path: Union[str, o
         if cl.is_leaf() and cl.name is not None:
             tip_index.setdefault(cl.name, i)
     tip_node, seqs = [], []
-    for header, seq in read_fasta(msa_path):
+    records = list(read_fasta(msa_path))
+    if pairing == "reference":
+        records = [(records[j][0], records[j - 1][1] if j else "") for j in range(len(records))]
+    for header, seq in records:
         i = tip_index.get(header)
         if i is not None and seq:
             tip_node.append(i)

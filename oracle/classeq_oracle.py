@@ -26,12 +26,16 @@ the reference checkout, ``core/src/...``):
 
 PARITY STATUS: the reference is Rust and cannot be compiled in this environment
 (no cargo/rustc, 465 un-vendored crates).  Reference-pinned known answers exist
-only for the hash arithmetic, the windowing, the "both strands / all windows"
-count (``one: 3754``), the result wire shape and the tree id / pre-order node ids
-(see ``tests/test_oracle_kats.py``).  **Placement decisions themselves are
-"parity unpinned"**: the only placement goldens in the reference depend on a
-missing Git-LFS model blob.  They are pinned here by agreement of two independent
-restatements (this file and ``oracle/classeq_oracle.cpp``).
+for the hash arithmetic, the windowing, the "both strands / all windows" count
+(``one: 3754``), the result wire shape, and - through the one model the reference
+itself wrote (``core/src/tests/data/.../outputs/Colletotrichum_acutatum_gapdh-PhyML.yaml``,
+committed compactly as ``tests/golden/reference_built_model_k12.json.gz``) - the whole
+tree of ``Tree::init_from_file`` and the MODEL CONTENT: every k-mer's node set (union
+of root -> tip id paths) and the header / sequence pairing of the build loop, all 2 158
+k-mers reproduced exactly (``tests/test_oracle_kats.py``).  **Placement decisions
+themselves are "parity unpinned"**: the only placement goldens in the reference
+depend on a missing Git-LFS model blob.  They are pinned here by agreement of two
+independent restatements (this file and ``oracle/classeq_oracle.cpp``).
 """
 from __future__ import annotations
 
@@ -456,17 +460,35 @@ def tree_from_newick(newick: str, file_name: str, min_branch_support: float) -> 
     return Tree(id=tid, name=file_name, min_branch_support=min_branch_support, root=root)
 
 
-def map_kmers_to_tree(tree: Tree, records: List[Tuple[str, str]], k_size: int = 35, m_size: int = 4) -> Tree:
-    """build_database/mod.rs:26-181 with the header/sequence pairing CORRECTED
-    (each tip is indexed with its own sequence; the reference pairs header i with
-    sequence i-1 and drops the last one, :93-116 - a build-side bug outside the
-    placement path, see SURVEY.md section 8c note).  Node set of a k-mer = union of the
-    root->tip id paths (both ends included) of every tip containing it."""
+def reference_pairing(records: List[Tuple[str, str]]) -> List[Tuple[str, str]]:
+    """The (header, sequence) pairs the reference's MSA loop actually indexes (build_database/mod.rs:93-116): at
+    every '>' line it hashes the sequence accumulated SO FAR (the previous record's) and sends it under the NEW
+    header, and nothing is flushed after the last line - header i is paired with sequence i-1, the first header
+    with the empty string, the last sequence is dropped.  Pinned by the reference's own build output
+    (tests/golden/reference_built_model_k12.json.gz, written by the reference from its Colletotrichum inputs)."""
+    return [(records[i][0], records[i - 1][1] if i else "") for i in range(len(records))]
+
+
+def map_kmers_to_tree(tree: Tree, records: List[Tuple[str, str]], k_size: int = 35, m_size: int = 4,
+                      pairing: str = "own", forward_only: bool = False) -> Tree:
+    """build_database/mod.rs:26-181.  Node set of a k-mer = union of the root->tip id paths (both ends included,
+    clade.rs:127-156) of every tip whose sequence contains it (kmers_map.rs:119-155).
+
+    ``pairing="own"`` (default): each tip is indexed with its own sequence - the CORRECTED pairing every model
+    of this repo is built with; ``pairing="reference"``: the pairing of :func:`reference_pairing` (the
+    reference's build-side defect, outside the placement path - SURVEY.md section 8c note).
+    ``forward_only``: windows of the forward strand only - the k-mer generation of the reference before v0.2.3
+    (CHANGELOG.md:177-179 "fix the kmers generation that will not use the reverse complement"), which is the
+    state that wrote the reference's golden build output; today's code indexes both strands (kmers_map.rs:387-395)."""
+    if pairing not in ("own", "reference"):
+        raise ValueError("pairing must be 'own' or 'reference'")
     km = KmersMap(k_size, m_size)
     leaves = {cl.name: path for cl, path in tree.root.get_leaves_with_paths(None)}
-    for header, seq in records:
+    for header, seq in (reference_pairing(records) if pairing == "reference" else records):
         path = set(leaves[header])
-        for kmer, h in km.build_kmer_from_string(seq):
+        kmers = (KmersMap.build_kmers_from_sequence(seq, k_size) if len(seq) >= k_size else []) if forward_only \
+            else km.build_kmer_from_string(seq)
+        for kmer, h in kmers:
             km.insert_or_append_kmer_hash(kmer, h, path)
     tree.kmers_map = km
     return tree

@@ -140,3 +140,50 @@ def assert_built_equal(a: dict, b: dict):
         ka = np.lexsort((a["set_node_ids"], seg))
         kb = np.lexsort((b["set_node_ids"], seg))
         assert np.array_equal(a["set_node_ids"][ka], b["set_node_ids"][kb])
+
+
+# ---- the reference's own build output (tests/golden/reference_built_model_k12.json.gz) ----
+def load_reference_built_model():
+    import gzip
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    return json.loads(gzip.decompress(open(os.path.join(here, "golden", "reference_built_model_k12.json.gz"), "rb").read()))
+
+
+def reference_built_case(tips):
+    """The reference-written k = 12 model as a builder case: (pin, FlatModel tree_only (uncollapsed tree, m = 0),
+    tip_node, bases, offsets) with the REFERENCE's pairing (sequence i-1 under header i, last sequence dropped,
+    build_database/mod.rs:93-116), and ``want`` = {k-mer hash: node-id set} a BOTH-strand builder must produce:
+    the reference wrote the model before it indexed reverse complements (v0.2.3), so the set of k-mer s is
+    golden[s] | golden[revcomp(s)]."""
+    import os
+    import numpy as np
+    from classeq2_b200 import build, host_murmur3_h1
+    from classeq2_b200.model import FlatModel
+    pin = load_reference_built_model()
+    here = os.path.dirname(os.path.abspath(__file__))
+    nwk = open(os.path.join(here, "golden", pin["name"])).read()
+    tree = build.tree_from_newick(nwk, pin["name"], -1e9)           # nothing is collapsed, as in the golden
+    clades, node_id, node_kind, child_off, child_idx = FlatModel.tree_arrays(tree.root)
+    tflat = FlatModel(pin["k_size"], 0, node_id, node_kind, child_off, child_idx)
+    idx = {c.name: i for i, c in enumerate(clades) if c.is_leaf()}
+    pairs = [(tips[i][0], tips[i - 1][1]) for i in range(1, len(tips))]   # header 0 gets the empty string: no k-mers
+    tip_node = np.array([idx[h] for h, _ in pairs], np.uint64)
+    bases = np.frombuffer("".join(s for _, s in pairs).encode(), np.uint8).copy()
+    offsets = np.zeros(len(pairs) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for _, s in pairs])
+    comp = str.maketrans("ACGT", "TGCA")
+    want = {}
+    for s, ids in pin["kmers"].items():
+        rc = s[::-1].translate(comp)
+        both = set(ids) | set(pin["kmers"].get(rc, []))
+        want[host_murmur3_h1(s.encode(), 0)] = both
+        want[host_murmur3_h1(rc.encode(), 0)] = both
+    return pin, tflat, tip_node, bases, offsets, want
+
+
+def built_as_map(a: dict) -> dict:
+    """``BuiltModel.arrays()`` -> {hash: set of node ids} (m = 0: a single bucket)."""
+    so, sn = a["set_off"], a["set_node_ids"]
+    return {int(h): set(sn[int(so[s]):int(so[s + 1])].tolist()) for h, s in zip(a["entry_hash"].tolist(), a["entry_set"].tolist())}

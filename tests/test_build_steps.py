@@ -95,3 +95,32 @@ def test_walk_degenerate_inputs(walk):
         a, b = _host(tflat, tip_node, bases, offsets), walk(tflat, tip_node, bases, offsets)
         assert_built_equal(a, b)
         assert len(b["entry_hash"]) == (2 if seqs and len(seqs[0]) == 35 else 0)
+
+
+def test_builders_reproduce_the_reference_written_model(walk, col_queries):
+    """cls_model_build and the CPU walk through the device builder's steps, fed with the reference's pairing, give
+    the model the reference itself wrote (closed under reverse complement: it predates v0.2.3)."""
+    from helpers import built_as_map, reference_built_case
+    pin, tflat, tip_node, bases, offsets, want = reference_built_case(col_queries[:171])
+    host = _host(tflat, tip_node, bases, offsets)
+    assert set(host["entry_bucket"].tolist()) == {0}
+    assert built_as_map(host) == want
+    assert built_as_map(walk(tflat, tip_node, bases, offsets)) == want
+
+
+def test_map_kmers_to_tree_reference_pairing(tmp_path, oracle, col_queries):
+    """build.map_kmers_to_tree(pairing="reference") == the oracle's restatement with the reference's pairing."""
+    import os
+    from classeq2_b200 import build
+    nwk = "Colletotrichum_acutatum_gapdh-PhyML.nwk"
+    golden = os.path.join(HERE, "golden", nwk)
+    tips = col_queries[:171]
+    msa = tmp_path / "tips.fasta"
+    msa.write_text("".join(f">{h}\n{s}\n" for h, s in tips))
+    got = build.map_kmers_to_tree(golden, msa, pairing="reference")
+    want = oracle.tree_from_newick(open(golden).read(), nwk, 70.0)
+    oracle.map_kmers_to_tree(want, tips, 35, 4, pairing="reference")
+    assert {k: {h: set(n) for h, n in v.items()} for k, v in got.kmers_map.map.items()} == \
+           {k: {h: set(n) for h, n in v.items()} for k, v in want.kmers_map.map.items()}
+    own = build.map_kmers_to_tree(golden, msa)
+    assert own.kmers_map.map != got.kmers_map.map

@@ -246,3 +246,40 @@ def test_counter_form_equals_set_form(model, ri):
     else:
         assert p.status == "IdentityFound"
         assert got == ("IdentityFound", p.clade, p.one, p.rest, p.iterations)
+
+
+def test_reference_built_model_pins_tree_and_builder(oracle, col_queries):
+    """The reference's OWN build output for its Colletotrichum inputs (tests/golden/reference_built_model_k12.json.gz,
+    written by an early version: k = 12, string keys, forward strand only) is reproduced exactly by the oracle:
+    the tree of Tree::init_from_file (tree.rs:164-364: ids, kinds, names, supports, lengths), the windows, the node
+    set of every k-mer (root -> tip id paths, clade.rs:127-156) and the pairing of the MSA loop (header i with
+    sequence i-1, build_database/mod.rs:93-116)."""
+    import os
+    from helpers import load_reference_built_model
+    pin = load_reference_built_model()
+    nwk = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", pin["name"])).read()
+    tree = oracle.tree_from_newick(nwk, pin["name"], -1e9)       # that version collapsed nothing
+    assert tree.id == pin["id"] and tree.name == pin["name"]
+
+    def strip(n):                                                # the old schema has no `parent` field
+        n = {k: v for k, v in n.items() if k != "parent"}
+        if "children" in n:
+            n["children"] = [strip(c) for c in n["children"]]
+        return n
+    assert strip(tree.root.to_obj()) == pin["root"]
+    tips = col_queries[:171]                                     # the reference's gap-free FASTA, in file order
+    oracle.map_kmers_to_tree(tree, tips, pin["k_size"], 0, pairing="reference", forward_only=True)
+    assert list(tree.kmers_map.map) == [0]                       # m = 0: one bucket
+    assert tree.kmers_map.map[0] == {oracle.hash_kmer(s): set(ids) for s, ids in pin["kmers"].items()}
+    # with the corrected pairing the map differs (that is the defect), with both strands it is the closure below
+    own = oracle.tree_from_newick(nwk, pin["name"], -1e9)
+    oracle.map_kmers_to_tree(own, tips, pin["k_size"], 0, forward_only=True)
+    assert own.kmers_map.map[0] != tree.kmers_map.map[0]
+    both = oracle.tree_from_newick(nwk, pin["name"], -1e9)
+    oracle.map_kmers_to_tree(both, tips, pin["k_size"], 0, pairing="reference")
+    comp = str.maketrans("ACGT", "TGCA")
+    want = {}
+    for s, ids in pin["kmers"].items():
+        rc = s[::-1].translate(comp)
+        want[oracle.hash_kmer(s)] = want[oracle.hash_kmer(rc)] = set(ids) | set(pin["kmers"].get(rc, []))
+    assert both.kmers_map.map[0] == want

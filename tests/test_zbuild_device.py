@@ -103,3 +103,11 @@ def test_map_kmers_to_tree_on_the_device(tmp_path, col_queries):
     host = build.map_kmers_to_tree(golden, msa)
     dev = build.map_kmers_to_tree(golden, msa, device=0)
     assert host.to_obj() == dev.to_obj()
+
+
+def test_device_builder_reproduces_the_reference_written_model(col_queries):
+    """Fed with the reference's pairing, the device builder gives the model the reference itself wrote
+    (tests/golden/reference_built_model_k12.json.gz; closed under reverse complement: it predates v0.2.3)."""
+    from helpers import built_as_map, reference_built_case
+    pin, tflat, tip_node, bases, offsets, want = reference_built_case(col_queries[:171])
+    assert built_as_map(_build((tflat, tip_node, bases, offsets), device=0)) == want
