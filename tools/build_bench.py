@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Times the two builders of the k-mer -> node-set map (cls_model_build on the host cores, cls_model_build_device on
 cuda:0) on a synthetic model and checks that they give the same arrays.
-usage: build_bench.py [n_tips=1000] [l_ref=1000] [seed=1001]"""
+usage: build_bench.py [n_tips=1000] [l_ref=1000] [seed=1001] [device-only]"""
 import os
 import sys
 import time
@@ -22,7 +22,8 @@ def main():
     tflat = synth.tree_only_flat(tree, 35, 4)
     bases, offs = synth.refs_to_batch(codes, lens)
     out = {}
-    for name, dev in (("device", 0), ("device_warm", 0), ("host", None)):
+    device_only = len(sys.argv) > 4 and sys.argv[4] == "device-only"   # under ncu: one device build, nothing else
+    for name, dev in ((("device", 0),) if device_only else (("device", 0), ("device_warm", 0), ("host", None))):
         t0 = time.perf_counter()
         bm = BuiltModel(tflat, tree.tip_node, bases, offs, device=dev)
         dt = time.perf_counter() - t0
@@ -31,6 +32,8 @@ def main():
         n_occ = int(2 * np.maximum(lens.astype(np.int64) - 34, 0).sum())
         print(f"{name:12s} {dt * 1e3:9.1f} ms  {n_occ / dt / 1e6:8.1f} M occurrences/s  entries={len(out[name]['entry_hash'])} "
               f"sets={len(out[name]['set_off']) - 1}", flush=True)
+    if device_only:
+        return
     same = all(np.array_equal(out["host"][k], out["device"][k]) for k in ("entry_hash", "entry_bucket", "entry_set", "set_off"))
     print("same entries / set numbering:", same)
 
