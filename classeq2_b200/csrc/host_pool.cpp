@@ -27,17 +27,31 @@ int host_threads() {
 
 namespace {
 
+// One parallel_for call.  It lives on the caller's stack for the duration of the call; workers only ever see it
+// through Pool::cur, under the pool mutex, and are counted in Pool::active for as long as they hold it - so every
+// field a worker reads belongs to the job it joined, never to a later one.
+struct Job {
+    const std::function<void(uint64_t, uint64_t)> &fn;
+    const uint64_t n, step;
+    std::atomic<uint64_t> next{0};
+    Job(const std::function<void(uint64_t, uint64_t)> &f, uint64_t n_, uint64_t step_) : fn(f), n(n_), step(step_) {}
+    void work() {
+        for (;;) {
+            const uint64_t a = next.fetch_add(step);
+            if (a >= n) break;
+            fn(a, std::min(n, a + step));
+        }
+    }
+};
+
 struct Pool {
     std::mutex job_mu;  // one job at a time
-    std::mutex mu;
+    std::mutex mu;      // guards cur, generation, active, stop
     std::condition_variable cv_work, cv_done;
     std::vector<std::thread> workers;
-    // current job
-    const std::function<void(uint64_t, uint64_t)> *fn = nullptr;
-    uint64_t n = 0, step = 0;
-    std::atomic<uint64_t> next{0};
-    uint64_t generation = 0;
-    int active = 0;
+    Job *cur = nullptr;       // the job workers may join (null between jobs and while a job drains)
+    uint64_t generation = 0;  // bumped once per job: a worker joins a job at most once
+    int active = 0;           // workers currently inside Job::work
     bool stop = false;
 
     Pool() {
@@ -49,48 +63,35 @@ struct Pool {
         cv_work.notify_all();
         for (auto &t : workers) t.join();
     }
-    void run_chunks() {
-        for (;;) {
-            const uint64_t st = step;  // one value for the claim and for the range it covers
-            const uint64_t a = next.fetch_add(st);
-            if (a >= n) break;
-            (*fn)(a, std::min(n, a + st));
-        }
-    }
     void loop() {
         uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
         for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv_work.wait(lk, [&] { return stop || generation != seen; });
-                if (stop) return;
-                seen = generation;
-                ++active;
-            }
-            run_chunks();
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (--active == 0) cv_done.notify_all();
-            }
+            cv_work.wait(lk, [&] { return stop || (cur && generation != seen); });
+            if (stop) return;
+            seen = generation;
+            Job *j = cur;
+            ++active;
+            lk.unlock();
+            j->work();
+            lk.lock();
+            if (--active == 0) cv_done.notify_all();
         }
     }
-    void run(uint64_t n_, uint64_t grain, const std::function<void(uint64_t, uint64_t)> &f) {
-        std::lock_guard<std::mutex> job(job_mu);
+    void run(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)> &f) {
+        std::lock_guard<std::mutex> one(job_mu);
         const uint64_t parts = (uint64_t)host_threads() * 4;
+        Job job(f, n, std::max<uint64_t>(grain, (n + parts - 1) / parts));
         {
             std::lock_guard<std::mutex> lk(mu);
-            fn = &f; n = n_;
-            step = std::max<uint64_t>(grain, (n_ + parts - 1) / parts);
-            next.store(0);
+            cur = &job;
             ++generation;
         }
         cv_work.notify_all();
-        run_chunks();
+        job.work();
         std::unique_lock<std::mutex> lk(mu);
-        // workers that woke up for this generation must have left run_chunks before fn goes away;
-        // workers that have not woken yet will find next >= n and do nothing
+        cur = nullptr;  // a worker that wakes up from here on finds no job; those inside are counted in `active`
         cv_done.wait(lk, [&] { return active == 0; });
-        fn = nullptr;
     }
 };
 
