@@ -1024,8 +1024,11 @@ int cls_debug_node_counts(cls_index *ix, const uint8_t *bases, uint64_t len, con
 int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable) try {
     if ((len && !bases) || !words_out || len >= (1ull << 31) || cap_words < (len + 15) / 16)
         return fail(CLS_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (portable < 0 || portable > kPackAvx512) return fail(CLS_ERR_INVALID_ARGUMENT, "unknown packer variant");
     if (len == 0) return 1;
-    return (portable ? pack_read_portable(bases, (uint32_t)len, words_out) : pack_read(bases, (uint32_t)len, words_out)) ? 1 : 0;
+    const int r = pack_read_variant(portable, bases, (uint32_t)len, words_out);
+    if (r < 0) return fail(CLS_ERR_UNSUPPORTED, "this CPU cannot run the requested packer variant");
+    return r;
 } CLS_ABI_CATCH
 
 uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, uint64_t seed) {

@@ -1,8 +1,10 @@
 // Host-side 2-bit packing of query bases (A=0 C=1 T=2 G=3 = (ascii >> 1) & 3, case-insensitive,
 // 16 bases per 32-bit word, base j of a word in bits 2j..2j+1).  Input side of the path: what the
 // reference's FASTA reader hands to place_sequence (sequence.rs:47-56 guarantees pure ACGT).
-// An AVX2 + BMI2 body (32 bases per step, PEXT gathers the two code bits of every byte) is picked
-// at run time; the portable SWAR body is the fallback.  Returns false on a non-ACGT byte.
+// The body is picked at run time: AVX-512 (BW + VL: 64 bases per step, masked loads and stores so that a read has
+// no scalar tail; the code bits are gathered with two multiply-adds and a 32 -> 8 bit narrowing), else AVX2 + BMI2
+// (32 bases per step, PEXT gathers the two code bits of every byte), else the portable SWAR body.  Returns false on
+// a non-ACGT byte.
 #include "host_pack.hpp"
 
 #include <cstring>
@@ -78,14 +80,56 @@ __attribute__((target("avx2,bmi2"))) bool pack_read_avx2(const uint8_t *s, uint3
     if (i < len) ok &= pack_read_swar(s + i, len - i, dst + w);
     return ok;
 }
+
+// 64 bases per step.  codes c = (x >> 1) & 3 as bytes; maddubs with weights (1, 4) joins two bases into 4 bits of a
+// 16-bit lane, madd with weights (1, 16) joins two of those into 8 bits of a 32-bit lane (4 bases), and vpmovdb
+// narrows the sixteen lanes to sixteen bytes = four words.  The last step of a read loads and stores under a mask:
+// exactly ceil(n / 16) words are written (the next read's words belong to another thread).
+__attribute__((target("avx512f,avx512bw,avx512vl"))) bool pack_read_avx512(const uint8_t *s, uint32_t len, uint32_t *dst) {
+    const __m512i up = _mm512_set1_epi8((char)0xDF), three = _mm512_set1_epi8(3);
+    const __m512i cA = _mm512_set1_epi8('A'), cC = _mm512_set1_epi8('C'), cG = _mm512_set1_epi8('G'), cT = _mm512_set1_epi8('T');
+    const __m512i w1 = _mm512_set1_epi16(0x0401), w2 = _mm512_set1_epi32(0x00100001);
+    __mmask64 bad = 0;
+    uint8_t *out = reinterpret_cast<uint8_t *>(dst);
+    uint32_t i = 0;
+    for (; i + 64 <= len; i += 64, out += 16) {
+        const __m512i x = _mm512_loadu_si512(s + i);
+        const __m512i y = _mm512_and_si512(x, up);
+        bad |= ~(_mm512_cmpeq_epi8_mask(y, cA) | _mm512_cmpeq_epi8_mask(y, cC) | _mm512_cmpeq_epi8_mask(y, cG) | _mm512_cmpeq_epi8_mask(y, cT));
+        const __m512i c = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
+        const __m512i q = _mm512_madd_epi16(_mm512_maddubs_epi16(c, w1), w2);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(out), _mm512_cvtepi32_epi8(q));
+    }
+    if (i < len) {
+        const uint32_t n = len - i;                                  // 1 .. 63 bases left
+        const __mmask64 k = ((__mmask64)1 << n) - 1;
+        const __m512i x = _mm512_maskz_loadu_epi8(k, s + i);
+        const __m512i y = _mm512_and_si512(x, up);
+        bad |= k & ~(_mm512_cmpeq_epi8_mask(y, cA) | _mm512_cmpeq_epi8_mask(y, cC) | _mm512_cmpeq_epi8_mask(y, cG) | _mm512_cmpeq_epi8_mask(y, cT));
+        const __m512i c = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
+        const __m512i q = _mm512_madd_epi16(_mm512_maddubs_epi16(c, w1), w2);
+        const __mmask16 kb = (__mmask16)((1u << (4 * ((n + 15) / 16))) - 1u);   // whole words: 4, 8, 12 or 16 bytes
+        _mm_mask_storeu_epi8(out, kb, _mm512_cvtepi32_epi8(q));
+    }
+    return bad == 0;
+}
 #endif
 
 using PackFn = bool (*)(const uint8_t *, uint32_t, uint32_t *);
 
-PackFn pick() {
+bool cpu_has(int variant) {
 #if defined(__x86_64__)
     __builtin_cpu_init();
-    if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) return pack_read_avx2;
+    if (variant == kPackAvx512) return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
+    if (variant == kPackAvx2) return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+#endif
+    return variant == kPackPortable;
+}
+
+PackFn pick() {
+#if defined(__x86_64__)
+    if (cpu_has(kPackAvx512)) return pack_read_avx512;
+    if (cpu_has(kPackAvx2)) return pack_read_avx2;
 #endif
     return pack_read_swar;
 }
@@ -98,5 +142,15 @@ bool pack_read(const uint8_t *s, uint32_t len, uint32_t *dst) {
 }
 
 bool pack_read_portable(const uint8_t *s, uint32_t len, uint32_t *dst) { return pack_read_swar(s, len, dst); }
+
+int pack_read_variant(int variant, const uint8_t *s, uint32_t len, uint32_t *dst) {
+    if (variant == kPackAuto) return pack_read(s, len, dst) ? 1 : 0;
+    if (!cpu_has(variant)) return -1;
+#if defined(__x86_64__)
+    if (variant == kPackAvx512) return pack_read_avx512(s, len, dst) ? 1 : 0;
+    if (variant == kPackAvx2) return pack_read_avx2(s, len, dst) ? 1 : 0;
+#endif
+    return pack_read_swar(s, len, dst) ? 1 : 0;
+}
 
 }  // namespace cls

@@ -346,10 +346,11 @@ uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, ui
  * cls_debug_pack_read: the host-side 2-bit packer used by cls_place_batch / cls_batch_upload
  * (code = (ascii >> 1) & 3 -> A=0 C=1 T=2 G=3, 16 bases per 32-bit word, base j in bits 2j..2j+1).
  * Writes ceil(len / 16) words (at most cap_words).  Returns 1 if every byte was A/C/G/T (either
- * case), 0 if a byte was invalid, negative on bad arguments.  `portable` != 0 forces the scalar
- * body (the default picks AVX2+BMI2 at run time when available); tests hold the two equal.
+ * case), 0 if a byte was invalid, negative on bad arguments.  `variant` picks the body: 0 = the one the
+ * library picked at run time (AVX-512, else AVX2+BMI2, else portable), 1 = portable SWAR, 2 = AVX2+BMI2,
+ * 3 = AVX-512 (CLS_ERR_UNSUPPORTED if this CPU cannot run it); tests hold them all equal.
  */
-int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable);
+int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int variant);
 
 /*
  * Host helpers mirroring the reference's input side (no GPU needed).

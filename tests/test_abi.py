@@ -152,25 +152,37 @@ def test_index_create_rejects_unsupported_models(col_npz):
 
 
 def test_host_packer_variants_agree_with_numpy():
-    """cls_debug_pack_read: the run-time dispatched (AVX2+BMI2) and the portable packer both equal a
-    numpy restatement of the layout, and both flag non-ACGT bytes."""
+    """cls_debug_pack_read: the run-time dispatched body and every named one this CPU can run (portable SWAR,
+    AVX2+BMI2, AVX-512) equal a numpy restatement of the layout, flag non-ACGT bytes at every position class, and
+    write exactly ceil(len / 16) words (the words after a read belong to the next read, packed by another thread)."""
     from classeq2_b200 import _lib
     rng = np.random.default_rng(5)
-    for L in list(range(0, 70)) + [127, 128, 129, 150, 151, 1000, 1911]:
+    ran = set()
+    for L in list(range(0, 200)) + [255, 256, 257, 1000, 1911]:
         codes = rng.integers(0, 4, L)
         s = np.frombuffer(b"ACTG", np.uint8)[codes].copy()          # code order A=0 C=1 T=2 G=3
         lower = rng.random(L) < 0.3
         s[lower] |= 0x20
-        want = np.zeros((L + 15) // 16 + 1, np.uint32)
+        nw = (L + 15) // 16
+        want = np.full(nw + 2, 0xDEADBEEF, np.uint32)               # sentinels after the read's words
+        want[:nw] = 0
         for j, c in enumerate(codes):
             want[j // 16] |= np.uint32(int(c) << (2 * (j % 16)))
-        for portable in (0, 1):
-            out = np.zeros(len(want), np.uint32)
+        for variant in (0, 1, 2, 3):
+            out = np.full(nw + 2, 0xDEADBEEF, np.uint32)
             buf = s if L else np.zeros(1, np.uint8)
-            rc = _lib.lib.cls_debug_pack_read(buf.ctypes.data_as(_lib.u8p), L, out.ctypes.data_as(_lib.u32p), len(out), portable)
-            assert rc == 1 and (out == want).all(), (L, portable)
-            if L:
-                bad = s.copy()
-                bad[int(rng.integers(L))] = ord("N")
-                rc = _lib.lib.cls_debug_pack_read(bad.ctypes.data_as(_lib.u8p), L, out.ctypes.data_as(_lib.u32p), len(out), portable)
-                assert rc == 0, (L, portable)
+            rc = _lib.lib.cls_debug_pack_read(buf.ctypes.data_as(_lib.u8p), L, out.ctypes.data_as(_lib.u32p), len(out), variant)
+            if rc == _lib.CLS_ERR_UNSUPPORTED:
+                assert variant in (2, 3)
+                continue
+            ran.add(variant)
+            assert rc == 1 and (out == want).all(), (L, variant)
+            for pos in ({0, L // 2, L - 1, int(rng.integers(L))} if L else ()):
+                for ch in (ord("N"), ord("U"), 0, 0x80 | ord("A"), ord("-")):
+                    bad = s.copy()
+                    bad[pos] = ch
+                    rc = _lib.lib.cls_debug_pack_read(bad.ctypes.data_as(_lib.u8p), L, out.ctypes.data_as(_lib.u32p), len(out), variant)
+                    assert rc == 0, (L, variant, pos, ch)
+    assert {0, 1} <= ran
+    out = np.zeros(4, np.uint32)
+    assert _lib.lib.cls_debug_pack_read(out.ctypes.data_as(_lib.u8p), 4, out.ctypes.data_as(_lib.u32p), 4, 7) == _lib.CLS_ERR_INVALID_ARGUMENT
