@@ -111,3 +111,38 @@ def test_device_builder_reproduces_the_reference_written_model(col_queries):
     from helpers import built_as_map, reference_built_case
     pin, tflat, tip_node, bases, offsets, want = reference_built_case(col_queries[:171])
     assert built_as_map(_build((tflat, tip_node, bases, offsets), device=0)) == want
+
+
+def test_placement_against_the_reference_written_model(cq_mod, oracle, col_queries):
+    """The model the reference wrote (k = 12, one bucket, forward-strand node sets) uploaded as it is: the 171 tip
+    sequences, their reverse complements and the other committed queries are placed exactly as the oracle places
+    them against the same model - the generic-k kernels on reference-authored node sets."""
+    from helpers import load_reference_built_model, outcome_of
+    cq = cq_mod
+    pin = load_reference_built_model()
+    otree = oracle.Tree.from_obj({"id": pin["id"], "name": pin["name"], "minBranchSupport": 70.0, "root": _with_parents(pin["root"])})
+    km = oracle.KmersMap(pin["k_size"], 0)
+    km.map[0] = {oracle.hash_kmer(s): set(ids) for s, ids in pin["kmers"].items()}
+    otree.kmers_map = km
+    flat = cq.FlatModel.from_tree(cq.Tree.from_obj(otree.to_obj()))
+    queries = [(h, s) for h, s in col_queries if s][:230]
+    queries += [(h + "_rc", oracle.KmersMap.reverse_complement(s)) for h, s in queries[:40]]
+    for f in (flat, flat.with_general_sets()):
+        ix = cq.Index(f, device=0)
+        for kn in (dict(), dict(remove_intersection=True)):
+            want = [outcome_of(oracle, h, s, otree, None, None, kn.get("remove_intersection")) for h, s in queries]
+            assert_rows_equal(ix.place_batch([s for _, s in queries], cq.PlaceParams(**kn)), want, [h for h, _ in queries])
+        ix.close()
+
+
+def _with_parents(node, parent=None):
+    out = dict(node, parent=parent)
+    if "children" in node:
+        out["children"] = [_with_parents(c, node["id"]) for c in node["children"]]
+    return out
+
+
+@pytest.fixture(scope="module")
+def cq_mod():
+    import classeq2_b200 as cq
+    return cq
