@@ -1,7 +1,7 @@
 """kb-scale reads against models with k != 35: the one-CTA-per-read geometry with the generic (any k) window hasher.
 The two halves are covered elsewhere (generic hasher: test_random_models / test_random_closed_models with short reads;
-one CTA per read: test_long_reads_cta_mode with k = 35); this file covers their combination.  It was written when the
-round's GPU time was spent, so its first run is the driver's (the file sorts last on purpose)."""
+one CTA per read: test_long_reads_cta_mode with k = 35); this file covers their combination (green on a B200:
+profiles/r1h/znew.log)."""
 import numpy as np
 import pytest
 
