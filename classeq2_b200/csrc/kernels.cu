@@ -263,8 +263,73 @@ struct ReadTables {
 // SHARED == true: several warps fill the tables of one read (CTA-per-read mode): counts are atomic and
 // start from zeroed bins.  SHARED == false: the warp owns the tables; a bin's count has one writer per
 // pass (the leader of its node set), so plain stores do and the bins need no zeroing.
+#ifdef CLS_INSERT_PLAIN
+// EXPERIMENT (off by default; `make variant NAME=plain EXTRA=-DCLS_INSERT_PLAIN=1`): the warp-owned tables without
+// shared-memory atomics.  A warp-wide CAS costs 64 cycles of the SM's atomic pipe (2 cycles per lane, twice for CAS)
+// and consume() - a quarter of scan_kernel's instructions - collects half of its stall samples behind them
+// (DESIGN.md section 9).  Here one lane per distinct key of the pass (match.any) probes with plain loads, writes its
+// key tentatively into an empty slot, and after a __syncwarp() the lane whose key is still there owns the slot; the
+// others move on.  No key is ever removed within a read, so linear probing stays consistent across passes.
+__device__ __forceinline__ uint32_t insert_hits_plain(const ReadTables &tb, bool hit, uint32_t slot_key, uint32_t set_off) {
+    const uint32_t lane = lane_id();
+    const uint32_t hm = __ballot_sync(kFull, hit);
+    if (hm == 0) return 0;   // warp-uniform
+    // ---- de-duplication set keyed by table slot: the same k-mer hash counts once per read
+    bool pending = false, fresh = false;
+    if (hit) pending = (uint32_t)(__ffs(__match_any_sync(hm, slot_key)) - 1) == lane;  // the same k-mer twice in one pass
+    uint32_t p1 = (slot_key >> 1) & tb.t1_mask;
+    while (__any_sync(kFull, pending)) {
+        uint32_t cur = kEmpty;
+        if (pending) {
+            cur = tb.t1[p1];
+            if (cur == kEmpty) tb.t1[p1] = slot_key;   // lanes with different keys may meet here: the last store stays
+        }
+        __syncwarp();
+        if (pending) {
+            if (cur == slot_key) pending = false;      // counted by an earlier pass
+            else if (cur == kEmpty && tb.t1[p1] == slot_key) { fresh = true; pending = false; }
+            else p1 = (p1 + 1) & tb.t1_mask;           // the slot holds another key (old, or the winner's)
+        }
+        __syncwarp();
+    }
+    const uint32_t fm = __ballot_sync(kFull, fresh);
+    if (fm == 0) return 0;   // warp-uniform; nothing was written
+    // ---- histogram by node-set record: one leader per distinct record among the fresh lanes
+    uint32_t peers = 0;
+    bool lead = false;
+    if (fresh) { peers = __match_any_sync(fm, set_off); lead = (uint32_t)(__ffs(peers) - 1) == lane; }
+    const uint32_t add = (uint32_t)__popc(peers);
+    uint32_t p2 = (set_off * 0x9E3779B1u) >> tb.t2_shift;
+    uint32_t n_sets = *tb.n_sets;   // broadcast load; written back by lane 0 below
+    while (__any_sync(kFull, lead)) {
+        uint32_t cur = kEmpty;
+        if (lead) {
+            cur = tb.t2k[p2];
+            if (cur == kEmpty) tb.t2k[p2] = set_off;
+        }
+        __syncwarp();
+        bool won = false;
+        if (lead) {
+            if (cur == set_off) { tb.t2c[p2] += add; lead = false; }   // a bin has one writer per pass: its leader
+            else if (cur == kEmpty && tb.t2k[p2] == set_off) { won = true; lead = false; }
+            else p2 = (p2 + 1) & tb.t2_mask;
+        }
+        const uint32_t wm = __ballot_sync(kFull, won);
+        if (won) { tb.lst[n_sets + __popc(wm & ((1u << lane) - 1u))] = p2; tb.t2c[p2] = add; }
+        n_sets += (uint32_t)__popc(wm);
+        __syncwarp();
+    }
+    if (lane == 0) *tb.n_sets = n_sets;
+    __syncwarp();
+    return (uint32_t)__popc(fm);
+}
+#endif
+
 template <bool SHARED>
 __device__ __forceinline__ uint32_t insert_hits(const ReadTables &tb, bool hit, uint32_t slot_key, uint32_t set_off) {
+#ifdef CLS_INSERT_PLAIN
+    if constexpr (!SHARED) return insert_hits_plain(tb, hit, slot_key, set_off);
+#endif
     bool fresh = false;
     if (hit) {
         uint32_t p1 = (slot_key >> 1) & tb.t1_mask;  // bit 0 is the slot within the bucket (mostly 0): not a hash bit
