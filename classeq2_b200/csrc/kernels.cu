@@ -265,9 +265,8 @@ struct ReadTables {
 // pass (the leader of its node set), so plain stores do and the bins need no zeroing.
 #ifdef CLS_INSERT_PLAIN
 // EXPERIMENT (off by default; `make variant NAME=plain EXTRA=-DCLS_INSERT_PLAIN=1`): the warp-owned tables without
-// shared-memory atomics.  A warp-wide CAS costs 64 cycles of the SM's atomic pipe (2 cycles per lane, twice for CAS)
-// and consume() - a quarter of scan_kernel's instructions - collects half of its stall samples behind them
-// (DESIGN.md section 9).  Here one lane per distinct key of the pass (match.any) probes with plain loads, writes its
+// shared-memory atomics.  consume() - a quarter of scan_kernel's instructions - collects half of its stall samples,
+// most of them behind the CAS results that its one-to-three-lane blocks wait for.  Here one lane per distinct key of the pass (match.any) probes with plain loads, writes its
 // key tentatively into an empty slot, and after a __syncwarp() the lane whose key is still there owns the slot; the
 // others move on.  No key is ever removed within a read, so linear probing stays consistent across passes.
 __device__ __forceinline__ uint32_t insert_hits_plain(const ReadTables &tb, bool hit, uint32_t slot_key, uint32_t set_off) {
