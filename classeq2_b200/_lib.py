@@ -80,6 +80,10 @@ class LevelCount(C.Structure):
                 ("excl", C.c_uint32), ("u", C.c_uint32)]
 
 
+class PlanClass(C.Structure):
+    _fields_ = [("first", C.c_uint32), ("count", C.c_uint32), ("max_len", C.c_uint32)]
+
+
 class ClsError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"classeq_b200 error {code}: {message}")
@@ -118,6 +122,7 @@ PROTOTYPES = {
     "cls_debug_node_counts": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(Params), C.POINTER(LevelCount), C.c_uint64, u64p,
                                         C.POINTER(Result)]),
     "cls_debug_host_murmur3_x64_128_h1": (C.c_uint64, [u8p, C.c_uint64, C.c_uint64]),
+    "cls_debug_plan_batch": (C.c_int, [C.c_uint32, C.POINTER(Batch), u8p, u32p, u32p, C.POINTER(PlanClass), C.c_uint32, u32p, u32p, u64p]),
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),
     "cls_filter_sequence": (C.c_uint64, [u8p, C.c_uint64, u8p, C.c_uint64]),
     "cls_model_build": (C.c_int, [C.POINTER(ModelView), C.c_uint64, u64p, u8p, u64p, C.POINTER(C.c_void_p)]),

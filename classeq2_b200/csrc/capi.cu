@@ -1021,6 +1021,24 @@ int cls_debug_node_counts(cls_index *ix, const uint8_t *bases, uint64_t len, con
     return CLS_OK;
 } CLS_ABI_CATCH
 
+int cls_debug_plan_batch(uint32_t k_size, const cls_batch *batch, uint8_t *pre_status, uint32_t *perm, uint32_t *word_off,
+                         cls_plan_class *classes, uint32_t cap_classes, uint32_t *n_classes, uint32_t *n_device, uint64_t *n_words) try {
+    if (!batch || !n_classes || !n_device || !n_words || k_size == 0) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument or k == 0");
+    PackedLayout lay;
+    std::vector<uint32_t> woff;
+    const int rc = plan_batch(batch, k_size, 0, lay, woff);
+    if (rc != CLS_OK) return rc;
+    *n_device = lay.n_device;
+    *n_words = lay.n_words;
+    *n_classes = (uint32_t)lay.classes.size();
+    if (pre_status) std::memcpy(pre_status, lay.pre_status.data(), lay.pre_status.size());
+    if (perm) std::memcpy(perm, lay.perm.data(), lay.perm.size() * 4);
+    if (word_off) std::memcpy(word_off, woff.data(), woff.size() * 4);
+    for (uint32_t c = 0; c < lay.classes.size() && c < cap_classes && classes; ++c)
+        classes[c] = cls_plan_class{lay.classes[c].first, lay.classes[c].count, lay.classes[c].max_len};
+    return CLS_OK;
+} CLS_ABI_CATCH
+
 int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable) try {
     if ((len && !bases) || !words_out || len >= (1ull << 31) || cap_words < (len + 15) / 16)
         return fail(CLS_ERR_INVALID_ARGUMENT, "bad arguments");

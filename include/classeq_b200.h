@@ -353,6 +353,20 @@ uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, ui
 int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int variant);
 
 /*
+ * cls_debug_plan_batch: the host-side planner of cls_place_batch / cls_batch_upload on its own (no GPU needed):
+ * queries shorter than k get their status on the host (pre_status[i] = CLS_STATUS_ERR_TOO_SHORT, else 0xFF), the
+ * others are grouped into LENGTH CLASSES - all reads of a class share one per-read table geometry; longest class
+ * first; input order is kept inside a class - and laid out back to back at word boundaries: perm[j] = caller index
+ * of the j-th read on the device (n_device of them), word_off[j] = its first packed word (word_off[n_device] =
+ * n_words), classes[c] = {first device position, count, longest read}.  Any output pointer may be NULL.
+ */
+typedef struct cls_plan_class {
+    uint32_t first, count, max_len;
+} cls_plan_class;
+int cls_debug_plan_batch(uint32_t k_size, const cls_batch *batch, uint8_t *pre_status, uint32_t *perm, uint32_t *word_off,
+                         cls_plan_class *classes, uint32_t cap_classes, uint32_t *n_classes, uint32_t *n_device, uint64_t *n_words);
+
+/*
  * Host helpers mirroring the reference's input side (no GPU needed).
  *
  * cls_filter_sequence: SequenceBody::remove_non_iupac_from_sequence
