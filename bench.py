@@ -48,11 +48,13 @@ def algorithmic_bytes(lens: np.ndarray) -> int:
     return int(((lens + 3) // 4 + 2 * (lens - K_SIZE + 1) * 16 + 32).sum())
 
 
-def make_workload(config: int, rank: int, world: int, n_reads_override=None):
+def make_workload(config: int, rank: int, world: int, n_reads_override=None, build_device=None):
     from classeq2_b200 import synth
     c = dict(synth.CONFIGS[config])
     t0 = time.time()
-    sm = synth.make_model(c["n_tips"], c["l_ref"], c["tree_seed"])
+    # build_device: the model's k-mer map is built on that GPU (cls_model_build_device) instead of the host cores;
+    # both builders give the same arrays (tests/test_zbuild_device.py), so the workload is the same either way
+    sm = synth.make_model(c["n_tips"], c["l_ref"], c["tree_seed"], device=build_device)
     n_total = n_reads_override or c["n_reads"]
     if config in (3, 5):  # the 10M reads of configs 3 and 5 are SHARDED over the ranks (strong)
         n_local = n_total // world + (1 if rank < n_total % world else 0)
@@ -187,7 +189,8 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sm, bases, offsets, scaling, gen_s = make_workload(args.config, rank, world, args.reads)
+    sm, bases, offsets, scaling, gen_s = make_workload(args.config, rank, world, args.reads,
+                                                       local_rank if args.device_build else None)
     n_local = len(offsets) - 1
     lens = np.diff(offsets.astype(np.int64))
     lookups_local = int((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum())
@@ -337,7 +340,7 @@ def run_sharded(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sm, bases, offsets, scaling, gen_s = make_workload(5, rank, world, args.reads)
+    sm, bases, offsets, scaling, gen_s = make_workload(5, rank, world, args.reads, local_rank if args.device_build else None)
     n_local = len(offsets) - 1
     lens = np.diff(offsets.astype(np.int64))
     lookups_local = int((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum())
@@ -487,6 +490,9 @@ def main():
     ap.add_argument("--reads", type=int, default=None, help="override the number of reads of the config")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="config 5: how routed k-mers cross NVLink")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
+    ap.add_argument("--device-build", action="store_true",
+                    help="set-up only: build the synthetic model's k-mer map on the GPU (cls_model_build_device) instead of the "
+                         "host cores - the same arrays, outside every timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -175,13 +175,14 @@ class SynthModel:
     flat: FlatModel       # full model (tree + entries + sets), owns its arrays
 
 
-def make_model(n_tips: int, l_ref, seed: int, k_size: int = 35, m_size: int = 4) -> SynthModel:
-    """Tree(N, seed) + Refs(N, Lref, seed+1) + the k-mer map built by ``cls_model_build``."""
+def make_model(n_tips: int, l_ref, seed: int, k_size: int = 35, m_size: int = 4, device: Optional[int] = None) -> SynthModel:
+    """Tree(N, seed) + Refs(N, Lref, seed+1) + the k-mer map built by ``cls_model_build`` (host) or, with
+    ``device`` given, by ``cls_model_build_device`` on that GPU (the same map, an order of magnitude sooner)."""
     tree = make_tree(n_tips, seed)
     codes, lens = make_refs(tree, l_ref, seed + 1)
     tflat = tree_only_flat(tree, k_size, m_size)
     bases, offsets = refs_to_batch(codes, lens)
-    bm = BuiltModel(tflat, tree.tip_node, bases, offsets)
+    bm = BuiltModel(tflat, tree.tip_node, bases, offsets, device=device)
     arr = bm.arrays()
     bm.close()
     flat = FlatModel(k_size, m_size, tree.node_id, tree.node_kind, tree.child_off, tree.child_idx,
