@@ -31,7 +31,8 @@ def test_library_exports_every_declared_symbol():
 def test_no_torch_in_the_library():
     from classeq2_b200 import _lib
     out = os.popen(f"ldd {_lib.LIB_PATH}").read()
-    assert "torch" not in out and "c10" not in out
+    names = [line.split()[0] for line in out.splitlines() if line.strip()]   # library names only: the load addresses are random hex
+    assert names and not [n for n in names if "torch" in n or "c10" in n], names
 
 
 def test_struct_layouts_match_header():
