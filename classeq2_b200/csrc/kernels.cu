@@ -1202,8 +1202,15 @@ __device__ __forceinline__ void descend_from_pairs(const DeviceIndex &ix, const 
     finish_read_reg<SLOTS>(ix, pp, cnt, excl, off, wt, n_matched, out);
 }
 
+// -DCLS_DESCEND_MINB=n (experiment): ask ptxas for n resident CTAs per SM (the default build leaves the register count to ptxas:
+// 40 registers, six CTAs = 48 warps per SM; the kernel waits on dependent loads with 8.7 eligible warps per scheduler)
+#ifdef CLS_DESCEND_MINB
+#define CLS_DESCEND_BOUNDS __launch_bounds__(256, CLS_DESCEND_MINB)
+#else
+#define CLS_DESCEND_BOUNDS __launch_bounds__(256)
+#endif
 template <int MAXSLOTS>
-__global__ void __launch_bounds__(256) descend_kernel(DeviceIndex ix, PlaceParams pp, ScanOut so, uint32_t first_read,
+__global__ void CLS_DESCEND_BOUNDS descend_kernel(DeviceIndex ix, PlaceParams pp, ScanOut so, uint32_t first_read,
                                                       uint32_t n_reads, ResultRec *__restrict__ results, uint32_t fan_cap) {
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
