@@ -283,3 +283,43 @@ def test_reference_built_model_pins_tree_and_builder(oracle, col_queries):
         rc = s[::-1].translate(comp)
         want[oracle.hash_kmer(s)] = want[oracle.hash_kmer(rc)] = set(ids) | set(pin["kmers"].get(rc, []))
     assert both.kmers_map.map[0] == want
+
+
+def test_reference_written_results_obey_the_descent_rules():
+    """1 111 placement records written by the reference itself (tests/golden/reference_gyrb_results_compact.json.gz:
+    two result files of its bsub-gyrB model, whose k-mer map is not available) against the rules the oracle and the
+    kernels implement: IdentityFound names a node WITHOUT non-leaf children (update_introspection_node.rs:32-87),
+    MaxResolutionReached a node WITH some (place_sequence.rs:456-465), a proposal has one > rest (:383-418), and
+    one <= 2 * (L - k + 1) - the count of distinct k-mers of both strands (kmers_map.rs:375-398) - with equality for
+    the queries that match a reference sequence completely."""
+    import gzip
+    import yaml
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    pin = json.loads(gzip.decompress(open(os.path.join(g, "reference_gyrb_results_compact.json.gz"), "rb").read()))
+    root = yaml.load(open(os.path.join(g, "bsub-gyrb-k35.tree-only.cls.yaml")), Loader=yaml.CSafeLoader)
+    nodes = {}
+    stack = [root]
+    while stack:
+        n = stack.pop()
+        nodes[n["id"]] = n
+        stack.extend(n.get("children") or [])
+    assert len(nodes) == 364
+
+    def has_nonleaf_child(i):
+        return any(c["kind"] != "LEAF" for c in nodes[i].get("children") or [])   # is_leaf() is by kind (clade.rs:166-172)
+
+    k = pin["k"]
+    n_id = n_max = n_full = 0
+    for tag, length, code, node, one, rest in pin["records"]:
+        if code == "IdentityFound":
+            n_id += 1
+            assert nodes[node]["kind"] != "LEAF" and not has_nonleaf_child(node), (tag, node)
+            assert one > rest >= 0
+            assert one <= 2 * (length - k + 1)
+            n_full += one == 2 * (length - k + 1)
+        elif code.startswith("MaxResolutionReached"):
+            n_max += 1
+            assert code == "MaxResolutionReached: LCA Accepted" and has_nonleaf_child(node), (tag, node)
+        else:
+            assert code.startswith("Unclassifiable")          # the older layout (fd8) carries no message
+    assert (n_id, n_max, len(pin["records"])) == (637, 472, 1111) and n_full == 328
