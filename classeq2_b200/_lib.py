@@ -84,6 +84,15 @@ class PlanClass(C.Structure):
     _fields_ = [("first", C.c_uint32), ("count", C.c_uint32), ("max_len", C.c_uint32)]
 
 
+class RecordTree(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("node_id", u64p), ("parent_id", C.POINTER(C.c_int64)), ("node_kind", u8p),
+                ("children_some", u8p), ("support", C.POINTER(C.c_double)), ("length", C.POINTER(C.c_double)),
+                ("has_name", u8p), ("name_off", u64p), ("names", C.c_char_p), ("child_off", u64p), ("child_idx", u64p),
+                ("has_annotations", C.c_uint32), ("reserved", C.c_uint32), ("n_annotations", C.c_uint64),
+                ("ann_clade", u64p), ("ann_yaml_off", u64p), ("ann_yaml", C.c_char_p), ("ann_json_off", u64p),
+                ("ann_json", C.c_char_p)]
+
+
 class ClsError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"classeq_b200 error {code}: {message}")
@@ -122,6 +131,9 @@ PROTOTYPES = {
     "cls_debug_node_counts": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(Params), C.POINTER(LevelCount), C.c_uint64, u64p,
                                         C.POINTER(Result)]),
     "cls_debug_host_murmur3_x64_128_h1": (C.c_uint64, [u8p, C.c_uint64, C.c_uint64]),
+    "cls_records_render": (C.c_int, [C.POINTER(RecordTree), C.c_uint64, u64p, C.c_char_p, C.POINTER(Result), C.c_uint32,
+                                     C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_void_p), u64p]),
+    "cls_text_free": (None, [C.c_void_p]),
     "cls_debug_plan_batch": (C.c_int, [C.c_uint32, C.POINTER(Batch), u8p, u32p, u32p, C.POINTER(PlanClass), C.c_uint32, u32p, u32p, u64p]),
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),
     "cls_filter_sequence": (C.c_uint64, [u8p, C.c_uint64, u8p, C.c_uint64]),

@@ -1,0 +1,419 @@
+// Native writer of the reference's result records: cls_result arrays + query headers + the Clade fields of the
+// tree -> the bytes `place_sequences` appends to `<out>.yaml|.jsonl` and `<out>.error`
+// (core/src/use_cases/place_sequences/mod.rs:160-249; PlacementResponse / PlacementStatus:
+// domain/dtos/placement_response.rs:7-94; AdherenceTest: adherence_test.rs:6-17; Clade: clade.rs:18-38;
+// the annotation join along the path to the root: mod.rs:180-224, clade.rs:95-125).
+// serde_yaml 0.9 block style and serde_json compact style are reproduced for this fixed record shape:
+// floats as the ryu crate prints them, strings quoted only where libyaml would quote them.  Host-only
+// (no CUDA): one block of records per task on the host pool, concatenated in input order.
+// The Python mirror (classeq2_b200/placement.py: placement_response + yaml_dump / json_dump) is the
+// second implementation; tests hold the two byte-identical, and both equal to a reference-written file.
+#include <algorithm>
+#include <charconv>
+#include <cstdio>
+#include <stdexcept>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/classeq_b200.h"
+#include "host_pool.hpp"
+
+namespace cls {
+int set_last_error(int code, const std::string &msg);  // capi.cu
+}
+
+namespace {
+
+// ---- f64 as serde_yaml / serde_json print it (the ryu crate): shortest round-trip digits, decimal notation for
+//      1e-5 <= |x| < 1e16, exponent form outside, a trailing ".0" on integral values in decimal notation ----------
+void ryu_float(double x, bool json, std::string &out) {
+    if (std::isnan(x)) { out += json ? "null" : ".nan"; return; }
+    if (std::isinf(x)) { out += json ? "null" : (x > 0 ? ".inf" : "-.inf"); return; }
+    if (x == 0) { out += std::signbit(x) ? "-0.0" : "0.0"; return; }
+    if (x < 0) { out += '-'; x = -x; }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);  // d[.ddd]e[+-]XX, shortest round trip
+    const char *e = static_cast<const char *>(memchr(buf, 'e', (size_t)(r.ptr - buf)));
+    std::string digits;
+    for (const char *p = buf; p < e; ++p)
+        if (*p != '.') digits += *p;
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int exp10 = atoi(std::string(e + 1, static_cast<const char *>(r.ptr)).c_str());
+    const int kk = exp10 + 1;  // value = 0.d1d2... * 10^kk
+    const int n = (int)digits.size();
+    if (0 < kk && kk <= 16) {
+        if (n <= kk) { out += digits; out.append((size_t)(kk - n), '0'); out += ".0"; }
+        else { out.append(digits, 0, (size_t)kk); out += '.'; out.append(digits, (size_t)kk, std::string::npos); }
+    } else if (-5 < kk && kk <= 0) {
+        out += "0."; out.append((size_t)(-kk), '0'); out += digits;
+    } else {
+        out += digits[0];
+        if (n > 1) { out += '.'; out.append(digits, 1, std::string::npos); }
+        out += 'e'; out += std::to_string(kk - 1);
+    }
+}
+
+// ---- strings ------------------------------------------------------------------------------------------------
+bool ieq(const std::string &s, const char *w) {
+    size_t i = 0;
+    for (; i < s.size() && w[i]; ++i)
+        if (tolower((unsigned char)s[i]) != w[i]) return false;
+    return i == s.size() && !w[i];
+}
+
+// Python's float(s.replace("_", "")) accepts the string (ASCII forms only)
+bool parses_as_float(const std::string &s0) {
+    std::string s;
+    for (char c : s0)
+        if (c != '_') s += c;
+    size_t i = 0;
+    if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
+    const std::string rest = s.substr(i);
+    if (ieq(rest, "inf") || ieq(rest, "infinity") || ieq(rest, "nan")) return true;
+    size_t nd = 0;
+    while (i < s.size() && isdigit((unsigned char)s[i])) { ++i; ++nd; }
+    if (i < s.size() && s[i] == '.') {
+        ++i;
+        while (i < s.size() && isdigit((unsigned char)s[i])) { ++i; ++nd; }
+    }
+    if (nd == 0) return false;
+    if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
+        ++i;
+        if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
+        size_t ne = 0;
+        while (i < s.size() && isdigit((unsigned char)s[i])) { ++i; ++ne; }
+        if (ne == 0) return false;
+    }
+    return i == s.size();
+}
+
+// str.strip() of the Python mirror: the code points for which str.isspace() holds
+bool is_space_cp(uint32_t c) {
+    return c == ' ' || (c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x1F) || c == 0x85 || c == 0xA0 || c == 0x1680 ||
+           (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+uint32_t decode_utf8(const unsigned char *p, size_t n) {   // first code point of p[0..n); malformed bytes stand for themselves
+    if (n >= 2 && (p[0] & 0xE0) == 0xC0) return ((p[0] & 0x1Fu) << 6) | (p[1] & 0x3Fu);
+    if (n >= 3 && (p[0] & 0xF0) == 0xE0) return ((p[0] & 0x0Fu) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3Fu);
+    if (n >= 4 && (p[0] & 0xF8) == 0xF0) return ((p[0] & 0x07u) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3Fu);
+    return p[0];
+}
+bool space_at_either_end(const std::string &s) {
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(s.data());
+    if (is_space_cp(decode_utf8(b, s.size()))) return true;
+    size_t i = s.size() - 1;
+    while (i > 0 && (b[i] & 0xC0) == 0x80) --i;   // back to the lead byte of the last code point
+    return is_space_cp(decode_utf8(b + i, s.size() - i));
+}
+
+// whether libyaml (hence serde_yaml) may emit the string as a plain scalar
+bool yaml_plain_ok(const std::string &s) {
+    if (s.empty() || space_at_either_end(s)) return false;
+    static const char special[] = "-?:,[]{}#&*!|>'\"%@`";
+    if (strchr(special, s[0]) && !(strchr("-?:", s[0]) && s.size() > 1 && s[1] != ' ' && s[1] != '\t')) return false;
+    if (s.find(": ") != std::string::npos || s.find(" #") != std::string::npos || s.back() == ':') return false;
+    for (unsigned char c : s)
+        if (c < 0x20 || c == 0x7F) return false;
+    static const char *words[] = {"null", "~", "true", "false", "yes", "no", "on", "off", "y", "n", ".nan", ".inf", "-.inf", "+.inf"};
+    for (const char *w : words)
+        if (ieq(s, w)) return false;
+    if (parses_as_float(s)) return false;
+    if (s.size() >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X' || s[1] == 'o' || s[1] == 'O')) return false;
+    if ((s[0] == '+' || s[0] == '-' || s[0] == '.') && s.size() > 1 && isdigit((unsigned char)s[1])) return false;
+    return true;
+}
+
+void yaml_string(const std::string &s, int indent, std::string &out) {
+    if (s.find('\n') != std::string::npos) {  // literal block scalar, serde_yaml's choice for multi-line strings
+        const bool keep = s.back() == '\n';
+        const std::string body = keep ? s.substr(0, s.size() - 1) : s;
+        out += keep ? "|" : "|-";
+        size_t a = 0;
+        for (;;) {
+            const size_t b = body.find('\n', a);
+            const std::string ln = body.substr(a, b == std::string::npos ? std::string::npos : b - a);
+            out += '\n';
+            if (!ln.empty()) { out.append((size_t)indent, ' '); out += ln; }
+            if (b == std::string::npos) break;
+            a = b + 1;
+        }
+        return;
+    }
+    if (yaml_plain_ok(s)) { out += s; return; }
+    const bool has_sq = s.find('\'') != std::string::npos, has_dq = s.find('"') != std::string::npos,
+               has_bs = s.find('\\') != std::string::npos;
+    if (!has_sq || has_dq || has_bs) {
+        out += '\'';
+        for (char c : s) { if (c == '\'') out += '\''; out += c; }
+        out += '\'';
+    } else {
+        out += '"';
+        for (char c : s) { if (c == '\\' || c == '"') out += '\\'; out += c; }
+        out += '"';
+    }
+}
+
+void json_string(const std::string &s, std::string &out) {  // serde_json: raw UTF-8, the short escapes, \u00XX for controls
+    out += '"';
+    char b[8];
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': out += "\\\""; break;
+            case '\\': out += "\\\\"; break;
+            case '\n': out += "\\n"; break;
+            case '\r': out += "\\r"; break;
+            case '\t': out += "\\t"; break;
+            case '\b': out += "\\b"; break;
+            case '\f': out += "\\f"; break;
+            default:
+                if (c < 0x20) { snprintf(b, sizeof b, "\\u%04x", c); out += b; }
+                else out += (char)c;
+        }
+    }
+    out += '"';
+}
+
+void rust_debug_str(const std::string &s, std::string &out) {  // format!("{:?}", String)
+    out += '"';
+    char b[16];
+    for (unsigned char c : s) {
+        if (c == '"') out += "\\\"";
+        else if (c == '\\') out += "\\\\";
+        else if (c == '\n') out += "\\n";
+        else if (c == '\r') out += "\\r";
+        else if (c == '\t') out += "\\t";
+        else if (c == 0) out += "\\0";
+        else if (c < 0x20 || c == 0x7F) { snprintf(b, sizeof b, "\\u{%x}", c); out += b; }
+        else out += (char)c;
+    }
+    out += '"';
+}
+
+const char *kind_name(uint8_t k) { return k == CLS_KIND_ROOT ? "ROOT" : k == CLS_KIND_LEAF ? "LEAF" : "NODE"; }
+
+struct TreeView {
+    const cls_record_tree *t;
+    std::unordered_map<uint64_t, uint64_t> by_id;  // Clade.id -> first node (pre-order) carrying it: get_node_by_id (clade.rs:95-109)
+    std::string name(uint64_t i) const { return std::string(t->names + t->name_off[i], t->names + t->name_off[i + 1]); }
+};
+
+// One Clade (clade.rs:18-38, serde camelCase, `None` name / support / length / children skipped, parent always present).
+// YAML: keys at column `indent`; `first` is what precedes the first key on its line (the padding, or "- " inside a list).
+void yaml_clade(const TreeView &tv, uint64_t i, int indent, const std::string &first, std::string &out) {
+    const cls_record_tree *t = tv.t;
+    const std::string pad((size_t)indent, ' ');
+    out += first; out += "id: "; out += std::to_string(t->node_id[i]); out += '\n';
+    out += pad; out += "parent: "; out += t->parent_id[i] < 0 ? std::string("null") : std::to_string(t->parent_id[i]); out += '\n';
+    out += pad; out += "kind: "; out += kind_name(t->node_kind[i]); out += '\n';
+    if (t->has_name[i]) { out += pad; out += "name: "; yaml_string(tv.name(i), indent + 2, out); out += '\n'; }
+    if (!std::isnan(t->support[i])) { out += pad; out += "support: "; ryu_float(t->support[i], false, out); out += '\n'; }
+    if (!std::isnan(t->length[i])) { out += pad; out += "length: "; ryu_float(t->length[i], false, out); out += '\n'; }
+    if (t->children_some[i]) {
+        const uint64_t a = t->child_off[i], b = t->child_off[i + 1];
+        if (a == b) { out += pad; out += "children: []\n"; }
+        else {
+            out += pad; out += "children:\n";   // serde_yaml does not indent sequences inside maps
+            for (uint64_t j = a; j < b; ++j) yaml_clade(tv, t->child_idx[j], indent + 2, pad + "- ", out);
+        }
+    }
+}
+
+void json_clade(const TreeView &tv, uint64_t i, std::string &out) {
+    const cls_record_tree *t = tv.t;
+    out += "{\"id\":"; out += std::to_string(t->node_id[i]);
+    out += ",\"parent\":"; out += t->parent_id[i] < 0 ? std::string("null") : std::to_string(t->parent_id[i]);
+    out += ",\"kind\":\""; out += kind_name(t->node_kind[i]); out += '"';
+    if (t->has_name[i]) { out += ",\"name\":"; json_string(tv.name(i), out); }
+    if (!std::isnan(t->support[i])) { out += ",\"support\":"; ryu_float(t->support[i], true, out); }
+    if (!std::isnan(t->length[i])) { out += ",\"length\":"; ryu_float(t->length[i], true, out); }
+    if (t->children_some[i]) {
+        out += ",\"children\":[";
+        for (uint64_t j = t->child_off[i]; j < t->child_off[i + 1]; ++j) {
+            if (j > t->child_off[i]) out += ',';
+            json_clade(tv, t->child_idx[j], out);
+        }
+        out += ']';
+    }
+    out += '}';
+}
+
+// Annotations of the clades on the path to the root (mod.rs:180-224): get_path_to_root (clade.rs:111-125) follows the
+// Clade.parent FIELDS from the first pre-order node with that id; records keep their file order among equal clades.
+void annotations_for(const TreeView &tv, uint64_t clade_id, std::vector<uint64_t> &picked) {
+    picked.clear();
+    const cls_record_tree *t = tv.t;
+    if (!t->n_annotations) return;
+    std::vector<uint64_t> path;
+    auto it = tv.by_id.find(clade_id);
+    uint64_t hops = 0;
+    while (it != tv.by_id.end() && hops <= t->n_nodes) {
+        path.push_back(it->first);
+        const int64_t p = t->parent_id[it->second];
+        if (p < 0) break;
+        path.push_back((uint64_t)p);
+        it = tv.by_id.find((uint64_t)p);
+        ++hops;
+    }
+    for (uint64_t a = 0; a < t->n_annotations; ++a)
+        for (uint64_t id : path)
+            if (t->ann_clade[a] == id) { picked.push_back(a); break; }
+    std::stable_sort(picked.begin(), picked.end(), [&](uint64_t x, uint64_t y) { return t->ann_clade[x] < t->ann_clade[y]; });
+}
+
+const char kErrTooShort[] = "The sequence does not contain enough kmers.";                        // place_sequence.rs:98-102
+const char kErrMaxIter[] = "The maximum number of iterations has been reached.";                  // :295-301
+const char kErrRootNoChildren[] = "The root node does not have children. This is unexpected.";    // :199-206
+const char kErrInvalidBase[] = "Invalid character in sequence";                                   // kmers_map.rs:440 (a panic there)
+const char kMsgNoRoot[] = "Query sequence has no overlapping kmers with the reference tree";       // :156-166
+const char kMsgNoIntrospection[] =
+    "Tree introspection not possible. Query sequence has no overlapping kmers with the reference tree";  // :446-454
+
+// One query: appends its record to `out` or its error text to `err`.  Returns false on an unknown status / node id.
+// Rendered Clade blocks by node: a batch places many reads on few clades, so a task renders each of them once.
+using CladeCache = std::unordered_map<uint64_t, std::string>;
+
+bool render_one(const TreeView &tv, const std::string &header, const cls_result *r, uint64_t i, bool yaml, std::string &out,
+                std::string &err, std::vector<uint64_t> &scratch, CladeCache &clade_text) {
+    const uint8_t st = r->status[i];
+    std::string code;
+    switch (st) {
+        case CLS_STATUS_ERR_TOO_SHORT: err += kErrTooShort; return true;
+        case CLS_STATUS_ERR_MAX_ITERATIONS: err += kErrMaxIter; return true;
+        case CLS_STATUS_ERR_ROOT_NO_CHILDREN: err += kErrRootNoChildren; return true;
+        case CLS_STATUS_ERR_INVALID_BASE: err += kErrInvalidBase; return true;
+        case CLS_STATUS_UNCL_NO_MATCH:
+            code = "Unclassifiable: Query sequence SequenceHeader("; rust_debug_str(header, code); code += ") may not be related to the phylogeny";
+            break;
+        case CLS_STATUS_UNCL_NO_ROOT: code = std::string("Unclassifiable: ") + kMsgNoRoot; break;
+        case CLS_STATUS_UNCL_COVERAGE: code = "Unclassifiable: Insufficient kmers coverage: " + std::to_string(r->n_root_matched ? r->n_root_matched[i] : 0u); break;
+        case CLS_STATUS_UNCL_NO_INTROSPECTION: code = std::string("Unclassifiable: ") + kMsgNoIntrospection; break;
+        case CLS_STATUS_MAX_RESOLUTION: code = "MaxResolutionReached: LCA Accepted"; break;
+        case CLS_STATUS_IDENTITY_FOUND: code = "IdentityFound"; break;
+        case CLS_STATUS_INCONCLUSIVE: code = "Inconclusive: Multiple proposals"; break;
+        default: return false;
+    }
+    const bool identity = st == CLS_STATUS_IDENTITY_FOUND, max_res = st == CLS_STATUS_MAX_RESOLUTION;
+    uint64_t node = 0;
+    if (identity) {
+        auto it = tv.by_id.find(r->node_id[i]);
+        if (it == tv.by_id.end()) return false;
+        node = it->second;
+    }
+    if (tv.t->has_annotations && (identity || max_res)) annotations_for(tv, r->node_id[i], scratch); else scratch.clear();
+    const cls_record_tree *t = tv.t;
+    if (yaml) {
+        out += "---\nquery: "; yaml_string(header, 2, out);
+        out += "\ncode: "; yaml_string(code, 2, out); out += '\n';
+        if (!scratch.empty()) {
+            out += "annotations:\n";
+            for (uint64_t a : scratch) out.append(t->ann_yaml + t->ann_yaml_off[a], t->ann_yaml + t->ann_yaml_off[a + 1]);
+        }
+        if (identity) {
+            out += "placement:\n  clade:\n";
+            auto c = clade_text.find(node);
+            if (c == clade_text.end()) { std::string t2; yaml_clade(tv, node, 4, "    ", t2); c = clade_text.emplace(node, std::move(t2)).first; }
+            out += c->second;
+            out += "  one: "; out += std::to_string(r->one[i]); out += "\n  rest: "; out += std::to_string(r->rest[i]); out += '\n';
+        } else if (max_res) {
+            out += "placement: "; out += std::to_string(r->node_id[i]); out += '\n';
+        } else if (st == CLS_STATUS_INCONCLUSIVE) {
+            out += "placement: "; yaml_string(code, 2, out); out += '\n';
+        }
+    } else {
+        out += "{\"query\":"; json_string(header, out);
+        out += ",\"code\":"; json_string(code, out);
+        if (!scratch.empty()) {
+            out += ",\"annotations\":[";
+            for (size_t k = 0; k < scratch.size(); ++k) {
+                if (k) out += ',';
+                out.append(t->ann_json + t->ann_json_off[scratch[k]], t->ann_json + t->ann_json_off[scratch[k] + 1]);
+            }
+            out += ']';
+        }
+        if (identity) {
+            out += ",\"placement\":{\"clade\":";
+            auto c = clade_text.find(node);
+            if (c == clade_text.end()) { std::string t2; json_clade(tv, node, t2); c = clade_text.emplace(node, std::move(t2)).first; }
+            out += c->second;
+            out += ",\"one\":"; out += std::to_string(r->one[i]); out += ",\"rest\":"; out += std::to_string(r->rest[i]); out += '}';
+        } else if (max_res) {
+            out += ",\"placement\":"; out += std::to_string(r->node_id[i]);
+        } else if (st == CLS_STATUS_INCONCLUSIVE) {
+            out += ",\"placement\":"; json_string(code, out);
+        }
+        out += "}\n";
+    }
+    return true;
+}
+
+char *to_malloc(const std::vector<std::string> &parts, uint64_t *len) {
+    size_t n = 0;
+    for (const auto &p : parts) n += p.size();
+    char *buf = static_cast<char *>(malloc(n + 1));
+    if (!buf) return nullptr;
+    size_t at = 0;
+    for (const auto &p : parts) { memcpy(buf + at, p.data(), p.size()); at += p.size(); }
+    buf[n] = 0;
+    *len = n;
+    return buf;
+}
+
+int render(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, const char *headers, const cls_result *res,
+           uint32_t format, char **out_text, uint64_t *out_len, char **err_text, uint64_t *err_len) {
+    using cls::set_last_error;
+    if (!tree || !res || !out_text || !out_len || !err_text || !err_len || (n && (!header_off || !headers)))
+        return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out_text = *err_text = nullptr;
+    *out_len = *err_len = 0;
+    if (format > 1) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "format must be 0 (yaml) or 1 (jsonl)");
+    if (n && (!res->status || !res->node_id || !res->one || !res->rest)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "result arrays are NULL");
+    TreeView tv{tree, {}};
+    tv.by_id.reserve(tree->n_nodes * 2);
+    for (uint64_t i = 0; i < tree->n_nodes; ++i) tv.by_id.emplace(tree->node_id[i], i);   // emplace keeps the first
+    constexpr uint64_t kBlock = 2048;
+    const uint64_t nblk = (n + kBlock - 1) / kBlock;
+    std::vector<std::string> outs(nblk), errs(nblk);
+    std::vector<uint8_t> bad(nblk, 0);
+    cls::parallel_for(nblk, 1, [&](uint64_t b0, uint64_t b1) {
+        std::vector<uint64_t> scratch;
+        CladeCache clade_text;
+        for (uint64_t b = b0; b < b1; ++b) {
+            std::string &o = outs[b], &e = errs[b];
+            const uint64_t hi = std::min(n, (b + 1) * kBlock);
+            for (uint64_t i = b * kBlock; i < hi; ++i) {
+                const std::string header(headers + header_off[i], headers + header_off[i + 1]);
+                if (!render_one(tv, header, res, i, format == 0, o, e, scratch, clade_text)) bad[b] = 1;
+            }
+        }
+    });
+    for (uint8_t x : bad)
+        if (x) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "unknown status, or a placement node id that is not in the tree");
+    *out_text = to_malloc(outs, out_len);
+    *err_text = to_malloc(errs, err_len);
+    if (!*out_text || !*err_text) {
+        free(*out_text); free(*err_text);
+        *out_text = *err_text = nullptr;
+        return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation of the rendered records failed");
+    }
+    return CLS_OK;
+}
+
+}  // namespace
+
+extern "C" int cls_records_render(const cls_record_tree *tree, uint64_t n_queries, const uint64_t *header_off, const char *headers,
+                                  const cls_result *result, uint32_t format, char **out_text, uint64_t *out_len, char **err_text,
+                                  uint64_t *err_len) {
+    try {
+        return render(tree, n_queries, header_off, headers, result, format, out_text, out_len, err_text, err_len);
+    } catch (const std::bad_alloc &) {
+        return cls::set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while rendering records");
+    } catch (const std::exception &e) {
+        return cls::set_last_error(CLS_ERR_INVALID_ARGUMENT, std::string("cls_records_render: ") + e.what());
+    }
+}
+
+extern "C" void cls_text_free(char *p) { free(p); }

@@ -12,7 +12,8 @@ Reference (paths relative to its checkout):
 Same argument meaning, same output files (``<out>.yaml|.jsonl`` and ``<out>.error``), same record
 shape and strings.  The per-query algorithm (the body of the ``par_bridge`` closure's call to
 ``place_sequence``, mod.rs:151-159) runs on the GPU through ``cls_place_batch``; this module only
-parses, batches and serialises.  Records are written in input order (the reference's order is the
+parses and batches; the records are serialised by the library's native writer (``cls_records_render``) or, as a
+cross-check, by the emitters below.  Records are written in input order (the reference's order is the
 nondeterministic completion order of its rayon tasks - compare outputs as maps keyed by query).
 """
 from __future__ import annotations
@@ -372,6 +373,76 @@ def placement_response(header: str, row: dict, tree: Tree, lookup: Optional[_Tre
     return o, None
 
 
+class RecordTree:
+    """The serde fields of every clade of a tree (+ its annotations, rendered once) as the flat arrays of
+    ``cls_record_tree``: what the library's native record writer ``cls_records_render`` needs."""
+
+    def __init__(self, tree: Tree):
+        clades, node_id, node_kind, child_off, child_idx = FlatModel.tree_arrays(tree.root)
+        n = len(clades)
+        nan = float("nan")
+        self.node_id, self.node_kind = node_id, node_kind
+        self.child_off, self.child_idx = child_off, (child_idx if len(child_idx) else np.zeros(1, np.uint64))
+        self.parent_id = np.array([-1 if c.parent is None else c.parent for c in clades], np.int64)
+        self.children_some = np.array([c.children is not None for c in clades], np.uint8)
+        self.support = np.array([nan if c.support is None else c.support for c in clades], np.float64)
+        self.length = np.array([nan if c.length is None else c.length for c in clades], np.float64)
+        self.has_name = np.array([c.name is not None for c in clades], np.uint8)
+        names = [(c.name or "").encode("utf-8") for c in clades]
+        self.name_off = np.zeros(n + 1, np.uint64)
+        self.name_off[1:] = np.cumsum([len(x) for x in names])
+        self.names = b"".join(names)
+        ann = tree.annotations or []
+        ys = [yaml_dump([a]).encode("utf-8") for a in ann]
+        js = [json_dump(a).encode("utf-8") for a in ann]
+        self.ann_clade = np.array([int(a["clade"]) for a in ann] or [0], np.uint64)
+        self.ann_yaml_off, self.ann_json_off = np.zeros(len(ann) + 1, np.uint64), np.zeros(len(ann) + 1, np.uint64)
+        if ann:
+            self.ann_yaml_off[1:] = np.cumsum([len(x) for x in ys])
+            self.ann_json_off[1:] = np.cumsum([len(x) for x in js])
+        self.ann_yaml, self.ann_json = b"".join(ys), b"".join(js)
+        v = self.view = _lib.RecordTree()
+        v.n_nodes = n
+        v.node_id, v.node_kind = _p(self.node_id, _lib.u64p), _p(self.node_kind, _lib.u8p)
+        v.parent_id = self.parent_id.ctypes.data_as(C.POINTER(C.c_int64))
+        v.children_some, v.has_name = _p(self.children_some, _lib.u8p), _p(self.has_name, _lib.u8p)
+        v.support = self.support.ctypes.data_as(C.POINTER(C.c_double))
+        v.length = self.length.ctypes.data_as(C.POINTER(C.c_double))
+        v.name_off, v.names = _p(self.name_off, _lib.u64p), self.names
+        v.child_off, v.child_idx = _p(self.child_off, _lib.u64p), _p(self.child_idx, _lib.u64p)
+        v.has_annotations = 0 if tree.annotations is None else 1
+        v.n_annotations = len(ann)
+        v.ann_clade = _p(self.ann_clade, _lib.u64p)
+        v.ann_yaml_off, v.ann_yaml = _p(self.ann_yaml_off, _lib.u64p), self.ann_yaml
+        v.ann_json_off, v.ann_json = _p(self.ann_json_off, _lib.u64p), self.ann_json
+
+
+def _p(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+def render_records(headers: List[str], res: BatchResult, rtree: RecordTree, output_format: str = "yaml") -> Tuple[bytes, bytes]:
+    """``cls_records_render``: the bytes the reference appends to ``<out>.yaml|.jsonl`` and to ``<out>.error`` for a
+    batch, written by the library (multi-threaded C++) - byte-identical to :func:`placement_response` +
+    :func:`yaml_dump` / :func:`json_dump` record by record."""
+    hb = [h.encode("utf-8") for h in headers]
+    off = np.zeros(len(hb) + 1, np.uint64)
+    if hb:
+        off[1:] = np.cumsum([len(x) for x in hb])
+    text = b"".join(hb)
+    out, err = C.c_void_p(), C.c_void_p()
+    n_out, n_err = C.c_uint64(), C.c_uint64()
+    cr = res.to_c()
+    _lib.check(_lib.lib.cls_records_render(C.byref(rtree.view), len(hb), _p(off, _lib.u64p), text, C.byref(cr),
+                                           0 if output_format == "yaml" else 1, C.byref(out), C.byref(n_out),
+                                           C.byref(err), C.byref(n_err)))
+    try:
+        return C.string_at(out, n_out.value), C.string_at(err, n_err.value)
+    finally:
+        _lib.lib.cls_text_free(out)
+        _lib.lib.cls_text_free(err)
+
+
 @dataclass
 class PlacementTime:
     """place_sequences/mod.rs:30-34 - at batch granularity the per-sequence time is the batch's
@@ -483,7 +554,8 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                     max_iterations: Optional[int] = None, min_match_coverage: Optional[float] = None,
                     overwrite: bool = False, output_format: str = "yaml",
                     remove_intersection: Optional[bool] = None, *, index: Optional[Index] = None,
-                    device: int = 0, batch_size: int = 1 << 20, ingest: str = "host") -> List[PlacementTime]:
+                    device: int = 0, batch_size: int = 1 << 20, ingest: str = "host",
+                    writer: str = "native") -> List[PlacementTime]:
     """Place every sequence of a FASTA input on ``tree`` and append one record per query to
     ``<out_file>.yaml|.jsonl`` (errors to ``<out_file>.error``), as the reference does.
 
@@ -491,7 +563,11 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
     right after ``load_database``); otherwise the model is uploaded for this call.
     ``ingest="device"`` parses, filters and packs the FASTA text on the GPU (``cls_fasta_upload``; file paths
     only, ASCII only) instead of with the host reader; the records and results are identical.
+    ``writer="native"`` (default) serialises the records in the library (``cls_records_render``, multi-threaded C++);
+    ``writer="python"`` uses this module's emitters - the two write byte-identical files (tests/test_record_writer.py).
     """
+    if writer not in ("native", "python"):
+        raise ValueError("writer must be 'native' or 'python'")
     if ingest not in ("host", "device"):
         raise ValueError("ingest must be 'host' or 'device'")
     if output_format not in ("yaml", "jsonl"):
@@ -525,11 +601,12 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
         batch_size = max(len(records), 1)
     else:
         records = read_fasta(query_sequence)
-    lookup = _TreeLookup(tree)
+    lookup = _TreeLookup(tree) if writer == "python" else None
+    rtree = RecordTree(tree) if writer == "native" else None
     params = PlaceParams(max_iterations, min_match_coverage, remove_intersection)
     times: List[PlacementTime] = []
     try:
-        with open(out_path, "a", encoding="utf-8") as fo, open(err_path, "a", encoding="utf-8") as fe:
+        with open(out_path, "ab") as fo, open(err_path, "ab") as fe:
             for a in range(0, len(records), batch_size):
                 chunk = records[a:a + batch_size]
                 t0 = time.perf_counter()
@@ -539,18 +616,23 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                 else:
                     res = index.place_batch([s for _, s in chunk], params)
                 per_seq_ms = (time.perf_counter() - t0) * 1e3 / max(len(chunk), 1)
-                buf_o, buf_e = [], []
-                for i, (header, _) in enumerate(chunk):
-                    obj, err = placement_response(header, res.row(i), tree, lookup)
-                    if err is not None:
-                        buf_e.append(err)                                    # err.to_string() (:160-169)
-                    elif output_format == "yaml":
-                        buf_o.append("---\n" + yaml_dump(obj))
-                    else:
-                        buf_o.append(json_dump(obj) + "\n")
-                    times.append(PlacementTime(header, per_seq_ms))
-                fo.write("".join(buf_o))
-                fe.write("".join(buf_e))
+                if rtree is not None:
+                    text_o, text_e = render_records([h for h, _ in chunk], res, rtree, output_format)
+                    times.extend(PlacementTime(header, per_seq_ms) for header, _ in chunk)
+                else:
+                    buf_o, buf_e = [], []
+                    for i, (header, _) in enumerate(chunk):
+                        obj, err = placement_response(header, res.row(i), tree, lookup)
+                        if err is not None:
+                            buf_e.append(err)                                # err.to_string() (:160-169)
+                        elif output_format == "yaml":
+                            buf_o.append("---\n" + yaml_dump(obj))
+                        else:
+                            buf_o.append(json_dump(obj) + "\n")
+                        times.append(PlacementTime(header, per_seq_ms))
+                    text_o, text_e = "".join(buf_o).encode("utf-8"), "".join(buf_e).encode("utf-8")
+                fo.write(text_o)
+                fe.write(text_e)
     finally:
         if device_batch is not None:
             device_batch.close()

@@ -353,6 +353,48 @@ uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, ui
 int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int variant);
 
 /*
+ * Native writer of the reference's result records (no GPU needed): what `place_sequences` appends to
+ * `<out>.yaml|.jsonl` and `<out>.error` for every query (place_sequences/mod.rs:160-249), from the cls_result arrays
+ * of a batch, the query headers and the serde fields of the tree's clades (clade.rs:18-38):
+ *   Err statuses            -> the error text, appended to `err_text`
+ *   Unclassifiable          -> {query, code}                                   (placement omitted, mod.rs:174-177)
+ *   MaxResolutionReached    -> {query, code, annotations?, placement: <clade id>}
+ *   IdentityFound           -> {query, code, annotations?, placement: {clade: <full Clade incl. children>, one, rest}}
+ * `annotations` = the tree's annotations whose clade lies on the path to the root of the placement clade
+ * (clade.rs:95-125), sorted by clade (mod.rs:180-224); every annotation is handed over ALREADY RENDERED, once per
+ * tree, as the YAML list item ("- clade: 45\n  meta:\n  - !Taxid 1452\n") and as the JSON object.
+ * format 0: serde_yaml documents ("---\n" + block style), 1: serde_json lines.  Nodes come in the order of
+ * cls_model_view (node 0 = root).  NaN support / length = None; parent_id < 0 = None.
+ * The two texts are malloc'ed by the library: release them with cls_text_free.
+ */
+typedef struct cls_record_tree {
+    uint64_t n_nodes;
+    const uint64_t *node_id;         /* Clade.id                                            */
+    const int64_t *parent_id;        /* Clade.parent, -1 = None                             */
+    const uint8_t *node_kind;        /* CLS_KIND_*                                          */
+    const uint8_t *children_some;    /* Clade.children is Some(..) (possibly empty)         */
+    const double *support;           /* NaN = None                                          */
+    const double *length;            /* NaN = None                                          */
+    const uint8_t *has_name;         /* Clade.name is Some                                  */
+    const uint64_t *name_off;        /* [n_nodes+1] byte offsets into names                 */
+    const char *names;               /* UTF-8, not terminated                               */
+    const uint64_t *child_off;       /* [n_nodes+1] CSR over child_idx, as in cls_model_view */
+    const uint64_t *child_idx;
+    uint32_t has_annotations;        /* Tree.annotations is Some                            */
+    uint32_t reserved;
+    uint64_t n_annotations;
+    const uint64_t *ann_clade;       /* [n_annotations] Annotation.clade                    */
+    const uint64_t *ann_yaml_off;    /* [n_annotations+1] into ann_yaml                     */
+    const char *ann_yaml;
+    const uint64_t *ann_json_off;    /* [n_annotations+1] into ann_json                     */
+    const char *ann_json;
+} cls_record_tree;
+int cls_records_render(const cls_record_tree *tree, uint64_t n_queries, const uint64_t *header_off, const char *headers,
+                       const cls_result *result, uint32_t format, char **out_text, uint64_t *out_len, char **err_text,
+                       uint64_t *err_len);
+void cls_text_free(char *text);
+
+/*
  * cls_debug_plan_batch: the host-side planner of cls_place_batch / cls_batch_upload on its own (no GPU needed):
  * queries shorter than k get their status on the host (pre_status[i] = CLS_STATUS_ERR_TOO_SHORT, else 0xFF), the
  * others are grouped into LENGTH CLASSES - all reads of a class share one per-read table geometry; longest class

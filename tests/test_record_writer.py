@@ -1,0 +1,204 @@
+"""The library's native record writer ``cls_records_render`` (classeq2_b200/csrc/record_writer.cpp) against the Python
+mirror (placement_response + yaml_dump / json_dump), byte for byte, and against a file the reference itself wrote.
+No GPU: results are made up from statuses."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import yaml
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ps():
+    from classeq2_b200 import placement
+    return placement
+
+
+def _python_render(ps, headers, res, tree, fmt):
+    lookup = ps._TreeLookup(tree)
+    out, err = [], []
+    for i, h in enumerate(headers):
+        obj, e = ps.placement_response(h, res.row(i), tree, lookup)
+        if e is not None:
+            err.append(e)
+        elif fmt == "yaml":
+            out.append("---\n" + ps.yaml_dump(obj))
+        else:
+            out.append(ps.json_dump(obj) + "\n")
+    return "".join(out).encode("utf-8"), "".join(err).encode("utf-8")
+
+
+def _check(ps, headers, res, tree):
+    rt = ps.RecordTree(tree)
+    for fmt in ("yaml", "jsonl"):
+        want = _python_render(ps, headers, res, tree, fmt)
+        got = ps.render_records(headers, res, rt, fmt)
+        assert got[0] == want[0], (fmt, _first_diff(got[0], want[0]))
+        assert got[1] == want[1]
+    return got
+
+
+def _first_diff(a, b):
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x != y:
+            return i, a[max(0, i - 60):i + 30], b[max(0, i - 60):i + 30]
+    return len(a), len(b)
+
+
+def test_reference_written_file_is_reproduced(ps):
+    """tests/golden/gyrb_result_v090.yaml (written by the reference, v0.9.0) from (status, node, one, rest) + the
+    tree-only model + the annotations file, by the native writer."""
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib, Clade, Tree
+    root = Clade.from_obj(yaml.load(open(os.path.join(GOLDEN, "bsub-gyrb-k35.tree-only.cls.yaml")), Loader=yaml.CSafeLoader))
+    tree = Tree("ce47d8bc-2885-3d2c-8247-5b8c8b28fefe", "bsub", 70.0, root)
+    tree.annotations = ps.load_annotations(os.path.join(GOLDEN, "bsub-gyrb-annotations.yaml"))
+    text = open(os.path.join(GOLDEN, "gyrb_result_v090.yaml")).read()
+    docs = list(yaml.safe_load_all(re.sub(r"!\w+ ", "", text)))
+    res, headers = cq.BatchResult(len(docs)), []
+    for i, o in enumerate(docs):
+        headers.append(o["query"])
+        if o["code"] == "IdentityFound":
+            res.status[i], res.node_id[i] = _lib.STATUS_IDENTITY_FOUND, o["placement"]["clade"]["id"]
+            res.one[i], res.rest[i] = o["placement"]["one"], o["placement"]["rest"]
+        else:
+            res.status[i], res.node_id[i] = _lib.STATUS_MAX_RESOLUTION, o["placement"]
+    out, err = _check(ps, headers, res, tree)
+    assert ps.render_records(headers, res, ps.RecordTree(tree), "yaml")[0].decode() == text and err == b""
+    for line in ps.render_records(headers, res, ps.RecordTree(tree), "jsonl")[0].decode().splitlines():
+        assert list(json.loads(line).keys()) == ["query", "code", "annotations", "placement"]
+
+
+def test_every_status_on_the_colletotrichum_outcomes(ps, col_tree, col_queries, col_expected):
+    import classeq2_b200 as cq
+    from helpers import expected_row
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    headers = [h for h, _ in col_queries]
+    by_header = dict(zip(col_expected["queries"], col_expected["outcomes"]["default"]))
+    res = cq.BatchResult(len(headers))
+    for i, h in enumerate(headers):
+        row = expected_row(by_header[h])
+        for k, v in row.items():
+            getattr(res, k)[i] = v
+    for ann in (None, [], [{"clade": 0, "meta": [ps.Tag("Taxid", 5), ps.Tag("SciName", "x: y")]}, {"clade": 18}, {"clade": 1},
+                           {"clade": 999999}, {"clade": 0, "meta": [ps.Tag("Note", "two\nlines\n")]}]):
+        tree.annotations = ann
+        out, err = _check(ps, headers, res, tree)
+        assert out.count(b"---\n") + err.count(b".") >= 1
+    # every cls_status, including the ones the fixture does not produce
+    res2 = cq.BatchResult(11)
+    res2.status[:] = np.arange(11)
+    res2.node_id[:] = 18
+    res2.n_root_matched[:] = 7
+    _check(ps, [f"q{i}" for i in range(11)], res2, tree)
+
+
+def test_adversarial_strings_floats_and_tree_shapes(ps):
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib, Clade, Tree
+    names = ["plain", "with space", " lead", "trail ", "a: b", "a #b", "key:", "-dash", "- dash", "?q", ":c", "null", "Null", "~", "true",
+             "YES", "no", "123", "1_000", "-1.5", ".5", "5.", "1e5", "0x1F", "0o7", "+.inf", ".nan", "inf", "nan", "it's", 'say "hi"',
+             "back\\slash", "it's \"both\"", "tab\there", "ctl\x01", "del\x7f", "two\nlines", "ends\n", "\n", "é", "日本語", " nbsp",
+             "nbsp ", "[list]", "{map}", "#c", "&a", "*a", "!t", "|p", ">f", "'q", "\"q", "%p", "@a", "`b", ",c", "a,b", "e5", "1e", "_", "1__0",
+             "", "0", "-", "--", "-?", "?", ":", "..", "+1", "-x", ".x", "a\rb", "x y", "　wide"]
+    floats = [0.0, -0.0, 1.0, 72.0, 1e-6, 1e-5, 9.999e-6, 0.000619153, 123456.789, 1e15, 1e16, 1.5e16, 1.7976931348623157e308, 5e-324, -3.25,
+              0.1, 1 / 3, 100.0, 1e21, 12345678901234567.0, float("inf"), 2.5e-7]
+    kids = []
+    for i, nm in enumerate(names):
+        sup = floats[i % len(floats)] if i % 3 else None
+        kids.append(Clade(id=10 + i, parent=(1 if i % 2 else None), kind="LEAF" if i % 4 else "NODE", name=nm, support=sup,
+                          length=floats[(i + 5) % len(floats)] if i % 5 else None, children=([] if i % 7 == 0 else None)))
+    inner = Clade(id=1, parent=0, kind="NODE", support=99.5, length=0.25, children=kids)
+    dup = Clade(id=1, parent=0, kind="NODE", name="second node with id 1", children=None)     # get_node_by_id: the first one wins
+    root = Clade(id=0, parent=None, kind="ROOT", length=0.0, children=[inner, dup])
+    tree = Tree("t", "t", 70.0, root)
+    tree.annotations = [{"clade": 1, "meta": [ps.Tag("SciName", nm) for nm in names[:12]]}, {"clade": 0}, {"clade": 10}]
+    n = len(names) + 6
+    res = cq.BatchResult(n)
+    headers = []
+    for i in range(n):
+        headers.append(names[i % len(names)])
+        res.status[i] = _lib.STATUS_IDENTITY_FOUND if i % 3 == 0 else (_lib.STATUS_UNCL_NO_MATCH if i % 3 == 1 else _lib.STATUS_MAX_RESOLUTION)
+        res.node_id[i] = [1, 10 + (i % len(names)), 0][i % 3] if i % 3 != 2 else [1, 4242, 10][i % 3]
+        res.one[i], res.rest[i] = i * 7, i
+    _check(ps, headers, res, tree)
+    # an IdentityFound whose node is not in the tree is an error, not a guess
+    bad = cq.BatchResult(1)
+    bad.status[0], bad.node_id[0] = _lib.STATUS_IDENTITY_FOUND, 424242
+    with pytest.raises(_lib.ClsError):
+        ps.render_records(["q"], bad, ps.RecordTree(tree), "yaml")
+
+
+def test_many_records_keep_their_order(ps, col_tree):
+    """More records than one writer block (2 048): blocks are rendered on the host pool and joined in input order."""
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    ids = [c.id for c in tree.root.walk() if not c.is_leaf()]
+    n = 20_000
+    rng = np.random.default_rng(1)
+    res = cq.BatchResult(n)
+    res.status[:] = rng.choice([_lib.STATUS_IDENTITY_FOUND, _lib.STATUS_MAX_RESOLUTION, _lib.STATUS_UNCL_COVERAGE, _lib.STATUS_ERR_TOO_SHORT,
+                                _lib.STATUS_UNCL_NO_MATCH], n)
+    res.node_id[:] = rng.choice(ids, n)
+    res.one[:] = rng.integers(0, 500, n)
+    res.n_root_matched[:] = rng.integers(0, 500, n)
+    _check(ps, [f"read_{i}" for i in range(n)], res, tree)
+
+
+class _OracleIndex:
+    """Stands in for ``Index`` so that ``place_sequences`` runs without a GPU: the batch is placed by the C++ oracle
+    (test infrastructure).  Everything else - FASTA reader, batching, record writers, files - is the product's."""
+
+    def __init__(self, flat):
+        from oracle import cpp_oracle
+        self.md = cpp_oracle.CppModel.from_flat(flat)
+
+    def place_batch(self, seqs, params=None):
+        import classeq2_b200 as cq
+        bases, offsets = cq.make_batch(seqs)
+        p = params or cq.PlaceParams()
+        out = self.md.place_batch(bases, offsets, p.max_iterations, p.min_match_coverage, p.remove_intersection, n_threads=4)
+        res = cq.BatchResult(len(offsets) - 1)
+        for name, _ in cq.engine.RESULT_DTYPES:
+            getattr(res, name)[:] = out[name]
+        return res
+
+    def close(self):
+        self.md.close()
+
+
+@pytest.mark.parametrize("fmt", ["yaml", "jsonl"])
+def test_place_sequences_files_with_both_writers(ps, tmp_path, col_tree, col_flat, col_expected, fmt):
+    """The whole host side of place_sequences (reader -> batches -> records -> result / error files) around an oracle
+    placement: the native and the Python writer give the same bytes, and every record is the oracle's response."""
+    import hashlib
+    import classeq2_b200 as cq
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    index = _OracleIndex(col_flat)
+    fa = os.path.join(GOLDEN, "colletotrichum_queries.fasta")
+    a, b = tmp_path / "n" / "r", tmp_path / "p" / "r"
+    cq.place_sequences(fa, tree, a, output_format=fmt, index=index, writer="native", batch_size=100)
+    cq.place_sequences(fa, tree, b, output_format=fmt, index=index, writer="python", batch_size=1 << 20)
+    index.close()
+    text = (tmp_path / "n" / f"r.{fmt}").read_bytes()
+    assert text == (tmp_path / "p" / f"r.{fmt}").read_bytes() and len(text) > 10000
+    assert (tmp_path / "n" / "r.error").read_bytes() == (tmp_path / "p" / "r.error").read_bytes()
+    recs = [json.loads(ln) for ln in text.decode().splitlines()] if fmt == "jsonl" else \
+        [_floats(o) for o in yaml.safe_load_all(text.decode())]
+    want = dict(zip(col_expected["queries"], col_expected["outcomes"]["default"]))
+    assert len(recs) == sum(1 for e in want.values() if "error" not in e)
+    for r in recs:
+        assert hashlib.sha1(json.dumps(r, sort_keys=True).encode()).hexdigest() == want[r["query"]]["response_sha1"], r["query"]
+
+
+def _floats(o):
+    if isinstance(o, dict):
+        return {k: (float(v) if k in ("length", "support") and v is not None else _floats(v)) for k, v in o.items()}
+    if isinstance(o, list):
+        return [_floats(v) for v in o]
+    return o

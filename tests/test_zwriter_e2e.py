@@ -1,0 +1,28 @@
+"""place_sequences end to end with the library's native record writer against the Python emitters: the two runs write
+byte-identical result and error files (YAML and JSON lines, with annotations).  The writer itself is covered without a
+GPU in tests/test_record_writer.py; this file sorts last among the GPU tests on purpose."""
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("fmt", ["yaml", "jsonl"])
+def test_native_and_python_writers_write_the_same_files(tmp_path, col_tree, fmt):
+    import classeq2_b200 as cq
+    from classeq2_b200 import placement as ps
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    tree.annotations = [{"clade": 0, "meta": [ps.Tag("SciName", "Colletotrichum acutatum complex"), ps.Tag("Taxid", 27357)]},
+                        {"clade": 18, "meta": [ps.Tag("Note", "two\nlines\n")]}, {"clade": 1}]
+    fa = os.path.join(GOLDEN, "colletotrichum_queries.fasta")
+    index = cq.Index(tree, device=0)
+    a, b = tmp_path / "n" / "r", tmp_path / "p" / "r"
+    ta = cq.place_sequences(fa, tree, a, output_format=fmt, index=index, writer="native")
+    tb = cq.place_sequences(fa, tree, b, output_format=fmt, index=index, writer="python")
+    index.close()
+    assert [t.sequence for t in ta] == [t.sequence for t in tb] and len(ta) > 300
+    fa_, fb_ = tmp_path / "n" / f"r.{fmt}", tmp_path / "p" / f"r.{fmt}"
+    assert fa_.read_bytes() == fb_.read_bytes() and len(fa_.read_bytes()) > 10000 and b"annotations" in fa_.read_bytes()
+    assert (tmp_path / "n" / "r.error").read_bytes() == (tmp_path / "p" / "r.error").read_bytes()
