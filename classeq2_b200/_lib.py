@@ -93,6 +93,10 @@ class RecordTree(C.Structure):
                 ("ann_json", C.c_char_p)]
 
 
+class FastaHostRecords(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("header_begin", u64p), ("header_end", u64p), ("offsets", u64p), ("bases", u8p)]
+
+
 class ClsError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"classeq_b200 error {code}: {message}")
@@ -134,6 +138,8 @@ PROTOTYPES = {
     "cls_records_render": (C.c_int, [C.POINTER(RecordTree), C.c_uint64, u64p, C.c_char_p, C.POINTER(Result), C.c_uint32,
                                      C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_void_p), u64p]),
     "cls_text_free": (None, [C.c_void_p]),
+    "cls_fasta_read": (C.c_int, [u8p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(FastaHostRecords)]),
+    "cls_fasta_text_destroy": (None, [C.c_void_p]),
     "cls_debug_plan_batch": (C.c_int, [C.c_uint32, C.POINTER(Batch), u8p, u32p, u32p, C.POINTER(PlanClass), C.c_uint32, u32p, u32p, u64p]),
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),
     "cls_filter_sequence": (C.c_uint64, [u8p, C.c_uint64, u8p, C.c_uint64]),

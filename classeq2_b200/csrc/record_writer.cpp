@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -417,3 +418,70 @@ extern "C" int cls_records_render(const cls_record_tree *tree, uint64_t n_querie
 }
 
 extern "C" void cls_text_free(char *p) { free(p); }
+
+// ---- the reference's FASTA reader on the host (file_or_stdin.rs:76-116 + sequence.rs:47-56), for texts the device ingest
+//      does not take (non-ASCII bytes, streams) and for callers without a resident batch.  Same record rules as
+//      cls_fasta_upload applies on the device; one pass over the text. ---------------------------------------------
+struct cls_fasta_text {
+    std::vector<uint64_t> header_begin, header_end, offsets;
+    std::vector<uint8_t> bases;
+};
+
+extern "C" int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_text **out, cls_fasta_host_records *rec) {
+    using cls::set_last_error;
+    if (!out || !rec || (n_bytes && !text)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    memset(rec, 0, sizeof *rec);
+    try {
+        auto ft = std::make_unique<cls_fasta_text>();
+        ft->offsets.push_back(0);
+        ft->bases.resize(n_bytes ? n_bytes : 1);
+        uint64_t kept = 0;              // filtered bases written so far
+        uint64_t rec_start = 0;         // first base of the record being read
+        bool have_header = false;       // the reader holds a non-empty header
+        uint64_t hb = 0, he = 0;        // its line
+        bool stop = false;
+        uint64_t a = 0;
+        while (a < n_bytes && !stop) {
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(text + a, '\n', n_bytes - a));
+            uint64_t b = nl ? (uint64_t)(nl - text) : n_bytes;      // line = [a, b)
+            const uint64_t next = nl ? b + 1 : n_bytes;
+            if (nl && b > a && text[b - 1] == '\r') --b;            // BufRead::lines: "\r\n" is a terminator, a lone "\r" is not
+            if (b > a) {                                            // empty lines are skipped (:87-89)
+                if (text[a] == '>') {
+                    if (have_header) {                              // send the previous record, even without sequence (:103-108)
+                        ft->header_begin.push_back(hb); ft->header_end.push_back(he);
+                        ft->offsets.push_back(kept);
+                        rec_start = kept;
+                    } else if (kept > rec_start) {                  // sequence without header: the reader errors out (:96-100)
+                        stop = true;
+                        kept = rec_start;
+                        break;
+                    }
+                    bool nonempty = false;                          // header = the line minus every '>' (:102)
+                    for (uint64_t i = a; i < b && !nonempty; ++i) nonempty = text[i] != '>';
+                    have_header = nonempty;
+                    hb = a; he = b;
+                } else {
+                    kept += cls_filter_sequence(text + a, b - a, ft->bases.data() + kept, ft->bases.size() - kept);
+                }
+            }
+            a = next;
+        }
+        if (!stop && have_header && kept > rec_start) {             // the trailing record needs a sequence (:111-113)
+            ft->header_begin.push_back(hb); ft->header_end.push_back(he);
+            ft->offsets.push_back(kept);
+        }
+        rec->n_records = ft->header_begin.size();
+        rec->header_begin = ft->header_begin.data();
+        rec->header_end = ft->header_end.data();
+        rec->offsets = ft->offsets.data();
+        rec->bases = ft->bases.data();
+        *out = ft.release();
+        return CLS_OK;
+    } catch (const std::bad_alloc &) {
+        return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while reading the FASTA text");
+    }
+}
+
+extern "C" void cls_fasta_text_destroy(cls_fasta_text *t) { delete t; }

@@ -81,6 +81,26 @@ def read_fasta_text(text: str) -> List[Tuple[str, str]]:
     return out
 
 
+def read_fasta_native(data: Union[bytes, bytearray, memoryview, str]) -> Tuple[List[str], np.ndarray, np.ndarray]:
+    """``cls_fasta_read``: the same reader in the library (C++, one pass over the bytes).  Returns ``(headers, bases,
+    offsets)`` - the records :func:`read_fasta_text` would return, the sequences as one ``cls_batch``-shaped pair."""
+    raw = data.encode("utf-8") if isinstance(data, str) else bytes(data)
+    arr = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(1, np.uint8)
+    h, rec = C.c_void_p(), _lib.FastaHostRecords()
+    _lib.check(_lib.lib.cls_fasta_read(arr.ctypes.data_as(_lib.u8p), len(raw), C.byref(h), C.byref(rec)))
+    try:
+        n = int(rec.n_records)
+        offsets = np.ctypeslib.as_array(rec.offsets, shape=(n + 1,)).copy()
+        total = int(offsets[-1])
+        bases = np.ctypeslib.as_array(rec.bases, shape=(max(total, 1),))[:total].copy()
+        hb = np.ctypeslib.as_array(rec.header_begin, shape=(n,)).tolist() if n else []
+        he = np.ctypeslib.as_array(rec.header_end, shape=(n,)).tolist() if n else []
+    finally:
+        _lib.lib.cls_fasta_text_destroy(h)
+    headers = [raw[a:b].replace(b">", b"").decode("utf-8") for a, b in zip(hb, he)]
+    return headers, bases, offsets
+
+
 def read_fasta(query: Union[str, os.PathLike, io.TextIOBase]) -> List[Tuple[str, str]]:
     """``FileOrStdin``: a path, ``"-"`` for stdin, or an open text stream."""
     if hasattr(query, "read"):
@@ -555,7 +575,7 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                     overwrite: bool = False, output_format: str = "yaml",
                     remove_intersection: Optional[bool] = None, *, index: Optional[Index] = None,
                     device: int = 0, batch_size: int = 1 << 20, ingest: str = "host",
-                    writer: str = "native") -> List[PlacementTime]:
+                    writer: str = "native", reader: str = "native") -> List[PlacementTime]:
     """Place every sequence of a FASTA input on ``tree`` and append one record per query to
     ``<out_file>.yaml|.jsonl`` (errors to ``<out_file>.error``), as the reference does.
 
@@ -565,9 +585,11 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
     only, ASCII only) instead of with the host reader; the records and results are identical.
     ``writer="native"`` (default) serialises the records in the library (``cls_records_render``, multi-threaded C++);
     ``writer="python"`` uses this module's emitters - the two write byte-identical files (tests/test_record_writer.py).
+    ``reader="native"`` (default, host ingest) parses the FASTA text in the library (``cls_fasta_read``); ``"python"``
+    uses :func:`read_fasta_text` - the same records (tests/test_fasta_reader.py).
     """
-    if writer not in ("native", "python"):
-        raise ValueError("writer must be 'native' or 'python'")
+    if writer not in ("native", "python") or reader not in ("native", "python"):
+        raise ValueError("writer / reader must be 'native' or 'python'")
     if ingest not in ("host", "device"):
         raise ValueError("ingest must be 'host' or 'device'")
     if output_format not in ("yaml", "jsonl"):
@@ -590,7 +612,7 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
     own_index = index is None
     if own_index:
         index = Index(tree, device=device)
-    device_batch = None
+    device_batch = host_bases = host_offsets = None
     if ingest == "device":
         if hasattr(query_sequence, "read") or str(query_sequence) == "-":
             raise ValueError("ingest='device' reads a file path")
@@ -599,6 +621,16 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
         device_batch, headers, _ = index.upload_fasta(raw)
         records = [(h, None) for h in headers]
         batch_size = max(len(records), 1)
+    elif reader == "native":
+        if hasattr(query_sequence, "read"):
+            raw = query_sequence.read()
+        elif str(query_sequence) == "-":
+            raw = sys.stdin.buffer.read()
+        else:
+            with open(query_sequence, "rb") as f:
+                raw = f.read()
+        headers, host_bases, host_offsets = read_fasta_native(raw)
+        records = [(h, None) for h in headers]
     else:
         records = read_fasta(query_sequence)
     lookup = _TreeLookup(tree) if writer == "python" else None
@@ -613,6 +645,9 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                 if device_batch is not None:
                     device_batch.place(params)
                     res = device_batch.fetch()
+                elif host_offsets is not None:
+                    off = host_offsets[a:a + len(chunk) + 1]
+                    res = index.place_batch((host_bases[int(off[0]):int(off[-1])], off - off[0]), params)
                 else:
                     res = index.place_batch([s for _, s in chunk], params)
                 per_seq_ms = (time.perf_counter() - t0) * 1e3 / max(len(chunk), 1)

@@ -395,6 +395,24 @@ int cls_records_render(const cls_record_tree *tree, uint64_t n_queries, const ui
 void cls_text_free(char *text);
 
 /*
+ * The reference's FASTA reader on the host (file_or_stdin.rs:76-116 with the filter of sequence.rs:47-56), for texts
+ * the device ingest does not take (bytes >= 0x80, streams) and for callers that want the batch in host memory: the
+ * records the reader sends, as a cls_batch-shaped pair (bases, offsets) plus where every header line sits in `text`
+ * (header = text[header_begin .. header_end) minus every '>').  Same record rules as cls_fasta_upload.  The arrays
+ * live in the handle: release it with cls_fasta_text_destroy.
+ */
+typedef struct cls_fasta_text cls_fasta_text;
+typedef struct cls_fasta_host_records {
+    uint64_t n_records;
+    const uint64_t *header_begin;
+    const uint64_t *header_end;
+    const uint64_t *offsets;        /* [n_records+1] into bases */
+    const uint8_t *bases;           /* filtered, upper-cased A/C/G/T */
+} cls_fasta_host_records;
+int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_text **out, cls_fasta_host_records *records);
+void cls_fasta_text_destroy(cls_fasta_text *t);
+
+/*
  * cls_debug_plan_batch: the host-side planner of cls_place_batch / cls_batch_upload on its own (no GPU needed):
  * queries shorter than k get their status on the host (pre_status[i] = CLS_STATUS_ERR_TOO_SHORT, else 0xFF), the
  * others are grouped into LENGTH CLASSES - all reads of a class share one per-read table geometry; longest class

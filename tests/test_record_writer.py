@@ -182,8 +182,8 @@ def test_place_sequences_files_with_both_writers(ps, tmp_path, col_tree, col_fla
     index = _OracleIndex(col_flat)
     fa = os.path.join(GOLDEN, "colletotrichum_queries.fasta")
     a, b = tmp_path / "n" / "r", tmp_path / "p" / "r"
-    cq.place_sequences(fa, tree, a, output_format=fmt, index=index, writer="native", batch_size=100)
-    cq.place_sequences(fa, tree, b, output_format=fmt, index=index, writer="python", batch_size=1 << 20)
+    cq.place_sequences(fa, tree, a, output_format=fmt, index=index, writer="native", reader="native", batch_size=100)
+    cq.place_sequences(fa, tree, b, output_format=fmt, index=index, writer="python", reader="python", batch_size=1 << 20)
     index.close()
     text = (tmp_path / "n" / f"r.{fmt}").read_bytes()
     assert text == (tmp_path / "p" / f"r.{fmt}").read_bytes() and len(text) > 10000
