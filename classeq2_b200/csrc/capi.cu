@@ -1053,40 +1053,4 @@ uint64_t cls_debug_host_murmur3_x64_128_h1(const uint8_t *data, uint64_t len, ui
     return murmur3_x64_128_h1(data, len, seed);
 }
 
-// sequence.rs:47-56: `sequence.to_uppercase().chars().filter(A|C|G|T)`.  Rust upper-cases with the
-// full Unicode mapping; the only non-ASCII scalars whose upper-case expansion contains an ASCII
-// A/C/G/T are U+1E97 (t with diaeresis -> "T" + U+0308), U+1E9A (a with right half ring -> "A" +
-// U+02BE), U+FB05 and U+FB06 (long-s-t / st ligatures -> "ST").  Every other non-ASCII byte
-// sequence contributes nothing.
-uint64_t cls_filter_sequence(const uint8_t *line, uint64_t len, uint8_t *out, uint64_t cap) {
-    uint64_t n = 0;
-    auto put = [&](uint8_t c) { if (n < cap && out) out[n] = c; ++n; };
-    // upper-cased base for A/C/G/T/a/c/g/t, 0 for every other byte
-    static const struct Lut { uint8_t v[256]; Lut() : v{} { for (const char *p = "ACGTacgt"; *p; ++p) v[(uint8_t)*p] = (uint8_t)(*p & 0xDF); } } lut;
-    for (uint64_t i = 0; i < len; ++i) {
-        // fast path: a stretch of ASCII with room in `out` - one table look-up and a branch-free store per byte
-        if (out) {
-            while (i < len && line[i] < 0x80 && n < cap) {
-                const uint8_t u = lut.v[line[i]];
-                out[n] = u;
-                n += u != 0;
-                ++i;
-            }
-            if (i >= len) break;
-        }
-        const uint8_t c = line[i];
-        if (c < 0x80) {
-            const uint8_t u = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c;
-            if (u == 'A' || u == 'C' || u == 'G' || u == 'T') put(u);
-        } else if (c == 0xE1 && i + 2 < len && line[i + 1] == 0xBA && (line[i + 2] == 0x97 || line[i + 2] == 0x9A)) {
-            put(line[i + 2] == 0x97 ? 'T' : 'A');
-            i += 2;
-        } else if (c == 0xEF && i + 2 < len && line[i + 1] == 0xAC && (line[i + 2] == 0x85 || line[i + 2] == 0x86)) {
-            put('T');
-            i += 2;
-        }
-    }
-    return n;
-}
-
 }  // extern "C"

@@ -372,6 +372,22 @@ int render(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, 
     *out_len = *err_len = 0;
     if (format > 1) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "format must be 0 (yaml) or 1 (jsonl)");
     if (n && (!res->status || !res->node_id || !res->one || !res->rest)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "result arrays are NULL");
+    // the child lists must form a forest (as cls_index_create demands of the same tree): the Clade writers recurse over them
+    {
+        std::vector<uint8_t> seen(tree->n_nodes, 0);
+        std::vector<uint32_t> depth(tree->n_nodes, 0);
+        for (uint64_t i = 0; i < tree->n_nodes; ++i) {
+            if (tree->child_off[i] > tree->child_off[i + 1]) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "child_off is not non-decreasing");
+            for (uint64_t j = tree->child_off[i]; j < tree->child_off[i + 1]; ++j) {
+                const uint64_t c = tree->child_idx[j];
+                if (c >= tree->n_nodes || c == 0 || seen[c]) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "child lists do not form a tree");
+                seen[c] = 1;
+                if (c <= i) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "nodes must come in pre-order (children after their parent)");
+                depth[c] = depth[i] + 1;
+                if (depth[c] > 20000) return set_last_error(CLS_ERR_UNSUPPORTED, "tree deeper than 20 000 levels");
+            }
+        }
+    }
     TreeView tv{tree, {}};
     tv.by_id.reserve(tree->n_nodes * 2);
     for (uint64_t i = 0; i < tree->n_nodes; ++i) tv.by_id.emplace(tree->node_id[i], i);   // emplace keeps the first
@@ -418,6 +434,44 @@ extern "C" int cls_records_render(const cls_record_tree *tree, uint64_t n_querie
 }
 
 extern "C" void cls_text_free(char *p) { free(p); }
+
+extern "C" {
+// sequence.rs:47-56: `sequence.to_uppercase().chars().filter(A|C|G|T)`.  Rust upper-cases with the
+// full Unicode mapping; the only non-ASCII scalars whose upper-case expansion contains an ASCII
+// A/C/G/T are U+1E97 (t with diaeresis -> "T" + U+0308), U+1E9A (a with right half ring -> "A" +
+// U+02BE), U+FB05 and U+FB06 (long-s-t / st ligatures -> "ST").  Every other non-ASCII byte
+// sequence contributes nothing.
+uint64_t cls_filter_sequence(const uint8_t *line, uint64_t len, uint8_t *out, uint64_t cap) {
+    uint64_t n = 0;
+    auto put = [&](uint8_t c) { if (n < cap && out) out[n] = c; ++n; };
+    // upper-cased base for A/C/G/T/a/c/g/t, 0 for every other byte
+    static const struct Lut { uint8_t v[256]; Lut() : v{} { for (const char *p = "ACGTacgt"; *p; ++p) v[(uint8_t)*p] = (uint8_t)(*p & 0xDF); } } lut;
+    for (uint64_t i = 0; i < len; ++i) {
+        // fast path: a stretch of ASCII with room in `out` - one table look-up and a branch-free store per byte
+        if (out) {
+            while (i < len && line[i] < 0x80 && n < cap) {
+                const uint8_t u = lut.v[line[i]];
+                out[n] = u;
+                n += u != 0;
+                ++i;
+            }
+            if (i >= len) break;
+        }
+        const uint8_t c = line[i];
+        if (c < 0x80) {
+            const uint8_t u = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c;
+            if (u == 'A' || u == 'C' || u == 'G' || u == 'T') put(u);
+        } else if (c == 0xE1 && i + 2 < len && line[i + 1] == 0xBA && (line[i + 2] == 0x97 || line[i + 2] == 0x9A)) {
+            put(line[i + 2] == 0x97 ? 'T' : 'A');
+            i += 2;
+        } else if (c == 0xEF && i + 2 < len && line[i + 1] == 0xAC && (line[i + 2] == 0x85 || line[i + 2] == 0x86)) {
+            put('T');
+            i += 2;
+        }
+    }
+    return n;
+}
+}  // extern "C"
 
 // ---- the reference's FASTA reader on the host (file_or_stdin.rs:76-116 + sequence.rs:47-56), for texts the device ingest
 //      does not take (non-ASCII bytes, streams) and for callers without a resident batch.  Same record rules as

@@ -363,8 +363,9 @@ int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out,
  * `annotations` = the tree's annotations whose clade lies on the path to the root of the placement clade
  * (clade.rs:95-125), sorted by clade (mod.rs:180-224); every annotation is handed over ALREADY RENDERED, once per
  * tree, as the YAML list item ("- clade: 45\n  meta:\n  - !Taxid 1452\n") and as the JSON object.
- * format 0: serde_yaml documents ("---\n" + block style), 1: serde_json lines.  Nodes come in the order of
- * cls_model_view (node 0 = root).  NaN support / length = None; parent_id < 0 = None.
+ * format 0: serde_yaml documents ("---\n" + block style), 1: serde_json lines.  Nodes come parents first (pre-order
+ * as a flattening of Tree.root produces it; node 0 = root) and the child lists must form a tree, else
+ * CLS_ERR_INVALID_ARGUMENT.  NaN support / length = None; parent_id < 0 = None.
  * The two texts are malloc'ed by the library: release them with cls_text_free.
  */
 typedef struct cls_record_tree {
