@@ -1,5 +1,7 @@
-"""Memory-safety fuzz of the library's host text code (FASTA reader, filter, record writer) under AddressSanitizer and
-UndefinedBehaviorSanitizer: tests/native/text_fuzz.cpp compiled against classeq2_b200/csrc/record_writer.cpp."""
+"""Memory-safety fuzz of the library's host code under AddressSanitizer and UndefinedBehaviorSanitizer: the text code
+(FASTA reader, filter, record writer: tests/native/text_fuzz.cpp against csrc/record_writer.cpp) and the model code
+(index serialisation of valid and malformed model views, host model builder: tests/native/model_fuzz.cpp against
+csrc/index_build.cpp and csrc/host_api.cpp)."""
 import os
 import shutil
 import subprocess
@@ -21,3 +23,16 @@ def test_reader_and_writer_are_clean_under_asan_ubsan(tmp_path):
     r = subprocess.run([exe, "150"], env=dict(os.environ, CLS_HOST_THREADS="4"), capture_output=True, text=True, timeout=600)
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
     assert r.returncode == 0 and r.stdout.strip() == "bad=0", (r.returncode, r.stdout, r.stderr[-500:])
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_model_serialisation_refuses_malformed_views_without_crashing(tmp_path):
+    exe = str(tmp_path / "model_fuzz")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-pthread",
+                        os.path.join(HERE, "native", "model_fuzz.cpp"), os.path.join(CSRC, "index_build.cpp"),
+                        os.path.join(CSRC, "host_api.cpp"), "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
+    r = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
+    assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
+    assert r.returncode == 0 and r.stdout.startswith("ok="), (r.returncode, r.stdout, r.stderr[-500:])
