@@ -36,3 +36,18 @@ def test_model_serialisation_refuses_malformed_views_without_crashing(tmp_path):
     r = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
     assert r.returncode == 0 and r.stdout.startswith("ok="), (r.returncode, r.stdout, r.stderr[-500:])
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_packer_bodies_stay_inside_their_buffers(tmp_path):
+    """Every body of the host 2-bit packer on exactly-sized heap buffers (lengths 0..700): no over-read, no word written
+    past ceil(len / 16), all bodies equal, invalid bytes reported."""
+    exe = str(tmp_path / "pack_fuzz")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                        os.path.join(HERE, "native", "pack_fuzz.cpp"), os.path.join(CSRC, "host_pack.cpp"), "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
+    assert r.returncode == 0 and r.stdout.startswith("bad=0"), (r.returncode, r.stdout, r.stderr[-500:])
