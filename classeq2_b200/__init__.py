@@ -10,8 +10,8 @@ from .engine import (BatchResult, Index, PlaceParams, ResidentBatch, debug_kmer_
 from .model import BuiltModel, Clade, FlatModel, KmersMap, Tree  # noqa: F401
 from .build import map_kmers_to_tree, tree_from_newick  # noqa: F401
 from .placement import (PlacementTime, load_annotations, load_database, place_sequences,  # noqa: F401
-                        read_fasta, save_database)
+                        place_sequences_native, read_fasta, save_database)
 
 __all__ = ["Index", "ResidentBatch", "PlaceParams", "BatchResult", "Clade", "KmersMap", "Tree",
-           "FlatModel", "BuiltModel", "debug_kmer_hashes", "host_murmur3_h1", "filter_sequence", "make_batch", "place_sequences", "load_database",
+           "FlatModel", "BuiltModel", "debug_kmer_hashes", "host_murmur3_h1", "filter_sequence", "make_batch", "place_sequences", "place_sequences_native", "load_database",
            "save_database", "map_kmers_to_tree", "tree_from_newick", "load_annotations", "read_fasta", "PlacementTime"]

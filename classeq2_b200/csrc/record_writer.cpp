@@ -20,6 +20,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include <sys/stat.h>
+#include <sys/types.h>
+
 #include "../../include/classeq_b200.h"
 #include "host_pool.hpp"
 
@@ -539,3 +542,151 @@ extern "C" int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_t
 }
 
 extern "C" void cls_fasta_text_destroy(cls_fasta_text *t) { delete t; }
+
+
+// ---- place_sequences as the reference spells it (core/src/use_cases/place_sequences/mod.rs:43-270): a query FASTA, an
+//      output path, the knobs -> result / error files.  cls_sequences_open does the path handling of :73-106 and reads the
+//      records (:118-119), cls_sequences_write appends what the closure at :160-249 appends for a batch of results, and
+//      cls_place_sequences strings them together around cls_place_batch. -------------------------------------------------
+struct cls_sequences {
+    std::string text;                 // the query file
+    cls_fasta_text *records = nullptr;
+    cls_fasta_host_records rec{};
+    std::vector<uint64_t> header_off; // headers with every '>' removed, back to back
+    std::string headers;
+    std::string out_path, err_path;
+    uint32_t format = 0;
+    uint64_t written = 0;             // records handed to cls_sequences_write so far
+    ~cls_sequences() { cls_fasta_text_destroy(records); }
+};
+
+namespace {
+
+// PathBuf::set_extension(ext): the extension of the FILE NAME is replaced (or appended when there is none; a leading
+// dot of the name does not start an extension)
+std::string with_extension(const std::string &path, const char *ext) {
+    const size_t slash = path.find_last_of('/');
+    const size_t name = slash == std::string::npos ? 0 : slash + 1;
+    const size_t dot = path.find_last_of('.');
+    std::string root = (dot == std::string::npos || dot <= name) ? path : path.substr(0, dot);
+    return root + "." + ext;
+}
+
+bool read_whole(FILE *f, std::string &out) {
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    return !ferror(f);
+}
+
+bool append_file(const std::string &path, const char *data, uint64_t n) {
+    FILE *f = fopen(path.c_str(), "ab");
+    if (!f) return false;
+    const bool ok = n == 0 || fwrite(data, 1, n, f) == n;
+    return fclose(f) == 0 && ok;
+}
+
+}  // namespace
+
+extern "C" int cls_sequences_open(const char *query_path, const char *out_file, uint32_t format, uint32_t overwrite,
+                                  cls_sequences **out, cls_batch *batch) {
+    using cls::set_last_error;
+    if (!out_file || !out || !batch) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    if (format > 1) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "format must be 0 (yaml) or 1 (jsonl)");
+    try {
+        auto s = std::make_unique<cls_sequences>();
+        s->format = format;
+        s->out_path = with_extension(out_file, format == 0 ? "yaml" : "jsonl");       // :73-90
+        s->err_path = with_extension(out_file, "error");
+        const size_t slash = s->out_path.find_last_of('/');
+        if (slash != std::string::npos && slash > 0) {
+            const std::string dir = s->out_path.substr(0, slash);
+            struct stat st;
+            if (stat(dir.c_str(), &st) != 0) mkdir(dir.c_str(), 0777);                 // create_dir, its error ignored (:92-94)
+        }
+        struct stat st;
+        if (stat(s->out_path.c_str(), &st) == 0) {
+            if (!overwrite) {                                                           // :96-101
+                std::string msg = "Could not overwrite existing file ";
+                rust_debug_str(s->out_path, msg);
+                msg += " when overwrite option is `false`.";
+                return set_last_error(CLS_ERR_INVALID_ARGUMENT, msg);
+            }
+            remove(s->out_path.c_str());
+        }
+        const bool use_stdin = !query_path || strcmp(query_path, "-") == 0;
+        FILE *f = use_stdin ? stdin : fopen(query_path, "rb");
+        if (!f) return set_last_error(CLS_ERR_INVALID_ARGUMENT, std::string("cannot open ") + query_path);
+        const bool ok = read_whole(f, s->text);
+        if (!use_stdin) fclose(f);
+        if (!ok) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "error while reading the query sequences");
+        const int rc = cls_fasta_read(reinterpret_cast<const uint8_t *>(s->text.data()), s->text.size(), &s->records, &s->rec);
+        if (rc != CLS_OK) return rc;
+        s->header_off.assign(s->rec.n_records + 1, 0);
+        for (uint64_t i = 0; i < s->rec.n_records; ++i) {
+            for (uint64_t j = s->rec.header_begin[i]; j < s->rec.header_end[i]; ++j)
+                if (s->text[j] != '>') s->headers += s->text[j];
+            s->header_off[i + 1] = s->headers.size();
+        }
+        if (!append_file(s->out_path, nullptr, 0) || !append_file(s->err_path, nullptr, 0))   // both files exist from here on
+            return set_last_error(CLS_ERR_INVALID_ARGUMENT, "cannot create " + s->out_path + " / " + s->err_path);
+        batch->n_queries = s->rec.n_records;
+        batch->bases = s->rec.bases;
+        batch->offsets = s->rec.offsets;
+        *out = s.release();
+        return CLS_OK;
+    } catch (const std::bad_alloc &) {
+        return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while opening the query sequences");
+    }
+}
+
+extern "C" int cls_sequences_write(cls_sequences *s, const cls_record_tree *tree, uint64_t n, const cls_result *result) {
+    using cls::set_last_error;
+    if (!s || !tree || !result) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (s->written + n > s->rec.n_records) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "more results than records");
+    char *o = nullptr, *e = nullptr;
+    uint64_t no = 0, ne = 0;
+    // header_off is absolute into `headers`: the writer takes the sub-array as it is
+    const int rc = cls_records_render(tree, n, s->header_off.data() + s->written, s->headers.data(), result, s->format, &o, &no, &e, &ne);
+    if (rc != CLS_OK) return rc;
+    const bool ok = append_file(s->out_path, o, no) && append_file(s->err_path, e, ne);
+    cls_text_free(o);
+    cls_text_free(e);
+    if (!ok) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "Error writing to file: " + s->out_path);
+    s->written += n;
+    return CLS_OK;
+}
+
+extern "C" void cls_sequences_close(cls_sequences *s) { delete s; }
+
+extern "C" int cls_place_sequences(cls_index *index, const cls_record_tree *tree, const char *query_path, const char *out_file,
+                                   const cls_params *params, uint32_t format, uint32_t overwrite, uint64_t *n_placed) {
+    using cls::set_last_error;
+    if (!index || !tree || !params) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_placed) *n_placed = 0;
+    cls_sequences *s = nullptr;
+    cls_batch all{};
+    int rc = cls_sequences_open(query_path, out_file, format, overwrite, &s, &all);
+    if (rc != CLS_OK) return rc;
+    std::unique_ptr<cls_sequences> guard(s);
+    try {
+        constexpr uint64_t kBatch = 1ull << 20;      // queries per device call: bounds the result arrays
+        const uint64_t cap = std::min<uint64_t>(all.n_queries, kBatch);
+        std::vector<uint8_t> status(cap);
+        std::vector<uint64_t> node(cap);
+        std::vector<int32_t> one(cap), rest(cap);
+        std::vector<uint32_t> nq(cap), nm(cap), nr(cap), it(cap);
+        cls_result res{status.data(), node.data(), one.data(), rest.data(), nq.data(), nm.data(), nr.data(), it.data()};
+        for (uint64_t a = 0; a < all.n_queries; a += kBatch) {
+            const uint64_t n = std::min<uint64_t>(kBatch, all.n_queries - a);
+            const cls_batch part{n, all.bases, all.offsets + a};   // offsets are absolute into `bases`
+            if ((rc = cls_place_batch(index, &part, params, &res)) != CLS_OK) return rc;
+            if ((rc = cls_sequences_write(s, tree, n, &res)) != CLS_OK) return rc;
+            if (n_placed) *n_placed += n;
+        }
+        return CLS_OK;
+    } catch (const std::bad_alloc &) {
+        return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed in cls_place_sequences");
+    }
+}

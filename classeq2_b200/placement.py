@@ -674,3 +674,30 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
         if own_index:
             index.close()
     return times
+
+
+def place_sequences_native(query_sequence: Union[str, os.PathLike], tree: Tree, out_file: Union[str, os.PathLike],
+                           max_iterations: Optional[int] = None, min_match_coverage: Optional[float] = None,
+                           overwrite: bool = False, output_format: str = "yaml",
+                           remove_intersection: Optional[bool] = None, *, index: Optional[Index] = None, device: int = 0) -> int:
+    """The whole use-case in ONE library call (``cls_place_sequences``): path handling, FASTA reader, placement on the GPU
+    and record writer all run in the library; this wrapper only flattens the tree.  Same arguments as
+    :func:`place_sequences` (a path or ``"-"`` for stdin), same files.  Returns the number of records placed."""
+    if output_format not in ("yaml", "jsonl"):
+        raise ValueError("output_format must be 'yaml' or 'jsonl'")
+    own_index = index is None
+    if own_index:
+        index = Index(tree, device=device)
+    try:
+        rtree = RecordTree(tree)
+        params = PlaceParams(max_iterations, min_match_coverage, remove_intersection).to_c()
+        n = C.c_uint64()
+        rc = _lib.lib.cls_place_sequences(index._h, C.byref(rtree.view), os.fspath(query_sequence).encode(), os.fspath(out_file).encode(),
+                                          C.byref(params), 0 if output_format == "yaml" else 1, 1 if overwrite else 0, C.byref(n))
+        if rc == _lib.CLS_ERR_INVALID_ARGUMENT and _lib.last_error().startswith("Could not overwrite existing file"):
+            raise FileExistsError(_lib.last_error())
+        _lib.check(rc)
+        return int(n.value)
+    finally:
+        if own_index:
+            index.close()

@@ -414,6 +414,24 @@ int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_text **out, 
 void cls_fasta_text_destroy(cls_fasta_text *t);
 
 /*
+ * `place_sequences` as the reference spells it (core/src/use_cases/place_sequences/mod.rs:43-53): a query FASTA (path,
+ * NULL or "-" for stdin), an output path, the knobs -> `<out>.yaml|.jsonl` and `<out>.error`.
+ *   cls_place_sequences    the whole use-case in one call: open, cls_place_batch per 2^20 queries, write, close
+ *   cls_sequences_open     path handling of mod.rs:73-106 (extension replaced by the format's, parent directory created,
+ *                          an existing result file removed if `overwrite`, else CLS_ERR_INVALID_ARGUMENT with the
+ *                          reference's message) + the reader (:118-119); `batch` receives a borrowed view of the records
+ *   cls_sequences_write    appends the records / error texts of the next `n` results (in record order) to the two files
+ * The split exists for callers that place on their own schedule (several GPUs, resident batches) and for tests.
+ */
+typedef struct cls_sequences cls_sequences;
+int cls_sequences_open(const char *query_path, const char *out_file, uint32_t format, uint32_t overwrite,
+                       cls_sequences **out, cls_batch *batch);
+int cls_sequences_write(cls_sequences *s, const cls_record_tree *tree, uint64_t n, const cls_result *result);
+void cls_sequences_close(cls_sequences *s);
+int cls_place_sequences(cls_index *index, const cls_record_tree *tree, const char *query_path, const char *out_file,
+                        const cls_params *params, uint32_t format, uint32_t overwrite, uint64_t *n_placed);
+
+/*
  * cls_debug_plan_batch: the host-side planner of cls_place_batch / cls_batch_upload on its own (no GPU needed):
  * queries shorter than k get their status on the host (pre_status[i] = CLS_STATUS_ERR_TOO_SHORT, else 0xFF), the
  * others are grouped into LENGTH CLASSES - all reads of a class share one per-read table geometry; longest class

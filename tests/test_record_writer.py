@@ -202,3 +202,48 @@ def _floats(o):
     if isinstance(o, list):
         return [_floats(v) for v in o]
     return o
+
+
+@pytest.mark.parametrize("fmt", ["yaml", "jsonl"])
+def test_native_sequences_open_and_write(ps, tmp_path, col_tree, col_flat, fmt):
+    """cls_sequences_open / cls_sequences_write - the two host halves of the one-call cls_place_sequences - around an
+    oracle placement: same files as the Python driver, same path handling (extension replaced, directory created,
+    overwrite refused with the reference's message, error file appended)."""
+    import ctypes as C
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    tree.annotations = [{"clade": 0, "meta": [ps.Tag("Rank", "genus")]}, {"clade": 18}]
+    index = _OracleIndex(col_flat)
+    fa = os.path.join(GOLDEN, "colletotrichum_queries.fasta")
+    cq.place_sequences(fa, tree, tmp_path / "p" / "r.whatever", output_format=fmt, index=index, writer="python", reader="python")
+    rt = ps.RecordTree(tree)
+
+    def run(out_file, overwrite, chunk):
+        h, b = C.c_void_p(), _lib.Batch()
+        rc = _lib.lib.cls_sequences_open(fa.encode(), str(out_file).encode(), 0 if fmt == "yaml" else 1, overwrite, C.byref(h), C.byref(b))
+        if rc != 0:
+            return rc, _lib.last_error()
+        n = int(b.n_queries)
+        offsets = np.ctypeslib.as_array(b.offsets, shape=(n + 1,)).copy()
+        bases = np.ctypeslib.as_array(b.bases, shape=(int(offsets[-1]),)).copy()
+        for a in range(0, n, chunk):
+            off = offsets[a:a + chunk + 1]
+            res = index.place_batch((bases[int(off[0]):int(off[-1])], off - off[0]))
+            cr = res.to_c()
+            _lib.check(_lib.lib.cls_sequences_write(h, C.byref(rt.view), len(off) - 1, C.byref(cr)))
+        _lib.lib.cls_sequences_close(h)
+        return 0, ""
+
+    out = tmp_path / "n" / "r.something"
+    assert run(out, 0, 97) == (0, "")
+    want_o, want_e = (tmp_path / "p" / f"r.{fmt}").read_bytes(), (tmp_path / "p" / "r.error").read_bytes()
+    assert (tmp_path / "n" / f"r.{fmt}").read_bytes() == want_o and len(want_o) > 10000
+    assert (tmp_path / "n" / "r.error").read_bytes() == want_e
+    rc, msg = run(out, 0, 97)                                   # the result file exists and overwrite is false (mod.rs:96-101)
+    assert rc == _lib.CLS_ERR_INVALID_ARGUMENT
+    assert msg == f'Could not overwrite existing file "{tmp_path}/n/r.{fmt}" when overwrite option is `false`.'
+    assert run(out, 1, 1 << 20) == (0, "")                      # overwrite: the result file starts over, the error file is appended
+    assert (tmp_path / "n" / f"r.{fmt}").read_bytes() == want_o
+    assert (tmp_path / "n" / "r.error").read_bytes() == want_e + want_e
+    index.close()

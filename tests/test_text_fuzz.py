@@ -18,6 +18,7 @@ def test_reader_and_writer_are_clean_under_asan_ubsan(tmp_path):
     r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-pthread",
                         os.path.join(HERE, "native", "text_fuzz.cpp"), os.path.join(CSRC, "record_writer.cpp"),
                         os.path.join(CSRC, "host_pool.cpp"), "-o", exe], capture_output=True, text=True)
+    assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
     if r.returncode != 0:
         pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
     r = subprocess.run([exe, "150"], env=dict(os.environ, CLS_HOST_THREADS="4"), capture_output=True, text=True, timeout=600)
@@ -31,6 +32,7 @@ def test_model_serialisation_refuses_malformed_views_without_crashing(tmp_path):
     r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-pthread",
                         os.path.join(HERE, "native", "model_fuzz.cpp"), os.path.join(CSRC, "index_build.cpp"),
                         os.path.join(CSRC, "host_api.cpp"), "-o", exe], capture_output=True, text=True)
+    assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
     if r.returncode != 0:
         pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
     r = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
@@ -46,6 +48,7 @@ def test_packer_bodies_stay_inside_their_buffers(tmp_path):
     r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
                         os.path.join(HERE, "native", "pack_fuzz.cpp"), os.path.join(CSRC, "host_pack.cpp"), "-o", exe],
                        capture_output=True, text=True)
+    assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
     if r.returncode != 0:
         pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)

@@ -26,3 +26,22 @@ def test_native_and_python_writers_write_the_same_files(tmp_path, col_tree, fmt)
     fa_, fb_ = tmp_path / "n" / f"r.{fmt}", tmp_path / "p" / f"r.{fmt}"
     assert fa_.read_bytes() == fb_.read_bytes() and len(fa_.read_bytes()) > 10000 and b"annotations" in fa_.read_bytes()
     assert (tmp_path / "n" / "r.error").read_bytes() == (tmp_path / "p" / "r.error").read_bytes()
+
+
+@pytest.mark.parametrize("fmt", ["yaml", "jsonl"])
+def test_one_call_place_sequences_writes_the_same_files(tmp_path, col_tree, fmt):
+    """cls_place_sequences (reader, cls_place_batch, writer and the file handling of mod.rs:73-106 in one library call)
+    against the Python driver; its two host halves are covered without a GPU in tests/test_record_writer.py."""
+    import classeq2_b200 as cq
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    fa = os.path.join(GOLDEN, "colletotrichum_queries.fasta")
+    index = cq.Index(tree, device=0)
+    n = cq.place_sequences_native(fa, tree, tmp_path / "c" / "r.out", output_format=fmt, index=index, remove_intersection=True)
+    t = cq.place_sequences(fa, tree, tmp_path / "p" / "r.out", output_format=fmt, index=index, remove_intersection=True, writer="python")
+    assert n == len(t) > 300
+    assert (tmp_path / "c" / f"r.{fmt}").read_bytes() == (tmp_path / "p" / f"r.{fmt}").read_bytes()
+    assert (tmp_path / "c" / "r.error").read_bytes() == (tmp_path / "p" / "r.error").read_bytes()
+    with pytest.raises(FileExistsError):
+        cq.place_sequences_native(fa, tree, tmp_path / "c" / "r.out", output_format=fmt, index=index)
+    assert cq.place_sequences_native(fa, tree, tmp_path / "c" / "r.out", output_format=fmt, index=index, overwrite=True) == n
+    index.close()
