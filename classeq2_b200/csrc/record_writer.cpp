@@ -618,9 +618,8 @@ extern "C" int cls_sequences_open(const char *query_path, const char *out_file, 
         const bool use_stdin = !query_path || strcmp(query_path, "-") == 0;
         FILE *f = use_stdin ? stdin : fopen(query_path, "rb");
         if (!f) return set_last_error(CLS_ERR_INVALID_ARGUMENT, std::string("cannot open ") + query_path);
-        const bool ok = read_whole(f, s->text);
-        if (!use_stdin) fclose(f);
-        if (!ok) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "error while reading the query sequences");
+        struct Close { FILE *f; bool own; ~Close() { if (own) fclose(f); } } closer{f, !use_stdin};   // also when an allocation throws
+        if (!read_whole(f, s->text)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "error while reading the query sequences");
         const int rc = cls_fasta_read(reinterpret_cast<const uint8_t *>(s->text.data()), s->text.size(), &s->records, &s->rec);
         if (rc != CLS_OK) return rc;
         s->header_off.assign(s->rec.n_records + 1, 0);
