@@ -1,13 +1,18 @@
-// Native writer of the reference's result records: cls_result arrays + query headers + the Clade fields of the
-// tree -> the bytes `place_sequences` appends to `<out>.yaml|.jsonl` and `<out>.error`
-// (core/src/use_cases/place_sequences/mod.rs:160-249; PlacementResponse / PlacementStatus:
-// domain/dtos/placement_response.rs:7-94; AdherenceTest: adherence_test.rs:6-17; Clade: clade.rs:18-38;
-// the annotation join along the path to the root: mod.rs:180-224, clade.rs:95-125).
-// serde_yaml 0.9 block style and serde_json compact style are reproduced for this fixed record shape:
-// floats as the ryu crate prints them, strings quoted only where libyaml would quote them.  Host-only
-// (no CUDA): one block of records per task on the host pool, concatenated in input order.
-// The Python mirror (classeq2_b200/placement.py: placement_response + yaml_dump / json_dump) is the
-// second implementation; tests hold the two byte-identical, and both equal to a reference-written file.
+// The text side of `place_sequences`, native and host-only (no CUDA):
+//   cls_records_render   cls_result arrays + query headers + the Clade fields of the tree -> the bytes the reference
+//                        appends to `<out>.yaml|.jsonl` and `<out>.error`
+//                        (core/src/use_cases/place_sequences/mod.rs:160-249; PlacementResponse / PlacementStatus:
+//                        domain/dtos/placement_response.rs:7-94; AdherenceTest: adherence_test.rs:6-17; Clade:
+//                        clade.rs:18-38; the annotation join along the path to the root: mod.rs:180-224, clade.rs:95-125).
+//                        serde_yaml 0.9 block style and serde_json compact style are reproduced for this fixed record
+//                        shape: floats as the ryu crate prints them, strings quoted only where libyaml would quote them.
+//                        One block of records per task on the host pool, concatenated in input order.
+//   cls_filter_sequence  SequenceBody::remove_non_iupac_from_sequence (sequence.rs:47-56)
+//   cls_fasta_read       the reader of file_or_stdin.rs:76-116, one pass over the bytes
+//   cls_sequences_open / cls_sequences_write / cls_place_sequences
+//                        the use-case itself (mod.rs:43-270): path handling, reader, cls_place_batch, writer
+// The Python mirror (classeq2_b200/placement.py) is the second implementation of all of it; tests hold the two
+// byte-identical, and both equal to a reference-written result file.
 #include <algorithm>
 #include <charconv>
 #include <cstdio>
