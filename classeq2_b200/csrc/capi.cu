@@ -124,7 +124,7 @@ struct PackedLayout {
 };
 
 struct Workspace {
-    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // stream3: only the three-stream pipeline (CLS_PIPE=3)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> chunk_ev;  // 4 per chunk: start, kernel start, kernel end, done
     PinBuf h_words, h_descs, h_results;
@@ -154,6 +154,7 @@ struct cls_index {
         for (auto &w : pool) {
             if (w->stream) { cudaStreamSynchronize(w->stream); cudaStreamDestroy(w->stream); }
             if (w->stream2) { cudaStreamSynchronize(w->stream2); cudaStreamDestroy(w->stream2); }
+            if (w->stream3) { cudaStreamSynchronize(w->stream3); cudaStreamDestroy(w->stream3); }
             for (auto &e : w->chunk_ev) if (e) cudaEventDestroy(e);
             for (auto &e : w->ev) if (e) cudaEventDestroy(e);
             w->h_words.release(); w->h_descs.release(); w->h_results.release();
@@ -565,34 +566,46 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
         }
         return CLS_OK;
     };
+    // EXPERIMENT, off by default (CLS_PIPE=3): copies in, kernels and copies out on THREE streams chained by events, so that
+    // the kernels of consecutive chunks never share the SMs.  With the default two alternating streams the persistent
+    // scan kernel of chunk c + 1 can start while the descent kernel of chunk c still holds warp slots: its CTAs that are
+    // not resident yet keep their whole static share of the reads and finish late.  Not measured yet.
+    static const bool pipe3 = [] { const char *e = getenv("CLS_PIPE"); return e && atoi(e) == 3; }();
+    if (pipe3 && !w->stream3) CU_TRY(cudaStreamCreateWithFlags(&w->stream3, cudaStreamNonBlocking));
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk &c = chunks[ci];
-        cudaStream_t st = (ci & 1) ? w->stream2 : w->stream;
+        cudaStream_t st = (ci & 1) ? w->stream2 : w->stream;                 // default: everything of a chunk on one of two streams
+        cudaStream_t st_in = pipe3 ? w->stream2 : st, st_k = pipe3 ? w->stream : st, st_out = pipe3 ? w->stream3 : st;
         cudaEvent_t *ev = &w->chunk_ev[4 * ci];
         const double tp = now_ms();
         pack_batch(batch, lay, word_off, h_words, h_descs, c.first, c.count);
         tm.pack_ms += now_ms() - tp;
         const size_t w0 = word_off[c.first], w1 = word_off[c.first + c.count];
-        CU_TRY(cudaEventRecord(ev[0], st));
-        CU_TRY(cudaMemcpyAsync(d_words + w0, h_words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(d_descs + c.first, h_descs + c.first, (size_t)c.count * sizeof(ReadDesc), cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaEventRecord(ev[1], st));
+        CU_TRY(cudaEventRecord(ev[0], st_in));
+        CU_TRY(cudaMemcpyAsync(d_words + w0, h_words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, st_in));
+        CU_TRY(cudaMemcpyAsync(d_descs + c.first, h_descs + c.first, (size_t)c.count * sizeof(ReadDesc), cudaMemcpyHostToDevice, st_in));
+        CU_TRY(cudaEventRecord(ev[1], st_in));
+        if (pipe3) CU_TRY(cudaStreamWaitEvent(st_k, ev[1], 0));
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         DevBuf &scratch = w->d_scratch[ci & 1];  // stream order protects its reuse by the chunk after next
+        if (pipe3 && place_scratch_bytes(c.count, c.max_len, ix->dix.k_size) > scratch.cap && scratch.p)
+            CU_TRY(cudaStreamSynchronize(st_k));   // growing a scratch buffer frees it: nothing on the kernel stream may still use it
         CU_TRY(scratch.reserve(place_scratch_bytes(c.count, c.max_len, ix->dix.k_size)));
         uint32_t nl = 0;
-        cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_res, g, ix->sm_count, st,
+        cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_res, g, ix->sm_count, st_k,
                                      scratch.p, scratch.cap, &nl);
         if (e != cudaSuccess) {
             cudaStreamSynchronize(w->stream); cudaStreamSynchronize(w->stream2);
+            if (w->stream3) cudaStreamSynchronize(w->stream3);
             if (e == cudaErrorInvalidConfiguration)
                 return fail(CLS_ERR_UNSUPPORTED, "query too long (or tree fan-out too large) for the per-read shared-memory tables");
             return fail(CLS_ERR_CUDA, std::string("place kernel launch: ") + cudaGetErrorString(e));
         }
         tm.kernel_launches += nl;
-        CU_TRY(cudaEventRecord(ev[2], st));
-        CU_TRY(cudaMemcpyAsync(h_res + c.first, d_res + c.first, (size_t)c.count * sizeof(ResultRec), cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaEventRecord(ev[3], st));
+        CU_TRY(cudaEventRecord(ev[2], st_k));
+        if (pipe3) CU_TRY(cudaStreamWaitEvent(st_out, ev[2], 0));
+        CU_TRY(cudaMemcpyAsync(h_res + c.first, d_res + c.first, (size_t)c.count * sizeof(ResultRec), cudaMemcpyDeviceToHost, st_out));
+        CU_TRY(cudaEventRecord(ev[3], st_out));
         if (ci >= 2) { rc = drain(ci - 1); if (rc != CLS_OK) return rc; }  // chunks older than the two in flight
     }
     // fields decided on the host (n_query_kmers of every query; queries that never reach the device): written
