@@ -879,7 +879,27 @@ struct ScanOut {
     uint2 *pairs;
     uint2 *meta;
     uint32_t cap;
+#ifdef CLS_DYNAMIC_READS
+    // EXPERIMENT (-DCLS_DYNAMIC_READS): the persistent warps take reads in blocks of kReadBlock from a global counter
+    // instead of a static stride, so that a CTA which becomes resident late (another kernel still holds its SM) or
+    // draws cheap reads does not decide when the launch ends.  counters[0]: scan kernel, counters[1]: descent kernel;
+    // zeroed by the launcher.
+    uint32_t *counters;
+#endif
 };
+#ifdef CLS_DYNAMIC_READS
+constexpr uint32_t kReadBlock = 4;
+// next read of this warp, or >= n_reads when the launch has run out of reads
+__device__ __forceinline__ uint32_t next_read(uint32_t *counter, uint32_t &base, uint32_t &used) {
+    if (used == kReadBlock) {
+        uint32_t b = 0;
+        if (lane_id() == 0) b = atomicAdd(counter, kReadBlock);
+        base = __shfl_sync(kFull, b, 0);
+        used = 0;
+    }
+    return base + used++;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // The placement kernel, persistent CTAs striding over the query range.
@@ -1086,8 +1106,18 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
     __syncthreads();
 
     const uint32_t gwarp = blockIdx.x * warps_per_cta + warp, gstride = gridDim.x * warps_per_cta;
+#ifdef CLS_DYNAMIC_READS
+    uint32_t dyn_base = 0, dyn_used = kReadBlock;
+    const bool dynamic = SPLIT && so.counters != nullptr;
+#endif
 #pragma unroll 1
+#ifdef CLS_DYNAMIC_READS
+    for (uint32_t r = gwarp;; r += gstride) {
+        if (dynamic) r = next_read(so.counters, dyn_base, dyn_used);
+        if (r >= n_reads) break;
+#else
     for (uint32_t r = gwarp; r < n_reads; r += gstride) {
+#endif
         const ReadDesc rd = reads[first_read + r];
         const uint32_t L = rd.len;
         const uint32_t W = L - 34u;  // host guarantees L >= k = 35
@@ -1218,8 +1248,17 @@ __global__ void CLS_DESCEND_BOUNDS descend_kernel(DeviceIndex ix, PlaceParams pp
     for (uint32_t o = lane; o < fan_cap; o += 32) { cnt[o] = 0; excl[o] = 0; }
     __syncwarp();
     const uint32_t gwarp = blockIdx.x * warps_per_cta + warp, gstride = gridDim.x * warps_per_cta;
+#ifdef CLS_DYNAMIC_READS
+    uint32_t dyn_base = 0, dyn_used = kReadBlock;
+#endif
 #pragma unroll 1
+#ifdef CLS_DYNAMIC_READS
+    for (uint32_t r = gwarp;; r += gstride) {
+        if (so.counters) r = next_read(so.counters + 1, dyn_base, dyn_used);
+        if (r >= n_reads) break;
+#else
     for (uint32_t r = gwarp; r < n_reads; r += gstride) {
+#endif
         const uint2 me = so.meta[r];
         if (me.y == kDone) continue;
         const uint2 *pr = so.pairs + (size_t)r * so.cap;
@@ -1264,13 +1303,25 @@ static bool split_disabled() {
     static const bool off = getenv("CLS_NO_SPLIT") != nullptr;
     return off;
 }
+static inline ScanOut no_scan_out() {
+    ScanOut so{};
+    so.pairs = nullptr; so.meta = nullptr; so.cap = 0;
+    return so;
+}
+#ifdef CLS_DYNAMIC_READS
+static inline size_t scratch_bytes_for(uint32_t n_reads, uint32_t cap) { return (size_t)n_reads * ((size_t)cap * 8 + 8) + 256 + 64; }
+#else
 static inline size_t scratch_bytes_for(uint32_t n_reads, uint32_t cap) { return (size_t)n_reads * ((size_t)cap * 8 + 8) + 256; }
+#endif
 static inline ScanOut carve_scratch(void *scratch, uint32_t n_reads, uint32_t cap) {
     char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
     ScanOut so;
     so.pairs = reinterpret_cast<uint2 *>(base);
     so.meta = so.pairs + (size_t)n_reads * cap;
     so.cap = cap;
+#ifdef CLS_DYNAMIC_READS
+    so.counters = reinterpret_cast<uint32_t *>(so.meta + n_reads);   // 8 bytes used, 64 reserved
+#endif
     return so;
 }
 template <int MAXSLOTS>
@@ -1285,6 +1336,9 @@ static cudaError_t launch_descend(const DeviceIndex &ix, const PlaceParams &pp, 
     uint32_t dgrid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + 7) / 8;
     if (dgrid > need) dgrid = need;
+#ifdef CLS_DYNAMIC_READS
+    if (so.counters && (e = cudaMemsetAsync(so.counters + 1, 0, 4, stream)) != cudaSuccess) return e;
+#endif
     descend_kernel<MAXSLOTS><<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
     return cudaGetLastError();
 }
@@ -1324,7 +1378,7 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
     // kb-scale reads of closed models: the histogram goes to the wide descent kernel when the caller gave scratch
     const bool split = CTA && CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCapWide) &&
                        (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024 && !split_disabled();
-    ScanOut so{nullptr, nullptr, 0};
+    ScanOut so = no_scan_out();
     if (split) so = carve_scratch(scratch, n_reads, kPairCapWide);
     place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so, trace);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1376,8 +1430,11 @@ static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, c
     uint32_t grid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
-    ScanOut so{nullptr, nullptr, 0};
+    ScanOut so = no_scan_out();
     if (split) so = carve_scratch(scratch, n_reads, kPairCap);
+#ifdef CLS_DYNAMIC_READS
+    if (split && (e = cudaMemsetAsync(so.counters, 0, 4, stream)) != cudaSuccess) return e;
+#endif
     kern<<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (n_launches) ++*n_launches;
