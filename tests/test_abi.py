@@ -187,3 +187,30 @@ def test_host_packer_variants_agree_with_numpy():
     assert {0, 1} <= ran
     out = np.zeros(4, np.uint32)
     assert _lib.lib.cls_debug_pack_read(out.ctypes.data_as(_lib.u8p), 4, out.ctypes.data_as(_lib.u32p), 4, 7) == _lib.CLS_ERR_INVALID_ARGUMENT
+
+def test_header_is_plain_c99_and_a_c_program_links(tmp_path):
+    """include/classeq_b200.h is what a foreign-language binding reads: it must be valid C (not only C++), and a C
+    program must link against the library and call into it."""
+    import shutil
+    import subprocess
+    from classeq2_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use.c"
+    src.write_text('#include "classeq_b200.h"\n#include <string.h>\n'
+                   "int main(void) {\n"
+                   "    cls_params p; cls_result r; cls_record_tree t; cls_index *ix = 0;\n"
+                   "    memset(&r, 0, sizeof r); memset(&t, 0, sizeof t);\n"
+                   "    cls_params_default(&p);\n"
+                   "    if (cls_abi_version() != CLS_ABI_VERSION || p.max_iterations != 1000) return 1;\n"
+                   "    if (cls_place_batch(ix, 0, &p, &r) != CLS_ERR_INVALID_ARGUMENT) return 2;   /* NULL handle: refused */\n"
+                   "    if (!cls_last_error()[0]) return 3;\n"
+                   "    return 0;\n}\n")
+    exe = tmp_path / "use"
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                        "-L", lib_dir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + lib_dir, "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert subprocess.run([str(exe)]).returncode == 0
