@@ -1,7 +1,7 @@
 #!/bin/bash
-# The first GPU call of the next round, in one go (about 6 minutes of box time on one B200):
+# The first GPU call of the next round, in one go (about 12 minutes of box time on one B200):
 #   HERE (no GPU), before the call:   bash tools/build_variants.sh
-#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 # 1. the GPU tests written after round 1's GPU time was spent, then the whole GPU suite;
 # 2. parity + kernel timing of every prepared kernel variant against the default library;
 # 3. end-to-end cls_place_batch with the default pipeline and with CLS_PIPE=3, default and best-looking variants;
