@@ -59,3 +59,19 @@ def test_golden_queries_file(col_queries):
     raw = open(os.path.join(here, "golden", "colletotrichum_queries.fasta"), "rb").read()
     headers, bases, offsets = read_fasta_native(raw)
     assert [(h, bytes(bases[int(offsets[i]):int(offsets[i + 1])]).decode()) for i, h in enumerate(headers)] == col_queries
+
+
+def test_reference_alignment_file_filters_to_the_gap_free_sequences(oracle, col_queries):
+    """The reference ships the 171 Colletotrichum sequences twice: gap-free, and as a MAFFT alignment (lower case, '-'
+    gaps) - the input of its own build test.  The reader's filter (sequence.rs:47-56) must turn the second into the
+    first: held for the oracle's reader, the Python mirror and the library's host reader."""
+    import os
+    from classeq2_b200.placement import read_fasta_native, read_fasta_text
+    here = os.path.dirname(os.path.abspath(__file__))
+    raw = open(os.path.join(here, "golden", "Colletotrichum_acutatum_gapdh_mafft.fasta"), "rb").read()
+    assert b"-" in raw and raw.lower().count(b"a") > raw.count(b"A")            # aligned, mostly lower case
+    want = col_queries[:171]
+    assert oracle.read_fasta_text(raw.decode()) == want
+    assert read_fasta_text(raw.decode()) == want
+    headers, bases, offsets = read_fasta_native(raw)
+    assert [(h, bytes(bases[int(offsets[i]):int(offsets[i + 1])]).decode()) for i, h in enumerate(headers)] == want
