@@ -124,3 +124,17 @@ def test_map_kmers_to_tree_reference_pairing(tmp_path, oracle, col_queries):
            {k: {h: set(n) for h, n in v.items()} for k, v in want.kmers_map.map.items()}
     own = build.map_kmers_to_tree(golden, msa)
     assert own.kmers_map.map != got.kmers_map.map
+
+
+def test_toy_newick_of_the_reference(oracle):
+    """core/src/tests/data/tree.nwk (six tips, supports written as fractions): the mirror's parser / sanitize and the
+    oracle's agree for thresholds below, between and above the supports; above them everything collapses into the root."""
+    from classeq2_b200 import build
+    toy = "(((A:0.1,B:0.2)0.7:0.5,(E:0.1,F:0.2)0.95:0.3)0.98:0.1,(C:0.3,D:0.4)0.99:0.5);"
+    for thr in (0.0, 0.5, 0.8, 0.97, 70.0):
+        a, b = build.tree_from_newick(toy, "tree.nwk", thr), oracle.tree_from_newick(toy, "tree.nwk", thr)
+        assert a.root.to_obj() == b.root.to_obj() and a.id == b.id
+    star = build.tree_from_newick(toy, "tree.nwk", 70.0).root
+    assert [c.name for c in star.children] == ["A", "B", "E", "F", "C", "D"] and all(c.is_leaf() for c in star.children)
+    full = build.tree_from_newick(toy, "tree.nwk", 0.0).root
+    assert [c.id for c in full.walk()] == list(range(11))        # phylotree numbers the nodes in pre-order
