@@ -100,33 +100,45 @@ bool parses_as_float(const std::string &s0) {
     return i == s.size();
 }
 
-// str.strip() of the Python mirror: the code points for which str.isspace() holds
-bool is_space_cp(uint32_t c) {
-    return c == ' ' || (c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x1F) || c == 0x85 || c == 0xA0 || c == 0x1680 ||
-           (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
-}
-uint32_t decode_utf8(const unsigned char *p, size_t n) {   // first code point of p[0..n); malformed bytes stand for themselves
-    if (n >= 2 && (p[0] & 0xE0) == 0xC0) return ((p[0] & 0x1Fu) << 6) | (p[1] & 0x3Fu);
-    if (n >= 3 && (p[0] & 0xF0) == 0xE0) return ((p[0] & 0x0Fu) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3Fu);
-    if (n >= 4 && (p[0] & 0xF8) == 0xF0) return ((p[0] & 0x07u) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3Fu);
-    return p[0];
-}
-bool space_at_either_end(const std::string &s) {
-    const unsigned char *b = reinterpret_cast<const unsigned char *>(s.data());
-    if (is_space_cp(decode_utf8(b, s.size()))) return true;
-    size_t i = s.size() - 1;
-    while (i > 0 && (b[i] & 0xC0) == 0x80) --i;   // back to the lead byte of the last code point
-    return is_space_cp(decode_utf8(b + i, s.size() - i));
+// One UTF-8 code point of s starting at byte i (advances i); malformed bytes come back as 0xFFFF'FFFF (treated as special).
+uint32_t next_cp(const std::string &s, size_t &i) {
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(s.data());
+    const size_t n = s.size() - i;
+    const unsigned char c = p[i];
+    auto cont = [&](size_t k) { return (p[i + k] & 0xC0) == 0x80; };
+    if (c < 0x80) { ++i; return c; }
+    if ((c & 0xE0) == 0xC0 && n >= 2 && cont(1)) { const uint32_t v = ((c & 0x1Fu) << 6) | (p[i + 1] & 0x3Fu); i += 2; return v; }
+    if ((c & 0xF0) == 0xE0 && n >= 3 && cont(1) && cont(2)) {
+        const uint32_t v = ((c & 0x0Fu) << 12) | ((p[i + 1] & 0x3Fu) << 6) | (p[i + 2] & 0x3Fu); i += 3; return v;
+    }
+    if ((c & 0xF8) == 0xF0 && n >= 4 && cont(1) && cont(2) && cont(3)) {
+        const uint32_t v = ((c & 0x07u) << 18) | ((p[i + 1] & 0x3Fu) << 12) | ((p[i + 2] & 0x3Fu) << 6) | (p[i + 3] & 0x3Fu); i += 4; return v;
+    }
+    ++i;
+    return 0xFFFFFFFFu;
 }
 
-// whether libyaml (hence serde_yaml) may emit the string as a plain scalar
+// Outside libyaml's printable set (IS_PRINTABLE: 0x0A, 0x20-0x7E, 0x85, 0xA0-0xD7FF, 0xE000-0xFFFD without the BOM); 0x85
+// and the Unicode line separators count as breaks, which a quoted one-line scalar cannot hold unescaped either.
+bool yaml_special(uint32_t o) {
+    return o < 0x20 || o == 0x7F || (o >= 0x80 && o <= 0x9F) || o == 0x2028 || o == 0x2029 || o == 0xFEFF ||
+           (o >= 0xD800 && o <= 0xDFFF) || o >= 0xFFFE;
+}
+bool has_yaml_special(const std::string &s) {
+    for (size_t i = 0; i < s.size();)
+        if (yaml_special(next_cp(s, i))) return true;
+    return false;
+}
+
+// whether libyaml (hence serde_yaml) may emit the string as a plain scalar - or, for text that reads as a number, a
+// boolean or null, whether serde_yaml leaves the choice to libyaml at all
 bool yaml_plain_ok(const std::string &s) {
-    if (s.empty() || space_at_either_end(s)) return false;
+    if (s.empty() || s.front() == ' ' || s.back() == ' ') return false;            // libyaml looks at 0x20 only
+    if (s.compare(0, 3, "---") == 0 || s.compare(0, 3, "...") == 0) return false;   // document markers
     static const char special[] = "-?:,[]{}#&*!|>'\"%@`";
     if (strchr(special, s[0]) && !(strchr("-?:", s[0]) && s.size() > 1 && s[1] != ' ' && s[1] != '\t')) return false;
     if (s.find(": ") != std::string::npos || s.find(" #") != std::string::npos || s.back() == ':') return false;
-    for (unsigned char c : s)
-        if (c < 0x20 || c == 0x7F) return false;
+    if (has_yaml_special(s)) return false;
     static const char *words[] = {"null", "~", "true", "false", "yes", "no", "on", "off", "y", "n", ".nan", ".inf", "-.inf", "+.inf"};
     for (const char *w : words)
         if (ieq(s, w)) return false;
@@ -153,17 +165,44 @@ void yaml_string(const std::string &s, int indent, std::string &out) {
         return;
     }
     if (yaml_plain_ok(s)) { out += s; return; }
-    const bool has_sq = s.find('\'') != std::string::npos, has_dq = s.find('"') != std::string::npos,
-               has_bs = s.find('\\') != std::string::npos;
-    if (!has_sq || has_dq || has_bs) {
+    // libyaml's choice when a plain scalar is not allowed (yaml_emitter_select_scalar_style): single quotes ('' for an
+    // apostrophe) unless the text holds a character outside its printable set - then double quotes with its escapes
+    if (!has_yaml_special(s)) {
         out += '\'';
         for (char c : s) { if (c == '\'') out += '\''; out += c; }
         out += '\'';
-    } else {
-        out += '"';
-        for (char c : s) { if (c == '\\' || c == '"') out += '\\'; out += c; }
-        out += '"';
+        return;
     }
+    out += '"';
+    char buf[16];
+    for (size_t i = 0; i < s.size();) {
+        const size_t at = i;
+        const uint32_t o = next_cp(s, i);
+        switch (o) {
+            case 0x00: out += "\\0"; continue;
+            case 0x07: out += "\\a"; continue;
+            case 0x08: out += "\\b"; continue;
+            case 0x09: out += "\\t"; continue;
+            case 0x0A: out += "\\n"; continue;
+            case 0x0B: out += "\\v"; continue;
+            case 0x0C: out += "\\f"; continue;
+            case 0x0D: out += "\\r"; continue;
+            case 0x1B: out += "\\e"; continue;
+            case '"': out += "\\\""; continue;
+            case '\\': out += "\\\\"; continue;
+            case 0x85: out += "\\N"; continue;
+            case 0x2028: out += "\\L"; continue;
+            case 0x2029: out += "\\P"; continue;
+            default: break;
+        }
+        if (!yaml_special(o)) { out.append(s, at, i - at); continue; }
+        const uint32_t v = o == 0xFFFFFFFFu ? (unsigned char)s[at] : o;   // a malformed byte stands for itself
+        if (v <= 0xFF) snprintf(buf, sizeof buf, "\\x%02X", v);
+        else if (v <= 0xFFFF) snprintf(buf, sizeof buf, "\\u%04X", v);
+        else snprintf(buf, sizeof buf, "\\U%08X", v);
+        out += buf;
+    }
+    out += '"';
 }
 
 void json_string(const std::string &s, std::string &out) {  // serde_json: raw UTF-8, the short escapes, \u00XX for controls

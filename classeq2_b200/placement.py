@@ -164,21 +164,34 @@ _YAML_SPECIAL_FIRST = set("-?:,[]{}#&*!|>'\"%@`")
 
 def _yaml_plain_ok(s: str) -> bool:
     """Whether libyaml (hence serde_yaml) may emit the string as a plain scalar."""
-    if s == "" or s != s.strip() or s[0] in _YAML_SPECIAL_FIRST and not (s[0] in "-?:" and len(s) > 1 and s[1] not in " \t"):
+    if s == "" or s[0] == " " or s[-1] == " " or s.startswith(("---", "...")):   # libyaml: 0x20 only; document markers
         return False
-    if ": " in s or " #" in s or s.endswith(":") or any(ord(c) < 0x20 or c == "\x7f" for c in s):
+    if s[0] in _YAML_SPECIAL_FIRST and not (s[0] in "-?:" and len(s) > 1 and s[1] not in " \t"):
+        return False
+    if ": " in s or " #" in s or s.endswith(":") or any(_yaml_special(ord(c)) for c in s):
         return False
     low = s.lower()
     if low in ("null", "~", "true", "false", "yes", "no", "on", "off", "y", "n", ".nan", ".inf", "-.inf", "+.inf"):
         return False
-    try:  # would re-parse as a number
-        float(s.replace("_", ""))
-        return False
+    try:  # would re-parse as a number (float() itself would also accept surrounding Unicode blanks: not a number to YAML)
+        if s == s.strip():
+            float(s.replace("_", ""))
+            return False
     except ValueError:
         pass
     if low.startswith(("0x", "0o")) or s[0] in "+-." and s[1:2].isdigit():
         return False
     return True
+
+
+_YAML_ESCAPES = {"\0": "\\0", "\a": "\\a", "\b": "\\b", "\t": "\\t", "\n": "\\n", "\v": "\\v", "\f": "\\f", "\r": "\\r",
+                 "\x1b": "\\e", '"': '\\"', "\\": "\\\\", "\x85": "\\N", "\u2028": "\\L", "\u2029": "\\P"}
+
+
+def _yaml_special(o: int) -> bool:
+    """Outside libyaml's printable set (IS_PRINTABLE: 0x0A, 0x20-0x7E, 0x85, 0xA0-0xD7FF, 0xE000-0xFFFD without the BOM);
+    0x85 and the Unicode line separators count as breaks, which a quoted one-line scalar cannot hold unescaped either."""
+    return o < 0x20 or o == 0x7F or 0x80 <= o <= 0x9F or o in (0x2028, 0x2029, 0xFEFF) or 0xD800 <= o <= 0xDFFF or o >= 0xFFFE
 
 
 def _yaml_scalar(v, indent: int) -> str:
@@ -198,9 +211,25 @@ def _yaml_scalar(v, indent: int) -> str:
         return "|" + chomp + "\n" + "\n".join((pad + ln) if ln else "" for ln in body.split("\n"))
     if _yaml_plain_ok(s):
         return s
-    if "'" not in s or '"' in s or "\\" in s:
+    # libyaml's choice when a plain scalar is not allowed: single quotes ('' for an apostrophe) unless the text holds a
+    # character outside its printable set - then double quotes with its escapes (yaml_emitter_select_scalar_style)
+    if not any(_yaml_special(ord(ch)) for ch in s):
         return "'" + s.replace("'", "''") + "'"
-    return '"' + s.replace("\\", "\\\\").replace('"', '\\"') + '"'
+    out = ['"']
+    for ch in s:
+        o = ord(ch)
+        if ch in _YAML_ESCAPES:
+            out.append(_YAML_ESCAPES[ch])
+        elif not _yaml_special(o):
+            out.append(ch)
+        elif o <= 0xFF:
+            out.append("\\x%02X" % o)
+        elif o <= 0xFFFF:
+            out.append("\\u%04X" % o)
+        else:
+            out.append("\\U%08X" % o)
+    out.append('"')
+    return "".join(out)
 
 
 def yaml_dump(obj, indent: int = 0) -> str:

@@ -247,3 +247,55 @@ def test_native_sequences_open_and_write(ps, tmp_path, col_tree, col_flat, fmt):
     assert (tmp_path / "n" / f"r.{fmt}").read_bytes() == want_o
     assert (tmp_path / "n" / "r.error").read_bytes() == want_e + want_e
     index.close()
+
+
+_ALPHABET = list("abzAZ019 _-.:,#'\"\\/|>!&*?[]{}%@`~+=()<;$^") + ["\t", "\x01", "\x7f", "é", "日", "\x85", "\xa0", "﻿", "\U0001F600", "\r", " "]
+
+
+def test_quoting_agrees_with_libyaml_on_random_strings(ps):
+    """Where serde_yaml leaves the scalar style to libyaml (text that does not read as a number / boolean / null), the
+    emitters must choose what libyaml's emitter chooses: plain, else single-quoted, else - for text outside its printable
+    set - double-quoted with its escapes.  PyYAML's C emitter IS libyaml's; 150 000 random strings."""
+    import random
+    dumper = getattr(yaml, "CSafeDumper", None)
+    if dumper is None:
+        pytest.skip("PyYAML without libyaml")
+    resolver = yaml.resolver.Resolver()
+    rng = random.Random(11)
+    n = 0
+    for _ in range(150_000):
+        s = "".join(rng.choice(_ALPHABET[:-1]) for _ in range(rng.randint(1, 7)))
+        if resolver.resolve(yaml.ScalarNode, s, (True, False)) != "tag:yaml.org,2002:str":
+            continue                                    # PyYAML's YAML 1.1 typing would quote it for its own reasons
+        low = s.lower()
+        try:
+            float(s.replace("_", ""))
+            continue
+        except ValueError:
+            pass
+        if low in ("null", "~", "true", "false", "yes", "no", "on", "off", "y", "n") or low.startswith(("0x", "0o")) or (
+                s[0] in "+-." and s[1:2].isdigit()):
+            continue                                    # serde_yaml's own "ambiguous" rule, not libyaml's
+        out = yaml.dump({"k": s}, Dumper=dumper, width=10**9, allow_unicode=True, default_flow_style=False)
+        want = out[3:].rstrip("\n") if out.startswith("k: ") else out[2:]
+        assert ps._yaml_scalar(s, 2) == want, repr(s)
+        n += 1
+    assert n > 100_000
+
+
+def test_native_writer_equals_python_on_random_headers(ps, col_tree):
+    """The same random strings (plus number-like and multi-line ones) as query headers and clade names: C++ == Python."""
+    import random
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib, Clade, Tree
+    rng = random.Random(12)
+    extra = ["1", "-1", "1e5", ".5", "0x10", "true", "NULL", "~", "yes", "007", "1_000", "+.inf", "a\nb", "x\n", "---", "...", "--- a", ".. ."]
+    strings = ["".join(rng.choice(_ALPHABET) for _ in range(rng.randint(1, 9))) for _ in range(6000)] + extra
+    kids = [Clade(id=10 + i, parent=1, kind="LEAF", name=s, length=0.5) for i, s in enumerate(strings[:400])]
+    root = Clade(id=0, parent=None, kind="ROOT", children=[Clade(id=1, parent=0, kind="NODE", children=kids)])
+    tree = Tree("t", "t", 70.0, root)
+    n = len(strings)
+    res = cq.BatchResult(n)
+    res.status[:] = [_lib.STATUS_UNCL_NO_MATCH if i % 2 else _lib.STATUS_UNCL_NO_ROOT for i in range(n)]
+    res.status[0], res.node_id[0] = _lib.STATUS_IDENTITY_FOUND, 1          # one record that prints all the names
+    _check(ps, strings, res, tree)
