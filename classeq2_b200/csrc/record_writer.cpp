@@ -67,37 +67,70 @@ void ryu_float(double x, bool json, std::string &out) {
 }
 
 // ---- strings ------------------------------------------------------------------------------------------------
-bool ieq(const std::string &s, const char *w) {
-    size_t i = 0;
-    for (; i < s.size() && w[i]; ++i)
-        if (tolower((unsigned char)s[i]) != w[i]) return false;
-    return i == s.size() && !w[i];
-}
-
-// Python's float(s.replace("_", "")) accepts the string (ASCII forms only)
-bool parses_as_float(const std::string &s0) {
-    std::string s;
-    for (char c : s0)
-        if (c != '_') s += c;
-    size_t i = 0;
-    if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
-    const std::string rest = s.substr(i);
-    if (ieq(rest, "inf") || ieq(rest, "infinity") || ieq(rest, "nan")) return true;
-    size_t nd = 0;
-    while (i < s.size() && isdigit((unsigned char)s[i])) { ++i; ++nd; }
-    if (i < s.size() && s[i] == '.') {
-        ++i;
-        while (i < s.size() && isdigit((unsigned char)s[i])) { ++i; ++nd; }
+// serde_yaml 0.9 (ser.rs serialize_str -> de.rs visit_untagged_scalar; the crate is not vendored in the reference tree, this
+// restates its published source): a string that would read back as null, a boolean, an integer or a finite float under
+// the YAML 1.2 core schema - or as digits with a leading zero - is emitted single-quoted; for everything else the style is
+// libyaml's choice.
+bool reads_as_another_type(const std::string &s) {
+    static const char *words[] = {"null", "Null", "NULL", "~", "true", "True", "TRUE", "false", "False", "FALSE"};
+    if (s.empty()) return true;
+    for (const char *w : words)
+        if (s == w) return true;
+    for (unsigned char c : s)
+        if (c >= 0x80) return false;
+    const std::string body = (s[0] == '+' || s[0] == '-') ? s.substr(1) : s;
+    auto digit = [](char c) { return c >= '0' && c <= '9'; };
+    if (body.size() > 2 && body[0] == '0' && (body[1] == 'x' || body[1] == 'o' || body[1] == 'b')) {   // parse_unsigned_int / parse_negative_int
+        const int bits_per = body[1] == 'x' ? 4 : body[1] == 'o' ? 3 : 1;
+        bool ok = true;
+        size_t first = std::string::npos;   // first non-zero digit
+        for (size_t i = 2; i < body.size() && ok; ++i) {
+            const char c = body[i];
+            const int v = digit(c) ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : 99;
+            ok = v < (1 << bits_per);
+            if (ok && v && first == std::string::npos) first = i;
+        }
+        if (ok) {
+            if (first == std::string::npos) return true;   // zero
+            const char c = body[first];
+            const int v = digit(c) ? c - '0' : (c | 0x20) - 'a' + 10;
+            int top = 0;
+            while ((v >> top) > 1) ++top;                   // bit length of the leading digit - 1
+            const size_t bits = (body.size() - first - 1) * (size_t)bits_per + (size_t)top + 1;
+            if (bits <= 128) return true;                   // fits u128 (from_str_radix)
+        }
     }
-    if (nd == 0) return false;
-    if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
+    bool all_digits = !body.empty();
+    for (char c : body) all_digits = all_digits && digit(c);
+    if (all_digits) return true;                            // an integer, or digits_but_not_number (a leading zero)
+    std::string unpositive = s;
+    if (s[0] == '+') {
+        unpositive = s.substr(1);
+        if (!unpositive.empty() && (unpositive[0] == '+' || unpositive[0] == '-')) return false;
+    }
+    if (unpositive == ".inf" || unpositive == ".Inf" || unpositive == ".INF" || s == "-.inf" || s == "-.Inf" || s == "-.INF" ||
+        s == ".nan" || s == ".NaN" || s == ".NAN")
+        return true;
+    // str::parse::<f64>(): [+-]? (digits+ [. digits*] | . digits+) [(e|E) [+-]? digits+], then is_finite()
+    size_t i = 0;
+    const std::string &u = unpositive;
+    if (i < u.size() && (u[i] == '+' || u[i] == '-')) ++i;
+    size_t ni = 0, nf = 0;
+    while (i < u.size() && digit(u[i])) { ++i; ++ni; }
+    if (i < u.size() && u[i] == '.') {
         ++i;
-        if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
+        while (i < u.size() && digit(u[i])) { ++i; ++nf; }
+    }
+    if (ni + nf == 0) return false;
+    if (i < u.size() && (u[i] == 'e' || u[i] == 'E')) {
+        ++i;
+        if (i < u.size() && (u[i] == '+' || u[i] == '-')) ++i;
         size_t ne = 0;
-        while (i < s.size() && isdigit((unsigned char)s[i])) { ++i; ++ne; }
+        while (i < u.size() && digit(u[i])) { ++i; ++ne; }
         if (ne == 0) return false;
     }
-    return i == s.size();
+    if (i != u.size()) return false;
+    return std::isfinite(strtod(u.c_str(), nullptr));
 }
 
 // One UTF-8 code point of s starting at byte i (advances i); malformed bytes come back as 0xFFFF'FFFF (treated as special).
@@ -133,18 +166,13 @@ bool has_yaml_special(const std::string &s) {
 // whether libyaml (hence serde_yaml) may emit the string as a plain scalar - or, for text that reads as a number, a
 // boolean or null, whether serde_yaml leaves the choice to libyaml at all
 bool yaml_plain_ok(const std::string &s) {
-    if (s.empty() || s.front() == ' ' || s.back() == ' ') return false;            // libyaml looks at 0x20 only
+    if (reads_as_another_type(s)) return false;                                     // serde_yaml forces single quotes
+    if (s.front() == ' ' || s.back() == ' ') return false;                          // libyaml looks at 0x20 only
     if (s.compare(0, 3, "---") == 0 || s.compare(0, 3, "...") == 0) return false;   // document markers
     static const char special[] = "-?:,[]{}#&*!|>'\"%@`";
     if (strchr(special, s[0]) && !(strchr("-?:", s[0]) && s.size() > 1 && s[1] != ' ' && s[1] != '\t')) return false;
     if (s.find(": ") != std::string::npos || s.find(" #") != std::string::npos || s.back() == ':') return false;
     if (has_yaml_special(s)) return false;
-    static const char *words[] = {"null", "~", "true", "false", "yes", "no", "on", "off", "y", "n", ".nan", ".inf", "-.inf", "+.inf"};
-    for (const char *w : words)
-        if (ieq(s, w)) return false;
-    if (parses_as_float(s)) return false;
-    if (s.size() >= 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X' || s[1] == 'o' || s[1] == 'O')) return false;
-    if ((s[0] == '+' || s[0] == '-' || s[0] == '.') && s.size() > 1 && isdigit((unsigned char)s[1])) return false;
     return true;
 }
 

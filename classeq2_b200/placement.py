@@ -162,24 +162,51 @@ class Tag:
 _YAML_SPECIAL_FIRST = set("-?:,[]{}#&*!|>'\"%@`")
 
 
+_F64 = None
+
+
+def _serde_yaml_reads_it_as_another_type(s: str) -> bool:
+    """serde_yaml 0.9 (``ser.rs`` ``serialize_str`` -> ``de.rs`` ``visit_untagged_scalar``; the crate is not vendored in the
+    reference tree, this restates its published source): a string that would read back as null, a boolean, an integer or
+    a finite float under the YAML 1.2 core schema - or as digits with a leading zero - is emitted single-quoted; for
+    everything else the style is libyaml's choice."""
+    global _F64
+    import math
+    import re
+    if _F64 is None:
+        _F64 = re.compile(r"[+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?\Z")
+    if s in ("", "null", "Null", "NULL", "~", "true", "True", "TRUE", "false", "False", "FALSE"):
+        return True
+    if not s.isascii():
+        return False
+    body = s[1:] if s[0] in "+-" else s
+    if body[:2] in ("0x", "0o", "0b"):                      # parse_unsigned_int / parse_negative_int
+        digits = {"0x": "0123456789abcdefABCDEF", "0o": "01234567", "0b": "01"}[body[:2]]
+        rest = body[2:]
+        if rest and all(c in digits for c in rest) and int(rest, {"0x": 16, "0o": 8, "0b": 2}[body[:2]]) < 2 ** 128:
+            return True
+    if body.isdigit():                                      # an integer, or digits_but_not_number (a leading zero)
+        return True
+    unpositive = s
+    if s[0] == "+":
+        unpositive = s[1:]
+        if unpositive[:1] in ("+", "-"):
+            return False
+    if unpositive in (".inf", ".Inf", ".INF") or s in ("-.inf", "-.Inf", "-.INF", ".nan", ".NaN", ".NAN"):
+        return True
+    return bool(_F64.match(unpositive)) and math.isfinite(float(unpositive))        # str::parse::<f64>() and is_finite()
+
+
 def _yaml_plain_ok(s: str) -> bool:
-    """Whether libyaml (hence serde_yaml) may emit the string as a plain scalar."""
-    if s == "" or s[0] == " " or s[-1] == " " or s.startswith(("---", "...")):   # libyaml: 0x20 only; document markers
+    """Whether the string goes out as a plain scalar: serde_yaml leaves the style to libyaml (see above) and libyaml's
+    ``yaml_emitter_analyze_scalar`` allows a plain scalar in block context."""
+    if _serde_yaml_reads_it_as_another_type(s):
+        return False
+    if s[0] == " " or s[-1] == " " or s.startswith(("---", "...")):   # libyaml: 0x20 only; document markers
         return False
     if s[0] in _YAML_SPECIAL_FIRST and not (s[0] in "-?:" and len(s) > 1 and s[1] not in " \t"):
         return False
     if ": " in s or " #" in s or s.endswith(":") or any(_yaml_special(ord(c)) for c in s):
-        return False
-    low = s.lower()
-    if low in ("null", "~", "true", "false", "yes", "no", "on", "off", "y", "n", ".nan", ".inf", "-.inf", "+.inf"):
-        return False
-    try:  # would re-parse as a number (float() itself would also accept surrounding Unicode blanks: not a number to YAML)
-        if s == s.strip():
-            float(s.replace("_", ""))
-            return False
-    except ValueError:
-        pass
-    if low.startswith(("0x", "0o")) or s[0] in "+-." and s[1:2].isdigit():
         return False
     return True
 

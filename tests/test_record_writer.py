@@ -267,15 +267,8 @@ def test_quoting_agrees_with_libyaml_on_random_strings(ps):
         s = "".join(rng.choice(_ALPHABET[:-1]) for _ in range(rng.randint(1, 7)))
         if resolver.resolve(yaml.ScalarNode, s, (True, False)) != "tag:yaml.org,2002:str":
             continue                                    # PyYAML's YAML 1.1 typing would quote it for its own reasons
-        low = s.lower()
-        try:
-            float(s.replace("_", ""))
-            continue
-        except ValueError:
-            pass
-        if low in ("null", "~", "true", "false", "yes", "no", "on", "off", "y", "n") or low.startswith(("0x", "0o")) or (
-                s[0] in "+-." and s[1:2].isdigit()):
-            continue                                    # serde_yaml's own "ambiguous" rule, not libyaml's
+        if ps._serde_yaml_reads_it_as_another_type(s):
+            continue                                    # serde_yaml's own rule (single quotes), not libyaml's choice
         out = yaml.dump({"k": s}, Dumper=dumper, width=10**9, allow_unicode=True, default_flow_style=False)
         want = out[3:].rstrip("\n") if out.startswith("k: ") else out[2:]
         assert ps._yaml_scalar(s, 2) == want, repr(s)
@@ -289,7 +282,11 @@ def test_native_writer_equals_python_on_random_headers(ps, col_tree):
     import classeq2_b200 as cq
     from classeq2_b200 import _lib, Clade, Tree
     rng = random.Random(12)
-    extra = ["1", "-1", "1e5", ".5", "0x10", "true", "NULL", "~", "yes", "007", "1_000", "+.inf", "a\nb", "x\n", "---", "...", "--- a", ".. ."]
+    extra = ["1", "-1", "1e5", ".5", "0x10", "true", "NULL", "~", "yes", "007", "1_000", "+.inf", "a\nb", "x\n", "---", "...", "--- a", ".. .",
+             "null", "nULL", "TRUE", "tRue", "no", "y", "+1", "++1", "-007", "0", "00", "0x1F", "0xg", "0x", "0o7", "0o8", "0b101", "0b2", "-0x1f",
+             "+0x1f", "0x" + "f" * 32, "0x1" + "0" * 32, "0o3" + "7" * 42, "0o4" + "0" * 42, "0b" + "1" * 128, "0b" + "1" * 129, "0x000", "1.5",
+             "1.", "+.5", "1E-5", "1e", "e5", ".", "-", "-.INF", ".NaN", ".nan", "-.nan", "inf", "nan", "infinity", "1e999", "1e-999", "12a",
+             "-1x", "1 2", "\u0661\u0662", "9" * 60, "-" + "9" * 60, "+-1", "-+1", "1e+5", "1e+", ".e5", "5.e5", "-.5e-3"]
     strings = ["".join(rng.choice(_ALPHABET) for _ in range(rng.randint(1, 9))) for _ in range(6000)] + extra
     kids = [Clade(id=10 + i, parent=1, kind="LEAF", name=s, length=0.5) for i, s in enumerate(strings[:400])]
     root = Clade(id=0, parent=None, kind="ROOT", children=[Clade(id=1, parent=0, kind="NODE", children=kids)])
