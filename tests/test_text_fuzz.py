@@ -21,7 +21,7 @@ def test_reader_and_writer_are_clean_under_asan_ubsan(tmp_path):
     assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
     if r.returncode != 0:
         pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
-    r = subprocess.run([exe, "150"], env=dict(os.environ, CLS_HOST_THREADS="4"), capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, "100"], env=dict(os.environ, CLS_HOST_THREADS="4"), capture_output=True, text=True, timeout=600)
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
     assert r.returncode == 0 and r.stdout.strip() == "bad=0", (r.returncode, r.stdout, r.stderr[-500:])
 
@@ -35,7 +35,7 @@ def test_model_serialisation_refuses_malformed_views_without_crashing(tmp_path):
     assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
     if r.returncode != 0:
         pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
-    r = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
     assert r.returncode == 0 and r.stdout.startswith("ok="), (r.returncode, r.stdout, r.stderr[-500:])
 
