@@ -476,14 +476,20 @@ int render(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, 
         for (uint64_t b = b0; b < b1; ++b) {
             std::string &o = outs[b], &e = errs[b];
             const uint64_t hi = std::min(n, (b + 1) * kBlock);
-            for (uint64_t i = b * kBlock; i < hi; ++i) {
-                const std::string header(headers + header_off[i], headers + header_off[i + 1]);
-                if (!render_one(tv, header, res, i, format == 0, o, e, scratch, clade_text)) bad[b] = 1;
+            try {   // nothing may escape a pool thread
+                for (uint64_t i = b * kBlock; i < hi; ++i) {
+                    const std::string header(headers + header_off[i], headers + header_off[i + 1]);
+                    if (!render_one(tv, header, res, i, format == 0, o, e, scratch, clade_text)) bad[b] = 1;
+                }
+            } catch (...) {
+                bad[b] = 2;
             }
         }
     });
-    for (uint8_t x : bad)
+    for (uint8_t x : bad) {
+        if (x == 2) return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while rendering records");
         if (x) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "unknown status, or a placement node id that is not in the tree");
+    }
     *out_text = to_malloc(outs, out_len);
     *err_text = to_malloc(errs, err_len);
     if (!*out_text || !*err_text) {
