@@ -438,13 +438,11 @@ char *to_malloc(const std::vector<std::string> &parts, uint64_t *len) {
     return buf;
 }
 
-int render(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, const char *headers, const cls_result *res,
-           uint32_t format, char **out_text, uint64_t *out_len, char **err_text, uint64_t *err_len) {
+// Renders blocks of 2 048 records on the host pool: outs[b] / errs[b] hold the record text / error text of block b.
+int render_blocks(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, const char *headers, const cls_result *res,
+                  uint32_t format, std::vector<std::string> &outs, std::vector<std::string> &errs) {
     using cls::set_last_error;
-    if (!tree || !res || !out_text || !out_len || !err_text || !err_len || (n && (!header_off || !headers)))
-        return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
-    *out_text = *err_text = nullptr;
-    *out_len = *err_len = 0;
+    if (!tree || !res || (n && (!header_off || !headers))) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (format > 1) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "format must be 0 (yaml) or 1 (jsonl)");
     if (n && (!res->status || !res->node_id || !res->one || !res->rest)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "result arrays are NULL");
     // the child lists must form a forest (as cls_index_create demands of the same tree): the Clade writers recurse over them
@@ -468,7 +466,8 @@ int render(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, 
     for (uint64_t i = 0; i < tree->n_nodes; ++i) tv.by_id.emplace(tree->node_id[i], i);   // emplace keeps the first
     constexpr uint64_t kBlock = 2048;
     const uint64_t nblk = (n + kBlock - 1) / kBlock;
-    std::vector<std::string> outs(nblk), errs(nblk);
+    outs.assign(nblk, std::string());
+    errs.assign(nblk, std::string());
     std::vector<uint8_t> bad(nblk, 0);
     cls::parallel_for(nblk, 1, [&](uint64_t b0, uint64_t b1) {
         std::vector<uint64_t> scratch;
@@ -490,6 +489,18 @@ int render(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, 
         if (x == 2) return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while rendering records");
         if (x) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "unknown status, or a placement node id that is not in the tree");
     }
+    return CLS_OK;
+}
+
+int render(const cls_record_tree *tree, uint64_t n, const uint64_t *header_off, const char *headers, const cls_result *res,
+           uint32_t format, char **out_text, uint64_t *out_len, char **err_text, uint64_t *err_len) {
+    using cls::set_last_error;
+    if (!out_text || !out_len || !err_text || !err_len) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out_text = *err_text = nullptr;
+    *out_len = *err_len = 0;
+    std::vector<std::string> outs, errs;
+    const int rc = render_blocks(tree, n, header_off, headers, res, format, outs, errs);
+    if (rc != CLS_OK) return rc;
     *out_text = to_malloc(outs, out_len);
     *err_text = to_malloc(errs, err_len);
     if (!*out_text || !*err_text) {
@@ -657,6 +668,15 @@ bool read_whole(FILE *f, std::string &out) {
     return !ferror(f);
 }
 
+bool append_blocks(const std::string &path, const std::vector<std::string> &blocks) {
+    FILE *f = fopen(path.c_str(), "ab");
+    if (!f) return false;
+    bool ok = true;
+    for (const std::string &b : blocks)
+        if (!b.empty() && fwrite(b.data(), 1, b.size(), f) != b.size()) { ok = false; break; }
+    return fclose(f) == 0 && ok;
+}
+
 bool append_file(const std::string &path, const char *data, uint64_t n) {
     FILE *f = fopen(path.c_str(), "ab");
     if (!f) return false;
@@ -722,17 +742,19 @@ extern "C" int cls_sequences_write(cls_sequences *s, const cls_record_tree *tree
     using cls::set_last_error;
     if (!s || !tree || !result) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
     if (s->written + n > s->rec.n_records) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "more results than records");
-    char *o = nullptr, *e = nullptr;
-    uint64_t no = 0, ne = 0;
-    // header_off is absolute into `headers`: the writer takes the sub-array as it is
-    const int rc = cls_records_render(tree, n, s->header_off.data() + s->written, s->headers.data(), result, s->format, &o, &no, &e, &ne);
-    if (rc != CLS_OK) return rc;
-    const bool ok = append_file(s->out_path, o, no) && append_file(s->err_path, e, ne);
-    cls_text_free(o);
-    cls_text_free(e);
-    if (!ok) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "Error writing to file: " + s->out_path);
-    s->written += n;
-    return CLS_OK;
+    try {
+        std::vector<std::string> outs, errs;
+        // header_off is absolute into `headers`: the writer takes the sub-array as it is; the blocks go to the files as
+        // they are (no concatenated copy of what can be a gigabyte of text)
+        const int rc = render_blocks(tree, n, s->header_off.data() + s->written, s->headers.data(), result, s->format, outs, errs);
+        if (rc != CLS_OK) return rc;
+        if (!append_blocks(s->out_path, outs) || !append_blocks(s->err_path, errs))
+            return set_last_error(CLS_ERR_INVALID_ARGUMENT, "Error writing to file: " + s->out_path);
+        s->written += n;
+        return CLS_OK;
+    } catch (const std::bad_alloc &) {
+        return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while writing records");
+    }
 }
 
 extern "C" void cls_sequences_close(cls_sequences *s) { delete s; }
