@@ -770,7 +770,8 @@ extern "C" int cls_place_sequences(cls_index *index, const cls_record_tree *tree
     if (rc != CLS_OK) return rc;
     std::unique_ptr<cls_sequences> guard(s);
     try {
-        constexpr uint64_t kBatch = 1ull << 20;      // queries per device call: bounds the result arrays
+        // queries per device call: bounds the result arrays (CLS_SEQ_BATCH: smaller batches, for tests of this loop)
+        static const uint64_t kBatch = [] { const char *e = getenv("CLS_SEQ_BATCH"); const long v = e ? atol(e) : 0; return v > 0 ? (uint64_t)v : 1ull << 20; }();
         const uint64_t cap = std::min<uint64_t>(all.n_queries, kBatch);
         std::vector<uint8_t> status(cap);
         std::vector<uint64_t> node(cap);

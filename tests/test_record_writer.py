@@ -296,3 +296,61 @@ def test_native_writer_equals_python_on_random_headers(ps, col_tree):
     res.status[:] = [_lib.STATUS_UNCL_NO_MATCH if i % 2 else _lib.STATUS_UNCL_NO_ROOT for i in range(n)]
     res.status[0], res.node_id[0] = _lib.STATUS_IDENTITY_FOUND, 1          # one record that prints all the names
     _check(ps, strings, res, tree)
+
+
+@pytest.mark.parametrize("fmt,batch", [("yaml", "100"), ("jsonl", "7"), ("yaml", "0")])
+def test_one_call_place_sequences_around_an_oracle_placer(ps, tmp_path, col_tree, col_flat, fmt, batch):
+    """cls_place_sequences itself - path handling, reader, the loop over batches with its result arrays, writer - with
+    cls_place_batch supplied by the C++ oracle (tests/native/place_seq_host.cpp): same files as the Python driver around
+    the same oracle.  Runs in a child process: CLS_SEQ_BATCH is read once."""
+    import subprocess
+    import sys
+    import textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run(["make", "-C", os.path.join(here, "native"), "libplace_seq_host.so"], check=True, capture_output=True)
+    import classeq2_b200 as cq
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    index = _OracleIndex(col_flat)
+    fa = os.path.join(GOLDEN, "colletotrichum_queries.fasta")
+    cq.place_sequences(fa, tree, tmp_path / "p" / "r", output_format=fmt, index=index, writer="python", reader="python", remove_intersection=True)
+    index.close()
+    child = textwrap.dedent(f"""
+        import ctypes as C, json, os, sys
+        sys.path.insert(0, {os.path.dirname(here)!r}); sys.path.insert(0, {here!r})
+        import numpy as np
+        import classeq2_b200 as cq
+        from classeq2_b200 import _lib, placement as ps
+        from oracle import cpp_oracle
+        z = np.load(os.path.join({GOLDEN!r}, "colletotrichum_model.npz"))
+        flat = cq.FlatModel(int(z["k_size"]), int(z["m_size"]), z["node_id"], z["node_kind"], z["child_off"], z["child_idx"],
+                            z["entry_bucket"], z["entry_hash"], z["entry_set"], z["set_off"], z["set_node_ids"])
+        tree = cq.Tree.from_obj({{"id": "t", "name": "t", "minBranchSupport": 70.0, "root": json.loads(bytes(z["tree_json"]).decode())["root"]}})
+        md = cpp_oracle.CppModel.from_flat(flat)
+        lib = C.CDLL(os.path.join({here!r}, "native", "libplace_seq_host.so"))
+        lib.psh_set_placer(C.cast(cpp_oracle.lib.orc_place_batch, C.c_void_p))
+        lib.psh_calls.restype = C.c_uint64
+        lib.cls_last_error.restype = C.c_char_p
+        lib.cls_place_sequences.argtypes = [C.c_void_p, C.POINTER(_lib.RecordTree), C.c_char_p, C.c_char_p, C.POINTER(_lib.Params), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+        rt = ps.RecordTree(tree)
+        p = cq.PlaceParams(remove_intersection=True).to_c()
+        n = C.c_uint64()
+        out = {str(tmp_path / "c" / "r.x")!r}.encode()
+        fmt = {0 if fmt == "yaml" else 1}
+        rc = lib.cls_place_sequences(md._h, C.byref(rt.view), {fa!r}.encode(), out, C.byref(p), fmt, 0, C.byref(n))
+        assert rc == 0, lib.cls_last_error()
+        rc2 = lib.cls_place_sequences(md._h, C.byref(rt.view), {fa!r}.encode(), out, C.byref(p), fmt, 0, C.byref(n))
+        assert rc2 == _lib.CLS_ERR_INVALID_ARGUMENT and lib.cls_last_error().startswith(b"Could not overwrite existing file")
+        rc3 = lib.cls_place_sequences(md._h, C.byref(rt.view), {fa!r}.encode(), out, C.byref(p), fmt, 1, C.byref(n))
+        assert rc3 == 0
+        print(json.dumps({{"n": n.value, "calls": lib.psh_calls()}}))
+    """)
+    r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, CLS_SEQ_BATCH=batch), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    want_o, want_e = (tmp_path / "p" / f"r.{fmt}").read_bytes(), (tmp_path / "p" / "r.error").read_bytes()
+    assert (tmp_path / "c" / f"r.{fmt}").read_bytes() == want_o and len(want_o) > 10000
+    assert (tmp_path / "c" / "r.error").read_bytes() == want_e + want_e          # the second successful run appends
+    n_records = len(want_o.split(b"---\n")) - 1 if fmt == "yaml" else want_o.count(b"\n")
+    assert info["n"] >= n_records
+    b = int(batch)
+    assert info["calls"] == 2 * (1 if b == 0 else -(-info["n"] // b))            # the loop really ran in batches
