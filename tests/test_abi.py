@@ -214,3 +214,31 @@ def test_header_is_plain_c99_and_a_c_program_links(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    from classeq2_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, lib_dir = tmp_path / "place_fasta", os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "examples", "place_fasta.c"), "-L", lib_dir, "-l:" + os.path.basename(_lib.LIB_PATH),
+                        "-Wl,-rpath," + lib_dir, "-lm", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    fa = tmp_path / "q.fasta"
+    fa.write_text(">like_a\nACGTTGCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGATCCCCGGGTACCGAGCTCGAATTCACTGGCCGTCGTTTTACA\n"
+                  ">like_d\nACGTTGCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGATCGGTTAACCGGTTAACCGTACGTACGATCGATCGGCTAGGT\n>short\nACGT\n")
+    return exe, fa
+
+
+@pytest.mark.skipif(_has_nvidia_node(), reason="only meaningful on a machine without a GPU")
+def test_c_example_builds_its_model_and_fails_loudly_without_gpu(tmp_path):
+    """examples/place_fasta.c: plain C against the header - model built on the host, then no device, no answer."""
+    import subprocess
+    exe, fa = _build_c_example(tmp_path)
+    r = subprocess.run([str(exe), str(fa), str(tmp_path / "out")], capture_output=True, text=True)
+    assert r.returncode == 3 and "k-mer entries" in r.stdout and "cls_index_create" in r.stderr
+    assert not (tmp_path / "out.yaml").exists()

@@ -45,3 +45,20 @@ def test_one_call_place_sequences_writes_the_same_files(tmp_path, col_tree, fmt)
         cq.place_sequences_native(fa, tree, tmp_path / "c" / "r.out", output_format=fmt, index=index)
     assert cq.place_sequences_native(fa, tree, tmp_path / "c" / "r.out", output_format=fmt, index=index, overwrite=True) == n
     index.close()
+
+
+def test_c_example_places_a_fasta_file(tmp_path):
+    """examples/place_fasta.c (plain C: cls_model_build, cls_index_create, cls_place_sequences) on a B200; the expected
+    placements are the oracle's for the same four-tip model."""
+    import subprocess
+    import yaml
+    from test_abi import _build_c_example
+    exe, fa = _build_c_example(tmp_path)
+    r = subprocess.run([str(exe), str(fa), str(tmp_path / "out.any")], capture_output=True, text=True)
+    assert r.returncode == 0 and "3 queries placed" in r.stdout, (r.stdout, r.stderr)
+    recs = list(yaml.safe_load_all((tmp_path / "out.yaml").read_text()))
+    assert [x["query"] for x in recs] == ["like_a", "like_d"] and all(x["code"] == "IdentityFound" for x in recs)
+    assert recs[0]["placement"]["clade"]["id"] == 1 and recs[1]["placement"]["clade"]["id"] == 4
+    assert (recs[0]["placement"]["one"], recs[0]["placement"]["rest"]) == (96, 16)
+    assert [c["name"] for c in recs[0]["placement"]["clade"]["children"]] == ["tip_a", "tip_b"]
+    assert (tmp_path / "out.error").read_text() == "The sequence does not contain enough kmers."
