@@ -75,3 +75,17 @@ def test_reference_alignment_file_filters_to_the_gap_free_sequences(oracle, col_
     assert read_fasta_text(raw.decode()) == want
     headers, bases, offsets = read_fasta_native(raw)
     assert [(h, bytes(bases[int(offsets[i]):int(offsets[i + 1])]).decode()) for i, h in enumerate(headers)] == want
+
+
+def test_byte_soup(oracle):
+    """Short random texts over an alphabet that is mostly structure ('>', line ends, blanks, a few bases and non-ASCII
+    letters): every combination of the record rules within a few lines."""
+    import random
+    from classeq2_b200.placement import read_fasta_text
+    rng = random.Random(5)
+    alpha = list("ACGTacgtNn>>\n\n\r -") + ["\r\n", "é", "ẗ"]
+    for t in range(6000):
+        s = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 60)))
+        _check(s)
+        if t % 10 == 0:
+            assert read_fasta_text(s) == oracle.read_fasta_text(s)
