@@ -260,7 +260,7 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err,
                     std::memcmp(&out.terms[off], rec.data(), rec.size() * sizeof(uint32_t)) == 0) { found = off; break; }
             }
             if (found == kEmpty) {
-                if (out.terms.size() + rec.size() >= 0xFFFFFFF0ull) { err = "node-set arena exceeds 2^32 words"; return CLS_ERR_UNSUPPORTED; }
+                if (out.terms.size() + rec.size() >= 0x7FFFFFF0ull) { err = "node-set arena exceeds 2^31 words"; return CLS_ERR_UNSUPPORTED; }  // bit 31 of a record offset is free (scan2_kernel)
                 found = (uint32_t)out.terms.size();
                 out.terms.insert(out.terms.end(), rec.begin(), rec.end());
                 cands.push_back(found);
@@ -373,20 +373,36 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err,
     out.n_entries_kept = kept.size();
 
     // ---- open-addressed table: 32-byte buckets of two slots, load factor in (0.25, 0.5] ----------
-    uint64_t nb = 1;
+    // A free slot of bucket j carries the "hash" (j + 1) & mask: a probe reaches bucket j only from a home bucket
+    // at cyclic distance < n_buckets - 1 behind it (checked below), never from j + 1, so the hash it asks for
+    // cannot equal the filler and the kernels may treat hash equality alone as a hit.
+    uint64_t nb = 4;
     while (nb < kept.size()) nb <<= 1;
-    out.n_buckets = nb;
-    out.table.assign(2 * nb, Slot{0, kEmpty, 0});
-    const uint64_t mask = nb - 1;
-    for (const KeptEntry &e : kept) {
-        uint64_t b = e.hash & mask;
-        for (;;) {
-            Slot *s = &out.table[2 * b];
-            if (s[0].set_off == kEmpty) { uint32_t ov = s[0].code & kOverflowBit; s[0] = Slot{e.hash, e.set_off, e.code | ov}; break; }
-            if (s[1].set_off == kEmpty) { s[1] = Slot{e.hash, e.set_off, e.code}; break; }
-            s[0].code |= kOverflowBit;
-            b = (b + 1) & mask;
+    for (;;) {
+        out.n_buckets = nb;
+        out.table.assign(2 * nb, Slot{0, kEmpty, 0});
+        const uint64_t mask = nb - 1;
+        uint64_t max_dist = 0;
+        for (const KeptEntry &e : kept) {
+            uint64_t b = e.hash & mask, dist = 0;
+            for (;;) {
+                Slot *s = &out.table[2 * b];
+                if (s[0].set_off == kEmpty) { uint32_t ov = s[0].code & kOverflowBit; s[0] = Slot{e.hash, e.set_off, e.code | ov}; break; }
+                if (s[1].set_off == kEmpty) { s[1] = Slot{e.hash, e.set_off, e.code}; break; }
+                s[0].code |= kOverflowBit;
+                b = (b + 1) & mask;
+                ++dist;
+            }
+            if (dist > max_dist) max_dist = dist;
         }
+        // a miss walks one bucket past the last overflowed one
+        if (max_dist + 2 < nb) {
+            for (uint64_t j = 0; j < nb; ++j)
+                for (int q = 0; q < 2; ++q)
+                    if (out.table[2 * j + q].set_off == kEmpty) out.table[2 * j + q].hash = (j + 1) & mask;
+            break;
+        }
+        nb <<= 1;   // pathological clustering in a tiny table: spread it out
     }
     return CLS_OK;
 }

@@ -263,72 +263,8 @@ struct ReadTables {
 // SHARED == true: several warps fill the tables of one read (CTA-per-read mode): counts are atomic and
 // start from zeroed bins.  SHARED == false: the warp owns the tables; a bin's count has one writer per
 // pass (the leader of its node set), so plain stores do and the bins need no zeroing.
-#ifdef CLS_INSERT_PLAIN
-// EXPERIMENT (off by default; `make variant NAME=plain EXTRA=-DCLS_INSERT_PLAIN=1`): the warp-owned tables without
-// shared-memory atomics.  consume() - a quarter of scan_kernel's instructions - collects half of its stall samples,
-// most of them behind the CAS results that its one-to-three-lane blocks wait for.  Here one lane per distinct key of the pass (match.any) probes with plain loads, writes its
-// key tentatively into an empty slot, and after a __syncwarp() the lane whose key is still there owns the slot; the
-// others move on.  No key is ever removed within a read, so linear probing stays consistent across passes.
-__device__ __forceinline__ uint32_t insert_hits_plain(const ReadTables &tb, bool hit, uint32_t slot_key, uint32_t set_off) {
-    const uint32_t lane = lane_id();
-    const uint32_t hm = __ballot_sync(kFull, hit);
-    if (hm == 0) return 0;   // warp-uniform
-    // ---- de-duplication set keyed by table slot: the same k-mer hash counts once per read
-    bool pending = false, fresh = false;
-    if (hit) pending = (uint32_t)(__ffs(__match_any_sync(hm, slot_key)) - 1) == lane;  // the same k-mer twice in one pass
-    uint32_t p1 = (slot_key >> 1) & tb.t1_mask;
-    while (__any_sync(kFull, pending)) {
-        uint32_t cur = kEmpty;
-        if (pending) {
-            cur = tb.t1[p1];
-            if (cur == kEmpty) tb.t1[p1] = slot_key;   // lanes with different keys may meet here: the last store stays
-        }
-        __syncwarp();
-        if (pending) {
-            if (cur == slot_key) pending = false;      // counted by an earlier pass
-            else if (cur == kEmpty && tb.t1[p1] == slot_key) { fresh = true; pending = false; }
-            else p1 = (p1 + 1) & tb.t1_mask;           // the slot holds another key (old, or the winner's)
-        }
-        __syncwarp();
-    }
-    const uint32_t fm = __ballot_sync(kFull, fresh);
-    if (fm == 0) return 0;   // warp-uniform; nothing was written
-    // ---- histogram by node-set record: one leader per distinct record among the fresh lanes
-    uint32_t peers = 0;
-    bool lead = false;
-    if (fresh) { peers = __match_any_sync(fm, set_off); lead = (uint32_t)(__ffs(peers) - 1) == lane; }
-    const uint32_t add = (uint32_t)__popc(peers);
-    uint32_t p2 = (set_off * 0x9E3779B1u) >> tb.t2_shift;
-    uint32_t n_sets = *tb.n_sets;   // broadcast load; written back by lane 0 below
-    while (__any_sync(kFull, lead)) {
-        uint32_t cur = kEmpty;
-        if (lead) {
-            cur = tb.t2k[p2];
-            if (cur == kEmpty) tb.t2k[p2] = set_off;
-        }
-        __syncwarp();
-        bool won = false;
-        if (lead) {
-            if (cur == set_off) { tb.t2c[p2] += add; lead = false; }   // a bin has one writer per pass: its leader
-            else if (cur == kEmpty && tb.t2k[p2] == set_off) { won = true; lead = false; }
-            else p2 = (p2 + 1) & tb.t2_mask;
-        }
-        const uint32_t wm = __ballot_sync(kFull, won);
-        if (won) { tb.lst[n_sets + __popc(wm & ((1u << lane) - 1u))] = p2; tb.t2c[p2] = add; }
-        n_sets += (uint32_t)__popc(wm);
-        __syncwarp();
-    }
-    if (lane == 0) *tb.n_sets = n_sets;
-    __syncwarp();
-    return (uint32_t)__popc(fm);
-}
-#endif
-
 template <bool SHARED>
 __device__ __forceinline__ uint32_t insert_hits(const ReadTables &tb, bool hit, uint32_t slot_key, uint32_t set_off) {
-#ifdef CLS_INSERT_PLAIN
-    if constexpr (!SHARED) return insert_hits_plain(tb, hit, slot_key, set_off);
-#endif
     bool fresh = false;
     if (hit) {
         uint32_t p1 = (slot_key >> 1) & tb.t1_mask;  // bit 0 is the slot within the bucket (mostly 0): not a hash bit
@@ -879,15 +815,13 @@ struct ScanOut {
     uint2 *pairs;
     uint2 *meta;
     uint32_t cap;
-#ifdef CLS_DYNAMIC_READS
-    // EXPERIMENT (-DCLS_DYNAMIC_READS): the persistent warps take reads in blocks of kReadBlock from a global counter
-    // instead of a static stride, so that a CTA which becomes resident late (another kernel still holds its SM) or
-    // draws cheap reads does not decide when the launch ends.  counters[0]: scan kernel, counters[1]: descent kernel;
-    // zeroed by the launcher.
+    // The persistent warps of scan2_kernel and descend_kernel take reads in blocks of kReadBlock from a global counter
+    // instead of a static stride: a CTA that becomes resident late (another kernel still holds its SM) or draws cheap
+    // reads does not decide when the launch ends (4.48 against 5.07 ms per 1 M reads of config 2, profiles/r2a).
+    // counters[0]: scan kernel, [1]: descent kernel, [2]: length of ov_list; zeroed by the launcher.
     uint32_t *counters;
-#endif
+    uint32_t *ov_list;   // reads scan2_kernel could not hand over (too many node sets): finished by scan_kernel afterwards
 };
-#ifdef CLS_DYNAMIC_READS
 constexpr uint32_t kReadBlock = 4;
 // next read of this warp, or >= n_reads when the launch has run out of reads
 __device__ __forceinline__ uint32_t next_read(uint32_t *counter, uint32_t &base, uint32_t &used) {
@@ -899,7 +833,6 @@ __device__ __forceinline__ uint32_t next_read(uint32_t *counter, uint32_t &base,
     }
     return base + used++;
 }
-#endif
 
 // ------------------------------------------------------------------------------------------
 // The placement kernel, persistent CTAs striding over the query range.
@@ -1070,13 +1003,13 @@ __device__ __forceinline__ uint64_t window_hash35(uint64_t a0, uint64_t b1, uint
     return mm_finish(h1 ^ tail, h2, 35ull);
 }
 
-#ifndef CLS_SCAN_MINB
-#define CLS_SCAN_MINB 4
-#endif
-template <bool CLOSED, bool SPLIT>
-__global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix, PlaceParams pp, const uint32_t *__restrict__ packed,
+// First-generation scan kernel, descent fused (finish_read*): general (mini-tree) models, callers without hand-over
+// scratch, and - with `ov_list` - the reads scan2_kernel left on its overflow list (*ov_count of them).
+template <bool CLOSED>
+__global__ void __launch_bounds__(256, 4) scan_kernel(DeviceIndex ix, PlaceParams pp, const uint32_t *__restrict__ packed,
                                                       const ReadDesc *__restrict__ reads, uint32_t first_read,
-                                                      uint32_t n_reads, ResultRec *__restrict__ results, PlaceGeom g, ScanOut so) {
+                                                      uint32_t n_reads, ResultRec *__restrict__ results, PlaceGeom g,
+                                                      const uint32_t *__restrict__ ov_list, const uint32_t *__restrict__ ov_count) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t tail_lut[64];
     init_tail_lut(tail_lut);
@@ -1106,18 +1039,10 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
     __syncthreads();
 
     const uint32_t gwarp = blockIdx.x * warps_per_cta + warp, gstride = gridDim.x * warps_per_cta;
-#ifdef CLS_DYNAMIC_READS
-    uint32_t dyn_base = 0, dyn_used = kReadBlock;
-    const bool dynamic = SPLIT && so.counters != nullptr;
-#endif
+    const uint32_t n_items = ov_list ? *ov_count : n_reads;
 #pragma unroll 1
-#ifdef CLS_DYNAMIC_READS
-    for (uint32_t r = gwarp;; r += gstride) {
-        if (dynamic) r = next_read(so.counters, dyn_base, dyn_used);
-        if (r >= n_reads) break;
-#else
-    for (uint32_t r = gwarp; r < n_reads; r += gstride) {
-#endif
+    for (uint32_t item = gwarp; item < n_items; item += gstride) {
+        const uint32_t r = ov_list ? ov_list[item] : item;
         const ReadDesc rd = reads[first_read + r];
         const uint32_t L = rd.len;
         const uint32_t W = L - 34u;  // host guarantees L >= k = 35
@@ -1195,23 +1120,9 @@ __global__ void __launch_bounds__(256, CLS_SCAN_MINB) scan_kernel(DeviceIndex ix
         }
         __syncwarp();
         const uint32_t D = *n_sets_smem;
-        if constexpr (SPLIT) {
-            // hand the read over to the descent kernel (its own launch: 64 warps per SM and the whole L1)
-            if (D <= so.cap) {
-                for (uint32_t j = lane; j < D; j += 32) {
-                    const uint32_t p2 = lst[j];
-                    so.pairs[(size_t)r * so.cap + j] = make_uint2(t2k[p2], t2c[p2]);
-                }
-                if (lane == 0) so.meta[r] = make_uint2(n_matched, D);
-            } else {
-                finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
-                if (lane == 0) so.meta[r] = make_uint2(n_matched, kDone);
-            }
-        } else {
-            if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
-            else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
-            else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
-        }
+        if (CLOSED && D <= 32) finish_read_reg<1>(ix, pp, tb, D, n_matched, results + first_read + r);
+        else if (CLOSED && D <= 64) finish_read_reg<2>(ix, pp, tb, D, n_matched, results + first_read + r);
+        else finish_read<CLOSED>(ix, pp, tb, D, n_matched, results + first_read + r);
         __syncwarp();
     }
 }
@@ -1232,33 +1143,21 @@ __device__ __forceinline__ void descend_from_pairs(const DeviceIndex &ix, const 
     finish_read_reg<SLOTS>(ix, pp, cnt, excl, off, wt, n_matched, out);
 }
 
-// -DCLS_DESCEND_MINB=n (experiment): ask ptxas for n resident CTAs per SM (the default build leaves the register count to ptxas:
-// 40 registers, six CTAs = 48 warps per SM; the kernel waits on dependent loads with 8.7 eligible warps per scheduler)
-#ifdef CLS_DESCEND_MINB
-#define CLS_DESCEND_BOUNDS __launch_bounds__(256, CLS_DESCEND_MINB)
-#else
+// (asking ptxas for 8 or 4 resident CTAs per SM changes nothing: 5.08 / 5.07 against 5.07 ms, profiles/r2a)
 #define CLS_DESCEND_BOUNDS __launch_bounds__(256)
-#endif
 template <int MAXSLOTS>
 __global__ void CLS_DESCEND_BOUNDS descend_kernel(DeviceIndex ix, PlaceParams pp, ScanOut so, uint32_t first_read,
                                                       uint32_t n_reads, ResultRec *__restrict__ results, uint32_t fan_cap) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     uint32_t *cnt = smem + (size_t)warp * 2 * fan_cap, *excl = cnt + fan_cap;
     for (uint32_t o = lane; o < fan_cap; o += 32) { cnt[o] = 0; excl[o] = 0; }
     __syncwarp();
-    const uint32_t gwarp = blockIdx.x * warps_per_cta + warp, gstride = gridDim.x * warps_per_cta;
-#ifdef CLS_DYNAMIC_READS
     uint32_t dyn_base = 0, dyn_used = kReadBlock;
-#endif
 #pragma unroll 1
-#ifdef CLS_DYNAMIC_READS
-    for (uint32_t r = gwarp;; r += gstride) {
-        if (so.counters) r = next_read(so.counters + 1, dyn_base, dyn_used);
+    for (;;) {
+        const uint32_t r = next_read(so.counters + 1, dyn_base, dyn_used);
         if (r >= n_reads) break;
-#else
-    for (uint32_t r = gwarp; r < n_reads; r += gstride) {
-#endif
         const uint2 me = so.meta[r];
         if (me.y == kDone) continue;
         const uint2 *pr = so.pairs + (size_t)r * so.cap;
@@ -1272,6 +1171,10 @@ __global__ void CLS_DESCEND_BOUNDS descend_kernel(DeviceIndex ix, PlaceParams pp
     }
 }
 
+namespace {
+#include "scan2_kernels.cuh"
+}  // namespace
+
 // ------------------------------------------------------------------------------------------
 // Host launchers
 // ------------------------------------------------------------------------------------------
@@ -1283,6 +1186,7 @@ static inline uint32_t ceil_log2(uint32_t x) {
 
 PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout) {
     PlaceGeom g{};
+    g.max_len = max_len;
     const uint32_t H = max_len >= k ? 2 * (max_len - k + 1) : 2;
     g.str_words = ((max_len + 15u) / 16u) * 4u + 4u;  // decoded in 16-base groups, + over-read pad
     g.pk_words = (((max_len + 15u) / 16u) + 4u + 3u) & ~3u;
@@ -1305,23 +1209,19 @@ static bool split_disabled() {
 }
 static inline ScanOut no_scan_out() {
     ScanOut so{};
-    so.pairs = nullptr; so.meta = nullptr; so.cap = 0;
+    so.pairs = nullptr; so.meta = nullptr; so.cap = 0; so.counters = nullptr; so.ov_list = nullptr;
     return so;
 }
-#ifdef CLS_DYNAMIC_READS
-static inline size_t scratch_bytes_for(uint32_t n_reads, uint32_t cap) { return (size_t)n_reads * ((size_t)cap * 8 + 8) + 256 + 64; }
-#else
-static inline size_t scratch_bytes_for(uint32_t n_reads, uint32_t cap) { return (size_t)n_reads * ((size_t)cap * 8 + 8) + 256; }
-#endif
+// hand-over scratch of a launch: pairs[n_reads][cap], meta[n_reads], 16 counters, ov_list[n_reads]
+static inline size_t scratch_bytes_for(uint32_t n_reads, uint32_t cap) { return (size_t)n_reads * ((size_t)cap * 8 + 8 + 4) + 256 + 64; }
 static inline ScanOut carve_scratch(void *scratch, uint32_t n_reads, uint32_t cap) {
     char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
     ScanOut so;
     so.pairs = reinterpret_cast<uint2 *>(base);
     so.meta = so.pairs + (size_t)n_reads * cap;
     so.cap = cap;
-#ifdef CLS_DYNAMIC_READS
-    so.counters = reinterpret_cast<uint32_t *>(so.meta + n_reads);   // 8 bytes used, 64 reserved
-#endif
+    so.counters = reinterpret_cast<uint32_t *>(so.meta + n_reads);
+    so.ov_list = so.counters + 16;
     return so;
 }
 template <int MAXSLOTS>
@@ -1336,9 +1236,6 @@ static cudaError_t launch_descend(const DeviceIndex &ix, const PlaceParams &pp, 
     uint32_t dgrid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + 7) / 8;
     if (dgrid > need) dgrid = need;
-#ifdef CLS_DYNAMIC_READS
-    if (so.counters && (e = cudaMemsetAsync(so.counters + 1, 0, 4, stream)) != cudaSuccess) return e;
-#endif
     descend_kernel<MAXSLOTS><<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
     return cudaGetLastError();
 }
@@ -1379,7 +1276,10 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
     const bool split = CTA && CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCapWide) &&
                        (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024 && !split_disabled();
     ScanOut so = no_scan_out();
-    if (split) so = carve_scratch(scratch, n_reads, kPairCapWide);
+    if (split) {
+        so = carve_scratch(scratch, n_reads, kPairCapWide);
+        if ((e = cudaMemsetAsync(so.counters, 0, 64, stream)) != cudaSuccess) return e;
+    }
     place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so, trace);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (n_launches) ++*n_launches;
@@ -1408,41 +1308,68 @@ size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k) {
 }
 
 template <bool CLOSED>
-static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
-                                 const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
-                                 const PlaceGeom &g, int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes,
-                                 uint32_t *n_launches) {
+static cudaError_t launch_scan_old(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
+                                   const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
+                                   const PlaceGeom &g, int sm_count, cudaStream_t stream, const uint32_t *ov_list,
+                                   const uint32_t *ov_count, uint32_t *n_launches) {
     const size_t ring = (size_t)4 * kRing * 4, group = (size_t)g.words_per_warp * 4;
     int warps = 8;
     while (warps > 1 && (group + ring) * warps > 200 * 1024) warps >>= 1;
-    static const size_t pad = [] { const char *e = getenv("CLS_SCAN_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
-    const size_t smem = (group + ring) * warps + pad;
+    const size_t smem = (group + ring) * warps;
     if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
-    const bool split = CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && !split_disabled() &&
-                       (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
-    auto kern = split ? scan_kernel<CLOSED, true> : scan_kernel<CLOSED, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<CLOSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<CLOSED>, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + warps - 1) / warps;
     if (grid > need) grid = need;
-    ScanOut so = no_scan_out();
-    if (split) so = carve_scratch(scratch, n_reads, kPairCap);
-#ifdef CLS_DYNAMIC_READS
-    if (split && (e = cudaMemsetAsync(so.counters, 0, 4, stream)) != cudaSuccess) return e;
-#endif
-    kern<<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so);
+    if (ov_list && grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;  // the overflow list is short (its length is known on the device only)
+    scan_kernel<CLOSED><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, ov_list, ov_count);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (n_launches) ++*n_launches;
-    if (split) {
-        if ((e = launch_descend<2>(ix, pp, so, first_read, n_reads, results, g.fan_cap, sm_count, stream)) != cudaSuccess) return e;
-        if (n_launches) ++*n_launches;
-    }
     return cudaSuccess;
+}
+
+template <int PPS>
+static cudaError_t launch_scan2(const DeviceIndex &ix, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read,
+                                uint32_t n_reads, const ScanOut &so, int sm_count, cudaStream_t stream) {
+    const size_t smem = (size_t)Scan2Layout<PPS>::kBytes * 8;
+    cudaError_t e = cudaFuncSetAttribute(scan2_kernel<PPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan2_kernel<PPS>, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    uint32_t grid = (uint32_t)(sm_count * occ);
+    const uint32_t need = (n_reads + 8 * kReadBlock - 1) / (8 * kReadBlock);
+    if (grid > need) grid = need;
+    scan2_kernel<PPS><<<grid, 256, smem, stream>>>(ix, packed, reads, first_read, n_reads, so);
+    return cudaGetLastError();
+}
+
+// Short reads, k = 35.  Closed models with hand-over scratch: scan2_kernel -> descend_kernel -> scan_kernel over the
+// (mostly empty) overflow list.  Otherwise the first-generation kernel with the descent fused.
+template <bool CLOSED>
+static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
+                                 const ReadDesc *reads, uint32_t first_read, uint32_t n_reads, ResultRec *results,
+                                 const PlaceGeom &g, int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes,
+                                 uint32_t *n_launches) {
+    const bool split = CLOSED && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && !split_disabled() &&
+                       (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024 && g.max_len <= Scan2Layout<8>::kMaxLen;
+    if (!split) return launch_scan_old<CLOSED>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, nullptr, n_launches);
+    const ScanOut so = carve_scratch(scratch, n_reads, kPairCap);
+    cudaError_t e = cudaMemsetAsync(so.counters, 0, 64, stream);
+    if (e != cudaSuccess) return e;
+    e = g.max_len <= Scan2Layout<4>::kMaxLen ? launch_scan2<4>(ix, packed, reads, first_read, n_reads, so, sm_count, stream)
+                                             : launch_scan2<8>(ix, packed, reads, first_read, n_reads, so, sm_count, stream);
+    if (e != cudaSuccess) return e;
+    if (n_launches) ++*n_launches;
+    if ((e = launch_descend<2>(ix, pp, so, first_read, n_reads, results, g.fan_cap, sm_count, stream)) != cudaSuccess) return e;
+    if (n_launches) ++*n_launches;
+    return launch_scan_old<true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, so.ov_list, so.counters + 2, n_launches);
 }
 
 cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,

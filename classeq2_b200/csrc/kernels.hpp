@@ -30,6 +30,7 @@ struct PlaceGeom {
     uint32_t fan_cap;         // vote counters per warp (max non-leaf fan-out of the tree)
     uint32_t words_per_warp;  // tables + strings of one group (warp or CTA), without the pre-mix rings
     uint32_t cta_per_read;    // 1: one CTA per read (long reads), 0: one warp per read
+    uint32_t max_len;         // longest read of the launch (bases)
 };
 
 PlaceGeom make_place_geom(uint32_t max_len, uint32_t k, uint32_t max_fanout);

@@ -14,13 +14,24 @@ constexpr uint64_t kC2 = 0x4cf5ad432745937fULL;
 
 __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-// x * C (mod 2^64) for a compile-time constant C
+// x * C (mod 2^64) for a compile-time constant C: IMAD.WIDE for lo * C.lo, then the two cross terms are
+// accumulated into the high word by two chained IMADs - three instructions (spelled in PTX: left to itself the
+// compiler emits two independent IMADs plus an add, four instructions for the same latency).
 template <uint64_t C>
 __device__ __forceinline__ uint64_t mulc(uint64_t x) {
     const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-    const uint64_t r = (uint64_t)lo * (uint32_t)C;
-    const uint32_t rh = (uint32_t)(r >> 32) + lo * (uint32_t)(C >> 32) + hi * (uint32_t)C;
-    return pack64((uint32_t)r, rh);
+    uint32_t rl, rh;
+    asm("{\n\t"
+        ".reg .u64 t;\n\t"
+        ".reg .u32 th;\n\t"
+        "mul.wide.u32 t, %2, %4;\n\t"
+        "mov.b64 {%0, th}, t;\n\t"
+        "mad.lo.u32 th, %2, %5, th;\n\t"
+        "mad.lo.u32 %1, %3, %4, th;\n\t"
+        "}"
+        : "=r"(rl), "=r"(rh)
+        : "r"(lo), "r"(hi), "n"((uint32_t)C), "n"((uint32_t)(C >> 32)));
+    return pack64(rl, rh);
 }
 
 // rotate left by a compile-time amount

@@ -326,8 +326,11 @@ cudaError_t launch_place_routed(const DeviceIndex &ix, const PlaceParams &pp, co
     const ProbeReply *rp = reinterpret_cast<const ProbeReply *>(replies);
     const bool split = ix.closed && scratch && scratch_bytes >= scratch_bytes_for(n_reads, kPairCap) && !split_disabled() &&
                        (size_t)2 * g.fan_cap * 4 * 8 <= 48 * 1024;
-    ScanOut so{nullptr, nullptr, 0};
-    if (split) so = carve_scratch(scratch, n_reads, kPairCap);
+    ScanOut so = no_scan_out();
+    if (split) {
+        so = carve_scratch(scratch, n_reads, kPairCap);
+        if ((e = cudaMemsetAsync(so.counters, 0, 64, stream)) != cudaSuccess) return e;
+    }
     auto kern = split ? place_routed_kernel<true, true> : (ix.closed ? place_routed_kernel<true, false> : place_routed_kernel<false, false>);
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, n_shards, seg_cap, runs, slot_win, rp, so);
