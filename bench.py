@@ -14,8 +14,11 @@ of synthetic reads of the named configuration (classeq2_b2
           timed region;
   roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
 
+The default workload is config 3 - the configuration the north-star target is quoted on (10 M x 150 bp reads,
+10k-tip tree): its reads are SHARDED over the ranks ("strong"; it fits one GPU too).  `--config 2|4` run one
+batch per GPU ("weak"), `--config 5` the hash-sharded index.
 N > 1 (launched by torchrun, one rank per GPU): queries shard across ranks with the index
-replicated and NO data-path collective; per-GPU work is fixed ("weak").
+replicated and NO data-path collective.
 `--impl reference` times the CPU restatement of the reference (oracle/classeq_oracle.cpp, all host
 cores) on a bounded sample of the same workload; the reference itself is Rust and cannot be built
 here (DESIGN.md).
@@ -40,6 +43,42 @@ NAMES = {2: "config2: synthetic 1,000-tip tree, 1 kb refs, 1M x 150 bp reads, in
          4: "config4: synthetic 5k-tip tree, 1.5 kb refs, 1M reads of skewed length 150-1550 bp",
          5: "config5: synthetic 100k-tip tree, ~600 bp refs, 10M x 150 bp reads sharded over the GPUs, index HASH-SHARDED "
             "(owner = hash >> 61 mod N), query k-mers routed by NCCL all-to-all over NVLink"}
+
+
+L2_NOTE = "256 MiB memset between steps of the GPU arm (outside the event pairs)"
+
+
+def common_config(config: int, n_total: int, world: int) -> dict:
+    """The `config` object both arms print (the driver compares them): the workload and nothing measured."""
+    sharded = config in (3, 5)
+    return {"workload": NAMES[config], "reads_total": int(n_total * (1 if sharded else world)),
+            "reads_per_gpu": int(n_total // world if sharded else n_total), "k": K_SIZE, "m": 4, "l2": L2_NOTE}
+
+
+def synth_reads(config: int) -> int:
+    return int(load_synth_data().CONFIGS[config]["n_reads"])
+
+
+def load_synth_data():
+    """classeq2_b200/synth_data.py by path: the generator is pure numpy, and the reference arm must not map the
+    product library (importing the package loads it)."""
+    import importlib.util
+    name = "classeq_synth_data"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "classeq2_b200", "synth_data.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def ncu_counters(config: int):
+    """Counters of the committed ncu capture of this config's kernels (profiles/ncu_counters.json), if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(f"config{config}")
+    return None
 
 
 def algorithmic_bytes(lens: np.ndarray) -> int:
@@ -145,12 +184,29 @@ def time_cpu_oracle(sm, bases, offsets, seconds: float, threads: int):
 
 
 def run_reference(args, rank, world):
+    """The reference's CPU path on the host cores: the C++ restatement (oracle/), its model built by the oracle's own
+    builder - nothing of the product is imported or mapped here."""
     if rank != 0:
         return
-    sm, bases, offsets, scaling, _ = make_workload(args.config, 0, 1, args.reads)
-    threads = os.cpu_count() or 1
     from oracle import cpp_oracle
-    md = cpp_oracle.CppModel.from_flat(sm.flat)
+    sd = load_synth_data()
+    c = dict(sd.CONFIGS[args.config])
+    n_total = args.reads or c["n_reads"]
+    threads = os.cpu_count() or 1
+    tree = sd.make_tree(c["n_tips"], c["tree_seed"])
+    codes, rlens = sd.make_refs(tree, c["l_ref"], c["tree_seed"] + 1)
+    rb, ro = sd.refs_to_batch(codes, rlens)
+    flat = cpp_oracle.build_model(K_SIZE, 4, tree.node_id, tree.node_kind, tree.child_off, tree.child_idx, tree.tip_node, rb, ro,
+                                  n_threads=threads)
+    md = cpp_oracle.CppModel.from_flat(flat)
+    scaling = "strong" if args.config in (3, 5) else "weak"
+    # the first chunks of the batch rank 0 of the GPU arm places (whole generator chunks: the same reads)
+    n_gen = min(n_total, 400_000)
+    if c["read_len"] == "skewed":
+        lens_in = sd.skewed_lengths(n_total, c["len_seed"])[:n_gen]
+    else:
+        lens_in = c["read_len"]
+    bases, offsets, _ = sd.make_reads(codes, rlens, n_gen, lens_in, c["tree_seed"] + 2)
     n_all = len(offsets) - 1
     # size the per-step sample so that warmup + steps finish within about two minutes
     n0 = min(n_all, 2000)
@@ -169,15 +225,18 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     lens = np.diff(off.astype(np.int64))
     value = n / dt
-    sample = f"first {n} reads of the batch per step, {threads} threads, C++ restatement of the reference (not the Rust binary)"
+    sample = (f"first {n} reads of the batch per step, {threads} threads, C++ restatement of the reference "
+              "(oracle/classeq_oracle.cpp; the Rust binary cannot be built here), model built by the oracle's own builder")
     line = {"impl": "reference", "metric": "queries placed/s", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": NAMES[args.config], "reads_per_step": n, "k": K_SIZE},
+            "config": common_config(args.config, n_total, max(1, args.gpus)),
             "lookups_per_s": float((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum() / dt),
-            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": sample,
+                             "reads_per_step": n},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+    md.close()
 
 
 def run_b200(args, rank, world, local_rank):
@@ -300,22 +359,47 @@ def run_b200(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = alg_bytes_local / (ms_local / args.steps / 1e3) / 1e9   # this GPU's kernel(s), GB/s
+        step_s = ms_local / args.steps / 1e3
+        achieved = alg_bytes_local / step_s / 1e9   # this GPU's kernels, GB/s
+        # secondary ceilings from the committed ncu capture of this config's kernels: the path is integer
+        # hashing plus random 32-byte probes - instruction issue and (when the table does not fit L2) HBM sectors
+        nc = ncu_counters(args.config)
+        secondary = None
+        traffic = None
+        if nc:
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            peak_issue = 148 * 4 * sm_hz
+            reads_per_s_gpu = n_local / step_s
+            traffic = nc["dram_bytes_per_read"] * n_local
+            secondary = {
+                "issue": {"warp_instructions_per_read": nc["warp_instructions_per_read"], "peak_warp_instructions_per_s": peak_issue,
+                          "frac": nc["warp_instructions_per_read"] * reads_per_s_gpu / peak_issue,
+                          "issue_active_pct_in_capture": nc.get("issue_active_pct")},
+                "dram_gbs": nc["dram_bytes_per_read"] * reads_per_s_gpu / 1e9,
+                "dram_frac_of_peak": nc["dram_bytes_per_read"] * reads_per_s_gpu / 1e9 / peak,
+                "l2_gbs": nc["l2_bytes_per_read"] * reads_per_s_gpu / 1e9,
+                "limiter": nc.get("limiter"), "capture": nc.get("capture"),
+                "note": "per-read counters of the committed capture x this run's reads/s on one GPU"}
+        cfg = common_config(args.config, args.reads or synth_reads(args.config), world)
         line = {
             "metric": "queries placed/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": NAMES[args.config], "reads_per_gpu": n_local, "reads_total": int(reads_total),
-                       "k": K_SIZE, "m": 4, "index_entries": int(info["n_entries"]),
-                       "table_bytes": int(info["table_bytes"]), "distinct_node_sets": int(info["n_distinct_sets"]),
-                       "parallelism": f"queries sharded x{world}, index replicated, no collective",
-                       "l2": "256 MiB memset between steps (outside the event pairs)"},
+            "config": cfg,
+            "index": {"index_entries": int(info["n_entries"]), "table_bytes": int(info["table_bytes"]),
+                      "distinct_node_sets": int(info["n_distinct_sets"]),
+                      "parallelism": f"queries sharded x{world}, index replicated, no collective"},
             "lookups_per_s": lookups_total / (ms_per_step / 1e3),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.config), "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes_local, "launches_per_step": launches_per_step,
-                         "kernel": "cls::scan_kernel<1,1> + cls::descend_kernel, timed together (config 4: + cls::place_kernel<35,1,1> for the kb-scale classes)", "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result; achieved = algorithmic bytes / CUDA-event time of the whole step (all launches of the step)"},
+                         "secondary": secondary,
+                         "kernel": "cls::scan2_kernel<4> + cls::descend_kernel<2> (+ cls::scan_kernel<1> over the overflow list), timed together "
+                                   "(config 4: + cls::place_kernel<35,1,1> for the kb-scale classes)",
+                         "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result; achieved = algorithmic bytes / CUDA-event "
+                                 "time of the whole step (all launches of the step); traffic = DRAM bytes per read of the committed ncu "
+                                 "capture x reads per step"},
             "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
             "status_histogram": status_hist, "step_ms": [round(x, 4) for x in step_ms],
             "setup_s": {"generate": round(gen_s, 1), "index_upload": round(upload_s, 2)},
@@ -486,7 +570,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="workload (default 3: the configuration of the north-star target; it fits one GPU)")
     ap.add_argument("--reads", type=int, default=None, help="override the number of reads of the config")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="config 5: how routed k-mers cross NVLink")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")

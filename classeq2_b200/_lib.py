@@ -68,7 +68,7 @@ class IndexInfo(C.Structure):
                 ("n_buckets", C.c_uint64), ("table_bytes", C.c_uint64), ("n_distinct_sets", C.c_uint64),
                 ("set_arena_bytes", C.c_uint64), ("n_nonleaf_nodes", C.c_uint64),
                 ("max_nonleaf_fanout", C.c_uint32), ("device", C.c_int32),
-                ("closed_sets", C.c_uint32), ("reserved", C.c_uint32)]
+                ("closed_sets", C.c_uint32), ("n_devices", C.c_uint32)]
 
 
 class FastaRecords(C.Structure):
@@ -122,6 +122,8 @@ PROTOTYPES = {
     "cls_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "cls_fasta_upload": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(FastaRecords)]),
     "cls_index_create_shard": (C.c_int, [C.POINTER(ModelView), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "cls_index_create_multi": (C.c_int, [C.POINTER(ModelView), C.c_uint64, C.POINTER(C.c_void_p)]),
+    "cls_index_create_devices": (C.c_int, [C.POINTER(ModelView), C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "cls_routed_windows": (C.c_int, [C.c_void_p, C.c_void_p, u64p]),
     "cls_route_hashes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, u64p, C.c_void_p]),
     "cls_shard_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

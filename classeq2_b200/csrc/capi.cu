@@ -146,6 +146,9 @@ struct cls_index {
     std::mutex mu;
     std::vector<std::unique_ptr<Workspace>> pool;
     cls_timing timing{};
+    // a multi-device handle (cls_index_create_devices): one full index per listed device; this front object
+    // owns no device memory of its own, and every call that works on one device goes to replicas[0]
+    std::vector<std::unique_ptr<cls_index>> replicas;
     cls_index() = default;
     cls_index(const cls_index &) = delete;
     cls_index &operator=(const cls_index &) = delete;
@@ -436,22 +439,19 @@ int cls_index_create(const cls_model_view *model, int device, cls_index **out) t
     return cls_index_create_shard(model, device, 0, 1, out);
 } CLS_ABI_CATCH
 
-int cls_index_create_shard(const cls_model_view *model, int device, uint32_t shard, uint32_t n_shards, cls_index **out) try {
-    if (!out) return fail(CLS_ERR_INVALID_ARGUMENT, "out is NULL");
-    *out = nullptr;
-    if (n_shards == 0 || n_shards > kMaxShards || shard >= n_shards)
-        return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8 and shard < n_shards");
-    HostIndex h;
-    std::string err;
-    int rc = build_host_index(model, h, err, shard, n_shards);
-    if (rc != CLS_OK) return fail(rc, err);
-    if (h.n_buckets > (1ull << (n_shards > 1 ? 28 : 30))) return fail(CLS_ERR_UNSUPPORTED, "k-mer table too large (2^30 buckets, 2^28 per shard)");
-
+// The host-built index `h` on one device.
+static int upload_index(const HostIndex &h, int device, uint32_t shard, uint32_t n_shards, std::unique_ptr<cls_index> &res) {
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(CLS_ERR_CUDA, "this library only carries sm_100a code; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
 
+    // EXPERIMENT (CLS_L2_FETCH=32|64|128): the probes are random 32-byte sectors; a larger L2 fetch granularity
+    // reads neighbours that nobody asks for (a hint the platform may ignore)
+    if (const char *gr = getenv("CLS_L2_FETCH")) {
+        const size_t want = (size_t)atoi(gr);
+        if (want) (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want);
+    }
     auto ix = std::make_unique<cls_index>();
     ix->device = device;
     ix->sm_count = prop.multiProcessorCount;
@@ -497,8 +497,66 @@ int cls_index_create_shard(const cls_model_view *model, int device, uint32_t sha
     ix->info.n_nonleaf_nodes = h.qnodes.size();
     ix->info.max_nonleaf_fanout = h.max_fanout;
     ix->info.device = device;
+    ix->info.n_devices = 1;
+    res = std::move(ix);
+    return CLS_OK;
+}
+
+static int build_index_host(const cls_model_view *model, uint32_t shard, uint32_t n_shards, HostIndex &h) {
+    std::string err;
+    int rc = build_host_index(model, h, err, shard, n_shards);
+    if (rc != CLS_OK) return fail(rc, err);
+    if (h.n_buckets > (1ull << (n_shards > 1 ? 28 : 30))) return fail(CLS_ERR_UNSUPPORTED, "k-mer table too large (2^30 buckets, 2^28 per shard)");
+    return CLS_OK;
+}
+
+int cls_index_create_shard(const cls_model_view *model, int device, uint32_t shard, uint32_t n_shards, cls_index **out) try {
+    if (!out) return fail(CLS_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (n_shards == 0 || n_shards > kMaxShards || shard >= n_shards)
+        return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_shards <= 8 and shard < n_shards");
+    HostIndex h;
+    int rc = build_index_host(model, shard, n_shards, h);
+    if (rc != CLS_OK) return rc;
+    std::unique_ptr<cls_index> ix;
+    if ((rc = upload_index(h, device, shard, n_shards, ix)) != CLS_OK) return rc;
     *out = ix.release();
     return CLS_OK;
+} CLS_ABI_CATCH
+
+int cls_index_create_devices(const cls_model_view *model, uint32_t n_devices, const int *devices, cls_index **out) try {
+    if (!out) return fail(CLS_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (n_devices == 0 || n_devices > 64 || !devices) return fail(CLS_ERR_INVALID_ARGUMENT, "need 1 <= n_devices <= 64 and a device list");
+    HostIndex h;
+    int rc = build_index_host(model, 0, 1, h);   // built once, uploaded to every device
+    if (rc != CLS_OK) return rc;
+    auto front = std::make_unique<cls_index>();
+    for (uint32_t d = 0; d < n_devices; ++d) {
+        std::unique_ptr<cls_index> rep;
+        if ((rc = upload_index(h, devices[d], 0, 1, rep)) != CLS_OK) return rc;
+        front->replicas.push_back(std::move(rep));
+    }
+    front->device = front->replicas[0]->device;
+    front->sm_count = front->replicas[0]->sm_count;
+    front->dix = front->replicas[0]->dix;
+    front->info = front->replicas[0]->info;
+    front->info.n_devices = n_devices;
+    *out = front.release();
+    return CLS_OK;
+} CLS_ABI_CATCH
+
+int cls_index_create_multi(const cls_model_view *model, uint64_t device_mask, cls_index **out) try {
+    if (!out) return fail(CLS_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CU_TRY(cudaGetDeviceCount(&n));
+    std::vector<int> devs;
+    for (int d = 0; d < n && d < 64; ++d)
+        if (device_mask == 0 || ((device_mask >> d) & 1ull)) devs.push_back(d);
+    if (devs.empty()) return fail(CLS_ERR_INVALID_ARGUMENT, "device_mask names no visible CUDA device");
+    if (device_mask >> (n < 64 ? n : 63) > (n < 64 ? 0ull : 1ull)) return fail(CLS_ERR_INVALID_ARGUMENT, "device_mask names a device that is not visible");
+    return cls_index_create_devices(model, (uint32_t)devs.size(), devs.data(), out);
 } CLS_ABI_CATCH
 
 void cls_index_destroy(cls_index *ix) { delete ix; }
@@ -509,8 +567,7 @@ int cls_index_get_info(const cls_index *ix, cls_index_info *info) try {
     return CLS_OK;
 } CLS_ABI_CATCH
 
-int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) try {
-    if (!ix || !batch || !params || !result) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) {
     if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
     const double t0 = now_ms();
     CU_TRY(cudaSetDevice(ix->device));
@@ -626,10 +683,78 @@ int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *par
     tm.total_ms = now_ms() - t0;
     { std::lock_guard<std::mutex> lk(ix->mu); ix->timing = tm; }
     return CLS_OK;
+}
+
+// Multi-device handle: the batch is cut into one contiguous part per replica (equal shares of the bases), every part
+// goes through the single-device pipeline on its own host thread (the packing loops of all parts share the one host
+// pool), and the result arrays are written in place - the reference's single process fanning out over its workers
+// (ports/cli/src/cmds/place_sequences.rs:125-156, place_sequences/mod.rs:123-126).
+static int place_batch_multi(cls_index *front, const cls_batch *batch, const cls_params *params, cls_result *result) {
+    const size_t nd = front->replicas.size();
+    const uint64_t n = batch->n_queries;
+    if (n && !batch->offsets) return fail(CLS_ERR_INVALID_ARGUMENT, "batch arrays are NULL");
+    std::vector<uint64_t> cut(nd + 1, n);
+    cut[0] = 0;
+    if (n) {
+        const uint64_t b0 = batch->offsets[0], total = batch->offsets[n] >= b0 ? batch->offsets[n] - b0 : 0;
+        for (size_t d = 1; d < nd; ++d) {
+            const uint64_t want = b0 + (uint64_t)((long double)total * d / nd);
+            uint64_t lo = cut[d - 1], hi = n;      // first query starting at or after `want` (offsets are checked per part)
+            while (lo < hi) { const uint64_t mid = (lo + hi) / 2; if (batch->offsets[mid] < want) lo = mid + 1; else hi = mid; }
+            cut[d] = lo;
+        }
+    }
+    std::vector<int> rcs(nd, CLS_OK);
+    std::vector<std::string> errs(nd);
+    auto run = [&](size_t d) {
+        const uint64_t a = cut[d], cnt = cut[d + 1] - a;
+        if (cnt == 0) return;
+        const cls_batch part{cnt, batch->bases, batch->offsets + a};   // offsets are absolute into `bases`
+        cls_result r{};
+        r.status = result->status ? result->status + a : nullptr;
+        r.node_id = result->node_id ? result->node_id + a : nullptr;
+        r.one = result->one ? result->one + a : nullptr;
+        r.rest = result->rest ? result->rest + a : nullptr;
+        r.n_query_kmers = result->n_query_kmers ? result->n_query_kmers + a : nullptr;
+        r.n_matched = result->n_matched ? result->n_matched + a : nullptr;
+        r.n_root_matched = result->n_root_matched ? result->n_root_matched + a : nullptr;
+        r.iterations = result->iterations ? result->iterations + a : nullptr;
+        try {
+            rcs[d] = place_batch_one(front->replicas[d].get(), &part, params, &r);
+        } catch (const std::bad_alloc &) {
+            rcs[d] = fail(CLS_ERR_OUT_OF_MEMORY, "host allocation failed");
+        } catch (const std::exception &e) {
+            rcs[d] = fail(CLS_ERR_INVALID_ARGUMENT, e.what());
+        }
+        if (rcs[d] != CLS_OK) errs[d] = g_last_error;   // thread-local: carry it to the caller's thread
+    };
+    std::vector<std::thread> th;
+    for (size_t d = 1; d < nd; ++d) th.emplace_back(run, d);
+    run(0);
+    for (auto &t : th) t.join();
+    cls_timing tm{};
+    for (size_t d = 0; d < nd; ++d) {
+        std::lock_guard<std::mutex> lk(front->replicas[d]->mu);
+        const cls_timing &t = front->replicas[d]->timing;
+        tm.pack_ms = std::max(tm.pack_ms, t.pack_ms); tm.h2d_ms = std::max(tm.h2d_ms, t.h2d_ms);
+        tm.kernel_ms = std::max(tm.kernel_ms, t.kernel_ms); tm.d2h_ms = std::max(tm.d2h_ms, t.d2h_ms);
+        tm.total_ms = std::max(tm.total_ms, t.total_ms); tm.kernel_launches += t.kernel_launches;
+    }
+    { std::lock_guard<std::mutex> lk(front->mu); front->timing = tm; }
+    for (size_t d = 0; d < nd; ++d)
+        if (rcs[d] != CLS_OK) return fail(rcs[d], errs[d]);
+    return CLS_OK;
+}
+
+int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) try {
+    if (!ix || !batch || !params || !result) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ix->replicas.empty()) return place_batch_multi(ix, batch, params, result);
+    return place_batch_one(ix, batch, params, result);
 } CLS_ABI_CATCH
 
 int cls_batch_upload(cls_index *ix, const cls_batch *batch, cls_resident_batch **out) try {
     if (!ix || !batch || !out) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ix->replicas.empty()) ix = ix->replicas[0].get();   // a multi-device handle: resident batches live on its first device
     *out = nullptr;
     CU_TRY(cudaSetDevice(ix->device));
     auto rb = std::make_unique<cls_resident_batch>();
@@ -655,6 +780,7 @@ int cls_batch_upload(cls_index *ix, const cls_batch *batch, cls_resident_batch *
 // ---- FASTA ingest on the device (file_or_stdin.rs:76-116, sequence.rs:47-56) -----------
 int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_resident_batch **out, cls_fasta_records *records) try {
     if (!ix || !out || !records || (n_bytes && !text)) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ix->replicas.empty()) ix = ix->replicas[0].get();   // a multi-device handle: resident batches live on its first device
     *out = nullptr;
     std::memset(records, 0, sizeof *records);
     if (n_bytes >= (1ull << 32)) return fail(CLS_ERR_UNSUPPORTED, "FASTA text of 4 GiB or more: split it (the tile summaries count in 32 bits)");
@@ -783,6 +909,7 @@ int cls_fasta_upload(cls_index *ix, const uint8_t *text, uint64_t n_bytes, cls_r
 
 int cls_place_resident(cls_index *ix, cls_resident_batch *rb, const cls_params *params, void *stream) try {
     if (!ix || !rb || !params) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ix->replicas.empty()) ix = ix->replicas[0].get();   // a multi-device handle: resident batches live on its first device
     if (rb->device != ix->device) return fail(CLS_ERR_INVALID_ARGUMENT, "resident batch lives on another device");
     if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
     CU_TRY(cudaSetDevice(ix->device));
@@ -795,6 +922,7 @@ int cls_place_resident(cls_index *ix, cls_resident_batch *rb, const cls_params *
 
 int cls_resident_fetch(cls_index *ix, cls_resident_batch *rb, void *stream, cls_result *result) try {
     if (!ix || !rb || !result) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ix->replicas.empty()) ix = ix->replicas[0].get();   // a multi-device handle: resident batches live on its first device
     CU_TRY(cudaSetDevice(ix->device));
     const size_t res_b = (size_t)rb->lay.n_device * sizeof(ResultRec);
     if (res_b) {
@@ -987,6 +1115,7 @@ int cls_debug_kmer_hashes(int device, uint32_t k_size, const uint8_t *bases, uin
 int cls_debug_node_counts(cls_index *ix, const uint8_t *bases, uint64_t len, const cls_params *params, cls_level_count *rows,
                           uint64_t cap, uint64_t *n_rows, cls_result *result) try {
     if (!ix || !params || !n_rows || (len && !bases) || (cap && !rows)) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ix->replicas.empty()) ix = ix->replicas[0].get();   // a multi-device handle: resident batches live on its first device
     *n_rows = 0;
     if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index");
     if (len < ix->dix.k_size || len >= (1ull << 20)) return fail(CLS_ERR_INVALID_ARGUMENT, "query shorter than k or longer than 2^20 bases");

@@ -19,6 +19,10 @@ static_assert(sizeof(Slot) == 16, "slot must be 16 bytes");
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kOverflowBit = 0x80000000u;
 constexpr uint32_t kCodeMask = 0x00FFFFFFu;
+// bits 24..31 of the code of slot 1: an 8-bit filter over the entries whose HOME is this bucket but which were stored
+// further along the chain (bit (hash >> 40) & 7).  A probe that misses in its home bucket follows the chain only if
+// its own bit is set (scan2_kernel); the overflow bit alone (every kernel may use it) says "some entry went on".
+constexpr uint32_t kBloomShift = 24;
 
 // ---- node-set records, GENERAL mode ("mini-trees") -----------------------------------
 // One record per DISTINCT node set: the set restricted to the non-leaf nodes of the model

@@ -384,7 +384,8 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err,
         const uint64_t mask = nb - 1;
         uint64_t max_dist = 0;
         for (const KeptEntry &e : kept) {
-            uint64_t b = e.hash & mask, dist = 0;
+            const uint64_t home = e.hash & mask;
+            uint64_t b = home, dist = 0;
             for (;;) {
                 Slot *s = &out.table[2 * b];
                 if (s[0].set_off == kEmpty) { uint32_t ov = s[0].code & kOverflowBit; s[0] = Slot{e.hash, e.set_off, e.code | ov}; break; }
@@ -393,6 +394,8 @@ int build_host_index(const cls_model_view *mv, HostIndex &out, std::string &err,
                 b = (b + 1) & mask;
                 ++dist;
             }
+            // the home bucket is full by now: slot 1's code carries the filter of the entries that moved on
+            if (dist) out.table[2 * home + 1].code |= 1u << (kBloomShift + (uint32_t)((e.hash >> 40) & 7u));
             if (dist > max_dist) max_dist = dist;
         }
         // a miss walks one bucket past the last overflowed one

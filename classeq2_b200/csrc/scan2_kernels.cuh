@@ -59,8 +59,16 @@ __device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t
 }
 __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-constexpr uint32_t kListCap = 128;     // {node-set record, count} entries a read may append before the merge
-constexpr uint32_t kMergeSlots = 128;  // slots of the merge table (>= kListCap: probing always terminates)
+// the bucket load of the lanes that have a window in the pass (the others keep their registers)
+__device__ __forceinline__ void ld_bucket_if(bool p, const Slot *table, uint64_t bucket, uint64_t &h0, uint64_t &m0, uint64_t &h1,
+                                             uint64_t &m1);
+constexpr uint32_t kListCap = 128;     // list area in entries
+constexpr uint32_t kListUse = 128;     // {node-set record, count} entries a read may append before the merge
+constexpr uint32_t kMergeSlots = 128;  // slots of the merge table (> kListUse: probing always terminates)
+#ifndef CLS_S2_BLOCK
+#define CLS_S2_BLOCK 8
+#endif
+constexpr uint32_t kScanBlock = CLS_S2_BLOCK;     // reads a warp takes from the global counter at a time
 
 // Per-warp shared memory, byte offsets from the warp's base (a multiple of 512: the ring halves alternate by
 // an XOR with 256 on the address).  PPS = passes per strand the geometry allows: 4 (reads of up to 162 bases)
@@ -82,6 +90,7 @@ struct Scan2Layout {
     static constexpr uint32_t oPkF = oStrR + 4 * kStrWords;
     static constexpr uint32_t oPkR = oPkF + 4 * kPkWords;
     static constexpr uint32_t kBytes = (oPkR + 4 * kPkWords + 511u) & ~511u;
+
     static constexpr uint32_t kMaxLen = 32 * PPS + 34;
 };
 
@@ -94,15 +103,91 @@ __device__ __forceinline__ void premix_ring(uint32_t src, uint32_t sh8, uint32_t
     sts_u64(dst + 512, premix_k2(x));
 }
 
+__device__ __forceinline__ void ld_bucket_if(bool p, const Slot *table, uint64_t bucket, uint64_t &h0, uint64_t &m0, uint64_t &h1,
+                                             uint64_t &m1) {
+#if CLS_S2_LD128
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "setp.ne.u32 p, %5, 0;\n\t"
+                 "@p ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%4];\n\t"
+                 "@p ld.global.nc.L1::no_allocate.v2.u64 {%2,%3}, [%4+16];\n\t"
+                 "}"
+                 : "+l"(h0), "+l"(m0), "+l"(h1), "+l"(m1)
+                 : "l"(table + 2 * bucket), "r"((uint32_t)p));
+#else
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "setp.ne.u32 p, %5, 0;\n\t"
+                 "@p ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];\n\t"
+                 "}"
+                 : "+l"(h0), "+l"(m0), "+l"(h1), "+l"(m1)
+                 : "l"(table + 2 * bucket), "r"((uint32_t)p));
+#endif
+}
+
+// 16 two-bit codes -> 16 ASCII letters (four words), by spreading the codes into nibbles for PRMT on "ACTG"
+__device__ __forceinline__ void decode16(uint32_t v, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t x = hlf ? v >> 16 : v & 0xFFFFu;
+        x = (x | (x << 8)) & 0x00FF00FFu;
+        x = (x | (x << 4)) & 0x0F0F0F0Fu;
+        x = (x | (x << 2)) & 0x33333333u;
+        out[2 * hlf] = __byte_perm(kAsciiLut, 0u, x & 0xFFFFu);
+        out[2 * hlf + 1] = __byte_perm(kAsciiLut, 0u, x >> 16);
+    }
+}
+
+// decode_read for reads of at most 16 packed words (PPS = 4 geometry): lanes 0-15 own the forward words, lanes
+// 16-31 the reverse-complement words (built from the forward ones by shuffles); one 16-byte store per lane.
+template <int PPS>
+__device__ __forceinline__ void decode_read16(const uint32_t *__restrict__ packed, uint32_t len, uint32_t wb) {
+    using Ly = Scan2Layout<PPS>;
+    const uint32_t lane = threadIdx.x & 31u, t = lane & 15u;
+    const uint32_t nw = (len + 15u) >> 4;
+    const uint32_t pad2 = 2u * (nw * 16u - len);  // unused bits at the top of the last word
+    uint32_t w = 0;
+    if (lane < nw) w = __ldg(packed + lane);
+    const uint32_t r = revcomp16(w);
+    // reverse-complement word t = bases [16t, 16t + 16) of the reversed string
+    const uint32_t a = __shfl_sync(kFull, r, (nw - 1u - t) & 31u), b = __shfl_sync(kFull, r, (nw - 2u - t) & 31u);
+    uint32_t v = w;
+    if (lane >= 16) v = t < nw ? __funnelshift_r(a, t + 1u < nw ? b : 0u, pad2) : 0u;
+    uint32_t q[4];
+    decode16(v, q);
+    const uint32_t sbase = wb + (lane >= 16 ? Ly::oStrR : Ly::oStrF) + 16u * t;
+    if (t < Ly::kStrWords / 4)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
+    sts_u32(wb + (lane >= 16 ? Ly::oPkR : Ly::oPkF) + 4u * t, v);
+}
+
 #ifndef CLS_SCAN2_MINB
 #define CLS_SCAN2_MINB 5
+#endif
+// A/B switches of this file (tools/build_variants.sh); the defaults are what measured best
+#ifndef CLS_S2_DIRECT
+#define CLS_S2_DIRECT 1       // lists of up to 32 entries are handed over unmerged
+#endif
+#ifndef CLS_S2_FASTDECODE
+#define CLS_S2_FASTDECODE 1   // decode_read16 for the PPS = 4 geometry
+#endif
+#ifndef CLS_S2_PREFETCH
+#define CLS_S2_PREFETCH 1     // L1 prefetch of the next read's packed bases
+#endif
+#ifndef CLS_S2_PREDLOAD
+#define CLS_S2_PREDLOAD 1     // lanes without a window do not load a bucket (0: they load bucket 0)
+#endif
+#ifndef CLS_S2_BLOOM
+#define CLS_S2_BLOOM 1        // a miss follows the overflow chain only if the home bucket's 8-bit filter has its bit
+#endif
+#ifndef CLS_S2_LD128
+#define CLS_S2_LD128 0        // the bucket as two 128-bit loads instead of one 256-bit load
 #endif
 
 // One pass (32 windows) whose bucket load is in flight.
 struct Flight {
     uint64_t h, q0, qm0, q1, qm1;   // window hash of this lane; the two slots {hash, set_off | code << 32} of its bucket
-    uint32_t b, gate;               // bucket index; the window's bucket-key prefix code
-    bool valid;                     // the lane has a window in this pass
+    uint32_t gate;                  // the window's bucket-key prefix code
 };
 
 // Per-lane constants and per-read state of the scan loop.
@@ -138,8 +223,6 @@ __device__ __forceinline__ void scan2_hash(Scan2Ctx &cx, uint32_t it, Flight &f)
     const uint32_t tv = __funnelshift_r(lds_u32(pbase + 8u * c + 8u), lds_u32(pbase + 8u * c + 12u), cx.sh2);
     __syncwarp();
     f.h = window_hash35(a0, b1, a2, b3, lds_u64(cx.wb + Ly::oLut + ((tv << 3) & 0x1F8u)));
-    f.valid = 32u * c + (threadIdx.x & 31u) < cx.W;
-    f.b = f.valid ? (uint32_t)f.h & cx.bmask : 0u;  // lanes past the last window load bucket 0 and ignore it
     f.gate = cx.gate_next & cx.code_mask;
     cx.gate_next = tv;
 }
@@ -149,26 +232,32 @@ template <int PPS>
 __device__ __forceinline__ void scan2_consume(Scan2Ctx &cx, const DeviceIndex &ix, const WarpMem &wm, uint32_t pi, Flight &f) {
     using Ly = Scan2Layout<PPS>;
     const uint32_t lane = threadIdx.x & 31u;
+    // lanes past the last window of the strand hashed (and probed) whatever the strings hold there: ignored
+    const bool valid = 32u * (pi >= cx.n_chunks ? pi - cx.n_chunks : pi) + lane < cx.W;
+    uint32_t b = (uint32_t)f.h & cx.bmask;
     // free slots carry a hash that no probe of their bucket can ask for (index_build.cpp), so equality is a hit
     bool e0 = f.q0 == f.h, e1 = f.q1 == f.h;
-    bool hit = f.valid && (e0 || e1);
-    uint64_t mm = e0 ? f.qm0 : f.qm1;
-    uint32_t want = (uint32_t)(mm >> 32) & kCodeMask;
-    // rare: the bucket overflowed at build time and the hash is not in it, or the entry's bucket key is not the one
-    // of this window's own prefix (models whose bucket keys disagree with their k-mers; kmers_map.rs:55-70 accepts
-    // the key of ANY window of the query)
-    const bool chase = f.valid && !(e0 || e1) && ((uint32_t)(f.qm0 >> 32) & kOverflowBit);
-    if (__any_sync(kFull, chase || (hit && f.gate != want))) {
+    // rare: the bucket overflowed at build time and the hash is not in it - follow the chain (all lanes stay together)
+#if CLS_S2_BLOOM
+    // ... and the home bucket's filter (index_build.cpp: one of eight bits per entry that went elsewhere) has its bit
+    bool chase = valid && !(e0 || e1) && (((uint32_t)(f.qm1 >> 32) >> (kBloomShift + (((uint32_t)(f.h >> 32) >> 8) & 7u))) & 1u);
+#else
+    bool chase = valid && !(e0 || e1) && ((uint32_t)(f.qm0 >> 32) & kOverflowBit);
+#endif
+    while (__any_sync(kFull, chase)) {
         if (chase) {
-            do {
-                f.b = (f.b + 1) & cx.bmask;
-                ld_bucket(ix.table, f.b, f.q0, f.qm0, f.q1, f.qm1);
-                e0 = f.q0 == f.h; e1 = f.q1 == f.h;
-            } while (!(e0 || e1) && ((uint32_t)(f.qm0 >> 32) & kOverflowBit));
-            hit = e0 || e1;
-            mm = e0 ? f.qm0 : f.qm1;
-            want = (uint32_t)(mm >> 32) & kCodeMask;
+            b = (b + 1) & cx.bmask;
+            ld_bucket(ix.table, b, f.q0, f.qm0, f.q1, f.qm1);
+            e0 = f.q0 == f.h; e1 = f.q1 == f.h;
+            chase = !(e0 || e1) && ((uint32_t)(f.qm0 >> 32) & kOverflowBit);
         }
+    }
+    bool hit = valid && (e0 || e1);
+    const uint64_t mm = e0 ? f.qm0 : f.qm1;
+    const uint32_t want = (uint32_t)(mm >> 32) & kCodeMask;
+    // rarer still: the entry's bucket key is not the one of this window's own prefix (models whose bucket keys disagree
+    // with their k-mers; kmers_map.rs:55-70 accepts the key of ANY window of the query)
+    if (__any_sync(kFull, hit && f.gate != want)) {
         if (hit && f.gate != want) {
             hit = false;
             for (uint32_t q = 0; q < cx.W && !hit; ++q)
@@ -177,7 +266,7 @@ __device__ __forceinline__ void scan2_consume(Scan2Ctx &cx, const DeviceIndex &i
         __syncwarp();
     }
     const uint32_t set_off = (uint32_t)mm;
-    const uint32_t slot_key = 2u * f.b + (e0 ? 0u : 1u);
+    const uint32_t slot_key = 2u * b + (e0 ? 0u : 1u);
     // test-and-set filter on 13 hash bits the bucket index does not use first; a miss ORs nothing in
     const uint32_t hh = (uint32_t)(f.h >> 32);
     const uint32_t fbit = hit ? 1u << ((hh >> 8) & 31u) : 0u;
@@ -208,7 +297,7 @@ __device__ __forceinline__ void scan2_consume(Scan2Ctx &cx, const DeviceIndex &i
     const bool lead = fresh && (peers & cx.lt) == 0;
     const uint32_t lm = __ballot_sync(kFull, lead);
     const uint32_t at = cx.n_list + (uint32_t)__popc(lm & cx.lt);
-    if (lead && at < kListCap) sts_v2(cx.wb + Ly::oList + 8u * at, set_off, (uint32_t)__popc(peers));
+    if (lead && at < kListUse) sts_v2(cx.wb + Ly::oList + 8u * at, set_off, (uint32_t)__popc(peers));
     cx.n_list += (uint32_t)__popc(lm);
 }
 
@@ -217,7 +306,14 @@ __device__ __forceinline__ void scan2_step(Scan2Ctx &cx, const DeviceIndex &ix, 
     const bool more = it < cx.n_total;   // warp-uniform
     if (more) scan2_hash<PPS, HALF>(cx, it, cur);
     if (it > 0 && it <= cx.n_total) scan2_consume<PPS>(cx, ix, wm, it - 1u, prev);
-    if (more) ld_bucket(ix.table, cur.b, cur.q0, cur.qm0, cur.q1, cur.qm1);
+    if (more) {
+        const bool valid = 32u * (it >= cx.n_chunks ? it - cx.n_chunks : it) + (threadIdx.x & 31u) < cx.W;
+#if CLS_S2_PREDLOAD
+        ld_bucket_if(valid, ix.table, (uint32_t)cur.h & cx.bmask, cur.q0, cur.qm0, cur.q1, cur.qm1);
+#else
+        ld_bucket_if(true, ix.table, valid ? (uint32_t)cur.h & cx.bmask : 0u, cur.q0, cur.qm0, cur.q1, cur.qm1);
+#endif
+    }
 }
 
 template <int PPS>
@@ -250,21 +346,39 @@ __global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
     cx.str_lane = 4u * (lane >> 2); cx.pk_lane = 4u * (lane >> 4);
     __syncwarp();
 
-    uint32_t dyn_base = 0, dyn_used = kReadBlock;
+    uint32_t blk_base = 0, blk_used = kScanBlock;
 #pragma unroll 1
     for (;;) {
-        const uint32_t r = next_read(so.counters, dyn_base, dyn_used);
+        if (blk_used == kScanBlock) {
+            // a new block of reads: their descriptors (64 bytes) are requested now, in one go
+            uint32_t b0 = 0;
+            if (lane == 0) b0 = atomicAdd(so.counters, kScanBlock);
+            blk_base = __shfl_sync(kFull, b0, 0);
+            blk_used = 0;
+            if (blk_base >= n_reads) break;
+            if (lane < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(reads + first_read + blk_base) + 32u * lane));
+        }
+        const uint32_t r = blk_base + blk_used;
         if (r >= n_reads) break;
+        ++blk_used;
+        // warp-uniform loads: the loop bounds derived from the descriptor live in uniform registers
         const ReadDesc rd = reads[first_read + r];
         const uint32_t L = rd.len;
+#if CLS_S2_PREFETCH
+        if (blk_used < kScanBlock && r + 1u < n_reads) {   // the next read's packed bases, while this one is placed
+            const uint32_t nxt = reads[first_read + r + 1u].word_off;
+            if (lane < 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(packed + nxt) + 32u * lane));
+        }
+#endif
         cx.W = L - 34u;  // host guarantees 35 <= L <= Ly::kMaxLen
         sts_v4(cx.wb + Ly::oFilter + 16u * lane, 0u);
         sts_v4(cx.wb + Ly::oFilter + 512u + 16u * lane, 0u);
-        decode_read(packed + rd.word_off, L, wm, Ly::kPkWords);
+        if constexpr (PPS == 4 && CLS_S2_FASTDECODE) decode_read16<PPS>(packed + rd.word_off, L, cx.wb);
+        else decode_read(packed + rd.word_off, L, wm, Ly::kPkWords);
         cx.n_chunks = (cx.W + 31u) >> 5; cx.n_total = 2u * cx.n_chunks;
         cx.n_list = 0; cx.gate_next = 0;
         Flight fa, fb;
-        fa.h = fa.q0 = fa.qm0 = fa.q1 = fa.qm1 = 0; fa.b = fa.gate = 0; fa.valid = false;
+        fa.h = fa.q0 = fa.qm0 = fa.q1 = fa.qm1 = 0; fa.gate = 0;
         fb = fa;
         __syncwarp();
         // two passes per iteration: the ring halves and the two register sets alternate; pass `it` is hashed, the
@@ -274,11 +388,19 @@ __global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
             scan2_step<PPS, 0>(cx, ix, wm, it, fa, fb);
             scan2_step<PPS, 1>(cx, ix, wm, it + 1u, fb, fa);
         }
-        // ---- merge the list by node-set record and hand the read over -------------------------------------------
+        // ---- hand the read over: the list itself, or merged by node-set record when it is long --------------------
         __syncwarp();
-        bool overflow = cx.n_list > kListCap;
+        bool overflow = cx.n_list > kListUse;
         uint32_t D = 0, n_matched = 0;
-        if (!overflow && cx.n_list) {
+        uint2 *row = so.pairs + (size_t)r * so.cap;
+        if (CLS_S2_DIRECT && cx.n_list <= 32) {
+            // the descent is linear in the weights: a node set listed twice votes exactly like its summed entry, and up to
+            // 32 pairs cost the descent kernel the same (one pair per lane) - hand the list over as it is
+            uint2 e = make_uint2(0u, 0u);
+            if (lane < cx.n_list) { e = lds_v2(cx.wb + Ly::oList + 8u * lane); row[lane] = e; }
+            n_matched = __reduce_add_sync(kFull, e.y);   // every distinct hit is in exactly one count
+            D = cx.n_list;
+        } else if (!overflow) {
             sts_v4(cx.wb + Ly::oMergeKey + 16u * lane, kEmpty);
             sts_v4(cx.wb + Ly::oMergeCnt + 16u * lane, 0u);
             __syncwarp();
@@ -297,17 +419,16 @@ __global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
                 }
             }
             __syncwarp();
-            uint2 *row = so.pairs + (size_t)r * so.cap;
 #pragma unroll
             for (uint32_t q = 0; q < kMergeSlots / 32; ++q) {
-                const uint32_t s = 32u * q + lane;
-                const uint32_t key = lds_u32(cx.wb + Ly::oMergeKey + 4u * s), cnt = lds_u32(cx.wb + Ly::oMergeCnt + 4u * s);
+                const uint32_t sl = 32u * q + lane;
+                const uint32_t key = lds_u32(cx.wb + Ly::oMergeKey + 4u * sl), cnt = lds_u32(cx.wb + Ly::oMergeCnt + 4u * sl);
                 const bool has = key != kEmpty;
                 const uint32_t bm = __ballot_sync(kFull, has);
                 const uint32_t at = D + (uint32_t)__popc(bm & cx.lt);
                 if (has && at < so.cap) row[at] = make_uint2(key, cnt);
                 D += (uint32_t)__popc(bm);
-                n_matched += cnt;   // every distinct hit is in exactly one count
+                n_matched += cnt;
             }
             n_matched = __reduce_add_sync(kFull, n_matched);
             overflow = D > so.cap;

@@ -90,16 +90,28 @@ class Index:
     """A model serialised to one GPU (``cls_index_create``): upload once per model."""
 
     def __init__(self, model: Union[FlatModel, Tree, "_lib.ModelView"], device: int = 0, keepalive=None,
-                 shard: int = 0, n_shards: int = 1):
+                 shard: int = 0, n_shards: int = 1, devices=None, device_mask: Optional[int] = None):
         """``n_shards > 1``: this handle holds the k-mer table entries with ``(hash >> 61) % n_shards ==
         shard`` only (``cls_index_create_shard``); such a handle serves the routed calls of
-        :mod:`classeq2_b200.parallel` and refuses ``place_batch``."""
+        :mod:`classeq2_b200.parallel` and refuses ``place_batch``.
+
+        ``devices`` (a list of CUDA devices, repeats allowed) or ``device_mask`` (bit d = device d, 0 = all visible):
+        ONE handle over several GPUs (``cls_index_create_devices`` / ``cls_index_create_multi``): the index is
+        replicated, ``place_batch`` cuts every batch into one part per replica and runs them side by side."""
         if isinstance(model, Tree):
             model = FlatModel.from_tree(model)
         view = model.view if hasattr(model, "view") else model
         self._keep = (model, keepalive)
         self._h = C.c_void_p()
-        _lib.check(_lib.lib.cls_index_create_shard(C.byref(view), int(device), int(shard), int(n_shards), C.byref(self._h)))
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _lib.check(_lib.lib.cls_index_create_devices(C.byref(view), len(devices), devs, C.byref(self._h)))
+            device = devices[0] if len(devices) else 0
+        elif device_mask is not None:
+            _lib.check(_lib.lib.cls_index_create_multi(C.byref(view), int(device_mask), C.byref(self._h)))
+            device = self.info()["device"]
+        else:
+            _lib.check(_lib.lib.cls_index_create_shard(C.byref(view), int(device), int(shard), int(n_shards), C.byref(self._h)))
         self.device = int(device)
         self.shard, self.n_shards = int(shard), int(n_shards)
 

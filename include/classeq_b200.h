@@ -182,6 +182,22 @@ int cls_device_count(void);
 int cls_index_create(const cls_model_view *model, int device, cls_index **out);
 void cls_index_destroy(cls_index *index);
 
+/*
+ * ONE handle over several GPUs of the box, for callers that are a single process fanning out internally - the
+ * reference's CLI, API and watcher (ports/cli/src/cmds/place_sequences.rs:125-156,
+ * ports/watcher/src/cmds/watch_dir/mod.rs:480-490; the worker pool of place_sequences/mod.rs:123-126).  The
+ * index is built once on the host and replicated on every listed device; cls_place_batch and
+ * cls_place_sequences cut each batch into one contiguous part per replica (equal shares of the bases) and run the
+ * parts side by side, one host thread + stream set per replica, all sharing the library's one host pool; results
+ * are identical to the single-device call.  Every other call on such a handle (resident batches, FASTA ingest,
+ * debug exports) works on its first device.
+ *   cls_index_create_multi    `device_mask` bit d = CUDA device d; 0 = every visible device
+ *   cls_index_create_devices  an explicit list; a device may be listed more than once (several replicas and
+ *                             pipelines on one GPU)
+ */
+int cls_index_create_multi(const cls_model_view *model, uint64_t device_mask, cls_index **out);
+int cls_index_create_devices(const cls_model_view *model, uint32_t n_devices, const int *devices, cls_index **out);
+
 /* Introspection of a created index (all sizes in elements unless stated). */
 typedef struct cls_index_info {
     uint32_t k_size, m_size;
@@ -194,7 +210,7 @@ typedef struct cls_index_info {
     uint32_t max_nonleaf_fanout;
     int32_t device;
     uint32_t closed_sets;      /* 1: terminal-list records + LCA jumps; 0: general mini-tree records */
-    uint32_t reserved;
+    uint32_t n_devices;        /* 1, or the number of replicas behind a multi-device handle (`device` = the first) */
 } cls_index_info;
 int cls_index_get_info(const cls_index *index, cls_index_info *info);
 

@@ -291,6 +291,98 @@ void orc_place_batch(const void *model, const uint8_t *bases, const uint64_t *of
     for (auto &t : th) t.join();
 }
 
+// ---- the k-mer map of a tree from its tips' sequences ------------------------------------------------------
+// Restates build_database/mod.rs:62 and :140-168 (every k-mer of a tip's sequence, both strands, is inserted with the
+// ids on the root -> tip path: `get_leaves_with_paths`, `insert_or_append_kmer_hash`), for callers that pair every tip
+// with its own sequence.  Own implementation (sort + group), shares nothing with the product's builders.
+// Output as flat arrays (orc_built_*): entries sorted by (hash, bucket); distinct node sets, ids ascending.
+struct Built {
+    std::vector<uint64_t> entry_bucket, entry_hash, entry_set, set_off, set_node_ids;
+};
+
+void *orc_model_build(uint32_t k_size, uint32_t m_size, uint64_t n_nodes, const uint64_t *node_id, const uint64_t *child_off,
+                      const uint64_t *child_idx, uint64_t n_tips, const uint64_t *tip_node, const uint8_t *bases,
+                      const uint64_t *offsets, int n_threads) {
+    struct Occ { uint64_t hash, bucket; uint32_t tip; };
+    Model probe; probe.k = k_size; probe.m = m_size;
+    std::vector<std::vector<Occ>> per_thread((size_t)std::max(1, n_threads));
+    std::atomic<uint64_t> next{0};
+    std::atomic<bool> bad{false};
+    auto worker = [&](int w) {
+        std::vector<uint64_t> h, pk; bool inv;
+        for (;;) {
+            const uint64_t t = next.fetch_add(1);
+            if (t >= n_tips) break;
+            const unsigned char *sq = bases + offsets[t];
+            const uint64_t len = offsets[t + 1] - offsets[t];
+            if (!build_kmers(probe, sq, len, h, pk, inv)) { if (inv) bad = true; continue; }
+            // build_kmers lists the forward windows, then the windows of the reverse complement; the bucket key of a
+            // window is the hash of its first m characters (kmers_map.rs:10-13), i.e. pk in the same order
+            for (size_t i = 0; i < h.size(); ++i) per_thread[(size_t)w].push_back(Occ{h[i], pk[i], (uint32_t)t});
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int w = 0; w < std::max(1, n_threads); ++w) th.emplace_back(worker, w);
+        for (auto &t : th) t.join();
+    }
+    if (bad) return nullptr;
+    std::vector<Occ> occ;
+    { size_t n = 0; for (auto &v : per_thread) n += v.size(); occ.reserve(n); }
+    for (auto &v : per_thread) { occ.insert(occ.end(), v.begin(), v.end()); std::vector<Occ>().swap(v); }
+    std::sort(occ.begin(), occ.end(), [](const Occ &a, const Occ &b) {
+        return a.hash != b.hash ? a.hash < b.hash : (a.bucket != b.bucket ? a.bucket < b.bucket : a.tip < b.tip);
+    });
+    // parent of every node, for the root -> tip paths
+    std::vector<int64_t> parent(n_nodes, -1);
+    for (uint64_t v = 0; v < n_nodes; ++v)
+        for (uint64_t j = child_off[v]; j < child_off[v + 1]; ++j) parent[child_idx[j]] = (int64_t)v;
+    auto *out = new Built();
+    struct VecHash { size_t operator()(const std::vector<uint32_t> &v) const { size_t x = 1469598103934665603ull; for (uint32_t e : v) { x ^= e; x *= 1099511628211ull; } return x; } };
+    std::unordered_map<std::vector<uint32_t>, uint64_t, VecHash> set_of_tips;
+    out->set_off.push_back(0);
+    std::vector<uint32_t> tips;
+    for (size_t i = 0; i < occ.size();) {
+        size_t j = i;
+        tips.clear();
+        while (j < occ.size() && occ[j].hash == occ[i].hash && occ[j].bucket == occ[i].bucket) {
+            if (tips.empty() || tips.back() != occ[j].tip) tips.push_back(occ[j].tip);
+            ++j;
+        }
+        auto it = set_of_tips.find(tips);
+        uint64_t sidx;
+        if (it == set_of_tips.end()) {
+            sidx = out->set_off.size() - 1;
+            set_of_tips.emplace(tips, sidx);
+            std::vector<uint64_t> ids;
+            for (uint32_t t : tips)
+                for (int64_t v = (int64_t)tip_node[t]; v >= 0; v = parent[(size_t)v]) ids.push_back(node_id[(size_t)v]);
+            std::sort(ids.begin(), ids.end());
+            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+            out->set_node_ids.insert(out->set_node_ids.end(), ids.begin(), ids.end());
+            out->set_off.push_back(out->set_node_ids.size());
+        } else {
+            sidx = it->second;
+        }
+        out->entry_bucket.push_back(occ[i].bucket); out->entry_hash.push_back(occ[i].hash); out->entry_set.push_back(sidx);
+        i = j;
+    }
+    return out;
+}
+void orc_built_sizes(const void *b, uint64_t *n_entries, uint64_t *n_sets, uint64_t *n_ids) {
+    const Built &x = *(const Built *)b;
+    *n_entries = x.entry_hash.size(); *n_sets = x.set_off.size() - 1; *n_ids = x.set_node_ids.size();
+}
+void orc_built_copy(const void *b, uint64_t *entry_bucket, uint64_t *entry_hash, uint64_t *entry_set, uint64_t *set_off, uint64_t *set_node_ids) {
+    const Built &x = *(const Built *)b;
+    std::copy(x.entry_bucket.begin(), x.entry_bucket.end(), entry_bucket);
+    std::copy(x.entry_hash.begin(), x.entry_hash.end(), entry_hash);
+    std::copy(x.entry_set.begin(), x.entry_set.end(), entry_set);
+    std::copy(x.set_off.begin(), x.set_off.end(), set_off);
+    std::copy(x.set_node_ids.begin(), x.set_node_ids.end(), set_node_ids);
+}
+void orc_built_destroy(void *b) { delete (Built *)b; }
+
 // All window hashes of one query, reference order (forward, then reverse complement).
 uint64_t orc_kmer_hashes(const uint8_t *bases, uint64_t len, uint32_t k, uint64_t *out, uint64_t cap) {
     Model md; md.k = k; md.m = 0;

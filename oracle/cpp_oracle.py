@@ -33,6 +33,11 @@ def _load():
     lib.orc_kmer_hashes.restype = C.c_uint64
     lib.orc_kmer_hashes.argtypes = [u8p, C.c_uint64, C.c_uint32, u64p, C.c_uint64]
     lib.orc_murmur3_x64_128.argtypes = [u8p, C.c_uint64, C.c_uint64, u64p]
+    lib.orc_model_build.restype = C.c_void_p
+    lib.orc_model_build.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, u64p, u64p, u64p, C.c_uint64, u64p, u8p, u64p, C.c_int]
+    lib.orc_built_sizes.argtypes = [C.c_void_p, u64p, u64p, u64p]
+    lib.orc_built_copy.argtypes = [C.c_void_p, u64p, u64p, u64p, u64p, u64p]
+    lib.orc_built_destroy.argtypes = [C.c_void_p]
     return lib
 
 
@@ -98,6 +103,36 @@ class CppModel:
             self.close()
         except Exception:
             pass
+
+
+class OracleFlat:
+    """Flat arrays of a model (the attributes CppModel.from_flat reads)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self.n_entries = len(self.entry_hash)
+
+
+def build_model(k_size, m_size, node_id, node_kind, child_off, child_idx, tip_node, bases, offsets, n_threads=None) -> OracleFlat:
+    """The k-mer map of a tree whose tip t carries the sequence bases[offsets[t]:offsets[t+1]] (both strands, node set =
+    ids on the root -> tip path), built by the oracle's own builder (build_database/mod.rs:62, :140-168)."""
+    u64 = lambda a: np.ascontiguousarray(a, dtype=np.uint64)  # noqa: E731
+    node_id, child_off, child_idx, tip_node, offsets = u64(node_id), u64(child_off), u64(child_idx), u64(tip_node), u64(offsets)
+    bases = np.ascontiguousarray(bases, np.uint8)
+    h = lib.orc_model_build(int(k_size), int(m_size), len(node_id), _p(node_id, u64p), _p(child_off, u64p), _p(child_idx, u64p),
+                            len(tip_node), _p(tip_node, u64p), _p(bases, u8p), _p(offsets, u64p), int(n_threads or os.cpu_count() or 1))
+    if not h:
+        raise ValueError("a tip sequence holds a character other than A, C, G, T")
+    h = C.c_void_p(h)
+    n = (C.c_uint64 * 3)()
+    lib.orc_built_sizes(h, C.cast(C.byref(n, 0), u64p), C.cast(C.byref(n, 8), u64p), C.cast(C.byref(n, 16), u64p))
+    eb, eh, es = (np.empty(n[0], np.uint64) for _ in range(3))
+    so, ids = np.empty(n[1] + 1, np.uint64), np.empty(max(1, n[2]), np.uint64)
+    lib.orc_built_copy(h, _p(eb, u64p), _p(eh, u64p), _p(es, u64p), _p(so, u64p), _p(ids, u64p))
+    lib.orc_built_destroy(h)
+    return OracleFlat(k_size=int(k_size), m_size=int(m_size), node_id=node_id, node_kind=np.ascontiguousarray(node_kind, np.uint8),
+                      child_off=child_off, child_idx=child_idx, entry_bucket=eb, entry_hash=eh, entry_set=es, set_off=so,
+                      set_node_ids=ids[: n[2]])
 
 
 def kmer_hashes(seq: bytes, k: int) -> np.ndarray:

@@ -84,3 +84,28 @@ def test_cpp_matches_python_on_synthetic(cpp, oracle):
     for ri in (False, True):
         out = md.place_batch(bases, offsets, remove_intersection=ri)
         _check(out, [outcome_of(oracle, "r", s, otree, None, None, ri) for s in seqs])
+
+
+@pytest.mark.parametrize("n_tips, l_ref, seed", [(12, 80, 3), (60, 300, 4242), (300, (200, 260), 9)])
+def test_oracle_builder_equals_product_builder(cpp, n_tips, l_ref, seed):
+    """The C++ oracle's own k-mer map builder (build_database/mod.rs:62, :140-168; it is what bench.py's reference arm
+    builds its model with) against the library's host builder: the same (bucket key, hash) -> node ids map."""
+    from classeq2_b200 import synth
+    sm = synth.make_model(n_tips, l_ref, seed)
+    b, o = synth.refs_to_batch(sm.ref_codes, sm.ref_lens)
+    t = sm.tree
+    f = cpp.build_model(35, 4, t.node_id, t.node_kind, t.child_off, t.child_idx, t.tip_node, b, o, n_threads=3)
+
+    def as_map(F):
+        so = F.set_off.astype(np.int64)
+        return {(int(F.entry_bucket[e]), int(F.entry_hash[e])): tuple(sorted(F.set_node_ids[so[int(F.entry_set[e])]:so[int(F.entry_set[e]) + 1]].tolist()))
+                for e in range(len(F.entry_hash))}
+
+    assert as_map(f) == as_map(sm.flat)
+    assert len(f.set_off) == len(sm.flat.set_off)   # the same number of distinct node sets
+    # and placements against either model agree
+    bases, offsets, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, 100, 150, seed + 2)
+    m1, m2 = cpp.CppModel.from_flat(f), cpp.CppModel.from_flat(sm.flat)
+    o1, o2 = m1.place_batch(bases, offsets), m2.place_batch(bases, offsets)
+    for k in o1:
+        assert (o1[k] == o2[k]).all(), k
