@@ -18,6 +18,7 @@ from typing import Dict, List, Optional, Tuple, Union
 import numpy as np
 
 from .model import BuiltModel, Clade, FlatModel, KmersMap, Tree
+from .engine import filter_sequence
 from .placement import read_fasta
 
 _LABEL = re.compile(r"[^(),:;]+")
@@ -125,18 +126,50 @@ def tree_from_newick(newick: str, file_name: str, min_branch_support: float) -> 
                 min_branch_support=float(min_branch_support), root=root)
 
 
+def build_loop_records(text: str) -> List[Tuple[str, str]]:
+    """The (header, sequence) pairs the reference's MSA loop indexes, in order (build_database/mod.rs:84-117): empty
+    lines are skipped; every line starting with '>' SENDS the new header (all '>' removed) together with the sequence
+    accumulated so far - i.e. the sequence of the PREVIOUS record (the first header gets whatever preceded it,
+    normally nothing) - and clears it; other lines are filtered to upper-case A/C/G/T and appended.  The sequence
+    after the last header is never sent."""
+    out: List[Tuple[str, str]] = []
+    parts: List[str] = []
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    for n, line in enumerate(lines):
+        if line.endswith("\r") and n < len(text.split("\n")) - 1:   # BufRead::lines: "\r\n" is a terminator, a bare "\r" is text
+            line = line[:-1]
+        if line == "":
+            continue
+        if line.startswith(">"):
+            out.append((line.replace(">", ""), "".join(parts)))
+            parts = []
+        else:
+            parts.append(filter_sequence(line))
+    return out
+
+
 def map_kmers_to_tree(tree_path: Union[str, os.PathLike], msa_path: Union[str, os.PathLike],
                       k_size: Optional[int] = None, m_size: Optional[int] = None,
                       min_branch_support: Optional[float] = None, device: Optional[int] = None,
-                      pairing: str = "own") -> Tree:
+                      pairing: str = "reference") -> Tree:
     """Same arguments and defaults as the reference (build_database/mod.rs:26-44: k = 35, m = 4, support >= 70).
-    Sequences whose header names no tip of the tree are ignored; tips without a sequence get no k-mers.
     ``device``: build the k-mer map on that GPU (``cls_model_build_device``) instead of the host builder; the
     result is the same map.
-    ``pairing``: ``"own"`` (default) indexes every tip with its own sequence; ``"reference"`` reproduces the
-    reference's MSA loop bit for bit - header i is indexed with sequence i-1, the first header gets no k-mers and
-    the last sequence is dropped (build_database/mod.rs:93-116; pinned by the reference's own build output,
-    tests/golden/reference_built_model_k12.json.gz)."""
+
+    ``pairing`` decides which sequence is indexed under which tip - the library calls (``cls_model_build*``) take
+    (tip, sequence) pairs and index exactly those, so the decision is made here, explicitly:
+
+    ``"reference"`` (default: a database built here equals the one the reference builds from the same files)
+        the reference's MSA loop bit for bit (:func:`build_loop_records`): header i is indexed with the sequence of
+        record i - 1, the first header gets no k-mers and the last sequence is dropped (build_database/mod.rs:93-116;
+        pinned by the reference's own build output, tests/golden/reference_built_model_k12.json.gz).  A header that
+        names no tip of the tree raises, as the reference panics (mod.rs:136-139).
+    ``"own"``
+        every tip with its own sequence - what the reference presumably meant; sequences whose header names no tip
+        are ignored, tips without a sequence get no k-mers.  Placements against such a database differ from
+        placements against a reference-built one."""
     if pairing not in ("own", "reference"):
         raise ValueError("pairing must be 'own' or 'reference'")
     k_size = 35 if k_size is None else int(k_size)
@@ -154,14 +187,22 @@ def map_kmers_to_tree(tree_path: Union[str, os.PathLike], msa_path: Union[str, o
         if cl.is_leaf() and cl.name is not None:
             tip_index.setdefault(cl.name, i)
     tip_node, seqs = [], []
-    records = list(read_fasta(msa_path))
     if pairing == "reference":
-        records = [(records[j][0], records[j - 1][1] if j else "") for j in range(len(records))]
-    for header, seq in records:
-        i = tip_index.get(header)
-        if i is not None and seq:
-            tip_node.append(i)
-            seqs.append(seq.encode("ascii"))
+        with open(msa_path, "r", encoding="utf-8", newline="") as f:
+            records = build_loop_records(f.read())
+        for header, seq in records:
+            i = tip_index.get(header)
+            if i is None:
+                raise ValueError(f"The sequence header does not match any tree leaf: {header}")
+            if seq:
+                tip_node.append(i)
+                seqs.append(seq.encode("ascii"))
+    else:
+        for header, seq in read_fasta(msa_path):
+            i = tip_index.get(header)
+            if i is not None and seq:
+                tip_node.append(i)
+                seqs.append(seq.encode("ascii"))
     offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
     if seqs:
         offsets[1:] = np.cumsum([len(s) for s in seqs])

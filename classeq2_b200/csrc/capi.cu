@@ -314,7 +314,7 @@ int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *par
     const PlaceParams pp = make_place_params(params);
     size_t want = 0;
     for (const LengthClass &c : lay.classes) {
-        want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size));
+        want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size, ix->dix.max_fanout));
     }
     if (want > scratch.cap) {
         if (scratch.p) CU_TRY(cudaStreamSynchronize(stream));  // an earlier placement on this stream may still use it
@@ -594,7 +594,11 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
     // results of finished chunks are scattered to the caller's arrays while later chunks run.
     struct Chunk { uint32_t first, count, max_len; };
     std::vector<Chunk> chunks;
-    static const uint64_t kChunkBases = [] { const char *e = getenv("CLS_CHUNK_MBASES"); return (uint64_t)(e ? atoi(e) : 24) << 20; }();  // bases per chunk
+    // bases per chunk: 24 M (160 k reads of 150 bases), more for big batches - at least a twelfth of the batch, so that
+    // the per-launch tails of the persistent kernels stay a small share of a chunk (CLS_CHUNK_MBASES fixes the size)
+    static const uint64_t kChunkEnv = [] { const char *e = getenv("CLS_CHUNK_MBASES"); return (uint64_t)(e ? atoi(e) : 0) << 20; }();
+    const uint64_t total_bases = batch->n_queries ? batch->offsets[batch->n_queries] - batch->offsets[0] : 0;
+    const uint64_t kChunkBases = kChunkEnv ? kChunkEnv : std::max<uint64_t>((uint64_t)24 << 20, total_bases / 12);
     for (const LengthClass &c : lay.classes) {
         const uint64_t per = std::max<uint64_t>(4096, kChunkBases / std::max<uint32_t>(c.max_len, 1));
         // the very first chunks are small so that the GPU starts early; later ones grow (fewer launch tails)
@@ -623,11 +627,11 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
         }
         return CLS_OK;
     };
-    // EXPERIMENT, off by default (CLS_PIPE=3): copies in, kernels and copies out on THREE streams chained by events, so that
-    // the kernels of consecutive chunks never share the SMs.  With the default two alternating streams the persistent
-    // scan kernel of chunk c + 1 can start while the descent kernel of chunk c still holds warp slots: its CTAs that are
-    // not resident yet keep their whole static share of the reads and finish late.  Not measured yet.
-    static const bool pipe3 = [] { const char *e = getenv("CLS_PIPE"); return e && atoi(e) == 3; }();
+    // Copies in, kernels and copies out run on THREE streams chained by events, so that the kernels of consecutive
+    // chunks never share the SMs (with everything of a chunk on one of two alternating streams the scan kernel of chunk
+    // c + 1 starts while the descent kernel of chunk c still holds warp slots: 8.13 against 7.70 ms per 1 M reads end to
+    // end, profiles/r2a).  CLS_PIPE=2 selects the two-stream pipeline (A/B).
+    static const bool pipe3 = [] { const char *e = getenv("CLS_PIPE"); return !(e && atoi(e) == 2); }();
     if (pipe3 && !w->stream3) CU_TRY(cudaStreamCreateWithFlags(&w->stream3, cudaStreamNonBlocking));
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const Chunk &c = chunks[ci];
@@ -645,9 +649,9 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
         if (pipe3) CU_TRY(cudaStreamWaitEvent(st_k, ev[1], 0));
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         DevBuf &scratch = w->d_scratch[ci & 1];  // stream order protects its reuse by the chunk after next
-        if (pipe3 && place_scratch_bytes(c.count, c.max_len, ix->dix.k_size) > scratch.cap && scratch.p)
+        if (pipe3 && place_scratch_bytes(c.count, c.max_len, ix->dix.k_size, ix->dix.max_fanout) > scratch.cap && scratch.p)
             CU_TRY(cudaStreamSynchronize(st_k));   // growing a scratch buffer frees it: nothing on the kernel stream may still use it
-        CU_TRY(scratch.reserve(place_scratch_bytes(c.count, c.max_len, ix->dix.k_size)));
+        CU_TRY(scratch.reserve(place_scratch_bytes(c.count, c.max_len, ix->dix.k_size, ix->dix.max_fanout)));
         uint32_t nl = 0;
         cudaError_t e = launch_place(ix->dix, pp, d_words, d_descs, c.first, c.count, d_res, g, ix->sm_count, st_k,
                                      scratch.p, scratch.cap, &nl);
@@ -1063,7 +1067,7 @@ int cls_place_routed(cls_index *ix, cls_resident_batch *rb, const void *d_replie
     CU_TRY(cudaSetDevice(ix->device));
     const PlaceParams pp = make_place_params(params);
     size_t want = 0;
-    for (const LengthClass &c : rb->lay.classes) want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size));
+    for (const LengthClass &c : rb->lay.classes) want = std::max(want, place_scratch_bytes(c.count, c.max_len, ix->dix.k_size, ix->dix.max_fanout));
     if (want > rb->d_scratch.cap) {
         if (rb->d_scratch.p) CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
         CU_TRY(rb->d_scratch.reserve(want));

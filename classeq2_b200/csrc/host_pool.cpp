@@ -11,8 +11,10 @@
 namespace cls {
 
 int host_threads() {
-    // CLS_HOST_THREADS overrides the default (all cores, at most 32).  Under torchrun every rank keeps the full
-    // pool: the ranks pack at different times, and a static split would idle cores while a rank waits for its GPU
+    // CLS_HOST_THREADS overrides the default: all cores, at most 32 - and under a launcher that runs one process per
+    // GPU (LOCAL_WORLD_SIZE = N > 1, torchrun) twice this rank's share of the cores: N pools of 32 threads on a 32-core
+    // box spent their time in the scheduler (pack_ms 3.2 -> 10.9 ms from 1 to 8 ranks, SCALE_r01), while an exact
+    // 1 / N split idles cores whenever the ranks pack at different times.
     static const int n = [] {
         if (const char *e = std::getenv("CLS_HOST_THREADS")) {
             const int v = std::atoi(e);
@@ -20,7 +22,12 @@ int host_threads() {
         }
         unsigned hc = std::thread::hardware_concurrency();
         if (hc == 0) hc = 4;
-        return (int)std::min(hc, 32u);
+        unsigned want = std::min(hc, 32u);
+        if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
+            const int lws = std::atoi(e);
+            if (lws > 1) want = std::max(2u, std::min(want, 2u * hc / (unsigned)lws));
+        }
+        return (int)want;
     }();
     return n;
 }

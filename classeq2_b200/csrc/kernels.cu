@@ -27,6 +27,7 @@
 // Integer/byte work bound by instruction issue (murmur3) and the HBM/L2 sector rate - no tensor cores.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <climits>
 #include <cstdlib>
 #include <cstdint>
@@ -822,7 +823,7 @@ struct ScanOut {
     uint32_t *counters;
     uint32_t *ov_list;   // reads scan2_kernel could not hand over (too many node sets): finished by scan_kernel afterwards
 };
-constexpr uint32_t kReadBlock = 4;
+constexpr uint32_t kReadBlock = 2;
 // next read of this warp, or >= n_reads when the launch has run out of reads
 __device__ __forceinline__ uint32_t next_read(uint32_t *counter, uint32_t &base, uint32_t &used) {
     if (used == kReadBlock) {
@@ -1173,6 +1174,7 @@ __global__ void CLS_DESCEND_BOUNDS descend_kernel(DeviceIndex ix, PlaceParams pp
 
 namespace {
 #include "scan2_kernels.cuh"
+#include "giant_kernels.cuh"
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1299,10 +1301,48 @@ static cudaError_t launch_place_m(const DeviceIndex &ix, const PlaceParams &pp, 
                           : launch_place_t<K, CLOSED, false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);
 }
 
+// ---- reads whose tables exceed the shared memory of an SM: tables in global memory (giant_kernels.cuh) ----
+static inline bool needs_giant(const PlaceGeom &g) {
+    return g.cta_per_read && (size_t)g.words_per_warp * 4 + (size_t)4 * kRing * 4 * 8 > (size_t)226 * 1024;
+}
+constexpr size_t kGiantWaveBytes = (size_t)1 << 30;   // arenas of one wave of giant reads
+static inline size_t giant_scratch_bytes(uint32_t n_reads, const PlaceGeom &g) {
+    const size_t per = (size_t)g.words_per_warp * 4;
+    const size_t wave = std::max<size_t>(1, kGiantWaveBytes / per);
+    return std::min<size_t>(n_reads, wave) * per + 256;
+}
+
+template <int K>
+static cudaError_t launch_giant(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed, const ReadDesc *reads,
+                                uint32_t first_read, uint32_t n_reads, ResultRec *results, const PlaceGeom &g, int sm_count,
+                                cudaStream_t stream, void *scratch, size_t scratch_bytes, uint32_t *n_launches) {
+    const size_t per = (size_t)g.words_per_warp * 4;
+    uint32_t *arenas = reinterpret_cast<uint32_t *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    if (!scratch || scratch_bytes < per + 256) return cudaErrorMemoryAllocation;
+    const uint32_t wave = (uint32_t)std::min<size_t>(n_reads, (scratch_bytes - 256) / per);
+    const uint32_t W = g.max_len - ix.k_size + 1, chunks = 2 * ((W + 31u) / 32u);
+    for (uint32_t a = 0; a < n_reads; a += wave) {
+        const uint32_t n = std::min(wave, n_reads - a);
+        // blocks per read: enough warps for its chunks, and about four blocks per SM over the wave
+        uint32_t bx = std::max<uint32_t>(1u, std::min<uint32_t>((chunks + 63u) / 64u, std::max<uint32_t>(1u, (uint32_t)(4 * sm_count) / n)));
+        const uint32_t bp = std::max<uint32_t>(1u, std::min<uint32_t>((g.words_per_warp + 256u * 64u - 1u) / (256u * 64u), std::max<uint32_t>(1u, (uint32_t)(8 * sm_count) / n)));
+        giant_prepare_kernel<<<dim3(bp, n), 256, 0, stream>>>(packed, reads, first_read + a, g, arenas);
+        giant_scan_kernel<K><<<dim3(bx, n), 256, 0, stream>>>(ix, reads, first_read + a, g, arenas);
+        if (ix.closed) giant_finish_kernel<true><<<n, 32, 0, stream>>>(ix, pp, first_read + a, results, g, arenas);
+        else giant_finish_kernel<false><<<n, 32, 0, stream>>>(ix, pp, first_read + a, results, g, arenas);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_launches) *n_launches += 3;
+    }
+    return cudaSuccess;
+}
+
 // ---- short reads, k = 35: scan kernel (+ descent kernel when the caller provides the hand-over scratch) ----
-size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k) {
-    if (split_disabled() || max_len < k || n_reads == 0) return 0;
-    const PlaceGeom g = make_place_geom(max_len, k, 1);
+size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k, uint32_t max_fanout) {
+    if (max_len < k || n_reads == 0) return 0;
+    const PlaceGeom g = make_place_geom(max_len, k, max_fanout);
+    if (needs_giant(g)) return giant_scratch_bytes(n_reads, g);
+    if (split_disabled()) return 0;
     if (g.cta_per_read) return scratch_bytes_for(n_reads, kPairCapWide);
     return k == 35 ? scratch_bytes_for(n_reads, kPairCap) : 0;
 }
@@ -1377,6 +1417,9 @@ cudaError_t launch_place(const DeviceIndex &ix, const PlaceParams &pp, const uin
                          const PlaceGeom &g, int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes,
                          uint32_t *n_launches) {
     if (n_reads == 0) return cudaSuccess;
+    if (needs_giant(g))
+        return ix.k_size == 35 ? launch_giant<35>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
+                               : launch_giant<0>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches);
     if (ix.k_size == 35 && !g.cta_per_read) {
         return ix.closed ? launch_scan_t<true>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, scratch, scratch_bytes, n_launches)
                          : launch_scan_t<false>(ix, pp, packed, reads, first_read, n_reads, results, g, sm_count, stream, nullptr, 0, n_launches);

@@ -51,7 +51,9 @@ cudaError_t launch_trace(const DeviceIndex &ix, const PlaceParams &pp, const uin
 // Scratch the short-read path (k = 35, closed models) wants for a launch over `n_reads` reads: the scan
 // kernel hands every read's {node set, weight} pairs to a separate descent kernel through it.  0 when that
 // path does not apply.  Without (enough) scratch the scan warps run the descent themselves.
-size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k);
+// Reads whose per-read tables exceed the shared memory of an SM (beyond ~4 kb at k = 35) keep their tables in this
+// scratch instead (giant_kernels.cuh): it is then REQUIRED, and sized for one wave of such reads.
+size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k, uint32_t max_fanout);
 
 // Places reads [first_read, first_read + n_reads) of a length class.  `n_launches` (optional) is
 // incremented once per kernel launched.

@@ -60,15 +60,17 @@ __device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t
 __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // the bucket load of the lanes that have a window in the pass (the others keep their registers)
-__device__ __forceinline__ void ld_bucket_if(bool p, const Slot *table, uint64_t bucket, uint64_t &h0, uint64_t &m0, uint64_t &h1,
+__device__ __forceinline__ void ld_bucket_if(bool p, uint64_t table, uint32_t bucket, uint64_t &h0, uint64_t &m0, uint64_t &h1,
                                              uint64_t &m1);
 constexpr uint32_t kListCap = 128;     // list area in entries
 constexpr uint32_t kListUse = 128;     // {node-set record, count} entries a read may append before the merge
 constexpr uint32_t kMergeSlots = 128;  // slots of the merge table (> kListUse: probing always terminates)
 #ifndef CLS_S2_BLOCK
-#define CLS_S2_BLOCK 8
+#define CLS_S2_BLOCK 2
 #endif
-constexpr uint32_t kScanBlock = CLS_S2_BLOCK;     // reads a warp takes from the global counter at a time
+// reads a warp takes from the global counter at a time: small, so that the last block of a launch is a small share of
+// a warp's work even in the chunked launches of cls_place_batch (about 30 reads per warp)
+constexpr uint32_t kScanBlock = CLS_S2_BLOCK;
 
 // Per-warp shared memory, byte offsets from the warp's base (a multiple of 512: the ring halves alternate by
 // an XOR with 256 on the address).  PPS = passes per strand the geometry allows: 4 (reads of up to 162 bases)
@@ -103,25 +105,29 @@ __device__ __forceinline__ void premix_ring(uint32_t src, uint32_t sh8, uint32_t
     sts_u64(dst + 512, premix_k2(x));
 }
 
-__device__ __forceinline__ void ld_bucket_if(bool p, const Slot *table, uint64_t bucket, uint64_t &h0, uint64_t &m0, uint64_t &h1,
+__device__ __forceinline__ void ld_bucket_if(bool p, uint64_t table, uint32_t bucket, uint64_t &h0, uint64_t &m0, uint64_t &h1,
                                              uint64_t &m1) {
 #if CLS_S2_LD128
     asm volatile("{\n\t"
                  ".reg .pred p;\n\t"
-                 "setp.ne.u32 p, %5, 0;\n\t"
-                 "@p ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%4];\n\t"
-                 "@p ld.global.nc.L1::no_allocate.v2.u64 {%2,%3}, [%4+16];\n\t"
+                 ".reg .u64 a;\n\t"
+                 "setp.ne.u32 p, %6, 0;\n\t"
+                 "mad.wide.u32 a, %5, 32, %4;\n\t"
+                 "@p ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [a];\n\t"
+                 "@p ld.global.nc.L1::no_allocate.v2.u64 {%2,%3}, [a+16];\n\t"
                  "}"
                  : "+l"(h0), "+l"(m0), "+l"(h1), "+l"(m1)
-                 : "l"(table + 2 * bucket), "r"((uint32_t)p));
+                 : "l"(table), "r"(bucket), "r"((uint32_t)p));
 #else
     asm volatile("{\n\t"
                  ".reg .pred p;\n\t"
-                 "setp.ne.u32 p, %5, 0;\n\t"
-                 "@p ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];\n\t"
+                 ".reg .u64 a;\n\t"
+                 "setp.ne.u32 p, %6, 0;\n\t"
+                 "mad.wide.u32 a, %5, 32, %4;\n\t"
+                 "@p ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [a];\n\t"
                  "}"
                  : "+l"(h0), "+l"(m0), "+l"(h1), "+l"(m1)
-                 : "l"(table + 2 * bucket), "r"((uint32_t)p));
+                 : "l"(table), "r"(bucket), "r"((uint32_t)p));
 #endif
 }
 
@@ -188,6 +194,7 @@ __device__ __forceinline__ void decode_read16(const uint32_t *__restrict__ packe
 struct Flight {
     uint64_t h, q0, qm0, q1, qm1;   // window hash of this lane; the two slots {hash, set_off | code << 32} of its bucket
     uint32_t gate;                  // the window's bucket-key prefix code
+    int32_t lim;                    // windows left in the strand when the pass began (warp-uniform): lane < lim has a window
 };
 
 // Per-lane constants and per-read state of the scan loop.
@@ -198,20 +205,23 @@ struct Scan2Ctx {
     uint32_t code_mask, bmask;
     uint32_t W, n_chunks, n_total;
     uint32_t n_list, gate_next;
+    uint32_t sb, pb;                // running shared-memory addresses: the next 32 offsets of the strand, the next tail words
+    int32_t lim;                    // windows of the strand not hashed yet
+    uint64_t table;                 // global address of the k-mer table
 };
 
 // Hash part of pass `it` (HALF = it & 1 = the ring half that holds the pass's own 32 offsets).
 template <int PPS, int HALF>
 __device__ __forceinline__ void scan2_hash(Scan2Ctx &cx, uint32_t it, Flight &f) {
     using Ly = Scan2Layout<PPS>;
-    const bool rc = it >= cx.n_chunks;
-    const uint32_t c = rc ? it - cx.n_chunks : it;
-    const uint32_t sbase = cx.wb + (rc ? Ly::oStrR : Ly::oStrF) + cx.str_lane, pbase = cx.wb + (rc ? Ly::oPkR : Ly::oPkF) + cx.pk_lane;
-    if (c == 0) {  // a strand begins: its first 32 offsets go to the half this pass reads first
-        premix_ring(sbase, cx.sh8, cx.A0 + 256u * HALF);
-        cx.gate_next = __funnelshift_r(lds_u32(pbase), lds_u32(pbase + 4), cx.sh2);
+    if (it == 0 || it == cx.n_chunks) {  // a strand begins: its first 32 offsets go to the half this pass reads first
+        const bool rc = it != 0;
+        const uint32_t s0 = cx.wb + (rc ? Ly::oStrR : Ly::oStrF) + cx.str_lane, p0 = cx.wb + (rc ? Ly::oPkR : Ly::oPkF) + cx.pk_lane;
+        premix_ring(s0, cx.sh8, cx.A0 + 256u * HALF);
+        cx.gate_next = __funnelshift_r(lds_u32(p0), lds_u32(p0 + 4), cx.sh2);
+        cx.sb = s0 + 32u; cx.pb = p0 + 8u; cx.lim = (int32_t)cx.W;
     }
-    premix_ring(sbase + 32u * (c + 1u), cx.sh8, cx.A0 + 256u * (1 - HALF));  // offsets 32 (c + 1) + lane -> the other half
+    premix_ring(cx.sb, cx.sh8, cx.A0 + 256u * (1 - HALF));  // the next 32 offsets -> the other half
     __syncwarp();
     uint64_t a0, b1, a2, b3;
     if (HALF == 0) {
@@ -220,11 +230,13 @@ __device__ __forceinline__ void scan2_hash(Scan2Ctx &cx, uint32_t it, Flight &f)
         a0 = lds_u64(cx.A0 + 256u); b1 = lds_u64(cx.O1); a2 = lds_u64(cx.O2); b3 = lds_u64(cx.O3);
     }
     // bases pos + 32 ...: the 3-base tail of this pass's windows, and the bucket-key prefix of the next pass's
-    const uint32_t tv = __funnelshift_r(lds_u32(pbase + 8u * c + 8u), lds_u32(pbase + 8u * c + 12u), cx.sh2);
+    const uint32_t tv = __funnelshift_r(lds_u32(cx.pb), lds_u32(cx.pb + 4u), cx.sh2);
     __syncwarp();
     f.h = window_hash35(a0, b1, a2, b3, lds_u64(cx.wb + Ly::oLut + ((tv << 3) & 0x1F8u)));
     f.gate = cx.gate_next & cx.code_mask;
+    f.lim = cx.lim;
     cx.gate_next = tv;
+    cx.sb += 32u; cx.pb += 8u; cx.lim -= 32;
 }
 
 // Consume the bucket of pass `pi`: match, gate by bucket key, de-duplicate, append to the read's list.
@@ -232,8 +244,8 @@ template <int PPS>
 __device__ __forceinline__ void scan2_consume(Scan2Ctx &cx, const DeviceIndex &ix, const WarpMem &wm, uint32_t pi, Flight &f) {
     using Ly = Scan2Layout<PPS>;
     const uint32_t lane = threadIdx.x & 31u;
-    // lanes past the last window of the strand hashed (and probed) whatever the strings hold there: ignored
-    const bool valid = 32u * (pi >= cx.n_chunks ? pi - cx.n_chunks : pi) + lane < cx.W;
+    // lanes past the last window of the strand hashed whatever the strings hold there: ignored
+    const bool valid = (int32_t)lane < f.lim;
     uint32_t b = (uint32_t)f.h & cx.bmask;
     // free slots carry a hash that no probe of their bucket can ask for (index_build.cpp), so equality is a hit
     bool e0 = f.q0 == f.h, e1 = f.q1 == f.h;
@@ -247,7 +259,7 @@ __device__ __forceinline__ void scan2_consume(Scan2Ctx &cx, const DeviceIndex &i
     while (__any_sync(kFull, chase)) {
         if (chase) {
             b = (b + 1) & cx.bmask;
-            ld_bucket(ix.table, b, f.q0, f.qm0, f.q1, f.qm1);
+            ld_bucket_if(true, cx.table, b, f.q0, f.qm0, f.q1, f.qm1);
             e0 = f.q0 == f.h; e1 = f.q1 == f.h;
             chase = !(e0 || e1) && ((uint32_t)(f.qm0 >> 32) & kOverflowBit);
         }
@@ -307,11 +319,11 @@ __device__ __forceinline__ void scan2_step(Scan2Ctx &cx, const DeviceIndex &ix, 
     if (more) scan2_hash<PPS, HALF>(cx, it, cur);
     if (it > 0 && it <= cx.n_total) scan2_consume<PPS>(cx, ix, wm, it - 1u, prev);
     if (more) {
-        const bool valid = 32u * (it >= cx.n_chunks ? it - cx.n_chunks : it) + (threadIdx.x & 31u) < cx.W;
+        const bool valid = (int32_t)(threadIdx.x & 31u) < cur.lim;
 #if CLS_S2_PREDLOAD
-        ld_bucket_if(valid, ix.table, (uint32_t)cur.h & cx.bmask, cur.q0, cur.qm0, cur.q1, cur.qm1);
+        ld_bucket_if(valid, cx.table, (uint32_t)cur.h & cx.bmask, cur.q0, cur.qm0, cur.q1, cur.qm1);
 #else
-        ld_bucket_if(true, ix.table, valid ? (uint32_t)cur.h & cx.bmask : 0u, cur.q0, cur.qm0, cur.q1, cur.qm1);
+        ld_bucket_if(true, cx.table, valid ? (uint32_t)cur.h & cx.bmask : 0u, cur.q0, cur.qm0, cur.q1, cur.qm1);
 #endif
     }
 }
@@ -337,6 +349,7 @@ __global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
     wm.pk_f = wbase + Ly::oPkF / 4; wm.pk_r = wbase + Ly::oPkR / 4;
     cx.code_mask = ix.m_eff >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ix.m_eff)) - 1u);
     cx.bmask = (uint32_t)ix.bucket_mask;  // at most 2^30 buckets (cls_index_create)
+    cx.table = reinterpret_cast<uint64_t>(ix.table);
     cx.sh8 = (lane & 3u) * 8u; cx.sh2 = (lane & 15u) * 2u;
     cx.lt = (1u << lane) - 1u;
     cx.A0 = cx.wb + Ly::oRingA + 8u * lane;
@@ -356,7 +369,7 @@ __global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
             blk_base = __shfl_sync(kFull, b0, 0);
             blk_used = 0;
             if (blk_base >= n_reads) break;
-            if (lane < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(reads + first_read + blk_base) + 32u * lane));
+            if (lane < (kScanBlock * 8u + 31u) / 32u) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(reads + first_read + blk_base) + 32u * lane));
         }
         const uint32_t r = blk_base + blk_used;
         if (r >= n_reads) break;
@@ -378,7 +391,8 @@ __global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
         cx.n_chunks = (cx.W + 31u) >> 5; cx.n_total = 2u * cx.n_chunks;
         cx.n_list = 0; cx.gate_next = 0;
         Flight fa, fb;
-        fa.h = fa.q0 = fa.qm0 = fa.q1 = fa.qm1 = 0; fa.gate = 0;
+        fa.h = fa.q0 = fa.qm0 = fa.q1 = fa.qm1 = 0; fa.gate = 0; fa.lim = 0;
+        cx.sb = cx.pb = 0; cx.lim = 0;
         fb = fa;
         __syncwarp();
         // two passes per iteration: the ring halves and the two register sets alternate; pass `it` is hashed, the

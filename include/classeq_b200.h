@@ -473,8 +473,12 @@ uint64_t cls_filter_sequence(const uint8_t *line, uint64_t len, uint8_t *out, ui
 /*
  * Host-side model builder (no GPU needed): the k-mer -> node-set map that the reference's
  * `map_kmers_to_tree` (core/src/use_cases/build_database/mod.rs:26-181) produces for a tree and
- * one sequence per tip, with every tip paired with ITS OWN sequence (the reference pairs header i
- * with sequence i-1, mod.rs:93-116 - a build-side defect outside the placement path).
+ * a list of (tip, sequence) pairs.  The call indexes EXACTLY the pairs it is given: which sequence
+ * goes with which tip is the caller's decision, and it matters - the reference's MSA loop pairs
+ * header i with the sequence of record i-1, gives the first header no k-mers and drops the last
+ * sequence (mod.rs:93-116), so a database that must equal a reference-built one has to be fed those
+ * pairs (the host mirror does so by default: classeq2_b200/build.py:map_kmers_to_tree(pairing=
+ * "reference"), build_loop_records; pairing="own" gives every tip its own sequence).
  * For every tip, every window of the sequence and of its reverse complement
  * (kmers_map.rs:375-398) is hashed; the node set of a (bucket key, hash) entry is the union of
  * the root->tip id paths (both ends included, clade.rs:127-156) of the tips containing it.

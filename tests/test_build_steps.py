@@ -122,7 +122,7 @@ def test_map_kmers_to_tree_reference_pairing(tmp_path, oracle, col_queries):
     oracle.map_kmers_to_tree(want, tips, 35, 4, pairing="reference")
     assert {k: {h: set(n) for h, n in v.items()} for k, v in got.kmers_map.map.items()} == \
            {k: {h: set(n) for h, n in v.items()} for k, v in want.kmers_map.map.items()}
-    own = build.map_kmers_to_tree(golden, msa)
+    own = build.map_kmers_to_tree(golden, msa, pairing="own")
     assert own.kmers_map.map != got.kmers_map.map
 
 
@@ -138,3 +138,23 @@ def test_toy_newick_of_the_reference(oracle):
     assert [c.name for c in star.children] == ["A", "B", "E", "F", "C", "D"] and all(c.is_leaf() for c in star.children)
     full = build.tree_from_newick(toy, "tree.nwk", 0.0).root
     assert [c.id for c in full.walk()] == list(range(11))        # phylotree numbers the nodes in pre-order
+
+
+def test_build_loop_line_rules(tmp_path):
+    """The MSA loop of the reference's builder (build_database/mod.rs:84-117), which is NOT the place_sequences reader:
+    every '>' line sends the new header with the sequence accumulated before it, leading sequence lines go to the first
+    header, the last sequence is never sent, an unknown header is an error (the reference panics, mod.rs:136-139)."""
+    import os
+    import pytest
+    from classeq2_b200 import build
+    text = "acgtn\n\n>t1\nAC-GT\nggNN\n>>t2>\r\n>t3\nTTTT\n"
+    assert build.build_loop_records(text) == [("t1", "ACGT"), ("t2", "ACGTGG"), ("t3", "")]
+    assert build.build_loop_records(">a\nAC\r\n>b") == [("a", ""), ("b", "AC")]
+    assert build.build_loop_records("") == []
+    nwk = "Colletotrichum_acutatum_gapdh-PhyML.nwk"
+    golden = os.path.join(HERE, "golden", nwk)
+    msa = tmp_path / "bad.fasta"
+    msa.write_text(">not_a_tip\nACGT\n")
+    with pytest.raises(ValueError, match="does not match any tree leaf"):
+        build.map_kmers_to_tree(golden, msa)                      # the default is the reference's pairing
+    assert build.map_kmers_to_tree(golden, msa, pairing="own").kmers_map.map == {}

@@ -236,7 +236,7 @@ def test_build_database_mirror_equals_oracle(tmp_path, oracle, col_queries, col_
     tips = col_queries[:171]
     msa = tmp_path / "tips.fasta"
     msa.write_text("".join(f">{h}\n{s}\n" for h, s in tips))
-    tree = build.map_kmers_to_tree(tmp_path / nwk, msa)
+    tree = build.map_kmers_to_tree(tmp_path / nwk, msa, pairing="own")
     want = oracle.tree_from_newick(open(os.path.join(GOLDEN, nwk)).read(), nwk, 70.0)
     oracle.map_kmers_to_tree(want, tips, 35, 4)
     assert (tree.id, tree.name, tree.min_branch_support) == (want.id, want.name, want.min_branch_support)

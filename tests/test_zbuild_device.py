@@ -100,8 +100,8 @@ def test_map_kmers_to_tree_on_the_device(tmp_path, col_queries):
     golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", nwk)
     msa = tmp_path / "tips.fasta"
     msa.write_text("".join(f">{h}\n{s}\n" for h, s in col_queries[:171]))
-    host = build.map_kmers_to_tree(golden, msa)
-    dev = build.map_kmers_to_tree(golden, msa, device=0)
+    host = build.map_kmers_to_tree(golden, msa, pairing="own")
+    dev = build.map_kmers_to_tree(golden, msa, device=0, pairing="own")
     assert host.to_obj() == dev.to_obj()
 
 
