@@ -337,6 +337,29 @@ def run_b200(args, rank, world, local_rank):
            "breakdown_ms_rank0": {k: round(tm[k], 3) for k in ("pack_ms", "h2d_ms", "kernel_ms", "d2h_ms", "total_ms")},
            "host_input": "ASCII bases + offsets in caller memory (what the reference's FASTA reader hands over)"}
 
+    # ---- ONE process, ONE handle, every visible GPU (cls_index_create_multi): the reference's callers are single
+    #      processes that fan out internally (ports/cli/src/cmds/place_sequences.rs:125-156); N = 1 arm only -----
+    e2e_multi = None
+    if world == 1 and torch.cuda.device_count() > 1 and not args.no_inprocess:
+        try:
+            n_dev = torch.cuda.device_count()
+            mix = cq.Index(sm.flat, device_mask=0)
+            out2 = cq.BatchResult(n_local)
+            for _ in range(2):
+                mix.place_batch_into(bases, offsets, out2, params)
+            t0 = time.perf_counter()
+            reps = max(1, args.steps // 2)
+            for _ in range(reps):
+                mix.place_batch_into(bases, offsets, out2, params)
+            dt = (time.perf_counter() - t0) / reps
+            same2 = all((getattr(out2, f) == getattr(res, f)).all() for f, _ in cq.engine.RESULT_DTYPES)
+            e2e_multi = {"value": n_local / dt, "unit": "reads/s", "n_devices": n_dev, "ms_per_step": dt * 1e3,
+                         "equals_single_device": bool(same2),
+                         "call": "one cls_place_batch on a cls_index_create_multi handle over every visible GPU, host ASCII in / host arrays out"}
+            mix.close()
+        except Exception as ex:  # noqa: BLE001
+            e2e_multi = {"error": repr(ex)[:300]}
+
     # ---- CPU baseline (rank 0, N = 1 only) + sampled parity ---------------------------------------------
     cpu = None
     parity = None
@@ -390,7 +413,7 @@ def run_b200(args, rank, world, local_rank):
                       "distinct_node_sets": int(info["n_distinct_sets"]),
                       "parallelism": f"queries sharded x{world}, index replicated, no collective"},
             "lookups_per_s": lookups_total / (ms_per_step / 1e3),
-            "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "e2e": e2e, "e2e_one_process_all_gpus": e2e_multi, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes_local, "launches_per_step": launches_per_step,
@@ -405,16 +428,35 @@ def run_b200(args, rank, world, local_rank):
             "setup_s": {"generate": round(gen_s, 1), "index_upload": round(upload_s, 2)},
             "wall_s_resident_region": round(wall_resident, 4),
         }
-        print(json.dumps(line), flush=True)
     rb.close()
     index.close()
+    # ---- N > 1 on the default workload: the hash-sharded index (config 5) rides along, so that the run that measures
+    #      the scaling of config 3 also measures the NVLink path (a nested object, not a second line) ------------------
+    c5 = None
+    if world > 1 and args.config == 3 and not args.no_config5:
+        torch.cuda.synchronize()
+        dist.barrier()
+        try:
+            a5 = argparse.Namespace(**vars(args))
+            a5.config, a5.reads, a5.steps, a5.warmup, a5.device_build = 5, args.reads5 * world, max(2, min(args.steps, 3)), 2, True
+            l5 = run_sharded(a5, rank, world, local_rank, embedded=True)
+            if rank == 0 and l5:
+                c5 = {k: l5[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "lookups_per_s", "e2e", "config", "nvlink",
+                                         "stage_ms_per_step_rank0", "parity", "roofline", "status_histogram")}
+        except Exception as ex:  # noqa: BLE001
+            c5 = {"error": repr(ex)[:300]}
+    if rank == 0:
+        line["config5"] = c5
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def run_sharded(args, rank, world, local_rank):
-    """Config 5: every rank owns one shard of the k-mer table and is home to its share of the reads."""
+def run_sharded(args, rank, world, local_rank, embedded=False):
+    """Config 5: every rank owns one shard of the k-mer table and is home to its share of the reads.
+    embedded=True: called from the default (config 3) run under torchrun, on its process group; returns the line
+    (rank 0) instead of printing it."""
     import torch
     import torch.distributed as dist
 
@@ -422,7 +464,7 @@ def run_sharded(args, rank, world, local_rank):
     from classeq2_b200.parallel import ShardedPlacer
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not embedded:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sm, bases, offsets, scaling, gen_s = make_workload(5, rank, world, args.reads, local_rank if args.device_build else None)
     n_local = len(offsets) - 1
@@ -492,6 +534,7 @@ def run_sharded(args, rank, world, local_rank):
     lookups_total = allred(float(lookups_local), dist.ReduceOp.SUM)
     value = reads_total / (ms_per_step / 1e3)
     res = [rb.fetch(st.cuda_stream) for rb in rbs]
+    line = None
 
     # end to end: host ASCII in, host arrays out, every sub-batch uploaded and fetched inside the timed region
     e2e_res = [sp.place(p, params) for p in parts]   # warm-up (first-use registration of the exchange buffers)
@@ -554,14 +597,16 @@ def run_sharded(args, rank, world, local_rank):
             "step_ms": [round(x, 3) for x in step_ms],
             "setup_s": {"generate": round(gen_s, 1), "index_upload": round(upload_s, 2)},
         }
-        print(json.dumps(line), flush=True)
+        if not embedded:
+            print(json.dumps(line), flush=True)
     for rb in rbs:
         rb.close()
     if world > 1:
         dist.barrier()
     sp.close()
-    if world > 1:
+    if world > 1 and not embedded:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def main():
@@ -575,6 +620,9 @@ def main():
     ap.add_argument("--reads", type=int, default=None, help="override the number of reads of the config")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="config 5: how routed k-mers cross NVLink")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
+    ap.add_argument("--no-config5", action="store_true", help="N > 1, default workload: skip the nested config-5 (hash-sharded index) measurement")
+    ap.add_argument("--reads5", type=int, default=1_250_000, help="reads per GPU of the nested config-5 measurement")
+    ap.add_argument("--no-inprocess", action="store_true", help="N = 1: skip the one-process-all-GPUs end-to-end number")
     ap.add_argument("--device-build", action="store_true",
                     help="set-up only: build the synthetic model's k-mer map on the GPU (cls_model_build_device) instead of the "
                          "host cores - the same arrays, outside every timed region")

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) build_hash_kernel(const uint8_t *__restri
     const uint32_t nb = nw + k - 1;
     const uint8_t *src = bases + seq_off[it.rank] + w0;
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
-        const uint8_t c = src[i];
+        const uint8_t c = src[i] & 0xDFu;   // upper-case, both strands (kmers_map.rs:410); letters were checked on the host
         f[i] = c;
         r[nb - 1 - i] = comp_byte(c);
     }
@@ -212,7 +212,7 @@ static int build_device(const cls_model_view *tree, uint64_t n_tips, const uint6
     Prep pr;
     {
         std::string err;
-        const int rc = prepare(tree, n_tips, tip_node, offsets, pr, err);
+        const int rc = prepare(tree, n_tips, tip_node, offsets, pr, err, bases);
         if (rc != CLS_OK) return set_last_error(rc, err);
     }
     const uint32_t k = tree->k_size, m = tree->m_size;

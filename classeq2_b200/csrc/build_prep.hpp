@@ -30,8 +30,10 @@ struct Prep {
 };
 
 // Returns 0 or a negative cls_error with `err` set.
+// `bases` (may be NULL: no check): sequences must hold A / C / G / T only, either case - the reference upper-cases both
+// strands (kmers_map.rs:410) and panics on anything else (:431-443).
 inline int prepare(const cls_model_view *tree, uint64_t n_tips, const uint64_t *tip_node, const uint64_t *offsets,
-                   Prep &p, std::string &err) {
+                   Prep &p, std::string &err, const uint8_t *bases = nullptr) {
     const uint64_t n_nodes = tree->n_nodes;
     const uint32_t k = tree->k_size;
     if (k == 0) { err = "k_size == 0"; return CLS_ERR_UNSUPPORTED; }
@@ -76,6 +78,11 @@ inline int prepare(const cls_model_view *tree, uint64_t n_tips, const uint64_t *
         if (tip_node[t] >= n_nodes) { err = "tip node out of range"; return CLS_ERR_INVALID_ARGUMENT; }
         if (offsets[t + 1] < offsets[t]) { err = "offsets decrease"; return CLS_ERR_INVALID_ARGUMENT; }
         if (offsets[t + 1] - offsets[t] > 0xFFFFFFFFull) { err = "a sequence is longer than 4 GiB"; return CLS_ERR_UNSUPPORTED; }
+        if (bases)
+            for (uint64_t i = offsets[t]; i < offsets[t + 1]; ++i) {
+                const uint8_t c = bases[i] & 0xDFu;
+                if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) { err = "a tip sequence holds a character other than A, C, G, T"; return CLS_ERR_INVALID_ARGUMENT; }
+            }
     }
     // rank the tips by (pre-order position of their node, tip index)
     p.rank_tip.resize(n_tips);

@@ -393,10 +393,16 @@ Workspace *acquire_ws(cls_index *ix) {
     for (auto &w : ix->pool)
         if (!w->in_use) { w->in_use = true; return w.get(); }
     auto w = std::make_unique<Workspace>();
-    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    bool ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &e : w->ev)
-        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        if (ok) ok = cudaEventCreate(&e) == cudaSuccess;
+    if (!ok) {   // nothing half-made is left behind
+        if (w->stream) cudaStreamDestroy(w->stream);
+        if (w->stream2) cudaStreamDestroy(w->stream2);
+        for (auto &e : w->ev) if (e) cudaEventDestroy(e);
+        return nullptr;
+    }
     w->in_use = true;
     ix->pool.push_back(std::move(w));
     return ix->pool.back().get();
@@ -407,10 +413,23 @@ void release_ws(cls_index *ix, Workspace *w) {
     w->in_use = false;
 }
 
+// Returns the workspace to the pool when the call ends.  If the call leaves before it has drained its own work
+// (`clean` still false: an error path after the first enqueue), copies and kernels may still be in flight on the
+// workspace's streams, using its pinned and device buffers: they are waited for first, so that the next caller that
+// takes the workspace cannot overwrite (or re-reserve, i.e. free) buffers the GPU is still working on.
 struct WsGuard {
     cls_index *ix;
     Workspace *w;
-    ~WsGuard() { if (w) release_ws(ix, w); }
+    bool clean = false;
+    ~WsGuard() {
+        if (!w) return;
+        if (!clean) {
+            if (w->stream) cudaStreamSynchronize(w->stream);
+            if (w->stream2) cudaStreamSynchronize(w->stream2);
+            if (w->stream3) cudaStreamSynchronize(w->stream3);
+        }
+        release_ws(ix, w);
+    }
 };
 
 }  // namespace
@@ -686,6 +705,7 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
     }
     tm.total_ms = now_ms() - t0;
     { std::lock_guard<std::mutex> lk(ix->mu); ix->timing = tm; }
+    guard.clean = true;   // every chunk has been drained: nothing of this call is in flight
     return CLS_OK;
 }
 

@@ -4,6 +4,7 @@
 // not part of the placement hot path ("next" row 4), but needed to manufacture
 // the synthetic models of BASELINE.json's configs without going through multi-GB YAML.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -15,6 +16,7 @@
 
 #include "../../include/classeq_b200.h"
 #include "built_model.hpp"
+#include "host_pool.hpp"
 #include "murmur3_host.hpp"
 
 namespace {
@@ -59,6 +61,22 @@ static int build_host(const cls_model_view *tree, uint64_t n_tips, const uint64_
     for (uint64_t t = 0; t < n_tips; ++t)
         if (tip_node[t] >= n_nodes) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "tip node out of range");
 
+    // ---- the inputs are not trusted: offsets must not decrease, sequences hold A/C/G/T only (either case: the
+    //      reference upper-cases both strands, kmers_map.rs:410, and panics on anything else, :431-443) ----------
+    for (uint64_t t = 0; t < n_tips; ++t)
+        if (offsets[t] > offsets[t + 1]) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "tip sequence offsets are not non-decreasing");
+    {
+        std::atomic<bool> bad{false};
+        cls::parallel_for(n_tips, 64, [&](uint64_t a, uint64_t b) {
+            for (uint64_t t = a; t < b; ++t)
+                for (uint64_t i = offsets[t]; i < offsets[t + 1]; ++i) {
+                    const uint8_t c = bases[i] & 0xDF;
+                    if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) { bad = true; return; }
+                }
+        });
+        if (bad) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "a tip sequence holds a character other than A, C, G, T");
+    }
+
     // ---- all (hash, bucket, tip) occurrences, both strands (kmers_map.rs:375-398) ---------------
     std::vector<uint64_t> occ_off(n_tips + 1, 0);
     for (uint64_t t = 0; t < n_tips; ++t) {
@@ -66,39 +84,33 @@ static int build_host(const cls_model_view *tree, uint64_t n_tips, const uint64_
         occ_off[t + 1] = occ_off[t] + (len >= k ? 2 * (len - k + 1) : 0);
     }
     std::vector<Occ> occ(occ_off[n_tips]);
-    {
-        unsigned hc = std::thread::hardware_concurrency();
-        const int nt = (int)std::max(1u, std::min(hc ? hc : 4u, 32u));
-        std::vector<std::thread> th;
-        for (int w = 0; w < nt; ++w)
-            th.emplace_back([&, w] {
-                std::vector<uint8_t> rc;
-                for (uint64_t t = w; t < n_tips; t += nt) {
-                    const uint8_t *s = bases + offsets[t];
-                    const uint64_t len = offsets[t + 1] - offsets[t];
-                    if (len < k) continue;
-                    rc.resize(len);
-                    for (uint64_t i = 0; i < len; ++i) {
-                        const uint8_t c = s[len - 1 - i] & 0xDF;
-                        rc[i] = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : 'C';
-                    }
-                    Occ *o = occ.data() + occ_off[t];
-                    const uint64_t W = len - k + 1;
-                    const uint32_t mm = std::min(m, k);
-                    for (int strand = 0; strand < 2; ++strand) {
-                        const uint8_t *d = strand ? rc.data() : s;
-                        for (uint64_t i = 0; i < W; ++i) {
-                            o->hash = cls::murmur3_x64_128_h1(d + i, k, 0);
-                            // kmers_map.rs:131-137: key 0 when m_size == 0, else h1(first m chars)
-                            o->bucket = m == 0 ? 0 : cls::murmur3_x64_128_h1(d + i, mm, 0);
-                            o->tip = (uint32_t)t;
-                            ++o;
-                        }
-                    }
+    cls::parallel_for(n_tips, 1, [&](uint64_t t0, uint64_t t1) {   // the host pool carries exceptions back to this thread
+        std::vector<uint8_t> fw, rc;
+        for (uint64_t t = t0; t < t1; ++t) {
+            const uint8_t *s = bases + offsets[t];
+            const uint64_t len = offsets[t + 1] - offsets[t];
+            if (len < k) continue;
+            fw.resize(len); rc.resize(len);
+            for (uint64_t i = 0; i < len; ++i) {
+                const uint8_t c = s[i] & 0xDF;   // upper-case, both strands
+                fw[i] = c;
+                rc[len - 1 - i] = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : 'C';
+            }
+            Occ *o = occ.data() + occ_off[t];
+            const uint64_t W = len - k + 1;
+            const uint32_t mm = std::min(m, k);
+            for (int strand = 0; strand < 2; ++strand) {
+                const uint8_t *d = strand ? rc.data() : fw.data();
+                for (uint64_t i = 0; i < W; ++i) {
+                    o->hash = cls::murmur3_x64_128_h1(d + i, k, 0);
+                    // kmers_map.rs:131-137: key 0 when m_size == 0, else h1(first m chars)
+                    o->bucket = m == 0 ? 0 : cls::murmur3_x64_128_h1(d + i, mm, 0);
+                    o->tip = (uint32_t)t;
+                    ++o;
                 }
-            });
-        for (auto &x : th) x.join();
-    }
+            }
+        }
+    });
     std::sort(occ.begin(), occ.end(), [](const Occ &a, const Occ &b) {
         if (a.hash != b.hash) return a.hash < b.hash;
         if (a.bucket != b.bucket) return a.bucket < b.bucket;

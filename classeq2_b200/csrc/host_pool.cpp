@@ -4,6 +4,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdlib>
+#include <exception>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -41,12 +42,22 @@ struct Job {
     const std::function<void(uint64_t, uint64_t)> &fn;
     const uint64_t n, step;
     std::atomic<uint64_t> next{0};
+    std::mutex err_mu;
+    std::exception_ptr err;   // the first exception thrown by fn on any thread; rethrown by Pool::run on the caller's
     Job(const std::function<void(uint64_t, uint64_t)> &f, uint64_t n_, uint64_t step_) : fn(f), n(n_), step(step_) {}
     void work() {
         for (;;) {
             const uint64_t a = next.fetch_add(step);
             if (a >= n) break;
-            fn(a, std::min(n, a + step));
+            try {
+                fn(a, std::min(n, a + step));
+            } catch (...) {
+                {
+                    std::lock_guard<std::mutex> lk(err_mu);
+                    if (!err) err = std::current_exception();
+                }
+                next.store(n);   // nobody starts another range
+            }
         }
     }
 };
@@ -95,10 +106,13 @@ struct Pool {
             ++generation;
         }
         cv_work.notify_all();
-        job.work();
-        std::unique_lock<std::mutex> lk(mu);
-        cur = nullptr;  // a worker that wakes up from here on finds no job; those inside are counted in `active`
-        cv_done.wait(lk, [&] { return active == 0; });
+        job.work();   // never throws: exceptions of fn are parked in the job
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cur = nullptr;  // a worker that wakes up from here on finds no job; those inside are counted in `active`
+            cv_done.wait(lk, [&] { return active == 0; });
+        }
+        if (job.err) std::rethrow_exception(job.err);   // the job (on this stack) is no longer referenced by any worker
     }
 };
 

@@ -1144,6 +1144,161 @@ __device__ __forceinline__ void descend_from_pairs(const DeviceIndex &ix, const 
     finish_read_reg<SLOTS>(ix, pp, cnt, excl, off, wt, n_matched, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// Several reads per warp: a read with at most G node sets (G = 8 or 16 lanes of a warp: a quarter or a half) leaves most
+// lanes of finish_read_reg idle - 62 % of 150-base reads have at most 16 sets.  finish_group runs 32 / G reads side by
+// side, one per group of G consecutive lanes: what is warp-uniform there is group-uniform here (held by every lane of the
+// group), reductions are butterflies inside the group, and every group carries its own status through a loop that ends
+// when all groups are done.  Only two-way levels are handled (the three vote sums travel in one word, 10 bits each, so the
+// caller keeps reads of 1 024 hits or more away); a level with a larger fan-out hands the read back (returns true) and
+// the caller runs it through finish_read_reg.  Same algorithm, same outcomes (place_sequence.rs:279-601).
+// ------------------------------------------------------------------------------------------
+template <int G> __device__ __forceinline__ uint32_t group_sum(uint32_t v) {
+#pragma unroll
+    for (int d = G / 2; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+    return v;
+}
+template <int G> __device__ __forceinline__ uint32_t group_min(uint32_t v) {
+#pragma unroll
+    for (int d = G / 2; d; d >>= 1) v = min(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
+template <int G> __device__ __forceinline__ uint32_t group_max(uint32_t v) {
+#pragma unroll
+    for (int d = G / 2; d; d >>= 1) v = max(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
+
+constexpr uint32_t kGroupIdle = 0xFFFFFFFEu, kGroupRedo = 0xFFFFFFFDu;
+
+// `have`: this lane's group holds a read; `set_off` / `weight`: the lane's pair of it (weight 0 = none); `n_matched`, `out`:
+// group-uniform.  Called by all 32 lanes.
+template <int G>
+__device__ __forceinline__ bool finish_group(const DeviceIndex &ix, const PlaceParams &pp, bool have, uint32_t set_off, uint32_t weight,
+                                             uint32_t n_matched, ResultRec *__restrict__ out) {
+    const uint32_t *__restrict__ terms = ix.terms;
+    const bool ri = pp.remove_intersection != 0;
+    // ---- restriction to the sets that contain tree.root.id (M_r, place_sequence.rs:156-166)
+    uint32_t lo = 0, hi = 0, first = 0xFFFFFFFFu, last = 0, w = 0;
+    if (have && weight) {
+        const uint32_t hdr = __ldg(terms + set_off);
+        if (hdr & kTermHasRoot) {
+            last = __ldg(terms + set_off + 1); first = __ldg(terms + set_off + 2);
+            w = weight;
+            lo = set_off + 2; hi = lo + (hdr & ~kTermHasRoot);
+        }
+    }
+    const uint32_t n_root = group_sum<G>(w);
+    // ---- gates (place_sequence.rs:120-139, :156-166, :199-206, :231-254)
+    uint32_t status = kUndecided, node_q = 0;
+    bool has_node = false;
+    int32_t one = 0, rest = 0;
+    if (!have) status = kGroupIdle;
+    else if (n_matched == 0) status = CLS_DEV_UNCL_NO_MATCH;
+    else if (n_root == 0) status = CLS_DEV_UNCL_NO_ROOT;
+    else if (ix.root_children_none) status = CLS_DEV_ERR_ROOT_NO_CHILDREN;
+    else {
+        const double x = (double)n_matched * pp.min_match_coverage;  // f64::round, half away from zero
+        double expected = floor(x);
+        if (x - expected >= 0.5) expected += 1.0;
+        if ((double)n_root < expected) status = CLS_DEV_UNCL_COVERAGE;
+    }
+    // ---- descent
+    uint32_t p = 0, depth_p = 0;
+    int32_t iteration = 0;  // never beyond max_iterations + 1
+    const int32_t max_iter = pp.max_iterations;
+    QInfo ip = ld_qinfo(ix.qinfo, 0);
+    while (__any_sync(kFull, status == kUndecided)) {
+        const bool act = status == kUndecided;
+        // pooled extremes of the live terminals -> every level down to their LCA is unanimous
+        const uint32_t umin = group_min<G>((act && w) ? first : 0xFFFFFFFFu), vmax = group_max<G>((act && w) ? last : 0u);
+        const bool sane = act && umin <= vmax;   // groups that are done (or hold nothing) look up (root, root)
+        const uint64_t dn = lca_depth_node(ix, sane ? umin : 0u, sane ? vmax : 0u);
+        const uint32_t A = (uint32_t)dn, depth_a = (uint32_t)(dn >> 32);
+        bool jump = act && depth_a > depth_p;
+        if (jump) {
+            const uint32_t d = depth_a - depth_p;
+            if ((int64_t)iteration + (int64_t)d > (int64_t)max_iter) { iteration = (max_iter > 0 ? max_iter : 0) + 1; status = CLS_DEV_ERR_MAX_ITERATIONS; jump = false; }
+            else { iteration += (int32_t)d; ip = ld_qinfo(ix.qinfo, A); p = A; depth_p = depth_a; }
+        }
+        const bool ident = jump && ip.child_count == 0;  // update_introspection_node.rs:32-87
+        if (__any_sync(kFull, ident)) {
+            const uint32_t ws = group_sum<G>(w);
+            if (ident) { status = CLS_DEV_IDENTITY_FOUND; node_q = A; has_node = true; one = (int32_t)ws; rest = 0; }
+        }
+        // ---- evaluate the children of p
+        bool ev = status == kUndecided;
+        if (ev) {
+            iteration++;
+            if (iteration > max_iter) { status = CLS_DEV_ERR_MAX_ITERATIONS; ev = false; }
+        }
+        const uint32_t m = ip.child_count, p_end = ip.q_end;
+        if (ev && m > 2) { status = kGroupRedo; ev = false; }
+        if (ev && w && first == p) {  // the set ends at p itself for some tip: that is no vote for any child
+            ++lo;
+            first = lo < hi ? __ldg(terms + lo) : 0xFFFFFFFFu;
+        }
+        const bool has = ev && w && lo < hi;
+        // children intervals tile [p+1, p_end): c1 = [p+1, bnd), c2 = [bnd, p_end)
+        QInfo i1{p_end, 0, 0, 0};
+        if (ev && m) i1 = ld_qinfo(ix.qinfo, p + 1);
+        const uint32_t bnd = i1.q_end;
+        const bool in1 = has && first < bnd, in2 = has && last >= bnd;
+        const uint32_t tot = group_sum<G>((in1 ? w : 0u) | ((in2 ? w : 0u) << 10) | (((in1 && in2) ? w : 0u) << 20));
+        const uint32_t c1 = tot & 1023u, c2 = (tot >> 10) & 1023u, both = tot >> 20;
+        const uint32_t U = c1 + c2 - both, x1 = c1 - both, x2 = c2 - both;
+        const uint32_t ncand = (c1 > 0) + (c2 > 0);
+        const int32_t one1 = (int32_t)((ri && ncand > 1) ? x1 : c1), rest1 = ncand > 1 ? (int32_t)(ri ? U - c1 : U - x1) : 0;
+        const int32_t one2 = (int32_t)((ri && ncand > 1) ? x2 : c2), rest2 = ncand > 1 ? (int32_t)(ri ? U - c2 : U - x2) : 0;
+        const bool pr1 = c1 > 0 && one1 > rest1, pr2 = c2 > 0 && one2 > rest2;
+        const uint32_t nprop = (uint32_t)pr1 + (uint32_t)pr2;
+        bool pick2 = pr2 && !pr1;
+        uint32_t n_best = nprop ? 1u : 0u;
+        if (pr1 && pr2) {  // provably unreachable; kept for fidelity (:519-599)
+            const int32_t d1 = one1 - rest1, d2 = one2 - rest2;
+            if (d1 == d2) n_best = 2; else pick2 = d2 > d1;
+        }
+        const uint32_t win_q = pick2 ? bnd : p + 1;
+        const int32_t win_one = pick2 ? one2 : one1, win_rest = pick2 ? rest2 : rest1;
+        QInfo iw = i1;
+        if (ev && pick2 && nprop) iw = ld_qinfo(ix.qinfo, bnd);
+        if (ev) {
+            if (nprop == 0) {
+                if (iteration == 1) status = CLS_DEV_UNCL_NO_INTROSPECTION;
+                else { status = CLS_DEV_MAX_RESOLUTION; node_q = p; has_node = true; }
+            } else if (n_best != 1) {
+                status = CLS_DEV_INCONCLUSIVE; node_q = p; has_node = true;
+            } else if (iw.child_count == 0) {  // update_introspection_node.rs:32-87
+                status = CLS_DEV_IDENTITY_FOUND; node_q = win_q; has_node = true; one = win_one; rest = win_rest;
+            } else {
+                p = win_q; ip = iw; depth_p++;
+                const uint32_t win_end = iw.q_end;
+                // every live set keeps its terminals inside the winner's interval (or drops out)
+                bool live = has && last >= win_q && first < win_end;
+                if (live && first < win_q) {
+                    lo = lower_bound_terms(terms, lo + 1, hi, win_q);
+                    first = __ldg(terms + lo);  // lo < hi because last >= win_q
+                    live = first < win_end;
+                }
+                if (live && last >= win_end) {
+                    hi = lower_bound_terms(terms, lo + 1, hi - 1, win_end);  // terms[lo] < win_end
+                    last = __ldg(terms + hi - 1);
+                }
+                if (!live) w = 0;
+            }
+        }
+    }
+    if (have && status != kGroupRedo && (threadIdx.x & (G - 1)) == 0) {
+        ResultRec res;
+        res.node_id = has_node ? ix.q_node_id[node_q] : 0;
+        res.one = one; res.rest = rest;
+        res.n_matched = n_matched; res.n_root_matched = n_root; res.iterations = (uint32_t)iteration;
+        res.status = status;
+        *out = res;
+    }
+    return status == kGroupRedo;
+}
+
 // (asking ptxas for 8 or 4 resident CTAs per SM changes nothing: 5.08 / 5.07 against 5.07 ms, profiles/r2a)
 #define CLS_DESCEND_BOUNDS __launch_bounds__(256)
 template <int MAXSLOTS>
@@ -1176,6 +1331,83 @@ namespace {
 #include "scan2_kernels.cuh"
 #include "giant_kernels.cuh"
 }  // namespace
+
+// The descent kernel of the short-read path (at most kPairCap pairs per read).  A warp takes 16 consecutive reads from the
+// global counter, sorts them into size classes by their number of pairs and runs four reads of at most 8 pairs, or two
+// of at most 16, side by side (finish_group); the others - and whatever finish_group hands back - go one read per warp.
+#ifndef CLS_DESCEND_GROUPS
+#define CLS_DESCEND_GROUPS 1
+#endif
+template <int G>
+__device__ __forceinline__ uint32_t run_groups(const DeviceIndex &ix, const PlaceParams &pp, const ScanOut &so, uint32_t first_read,
+                                               ResultRec *__restrict__ results, uint32_t mask, uint32_t my_r, uint2 my_me) {
+    constexpr uint32_t kGroups = 32 / G;
+    const uint32_t lane = lane_id(), grp = lane / G, sub = lane & (G - 1);
+    uint32_t redo = 0;
+    while (mask) {
+        // the next (up to) kGroups reads of the class: group g takes the g-th lowest set bit
+        uint32_t mine = 0xFFFFFFFFu, picked = 0, rest = mask;
+#pragma unroll
+        for (uint32_t g = 0; g < kGroups; ++g) {
+            if (rest) {
+                const uint32_t j = (uint32_t)__ffs(rest) - 1u;
+                rest &= rest - 1u;
+                picked |= 1u << j;
+                if (g == grp) mine = j;
+            }
+        }
+        mask = rest;
+        const bool have = mine != 0xFFFFFFFFu;
+        const uint32_t src = have ? mine : 0u;
+        const uint32_t r = __shfl_sync(kFull, my_r, src), nm = __shfl_sync(kFull, my_me.x, src), D = __shfl_sync(kFull, my_me.y, src);
+        uint2 pr = make_uint2(0u, 0u);
+        if (have && sub < D) pr = so.pairs[(size_t)r * so.cap + sub];
+        const bool again = finish_group<G>(ix, pp, have, pr.x, pr.y, nm, results + first_read + r);
+        const uint32_t am = __ballot_sync(kFull, again && sub == 0);   // bit g * G: group g hands its read back
+#pragma unroll
+        for (uint32_t g = 0; g < kGroups; ++g)
+            if ((am >> (g * G)) & 1u) redo |= 1u << __shfl_sync(kFull, mine, g * G);
+        (void)picked;
+    }
+    return redo;
+}
+
+__global__ void __launch_bounds__(256) descend16_kernel(DeviceIndex ix, PlaceParams pp, ScanOut so, uint32_t first_read,
+                                                        uint32_t n_reads, ResultRec *__restrict__ results, uint32_t fan_cap) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t *cnt = smem + (size_t)warp * 2 * fan_cap, *excl = cnt + fan_cap;
+    for (uint32_t o = lane; o < fan_cap; o += 32) { cnt[o] = 0; excl[o] = 0; }
+    __syncwarp();
+#pragma unroll 1
+    for (;;) {
+        uint32_t b0 = 0;
+        if (lane == 0) b0 = atomicAdd(so.counters + 1, 16u);
+        const uint32_t base = __shfl_sync(kFull, b0, 0);
+        if (base >= n_reads) break;
+        const uint32_t my_r = base + (lane & 15u);
+        uint2 my_me = make_uint2(0u, kDone);
+        if (lane < 16 && my_r < n_reads) my_me = so.meta[my_r];
+        const bool todo = lane < 16 && my_me.y != kDone;
+        const bool small_ok = todo && my_me.x < 1024u;
+        uint32_t m8 = __ballot_sync(kFull, small_ok && my_me.y <= 8u);
+        uint32_t m16 = __ballot_sync(kFull, small_ok && my_me.y > 8u && my_me.y <= 16u);
+        uint32_t big = __ballot_sync(kFull, todo) & ~(m8 | m16);
+        // a lone read of a class is cheaper in the next class up than in a mostly empty group round
+        if (__popc(m8) == 1) { m16 |= m8; m8 = 0; }
+        if (__popc(m16) == 1) { big |= m16; m16 = 0; }
+        big |= run_groups<8>(ix, pp, so, first_read, results, m8, my_r, my_me);
+        big |= run_groups<16>(ix, pp, so, first_read, results, m16, my_r, my_me);
+        while (big) {
+            const uint32_t j = (uint32_t)__ffs(big) - 1u;
+            big &= big - 1u;
+            const uint32_t r = __shfl_sync(kFull, my_r, j), nm = __shfl_sync(kFull, my_me.x, j), D = __shfl_sync(kFull, my_me.y, j);
+            const uint2 *pr = so.pairs + (size_t)r * so.cap;
+            if (D <= 32) descend_from_pairs<1>(ix, pp, cnt, excl, pr, D, nm, results + first_read + r);
+            else descend_from_pairs<2>(ix, pp, cnt, excl, pr, D, nm, results + first_read + r);
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // Host launchers
@@ -1238,7 +1470,15 @@ static cudaError_t launch_descend(const DeviceIndex &ix, const PlaceParams &pp, 
     uint32_t dgrid = (uint32_t)(sm_count * occ);
     const uint32_t need = (n_reads + 7) / 8;
     if (dgrid > need) dgrid = need;
-    descend_kernel<MAXSLOTS><<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
+    static const bool groups = [] { const char *v = getenv("CLS_DESCEND_GROUPS"); return v ? atoi(v) != 0 : CLS_DESCEND_GROUPS != 0; }();
+    if (MAXSLOTS == 2 && groups) {
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, descend16_kernel, 256, dsmem)) != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        dgrid = std::min<uint32_t>((uint32_t)(sm_count * occ), (n_reads + 127) / 128);
+        descend16_kernel<<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
+    } else {
+        descend_kernel<MAXSLOTS><<<dgrid, 256, dsmem, stream>>>(ix, pp, so, first_read, n_reads, results, fan_cap);
+    }
     return cudaGetLastError();
 }
 
@@ -1373,20 +1613,20 @@ static cudaError_t launch_scan_old(const DeviceIndex &ix, const PlaceParams &pp,
     return cudaSuccess;
 }
 
-template <int PPS>
+template <int PPS, int MINB>
 static cudaError_t launch_scan2(const DeviceIndex &ix, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read,
                                 uint32_t n_reads, const ScanOut &so, int sm_count, cudaStream_t stream) {
     const size_t smem = (size_t)Scan2Layout<PPS>::kBytes * 8;
-    cudaError_t e = cudaFuncSetAttribute(scan2_kernel<PPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(scan2_kernel<PPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan2_kernel<PPS>, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan2_kernel<PPS, MINB>, 256, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)(sm_count * occ);
-    const uint32_t need = (n_reads + 8 * kReadBlock - 1) / (8 * kReadBlock);
+    const uint32_t need = (n_reads + 8 * kScanBlock - 1) / (8 * kScanBlock);
     if (grid > need) grid = need;
-    scan2_kernel<PPS><<<grid, 256, smem, stream>>>(ix, packed, reads, first_read, n_reads, so);
+    scan2_kernel<PPS, MINB><<<grid, 256, smem, stream>>>(ix, packed, reads, first_read, n_reads, so);
     return cudaGetLastError();
 }
 
@@ -1403,8 +1643,13 @@ static cudaError_t launch_scan_t(const DeviceIndex &ix, const PlaceParams &pp, c
     const ScanOut so = carve_scratch(scratch, n_reads, kPairCap);
     cudaError_t e = cudaMemsetAsync(so.counters, 0, 64, stream);
     if (e != cudaSuccess) return e;
-    e = g.max_len <= Scan2Layout<4>::kMaxLen ? launch_scan2<4>(ix, packed, reads, first_read, n_reads, so, sm_count, stream)
-                                             : launch_scan2<8>(ix, packed, reads, first_read, n_reads, so, sm_count, stream);
+    // a table well inside the 126 MB L2 wants registers, one that lives in HBM wants warps (scan2_kernels.cuh)
+    static const int force_minb = [] { const char *v = getenv("CLS_SCAN2_MINB"); return v ? atoi(v) : 0; }();
+    const bool l2_resident = (ix.bucket_mask + 1) * sizeof(Slot) * 2 <= ((size_t)96 << 20);
+    const bool minb4 = force_minb ? force_minb == 4 : l2_resident;
+    if (g.max_len > Scan2Layout<4>::kMaxLen) e = launch_scan2<8, 4>(ix, packed, reads, first_read, n_reads, so, sm_count, stream);
+    else if (minb4) e = launch_scan2<4, 4>(ix, packed, reads, first_read, n_reads, so, sm_count, stream);
+    else e = launch_scan2<4, 5>(ix, packed, reads, first_read, n_reads, so, sm_count, stream);
     if (e != cudaSuccess) return e;
     if (n_launches) ++*n_launches;
     if ((e = launch_descend<2>(ix, pp, so, first_read, n_reads, results, g.fan_cap, sm_count, stream)) != cudaSuccess) return e;

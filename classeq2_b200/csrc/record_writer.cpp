@@ -19,6 +19,7 @@
 #include <stdexcept>
 #include <cmath>
 #include <cstdlib>
+#include <cerrno>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -573,6 +574,31 @@ struct cls_fasta_text {
     std::vector<uint8_t> bases;
 };
 
+// str::from_utf8 on one line (BufRead::lines yields Err for a line that is not valid UTF-8: the reader then returns, and
+// the caller places what was sent so far, file_or_stdin.rs:85)
+static bool valid_utf8(const uint8_t *p, uint64_t n) {
+    uint64_t i = 0;
+    while (i < n) {
+        const uint8_t c = p[i];
+        if (c < 0x80) { ++i; continue; }
+        uint32_t need, lo = 0x80, hi = 0xBF;
+        if (c >= 0xC2 && c <= 0xDF) need = 1;
+        else if (c == 0xE0) { need = 2; lo = 0xA0; }
+        else if ((c >= 0xE1 && c <= 0xEC) || c == 0xEE || c == 0xEF) need = 2;
+        else if (c == 0xED) { need = 2; hi = 0x9F; }
+        else if (c == 0xF0) { need = 3; lo = 0x90; }
+        else if (c >= 0xF1 && c <= 0xF3) need = 3;
+        else if (c == 0xF4) { need = 3; hi = 0x8F; }
+        else return false;
+        if (i + need >= n) return false;   // truncated sequence
+        if (p[i + 1] < lo || p[i + 1] > hi) return false;
+        for (uint32_t j = 2; j <= need; ++j)
+            if ((p[i + j] & 0xC0) != 0x80) return false;
+        i += need + 1;
+    }
+    return true;
+}
+
 extern "C" int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_text **out, cls_fasta_host_records *rec) {
     using cls::set_last_error;
     if (!out || !rec || (n_bytes && !text)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -594,6 +620,13 @@ extern "C" int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_t
             const uint64_t next = nl ? b + 1 : n_bytes;
             if (nl && b > a && text[b - 1] == '\r') --b;            // BufRead::lines: "\r\n" is a terminator, a lone "\r" is not
             if (b > a) {                                            // empty lines are skipped (:87-89)
+                bool ascii = true;
+                for (uint64_t i = a; i < b && ascii; ++i) ascii = text[i] < 0x80;
+                if (!ascii && !valid_utf8(text + a, b - a)) {       // `line?`: the reader returns here, the pending record is not sent
+                    stop = true;
+                    kept = rec_start;
+                    break;
+                }
                 if (text[a] == '>') {
                     if (have_header) {                              // send the previous record, even without sequence (:103-108)
                         ft->header_begin.push_back(hb); ft->header_end.push_back(he);
@@ -711,13 +744,16 @@ extern "C" int cls_sequences_open(const char *query_path, const char *out_file, 
                 msg += " when overwrite option is `false`.";
                 return set_last_error(CLS_ERR_INVALID_ARGUMENT, msg);
             }
-            remove(s->out_path.c_str());
+            if (remove(s->out_path.c_str()) != 0)                                        // :103-110
+                return set_last_error(CLS_ERR_INVALID_ARGUMENT, std::string("Could not remove file given ") + strerror(errno));
         }
         const bool use_stdin = !query_path || strcmp(query_path, "-") == 0;
         FILE *f = use_stdin ? stdin : fopen(query_path, "rb");
-        if (!f) return set_last_error(CLS_ERR_INVALID_ARGUMENT, std::string("cannot open ") + query_path);
-        struct Close { FILE *f; bool own; ~Close() { if (own) fclose(f); } } closer{f, !use_stdin};   // also when an allocation throws
-        if (!read_whole(f, s->text)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "error while reading the query sequences");
+        // a query that cannot be opened or read is NOT an error of the use-case: the reference drops the reader's
+        // Result (`let _ = query_sequence.sequence_content_by_channel(sender)`, :119), creates both files and
+        // returns Ok with nothing placed
+        struct Close { FILE *f; bool own; ~Close() { if (f && own) fclose(f); } } closer{f, !use_stdin};   // also when an allocation throws
+        if (!f || !read_whole(f, s->text)) s->text.clear();
         const int rc = cls_fasta_read(reinterpret_cast<const uint8_t *>(s->text.data()), s->text.size(), &s->records, &s->rec);
         if (rc != CLS_OK) return rc;
         s->header_off.assign(s->rec.n_records + 1, 0);

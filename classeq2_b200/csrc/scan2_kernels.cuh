@@ -167,12 +167,9 @@ __device__ __forceinline__ void decode_read16(const uint32_t *__restrict__ packe
     sts_u32(wb + (lane >= 16 ? Ly::oPkR : Ly::oPkF) + 4u * t, v);
 }
 
-#ifndef CLS_SCAN2_MINB
-#define CLS_SCAN2_MINB 5
-#endif
 // A/B switches of this file (tools/build_variants.sh); the defaults are what measured best
 #ifndef CLS_S2_DIRECT
-#define CLS_S2_DIRECT 1       // lists of up to 32 entries are handed over unmerged
+#define CLS_S2_DIRECT 1       // lists of up to 32 entries are merged in registers (one match.any), not through the table
 #endif
 #ifndef CLS_S2_FASTDECODE
 #define CLS_S2_FASTDECODE 1   // decode_read16 for the PPS = 4 geometry
@@ -328,8 +325,11 @@ __device__ __forceinline__ void scan2_step(Scan2Ctx &cx, const DeviceIndex &ix, 
     }
 }
 
-template <int PPS>
-__global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
+// MINB = resident CTAs per SM ptxas is asked for: 5 (48 registers, 40 warps per SM) hides the HBM latency of a table that
+// does not fit L2 (config 3: 5.14 against 5.36 ms per 1 M reads); 4 (64 registers, no re-materialised constants) is the
+// faster one when the table is L2-resident (config 2: 4.14 against 4.24 ms).  The launcher picks by table size.
+template <int PPS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     scan2_kernel(DeviceIndex ix, const uint32_t *__restrict__ packed, const ReadDesc *__restrict__ reads, uint32_t first_read,
                  uint32_t n_reads, ScanOut so) {
     using Ly = Scan2Layout<PPS>;
@@ -408,12 +408,22 @@ __global__ void __launch_bounds__(256, PPS == 4 ? CLS_SCAN2_MINB : 4)
         uint32_t D = 0, n_matched = 0;
         uint2 *row = so.pairs + (size_t)r * so.cap;
         if (CLS_S2_DIRECT && cx.n_list <= 32) {
-            // the descent is linear in the weights: a node set listed twice votes exactly like its summed entry, and up to
-            // 32 pairs cost the descent kernel the same (one pair per lane) - hand the list over as it is
+            // one entry per lane: entries of the same node-set record are summed into the lowest lane that holds it (the
+            // descent kernel runs several reads side by side when they have few node sets, so fewer pairs pay)
+            const bool valid = lane < cx.n_list;
             uint2 e = make_uint2(0u, 0u);
-            if (lane < cx.n_list) { e = lds_v2(cx.wb + Ly::oList + 8u * lane); row[lane] = e; }
-            n_matched = __reduce_add_sync(kFull, e.y);   // every distinct hit is in exactly one count
-            D = cx.n_list;
+            if (valid) e = lds_v2(cx.wb + Ly::oList + 8u * lane);
+            const uint32_t peers = __match_any_sync(kFull, valid ? e.x : (0x80000000u | lane));
+            const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+            const bool is_lead = valid && leader == lane;
+            if (valid && !is_lead) reds_add(cx.wb + Ly::oList + 8u * leader + 4u, e.y);
+            __syncwarp();
+            uint32_t wsum = 0;
+            if (is_lead) wsum = lds_u32(cx.wb + Ly::oList + 8u * lane + 4u);
+            const uint32_t lm = __ballot_sync(kFull, is_lead);
+            if (is_lead) row[__popc(lm & cx.lt)] = make_uint2(e.x, wsum);
+            n_matched = __reduce_add_sync(kFull, wsum);   // every distinct hit is in exactly one count
+            D = (uint32_t)__popc(lm);
         } else if (!overflow) {
             sts_v4(cx.wb + Ly::oMergeKey + 16u * lane, kEmpty);
             sts_v4(cx.wb + Ly::oMergeCnt + 16u * lane, 0u);

@@ -34,9 +34,10 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session", autouse=True)
 def _built_library():
-    """The in-tree shared objects are build artefacts (git-ignored): build them if missing."""
+    """The in-tree shared objects are build artefacts (git-ignored): `make` them (incremental - a library older than
+    its sources is rebuilt, never tested)."""
     import __graft_entry__ as g
-    g.build(only_if_missing=True)
+    g.build()
 
 
 @pytest.fixture(scope="session")

@@ -23,7 +23,7 @@ extern "C" int bsh_model_build(const cls_model_view *tree, uint64_t n_tips, cons
     *out = nullptr;
     Prep pr;
     std::string err;
-    const int rc = prepare(tree, n_tips, tip_node, offsets, pr, err);
+    const int rc = prepare(tree, n_tips, tip_node, offsets, pr, err, bases);
     if (rc != CLS_OK) return rc;
     const uint32_t k = tree->k_size, m = tree->m_size;
     const uint64_t N = pr.occ_off[n_tips];
@@ -41,7 +41,7 @@ extern "C" int bsh_model_build(const cls_model_view *tree, uint64_t n_tips, cons
         const uint32_t nw = (uint32_t)std::min<uint64_t>(W - w0, kTileWindows), nb = nw + k - 1;
         const uint8_t *src = bases + pr.seq_off[it.rank] + w0;
         f.assign(nb, 0); r.assign(nb, 0);
-        for (uint32_t i = 0; i < nb; ++i) { f[i] = src[i]; r[nb - 1 - i] = comp_byte(src[i]); }
+        for (uint32_t i = 0; i < nb; ++i) { f[i] = src[i] & 0xDFu; r[nb - 1 - i] = comp_byte(src[i]); }
         const uint32_t mm = std::min(m, k);
         for (uint32_t x = 0; x < 2 * nw; ++x) {
             const TileItem ti = tile_item(x, nw, W, w0);

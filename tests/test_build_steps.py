@@ -27,7 +27,8 @@ def walk():
         h = C.c_void_p()
         rc = lib.bsh_model_build(C.byref(tflat.view), len(tip_node), tip_node.ctypes.data_as(_lib.u64p),
                                  bases.ctypes.data_as(_lib.u8p), offsets.ctypes.data_as(_lib.u64p), C.byref(h))
-        assert rc == 0, rc
+        if rc != 0:
+            raise _lib.ClsError(rc, "bsh_model_build")
         bm = BuiltModel.__new__(BuiltModel)       # read the handle with the product's own view call
         bm.tree_only, bm._h, bm.view = tflat, h, _lib.ModelView()
         _lib.check(_lib.lib.cls_built_model_view(h, C.byref(tflat.view), C.byref(bm.view)))
@@ -51,8 +52,31 @@ def test_walk_equals_host_builder_random(walk, k, m):
     for it in range(6):
         case = random_build_case(rng, n_internal=int(rng.integers(0, 25)), k=k, m=m, max_len=int(rng.integers(k, 260)),
                                  dup_tips=it % 3, internal_tips=it % 2,
-                                 letters=b"ACGT" if it % 2 == 0 else b"ACGTacgtN")
+                                 letters=b"ACGT" if it % 2 == 0 else b"ACGTacgt")
         assert_built_equal(_host(*case), walk(*case))
+        if it % 2:   # lower-case letters are the same k-mers (both strands are upper-cased, kmers_map.rs:410)
+            tflat, tip_node, bases, offsets = case
+            up = np.frombuffer(bytes(bases).upper(), np.uint8).copy()
+            assert_built_equal(_host(tflat, tip_node, up, offsets), _host(*case))
+
+
+def test_builders_reject_non_acgt(walk):
+    """Anything but A / C / G / T (either case) in a tip sequence is an error in every builder - the reference
+    panics (kmers_map.rs:431-443) - and so are decreasing offsets; never a silently different model."""
+    from classeq2_b200._lib import ClsError
+    rng = np.random.default_rng(5)
+    tflat, tip_node, bases, offsets = random_build_case(rng, n_internal=4, k=35, m=4, max_len=120)
+    bad = bases.copy()
+    bad[len(bad) // 2] = ord("N")
+    for builder in (_host, walk):
+        with pytest.raises(ClsError):
+            builder(tflat, tip_node, bad, offsets)
+    off2 = offsets.copy()
+    if len(off2) > 2:
+        off2[1], off2[2] = off2[2], off2[1]
+        if off2[1] != off2[2]:
+            with pytest.raises(ClsError):
+                _host(tflat, tip_node, bases, off2)
 
 
 def test_walk_multi_tile_sequences(walk):

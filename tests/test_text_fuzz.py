@@ -31,7 +31,7 @@ def test_model_serialisation_refuses_malformed_views_without_crashing(tmp_path):
     exe = str(tmp_path / "model_fuzz")
     r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-pthread",
                         os.path.join(HERE, "native", "model_fuzz.cpp"), os.path.join(CSRC, "index_build.cpp"),
-                        os.path.join(CSRC, "host_api.cpp"), "-o", exe], capture_output=True, text=True)
+                        os.path.join(CSRC, "host_api.cpp"), os.path.join(CSRC, "host_pool.cpp"), "-o", exe], capture_output=True, text=True)
     assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
     if r.returncode != 0:
         pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")

@@ -13,10 +13,13 @@ import classeq2_b200 as cq  # noqa: E402
 from classeq2_b200 import synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-c = synth.CONFIGS[2]
+cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+n_dev = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # > 0: one multi-device handle over that many replicas
+c = synth.CONFIGS[cfg]
 sm = synth.make_model(c["n_tips"], c["l_ref"], c["tree_seed"])
 bases, offsets, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, n, 150, c["tree_seed"] + 2)
-ix = cq.Index(sm.flat, device=0)
+import torch  # noqa: E402
+ix = cq.Index(sm.flat, device=0) if n_dev == 0 else cq.Index(sm.flat, devices=[d % torch.cuda.device_count() for d in range(n_dev)])
 out = cq.BatchResult(n)
 for _ in range(3):
     ix.place_batch_into(bases, offsets, out)
@@ -27,6 +30,6 @@ for _ in range(10):
     ts.append(time.perf_counter() - t0)
 dt = float(np.mean(ts))
 knobs = {k: os.environ[k] for k in ("CLS_PIPE", "CLS_CHUNK_MBASES", "CLS_CHUNK_RAMP", "CLS_HOST_THREADS", "CLASSEQ_B200_LIB") if k in os.environ}
-print(f"{knobs} e2e {dt * 1e3:.2f} ms (min {min(ts) * 1e3:.2f})  {n / dt / 1e6:.1f} M reads/s  "
+print(f"config{cfg} n={n} replicas={n_dev} {knobs} e2e {dt * 1e3:.2f} ms (min {min(ts) * 1e3:.2f})  {n / dt / 1e6:.1f} M reads/s  "
       f"status_hist={np.bincount(out.status, minlength=11).tolist()} sum(node)={int(out.node_id.sum())}",
       {k: round(v, 2) for k, v in ix.timing().items()})
