@@ -154,6 +154,27 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def probe_ceiling(table_bytes: int):
+    """Measured rate of random 32-byte probes of a table of this size on one B200 (profiles/probe_ceiling.json, from
+    tools/micro/probe_bench.cu), interpolated in log(table size).  G probes/s, or None."""
+    p = os.path.join(ROOT, "profiles", "probe_ceiling.json")
+    try:
+        pts = sorted((float(k), float(v)) for k, v in json.load(open(p))["g_probes_per_s_by_table_mib"].items())
+    except (OSError, ValueError, KeyError):
+        return None
+    mib = table_bytes / float(1 << 20)
+    if mib <= pts[0][0]:
+        return pts[0][1]
+    if mib >= pts[-1][0]:
+        return pts[-1][1]
+    import math
+    for (a, va), (b, vb) in zip(pts, pts[1:]):
+        if a <= mib <= b:
+            t = (math.log(mib) - math.log(a)) / (math.log(b) - math.log(a))
+            return va + t * (vb - va)
+    return None
+
+
 def ncu_traffic(config: int):
     """dram bytes per launch of the place kernel from the committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -318,6 +339,11 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- end to end through the C ABI with host buffers: `e2e` ----------------------------------------
     out = cq.BatchResult(n_local)
+    # the step's inputs sit in PINNED host memory (what a reader that fills a reusable buffer hands over): with few host
+    # cores per GPU the library copies the ASCII bases straight from it and packs on the device (cls_set_pack_mode)
+    pinned = torch.empty(len(bases), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = bases
+    bases = pinned.numpy()
     for _ in range(max(1, min(args.warmup, 2))):
         index.place_batch_into(bases, offsets, out, params)
     barrier()
@@ -329,13 +355,13 @@ def run_b200(args, rank, world, local_rank):
     e2e_s = allmax(e2e_local)
     tm = index.timing()
     same = all((getattr(out, f) == getattr(res, f)).all() for f, _ in cq.engine.RESULT_DTYPES)
-    n_device = int((lens >= K_SIZE).sum())
-    d2h = 32 * n_device
-    h2d = rb.nbytes() - d2h
-    e2e = {"value": reads_total / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": e2e_s * 1e3,
+    e2e = {"value": reads_total / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(allsum(float(tm["h2d_bytes"]))),
+           "d2h_bytes_per_step": int(allsum(float(tm["d2h_bytes"]))), "ms_per_step": e2e_s * 1e3,
            "breakdown_ms_rank0": {k: round(tm[k], 3) for k in ("pack_ms", "h2d_ms", "kernel_ms", "d2h_ms", "total_ms")},
-           "host_input": "ASCII bases + offsets in caller memory (what the reference's FASTA reader hands over)"}
+           "pack": ["host (2-bit words cross PCIe)", "device (ASCII staged through pinned memory)",
+                    "device (ASCII copied straight from the caller's pinned memory)"][int(tm["pack_on_device"])],
+           "host_input": "ASCII bases (pinned host memory) + offsets in caller memory (what the reference's FASTA reader hands over); "
+                         "bytes counted by the library from the copies it enqueues, summed over the ranks"}
 
     # ---- ONE process, ONE handle, every visible GPU (cls_index_create_multi): the reference's callers are single
     #      processes that fan out internally (ports/cli/src/cmds/place_sequences.rs:125-156); N = 1 arm only -----
@@ -403,6 +429,23 @@ def run_b200(args, rank, world, local_rank):
                 "l2_gbs": nc["l2_bytes_per_read"] * reads_per_s_gpu / 1e9,
                 "limiter": nc.get("limiter"), "capture": nc.get("capture"),
                 "note": "per-read counters of the committed capture x this run's reads/s on one GPU"}
+        # the ceiling of the table probes themselves: random 32-byte reads of a table of this size (a miss moves a whole
+        # 128-byte line from HBM), measured by tools/micro/probe_bench.cu on this GPU model
+        pc = probe_ceiling(int(info["table_bytes"]))
+        if pc:
+            look_gpu = lookups_local / step_s / 1e9
+            scan_share = None
+            if nc and nc.get("kernels"):
+                scan_ms = sum(k["time_ms"] for k in nc["kernels"] if "scan" in k["kernel"])
+                scan_share = scan_ms / nc["step_ms_in_capture"] if nc.get("step_ms_in_capture") else None
+            probe = {"table_mib": info["table_bytes"] / float(1 << 20), "ceiling_g_probes_per_s": pc,
+                     "achieved_g_probes_per_s_whole_step": look_gpu, "frac_whole_step": look_gpu / pc,
+                     "source": "profiles/probe_ceiling.json (tools/micro/probe_bench.cu, profiles/r2b/probe_bench.log)"}
+            if scan_share:
+                probe["achieved_g_probes_per_s_scan_kernel"] = look_gpu / scan_share
+                probe["frac_scan_kernel"] = look_gpu / scan_share / pc
+                probe["scan_kernel_share_of_step_in_capture"] = scan_share
+            secondary = dict(secondary or {}, random_probe=probe)
         cfg = common_config(args.config, args.reads or synth_reads(args.config), world)
         line = {
             "metric": "queries placed/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,

@@ -60,7 +60,8 @@ class Result(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("pack_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double),
-                ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+                ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("pack_on_device", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class IndexInfo(C.Structure):
@@ -120,6 +121,7 @@ PROTOTYPES = {
     "cls_resident_destroy": (None, [C.c_void_p]),
     "cls_resident_bytes": (C.c_uint64, [C.c_void_p]),
     "cls_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "cls_set_pack_mode": (C.c_int, [C.c_int]),
     "cls_fasta_upload": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(FastaRecords)]),
     "cls_index_create_shard": (C.c_int, [C.POINTER(ModelView), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "cls_index_create_multi": (C.c_int, [C.POINTER(ModelView), C.c_uint64, C.POINTER(C.c_void_p)]),

@@ -130,6 +130,10 @@ struct Workspace {
     PinBuf h_words, h_descs, h_results;
     DevBuf d_words, d_descs, d_results;
     DevBuf d_scratch[2];                // scan -> descent hand-over of the chunk in flight on each stream
+    // packing on the device (pack_kernels.cu): the batch's ASCII bases, where every read starts in them, invalid-base flags
+    DevBuf d_ascii, d_src, d_bad;
+    PinBuf h_src, h_bad, h_stage[2];    // h_stage: pinned staging ring for bases in pageable caller memory
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     PackedLayout lay;                   // reused across calls
     bool in_use = false;
 };
@@ -163,6 +167,9 @@ struct cls_index {
             w->h_words.release(); w->h_descs.release(); w->h_results.release();
             w->d_words.release(); w->d_descs.release(); w->d_results.release();
             w->d_scratch[0].release(); w->d_scratch[1].release();
+            for (auto &e : w->stage_ev) if (e) cudaEventDestroy(e);
+            w->d_ascii.release(); w->d_src.release(); w->d_bad.release();
+            w->h_src.release(); w->h_bad.release(); w->h_stage[0].release(); w->h_stage[1].release();
         }
         d_table.release(); d_arena.release(); d_qnodes.release(); d_qchild.release(); d_qid.release();
         d_terms.release(); d_qinfo.release(); d_lca.release();
@@ -357,13 +364,14 @@ void scatter_host_decided(const PackedLayout &lay, uint32_t k, cls_result *out) 
 
 // Device result records [first, first + count) (device order) -> the caller's arrays (caller order).
 // Queries demoted on the host while packing (invalid base) keep their host status.
-void scatter_device_range(const PackedLayout &lay, const ResultRec *recs, cls_result *out, uint64_t first, uint64_t count) {
+void scatter_device_range(const PackedLayout &lay, const ResultRec *recs, cls_result *out, uint64_t first, uint64_t count,
+                          const uint8_t *bad = nullptr) {
     parallel_for(count, 65536, [&](uint64_t a, uint64_t b) {
         for (uint64_t j = first + a; j < first + b; ++j) {
             const uint64_t i = lay.perm[j];
             const ResultRec &r = recs[j];
-            if (lay.pre_status[i] != 0xFF) {
-                if (out->status) out->status[i] = lay.pre_status[i];
+            if (lay.pre_status[i] != 0xFF || (bad && bad[j])) {   // bad: flagged by the device packer
+                if (out->status) out->status[i] = lay.pre_status[i] != 0xFF ? lay.pre_status[i] : (uint8_t)CLS_STATUS_ERR_INVALID_BASE;
                 if (out->node_id) out->node_id[i] = 0;
                 if (out->one) out->one[i] = 0;
                 if (out->rest) out->rest[i] = 0;
@@ -586,8 +594,91 @@ int cls_index_get_info(const cls_index *ix, cls_index_info *info) try {
     return CLS_OK;
 } CLS_ABI_CATCH
 
-static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) {
-    if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
+// Where the 2-bit packing of a cls_place_batch call runs.  On the host (AVX-512 / AVX2 packer on the host pool, 38 bytes
+// per 150-base read cross PCIe) when the process has cores to spare; on the device (the ASCII bases cross PCIe as they
+// are, 150 bytes per read - straight from the caller's memory when it is pinned, else through a pinned staging ring -
+// and pack_kernels.cu packs them) when several GPUs share few host cores: eight ranks of a 32-core box each packed
+// with their share of the cores and the 1 -> 8 GPU end-to-end curve collapsed (SCALE_r01: efficiency 0.33).
+// CLS_PACK=host|device forces the choice; the default is "device" below eight cores per GPU in use.
+static std::atomic<int> g_pack_mode{-1};   // cls_set_pack_mode; -1: not set, CLS_PACK decides
+static bool pack_on_device(size_t n_devices_of_handle) {
+    static const int env = [] {
+        const char *e = getenv("CLS_PACK");
+        if (!e) return 0;
+        return !strcmp(e, "device") ? 2 : !strcmp(e, "host") ? 1 : 0;
+    }();
+    const int set = g_pack_mode.load();
+    const int forced = set >= 0 ? set : env;
+    if (forced) return forced == 2;
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    unsigned gpus = (unsigned)std::max<size_t>(1, n_devices_of_handle);
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) gpus = std::max(gpus, (unsigned)std::max(1, atoi(e)));
+    return hc / gpus < 8;
+}
+
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Reads of a batch planned just in time (place_batch_impl, `fast`): the optimistic plan of a batch of short reads - every
+// read has k .. 162 bases (one geometry of the scan kernel), so the device order is the input order, nothing is decided
+// on the host, and the layout of a chunk (word offsets, lengths) is written right before the chunk is enqueued instead of
+// in a pass over the whole batch before the first copy starts (0.7 ms per million reads on sixteen threads, 2.7 ms on
+// four: SCALE_r01's end-to-end curve).  Returns false - nothing written beyond `end` - when a read does not qualify;
+// the caller then starts over with the general plan (plan_batch).
+constexpr uint32_t kFastMaxLen = 162;
+static bool plan_reads_fast(const cls_batch *batch, uint32_t k, PackedLayout &lay, std::vector<uint32_t> &word_off, uint64_t first,
+                            uint64_t end, uint64_t &words_so_far, uint32_t &max_len) {
+    constexpr uint64_t kBlk = 8192;
+    const uint64_t n = end - first, nblk = (n + kBlk - 1) / kBlk;
+    std::vector<uint64_t> bw(nblk + 1, 0);
+    std::vector<uint32_t> bmx(nblk, 0);
+    std::atomic<bool> ok{true};
+    parallel_for(nblk, 4, [&](uint64_t b0, uint64_t b1) {
+        for (uint64_t blk = b0; blk < b1; ++blk) {
+            uint64_t wsum = 0;
+            uint32_t mx = 0;
+            bool good = true;
+            const uint64_t hi = std::min(end, first + (blk + 1) * kBlk);
+            for (uint64_t i = first + blk * kBlk; i < hi; ++i) {
+                const uint64_t o0 = batch->offsets[i], o1 = batch->offsets[i + 1];
+                const uint64_t len = o1 - o0;
+                good &= (o1 >= o0) & (len >= k) & (len <= kFastMaxLen);
+                lay.lens[i] = (uint32_t)len;
+                wsum += (len + 15u) / 16u;
+                mx = std::max(mx, (uint32_t)std::min<uint64_t>(len, 0xFFFFFFFFu));
+            }
+            if (!good) ok = false;
+            bw[blk + 1] = wsum;
+            bmx[blk] = mx;
+        }
+    });
+    if (!ok) return false;
+    bw[0] = words_so_far;
+    for (uint64_t b = 0; b < nblk; ++b) { bw[b + 1] += bw[b]; max_len = std::max(max_len, bmx[b]); }
+    if (bw[nblk] >= 0xFFFFFFFFull) return false;   // the general plan reports it
+    parallel_for(nblk, 4, [&](uint64_t b0, uint64_t b1) {
+        for (uint64_t blk = b0; blk < b1; ++blk) {
+            uint64_t wo = bw[blk];
+            const uint64_t hi = std::min(end, first + (blk + 1) * kBlk);
+            for (uint64_t i = first + blk * kBlk; i < hi; ++i) {
+                lay.perm[i] = (uint32_t)i;
+                lay.pre_status[i] = 0xFF;
+                word_off[i] = (uint32_t)wo;
+                wo += (lay.lens[i] + 15u) / 16u;
+            }
+        }
+    });
+    words_so_far = bw[nblk];
+    word_off[end] = (uint32_t)words_so_far;
+    return true;
+}
+
+static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result,
+                            size_t n_devices_of_handle, bool fast, bool *fell_back) {
     const double t0 = now_ms();
     CU_TRY(cudaSetDevice(ix->device));
     Workspace *w = acquire_ws(ix);
@@ -595,8 +686,21 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
     WsGuard guard{ix, w};
     PackedLayout &lay = w->lay;
     std::vector<uint32_t> &word_off = lay.word_off;
-    int rc = plan_batch(batch, ix->dix.k_size, ix->dix.max_fanout, lay, word_off);
-    if (rc != CLS_OK) return rc;
+    int rc = CLS_OK;
+    const uint64_t nq = batch->n_queries;
+    uint64_t fast_words = 0;       // fast plan: packed words of the reads planned so far
+    uint64_t fast_planned = 0;     //            ... and how many reads that is
+    if (fast) {
+        const uint64_t tb = batch->offsets[nq] - batch->offsets[0];
+        lay.classes.clear();
+        lay.n_queries = nq; lay.n_device = (uint32_t)nq;
+        lay.n_words = (tb + 15 * nq) / 16 + 1;   // an upper bound, for the buffers
+        lay.pre_status.resize(nq); lay.lens.resize(nq); lay.perm.resize(nq); word_off.resize((size_t)nq + 1);
+        lay.classes.push_back(LengthClass{0, (uint32_t)nq, (uint32_t)std::min<uint64_t>(kFastMaxLen, std::max<uint64_t>(tb / nq, ix->dix.k_size))});
+    } else {
+        rc = plan_batch(batch, ix->dix.k_size, ix->dix.max_fanout, lay, word_off);
+        if (rc != CLS_OK) return rc;
+    }
     cls_timing tm{};
     tm.pack_ms = now_ms() - t0;  // planning counts as packing
     static const bool dbg = getenv("CLS_DEBUG_TIMING") != nullptr;
@@ -604,9 +708,25 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
     const size_t words_b = (size_t)lay.n_words * 4, descs_b = (size_t)lay.n_device * sizeof(ReadDesc),
                  res_b = (size_t)lay.n_device * sizeof(ResultRec);
     PlaceParams pp = make_place_params(params);
+    const uint64_t base0 = batch->n_queries ? batch->offsets[0] : 0;
+    const uint64_t ascii_b = batch->n_queries ? batch->offsets[batch->n_queries] - base0 : 0;
+    const bool dev_pack = lay.n_device && ascii_b && pack_on_device(n_devices_of_handle);
+    // the whole range must be pinned for a direct copy (first and last byte looked at; a registration covers a range)
+    const bool src_pinned = dev_pack && is_pinned_host(batch->bases + base0) && is_pinned_host(batch->bases + base0 + ascii_b - 1);
+    constexpr uint64_t kPiece = (uint64_t)32 << 20;   // bases per copy
     if (lay.n_device) {
-        CU_TRY(w->h_words.reserve(words_b + 16)); CU_TRY(w->h_descs.reserve(descs_b)); CU_TRY(w->h_results.reserve(res_b));
+        if (!dev_pack) CU_TRY(w->h_words.reserve(words_b + 16));
+        CU_TRY(w->h_descs.reserve(descs_b)); CU_TRY(w->h_results.reserve(res_b));
         CU_TRY(w->d_words.reserve(words_b + 16)); CU_TRY(w->d_descs.reserve(descs_b)); CU_TRY(w->d_results.reserve(res_b));
+        if (dev_pack) {
+            CU_TRY(w->d_ascii.reserve(ascii_b + 16)); CU_TRY(w->d_src.reserve((size_t)lay.n_device * 8)); CU_TRY(w->d_bad.reserve(lay.n_device));
+            CU_TRY(w->h_src.reserve((size_t)lay.n_device * 8)); CU_TRY(w->h_bad.reserve(lay.n_device));
+            if (!src_pinned)
+                for (int q = 0; q < 2; ++q) {
+                    CU_TRY(w->h_stage[q].reserve(std::min(kPiece, ascii_b)));
+                    if (!w->stage_ev[q]) CU_TRY(cudaEventCreateWithFlags(&w->stage_ev[q], cudaEventDisableTiming));
+                }
+        }
     }
     // Chunks of every length class go through pack (host threads) -> H2D -> kernel -> D2H on two
     // alternating streams: chunk c+1 is packed and copied while chunk c is on the SMs, and the
@@ -629,6 +749,15 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
             a += n;
             if (ramp) step = std::min<uint64_t>(step * 2, per * (uint64_t)ramp);
         }
+        // ... and the very last ones shrink again: what follows the last kernel (its results' way back, their scatter) is
+        // exposed, and is as long as the last chunk
+        if (ramp && &c == &lay.classes.back())
+            for (int r = 0; r < 3 && chunks.back().count > std::max<uint64_t>(8192, per / 4); ++r) {
+                Chunk last = chunks.back();
+                const uint32_t half = last.count / 2;
+                chunks.back().count = last.count - half;
+                chunks.push_back(Chunk{last.first + (last.count - half), half, last.max_len});
+            }
     }
     while (w->chunk_ev.size() < 4 * chunks.size()) {
         cudaEvent_t e = nullptr;
@@ -638,11 +767,36 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
     uint32_t *h_words = (uint32_t *)w->h_words.p, *d_words = (uint32_t *)w->d_words.p;
     ReadDesc *h_descs = (ReadDesc *)w->h_descs.p, *d_descs = (ReadDesc *)w->d_descs.p;
     ResultRec *h_res = (ResultRec *)w->h_results.p, *d_res = (ResultRec *)w->d_results.p;
+    uint64_t *h_src = (uint64_t *)w->h_src.p, *d_src = (uint64_t *)w->d_src.p;
+    uint8_t *h_bad = (uint8_t *)w->h_bad.p, *d_bad = (uint8_t *)w->d_bad.p, *d_ascii = (uint8_t *)w->d_ascii.p;
     size_t scattered = 0;
     auto drain = [&](size_t upto) -> int {  // scatter the chunks whose D2H has completed (blocking up to `upto`)
         for (; scattered < upto; ++scattered) {
             CU_TRY(cudaEventSynchronize(w->chunk_ev[4 * scattered + 3]));
-            scatter_device_range(lay, h_res, result, chunks[scattered].first, chunks[scattered].count);
+            scatter_device_range(lay, h_res, result, chunks[scattered].first, chunks[scattered].count, dev_pack ? h_bad : nullptr);
+        }
+        return CLS_OK;
+    };
+    // device packing: the caller's bases go up in input order, piece by piece, on the copy stream; a chunk's pack kernel
+    // runs once everything up to the last base of its reads is there (one length class: chunk c needs just its own range)
+    uint64_t uploaded = 0, piece_no = 0;
+    auto upload_to = [&](uint64_t end, cudaStream_t st_in) -> int {
+        while (uploaded < end) {
+            const uint64_t n = std::min(kPiece, end - uploaded);
+            const uint8_t *src = batch->bases + base0 + uploaded;
+            if (!src_pinned) {
+                const int q = (int)(piece_no & 1);
+                if (piece_no >= 2) CU_TRY(cudaEventSynchronize(w->stage_ev[q]));   // the copy that last read this slot
+                uint8_t *dst = (uint8_t *)w->h_stage[q].p;
+                parallel_for(n, (uint64_t)1 << 20, [&](uint64_t a, uint64_t b) { memcpy(dst + a, src + a, b - a); });
+                src = dst;
+                CU_TRY(cudaMemcpyAsync(d_ascii + uploaded, src, n, cudaMemcpyHostToDevice, st_in));
+                CU_TRY(cudaEventRecord(w->stage_ev[q], st_in));
+            } else {
+                CU_TRY(cudaMemcpyAsync(d_ascii + uploaded, src, n, cudaMemcpyHostToDevice, st_in));
+            }
+            tm.h2d_bytes += n;
+            uploaded += n; ++piece_no;
         }
         return CLS_OK;
     };
@@ -653,19 +807,63 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
     static const bool pipe3 = [] { const char *e = getenv("CLS_PIPE"); return !(e && atoi(e) == 2); }();
     if (pipe3 && !w->stream3) CU_TRY(cudaStreamCreateWithFlags(&w->stream3, cudaStreamNonBlocking));
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        if (fast) {   // the layout of this chunk's reads, just in time
+            const double tq = now_ms();
+            uint32_t mx = 0;
+            const uint64_t end = (uint64_t)chunks[ci].first + chunks[ci].count;
+            if (!plan_reads_fast(batch, ix->dix.k_size, lay, word_off, fast_planned, end, fast_words, mx)) {
+                // a read that is too short, too long or has bad offsets: everything in flight is waited for (the guard),
+                // and the caller starts over with the general plan
+                *fell_back = true;
+                return CLS_OK;
+            }
+            fast_planned = end;
+            chunks[ci].max_len = mx;
+            tm.pack_ms += now_ms() - tq;
+        }
         const Chunk &c = chunks[ci];
         cudaStream_t st = (ci & 1) ? w->stream2 : w->stream;                 // default: everything of a chunk on one of two streams
         cudaStream_t st_in = pipe3 ? w->stream2 : st, st_k = pipe3 ? w->stream : st, st_out = pipe3 ? w->stream3 : st;
         cudaEvent_t *ev = &w->chunk_ev[4 * ci];
         const double tp = now_ms();
-        pack_batch(batch, lay, word_off, h_words, h_descs, c.first, c.count);
-        tm.pack_ms += now_ms() - tp;
         const size_t w0 = word_off[c.first], w1 = word_off[c.first + c.count];
-        CU_TRY(cudaEventRecord(ev[0], st_in));
-        CU_TRY(cudaMemcpyAsync(d_words + w0, h_words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, st_in));
+        if (dev_pack) {
+            // descriptors and source offsets of the chunk's reads; how far into the bases the chunk reaches
+            std::atomic<uint64_t> need{0};
+            parallel_for(c.count, 16384, [&](uint64_t a0, uint64_t b0) {
+                uint64_t mx = 0;
+                for (uint64_t j = c.first + a0; j < c.first + b0; ++j) {
+                    const uint64_t i = lay.perm[j];
+                    h_descs[j] = ReadDesc{word_off[j], lay.lens[i]};
+                    h_src[j] = batch->offsets[i] - base0;
+                    mx = std::max(mx, batch->offsets[i + 1] - base0);
+                }
+                uint64_t cur = need.load();
+                while (cur < mx && !need.compare_exchange_weak(cur, mx)) {}
+            });
+            CU_TRY(cudaEventRecord(ev[0], st_in));
+            CU_TRY(cudaMemsetAsync(d_bad + c.first, 0, c.count, st_in));
+            rc = upload_to(need.load(), st_in);
+            if (rc != CLS_OK) return rc;
+            tm.pack_ms += now_ms() - tp;
+            CU_TRY(cudaMemcpyAsync(d_src + c.first, h_src + c.first, (size_t)c.count * 8, cudaMemcpyHostToDevice, st_in));
+            tm.h2d_bytes += (uint64_t)c.count * 8;
+        } else {
+            pack_batch(batch, lay, word_off, h_words, h_descs, c.first, c.count);
+            tm.pack_ms += now_ms() - tp;
+            CU_TRY(cudaEventRecord(ev[0], st_in));
+            CU_TRY(cudaMemcpyAsync(d_words + w0, h_words + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, st_in));
+            tm.h2d_bytes += (w1 - w0) * 4;
+        }
         CU_TRY(cudaMemcpyAsync(d_descs + c.first, h_descs + c.first, (size_t)c.count * sizeof(ReadDesc), cudaMemcpyHostToDevice, st_in));
+        tm.h2d_bytes += (uint64_t)c.count * sizeof(ReadDesc);
         CU_TRY(cudaEventRecord(ev[1], st_in));
         if (pipe3) CU_TRY(cudaStreamWaitEvent(st_k, ev[1], 0));
+        if (dev_pack) {
+            cudaError_t pe = launch_ascii_pack(d_ascii, d_src, d_descs, c.first, c.count, c.max_len, d_words, d_bad, st_k);
+            if (pe != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("pack kernel launch: ") + cudaGetErrorString(pe));
+            tm.kernel_launches += 1;
+        }
         PlaceGeom g = make_place_geom(c.max_len, ix->dix.k_size, ix->dix.max_fanout);
         DevBuf &scratch = w->d_scratch[ci & 1];  // stream order protects its reuse by the chunk after next
         if (pipe3 && place_scratch_bytes(c.count, c.max_len, ix->dix.k_size, ix->dix.max_fanout) > scratch.cap && scratch.p)
@@ -685,6 +883,11 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
         CU_TRY(cudaEventRecord(ev[2], st_k));
         if (pipe3) CU_TRY(cudaStreamWaitEvent(st_out, ev[2], 0));
         CU_TRY(cudaMemcpyAsync(h_res + c.first, d_res + c.first, (size_t)c.count * sizeof(ResultRec), cudaMemcpyDeviceToHost, st_out));
+        tm.d2h_bytes += (uint64_t)c.count * sizeof(ResultRec);
+        if (dev_pack) {
+            CU_TRY(cudaMemcpyAsync(h_bad + c.first, d_bad + c.first, c.count, cudaMemcpyDeviceToHost, st_out));
+            tm.d2h_bytes += c.count;
+        }
         CU_TRY(cudaEventRecord(ev[3], st_out));
         if (ci >= 2) { rc = drain(ci - 1); if (rc != CLS_OK) return rc; }  // chunks older than the two in flight
     }
@@ -704,9 +907,30 @@ static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_para
         cudaEventElapsedTime(&ms, ev[2], ev[3]); tm.d2h_ms += ms;
     }
     tm.total_ms = now_ms() - t0;
+    tm.pack_on_device = dev_pack ? (src_pinned ? 2u : 1u) : 0u;
     { std::lock_guard<std::mutex> lk(ix->mu); ix->timing = tm; }
     guard.clean = true;   // every chunk has been drained: nothing of this call is in flight
     return CLS_OK;
+}
+
+static int place_batch_one(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result,
+                           size_t n_devices_of_handle = 1) {
+    if (ix->n_shards > 1) return fail(CLS_ERR_INVALID_ARGUMENT, "this handle holds one shard of the index: use the routed calls");
+    // batches that look like short reads (k = 35, mean length within the one-warp geometry) try the just-in-time plan
+    static const bool no_fast = getenv("CLS_NO_FASTPLAN") != nullptr;
+    const uint64_t n = batch->n_queries;
+    bool fast = !no_fast && ix->dix.k_size == 35 && n >= 1 && n < 0xFFFFFFFFull && batch->offsets && batch->bases;
+    if (fast) {
+        const uint64_t o0 = batch->offsets[0], o1 = batch->offsets[n];
+        fast = o1 >= o0 && (o1 - o0) >= n * 35 && (o1 - o0) <= n * (uint64_t)kFastMaxLen;
+    }
+    if (fast) {
+        bool fell_back = false;
+        const int rc = place_batch_impl(ix, batch, params, result, n_devices_of_handle, true, &fell_back);
+        if (!fell_back) return rc;
+    }
+    bool unused = false;
+    return place_batch_impl(ix, batch, params, result, n_devices_of_handle, false, &unused);
 }
 
 // Multi-device handle: the batch is cut into one contiguous part per replica (equal shares of the bases), every part
@@ -744,7 +968,7 @@ static int place_batch_multi(cls_index *front, const cls_batch *batch, const cls
         r.n_root_matched = result->n_root_matched ? result->n_root_matched + a : nullptr;
         r.iterations = result->iterations ? result->iterations + a : nullptr;
         try {
-            rcs[d] = place_batch_one(front->replicas[d].get(), &part, params, &r);
+            rcs[d] = place_batch_one(front->replicas[d].get(), &part, params, &r, nd);
         } catch (const std::bad_alloc &) {
             rcs[d] = fail(CLS_ERR_OUT_OF_MEMORY, "host allocation failed");
         } catch (const std::exception &e) {
@@ -763,11 +987,18 @@ static int place_batch_multi(cls_index *front, const cls_batch *batch, const cls
         tm.pack_ms = std::max(tm.pack_ms, t.pack_ms); tm.h2d_ms = std::max(tm.h2d_ms, t.h2d_ms);
         tm.kernel_ms = std::max(tm.kernel_ms, t.kernel_ms); tm.d2h_ms = std::max(tm.d2h_ms, t.d2h_ms);
         tm.total_ms = std::max(tm.total_ms, t.total_ms); tm.kernel_launches += t.kernel_launches;
+        tm.h2d_bytes += t.h2d_bytes; tm.d2h_bytes += t.d2h_bytes; tm.pack_on_device = std::max(tm.pack_on_device, t.pack_on_device);
     }
     { std::lock_guard<std::mutex> lk(front->mu); front->timing = tm; }
     for (size_t d = 0; d < nd; ++d)
         if (rcs[d] != CLS_OK) return fail(rcs[d], errs[d]);
     return CLS_OK;
+}
+
+int cls_set_pack_mode(int mode) {
+    if (mode < 0 || mode > 2) return fail(CLS_ERR_INVALID_ARGUMENT, "pack mode must be 0 (automatic), 1 (host) or 2 (device)");
+    const int prev = g_pack_mode.exchange(mode);
+    return prev < 0 ? 0 : prev;
 }
 
 int cls_place_batch(cls_index *ix, const cls_batch *batch, const cls_params *params, cls_result *result) try {

@@ -75,6 +75,11 @@ cudaError_t launch_place_routed(const DeviceIndex &ix, const PlaceParams &pp, co
                                 uint32_t n_shards, uint64_t seg_cap, const uint2 *runs, const uint16_t *slot_win, const void *replies,
                                 int sm_count, cudaStream_t stream, void *scratch, size_t scratch_bytes);
 
+// 2-bit packing on the device (pack_kernels.cu): ASCII bases of reads [first, first + count) -> packed words at their
+// descriptors' word offsets; bad[j] = 1 for a read with a byte other than A/C/G/T (either case).
+cudaError_t launch_ascii_pack(const uint8_t *ascii, const uint64_t *src_off, const ReadDesc *descs, uint32_t first, uint32_t count,
+                              uint32_t max_len, uint32_t *words, uint8_t *bad, cudaStream_t stream);
+
 cudaError_t launch_hash_only(const uint32_t *packed, uint32_t len, uint32_t k, uint64_t *out, cudaStream_t stream);
 
 }  // namespace cls

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CLS_ABI_VERSION 1
+#define CLS_ABI_VERSION 2
 
 typedef enum cls_error {
     CLS_OK = 0,
@@ -158,6 +158,10 @@ typedef struct cls_timing {
     double d2h_ms;     /* result records device -> host           */
     double total_ms;   /* wall clock of the call                  */
     uint64_t kernel_launches;
+    uint64_t h2d_bytes;      /* bytes copied host -> device by the call (ABI version 2)                     */
+    uint64_t d2h_bytes;      /* bytes copied device -> host by the call                                      */
+    uint32_t pack_on_device; /* 0: bases packed to 2 bit on the host; 1: on the device, ASCII staged through */
+    uint32_t reserved;       /* pinned memory; 2: on the device, ASCII copied straight from pinned caller memory */
 } cls_timing;
 
 typedef struct cls_index cls_index;                 /* a model resident on one GPU            */
@@ -240,6 +244,16 @@ void cls_resident_destroy(cls_resident_batch *rb);
 uint64_t cls_resident_bytes(const cls_resident_batch *rb);
 
 int cls_get_timing(const cls_index *index, cls_timing *out);
+
+/*
+ * Where cls_place_batch packs the query bases to 2 bit: 0 = automatic (on the host when the process has at least
+ * eight cores per GPU in use, else on the device), 1 = on the host, 2 = on the device (the ASCII bases cross PCIe as
+ * they are - straight from `batch->bases` when that memory is pinned, cudaHostAlloc / cudaHostRegister, else through a
+ * pinned staging ring).  Process-wide; overrides the CLS_PACK=host|device environment variable.  Results are
+ * identical either way.  Returns the previous mode, or a negative cls_error.  The reference has no counterpart: its
+ * reader hands place_sequence a String (place_sequences/mod.rs:118-159).
+ */
+int cls_set_pack_mode(int mode);
 
 /*
  * FASTA ingest on the device: the raw bytes of a (multi-)FASTA file go to the GPU, which classifies

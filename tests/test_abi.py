@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in the header but not exported"
         assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
-    assert _lib.lib.cls_abi_version() == 1
+    assert _lib.lib.cls_abi_version() == 2
 
 
 def test_no_torch_in_the_library():

@@ -20,6 +20,10 @@ sm = synth.make_model(c["n_tips"], c["l_ref"], c["tree_seed"])
 bases, offsets, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, n, 150, c["tree_seed"] + 2)
 import torch  # noqa: E402
 ix = cq.Index(sm.flat, device=0) if n_dev == 0 else cq.Index(sm.flat, devices=[d % torch.cuda.device_count() for d in range(n_dev)])
+if os.environ.get("PIN"):      # the bases in pinned memory (a device pack then copies straight from them)
+    pin = torch.empty(len(bases), dtype=torch.uint8).pin_memory()
+    pin.numpy()[:] = bases
+    bases = pin.numpy()
 out = cq.BatchResult(n)
 for _ in range(3):
     ix.place_batch_into(bases, offsets, out)
@@ -29,7 +33,7 @@ for _ in range(10):
     ix.place_batch_into(bases, offsets, out)
     ts.append(time.perf_counter() - t0)
 dt = float(np.mean(ts))
-knobs = {k: os.environ[k] for k in ("CLS_PIPE", "CLS_CHUNK_MBASES", "CLS_CHUNK_RAMP", "CLS_HOST_THREADS", "CLASSEQ_B200_LIB") if k in os.environ}
+knobs = {k: os.environ[k] for k in ("CLS_PIPE", "CLS_CHUNK_MBASES", "CLS_CHUNK_RAMP", "CLS_HOST_THREADS", "CLASSEQ_B200_LIB", "CLS_PACK", "PIN") if k in os.environ}
 print(f"config{cfg} n={n} replicas={n_dev} {knobs} e2e {dt * 1e3:.2f} ms (min {min(ts) * 1e3:.2f})  {n / dt / 1e6:.1f} M reads/s  "
       f"status_hist={np.bincount(out.status, minlength=11).tolist()} sum(node)={int(out.node_id.sum())}",
       {k: round(v, 2) for k, v in ix.timing().items()})
