@@ -599,7 +599,7 @@ int cls_index_get_info(const cls_index *ix, cls_index_info *info) try {
 // are, 150 bytes per read - straight from the caller's memory when it is pinned, else through a pinned staging ring -
 // and pack_kernels.cu packs them) when several GPUs share few host cores: eight ranks of a 32-core box each packed
 // with their share of the cores and the 1 -> 8 GPU end-to-end curve collapsed (SCALE_r01: efficiency 0.33).
-// CLS_PACK=host|device forces the choice; the default is "device" below eight cores per GPU in use.
+// CLS_PACK=host|device forces the choice; the default is "device" below sixteen cores per GPU in use (two GPUs on a 24-core box: 31.2 against 35.7 ms per 5 M reads, profiles/r2b).
 static std::atomic<int> g_pack_mode{-1};   // cls_set_pack_mode; -1: not set, CLS_PACK decides
 static bool pack_on_device(size_t n_devices_of_handle) {
     static const int env = [] {
@@ -614,7 +614,7 @@ static bool pack_on_device(size_t n_devices_of_handle) {
     if (hc == 0) hc = 4;
     unsigned gpus = (unsigned)std::max<size_t>(1, n_devices_of_handle);
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) gpus = std::max(gpus, (unsigned)std::max(1, atoi(e)));
-    return hc / gpus < 8;
+    return hc / gpus < 16;
 }
 
 static bool is_pinned_host(const void *p) {

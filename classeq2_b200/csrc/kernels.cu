@@ -846,7 +846,8 @@ __global__ void __launch_bounds__(CTA ? 512 : 256, CTA ? 2 : 4) place_kernel(Dev
                                                        const uint32_t *__restrict__ packed,
                                                        const ReadDesc *__restrict__ reads, uint32_t first_read,
                                                        uint32_t n_reads, ResultRec *__restrict__ results,
-                                                       PlaceGeom g, ScanOut so, TraceBuf trace) {
+                                                       PlaceGeom g, ScanOut so, TraceBuf trace,
+                                                       const uint8_t *__restrict__ only = nullptr) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint64_t tail_lut[64];
     init_tail_lut(tail_lut);
@@ -884,6 +885,9 @@ __global__ void __launch_bounds__(CTA ? 512 : 256, CTA ? 2 : 4) place_kernel(Dev
     const uint32_t gstride = CTA ? gridDim.x : gridDim.x * warps_per_cta;
 #pragma unroll 1
     for (uint32_t r = gwarp; r < n_reads; r += gstride) {
+        // `only` given (kb-scale reads after scanfrag_kernel + gather_kernel, frag_kernels.cuh): just the reads those two
+        // handed back
+        if (only && only[r] != 1) continue;   // kRedoPlace
         const ReadDesc rd = reads[first_read + r];
         const uint32_t L = rd.len;
         const uint32_t W = L - k + 1;  // host guarantees L >= k
@@ -1329,6 +1333,7 @@ __global__ void CLS_DESCEND_BOUNDS descend_kernel(DeviceIndex ix, PlaceParams pp
 
 namespace {
 #include "scan2_kernels.cuh"
+#include "frag_kernels.cuh"
 #include "giant_kernels.cuh"
 }  // namespace
 
@@ -1482,6 +1487,22 @@ static cudaError_t launch_descend(const DeviceIndex &ix, const PlaceParams &pp, 
     return cudaGetLastError();
 }
 
+// ---- kb-scale reads, k = 35, closed models: scanfrag_kernel hashes and probes (frag_kernels.cuh), the placement kernel takes
+//      it from there.  The hits of one WAVE of reads live behind the hand-over scratch: 8 bytes per window and strand.
+constexpr size_t kFragWaveBytes = (size_t)1 << 30;
+static bool frag_disabled() {
+    static const bool off = getenv("CLS_NO_FRAG") != nullptr;
+    return off;
+}
+static inline uint32_t frag_hit_stride(const PlaceGeom &g) { return 2u * (g.max_len - 34u); }
+static inline uint32_t frag_wave_reads(uint32_t n_reads, const PlaceGeom &g) {
+    const size_t per = (size_t)frag_hit_stride(g) * 8 + 1;
+    return (uint32_t)std::min<size_t>(n_reads, std::max<size_t>(1, kFragWaveBytes / per));
+}
+static inline size_t frag_scratch_bytes(uint32_t n_reads, const PlaceGeom &g) {
+    return (size_t)frag_wave_reads(n_reads, g) * ((size_t)frag_hit_stride(g) * 8 + 1) + 512;
+}
+
 template <int K, bool CLOSED, bool CTA>
 static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, const uint32_t *packed,
                                   const ReadDesc *reads, uint32_t first_read, uint32_t n_reads,
@@ -1522,9 +1543,58 @@ static cudaError_t launch_place_t(const DeviceIndex &ix, const PlaceParams &pp, 
         so = carve_scratch(scratch, n_reads, kPairCapWide);
         if ((e = cudaMemsetAsync(so.counters, 0, 64, stream)) != cudaSuccess) return e;
     }
-    place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so, trace);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (n_launches) ++*n_launches;
+    bool two_phase = false;
+    if constexpr (K == 35 && CLOSED && CTA) {
+        const size_t pair_b = (scratch_bytes_for(n_reads, kPairCapWide) + 255) & ~(size_t)255;
+        two_phase = split && !frag_disabled() && !trace.rows && scratch_bytes >= pair_b + frag_scratch_bytes(n_reads, g);
+        if (two_phase) {
+            char *base = reinterpret_cast<char *>(((uintptr_t)scratch + 255) & ~(uintptr_t)255) + pair_b;
+            const uint32_t wave = frag_wave_reads(n_reads, g), stride = frag_hit_stride(g);
+            uint32_t *counter = reinterpret_cast<uint32_t *>(base);
+            uint2 *hits = reinterpret_cast<uint2 *>(base + 256);
+            uint8_t *redo = reinterpret_cast<uint8_t *>(hits + (size_t)wave * stride);
+            const uint32_t frags = (g.max_len - 34u + kFragWindows - 1u) / kFragWindows;
+            const size_t fsmem = (size_t)Scan2Layout<4>::kBytes * 8;
+            if ((e = cudaFuncSetAttribute(scanfrag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)) != cudaSuccess) return e;
+            int focc = 0;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, scanfrag_kernel, 256, fsmem)) != cudaSuccess) return e;
+            if (focc < 1) focc = 1;
+            for (uint32_t a = 0; a < n_reads; a += wave) {
+                const uint32_t n = std::min(wave, n_reads - a);
+                if ((e = cudaMemsetAsync(counter, 0, 4, stream)) != cudaSuccess) return e;
+                if ((e = cudaMemsetAsync(redo, 0, n, stream)) != cudaSuccess) return e;
+                const uint64_t units = (uint64_t)n * frags;
+                const uint32_t fgrid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count * focc, (units + 7) / 8);
+                scanfrag_kernel<<<fgrid, 256, fsmem, stream>>>(ix, packed, reads, first_read + a, n, frags, hits, stride, redo, counter);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                ScanOut sa = so;
+                sa.pairs = so.pairs + (size_t)a * so.cap;
+                sa.meta = so.meta + a;
+                int gocc = 0;
+                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, gather_kernel, 256, 0)) != cudaSuccess) return e;
+                gather_kernel<<<std::min<uint32_t>((uint32_t)(sm_count * std::max(gocc, 1)), n), 256, 0, stream>>>(reads, first_read + a, n, hits, stride,
+                                                                                                                redo, sa);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                // reads with more node-set records than the descent kernel holds in registers: walked from shared memory
+                const size_t wsmem = (size_t)kWideWarps * (5u * kGListCap + 2u * g.fan_cap) * 4;
+                if ((e = cudaFuncSetAttribute(descend_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)) != cudaSuccess) return e;
+                if ((e = cudaMemsetAsync(counter, 0, 4, stream)) != cudaSuccess) return e;
+                descend_wide_kernel<<<std::min<uint32_t>((uint32_t)(2 * sm_count), (n + 127) / 128), 32 * kWideWarps, wsmem, stream>>>(
+                    ix, pp, first_read + a, n, hits, stride, redo, results, g.fan_cap, counter);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                // the reads the kernels handed back (foreign bucket keys, a table that filled up): hashed again, as ever
+                const uint32_t pgrid = std::min<uint32_t>((uint32_t)(sm_count * occ), n);
+                place_kernel<K, CLOSED, CTA><<<pgrid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read + a, n, results, g, sa, trace, redo);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+                if (n_launches) *n_launches += 4;
+            }
+        }
+    }
+    if (!two_phase) {
+        place_kernel<K, CLOSED, CTA><<<grid, warps * 32, smem, stream>>>(ix, pp, packed, reads, first_read, n_reads, results, g, so, trace);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (n_launches) ++*n_launches;
+    }
     if (split) {
         if ((e = launch_descend<8>(ix, pp, so, first_read, n_reads, results, g.fan_cap, sm_count, stream)) != cudaSuccess) return e;
         if (n_launches) ++*n_launches;
@@ -1583,7 +1653,10 @@ size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t k, uint3
     const PlaceGeom g = make_place_geom(max_len, k, max_fanout);
     if (needs_giant(g)) return giant_scratch_bytes(n_reads, g);
     if (split_disabled()) return 0;
-    if (g.cta_per_read) return scratch_bytes_for(n_reads, kPairCapWide);
+    if (g.cta_per_read) {
+        const size_t pair_b = (scratch_bytes_for(n_reads, kPairCapWide) + 255) & ~(size_t)255;
+        return k == 35 && !frag_disabled() ? pair_b + frag_scratch_bytes(n_reads, g) : pair_b;
+    }
     return k == 35 ? scratch_bytes_for(n_reads, kPairCap) : 0;
 }
 

@@ -247,7 +247,7 @@ int cls_get_timing(const cls_index *index, cls_timing *out);
 
 /*
  * Where cls_place_batch packs the query bases to 2 bit: 0 = automatic (on the host when the process has at least
- * eight cores per GPU in use, else on the device), 1 = on the host, 2 = on the device (the ASCII bases cross PCIe as
+ * sixteen cores per GPU in use, else on the device), 1 = on the host, 2 = on the device (the ASCII bases cross PCIe as
  * they are - straight from `batch->bases` when that memory is pinned, cudaHostAlloc / cudaHostRegister, else through a
  * pinned staging ring).  Process-wide; overrides the CLS_PACK=host|device environment variable.  Results are
  * identical either way.  Returns the previous mode, or a negative cls_error.  The reference has no counterpart: its

@@ -380,6 +380,35 @@ def test_long_reads_cta_mode(cq, general):
     ix.close(), md.close()
 
 
+def test_long_reads_foreign_bucket_keys(cq):
+    """kb-scale reads against a model in which some entries sit under the bucket key of ANOTHER prefix than their own
+    k-mer's: such a hit counts when any window of the query has that prefix (kmers_map.rs:55-70).  The fragment kernel
+    cannot settle that from one fragment and hands the read back to the placement kernel (frag_kernels.cuh, `redo`)."""
+    from classeq2_b200 import synth
+    from classeq2_b200.model import FlatModel
+    from oracle import cpp_oracle
+    rng = np.random.default_rng(515)
+    sm = synth.make_model(48, 1600, 9191)
+    f0 = sm.flat
+    eb = f0.entry_bucket.copy()
+    idx = rng.choice(len(eb), len(eb) // 40, replace=False)
+    eb[idx] = eb[rng.permutation(idx)]          # keys of other entries: all of them keys of real ACGT prefixes
+    flat = FlatModel(f0.k_size, f0.m_size, f0.node_id, f0.node_kind, f0.child_off, f0.child_idx, eb, f0.entry_hash, f0.entry_set,
+                     f0.set_off, f0.set_node_ids)
+    lens = np.concatenate([synth.skewed_lengths(120, 78), np.array([150, 162, 163, 290, 291, 400, 1600])])
+    bases, offsets, _ = synth.make_reads(sm.ref_codes, sm.ref_lens, len(lens), lens, 9193)
+    md = cpp_oracle.CppModel.from_flat(flat)
+    want = md.place_batch(bases, offsets)
+    base_want = cpp_oracle.CppModel.from_flat(f0).place_batch(bases, offsets)
+    assert (want["n_matched"] != base_want["n_matched"]).any()   # the moved keys do change what counts
+    ix = cq.Index(flat, device=0)
+    got = ix.place_batch((bases, offsets))
+    for f in ("status", "node_id", "one", "rest", "n_query_kmers", "n_matched", "n_root_matched"):
+        bad = np.flatnonzero(getattr(got, f) != want[f])
+        assert bad.size == 0, (f, bad[:5], getattr(got, f)[bad[:5]], want[f][bad[:5]], lens[bad[:5]])
+    ix.close(), md.close()
+
+
 # ---- reads with MANY distinct node sets: every hand-over / fallback of the short-read path ----------
 def _many_sets_model(cq, oracle, rng, n_tips, n_reads, pool):
     """A model whose k-mer index holds exactly the windows of `n_reads` random 150-mers, every window
