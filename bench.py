@@ -298,6 +298,14 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allgather(x: float):
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def allsum(x: float) -> float:
         if world == 1:
             return x
@@ -359,7 +367,9 @@ def run_b200(args, rank, world, local_rank):
            "d2h_bytes_per_step": int(allsum(float(tm["d2h_bytes"]))), "ms_per_step": e2e_s * 1e3,
            "breakdown_ms_rank0": {k: round(tm[k], 3) for k in ("pack_ms", "h2d_ms", "kernel_ms", "d2h_ms", "total_ms")},
            "pack": ["host (2-bit words cross PCIe)", "device (ASCII staged through pinned memory)",
-                    "device (ASCII copied straight from the caller's pinned memory)"][int(tm["pack_on_device"])],
+                    "device (ASCII copied straight from the caller's pinned memory)",
+                    "mixed (the chunks of a call are dealt to the host packer and to the device packer)"][int(tm["pack_on_device"])],
+           "ms_per_step_by_rank": [round(x * 1e3, 3) for x in allgather(e2e_local)],
            "host_input": "ASCII bases (pinned host memory) + offsets in caller memory (what the reference's FASTA reader hands over); "
                          "bytes counted by the library from the copies it enqueues, summed over the ranks"}
 

@@ -600,21 +600,29 @@ int cls_index_get_info(const cls_index *ix, cls_index_info *info) try {
 // and pack_kernels.cu packs them) when several GPUs share few host cores: eight ranks of a 32-core box each packed
 // with their share of the cores and the 1 -> 8 GPU end-to-end curve collapsed (SCALE_r01: efficiency 0.33).
 // CLS_PACK=host|device forces the choice; the default is "device" below sixteen cores per GPU in use (two GPUs on a 24-core box: 31.2 against 35.7 ms per 5 M reads, profiles/r2b).
+// Mixed (the default for batches of short reads below sixteen cores per GPU): the chunks of a call are dealt to both -
+// the host cores pack some while the copy engine moves the ASCII of the others - in the ratio that lets the two finish
+// together (about 2.5 GB/s of ASCII per core against about 24 GB/s per GPU when eight GPUs pull from one host).
 static std::atomic<int> g_pack_mode{-1};   // cls_set_pack_mode; -1: not set, CLS_PACK decides
-static bool pack_on_device(size_t n_devices_of_handle) {
+enum PackMode { kPackOnHost = 1, kPackOnDevice = 2, kPackMixed = 3 };
+static PackMode resolve_pack_mode(size_t n_devices_of_handle, bool fast_plan, double &host_share) {
     static const int env = [] {
         const char *e = getenv("CLS_PACK");
         if (!e) return 0;
-        return !strcmp(e, "device") ? 2 : !strcmp(e, "host") ? 1 : 0;
+        return !strcmp(e, "device") ? 2 : !strcmp(e, "host") ? 1 : !strcmp(e, "mixed") ? 3 : 0;
     }();
-    const int set = g_pack_mode.load();
-    const int forced = set >= 0 ? set : env;
-    if (forced) return forced == 2;
     unsigned hc = std::thread::hardware_concurrency();
     if (hc == 0) hc = 4;
     unsigned gpus = (unsigned)std::max<size_t>(1, n_devices_of_handle);
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) gpus = std::max(gpus, (unsigned)std::max(1, atoi(e)));
-    return hc / gpus < 16;
+    const double cores = std::max(1.0, std::min((double)hc / gpus, (double)host_threads())), r_host = 2.5 * cores, r_pcie = 24.0;
+    host_share = std::min(0.9, r_host / (r_pcie + 0.73 * r_host));   // a host-packed base still sends 0.27 bytes
+    const int set = g_pack_mode.load();
+    const int forced = set > 0 ? set : (set < 0 ? env : 0);
+    if (forced == kPackOnHost || forced == kPackOnDevice) return (PackMode)forced;
+    if (forced == kPackMixed) return fast_plan ? kPackMixed : kPackOnDevice;
+    if (hc / gpus >= 16) return kPackOnHost;
+    return fast_plan ? kPackMixed : kPackOnDevice;
 }
 
 static bool is_pinned_host(const void *p) {
@@ -710,12 +718,14 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
     PlaceParams pp = make_place_params(params);
     const uint64_t base0 = batch->n_queries ? batch->offsets[0] : 0;
     const uint64_t ascii_b = batch->n_queries ? batch->offsets[batch->n_queries] - base0 : 0;
-    const bool dev_pack = lay.n_device && ascii_b && pack_on_device(n_devices_of_handle);
+    double host_share = 0.0;
+    const PackMode pack_mode = lay.n_device && ascii_b ? resolve_pack_mode(n_devices_of_handle, fast, host_share) : kPackOnHost;
+    const bool dev_pack = pack_mode != kPackOnHost, mix = pack_mode == kPackMixed;
     // the whole range must be pinned for a direct copy (first and last byte looked at; a registration covers a range)
     const bool src_pinned = dev_pack && is_pinned_host(batch->bases + base0) && is_pinned_host(batch->bases + base0 + ascii_b - 1);
     constexpr uint64_t kPiece = (uint64_t)32 << 20;   // bases per copy
     if (lay.n_device) {
-        if (!dev_pack) CU_TRY(w->h_words.reserve(words_b + 16));
+        if (!dev_pack || mix) CU_TRY(w->h_words.reserve(words_b + 16));
         CU_TRY(w->h_descs.reserve(descs_b)); CU_TRY(w->h_results.reserve(res_b));
         CU_TRY(w->d_words.reserve(words_b + 16)); CU_TRY(w->d_descs.reserve(descs_b)); CU_TRY(w->d_results.reserve(res_b));
         if (dev_pack) {
@@ -770,10 +780,12 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
     uint64_t *h_src = (uint64_t *)w->h_src.p, *d_src = (uint64_t *)w->d_src.p;
     uint8_t *h_bad = (uint8_t *)w->h_bad.p, *d_bad = (uint8_t *)w->d_bad.p, *d_ascii = (uint8_t *)w->d_ascii.p;
     size_t scattered = 0;
+    std::vector<uint8_t> chunk_dev(chunks.size(), 0);   // chunk packed on the device (its invalid-base flags come back with the results)
+    double host_acc = 0.5;                               // mixed: error diffusion of the host's share over the chunks
     auto drain = [&](size_t upto) -> int {  // scatter the chunks whose D2H has completed (blocking up to `upto`)
         for (; scattered < upto; ++scattered) {
             CU_TRY(cudaEventSynchronize(w->chunk_ev[4 * scattered + 3]));
-            scatter_device_range(lay, h_res, result, chunks[scattered].first, chunks[scattered].count, dev_pack ? h_bad : nullptr);
+            scatter_device_range(lay, h_res, result, chunks[scattered].first, chunks[scattered].count, chunk_dev[scattered] ? h_bad : nullptr);
         }
         return CLS_OK;
     };
@@ -827,7 +839,13 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
         cudaEvent_t *ev = &w->chunk_ev[4 * ci];
         const double tp = now_ms();
         const size_t w0 = word_off[c.first], w1 = word_off[c.first + c.count];
-        if (dev_pack) {
+        bool dev_c = dev_pack;
+        if (mix) {
+            host_acc += host_share;
+            if (host_acc >= 1.0) { host_acc -= 1.0; dev_c = false; }
+        }
+        chunk_dev[ci] = dev_c ? 1 : 0;
+        if (dev_c) {
             // descriptors and source offsets of the chunk's reads; how far into the bases the chunk reaches
             std::atomic<uint64_t> need{0};
             parallel_for(c.count, 16384, [&](uint64_t a0, uint64_t b0) {
@@ -843,6 +861,9 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
             });
             CU_TRY(cudaEventRecord(ev[0], st_in));
             CU_TRY(cudaMemsetAsync(d_bad + c.first, 0, c.count, st_in));
+            // (just-in-time plan: the device order is the input order, a chunk's bases are one range - the ranges of
+            // host-packed chunks are never sent)
+            if (fast && uploaded < h_src[c.first]) uploaded = h_src[c.first];
             rc = upload_to(need.load(), st_in);
             if (rc != CLS_OK) return rc;
             tm.pack_ms += now_ms() - tp;
@@ -859,7 +880,7 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
         tm.h2d_bytes += (uint64_t)c.count * sizeof(ReadDesc);
         CU_TRY(cudaEventRecord(ev[1], st_in));
         if (pipe3) CU_TRY(cudaStreamWaitEvent(st_k, ev[1], 0));
-        if (dev_pack) {
+        if (dev_c) {
             cudaError_t pe = launch_ascii_pack(d_ascii, d_src, d_descs, c.first, c.count, c.max_len, d_words, d_bad, st_k);
             if (pe != cudaSuccess) return fail(CLS_ERR_CUDA, std::string("pack kernel launch: ") + cudaGetErrorString(pe));
             tm.kernel_launches += 1;
@@ -884,7 +905,7 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
         if (pipe3) CU_TRY(cudaStreamWaitEvent(st_out, ev[2], 0));
         CU_TRY(cudaMemcpyAsync(h_res + c.first, d_res + c.first, (size_t)c.count * sizeof(ResultRec), cudaMemcpyDeviceToHost, st_out));
         tm.d2h_bytes += (uint64_t)c.count * sizeof(ResultRec);
-        if (dev_pack) {
+        if (dev_c) {
             CU_TRY(cudaMemcpyAsync(h_bad + c.first, d_bad + c.first, c.count, cudaMemcpyDeviceToHost, st_out));
             tm.d2h_bytes += c.count;
         }
@@ -907,7 +928,7 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
         cudaEventElapsedTime(&ms, ev[2], ev[3]); tm.d2h_ms += ms;
     }
     tm.total_ms = now_ms() - t0;
-    tm.pack_on_device = dev_pack ? (src_pinned ? 2u : 1u) : 0u;
+    tm.pack_on_device = mix ? 3u : dev_pack ? (src_pinned ? 2u : 1u) : 0u;
     { std::lock_guard<std::mutex> lk(ix->mu); ix->timing = tm; }
     guard.clean = true;   // every chunk has been drained: nothing of this call is in flight
     return CLS_OK;
@@ -996,7 +1017,7 @@ static int place_batch_multi(cls_index *front, const cls_batch *batch, const cls
 }
 
 int cls_set_pack_mode(int mode) {
-    if (mode < 0 || mode > 2) return fail(CLS_ERR_INVALID_ARGUMENT, "pack mode must be 0 (automatic), 1 (host) or 2 (device)");
+    if (mode < 0 || mode > 3) return fail(CLS_ERR_INVALID_ARGUMENT, "pack mode must be 0 (automatic), 1 (host), 2 (device) or 3 (mixed)");
     const int prev = g_pack_mode.exchange(mode);
     return prev < 0 ? 0 : prev;
 }

@@ -160,8 +160,8 @@ typedef struct cls_timing {
     uint64_t kernel_launches;
     uint64_t h2d_bytes;      /* bytes copied host -> device by the call (ABI version 2)                     */
     uint64_t d2h_bytes;      /* bytes copied device -> host by the call                                      */
-    uint32_t pack_on_device; /* 0: bases packed to 2 bit on the host; 1: on the device, ASCII staged through */
-    uint32_t reserved;       /* pinned memory; 2: on the device, ASCII copied straight from pinned caller memory */
+    uint32_t pack_on_device; /* 0: bases packed to 2 bit on the host; 1: on the device, ASCII staged through pinned memory; */
+    uint32_t reserved;       /* 2: on the device, ASCII copied straight from pinned caller memory; 3: mixed (cls_set_pack_mode) */
 } cls_timing;
 
 typedef struct cls_index cls_index;                 /* a model resident on one GPU            */
@@ -246,12 +246,14 @@ uint64_t cls_resident_bytes(const cls_resident_batch *rb);
 int cls_get_timing(const cls_index *index, cls_timing *out);
 
 /*
- * Where cls_place_batch packs the query bases to 2 bit: 0 = automatic (on the host when the process has at least
- * sixteen cores per GPU in use, else on the device), 1 = on the host, 2 = on the device (the ASCII bases cross PCIe as
- * they are - straight from `batch->bases` when that memory is pinned, cudaHostAlloc / cudaHostRegister, else through a
- * pinned staging ring).  Process-wide; overrides the CLS_PACK=host|device environment variable.  Results are
- * identical either way.  Returns the previous mode, or a negative cls_error.  The reference has no counterpart: its
- * reader hands place_sequence a String (place_sequences/mod.rs:118-159).
+ * Where cls_place_batch packs the query bases to 2 bit: 1 = on the host (AVX-512 / AVX2 packer on the library's host
+ * pool; 38 bytes per 150-base read cross PCIe), 2 = on the device (the ASCII bases cross PCIe as they are - straight
+ * from `batch->bases` when that memory is pinned, cudaHostAlloc / cudaHostRegister, else through a pinned staging
+ * ring), 3 = mixed (batches of short reads: the chunks of a call are dealt to both in the ratio that lets the host
+ * cores and the copy engine finish together; other batches: as 2), 0 = automatic: on the host with sixteen cores or
+ * more per GPU in use, else mixed.  Process-wide; overrides the CLS_PACK=host|device|mixed environment variable.
+ * Results are identical in every mode.  Returns the previous mode, or a negative cls_error.  The reference has no
+ * counterpart: its reader hands place_sequence a String (place_sequences/mod.rs:118-159).
  */
 int cls_set_pack_mode(int mode);
 

@@ -116,16 +116,29 @@ def test_device_pack_large_batch_many_pieces(cq, pack_mode):
     tm = ix.timing()
     assert tm["pack_on_device"] == 1 and tm["h2d_bytes"] >= len(bases)
     _fields_equal(cq, host, dev)
+    # mixed: some chunks packed by the host, the others on the device; a few invalid bases in both kinds of chunk
+    bad = bases.copy()
+    for r in (5, n // 3, n // 2, n - 9):
+        bad[int(offsets[r]) + 17] = ord("N")
+    pack_mode(1)
+    ix.place_batch_into(bad, offsets, host)
+    pack_mode(3)
+    ix.place_batch_into(bad, offsets, dev)
+    tm = ix.timing()
+    assert tm["pack_on_device"] == 3 and 0 < tm["h2d_bytes"] < len(bases) + 20 * n
+    _fields_equal(cq, host, dev)
+    from classeq2_b200 import _lib
+    assert (dev.status == _lib.STATUS_ERR_INVALID_BASE).sum() == 4
     ix.close()
 
 
 def test_pack_mode_argument_is_checked(cq):
     from classeq2_b200 import _lib
-    assert _lib.lib.cls_set_pack_mode(3) < 0 and _lib.lib.cls_set_pack_mode(-1) < 0
+    assert _lib.lib.cls_set_pack_mode(4) < 0 and _lib.lib.cls_set_pack_mode(-1) < 0
     assert _lib.lib.cls_set_pack_mode(0) >= 0
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_just_in_time_plan_and_its_fallback(cq, pack_mode, mode):
     """Batches whose reads all have 35 .. 162 bases are planned chunk by chunk while the GPU already works
     (plan_reads_fast); one read outside that range anywhere in the batch sends the call back to the general plan.

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round 2, call 20: mixed packing: tests, end-to-end A/B with 4 host threads' worth of cores
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_device_pack.py tests/test_abi.py -m gpu -x -q > gpurun_out/c20_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/c20_pytest.log
+tail -12 gpurun_out/c20_pytest.log
+run() { env "$@" timeout 300 python tools/e2e_bench.py $N 3 2>&1 | tail -1 | cut -c1-330 | tee -a gpurun_out/c20_e2e.log; }
+N=1250000
+run CLS_PACK=host PIN=1 CLS_HOST_THREADS=4
+run CLS_PACK=device PIN=1 CLS_HOST_THREADS=4
+run CLS_PACK=mixed PIN=1 CLS_HOST_THREADS=4
+run CLS_PACK=mixed PIN=1
+run PIN=1
+N=10000000
+run CLS_PACK=mixed PIN=1
+run PIN=1
