@@ -600,9 +600,12 @@ int cls_index_get_info(const cls_index *ix, cls_index_info *info) try {
 // and pack_kernels.cu packs them) when several GPUs share few host cores: eight ranks of a 32-core box each packed
 // with their share of the cores and the 1 -> 8 GPU end-to-end curve collapsed (SCALE_r01: efficiency 0.33).
 // CLS_PACK=host|device forces the choice; the default is "device" below sixteen cores per GPU in use (two GPUs on a 24-core box: 31.2 against 35.7 ms per 5 M reads, profiles/r2b).
-// Mixed (the default for batches of short reads below sixteen cores per GPU): the chunks of a call are dealt to both -
-// the host cores pack some while the copy engine moves the ASCII of the others - in the ratio that lets the two finish
-// together (about 2.5 GB/s of ASCII per core against about 24 GB/s per GPU when eight GPUs pull from one host).
+// Mixed (cls_set_pack_mode(3), CLS_PACK=mixed; batches of short reads only): the chunks of a call are dealt to both - the
+// host cores pack some while the copy engine moves the ASCII of the others - in the ratio that would let the two finish
+// together (about 2.5 GB/s of ASCII per core against about 24 GB/s per GPU).  Never the automatic choice: on the
+// boxes measured it lost to device packing (8 GPUs, 32 cores: 23.5 against 20.4 ms per step - the host cores are the
+// scarcer resource there, and the 20 ms are the 1.66 GB of a step crossing PCIe at the 83 GB/s the eight GPUs get
+// together; profiles/r2b/bench_cfg3_n8_*.json).
 static std::atomic<int> g_pack_mode{-1};   // cls_set_pack_mode; -1: not set, CLS_PACK decides
 enum PackMode { kPackOnHost = 1, kPackOnDevice = 2, kPackMixed = 3 };
 static PackMode resolve_pack_mode(size_t n_devices_of_handle, bool fast_plan, double &host_share) {
@@ -621,8 +624,7 @@ static PackMode resolve_pack_mode(size_t n_devices_of_handle, bool fast_plan, do
     const int forced = set > 0 ? set : (set < 0 ? env : 0);
     if (forced == kPackOnHost || forced == kPackOnDevice) return (PackMode)forced;
     if (forced == kPackMixed) return fast_plan ? kPackMixed : kPackOnDevice;
-    if (hc / gpus >= 16) return kPackOnHost;
-    return fast_plan ? kPackMixed : kPackOnDevice;
+    return hc / gpus >= 16 ? kPackOnHost : kPackOnDevice;
 }
 
 static bool is_pinned_host(const void *p) {
@@ -639,7 +641,7 @@ static bool is_pinned_host(const void *p) {
 // the caller then starts over with the general plan (plan_batch).
 constexpr uint32_t kFastMaxLen = 162;
 static bool plan_reads_fast(const cls_batch *batch, uint32_t k, PackedLayout &lay, std::vector<uint32_t> &word_off, uint64_t first,
-                            uint64_t end, uint64_t &words_so_far, uint32_t &max_len) {
+                            uint64_t end, uint64_t &words_so_far, uint32_t &max_len, ReadDesc *descs, uint64_t *src, uint64_t base0) {
     constexpr uint64_t kBlk = 8192;
     const uint64_t n = end - first, nblk = (n + kBlk - 1) / kBlk;
     std::vector<uint64_t> bw(nblk + 1, 0);
@@ -676,6 +678,8 @@ static bool plan_reads_fast(const cls_batch *batch, uint32_t k, PackedLayout &la
                 lay.perm[i] = (uint32_t)i;
                 lay.pre_status[i] = 0xFF;
                 word_off[i] = (uint32_t)wo;
+                descs[i] = ReadDesc{(uint32_t)wo, lay.lens[i]};
+                if (src) src[i] = batch->offsets[i] - base0;   // device packing: where the read's bases start
                 wo += (lay.lens[i] + 15u) / 16u;
             }
         }
@@ -827,7 +831,7 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
             const double tq = now_ms();
             uint32_t mx = 0;
             const uint64_t end = (uint64_t)chunks[ci].first + chunks[ci].count;
-            if (!plan_reads_fast(batch, ix->dix.k_size, lay, word_off, fast_planned, end, fast_words, mx)) {
+            if (!plan_reads_fast(batch, ix->dix.k_size, lay, word_off, fast_planned, end, fast_words, mx, h_descs, dev_pack ? h_src : nullptr, base0)) {
                 // a read that is too short, too long or has bad offsets: everything in flight is waited for (the guard),
                 // and the caller starts over with the general plan
                 *fell_back = true;
@@ -851,8 +855,9 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
         chunk_dev[ci] = dev_c ? 1 : 0;
         if (dev_c) {
             // descriptors and source offsets of the chunk's reads; how far into the bases the chunk reaches
-            std::atomic<uint64_t> need{0};
-            parallel_for(c.count, 16384, [&](uint64_t a0, uint64_t b0) {
+            // (the just-in-time plan has written them already, and the chunk's bases are one range)
+            std::atomic<uint64_t> need{fast ? batch->offsets[(uint64_t)c.first + c.count] - base0 : 0};
+            if (!fast) parallel_for(c.count, 16384, [&](uint64_t a0, uint64_t b0) {
                 uint64_t mx = 0;
                 for (uint64_t j = c.first + a0; j < c.first + b0; ++j) {
                     const uint64_t i = lay.perm[j];

@@ -13,9 +13,11 @@ namespace cls {
 
 int host_threads() {
     // CLS_HOST_THREADS overrides the default: all cores, at most 32 - and under a launcher that runs one process per
-    // GPU (LOCAL_WORLD_SIZE = N > 1, torchrun) twice this rank's share of the cores: N pools of 32 threads on a 32-core
-    // box spent their time in the scheduler (pack_ms 3.2 -> 10.9 ms from 1 to 8 ranks, SCALE_r01), while an exact
-    // 1 / N split idles cores whenever the ranks pack at different times.
+    // GPU (LOCAL_WORLD_SIZE = N > 1, torchrun) this rank's share of the cores.  N pools of 32 threads on a 32-core box
+    // spent their time in the scheduler (pack_ms 3.2 -> 10.9 ms from 1 to 8 ranks, SCALE_r01); twice the share (round 2's
+    // first choice, good for host packing alone) still left every parallel loop of a rank waiting for a worker that had
+    // to get a time slice on a core another rank was using: fifty short loops per call took 15 ms of a 20 ms call with
+    // device packing (profiles/r2b/bench_cfg3_n8_*.json).
     static const int n = [] {
         if (const char *e = std::getenv("CLS_HOST_THREADS")) {
             const int v = std::atoi(e);
@@ -26,7 +28,7 @@ int host_threads() {
         unsigned want = std::min(hc, 32u);
         if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
             const int lws = std::atoi(e);
-            if (lws > 1) want = std::max(2u, std::min(want, 2u * hc / (unsigned)lws));
+            if (lws > 1) want = std::max(2u, std::min(want, hc / (unsigned)lws));
         }
         return (int)want;
     }();

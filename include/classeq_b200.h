@@ -251,7 +251,7 @@ int cls_get_timing(const cls_index *index, cls_timing *out);
  * from `batch->bases` when that memory is pinned, cudaHostAlloc / cudaHostRegister, else through a pinned staging
  * ring), 3 = mixed (batches of short reads: the chunks of a call are dealt to both in the ratio that lets the host
  * cores and the copy engine finish together; other batches: as 2), 0 = automatic: on the host with sixteen cores or
- * more per GPU in use, else mixed.  Process-wide; overrides the CLS_PACK=host|device|mixed environment variable.
+ * more per GPU in use, else on the device.  Process-wide; overrides the CLS_PACK=host|device|mixed environment variable.
  * Results are identical in every mode.  Returns the previous mode, or a negative cls_error.  The reference has no
  * counterpart: its reader hands place_sequence a String (place_sequences/mod.rs:118-159).
  */
