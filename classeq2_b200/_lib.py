@@ -149,6 +149,7 @@ PROTOTYPES = {
     "cls_sequences_close": (None, [C.c_void_p]),
     "cls_place_sequences": (C.c_int, [C.c_void_p, C.POINTER(RecordTree), C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_uint32,
                                       C.c_uint32, u64p]),
+    "cls_debug_plan_fast": (C.c_int, [C.c_uint32, C.POINTER(Batch), C.c_uint64, u32p, u32p, u64p, u32p, u64p]),
     "cls_debug_plan_batch": (C.c_int, [C.c_uint32, C.POINTER(Batch), u8p, u32p, u32p, C.POINTER(PlanClass), C.c_uint32, u32p, u32p, u64p]),
     "cls_debug_pack_read": (C.c_int, [u8p, C.c_uint64, u32p, C.c_uint64, C.c_int]),
     "cls_filter_sequence": (C.c_uint64, [u8p, C.c_uint64, u8p, C.c_uint64]),

@@ -1466,6 +1466,39 @@ int cls_debug_plan_batch(uint32_t k_size, const cls_batch *batch, uint8_t *pre_s
     return CLS_OK;
 } CLS_ABI_CATCH
 
+int cls_debug_plan_fast(uint32_t k_size, const cls_batch *batch, uint64_t chunk_reads, uint32_t *word_off, uint32_t *lens,
+                        uint64_t *src_off, uint32_t *max_len, uint64_t *n_planned) try {
+    if (!batch || !n_planned || k_size == 0 || chunk_reads == 0) return fail(CLS_ERR_INVALID_ARGUMENT, "NULL argument, k == 0 or chunk_reads == 0");
+    const uint64_t n = batch->n_queries;
+    *n_planned = 0;
+    if (max_len) *max_len = 0;
+    if (n == 0) return CLS_OK;
+    if (!batch->offsets || n >= 0xFFFFFFFFull) return fail(CLS_ERR_INVALID_ARGUMENT, "batch arrays are NULL or too long");
+    PackedLayout lay;
+    std::vector<uint32_t> woff((size_t)n + 1);
+    std::vector<ReadDesc> descs(n);
+    std::vector<uint64_t> src(n);
+    lay.pre_status.resize(n); lay.lens.resize(n); lay.perm.resize(n);
+    uint64_t words = 0, planned = 0;
+    uint32_t mx = 0;
+    const uint64_t base0 = batch->offsets[0];
+    while (planned < n) {   // chunk by chunk, as place_batch_impl does
+        const uint64_t end = std::min(n, planned + chunk_reads);
+        if (!plan_reads_fast(batch, k_size, lay, woff, planned, end, words, mx, descs.data(), src.data(), base0)) break;
+        planned = end;
+    }
+    *n_planned = planned;
+    if (max_len) *max_len = mx;
+    for (uint64_t i = 0; i < planned; ++i) {
+        if (lay.perm[i] != i || lay.pre_status[i] != 0xFF || descs[i].word_off != woff[i] || descs[i].len != lay.lens[i])
+            return fail(CLS_ERR_INVALID_ARGUMENT, "internal: the just-in-time plan is inconsistent");
+    }
+    if (word_off) std::memcpy(word_off, woff.data(), (size_t)(planned + (planned ? 1 : 0)) * 4);
+    if (lens) std::memcpy(lens, lay.lens.data(), (size_t)planned * 4);
+    if (src_off) std::memcpy(src_off, src.data(), (size_t)planned * 8);
+    return CLS_OK;
+} CLS_ABI_CATCH
+
 int cls_debug_pack_read(const uint8_t *bases, uint64_t len, uint32_t *words_out, uint64_t cap_words, int portable) try {
     if ((len && !bases) || !words_out || len >= (1ull << 31) || cap_words < (len + 15) / 16)
         return fail(CLS_ERR_INVALID_ARGUMENT, "bad arguments");

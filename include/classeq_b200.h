@@ -478,6 +478,18 @@ int cls_debug_plan_batch(uint32_t k_size, const cls_batch *batch, uint8_t *pre_s
                          cls_plan_class *classes, uint32_t cap_classes, uint32_t *n_classes, uint32_t *n_device, uint64_t *n_words);
 
 /*
+ * cls_debug_plan_fast: the JUST-IN-TIME plan cls_place_batch uses for batches of short reads (every read has k .. 162
+ * bases: the device order is the input order and nothing is decided on the host), run chunk by chunk over the whole
+ * batch (`chunk_reads` per step) without a GPU.  *n_planned = reads planned before the first chunk holding a read that
+ * does not qualify (cls_place_batch then starts over with the general plan of cls_debug_plan_batch) - the whole
+ * batch when all qualify; word_off[j] (n_planned + 1 entries), lens[j], src_off[j] (where read j starts in
+ * batch->bases, relative to the first read) for the planned reads; *max_len = their longest.  Output pointers other
+ * than n_planned may be NULL.
+ */
+int cls_debug_plan_fast(uint32_t k_size, const cls_batch *batch, uint64_t chunk_reads, uint32_t *word_off, uint32_t *lens,
+                        uint64_t *src_off, uint32_t *max_len, uint64_t *n_planned);
+
+/*
  * Host helpers mirroring the reference's input side (no GPU needed).
  *
  * cls_filter_sequence: SequenceBody::remove_non_iupac_from_sequence

@@ -96,3 +96,53 @@ def test_plan_degenerate_batches():
     nc, nd, nw = C.c_uint32(), C.c_uint32(), C.c_uint64()
     rc = _lib.lib.cls_debug_plan_batch(35, C.byref(b), None, None, None, None, 0, C.byref(nc), C.byref(nd), C.byref(nw))
     assert rc == _lib.CLS_ERR_INVALID_ARGUMENT
+
+
+# ---- the just-in-time plan of short-read batches (capi.cu: plan_reads_fast) --------------------------------------
+def plan_fast(lens, k, chunk, first_offset=0):
+    lens = np.asarray(lens, np.uint64)
+    n = len(lens)
+    offsets = np.full(n + 1, first_offset, np.uint64)
+    offsets[1:] += np.cumsum(lens)
+    bases = np.zeros(1, np.uint8)
+    b = _lib.Batch(n, bases.ctypes.data_as(_lib.u8p), offsets.ctypes.data_as(_lib.u64p))
+    woff, ln, src = np.zeros(n + 1, np.uint32), np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint64)
+    mx, npl = C.c_uint32(), C.c_uint64()
+    _lib.check(_lib.lib.cls_debug_plan_fast(k, C.byref(b), chunk, woff.ctypes.data_as(_lib.u32p), ln.ctypes.data_as(_lib.u32p),
+                                            src.ctypes.data_as(_lib.u64p), C.byref(mx), C.byref(npl)))
+    p = npl.value
+    return dict(n_planned=p, woff=woff[:p + 1], lens=ln[:p], src=src[:p], max_len=mx.value)
+
+
+@pytest.mark.parametrize("chunk", [1, 7, 8192, 10_000, 1 << 20])
+def test_fast_plan_equals_the_general_plan_on_short_reads(chunk):
+    """Every read within 35 .. 162 bases: the device order is the input order, the word offsets are those of the
+    general plan laid out in input order, whatever the chunking."""
+    rng = np.random.default_rng(chunk)
+    for lens in (np.full(30_000, 150), rng.integers(35, 163, 30_000), np.array([35]), np.array([162, 35, 162])):
+        f = plan_fast(lens, 35, chunk, first_offset=12345)
+        assert f["n_planned"] == len(lens) and f["max_len"] == lens.max()
+        assert (f["lens"] == lens).all()
+        words = (np.asarray(lens) + 15) // 16
+        assert (f["woff"] == np.concatenate([[0], np.cumsum(words)])).all()
+        assert (f["src"] == np.concatenate([[0], np.cumsum(lens)[:-1]])).all()
+        g = plan(lens, 35)                         # the general plan: the same reads, grouped by length class
+        assert sorted(g["perm"].tolist()) == list(range(len(lens))) and g["n_words"] == int(words.sum())
+
+
+def test_fast_plan_stops_at_the_first_chunk_with_a_read_out_of_range():
+    lens = np.full(1000, 150)
+    for bad_at, bad_len in ((0, 34), (499, 163), (999, 0), (500, 5000)):
+        l2 = lens.copy()
+        l2[bad_at] = bad_len
+        for chunk in (1, 64, 1000):
+            f = plan_fast(l2, 35, chunk)
+            assert f["n_planned"] == (bad_at // chunk) * chunk, (bad_at, bad_len, chunk)
+    # decreasing offsets are refused like any read out of range (the general plan then reports them)
+    offsets = np.array([0, 150, 100, 250], np.uint64)
+    b = _lib.Batch(3, np.zeros(1, np.uint8).ctypes.data_as(_lib.u8p), offsets.ctypes.data_as(_lib.u64p))
+    npl = C.c_uint64(99)
+    _lib.check(_lib.lib.cls_debug_plan_fast(35, C.byref(b), 8, None, None, None, None, C.byref(npl)))
+    assert npl.value == 0
+    # and the empty batch
+    assert plan_fast([], 35, 8)["n_planned"] == 0
