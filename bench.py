@@ -498,12 +498,80 @@ def run_b200(args, rank, world, local_rank):
                                          "stage_ms_per_step_rank0", "parity", "roofline", "status_histogram")}
         except Exception as ex:  # noqa: BLE001
             c5 = {"error": repr(ex)[:300]}
+    # ---- N = 1 on the default workload: the kb-scale reads of config 4 ride along (resident value + sampled parity),
+    #      so that the driver's one-GPU run also measures the fragment path (scanfrag / gather / wide descent kernels)
+    c4 = None
+    if world == 1 and args.config == 3 and not args.no_config4:
+        try:
+            c4 = run_config4_nested(args, local_rank)
+        except Exception as ex:  # noqa: BLE001
+            c4 = {"error": repr(ex)[:300]}
     if rank == 0:
         line["config5"] = c5
+        line["config4"] = c4
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_config4_nested(args, local_rank):
+    """Config 4 (5 k tips x 1.5 kb refs, 1 M reads of 150-1 550 bases) kernel-resident on one GPU: value, lookups/s,
+    a sampled parity check against the oracle.  A nested object of the default line, not a line of its own."""
+    import torch
+
+    import classeq2_b200 as cq
+    from oracle import cpp_oracle
+
+    n4 = min(args.reads4, 1_000_000)
+    sm, bases, offsets, _, gen_s = make_workload(4, 0, 1, n4, local_rank if args.device_build else None)
+    lens = np.diff(offsets.astype(np.int64))
+    lookups = int((2 * (lens[lens >= K_SIZE] - K_SIZE + 1)).sum())
+    index = cq.Index(sm.flat, device=local_rank)
+    info = index.info()
+    rb = index.upload((bases, offsets))
+    stream = torch.cuda.Stream(device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    params = cq.PlaceParams()
+    steps = max(2, min(args.steps, 3))
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            rb.place(params, stream.cuda_stream)
+        ev = []
+        for i in range(steps):
+            flush.fill_(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            rb.place(params, stream.cuda_stream)
+            b.record(stream)
+            ev.append((a, b))
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    ms_per_step = float(np.mean(ms))
+    res = rb.fetch(stream.cuda_stream)
+    n_chk = min(len(lens), 2000)
+    md = cpp_oracle.CppModel.from_flat(sm.flat)
+    o = md.place_batch(bases[: int(offsets[n_chk])], offsets[: n_chk + 1], n_threads=os.cpu_count() or 1)
+    md.close()
+    bad = sum(int((o[f] != getattr(res, f)[:n_chk]).sum()) for f, _ in cq.engine.RESULT_DTYPES)
+    alg = algorithmic_bytes(lens)
+    peak, _ = measured_peak()
+    pc = probe_ceiling(int(info["table_bytes"]))
+    out = {"value": len(lens) / (ms_per_step / 1e3), "unit": "reads/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": 2,
+           "lookups_per_s": lookups / (ms_per_step / 1e3),
+           "config": {"workload": NAMES[4], "reads": int(len(lens)), "mean_read_length": float(lens.mean()),
+                      "index_entries": int(info["n_entries"]), "table_bytes": int(info["table_bytes"])},
+           "roofline": {"bound": "hbm", "achieved": alg / (ms_per_step / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms_per_step / 1e3) / 1e9 / peak,
+                        "random_probe_ceiling_g_per_s": pc, "achieved_g_probes_per_s": lookups / (ms_per_step / 1e3) / 1e9,
+                        "kernel": "cls::scanfrag_kernel + cls::gather_kernel + cls::descend_kernel<8> + cls::descend_wide_kernel "
+                                  "(+ cls::scan2_kernel / descend16_kernel for the classes of up to 290 bases)"},
+           "parity": {"checked_reads": n_chk, "mismatching_fields": bad},
+           "status_histogram": np.bincount(res.status, minlength=11).tolist(), "step_ms": [round(x, 3) for x in ms],
+           "setup_s": round(gen_s, 1)}
+    rb.close()
+    index.close()
+    return out
 
 
 def run_sharded(args, rank, world, local_rank, embedded=False):
@@ -673,6 +741,8 @@ def main():
     ap.add_argument("--reads", type=int, default=None, help="override the number of reads of the config")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="config 5: how routed k-mers cross NVLink")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size in seconds of work")
+    ap.add_argument("--no-config4", action="store_true", help="N = 1, default workload: skip the nested config-4 (kb-scale reads) measurement")
+    ap.add_argument("--reads4", type=int, default=400_000, help="reads of the nested config-4 measurement")
     ap.add_argument("--no-config5", action="store_true", help="N > 1, default workload: skip the nested config-5 (hash-sharded index) measurement")
     ap.add_argument("--reads5", type=int, default=1_250_000, help="reads per GPU of the nested config-5 measurement")
     ap.add_argument("--no-inprocess", action="store_true", help="N = 1: skip the one-process-all-GPUs end-to-end number")
