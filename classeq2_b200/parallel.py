@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import numpy as np
 
 from .engine import RESULT_DTYPES, BatchResult
@@ -184,7 +186,10 @@ class ShardedPlacer:
         if transport == "p2p":
             if max_windows <= 0:
                 raise ValueError("transport='p2p' needs max_windows (k-mer windows of the largest batch)")
-            self.peers = PeerBuffers(device, rank, world, (int(max_windows / world * slack) + 65536 + 3) & ~3, group)
+            # a multiple of 32 slots: every rank's segment of a reply box then starts on a 128-byte line (32 x 12 B = 3 lines),
+            # so that the probe kernel's 384-byte rows are whole lines on the wire (CLS_SEG_ALIGN=4: round 1's alignment)
+            al = max(4, int(os.environ.get("CLS_SEG_ALIGN", "32")))
+            self.peers = PeerBuffers(device, rank, world, (int(max_windows / world * slack) + 65536 + al - 1) // al * al, group)
         elif transport != "nccl":
             raise ValueError("transport must be 'nccl' or 'p2p'")
 
@@ -274,8 +279,13 @@ class ShardedPlacer:
         # the counts all-to-all doubles as "every rank's route kernel has completed": my inbox is whole
         counts_from = exchange_plan(counts_to, self.group) if world > 1 else counts_to.copy()
         ev[2].record(st)
-        # stage 4+5: answer every sender's segment straight into that sender's reply box (my segment of it)
-        for s_rank in range(world):
+        # stage 4+5: answer every sender's segment straight into that sender's reply box (my segment of it).  The ranks walk
+        # the senders in STAGGERED order (me, me + 1, ...): with the same order on every rank all eight GPUs stored into ONE
+        # GPU's reply box at a time - 900 GB/s of NVLink ingress shared by eight writers while seven links idled (175 GB/s
+        # out per GPU, 17.5 of the 29 ms of a step; profiles/r2b).  CLS_PROBE_ORDER=same restores that order (A/B).
+        same_order = os.environ.get("CLS_PROBE_ORDER") == "same"
+        for j in range(world):
+            s_rank = j if same_order else (me + j) % world
             self.index.shard_probe(pb.inbox[me] + s_rank * seg_cap * 8, int(counts_from[s_rank]),
                                    pb.reply[s_rank] + me * seg_cap * REPLY_BYTES, st.cuda_stream)
         if world > 1:
