@@ -62,9 +62,15 @@ int main(int argc, char **argv) {
     rt.support = support; rt.length = length; rt.has_name = has_name; rt.name_off = name_off; rt.names = names;
     rt.child_off = child_off; rt.child_idx = child_idx;
 
-    if (argc < 3) { fprintf(stderr, "usage: %s queries.fasta out_path\n", argv[0]); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: %s queries.fasta out_path [device_mask]\n", argv[0]); return 2; }
     cls_index *index = NULL;
-    CHECK(cls_index_create(&model, 0, &index));
+    if (argc > 3) {
+        /* one handle over several GPUs: bit d of the mask = CUDA device d ("0" = every visible device); the batches of
+         * cls_place_sequences are then cut over them inside the library */
+        CHECK(cls_index_create_multi(&model, strtoull(argv[3], NULL, 0), &index));
+    } else {
+        CHECK(cls_index_create(&model, 0, &index));
+    }
     cls_params params;
     cls_params_default(&params);
     uint64_t n = 0;
