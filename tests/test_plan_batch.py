@@ -146,3 +146,28 @@ def test_fast_plan_stops_at_the_first_chunk_with_a_read_out_of_range():
     assert npl.value == 0
     # and the empty batch
     assert plan_fast([], 35, 8)["n_planned"] == 0
+
+
+def test_fast_plan_survives_arbitrary_offsets():
+    """Offsets that decrease, jump by 2^40 or wrap: never a crash, never more reads planned than there are, and what is
+    planned obeys the 35 .. 162 rule."""
+    rng = np.random.default_rng(99)
+    for it in range(300):
+        n = int(rng.integers(1, 400))
+        lens = rng.integers(35, 163, n).astype(np.int64)
+        offsets = np.zeros(n + 1, np.int64)
+        offsets[1:] = np.cumsum(lens)
+        for _ in range(int(rng.integers(0, 4))):          # damage a few entries
+            j = int(rng.integers(0, n + 1))
+            offsets[j] = int(rng.choice([0, offsets[j] - 1000, offsets[j] + (1 << 40), -1, offsets[j] + 500]))
+        off_u = offsets.astype(np.uint64)
+        b = _lib.Batch(n, np.zeros(1, np.uint8).ctypes.data_as(_lib.u8p), off_u.ctypes.data_as(_lib.u64p))
+        woff, ln = np.zeros(n + 1, np.uint32), np.zeros(n, np.uint32)
+        npl = C.c_uint64()
+        chunk = int(rng.choice([1, 3, 64, 1000]))
+        _lib.check(_lib.lib.cls_debug_plan_fast(35, C.byref(b), chunk, woff.ctypes.data_as(_lib.u32p), ln.ctypes.data_as(_lib.u32p),
+                                                None, None, C.byref(npl)))
+        p = npl.value
+        assert p <= n and p % chunk == 0 or p == n
+        true_len = np.diff(off_u[: p + 1].astype(np.int64)) if p else np.zeros(0, np.int64)
+        assert ((true_len >= 35) & (true_len <= 162)).all() and (ln[:p] == true_len).all()
