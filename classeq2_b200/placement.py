@@ -513,10 +513,25 @@ def render_records(headers: List[str], res: BatchResult, rtree: RecordTree, outp
                                            0 if output_format == "yaml" else 1, C.byref(out), C.byref(n_out),
                                            C.byref(err), C.byref(n_err)))
     try:
-        return C.string_at(out, n_out.value), C.string_at(err, n_err.value)
+        return _c_text(out, n_out.value), _c_text(err, n_err.value)
     finally:
         _lib.lib.cls_text_free(out)
         _lib.lib.cls_text_free(err)
+
+
+_C_TEXT_PIECE = 1 << 30
+
+
+def _c_text(ptr, n: int) -> bytes:
+    """``n`` bytes at ``ptr`` as ``bytes``.  ``ctypes.string_at`` takes a C ``int`` size: beyond 2 GiB it silently
+    wraps (a million IdentityFound records near the root of a tree are several GB of YAML), so big texts are copied
+    in pieces."""
+    if not n:
+        return b""
+    if n <= _C_TEXT_PIECE:
+        return C.string_at(ptr, n)
+    base = ptr.value if isinstance(ptr, C.c_void_p) else int(ptr)
+    return b"".join(C.string_at(base + a, min(_C_TEXT_PIECE, n - a)) for a in range(0, n, _C_TEXT_PIECE))
 
 
 @dataclass

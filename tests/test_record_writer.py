@@ -150,6 +150,31 @@ def test_many_records_keep_their_order(ps, col_tree):
     _check(ps, [f"read_{i}" for i in range(n)], res, tree)
 
 
+def test_rendered_text_beyond_one_copy_piece_is_not_truncated(ps, col_tree, monkeypatch):
+    """``ctypes.string_at`` takes a C int: a rendered batch beyond 2 GiB used to come back silently truncated (size
+    modulo 2^32).  The text is copied in pieces now; with a small piece size the pieced copy must equal the whole."""
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    ids = [c.id for c in tree.root.walk() if not c.is_leaf()]
+    n = 300
+    res = cq.BatchResult(n)
+    res.status[:] = _lib.STATUS_IDENTITY_FOUND
+    res.node_id[:] = np.random.default_rng(3).choice(ids, n)
+    headers = [f"q{i}" for i in range(n)]
+    rt = ps.RecordTree(tree)
+    whole = ps.render_records(headers, res, rt, "yaml")
+    assert len(whole[0]) > 100_000
+    for piece in (1, 4097, 65536):
+        monkeypatch.setattr(ps, "_C_TEXT_PIECE", piece if piece > 1 else 1000)
+        assert ps.render_records(headers, res, rt, "yaml") == whole
+    import ctypes
+    buf = ctypes.create_string_buffer(b"abcdefghij", 10)
+    monkeypatch.setattr(ps, "_C_TEXT_PIECE", 3)
+    assert ps._c_text(ctypes.c_void_p(ctypes.addressof(buf)), 10) == b"abcdefghij"
+    assert ps._c_text(ctypes.c_void_p(ctypes.addressof(buf)), 0) == b""
+
+
 class _OracleIndex:
     """Stands in for ``Index`` so that ``place_sequences`` runs without a GPU: the batch is placed by the C++ oracle
     (test infrastructure).  Everything else - FASTA reader, batching, record writers, files - is the product's."""
