@@ -501,6 +501,12 @@ def render_records(headers: List[str], res: BatchResult, rtree: RecordTree, outp
     """``cls_records_render``: the bytes the reference appends to ``<out>.yaml|.jsonl`` and to ``<out>.error`` for a
     batch, written by the library (multi-threaded C++) - byte-identical to :func:`placement_response` +
     :func:`yaml_dump` / :func:`json_dump` record by record."""
+    return _render(headers, res, rtree, output_format, None, None)
+
+
+def _render(headers: List[str], res: BatchResult, rtree: RecordTree, output_format: str, fo, fe):
+    """``cls_records_render``; the two texts go straight from the library's buffers to the files ``fo`` / ``fe`` (no
+    copy through ``bytes``: a batch of a million records can be gigabytes of YAML), or come back as ``bytes``."""
     hb = [h.encode("utf-8") for h in headers]
     off = np.zeros(len(hb) + 1, np.uint64)
     if hb:
@@ -513,7 +519,12 @@ def render_records(headers: List[str], res: BatchResult, rtree: RecordTree, outp
                                            0 if output_format == "yaml" else 1, C.byref(out), C.byref(n_out),
                                            C.byref(err), C.byref(n_err)))
     try:
-        return _c_text(out, n_out.value), _c_text(err, n_err.value)
+        if fo is None:
+            return _c_text(out, n_out.value), _c_text(err, n_err.value)
+        for f, ptr, n in ((fo, out, n_out.value), (fe, err, n_err.value)):
+            if n:
+                f.write(memoryview((C.c_ubyte * n).from_address(ptr.value)))
+        return None
     finally:
         _lib.lib.cls_text_free(out)
         _lib.lib.cls_text_free(err)
@@ -723,8 +734,9 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
                     res = index.place_batch([s for _, s in chunk], params)
                 per_seq_ms = (time.perf_counter() - t0) * 1e3 / max(len(chunk), 1)
                 if rtree is not None:
-                    text_o, text_e = render_records([h for h, _ in chunk], res, rtree, output_format)
+                    _render([h for h, _ in chunk], res, rtree, output_format, fo, fe)
                     times.extend(PlacementTime(header, per_seq_ms) for header, _ in chunk)
+                    continue
                 else:
                     buf_o, buf_e = [], []
                     for i, (header, _) in enumerate(chunk):
