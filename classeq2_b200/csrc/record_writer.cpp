@@ -350,29 +350,89 @@ const char kMsgNoRoot[] = "Query sequence has no overlapping kmers with the refe
 const char kMsgNoIntrospection[] =
     "Tree introspection not possible. Query sequence has no overlapping kmers with the reference tree";  // :446-454
 
-// One query: appends its record to `out` or its error text to `err`.  Returns false on an unknown status / node id.
-// Rendered Clade blocks by node: a batch places many reads on few clades, so a task renders each of them once.
-using CladeCache = std::unordered_map<uint64_t, std::string>;
+// A header that is certainly a plain YAML scalar (and needs no JSON escape): it starts with an ASCII letter, holds only
+// [A-Za-z0-9_] and is none of the words serde_yaml quotes - the common shape of a read name; everything else takes the
+// general path (yaml_string / json_string), which gives the same text for these.
+bool simple_header(const char *p, size_t n) {
+    if (n == 0 || !((p[0] >= 'A' && p[0] <= 'Z') || (p[0] >= 'a' && p[0] <= 'z'))) return false;
+    bool letters_only = true;
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned char c = (unsigned char)p[i];
+        const bool letter = (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z');
+        if (!(letter || (c >= '0' && c <= '9') || c == '_')) return false;
+        letters_only = letters_only && letter;
+    }
+    return !(letters_only && (n == 4 || n == 5));   // null / true / false in their three spellings have 4 or 5 letters
+}
 
-bool render_one(const TreeView &tv, const std::string &header, const cls_result *r, uint64_t i, bool yaml, std::string &out,
-                std::string &err, std::vector<uint64_t> &scratch, CladeCache &clade_text) {
+// What does not change from record to record, rendered once per call: the `code` line of every status whose text is
+// fixed, and the Clade block of every node an IdentityFound record of the batch names (a batch places many reads on few
+// clades; the blocks are rendered on the host pool before the records are).
+struct Fixed {
+    std::string code_yaml[16], code_json[16];   // by status: "\ncode: <scalar>\n" / ",\"code\":<string>"
+    std::string incon_yaml, incon_json;         // the Inconclusive code again, as the placement
+    std::vector<std::string> clade_text;        // by node index (pre-order); empty = not rendered
+};
+
+// The statuses whose `code` text is the same for every record.
+bool fixed_code(uint8_t st, std::string *text = nullptr) {
+    const char *head = nullptr, *tail = "";
+    switch (st) {
+        case CLS_STATUS_UNCL_NO_ROOT: head = "Unclassifiable: "; tail = kMsgNoRoot; break;
+        case CLS_STATUS_UNCL_NO_INTROSPECTION: head = "Unclassifiable: "; tail = kMsgNoIntrospection; break;
+        case CLS_STATUS_MAX_RESOLUTION: head = "MaxResolutionReached: LCA Accepted"; break;
+        case CLS_STATUS_IDENTITY_FOUND: head = "IdentityFound"; break;
+        case CLS_STATUS_INCONCLUSIVE: head = "Inconclusive: Multiple proposals"; break;
+        default: return false;
+    }
+    if (text) { *text = head; *text += tail; }
+    return true;
+}
+
+void make_fixed_codes(Fixed &fx) {
+    std::string c;
+    for (int st = 0; st < 16; ++st)
+        if (fixed_code((uint8_t)st, &c)) {
+            fx.code_yaml[st] = "\ncode: "; yaml_string(c, 2, fx.code_yaml[st]); fx.code_yaml[st] += '\n';
+            fx.code_json[st] = ",\"code\":"; json_string(c, fx.code_json[st]);
+        }
+    fixed_code(CLS_STATUS_INCONCLUSIVE, &c);
+    yaml_string(c, 2, fx.incon_yaml);
+    json_string(c, fx.incon_json);
+}
+
+void append_u64(std::string &out, uint64_t v) {
+    char b[24];
+    auto r = std::to_chars(b, b + sizeof b, v);
+    out.append(b, (size_t)(r.ptr - b));
+}
+void append_i64(std::string &out, int64_t v) {
+    char b[24];
+    auto r = std::to_chars(b, b + sizeof b, v);
+    out.append(b, (size_t)(r.ptr - b));
+}
+
+// One query: appends its record to `out` or its error text to `err`.  Returns false on an unknown status / node id.
+bool render_one(const TreeView &tv, const Fixed &fx, const char *hp, size_t hn, const cls_result *r, uint64_t i, bool yaml,
+                std::string &out, std::string &err, std::vector<uint64_t> &scratch, std::string &header, std::string &code) {
     const uint8_t st = r->status[i];
-    std::string code;
     switch (st) {
         case CLS_STATUS_ERR_TOO_SHORT: err += kErrTooShort; return true;
         case CLS_STATUS_ERR_MAX_ITERATIONS: err += kErrMaxIter; return true;
         case CLS_STATUS_ERR_ROOT_NO_CHILDREN: err += kErrRootNoChildren; return true;
         case CLS_STATUS_ERR_INVALID_BASE: err += kErrInvalidBase; return true;
-        case CLS_STATUS_UNCL_NO_MATCH:
-            code = "Unclassifiable: Query sequence SequenceHeader("; rust_debug_str(header, code); code += ") may not be related to the phylogeny";
-            break;
-        case CLS_STATUS_UNCL_NO_ROOT: code = std::string("Unclassifiable: ") + kMsgNoRoot; break;
-        case CLS_STATUS_UNCL_COVERAGE: code = "Unclassifiable: Insufficient kmers coverage: " + std::to_string(r->n_root_matched ? r->n_root_matched[i] : 0u); break;
-        case CLS_STATUS_UNCL_NO_INTROSPECTION: code = std::string("Unclassifiable: ") + kMsgNoIntrospection; break;
-        case CLS_STATUS_MAX_RESOLUTION: code = "MaxResolutionReached: LCA Accepted"; break;
-        case CLS_STATUS_IDENTITY_FOUND: code = "IdentityFound"; break;
-        case CLS_STATUS_INCONCLUSIVE: code = "Inconclusive: Multiple proposals"; break;
+        case CLS_STATUS_UNCL_NO_MATCH: case CLS_STATUS_UNCL_COVERAGE: case CLS_STATUS_UNCL_NO_ROOT:
+        case CLS_STATUS_UNCL_NO_INTROSPECTION: case CLS_STATUS_MAX_RESOLUTION: case CLS_STATUS_IDENTITY_FOUND:
+        case CLS_STATUS_INCONCLUSIVE: break;
         default: return false;
+    }
+    const bool simple = simple_header(hp, hn);
+    if (!simple || st == CLS_STATUS_UNCL_NO_MATCH) header.assign(hp, hn);
+    const bool fixed = fixed_code(st);
+    if (st == CLS_STATUS_UNCL_NO_MATCH) {
+        code = "Unclassifiable: Query sequence SequenceHeader("; rust_debug_str(header, code); code += ") may not be related to the phylogeny";
+    } else if (st == CLS_STATUS_UNCL_COVERAGE) {
+        code = "Unclassifiable: Insufficient kmers coverage: "; append_u64(code, r->n_root_matched ? r->n_root_matched[i] : 0u);
     }
     const bool identity = st == CLS_STATUS_IDENTITY_FOUND, max_res = st == CLS_STATUS_MAX_RESOLUTION;
     uint64_t node = 0;
@@ -384,26 +444,28 @@ bool render_one(const TreeView &tv, const std::string &header, const cls_result 
     if (tv.t->has_annotations && (identity || max_res)) annotations_for(tv, r->node_id[i], scratch); else scratch.clear();
     const cls_record_tree *t = tv.t;
     if (yaml) {
-        out += "---\nquery: "; yaml_string(header, 2, out);
-        out += "\ncode: "; yaml_string(code, 2, out); out += '\n';
+        out += "---\nquery: ";
+        if (simple) out.append(hp, hn); else yaml_string(header, 2, out);
+        if (fixed) out += fx.code_yaml[st];
+        else { out += "\ncode: "; yaml_string(code, 2, out); out += '\n'; }
         if (!scratch.empty()) {
             out += "annotations:\n";
             for (uint64_t a : scratch) out.append(t->ann_yaml + t->ann_yaml_off[a], t->ann_yaml + t->ann_yaml_off[a + 1]);
         }
         if (identity) {
             out += "placement:\n  clade:\n";
-            auto c = clade_text.find(node);
-            if (c == clade_text.end()) { std::string t2; yaml_clade(tv, node, 4, "    ", t2); c = clade_text.emplace(node, std::move(t2)).first; }
-            out += c->second;
-            out += "  one: "; out += std::to_string(r->one[i]); out += "\n  rest: "; out += std::to_string(r->rest[i]); out += '\n';
+            out += fx.clade_text[node];
+            out += "  one: "; append_i64(out, r->one[i]); out += "\n  rest: "; append_i64(out, r->rest[i]); out += '\n';
         } else if (max_res) {
-            out += "placement: "; out += std::to_string(r->node_id[i]); out += '\n';
+            out += "placement: "; append_u64(out, r->node_id[i]); out += '\n';
         } else if (st == CLS_STATUS_INCONCLUSIVE) {
-            out += "placement: "; yaml_string(code, 2, out); out += '\n';
+            out += "placement: "; out += fx.incon_yaml; out += '\n';
         }
     } else {
-        out += "{\"query\":"; json_string(header, out);
-        out += ",\"code\":"; json_string(code, out);
+        out += "{\"query\":";
+        if (simple) { out += '"'; out.append(hp, hn); out += '"'; } else json_string(header, out);
+        if (fixed) out += fx.code_json[st];
+        else { out += ",\"code\":"; json_string(code, out); }
         if (!scratch.empty()) {
             out += ",\"annotations\":[";
             for (size_t k = 0; k < scratch.size(); ++k) {
@@ -414,27 +476,29 @@ bool render_one(const TreeView &tv, const std::string &header, const cls_result 
         }
         if (identity) {
             out += ",\"placement\":{\"clade\":";
-            auto c = clade_text.find(node);
-            if (c == clade_text.end()) { std::string t2; json_clade(tv, node, t2); c = clade_text.emplace(node, std::move(t2)).first; }
-            out += c->second;
-            out += ",\"one\":"; out += std::to_string(r->one[i]); out += ",\"rest\":"; out += std::to_string(r->rest[i]); out += '}';
+            out += fx.clade_text[node];
+            out += ",\"one\":"; append_i64(out, r->one[i]); out += ",\"rest\":"; append_i64(out, r->rest[i]); out += '}';
         } else if (max_res) {
-            out += ",\"placement\":"; out += std::to_string(r->node_id[i]);
+            out += ",\"placement\":"; append_u64(out, r->node_id[i]);
         } else if (st == CLS_STATUS_INCONCLUSIVE) {
-            out += ",\"placement\":"; json_string(code, out);
+            out += ",\"placement\":"; out += fx.incon_json;
         }
         out += "}\n";
     }
     return true;
 }
 
+// The blocks back to back in one malloc'ed text; copied on the host pool (a fresh gigabyte of pages is faulted in by
+// whoever writes it first: one thread would spend longer here than the pool spends rendering).
 char *to_malloc(const std::vector<std::string> &parts, uint64_t *len) {
-    size_t n = 0;
-    for (const auto &p : parts) n += p.size();
+    std::vector<size_t> at(parts.size() + 1, 0);
+    for (size_t i = 0; i < parts.size(); ++i) at[i + 1] = at[i] + parts[i].size();
+    const size_t n = at.back();
     char *buf = static_cast<char *>(malloc(n + 1));
     if (!buf) return nullptr;
-    size_t at = 0;
-    for (const auto &p : parts) { memcpy(buf + at, p.data(), p.size()); at += p.size(); }
+    cls::parallel_for(parts.size(), 1, [&](uint64_t p0, uint64_t p1) {
+        for (uint64_t i = p0; i < p1; ++i) memcpy(buf + at[i], parts[i].data(), parts[i].size());
+    });
     buf[n] = 0;
     *len = n;
     return buf;
@@ -466,22 +530,65 @@ int render_blocks(const cls_record_tree *tree, uint64_t n, const uint64_t *heade
     TreeView tv{tree, {}};
     tv.by_id.reserve(tree->n_nodes * 2);
     for (uint64_t i = 0; i < tree->n_nodes; ++i) tv.by_id.emplace(tree->node_id[i], i);   // emplace keeps the first
+    const bool yaml = format == 0;
     constexpr uint64_t kBlock = 2048;
     const uint64_t nblk = (n + kBlock - 1) / kBlock;
     outs.assign(nblk, std::string());
     errs.assign(nblk, std::string());
     std::vector<uint8_t> bad(nblk, 0);
+    Fixed fx;
+    make_fixed_codes(fx);
+    fx.clade_text.assign(tree->n_nodes, std::string());
+    // pass 1: the node behind every IdentityFound record (an id that is not in the tree is reported by pass 3), the
+    // distinct ones collected per task
+    std::vector<uint64_t> wanted;
+    {
+        std::vector<uint8_t> mark(tree->n_nodes, 0);   // written with 1 only, by any task: relaxed atomics
+        cls::parallel_for(n, 16384, [&](uint64_t a, uint64_t b) {
+            for (uint64_t i = a; i < b; ++i) {
+                if (res->status[i] != CLS_STATUS_IDENTITY_FOUND) continue;
+                auto it = tv.by_id.find(res->node_id[i]);
+                if (it != tv.by_id.end()) __atomic_store_n(&mark[it->second], (uint8_t)1, __ATOMIC_RELAXED);
+            }
+        });
+        for (uint64_t i = 0; i < tree->n_nodes; ++i)
+            if (mark[i]) wanted.push_back(i);
+    }
+    // pass 2: their Clade blocks, each rendered once (pre-order: the big subtrees come first)
+    std::vector<uint8_t> bad2(wanted.size(), 0);
+    cls::parallel_for(wanted.size(), 1, [&](uint64_t a, uint64_t b) {
+        for (uint64_t w = a; w < b; ++w) {
+            try {   // nothing may escape a pool thread
+                if (yaml) yaml_clade(tv, wanted[w], 4, "    ", fx.clade_text[wanted[w]]);
+                else json_clade(tv, wanted[w], fx.clade_text[wanted[w]]);
+            } catch (...) {
+                bad2[w] = 1;
+            }
+        }
+    });
+    for (uint8_t x : bad2)
+        if (x) return set_last_error(CLS_ERR_OUT_OF_MEMORY, "host allocation failed while rendering records");
+    // pass 3: the records
     cls::parallel_for(nblk, 1, [&](uint64_t b0, uint64_t b1) {
         std::vector<uint64_t> scratch;
-        CladeCache clade_text;
+        std::string header, code;
         for (uint64_t b = b0; b < b1; ++b) {
             std::string &o = outs[b], &e = errs[b];
-            const uint64_t hi = std::min(n, (b + 1) * kBlock);
+            const uint64_t lo = b * kBlock, hi = std::min(n, (b + 1) * kBlock);
             try {   // nothing may escape a pool thread
-                for (uint64_t i = b * kBlock; i < hi; ++i) {
-                    const std::string header(headers + header_off[i], headers + header_off[i + 1]);
-                    if (!render_one(tv, header, res, i, format == 0, o, e, scratch, clade_text)) bad[b] = 1;
-                }
+                // the block's text in one allocation: Clade blocks + headers + about a hundred bytes of keys per record
+                // (annotations, quoted headers and NoMatch codes, which repeat the header, may still grow it)
+                size_t est = (hi - lo) * 160 + 2 * (size_t)(header_off[hi] - header_off[lo]);
+                for (uint64_t i = lo; i < hi; ++i)
+                    if (res->status[i] == CLS_STATUS_IDENTITY_FOUND) {
+                        auto it = tv.by_id.find(res->node_id[i]);
+                        if (it != tv.by_id.end()) est += fx.clade_text[it->second].size();
+                    }
+                o.reserve(est);
+                for (uint64_t i = lo; i < hi; ++i)
+                    if (!render_one(tv, fx, headers + header_off[i], (size_t)(header_off[i + 1] - header_off[i]), res, i, yaml, o, e,
+                                    scratch, header, code))
+                        bad[b] = 1;
             } catch (...) {
                 bad[b] = 2;
             }

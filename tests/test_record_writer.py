@@ -323,6 +323,35 @@ def test_native_writer_equals_python_on_random_headers(ps, col_tree):
     _check(ps, strings, res, tree)
 
 
+def test_read_name_fast_path_of_the_native_writer(ps, col_tree):
+    """The native writer skips the quoting analysis for headers that start with a letter and hold only [A-Za-z0-9_]
+    (and are not 4 or 5 letters long: null / true / false in their spellings): the same text as the general path, on
+    every status, for word-like headers around that boundary."""
+    import random
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    rng = random.Random(5)
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    tree.annotations = [{"clade": 0, "meta": [ps.Tag("Rank", "genus")]}]
+    ids = [c.id for c in tree.root.walk() if not c.is_leaf()]
+    words = ["null", "Null", "NULL", "nULL", "true", "True", "TRUE", "tRUE", "false", "False", "FALSE", "fALSE", "nulls", "truer", "a", "A", "z9",
+             "read_1", "Read", "reads", "yes", "no", "on", "off", "y", "n", "inf", "nan", "NaN", "e5", "E5", "x0", "_a", "a_", "0a", "a0", "abcd",
+             "abcde", "abcdef", "ab_d", "ab1d", "A_1", "_", "__", "a-b", "a.b", "a b", "a:b", "é", "aé", "~", "q" * 300]
+    alpha = "abcxyzABCXYZ0189_"
+    headers = words + ["".join(rng.choice(alpha) for _ in range(rng.randint(1, 8))) for _ in range(4000)]
+    n = len(headers)
+    statuses = [_lib.STATUS_IDENTITY_FOUND, _lib.STATUS_MAX_RESOLUTION, _lib.STATUS_UNCL_COVERAGE, _lib.STATUS_UNCL_NO_MATCH,
+                _lib.STATUS_UNCL_NO_ROOT, _lib.STATUS_UNCL_NO_INTROSPECTION, _lib.STATUS_INCONCLUSIVE, _lib.STATUS_ERR_TOO_SHORT]
+    for shift in range(2):
+        res = cq.BatchResult(n)
+        res.status[:] = [statuses[(i + shift * 3) % len(statuses)] for i in range(n)]
+        res.node_id[:] = [ids[i % len(ids)] for i in range(n)]
+        res.one[:] = np.arange(n) % 400 - 3
+        res.rest[:] = np.arange(n) % 7
+        res.n_root_matched[:] = np.arange(n) % 233
+        _check(ps, headers, res, tree)
+
+
 @pytest.mark.parametrize("fmt,batch", [("yaml", "100"), ("jsonl", "7"), ("yaml", "0")])
 def test_one_call_place_sequences_around_an_oracle_placer(ps, tmp_path, col_tree, col_flat, fmt, batch):
     """cls_place_sequences itself - path handling, reader, the loop over batches with its result arrays, writer - with
