@@ -679,7 +679,7 @@ uint64_t cls_filter_sequence(const uint8_t *line, uint64_t len, uint8_t *out, ui
 //      cls_fasta_upload applies on the device; one pass over the text. ---------------------------------------------
 struct cls_fasta_text {
     std::vector<uint64_t> header_begin, header_end, offsets;
-    std::vector<uint8_t> bases;
+    std::unique_ptr<uint8_t[]> bases;   // as long as the text; [0, offsets.back()) is written
 };
 
 // str::from_utf8 on one line (BufRead::lines yields Err for a line that is not valid UTF-8: the reader then returns, and
@@ -707,6 +707,56 @@ static bool valid_utf8(const uint8_t *p, uint64_t n) {
     return true;
 }
 
+// cls_fasta_read works on CHUNKS of whole lines, a wave of them at a time on the host pool: a chunk is scanned without
+// knowing the reader's state at its first line - its filtered bases go to a buffer of its own, and every line that the
+// state machine has to see (a header line, a line that is not valid UTF-8) becomes an event carrying the number of bases
+// the chunk had kept before it.  The reader of file_or_stdin.rs:76-116 then runs over the events alone, in file order
+// (a few bytes per record), and the chunks' bases are copied to where that pass says they start.
+namespace {
+
+struct FaEvent {
+    uint64_t begin, end;   // the line, [begin, end)
+    uint64_t kept;         // bases the chunk had kept before this line
+    uint8_t kind;          // 0: header line with text, 1: header line of '>' only, 2: a line that is not valid UTF-8
+};
+struct FaChunk {
+    uint64_t a = 0, b = 0;           // whole lines [a, b) of the text
+    uint64_t kept = 0;               // filtered bases of the chunk
+    std::vector<FaEvent> events;
+    std::vector<uint8_t> bases;      // sized to the chunk (reused by the following waves)
+};
+
+void fasta_scan_chunk(const uint8_t *text, FaChunk &c) {
+    c.events.clear();
+    c.kept = 0;
+    if (c.bases.size() < c.b - c.a) c.bases.resize(c.b - c.a);
+    uint64_t a = c.a;
+    while (a < c.b) {
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(text + a, '\n', c.b - a));
+        uint64_t b = nl ? (uint64_t)(nl - text) : c.b;              // line = [a, b)
+        const uint64_t next = nl ? b + 1 : c.b;
+        if (nl && b > a && text[b - 1] == '\r') --b;                // BufRead::lines: "\r\n" is a terminator, a lone "\r" is not
+        if (b > a) {                                                // empty lines are skipped (:87-89)
+            bool ascii = true;
+            for (uint64_t i = a; i < b && ascii; ++i) ascii = text[i] < 0x80;
+            if (!ascii && !valid_utf8(text + a, b - a)) {           // `line?`: the reader returns here
+                c.events.push_back(FaEvent{a, b, c.kept, 2});
+                return;                                             // nothing after it is ever looked at
+            }
+            if (text[a] == '>') {
+                bool nonempty = false;                              // header = the line minus every '>' (:102)
+                for (uint64_t i = a; i < b && !nonempty; ++i) nonempty = text[i] != '>';
+                c.events.push_back(FaEvent{a, b, c.kept, (uint8_t)(nonempty ? 0 : 1)});
+            } else {
+                c.kept += cls_filter_sequence(text + a, b - a, c.bases.data() + c.kept, c.bases.size() - c.kept);
+            }
+        }
+        a = next;
+    }
+}
+
+}  // namespace
+
 extern "C" int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_text **out, cls_fasta_host_records *rec) {
     using cls::set_last_error;
     if (!out || !rec || (n_bytes && !text)) return set_last_error(CLS_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -715,46 +765,60 @@ extern "C" int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_t
     try {
         auto ft = std::make_unique<cls_fasta_text>();
         ft->offsets.push_back(0);
-        ft->bases.resize(n_bytes ? n_bytes : 1);
-        uint64_t kept = 0;              // filtered bases written so far
+        ft->bases.reset(new uint8_t[n_bytes ? n_bytes : 1]);   // not zero-filled: only [0, offsets.back()) is ever read
+        // chunk size: 2 MiB of text (CLS_FASTA_CHUNK bytes: tests run the stitching over chunks of a few lines)
+        uint64_t chunk_bytes = 2u << 20;
+        if (const char *e = getenv("CLS_FASTA_CHUNK")) { const long long v = atoll(e); if (v > 0) chunk_bytes = (uint64_t)v; }
+        const size_t wave = (size_t)std::max(1, cls::host_threads()) * 2;
+        std::vector<FaChunk> chunks(wave);
+        std::vector<uint64_t> dst(wave);
+        uint64_t kept = 0;              // filtered bases sent or pending so far
         uint64_t rec_start = 0;         // first base of the record being read
         bool have_header = false;       // the reader holds a non-empty header
         uint64_t hb = 0, he = 0;        // its line
         bool stop = false;
-        uint64_t a = 0;
-        while (a < n_bytes && !stop) {
-            const uint8_t *nl = static_cast<const uint8_t *>(memchr(text + a, '\n', n_bytes - a));
-            uint64_t b = nl ? (uint64_t)(nl - text) : n_bytes;      // line = [a, b)
-            const uint64_t next = nl ? b + 1 : n_bytes;
-            if (nl && b > a && text[b - 1] == '\r') --b;            // BufRead::lines: "\r\n" is a terminator, a lone "\r" is not
-            if (b > a) {                                            // empty lines are skipped (:87-89)
-                bool ascii = true;
-                for (uint64_t i = a; i < b && ascii; ++i) ascii = text[i] < 0x80;
-                if (!ascii && !valid_utf8(text + a, b - a)) {       // `line?`: the reader returns here, the pending record is not sent
-                    stop = true;
-                    kept = rec_start;
-                    break;
+        uint64_t at = 0;                // first byte of the next chunk (a line start)
+        while (at < n_bytes && !stop) {
+            size_t nc = 0;
+            for (; nc < wave && at < n_bytes; ++nc) {               // cut the wave's chunks at line ends
+                uint64_t end = n_bytes;
+                if (n_bytes - at > chunk_bytes) {
+                    const uint8_t *nl = static_cast<const uint8_t *>(memchr(text + at + chunk_bytes - 1, '\n', n_bytes - (at + chunk_bytes - 1)));
+                    if (nl) end = (uint64_t)(nl - text) + 1;
                 }
-                if (text[a] == '>') {
+                chunks[nc].a = at; chunks[nc].b = end;
+                at = end;
+            }
+            cls::parallel_for(nc, 1, [&](uint64_t c0, uint64_t c1) {
+                for (uint64_t c = c0; c < c1; ++c) fasta_scan_chunk(text, chunks[c]);
+            });
+            size_t copy_n = 0;                                      // chunks whose bases are kept
+            for (size_t c = 0; c < nc && !stop; ++c) {
+                const uint64_t base = kept;                         // where the chunk's bases start
+                for (const FaEvent &e : chunks[c].events) {
+                    kept = base + e.kept;
+                    if (e.kind == 2) { stop = true; break; }        // the pending record is not sent
                     if (have_header) {                              // send the previous record, even without sequence (:103-108)
                         ft->header_begin.push_back(hb); ft->header_end.push_back(he);
                         ft->offsets.push_back(kept);
                         rec_start = kept;
                     } else if (kept > rec_start) {                  // sequence without header: the reader errors out (:96-100)
                         stop = true;
-                        kept = rec_start;
                         break;
                     }
-                    bool nonempty = false;                          // header = the line minus every '>' (:102)
-                    for (uint64_t i = a; i < b && !nonempty; ++i) nonempty = text[i] != '>';
-                    have_header = nonempty;
-                    hb = a; he = b;
-                } else {
-                    kept += cls_filter_sequence(text + a, b - a, ft->bases.data() + kept, ft->bases.size() - kept);
+                    have_header = e.kind == 0;
+                    hb = e.begin; he = e.end;
                 }
+                dst[c] = base;
+                copy_n = c + 1;
+                if (!stop) kept = base + chunks[c].kept;
             }
-            a = next;
+            cls::parallel_for(copy_n, 1, [&](uint64_t c0, uint64_t c1) {
+                for (uint64_t c = c0; c < c1; ++c)
+                    if (chunks[c].kept) memcpy(ft->bases.get() + dst[c], chunks[c].bases.data(), chunks[c].kept);
+            });
         }
+        if (stop) kept = rec_start;
         if (!stop && have_header && kept > rec_start) {             // the trailing record needs a sequence (:111-113)
             ft->header_begin.push_back(hb); ft->header_end.push_back(he);
             ft->offsets.push_back(kept);
@@ -763,7 +827,7 @@ extern "C" int cls_fasta_read(const uint8_t *text, uint64_t n_bytes, cls_fasta_t
         rec->header_begin = ft->header_begin.data();
         rec->header_end = ft->header_end.data();
         rec->offsets = ft->offsets.data();
-        rec->bases = ft->bases.data();
+        rec->bases = ft->bases.get();
         *out = ft.release();
         return CLS_OK;
     } catch (const std::bad_alloc &) {

@@ -40,7 +40,22 @@ int main(int argc, char **argv) {
         const std::string text = soup(rnd() % 3000, r % 3);
         cls_fasta_text *h = nullptr;
         cls_fasta_host_records rec;
+        setenv("CLS_FASTA_CHUNK", std::to_string(1 + rnd() % 200).c_str(), 1);   // chunks of a few lines: the stitching pass sees every rule
         if (cls_fasta_read(reinterpret_cast<const uint8_t *>(text.data()), text.size(), &h, &rec) != CLS_OK) { ++bad; continue; }
+        {   // ... and gives what one chunk gives
+            setenv("CLS_FASTA_CHUNK", "1000000000", 1);
+            cls_fasta_text *h1 = nullptr;
+            cls_fasta_host_records r1;
+            if (cls_fasta_read(reinterpret_cast<const uint8_t *>(text.data()), text.size(), &h1, &r1) != CLS_OK) { ++bad; continue; }
+            if (r1.n_records != rec.n_records) ++bad;
+            else {
+                for (uint64_t i = 0; i < rec.n_records; ++i)
+                    if (r1.header_begin[i] != rec.header_begin[i] || r1.header_end[i] != rec.header_end[i] || r1.offsets[i + 1] != rec.offsets[i + 1]) ++bad;
+                for (uint64_t j = 0; j < rec.offsets[rec.n_records]; ++j)
+                    if (r1.bases[j] != rec.bases[j]) ++bad;
+            }
+            cls_fasta_text_destroy(h1);
+        }
         for (uint64_t i = 0; i < rec.n_records; ++i) {
             if (rec.offsets[i] > rec.offsets[i + 1] || rec.header_begin[i] >= rec.header_end[i] || rec.header_end[i] > text.size()) ++bad;
             if (text[rec.header_begin[i]] != '>') ++bad;

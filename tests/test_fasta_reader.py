@@ -89,3 +89,86 @@ def test_byte_soup(oracle):
         _check(s)
         if t % 10 == 0:
             assert read_fasta_text(s) == oracle.read_fasta_text(s)
+
+
+def _read_fasta_bytes(raw: bytes):
+    """The reader on BYTES: ``BufRead::lines`` yields ``Err`` for a line that is not valid UTF-8 and the reader returns
+    there (`line?`, file_or_stdin.rs:85) - the records sent so far stand, the pending one is never sent.  Up to that
+    line this is read_fasta_text's state machine."""
+    from classeq2_b200.placement import filter_sequence
+    out, header, parts = [], "", []
+    lines = raw.split(b"\n")
+    terminated = [True] * len(lines)
+    terminated[-1] = False
+    if lines and lines[-1] == b"":
+        lines.pop()
+    for bline, term in zip(lines, terminated):
+        if term and bline.endswith(b"\r"):
+            bline = bline[:-1]
+        if bline == b"":
+            continue
+        try:
+            line = bline.decode("utf-8")
+        except UnicodeDecodeError:
+            return out
+        if line.startswith(">"):
+            if header != "":
+                out.append((header, "".join(parts)))
+                parts = []
+            elif parts:
+                return out
+            header = line.replace(">", "")
+        else:
+            f = filter_sequence(line)
+            if f:
+                parts.append(f)
+    if header != "" and parts:
+        out.append((header, "".join(parts)))
+    return out
+
+
+def _native_records(raw: bytes):
+    from classeq2_b200.placement import read_fasta_native
+    headers, bases, offsets = read_fasta_native(raw)
+    return [(h, bytes(bases[int(offsets[i]):int(offsets[i + 1])]).decode()) for i, h in enumerate(headers)]
+
+
+def test_reader_stops_at_a_line_that_is_not_valid_utf8():
+    s = "ACGTTGCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGATCCCCGGGTACCGAGCTCGAATTC"
+    good = f">a\n{s}\n>b\n{s}\n".encode()
+    cases = [
+        (good + b">c\n" + s.encode() + b"\n\xff\n>d\n" + s.encode() + b"\n", 2),          # the pending record c is not sent
+        (good + b">c \xc3\n" + s.encode() + b"\n", 1),                                    # truncated sequence in a header: b is pending, not sent
+        (good + b"\xed\xa0\x80\n", 1),                                                    # a surrogate
+        (good + b"\xc0\xaf\n", 1),                                                        # an overlong form
+        (good + b"\xf4\x90\x80\x80\n", 1),                                                # beyond U+10FFFF
+        (b"\x80\n" + good, 0),
+        (good + ">é日\n".encode() + s.encode() + b"\n", 3),                               # valid non-ASCII goes on
+    ]
+    for raw, n in cases:
+        got = _native_records(raw)
+        assert got == _read_fasta_bytes(raw) and len(got) == n, (raw[-40:], len(got), n)
+
+
+@pytest.mark.parametrize("chunk", ["1", "3", "17", "64", "1000"])
+def test_chunked_reader_gives_the_same_records_whatever_the_chunk_size(monkeypatch, chunk):
+    """cls_fasta_read scans chunks of whole lines on the host pool and runs the reader's state machine over their events
+    (header lines, invalid lines): with chunks of a few bytes (CLS_FASTA_CHUNK) every record rule meets a chunk boundary -
+    header at the end of a chunk, wrapped sequences over several, the stop conditions inside a later chunk of a wave and
+    in a later wave."""
+    import random
+    monkeypatch.setenv("CLS_FASTA_CHUNK", chunk)
+    monkeypatch.setenv("CLS_HOST_THREADS", "4")
+    rng = random.Random(int(chunk))
+    s = "ACGTTGCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGATCCCCGGGTACCGAGCTCGAATTC"
+    fixed = [f">a\n{s}\n>b\n{s[:30]}\n{s[30:]}\n>c\r\n{s}\r\n", f"{s}\n>a\n{s}\n", f">a\n{s}\n>\n{s}\n>c\n{s}\n", f">a\n>b\n{s}\n>c\n",
+             f">a\n{s}\n>\n>b\n{s}\n", "", "\n\n\n", ">a", f">a\n{s}"] + [f">r{i}\n{s}\n" * 40 for i in range(2)]
+    for t in fixed:
+        assert _native_records(t.encode()) == _read_fasta_bytes(t.encode()), t[:80]
+    alpha = [b"A", b"C", b"G", b"T", b"a", b"n", b">", b">", b"\n", b"\n", b"\n", b"\r", b" ", b"-", b"\r\n", "é".encode(), "ẗ".encode()]
+    for t in range(1500):
+        parts = [rng.choice(alpha) for _ in range(rng.randint(0, 120))]
+        if t % 3 == 0 and parts:                                  # one byte that breaks UTF-8 somewhere
+            parts[rng.randrange(len(parts))] = bytes([rng.choice([0xFF, 0x80, 0xC3, 0xE1])])
+        raw = b"".join(parts)
+        assert _native_records(raw) == _read_fasta_bytes(raw), raw
