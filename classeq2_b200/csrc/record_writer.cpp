@@ -842,8 +842,19 @@ extern "C" void cls_fasta_text_destroy(cls_fasta_text *t) { delete t; }
 //      output path, the knobs -> result / error files.  cls_sequences_open does the path handling of :73-106 and reads the
 //      records (:118-119), cls_sequences_write appends what the closure at :160-249 appends for a batch of results, and
 //      cls_place_sequences strings them together around cls_place_batch. -------------------------------------------------
+// Bytes of a file in a malloc'ed buffer (not zero-filled first, unlike a std::string that is resized).
+struct RawText {
+    char *p = nullptr;
+    size_t n = 0;
+    RawText() = default;
+    RawText(const RawText &) = delete;
+    RawText &operator=(const RawText &) = delete;
+    ~RawText() { free(p); }
+    void clear() { n = 0; }
+};
+
 struct cls_sequences {
-    std::string text;                 // the query file
+    RawText text;                     // the query file
     cls_fasta_text *records = nullptr;
     cls_fasta_host_records rec{};
     std::vector<uint64_t> header_off; // headers with every '>' removed, back to back
@@ -866,10 +877,23 @@ std::string with_extension(const std::string &path, const char *ext) {
     return root + "." + ext;
 }
 
-bool read_whole(FILE *f, std::string &out) {
-    char buf[1 << 16];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+// The whole of `f` (a regular file is read in one piece into a buffer of its size; a pipe grows the buffer as it comes).
+bool read_whole(FILE *f, RawText &out) {
+    out.n = 0;
+    size_t cap = (size_t)1 << 20;
+    struct stat st;
+    if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) cap = (size_t)st.st_size + 1;   // + 1: the read that finds EOF
+    for (;;) {
+        if (out.n == cap || !out.p) {
+            if (out.p) cap += cap / 2;
+            char *q = static_cast<char *>(realloc(out.p, cap));
+            if (!q) throw std::bad_alloc();
+            out.p = q;
+        }
+        const size_t got = fread(out.p + out.n, 1, cap - out.n, f);
+        out.n += got;
+        if (got == 0) break;
+    }
     return !ferror(f);
 }
 
@@ -926,12 +950,20 @@ extern "C" int cls_sequences_open(const char *query_path, const char *out_file, 
         // returns Ok with nothing placed
         struct Close { FILE *f; bool own; ~Close() { if (f && own) fclose(f); } } closer{f, !use_stdin};   // also when an allocation throws
         if (!f || !read_whole(f, s->text)) s->text.clear();
-        const int rc = cls_fasta_read(reinterpret_cast<const uint8_t *>(s->text.data()), s->text.size(), &s->records, &s->rec);
+        const int rc = cls_fasta_read(reinterpret_cast<const uint8_t *>(s->text.p), s->text.n, &s->records, &s->rec);
         if (rc != CLS_OK) return rc;
         s->header_off.assign(s->rec.n_records + 1, 0);
-        for (uint64_t i = 0; i < s->rec.n_records; ++i) {
-            for (uint64_t j = s->rec.header_begin[i]; j < s->rec.header_end[i]; ++j)
-                if (s->text[j] != '>') s->headers += s->text[j];
+        uint64_t hbytes = 0;
+        for (uint64_t i = 0; i < s->rec.n_records; ++i) hbytes += s->rec.header_end[i] - s->rec.header_begin[i];
+        s->headers.reserve(hbytes);
+        for (uint64_t i = 0; i < s->rec.n_records; ++i) {          // the header line minus every '>' (:102)
+            const char *a = s->text.p + s->rec.header_begin[i], *e = s->text.p + s->rec.header_end[i];
+            while (a < e) {
+                const char *g = static_cast<const char *>(memchr(a, '>', (size_t)(e - a)));
+                if (!g) g = e;
+                s->headers.append(a, g);
+                a = g + 1;
+            }
             s->header_off[i + 1] = s->headers.size();
         }
         if (!append_file(s->out_path, nullptr, 0) || !append_file(s->err_path, nullptr, 0))   // both files exist from here on
