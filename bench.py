@@ -666,15 +666,19 @@ def run_sharded(args, rank, world, local_rank, embedded=False):
     torch.cuda.synchronize()
     e2e_s = allred((time.perf_counter() - t0) / max(1, args.steps // 2), dist.ReduceOp.MAX)
 
-    # parity: the replicated index on this GPU must give the very same arrays for a sample of the reads
-    n_chk = min(len(parts[0][1]) - 1, 20000)
+    # parity: the replicated index on this GPU must give the very same arrays for EVERY read of EVERY sub-batch of this
+    # rank (resident and end-to-end results alike); the counts are summed over the ranks
     rep_ix = cq.Index(sm.flat, device=local_rank)
-    want = rep_ix.place_batch((parts[0][0][: int(parts[0][1][n_chk])], parts[0][1][: n_chk + 1]), params)
-    bad = sum(int((getattr(want, f) != getattr(res[0], f)[:n_chk]).sum()) for f, _ in cq.engine.RESULT_DTYPES)
-    bad_e2e = sum(int((getattr(e2e_res[0], f) != getattr(res[0], f)).sum()) for f, _ in cq.engine.RESULT_DTYPES)
+    n_chk = bad = bad_e2e = 0
+    for j, p in enumerate(parts):
+        want = rep_ix.place_batch(p, params)
+        bad += sum(int((getattr(want, f) != getattr(res[j], f)).sum()) for f, _ in cq.engine.RESULT_DTYPES)
+        bad_e2e += sum(int((getattr(e2e_res[j], f) != getattr(res[j], f)).sum()) for f, _ in cq.engine.RESULT_DTYPES)
+        n_chk += len(p[1]) - 1
     rep_info = rep_ix.info()
     rep_ix.close()
     bad = int(allred(float(bad + bad_e2e), dist.ReduceOp.SUM))
+    n_chk = int(allred(float(n_chk), dist.ReduceOp.SUM))
 
     if rank == 0:
         peak, peak_src = measured_peak()
