@@ -8,7 +8,7 @@
 //                        shape: floats as the ryu crate prints them, strings quoted only where libyaml would quote them.
 //                        One block of records per task on the host pool, concatenated in input order.
 //   cls_filter_sequence  SequenceBody::remove_non_iupac_from_sequence (sequence.rs:47-56)
-//   cls_fasta_read       the reader of file_or_stdin.rs:76-116, one pass over the bytes
+//   cls_fasta_read       the reader of file_or_stdin.rs:76-116 (chunks of whole lines scanned on the host pool)
 //   cls_sequences_open / cls_sequences_write / cls_place_sequences
 //                        the use-case itself (mod.rs:43-270): path handling, reader, cls_place_batch, writer
 // The Python mirror (classeq2_b200/placement.py) is the second implementation of all of it; tests hold the two
