@@ -38,6 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K_SIZE = 35
+NOMINAL_HBM_GBS = 8000.0   # B200 HBM3e, nominal (SURVEY.md 8d asks for both denominators; `peak` is the measured one)
 NAMES = {2: "config2: synthetic 1,000-tip tree, 1 kb refs, 1M x 150 bp reads, index replicated",
          3: "config3: synthetic 10k-tip tree, ~600 bp refs, 10M x 150 bp reads sharded over the GPUs, index replicated",
          4: "config4: synthetic 5k-tip tree, 1.5 kb refs, 1M reads of skewed length 150-1550 bp",
@@ -338,6 +339,7 @@ def run_b200(args, rank, world, local_rank):
     launches_per_step = int(index.timing()["kernel_launches"])
     reads_total = allsum(float(n_local))
     lookups_total = allsum(float(lookups_local))
+    alg_bytes_total = allsum(float(alg_bytes_local))
     ms_per_step = ms_total / args.steps
     value = reads_total / (ms_per_step / 1e3)
 
@@ -469,10 +471,15 @@ def run_b200(args, rank, world, local_rank):
             "e2e": e2e, "e2e_one_process_all_gpus": e2e_multi, "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
+                         # both denominators (measured copy bandwidth / nominal HBM3e), and the whole job against N GPUs
+                         "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": achieved / NOMINAL_HBM_GBS,
+                         "aggregate": {"n_gpus": world, "achieved": alg_bytes_total / (ms_per_step / 1e3) / 1e9, "peak": peak * world,
+                                       "frac": alg_bytes_total / (ms_per_step / 1e3) / 1e9 / (peak * world)},
                          "algorithmic_bytes_per_step": alg_bytes_local, "launches_per_step": launches_per_step,
                          "secondary": secondary,
-                         "kernel": "cls::scan2_kernel<4> + cls::descend_kernel<2> (+ cls::scan_kernel<1> over the overflow list), timed together "
-                                   "(config 4: + cls::place_kernel<35,1,1> for the kb-scale classes)",
+                         "kernel": "cls::scan2_kernel<4> + cls::descend16_kernel (+ cls::descend_kernel<2> for reads with more than 16 node sets, "
+                                   "cls::scan_kernel<1> over the overflow list), timed together "
+                                   "(config 4: cls::scanfrag_kernel + cls::gather_kernel + cls::descend_kernel<8> / cls::descend_wide_kernel for the kb-scale classes)",
                          "note": "3782 B per 150 bp read = 38 packed + 232 x 16 probe + 32 result; achieved = algorithmic bytes / CUDA-event "
                                  "time of the whole step (all launches of the step); traffic = DRAM bytes per read of the committed ncu "
                                  "capture x reads per step"},
