@@ -54,3 +54,20 @@ def test_packer_bodies_stay_inside_their_buffers(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
     assert r.returncode == 0 and r.stdout.startswith("bad=0"), (r.returncode, r.stdout, r.stderr[-500:])
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_every_table_entry_is_found_by_the_kernels_probe_walks(tmp_path):
+    """The uploaded k-mer table against the two probe walks of the kernels restated on the host (tests/native/
+    table_probe.cpp): overflow chains, the 8-bit chain filter, free-slot fillers, unreachable bucket keys, shards - on
+    random, clustered and tiny-valued hashes."""
+    exe = str(tmp_path / "table_probe")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-pthread",
+                        os.path.join(HERE, "native", "table_probe.cpp"), os.path.join(CSRC, "index_build.cpp"),
+                        os.path.join(CSRC, "host_api.cpp"), os.path.join(CSRC, "host_pool.cpp"), "-o", exe], capture_output=True, text=True)
+    assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
+    if r.returncode != 0:
+        pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
+    r = subprocess.run([exe, "120"], capture_output=True, text=True, timeout=600)
+    assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
+    assert r.returncode == 0 and r.stdout.startswith("bad=0 "), (r.returncode, r.stdout, r.stderr[-500:])
