@@ -71,3 +71,20 @@ def test_every_table_entry_is_found_by_the_kernels_probe_walks(tmp_path):
     r = subprocess.run([exe, "120"], capture_output=True, text=True, timeout=600)
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
     assert r.returncode == 0 and r.stdout.startswith("bad=0 "), (r.returncode, r.stdout, r.stderr[-500:])
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_closed_model_records_agree_with_the_tree_and_the_sets(tmp_path):
+    """What the descent kernels read for a closed model - pre-order numbering and subtree intervals of the non-leaf nodes,
+    the Euler tour + sparse table behind lca_depth_node, one terminal list per node set - against the tree and the sets
+    themselves on random trees (tests/native/closed_records.cpp)."""
+    exe = str(tmp_path / "closed_records")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-pthread",
+                        os.path.join(HERE, "native", "closed_records.cpp"), os.path.join(CSRC, "index_build.cpp"),
+                        os.path.join(CSRC, "host_api.cpp"), os.path.join(CSRC, "host_pool.cpp"), "-o", exe], capture_output=True, text=True)
+    assert "undefined reference" not in r.stderr and "error:" not in r.stderr, r.stderr[-2000:]   # a real build error is a failure
+    if r.returncode != 0:
+        pytest.skip(f"cannot build with the sanitizers here: {r.stderr[-300:]}")
+    r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
+    assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
+    assert r.returncode == 0 and r.stdout.startswith("bad=0 "), (r.returncode, r.stdout, r.stderr[-500:])
