@@ -7,7 +7,8 @@
 //     depth) of every pair tried;
 //   * a set that holds the root: terminals ascending, the copy of the last one in word 1, and "some terminal lies in
 //     [x, q_end[x])" is exactly "x is a member" for EVERY non-leaf node x (device_types.hpp); a set without the root
-//     carries an empty list.
+//     carries an empty list;
+//   * the same tree with arbitrary (not upward closed) sets: the mini-tree records, decoded back, hold exactly the sets.
 // Built and run by tests/test_text_fuzz.py (ASan + UBSan).
 #include <algorithm>
 #include <cstdint>
@@ -42,7 +43,7 @@ static uint64_t lca_depth_node(const cls::HostIndex &h, uint32_t u, uint32_t v) 
 
 int main(int argc, char **argv) {
     const int rounds = argc > 1 ? atoi(argv[1]) : 60;
-    long bad = 0, sets_checked = 0, pairs = 0, rooted = 0;
+    long bad = 0, sets_checked = 0, pairs = 0, rooted = 0, general = 0;
     for (int r = 0; r < rounds; ++r) {
         const uint64_t n = 1 + rnd() % (r % 5 == 0 ? 600 : 60);
         const bool sparse_ids = r % 3 == 1;
@@ -156,7 +157,67 @@ int main(int argc, char **argv) {
                 if (in_list != (members[s].count(node_of_q[x]) != 0)) ++bad;
             }
         }
+        // ---- the same tree with ARBITRARY node sets (not upward closed): mini-tree records.  Decoded back - entry 0 is the
+        //      root, the children of entry e are e + 1, e + 1 + size(e + 1), ... below e + size(e), an entry names its node
+        //      by its ordinal among the parent's non-leaf children - the PRESENT entries are exactly the set's non-leaf members
+        {
+            std::vector<std::set<uint64_t>> mem2(n_sets);
+            std::vector<uint64_t> off2{0}, ids2;
+            for (uint64_t s2 = 0; s2 < n_sets; ++s2) {
+                const uint64_t picks = rnd() % 7;
+                for (uint64_t p2 = 0; p2 < picks; ++p2) mem2[s2].insert(rnd() % n);
+                if (s2 % 4 == 0) mem2[s2] = members[s2];                     // some closed ones among them
+                for (uint64_t i : mem2[s2]) ids2.push_back(node_id[i]);
+                if (rnd() % 4 == 0) ids2.push_back(0xFFFFFFFFFFull + rnd() % 9);   // an id that is not in the tree: ignored
+                off2.push_back(ids2.size());
+            }
+            if (ids2.empty()) ids2.push_back(0);
+            cls_model_view mv2 = mv;
+            mv2.set_off = off2.data(); mv2.set_node_ids = ids2.data();
+            mv2.flags = r % 2 ? CLS_MODEL_FORCE_GENERAL_SETS : 0;
+            cls::HostIndex g;
+            if (cls::build_host_index(&mv2, g, err) != CLS_OK) { printf("refused: %s\n", err.c_str()); ++bad; continue; }
+            if (mv2.flags && g.closed) ++bad;
+            if (g.closed) continue;                                            // by chance every rooted set was closed
+            const uint64_t gmask = g.n_buckets - 1;
+            for (uint64_t s2 = 0; s2 < n_sets; ++s2) {
+                uint64_t b = eh[s2] & gmask;
+                const cls::Slot *slot = nullptr;
+                for (uint64_t step = 0; step < g.n_buckets && !slot; ++step, b = (b + 1) & gmask)
+                    for (int q = 0; q < 2; ++q)
+                        if (g.table[2 * b + q].hash == eh[s2] && g.table[2 * b + q].set_off != cls::kEmpty) slot = &g.table[2 * b + q];
+                if (!slot || slot->set_off >= g.arena.size()) { ++bad; continue; }
+                const cls::SetWord *rec = &g.arena[slot->set_off];
+                const uint32_t ne = rec[0].y;
+                if (ne == 0 || slot->set_off + 1 + ne > g.arena.size()) { ++bad; continue; }
+                if (((rec[0].x & cls::kSetHasRoot) != 0) != (mem2[s2].count(0) != 0)) ++bad;
+                std::set<uint32_t> present;
+                std::vector<std::pair<uint32_t, uint32_t>> stack{{0u, 0u}};  // (entry, q)
+                uint32_t visited = 0;
+                while (!stack.empty()) {
+                    const auto [e, q] = stack.back();
+                    stack.pop_back();
+                    ++visited;
+                    if (rec[1 + e].x & cls::kPresentBit) present.insert(q);
+                    const uint32_t size = rec[1 + e].y;
+                    if (size == 0 || e + size > ne) { ++bad; break; }
+                    uint32_t last_ord = 0;
+                    bool first = true;
+                    for (uint32_t c = e + 1; c < e + size; c += rec[1 + c].y) {
+                        const uint32_t ord = rec[1 + c].x & ~cls::kPresentBit;
+                        if (rec[1 + c].y == 0 || ord >= g.qnodes[q].child_count || (!first && ord <= last_ord)) { ++bad; break; }
+                        first = false; last_ord = ord;
+                        stack.push_back({c, g.q_child_list[g.qnodes[q].child_first + ord]});
+                    }
+                }
+                if (visited != ne) ++bad;
+                std::set<uint32_t> want;
+                for (uint64_t i : mem2[s2]) if (nonleaf(i)) want.insert(q_of[i]);   // same tree, same q numbering as above
+                if (present != want) ++bad;
+                ++general;
+            }
+        }
     }
-    printf("bad=%ld sets=%ld rooted=%ld lca_pairs=%ld\n", bad, sets_checked, rooted, pairs);
-    return bad == 0 && rooted > 100 && pairs > 1000 ? 0 : 1;
+    printf("bad=%ld sets=%ld rooted=%ld lca_pairs=%ld general_sets=%ld\n", bad, sets_checked, rooted, pairs, general);
+    return bad == 0 && rooted > 100 && pairs > 1000 && general > 100 ? 0 : 1;
 }
