@@ -24,7 +24,7 @@ namespace fakek {
 const void *oracle_model = nullptr;          // set by the test before the first placement
 std::atomic<uint64_t> place_launches{0}, pack_launches{0}, reads_placed{0};
 std::atomic<uint32_t> fail_above_len{0};     // launch_place reports cudaErrorInvalidConfiguration for longer reads (0: never)
-std::atomic<uint64_t> min_scratch_seen{~0ull};
+std::atomic<bool> null_placement{false};     // host-overhead timing: the launch writes "no match" records and returns
 }  // namespace fakek
 
 namespace cls {
@@ -42,6 +42,11 @@ cudaError_t launch_place(const DeviceIndex &, const PlaceParams &pp, const uint3
                          uint32_t n_reads, ResultRec *results, const PlaceGeom &g, int, cudaStream_t, void *scratch, size_t scratch_bytes,
                          uint32_t *n_launches) {
     if (fakek::fail_above_len && g.max_len > fakek::fail_above_len) return cudaErrorInvalidConfiguration;
+    if (fakek::null_placement) {
+        for (uint32_t j = first_read; j < first_read + n_reads; ++j) results[j] = ResultRec{0, 0, 0, 0, 0, 0, CLS_DEV_UNCL_NO_MATCH};
+        if (n_launches) *n_launches += 2;
+        return cudaSuccess;
+    }
     if (!fakek::oracle_model) return cudaErrorUnknown;
     const size_t want = place_scratch_bytes(n_reads, g.max_len, 0, 0);
     if (!scratch || scratch_bytes < want) return cudaErrorInvalidValue;       // the host must have reserved what it was told to
@@ -71,6 +76,7 @@ cudaError_t launch_place(const DeviceIndex &, const PlaceParams &pp, const uint3
 
 cudaError_t launch_ascii_pack(const uint8_t *ascii, const uint64_t *src_off, const ReadDesc *descs, uint32_t first, uint32_t count,
                               uint32_t max_len, uint32_t *words, uint8_t *bad, cudaStream_t) {
+    if (fakek::null_placement) return cudaSuccess;
     for (uint32_t j = first; j < first + count; ++j) {
         const ReadDesc d = descs[j];
         if (d.len > max_len) return cudaErrorInvalidValue;
