@@ -4,7 +4,7 @@
 // (tests/native/fake_kernels.cpp).  The results must equal the oracle's on the caller's ASCII batch, for every way the
 // host side can take: the just-in-time plan of short reads and its fallback, the general plan over many length classes,
 // host / device / mixed packing from pageable and from pinned memory, many chunks, queries decided on the host (too
-// short, invalid base), resident batches, one handle over several devices, concurrent callers on one handle, a failing
+// short, invalid base), resident batches, the host side of the device FASTA ingest against the host reader, one handle over several devices, concurrent callers on one handle, a failing
 // launch.  Built with AddressSanitizer + UBSan and with ThreadSanitizer by tests/test_capi_fake.py.
 #include <atomic>
 #include <cstdint>
@@ -259,6 +259,58 @@ int main(int argc, char **argv) {
         fakek::fail_above_len = 0;
         EXPECT(cls_place_batch(ix, &bv, &params, &rv) == CLS_OK);
         compare(mixed, r, orc, params, "after a failed launch");
+    }
+    // ---- 5b. FASTA ingest "on the device": cls_fasta_upload's host side (record rules over the per-header-line facts,
+    //      header ends, planning) against the host reader cls_fasta_read - same records, same placements -------------------------
+    for (int t = 0; t < 40; ++t) {
+        std::string text;
+        const int n_rec = (int)(rnd() % 60);
+        const char *eol = t % 3 == 1 ? "\r\n" : "\n";
+        for (int i = 0; i < n_rec; ++i) {
+            if (!(t % 7 == 3 && i == 0)) {                                      // t % 7 == 3: sequence before the first header
+                text += rnd() % 9 == 0 ? ">>" : ">";
+                if (rnd() % 11) text += "read_" + std::to_string(i) + (rnd() % 3 ? "" : " some>text");   // else: an empty header
+                text += eol;
+            }
+            const Batch one = make_reads(1, 20, 260, 0);
+            std::string body(one.bases.begin(), one.bases.begin() + (long)one.offsets[1]);
+            if (rnd() % 12 == 0) body.clear();
+            for (size_t a = 0; a < body.size();) {                               // wrapped lines with junk the filter deletes
+                const size_t w = 1 + rnd() % 90;
+                text += body.substr(a, w);
+                if (rnd() % 5 == 0) text += "NN--  xyz";
+                text += eol;
+                if (rnd() % 13 == 0) text += eol;
+                a += w;
+            }
+        }
+        if (t % 5 == 0 && !text.empty()) text.pop_back();                        // no final newline
+        cls_fasta_text *ft = nullptr;
+        cls_fasta_host_records hr{};
+        EXPECT(cls_fasta_read(reinterpret_cast<const uint8_t *>(text.data()), text.size(), &ft, &hr) == CLS_OK);
+        cls_resident_batch *rb = nullptr;
+        cls_fasta_records dr{};
+        EXPECT(cls_fasta_upload(ix, reinterpret_cast<const uint8_t *>(text.data()), text.size(), &rb, &dr) == CLS_OK);
+        if (!ft || !rb) { ++g_bad; continue; }
+        EXPECT(dr.n_records == hr.n_records);
+        Batch b;
+        b.bases.assign(hr.bases, hr.bases + hr.offsets[hr.n_records]);
+        if (b.bases.empty()) b.bases.push_back('A');
+        b.offsets.assign(hr.offsets, hr.offsets + hr.n_records + 1);
+        for (uint64_t i = 0; i < hr.n_records && i < dr.n_records; ++i)
+            EXPECT(dr.header_begin[i] == hr.header_begin[i] && dr.header_end[i] == hr.header_end[i] && dr.length[i] == hr.offsets[i + 1] - hr.offsets[i]);
+        Results r(dr.n_records);
+        cls_result rv = r.view();
+        EXPECT(cls_place_resident(ix, rb, &params, nullptr) == CLS_OK && cls_resident_fetch(ix, rb, nullptr, &rv) == CLS_OK);
+        if (dr.n_records == hr.n_records) compare(b, r, orc, params, "fasta upload");
+        cls_resident_destroy(rb);
+        cls_fasta_text_destroy(ft);
+    }
+    {   // a non-ASCII byte: refused, the host reader takes such files
+        const std::string text = ">a\nACGT\xC3\xA9" "ACGT\n";
+        cls_resident_batch *rb = nullptr;
+        cls_fasta_records dr{};
+        EXPECT(cls_fasta_upload(ix, reinterpret_cast<const uint8_t *>(text.data()), text.size(), &rb, &dr) == CLS_ERR_UNSUPPORTED && !rb);
     }
     }
     // ---- 6. concurrent callers on one handle (per-call workspaces) -------------------------------------------------------------

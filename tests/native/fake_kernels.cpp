@@ -4,7 +4,8 @@
 //                       oracle (oracle/classeq_oracle.cpp, linked into the test) - what the placement kernels compute,
 //                       by other means; the result records land where the kernels would write them;
 //   launch_ascii_pack   pack_kernels.cu's job on the host (ASCII -> 2-bit words at the descriptors' offsets, bad flags);
-//   the routed / FASTA / trace launches are not part of these tests and report an error.
+//   launch_fasta_*      fasta_kernels.cu's passes as serial walks (the host side of cls_fasta_upload is what is tested);
+//   the routed / trace launches are not part of these tests and report an error.
 // Everything the HOST side hands over - word offsets, descriptors, source offsets, chunk ranges, scratch sizes - has to
 // be right for the results to equal the oracle's on the caller's ASCII batch.
 #include <atomic>
@@ -107,10 +108,53 @@ cudaError_t launch_place_routed(const DeviceIndex &, const PlaceParams &, const 
                                 size_t) { return cudaErrorUnknown; }
 cudaError_t launch_hash_only(const uint32_t *, uint32_t, uint32_t, uint64_t *, cudaStream_t) { return cudaErrorUnknown; }
 
+// fasta_kernels.cu's three passes as one serial walk each: what cls_fasta_upload's host side consumes is the totals,
+// the per-header-line facts and the compacted 2-bit codes - the tile summaries in between stay unused here.
 size_t fasta_tile_bytes() { return 64; }
 uint32_t fasta_n_tiles(uint64_t n) { return (uint32_t)((n + 4095) / 4096); }
-cudaError_t launch_fasta_scan(const uint8_t *, uint64_t, void *, TileBase *, TileBase *, uint32_t *, cudaStream_t) { return cudaErrorUnknown; }
-cudaError_t launch_fasta_write(const uint8_t *, uint64_t, const TileBase *, uint8_t *, uint64_t *, uint64_t *, uint32_t *, cudaStream_t) { return cudaErrorUnknown; }
-cudaError_t launch_fasta_pack(const uint8_t *, const uint64_t *, const uint32_t *, const uint32_t *, uint32_t, uint32_t *, int, cudaStream_t) { return cudaErrorUnknown; }
+namespace {
+bool fasta_is_base(uint8_t c) { const uint8_t u = c & 0xDFu; return c < 0x80 && (u == 'A' || u == 'C' || u == 'G' || u == 'T'); }
+template <class H, class B>
+void fasta_walk(const uint8_t *text, uint64_t n, H on_header_byte, B on_base) {
+    bool at_start = true, in_hdr = false;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t c = text[i];
+        const bool line_start = at_start;
+        if (at_start) in_hdr = c == '>';
+        if (in_hdr) on_header_byte(i, c, line_start);
+        else if (fasta_is_base(c)) on_base(c);
+        at_start = c == '\n';
+    }
+}
+}  // namespace
+cudaError_t launch_fasta_scan(const uint8_t *text, uint64_t n, void *, TileBase *, TileBase *totals, uint32_t *non_ascii, cudaStream_t) {
+    uint64_t kept = 0, hdrs = 0;
+    for (uint64_t i = 0; i < n; ++i) if (text[i] & 0x80u) *non_ascii = 1;
+    fasta_walk(text, n, [&](uint64_t, uint8_t, bool line_start) { hdrs += line_start; }, [&](uint8_t) { ++kept; });
+    *totals = TileBase{kept, hdrs, 0u, 0u};
+    return cudaSuccess;
+}
+cudaError_t launch_fasta_write(const uint8_t *text, uint64_t n, const TileBase *, uint8_t *codes, uint64_t *hdr_pos, uint64_t *hdr_kept,
+                               uint32_t *hdr_flag, cudaStream_t) {
+    uint64_t kept = 0, hdrs = 0;
+    fasta_walk(text, n,
+               [&](uint64_t i, uint8_t c, bool line_start) {
+                   if (line_start) { hdr_pos[hdrs] = i; hdr_kept[hdrs] = kept; ++hdrs; }
+                   const bool terminator = c == '\n' || (c == '\r' && i + 1 < n && text[i + 1] == '\n');
+                   if (c != '>' && !terminator) hdr_flag[hdrs - 1] |= 1u;
+               },
+               [&](uint8_t c) { codes[kept++] = (uint8_t)((c >> 1) & 3u); });
+    return cudaSuccess;
+}
+cudaError_t launch_fasta_pack(const uint8_t *codes, const uint64_t *src, const uint32_t *word_off, const uint32_t *len, uint32_t n_records,
+                              uint32_t *words, int, cudaStream_t) {
+    for (uint32_t r = 0; r < n_records; ++r)
+        for (uint32_t w = 0; w < (len[r] + 15) / 16; ++w) {
+            uint32_t v = 0;
+            for (uint32_t j = 16 * w; j < len[r] && j < 16 * w + 16; ++j) v |= (uint32_t)codes[src[r] + j] << (2 * (j % 16));
+            words[word_off[r] + w] = v;
+        }
+    return cudaSuccess;
+}
 
 }  // namespace cls

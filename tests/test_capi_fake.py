@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(ROOT, "classeq2_b200", "csrc")
 FAKE = os.path.join(HERE, "native", "fakecuda")
 SOURCES = [(os.path.join(CSRC, "capi.cu"), True)] + [(os.path.join(CSRC, f), False) for f in
-                                                      ("index_build.cpp", "host_api.cpp", "host_pack.cpp", "host_pool.cpp")] + \
+                                                      ("index_build.cpp", "host_api.cpp", "host_pack.cpp", "host_pool.cpp", "record_writer.cpp")] + \
           [(os.path.join(HERE, "native", f), False) for f in ("capi_fake_main.cpp", "fake_kernels.cpp")]
 
 
