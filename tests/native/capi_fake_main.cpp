@@ -21,7 +21,7 @@
 
 namespace fakek {
 extern const void *oracle_model;
-extern std::atomic<uint64_t> place_launches, pack_launches, reads_placed;
+extern std::atomic<uint64_t> place_launches, pack_launches, reads_placed, async_errors;
 extern std::atomic<uint32_t> fail_above_len;
 }  // namespace fakek
 extern "C" {
@@ -114,6 +114,9 @@ int main(int argc, char **argv) {
     cls_model_view tree{};
     tree.k_size = 35; tree.m_size = 4;
     tree.n_nodes = node_id.size(); tree.node_id = node_id.data(); tree.node_kind = kind.data(); tree.child_off = child_off.data(); tree.child_idx = child_idx.data();
+    static const bool trace = getenv("CAPI_FAKE_TRACE") != nullptr;
+#define STEP(what) do { if (trace) fprintf(stderr, "[capi_fake] %s\n", what); } while (0)
+    STEP("model build");
     cls_built_model *bm = nullptr;
     if (cls_model_build(&tree, tip_node.size(), tip_node.data(), refs.bases.data(), refs.offsets.data(), &bm) != CLS_OK) { printf("model build failed: %s\n", cls_last_error()); return 1; }
     cls_model_view model{};
@@ -142,6 +145,7 @@ int main(int argc, char **argv) {
     cls_params params;
     cls_params_default(&params);
     cls_index *ix = nullptr;
+    STEP("index create");
     if (cls_index_create(&model, 0, &ix) != CLS_OK) { printf("index: %s\n", cls_last_error()); return 1; }
 
     // ---- 1. short reads (the just-in-time plan), every packing mode, pageable and pinned bases ---------------------------
@@ -154,6 +158,7 @@ int main(int argc, char **argv) {
             cudaHostAlloc(&pinned, shorts.bases.size(), cudaHostAllocDefault);
             memcpy(pinned, shorts.bases.data(), shorts.bases.size());
             cls_set_pack_mode(mode);
+            STEP("1. short reads");
             Results r(shorts.n());
             cls_result rv = r.view();
             const cls_batch bv = shorts.view(pin ? static_cast<const uint8_t *>(pinned) : nullptr);
@@ -313,6 +318,7 @@ int main(int argc, char **argv) {
         EXPECT(cls_fasta_upload(ix, reinterpret_cast<const uint8_t *>(text.data()), text.size(), &rb, &dr) == CLS_ERR_UNSUPPORTED && !rb);
     }
     }
+    STEP("6. concurrent callers");
     // ---- 6. concurrent callers on one handle (per-call workspaces) -------------------------------------------------------------
     {
         std::vector<Batch> bs;
@@ -334,6 +340,7 @@ int main(int argc, char **argv) {
         for (int t = 0; t < 4; ++t) compare(bs[t], rs[t], orc, params, "concurrent callers");
     }
     cls_index_destroy(ix);
+    STEP("7. three devices");
     // ---- 7. one handle over three devices: the batch is cut by bases, the parts run side by side ----------------------------------
     {
         cls_index *multi = nullptr;
@@ -358,6 +365,7 @@ int main(int argc, char **argv) {
     fakek::oracle_model = nullptr;
     orc_model_destroy(orc);
     cls_built_model_destroy(bm);
+    EXPECT(fakek::async_errors == 0);
     EXPECT(fakecuda::live_allocs() == 0);                                                // every device / pinned buffer was released
     printf("bad=%ld reads=%ld place_launches=%llu pack_launches=%llu\n", g_bad, g_reads, (unsigned long long)fakek::place_launches.load(),
            (unsigned long long)fakek::pack_launches.load());

@@ -25,6 +25,7 @@ namespace fakek {
 const void *oracle_model = nullptr;          // set by the test before the first placement
 std::atomic<uint64_t> place_launches{0}, pack_launches{0}, reads_placed{0};
 std::atomic<uint32_t> fail_above_len{0};     // launch_place reports cudaErrorInvalidConfiguration for longer reads (0: never)
+std::atomic<uint64_t> async_errors{0};        // a launch body met a descriptor its launch does not cover
 std::atomic<bool> null_placement{false};     // host-overhead timing: the launch writes "no match" records and returns
 }  // namespace fakek
 
@@ -39,61 +40,69 @@ PlaceGeom make_place_geom(uint32_t max_len, uint32_t, uint32_t max_fanout) {
 
 size_t place_scratch_bytes(uint32_t n_reads, uint32_t max_len, uint32_t, uint32_t) { return 64 + (size_t)n_reads * 8 + max_len; }
 
+// A launch is checked here and runs IN STREAM ORDER (fakecuda::enqueue: on the stream's worker thread in the
+// asynchronous mode of the fake runtime), like a kernel.
 cudaError_t launch_place(const DeviceIndex &, const PlaceParams &pp, const uint32_t *packed, const ReadDesc *reads, uint32_t first_read,
-                         uint32_t n_reads, ResultRec *results, const PlaceGeom &g, int, cudaStream_t, void *scratch, size_t scratch_bytes,
+                         uint32_t n_reads, ResultRec *results, const PlaceGeom &g, int, cudaStream_t stream, void *scratch, size_t scratch_bytes,
                          uint32_t *n_launches) {
     if (fakek::fail_above_len && g.max_len > fakek::fail_above_len) return cudaErrorInvalidConfiguration;
     if (fakek::null_placement) {
-        for (uint32_t j = first_read; j < first_read + n_reads; ++j) results[j] = ResultRec{0, 0, 0, 0, 0, 0, CLS_DEV_UNCL_NO_MATCH};
+        fakecuda::enqueue(stream, [=] { for (uint32_t j = first_read; j < first_read + n_reads; ++j) results[j] = ResultRec{0, 0, 0, 0, 0, 0, CLS_DEV_UNCL_NO_MATCH}; });
         if (n_launches) *n_launches += 2;
         return cudaSuccess;
     }
-    if (!fakek::oracle_model) return cudaErrorUnknown;
+    const void *model = fakek::oracle_model;
+    if (!model) return cudaErrorUnknown;
     const size_t want = place_scratch_bytes(n_reads, g.max_len, 0, 0);
     if (!scratch || scratch_bytes < want) return cudaErrorInvalidValue;       // the host must have reserved what it was told to
-    static_cast<volatile char *>(scratch)[want - 1] = 1;                        // ... really (ASan looks at it)
-    std::vector<uint8_t> bases;
-    std::vector<uint64_t> offsets{0};
-    for (uint32_t j = first_read; j < first_read + n_reads; ++j) {
-        const ReadDesc d = reads[j];
-        if (d.len > g.max_len) return cudaErrorInvalidValue;                    // the geometry of a launch covers its longest read
-        for (uint32_t i = 0; i < d.len; ++i) bases.push_back((uint8_t)"ACTG"[(packed[d.word_off + i / 16] >> (2 * (i % 16))) & 3u]);
-        offsets.push_back(bases.size());
-    }
-    if (bases.empty()) bases.push_back('A');
-    std::vector<uint8_t> status(n_reads);
-    std::vector<uint64_t> node(n_reads);
-    std::vector<int32_t> one(n_reads), rest(n_reads);
-    std::vector<uint32_t> nq(n_reads), nm(n_reads), nr(n_reads), it(n_reads);
-    orc_place_batch(fakek::oracle_model, bases.data(), offsets.data(), n_reads, pp.max_iterations, pp.min_match_coverage, pp.remove_intersection,
-                    n_reads >= 256 ? 4 : 1, status.data(), node.data(), one.data(), rest.data(), nq.data(), nm.data(), nr.data(), it.data());
-    for (uint32_t j = 0; j < n_reads; ++j)
-        results[first_read + j] = ResultRec{node[j], one[j], rest[j], nm[j], nr[j], it[j], status[j]};
+    const uint32_t max_len = g.max_len;
+    fakecuda::enqueue(stream, [=] {
+        static_cast<volatile char *>(scratch)[want - 1] = 1;                    // the scratch is really there (ASan), and nobody else uses it now (TSan)
+        std::vector<uint8_t> bases;
+        std::vector<uint64_t> offsets{0};
+        for (uint32_t j = first_read; j < first_read + n_reads; ++j) {
+            const ReadDesc d = reads[j];
+            if (d.len > max_len) { ++fakek::async_errors; return; }             // the geometry of a launch covers its longest read
+            for (uint32_t i = 0; i < d.len; ++i) bases.push_back((uint8_t)"ACTG"[(packed[d.word_off + i / 16] >> (2 * (i % 16))) & 3u]);
+            offsets.push_back(bases.size());
+        }
+        if (bases.empty()) bases.push_back('A');
+        std::vector<uint8_t> status(n_reads);
+        std::vector<uint64_t> node(n_reads);
+        std::vector<int32_t> one(n_reads), rest(n_reads);
+        std::vector<uint32_t> nq(n_reads), nm(n_reads), nr(n_reads), it(n_reads);
+        orc_place_batch(model, bases.data(), offsets.data(), n_reads, pp.max_iterations, pp.min_match_coverage, pp.remove_intersection,
+                        n_reads >= 256 ? 4 : 1, status.data(), node.data(), one.data(), rest.data(), nq.data(), nm.data(), nr.data(), it.data());
+        for (uint32_t j = 0; j < n_reads; ++j)
+            results[first_read + j] = ResultRec{node[j], one[j], rest[j], nm[j], nr[j], it[j], status[j]};
+        fakek::reads_placed += n_reads;
+    });
     if (n_launches) *n_launches += 2;
     ++fakek::place_launches;
-    fakek::reads_placed += n_reads;
     return cudaSuccess;
 }
 
 cudaError_t launch_ascii_pack(const uint8_t *ascii, const uint64_t *src_off, const ReadDesc *descs, uint32_t first, uint32_t count,
-                              uint32_t max_len, uint32_t *words, uint8_t *bad, cudaStream_t) {
+                              uint32_t max_len, uint32_t *words, uint8_t *bad, cudaStream_t stream) {
     if (fakek::null_placement) return cudaSuccess;
-    for (uint32_t j = first; j < first + count; ++j) {
-        const ReadDesc d = descs[j];
-        if (d.len > max_len) return cudaErrorInvalidValue;
-        const uint8_t *s = ascii + src_off[j];
-        uint8_t any_bad = 0;
-        for (uint32_t w = 0; w < (d.len + 15) / 16; ++w) {
-            uint32_t v = 0;
-            for (uint32_t i = 16 * w; i < d.len && i < 16 * w + 16; ++i) {
-                const uint8_t c = s[i] & 0xDF;
-                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') any_bad = 1;
-                v |= ((uint32_t)(s[i] >> 1) & 3u) << (2 * (i % 16));
+    fakecuda::enqueue(stream, [=] {
+        for (uint32_t j = first; j < first + count; ++j) {
+            const ReadDesc d = descs[j];
+            if (d.len > max_len) { ++fakek::async_errors; return; }
+            const uint8_t *s = ascii + src_off[j];
+            uint8_t any_bad = 0;
+            for (uint32_t w = 0; w < (d.len + 15) / 16; ++w) {
+                uint32_t v = 0;
+                for (uint32_t i = 16 * w; i < d.len && i < 16 * w + 16; ++i) {
+                    const uint8_t c = s[i] & 0xDF;
+                    if (c != 'A' && c != 'C' && c != 'G' && c != 'T') any_bad = 1;
+                    v |= ((uint32_t)(s[i] >> 1) & 3u) << (2 * (i % 16));
+                }
+                words[d.word_off + w] = v;
             }
-            words[d.word_off + w] = v;
+            if (any_bad) bad[j] = 1;
         }
-        if (any_bad) bad[j] = 1;
-    }
+    });
     ++fakek::pack_launches;
     return cudaSuccess;
 }

@@ -1,25 +1,86 @@
 // TEST INFRASTRUCTURE.  A stand-in for <cuda_runtime.h> that lets the HOST side of the library (classeq2_b200/csrc/
 // capi.cu: planning, packing, chunked pipeline, scatter, multi-device fan-out, workspaces) compile with g++ and run
 // without a GPU, under AddressSanitizer / ThreadSanitizer.  "Device" memory is malloc'ed host memory (so a copy that
-// runs past a device buffer is an ASan report), every "asynchronous" call completes before it returns (stream order
-// cannot be violated here - what is checked is the host logic, its buffer sizes and its threads), events carry the
-// host clock.  The kernels' launch functions are supplied by tests/native/fake_kernels.cpp.  Nothing of this is ever
-// linked into the product.
+// runs past a device buffer is an ASan report), events carry the host clock.  Two modes:
+//   * synchronous (default): every "asynchronous" call completes before it returns - the host logic, its buffer sizes
+//     and its threads are what is checked;
+//   * FAKE_CUDA_ASYNC=1: every stream is a worker thread that runs what was enqueued on it in order - copies, memsets,
+//     the fake kernels, event records, waits for events of other streams - while the host thread goes on.  A missing
+//     dependency between streams, or between a stream and the host (a buffer reused while a copy may still read it, a
+//     result read before its copy has completed), is then a DATA RACE between threads, which ThreadSanitizer reports,
+//     or a wrong result.  cudaFree / cudaFreeHost wait for every stream first, as the real ones synchronise the device.
+// The kernels' launch functions are supplied by tests/native/fake_kernels.cpp.  Nothing of this is ever linked into the
+// product.
 #pragma once
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <set>
+#include <thread>
 
 typedef int cudaError_t;
 enum : int { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorInvalidConfiguration = 9,
              cudaErrorInvalidDevice = 101, cudaErrorUnknown = 999 };
-struct FakeCudaStream { int device; };
-struct FakeCudaEvent { double t_ms; };
+namespace fakecuda {
+inline bool async() { static const bool a = [] { const char *e = getenv("FAKE_CUDA_ASYNC"); return e && atoi(e) != 0; }(); return a; }
+inline double now_ms() { using namespace std::chrono; return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count(); }
+// One cudaEventRecord: done once the stream reaches it.
+struct Ticket {
+    std::mutex m;
+    std::condition_variable cv;
+    bool done = false;
+    double t_ms = 0.0;
+    void signal() { { std::lock_guard<std::mutex> lk(m); done = true; t_ms = now_ms(); } cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return done; }); }
+};
+}  // namespace fakecuda
+struct FakeCudaStream {
+    int device = 0;
+    std::mutex m;
+    std::condition_variable cv_work, cv_idle;
+    std::deque<std::function<void()>> q;
+    bool busy = false, stop = false;
+    std::thread worker;
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || !q.empty(); });
+            if (q.empty()) return;                 // stop, and nothing left
+            std::function<void()> f = std::move(q.front());
+            q.pop_front();
+            busy = true;
+            lk.unlock();
+            f();
+            lk.lock();
+            busy = false;
+            if (q.empty()) cv_idle.notify_all();
+        }
+    }
+    void push(std::function<void()> f) { { std::lock_guard<std::mutex> lk(m); q.push_back(std::move(f)); } cv_work.notify_one(); }
+    void drain() { std::unique_lock<std::mutex> lk(m); cv_idle.wait(lk, [&] { return q.empty() && !busy; }); }
+};
+struct FakeCudaEvent { std::shared_ptr<fakecuda::Ticket> cur; double t_ms = 0.0; };
 typedef FakeCudaStream *cudaStream_t;
 typedef FakeCudaEvent *cudaEvent_t;
+namespace fakecuda {
+inline std::mutex &streams_mu() { static std::mutex m; return m; }
+inline std::set<FakeCudaStream *> &streams() { static std::set<FakeCudaStream *> s; return s; }
+// Runs `f` in stream order: on the stream's worker (async mode, a real stream) or right here.
+inline void enqueue(cudaStream_t s, std::function<void()> f) { if (async() && s) s->push(std::move(f)); else f(); }
+inline void sync_all_streams() {
+    if (!async()) return;
+    std::set<FakeCudaStream *> all;
+    { std::lock_guard<std::mutex> lk(streams_mu()); all = streams(); }
+    for (FakeCudaStream *s : all) s->drain();
+}
+}  // namespace fakecuda
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
 enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
@@ -35,7 +96,6 @@ inline std::mutex &mu() { static std::mutex m; return m; }
 inline std::map<const char *, size_t> &pinned() { static std::map<const char *, size_t> m; return m; }   // cudaHostAlloc'ed ranges
 inline int device_count() { const char *e = getenv("FAKE_CUDA_DEVICES"); const int n = e ? atoi(e) : 4; return n > 0 ? n : 4; }
 inline int &current() { static thread_local int d = 0; return d; }
-inline double now_ms() { using namespace std::chrono; return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count(); }
 inline long &live_allocs() { static long n = 0; return n; }    // device + pinned allocations not yet freed (leak check of the tests)
 inline bool &skip_copies() { static bool b = false; return b; }   // host-overhead timing (tools/micro/host_floor.cpp): a DMA costs the host nothing
 }  // namespace fakecuda
@@ -50,7 +110,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) {
     return cudaSuccess;
 }
 inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
-inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { fakecuda::sync_all_streams(); return cudaSuccess; }
 inline cudaError_t cudaMalloc(void **p, size_t n) {
     *p = malloc(n ? n : 1);
     if (!*p) return cudaErrorMemoryAllocation;
@@ -59,6 +119,7 @@ inline cudaError_t cudaMalloc(void **p, size_t n) {
     return cudaSuccess;
 }
 inline cudaError_t cudaFree(void *p) {
+    fakecuda::sync_all_streams();
     if (p) { std::lock_guard<std::mutex> lk(fakecuda::mu()); --fakecuda::live_allocs(); }
     free(p);
     return cudaSuccess;
@@ -72,6 +133,7 @@ inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) {
     return cudaSuccess;
 }
 inline cudaError_t cudaFreeHost(void *p) {
+    fakecuda::sync_all_streams();
     if (p) { std::lock_guard<std::mutex> lk(fakecuda::mu()); fakecuda::pinned().erase(static_cast<const char *>(p)); --fakecuda::live_allocs(); }
     free(p);
     return cudaSuccess;
@@ -87,19 +149,60 @@ inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void
     return cudaSuccess;
 }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memcpy(d, s, n); return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n && !fakecuda::skip_copies()) memcpy(d, s, n); return cudaSuccess; }
+// (the blocking calls and the NULL stream run on the calling thread: the library's pipelines use their own non-blocking streams)
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st) {
+    if (n && !fakecuda::skip_copies()) fakecuda::enqueue(st, [d, s, n] { memcpy(d, s, n); });
+    return cudaSuccess;
+}
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new FakeCudaStream{fakecuda::current()}; return cudaSuccess; }
-inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
-inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new FakeCudaEvent{0.0}; return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { if (n) fakecuda::enqueue(st, [d, v, n] { memset(d, v, n); }); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+    FakeCudaStream *st = new FakeCudaStream;
+    st->device = fakecuda::current();
+    if (fakecuda::async()) {
+        st->worker = std::thread([st] { st->loop(); });
+        std::lock_guard<std::mutex> lk(fakecuda::streams_mu());
+        fakecuda::streams().insert(st);
+    }
+    *s = st;
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { if (fakecuda::async() && s) s->drain(); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    if (!s) return cudaSuccess;
+    if (fakecuda::async()) {
+        s->drain();
+        { std::lock_guard<std::mutex> lk(s->m); s->stop = true; }
+        s->cv_work.notify_all();
+        s->worker.join();
+        std::lock_guard<std::mutex> lk(fakecuda::streams_mu());
+        fakecuda::streams().erase(s);
+    }
+    delete s;
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new FakeCudaEvent; return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = fakecuda::now_ms(); return cudaSuccess; }
-inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
+// The event's fields belong to the host thread that uses it (as in the library: one workspace, one caller at a time);
+// what crosses to the stream threads is the ticket of one record.
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+    auto t = std::make_shared<fakecuda::Ticket>();
+    e->cur = t;
+    fakecuda::enqueue(s, [t] { t->signal(); });
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { if (e->cur) e->cur->wait(); return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    if (std::shared_ptr<fakecuda::Ticket> t = e->cur) fakecuda::enqueue(s, [t] { t->wait(); });   // the record seen at the time of the call
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    if (!a->cur || !b->cur) return cudaErrorInvalidValue;
+    a->cur->wait(); b->cur->wait();
+    *ms = (float)(b->cur->t_ms - a->cur->t_ms);
+    return cudaSuccess;
+}
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

@@ -5,8 +5,8 @@ callers, a failing launch - end to end WITHOUT a GPU.  capi.cu is compiled with 
 (tests/native/fakecuda/cuda_runtime.h: device memory is host memory, every call completes before it returns); the
 placement launch unpacks the reads it is handed and gives them to the C++ oracle (tests/native/fake_kernels.cpp); the
 results must equal the oracle's on the caller's ASCII batch (tests/native/capi_fake_main.cpp).  Run under
-AddressSanitizer + UBSan (every scenario: a copy past a "device" buffer is a report) and under ThreadSanitizer (the
-scenarios with several host threads).  The kernels themselves are what the ``-m gpu`` tests are for."""
+AddressSanitizer + UBSan (a copy past a "device" buffer is a report) and, with every stream of the fake runtime a
+worker thread, under ThreadSanitizer (a missing stream dependency is a data race).  The kernels themselves are what the ``-m gpu`` tests are for."""
 import os
 import shutil
 import subprocess
@@ -51,19 +51,44 @@ def _build(tmp_path, name, san):
     return exe
 
 
-@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-def test_place_batch_host_side_equals_the_oracle_under_asan(tmp_path):
-    exe = _build(tmp_path, "asan", ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"])
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+@pytest.fixture(scope="module")
+def runs(tmp_path_factory):
+    """Both builds side by side, then both runs side by side (the oracle dominates either): {name: CompletedProcess}."""
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    tmp = tmp_path_factory.mktemp("capi_fake")
+    exes = {"asan": _build(tmp, "asan", ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]),
+            "tsan": _build(tmp, "tsan", ["-fsanitize=thread"])}
+    # asan: the synchronous runtime (host logic, buffer sizes); tsan: every stream a worker thread (FAKE_CUDA_ASYNC=1) - a
+    # missing dependency between streams, or between a stream and the host, is a data race there
+    procs = {"asan": subprocess.Popen([exes["asan"]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True),
+             "tsan": subprocess.Popen([exes["tsan"]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                      env=dict(os.environ, FAKE_CUDA_ASYNC="1"))}
+    out = {}
+    for name, p in procs.items():
+        try:
+            so, se = p.communicate(timeout=1200)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            so, se = p.communicate()
+            se += "\n[timed out]"
+        out[name] = subprocess.CompletedProcess(p.args, p.returncode, so, se)
+    return out
+
+
+def test_place_batch_host_side_equals_the_oracle_under_asan(runs):
+    r = runs["asan"]
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:4000]
     assert r.returncode == 0 and r.stdout.startswith("bad=0 "), (r.returncode, r.stdout, r.stderr[-1500:])
 
 
-@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-def test_place_batch_host_threads_are_clean_under_tsan(tmp_path):
-    exe = _build(tmp_path, "tsan", ["-fsanitize=thread"])
-    r = subprocess.run([exe, "threads"], capture_output=True, text=True, timeout=900)
+def test_place_batch_streams_and_threads_are_race_free_under_tsan(runs):
+    """Every scenario again with the streams of the fake runtime as worker threads: copies, fake kernels and event waits run
+    in stream order next to the host thread, so the dependencies of the three-stream pipeline (copies in -> kernels ->
+    copies out, the staging ring, the scratch buffers, the scatter of finished chunks) are what keeps this free of races.
+    Dropping the kernel stream's wait for the copy-in of the later chunks is reported here (checked by mutation)."""
+    r = runs["tsan"]
     if "FATAL: ThreadSanitizer" in r.stderr and "unexpected memory mapping" in r.stderr:
         pytest.skip("ThreadSanitizer cannot map its shadow memory in this container")
-    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+    assert "WARNING: ThreadSanitizer" not in r.stderr and "[timed out]" not in r.stderr, r.stderr[:4000]
     assert r.returncode == 0 and r.stdout.startswith("bad=0 "), (r.returncode, r.stdout, r.stderr[-1500:])
