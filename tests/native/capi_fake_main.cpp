@@ -204,11 +204,14 @@ int main(int argc, char **argv) {
         cls_resident_batch *rb = nullptr;
         EXPECT(cls_batch_upload(ix, &bv, &rb) == CLS_OK);
         if (rb) {
-            EXPECT(cls_place_resident(ix, rb, &p2, nullptr) == CLS_OK && cls_place_resident(ix, rb, &p2, nullptr) == CLS_OK);
+            cudaStream_t user = nullptr;                                  // the caller's stream (bench.py hands a torch stream over)
+            cudaStreamCreateWithFlags(&user, cudaStreamNonBlocking);
+            EXPECT(cls_place_resident(ix, rb, &p2, user) == CLS_OK && cls_place_resident(ix, rb, &p2, user) == CLS_OK);
             Results r2(mixed.n());
             cls_result rv2 = r2.view();
-            EXPECT(cls_resident_fetch(ix, rb, nullptr, &rv2) == CLS_OK);
+            EXPECT(cls_resident_fetch(ix, rb, user, &rv2) == CLS_OK);
             compare(mixed, r2, orc, p2, "resident");
+            cudaStreamDestroy(user);
             EXPECT(cls_resident_bytes(rb) > 0);
             cls_resident_destroy(rb);
         }
