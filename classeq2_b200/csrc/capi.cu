@@ -342,10 +342,12 @@ int launch_classes(cls_index *ix, const PackedLayout &lay, const cls_params *par
 
 // Fields decided on the host (n_query_kmers of every query; everything for queries that never
 // reach the device).
-void scatter_host_decided(const PackedLayout &lay, uint32_t k, cls_result *out) {
-    const uint64_t n = lay.n_queries;
-    parallel_for(n, 65536, [&](uint64_t a, uint64_t b) {
-        for (uint64_t i = a; i < b; ++i) {
+// (queries [first, end) in caller order: cls_place_batch writes them piece by piece between its chunks)
+void scatter_host_decided(const PackedLayout &lay, uint32_t k, cls_result *out, uint64_t first = 0, uint64_t end = ~0ull) {
+    if (end > lay.n_queries) end = lay.n_queries;
+    if (first >= end) return;
+    parallel_for(end - first, 65536, [&](uint64_t a0, uint64_t b0) {
+        for (uint64_t i = first + a0; i < first + b0; ++i) {
             const uint64_t len = lay.lens[i];
             const uint8_t ps = lay.pre_status[i];
             if (out->n_query_kmers) out->n_query_kmers[i] = len >= k ? (uint32_t)(2 * (len - k + 1)) : 0u;
@@ -788,6 +790,7 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
     uint64_t *h_src = (uint64_t *)w->h_src.p, *d_src = (uint64_t *)w->d_src.p;
     uint8_t *h_bad = (uint8_t *)w->h_bad.p, *d_bad = (uint8_t *)w->d_bad.p, *d_ascii = (uint8_t *)w->d_ascii.p;
     size_t scattered = 0;
+    uint64_t host_done = 0;                              // queries (caller order) whose host-decided fields are written
     std::vector<uint8_t> chunk_dev(chunks.size(), 0);   // chunk packed on the device (its invalid-base flags come back with the results)
     double host_acc = 0.5;                               // mixed: error diffusion of the host's share over the chunks
     auto drain = [&](size_t upto) -> int {  // scatter the chunks whose D2H has completed (blocking up to `upto`)
@@ -920,11 +923,17 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
         }
         CU_TRY(cudaEventRecord(ev[3], st_out));
         if (ci >= 2) { rc = drain(ci - 1); if (rc != CLS_OK) return rc; }  // chunks older than the two in flight
+        // fields decided on the host (n_query_kmers of every query; queries that never reach the device), a piece of the
+        // caller's arrays per chunk - while the GPU has work, not in one pass after the last enqueue, where the last,
+        // small chunks leave the GPU before a pass over ten million queries ends.  Just-in-time plan: the reads planned so
+        // far (their lengths are known); general plan: an equal share per chunk.  A query demoted by a packer later on
+        // (invalid base) is written again by the scatter of its chunk.
+        const uint64_t upto = fast ? fast_planned : (uint64_t)((long double)nq * (ci + 1) / chunks.size());
+        scatter_host_decided(lay, ix->dix.k_size, result, host_done, upto);
+        host_done = std::max(host_done, std::min(upto, nq));
     }
-    // fields decided on the host (n_query_kmers of every query; queries that never reach the device): written
-    // while the last chunks are still on the device
     const double th = now_ms();
-    scatter_host_decided(lay, ix->dix.k_size, result);
+    scatter_host_decided(lay, ix->dix.k_size, result, host_done, nq);   // what is left (all of it when nothing reaches the device)
     if (dbg) fprintf(stderr, "[place_batch] enqueue done at %.2f ms, host-decided fields %.2f ms\n", th - t0, now_ms() - th);
     rc = drain(chunks.size());
     if (rc != CLS_OK) return rc;
