@@ -22,29 +22,32 @@ SOURCES = [(os.path.join(CSRC, "capi.cu"), True)] + [(os.path.join(CSRC, f), Fal
           [(os.path.join(HERE, "native", f), False) for f in ("capi_fake_main.cpp", "fake_kernels.cpp")]
 
 
-def _build(tmp_path, name, san):
-    """One object per source, compiled side by side; the oracle is compiled once, without a sanitizer (it is the checker,
-    and its allocations dominate the run time under one)."""
+def _compile(tmp_path, name, san):
+    """Starts the compilers: one object per source, side by side.  The oracle is compiled once, without a sanitizer (it is
+    the checker, and its allocations dominate the run time under one)."""
     out = tmp_path / name
     out.mkdir()
-    jobs = []
+    jobs, objs = [], []
     orc = tmp_path / "orc.o"
-    if not orc.exists():
-        jobs.append((subprocess.Popen(["g++", "-O2", "-std=c++17", "-pthread", "-c", os.path.join(ROOT, "oracle", "classeq_oracle.cpp"), "-o", str(orc)],
-                                      stderr=subprocess.PIPE, text=True), str(orc)))
-    objs = []
+    if not getattr(_compile, "orc_started", False):
+        _compile.orc_started = True
+        jobs.append(subprocess.Popen(["g++", "-O2", "-std=c++17", "-pthread", "-c", os.path.join(ROOT, "oracle", "classeq_oracle.cpp"), "-o", str(orc)],
+                                     stderr=subprocess.PIPE, text=True))
     for src, is_cu in SOURCES:
         obj = str(out / (os.path.basename(src) + ".o"))
         objs.append(obj)
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", *san, "-I", FAKE] + (["-x", "c++"] if is_cu else []) + ["-c", src, "-o", obj]
-        jobs.append((subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True), obj))
-    for p, obj in jobs:
+        jobs.append(subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True))
+    return jobs, objs, str(orc), str(out / "capi_fake"), san
+
+
+def _link(jobs, objs, orc, exe, san):
+    for p in jobs:
         _, err = p.communicate()
         assert "error:" not in err, err[-3000:]                      # a real build error is a failure
         if p.returncode != 0:
             pytest.skip(f"cannot build with {san} here: {err[-300:]}")
-    exe = str(out / "capi_fake")
-    r = subprocess.run(["g++", "-pthread", *san, *objs, str(orc), "-o", exe], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-pthread", *san, *objs, orc, "-o", exe], capture_output=True, text=True)
     assert "undefined reference" not in r.stderr, r.stderr[-3000:]
     if r.returncode != 0:
         pytest.skip(f"cannot link with {san} here: {r.stderr[-300:]}")
@@ -57,8 +60,9 @@ def runs(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("needs g++")
     tmp = tmp_path_factory.mktemp("capi_fake")
-    exes = {"asan": _build(tmp, "asan", ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]),
-            "tsan": _build(tmp, "tsan", ["-fsanitize=thread"])}
+    _compile.orc_started = False
+    started = [_compile(tmp, "asan", ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]), _compile(tmp, "tsan", ["-fsanitize=thread"])]
+    exes = {"asan": _link(*started[0]), "tsan": _link(*started[1])}
     # asan: the synchronous runtime (host logic, buffer sizes); tsan: every stream a worker thread (FAKE_CUDA_ASYNC=1) - a
     # missing dependency between streams, or between a stream and the host, is a data race there
     procs = {"asan": subprocess.Popen([exes["asan"]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True),
