@@ -10,12 +10,14 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include "../../include/classeq_b200.h"
 
@@ -80,6 +82,7 @@ int main(int argc, char **argv) {
     const int scale = 1;
     setenv("CLS_CHUNK_MBASES", "1", 1);           // 1 Mi bases per chunk: a few thousand reads are already several chunks
     setenv("CLS_HOST_THREADS", "4", 1);
+    setenv("CLS_SEQ_BATCH", "3000", 1);           // cls_place_sequences: several batches, so that the writer overlaps a placement
     // ---- a model: random binary tree over 24 tips, sequences evolved along it, k = 35, m = 4 -----------------------------
     const uint32_t n_tips = 24;
     std::vector<uint64_t> node_id, child_off{0}, child_idx, tip_node;
@@ -320,6 +323,72 @@ int main(int argc, char **argv) {
         cls_fasta_records dr{};
         EXPECT(cls_fasta_upload(ix, reinterpret_cast<const uint8_t *>(text.data()), text.size(), &rb, &dr) == CLS_ERR_UNSUPPORTED && !rb);
     }
+    }
+    // ---- 5c. the whole use-case in one call: cls_place_sequences = reader + the REAL cls_place_batch per batch of 3 000 queries
+    //      + the writer, which renders and appends batch i on a second thread while batch i + 1 is placed ------------------------------
+    {
+        STEP("5c. cls_place_sequences");
+        const uint64_t nn = node_id.size();
+        std::vector<int64_t> parent_id(nn, -1);
+        for (uint64_t i = 0; i < nn; ++i) for (uint64_t j = child_off[i]; j < child_off[i + 1]; ++j) parent_id[child_idx[j]] = (int64_t)node_id[i];
+        std::vector<uint8_t> children_some(nn), has_name(nn);
+        std::vector<double> support(nn), length(nn);
+        std::vector<uint64_t> name_off{0};
+        std::string names;
+        for (uint64_t i = 0; i < nn; ++i) {
+            children_some[i] = kind[i] != CLS_KIND_LEAF;
+            has_name[i] = kind[i] == CLS_KIND_LEAF;
+            if (has_name[i]) names += "tip_" + std::to_string(i);
+            name_off.push_back(names.size());
+            support[i] = kind[i] == CLS_KIND_NODE ? 70.0 + (double)(i % 30) : NAN;
+            length[i] = 0.001 * (double)(i + 1);
+        }
+        const uint64_t no_ann[2] = {0, 0};
+        cls_record_tree rt{};
+        rt.n_nodes = nn; rt.node_id = node_id.data(); rt.parent_id = parent_id.data(); rt.node_kind = kind.data(); rt.children_some = children_some.data();
+        rt.support = support.data(); rt.length = length.data(); rt.has_name = has_name.data(); rt.name_off = name_off.data(); rt.names = names.data();
+        rt.child_off = child_off.data(); rt.child_idx = child_idx.data();
+        rt.ann_clade = no_ann; rt.ann_yaml_off = no_ann; rt.ann_yaml = ""; rt.ann_json_off = no_ann; rt.ann_json = "";
+        const Batch reads = make_reads(10000, 20, 120, 0);                       // some below k: lines of the error file
+        std::string fasta, headers;
+        std::vector<uint64_t> header_off{0};
+        for (uint64_t i = 0; i < reads.n(); ++i) {
+            const std::string h = "q" + std::to_string(i) + (i % 3 ? "" : " with text");
+            if (reads.offsets[i + 1] == reads.offsets[i]) continue;             // (make_reads never makes one; the reader would drop a trailing one)
+            fasta += ">" + h + "\n";
+            fasta.append(reads.bases.begin() + (long)reads.offsets[i], reads.bases.begin() + (long)reads.offsets[i + 1]);
+            fasta += "\n";
+            headers += h;
+            header_off.push_back(headers.size());
+        }
+        char dir[] = "/tmp/capi_fake_XXXXXX";
+        if (!mkdtemp(dir)) { printf("mkdtemp failed\n"); return 1; }
+        const std::string in = std::string(dir) + "/in.fasta", out = std::string(dir) + "/res.x";
+        FILE *f = fopen(in.c_str(), "wb");
+        fwrite(fasta.data(), 1, fasta.size(), f);
+        fclose(f);
+        for (uint32_t fmt = 0; fmt < 2; ++fmt) {
+            uint64_t placed = 0;
+            EXPECT(cls_place_sequences(ix, &rt, in.c_str(), out.c_str(), &params, fmt, 1, &placed) == CLS_OK && placed == reads.n());
+            // expected: one cls_place_batch over everything (upper-cased, as the reader hands it over) + one render
+            Batch up = reads;
+            for (auto &c : up.bases) c &= 0xDF;
+            Results r(up.n());
+            cls_result rv = r.view();
+            const cls_batch bv = up.view();
+            EXPECT(cls_place_batch(ix, &bv, &params, &rv) == CLS_OK);
+            compare(up, r, orc, params, "place_sequences: the batch");
+            char *ot = nullptr, *et = nullptr;
+            uint64_t ol = 0, el = 0;
+            EXPECT(cls_records_render(&rt, up.n(), header_off.data(), headers.data(), &rv, fmt, &ot, &ol, &et, &el) == CLS_OK);
+            auto slurp = [](const std::string &p) { std::string t; FILE *g = fopen(p.c_str(), "rb"); if (!g) return t; char buf[65536]; size_t k; while ((k = fread(buf, 1, sizeof buf, g)) > 0) t.append(buf, k); fclose(g); return t; };
+            const std::string got_o = slurp(std::string(dir) + (fmt ? "/res.jsonl" : "/res.yaml")), got_e = slurp(std::string(dir) + "/res.error");
+            EXPECT(ot && got_o == std::string(ot, ol) && ol > 100000);
+            EXPECT(et && got_e.size() >= el && got_e.compare(got_e.size() - el, el, et, el) == 0 && el > 0);   // the error file is appended to
+            cls_text_free(ot); cls_text_free(et);
+        }
+        for (const char *n : {"/in.fasta", "/res.yaml", "/res.jsonl", "/res.error"}) remove((std::string(dir) + n).c_str());
+        rmdir(dir);
     }
     STEP("6. concurrent callers");
     // ---- 6. concurrent callers on one handle (per-call workspaces) -------------------------------------------------------------
