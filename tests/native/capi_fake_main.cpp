@@ -174,12 +174,13 @@ int main(int argc, char **argv) {
         }
     EXPECT(fakek::pack_launches > 0);
     if (!threads_only) {
-    // ---- 2. the fallback of the just-in-time plan: one read that is too short / too long / invalid, late in the batch ------
+    // ---- 2. late in a batch of short reads: one read that is too short / too long (the just-in-time plan falls back to the
+    //      general one), or reads with an invalid base (it does not: the packer that meets them flags them) ------
     for (int kind_of = 0; kind_of < 3; ++kind_of)
         for (int mode = 1 + kind_of % 2; mode <= 2; mode += 2) {
             cls_set_pack_mode(mode);
             Batch b = make_reads(7000, 40, 80, 0);
-            Batch odd = kind_of == 0 ? make_reads(1, 10, 20, 0) : kind_of == 1 ? make_reads(1, 300, 300, 0) : make_reads(4, 60, 60, 1);
+            Batch odd = kind_of == 0 ? make_reads(1, 10, 20, 0) : kind_of == 1 ? make_reads(1, 300, 300, 0) : make_reads(8, 60, 60, 4);
             b.bases.insert(b.bases.end(), odd.bases.begin(), odd.bases.begin() + (long)odd.offsets.back());
             for (uint64_t i = 1; i < odd.offsets.size(); ++i) b.offsets.push_back(b.offsets[7000] + odd.offsets[i]);
             const Batch tail = make_reads(500, 40, 80, 0);
