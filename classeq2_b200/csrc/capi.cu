@@ -827,7 +827,12 @@ static int place_batch_impl(cls_index *ix, const cls_batch *batch, const cls_par
     // chunks never share the SMs (with everything of a chunk on one of two alternating streams the scan kernel of chunk
     // c + 1 starts while the descent kernel of chunk c still holds warp slots: 8.13 against 7.70 ms per 1 M reads end to
     // end, profiles/r2a).  CLS_PIPE=2 selects the two-stream pipeline (A/B).
-    static const bool pipe3 = [] { const char *e = getenv("CLS_PIPE"); return !(e && atoi(e) == 2); }();
+    // With device packing the bases go up in pieces that do not end where the chunks end: a piece copied for chunk c holds
+    // the first bases of chunk c + 1, so all copies in have to share ONE stream for a chunk's pack kernel to wait for them
+    // (the two-stream pipeline let it read bases another stream was still copying: found by ThreadSanitizer on the fake
+    // runtime with asynchronous streams, tests/test_capi_fake.py) - device packing always takes the three-stream pipeline.
+    static const bool pipe3_env = [] { const char *e = getenv("CLS_PIPE"); return !(e && atoi(e) == 2); }();
+    const bool pipe3 = pipe3_env || dev_pack;
     if (pipe3 && !w->stream3) CU_TRY(cudaStreamCreateWithFlags(&w->stream3, cudaStreamNonBlocking));
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         if (fast) {   // the layout of this chunk's reads, just in time
