@@ -81,7 +81,7 @@ int main(int argc, char **argv) {
     const bool threads_only = argc > 1 && !strcmp(argv[1], "threads");   // the ThreadSanitizer build: the scenarios with more than one host thread
     const int scale = 1;
     setenv("CLS_CHUNK_MBASES", "1", 1);           // 1 Mi bases per chunk: a few thousand reads are already several chunks
-    setenv("CLS_HOST_THREADS", "4", 1);
+    setenv("CLS_HOST_THREADS", "4", 0);   // (not overwritten: a run with one thread takes the pool out)
     setenv("CLS_SEQ_BATCH", "3000", 1);           // cls_place_sequences: several batches, so that the writer overlaps a placement
     // ---- a model: random binary tree over 24 tips, sequences evolved along it, k = 35, m = 4 -----------------------------
     const uint32_t n_tips = 24;
