@@ -435,6 +435,53 @@ int main(int argc, char **argv) {
             cls_index_destroy(multi);
         }
     }
+    // ---- 8. an allocation that fails (device or pinned), at every position in turn: the call reports it, nothing is leaked,
+    //      and the same handle places the batch once memory is back -----------------------------------------------------------------
+    if (!threads_only) {
+        STEP("8. failing allocations");
+        const Batch b = make_reads(600, 30, 300, 7);
+        const cls_batch bv = b.view();
+        int failed_creates = 0, failed_calls = 0;
+        for (long n = 1; n < 200; ++n) {                                    // cls_index_create
+            const long before = fakecuda::live_allocs();
+            fakecuda::fail_alloc_in() = n;
+            cls_index *x = nullptr;
+            const int rc = cls_index_create(&model, 1, &x);
+            const bool hit = fakecuda::fail_alloc_in().exchange(0) == 0;     // the failure was consumed
+            if (!hit) { EXPECT(rc == CLS_OK && x); cls_index_destroy(x); EXPECT(fakecuda::live_allocs() == before); break; }
+            EXPECT(rc != CLS_OK && !x && cls_last_error()[0] != 0);
+            EXPECT(fakecuda::live_allocs() == before);
+            ++failed_creates;
+        }
+        for (int mode = 1; mode <= 2; ++mode) {                             // cls_place_batch and the resident calls, host and device packing
+            cls_set_pack_mode(mode);
+            for (long n = 1; n < 200; ++n) {
+                cls_index *x = nullptr;
+                EXPECT(cls_index_create(&model, 2, &x) == CLS_OK);
+                if (!x) break;
+                Results r(b.n());
+                cls_result rv = r.view();
+                fakecuda::fail_alloc_in() = n;
+                const int rc = cls_place_batch(x, &bv, &params, &rv);
+                cls_resident_batch *rb = nullptr;
+                const int rc2 = rc == CLS_OK ? cls_batch_upload(x, &bv, &rb) : CLS_OK;
+                const int rc3 = rb ? cls_place_resident(x, rb, &params, nullptr) : CLS_OK;
+                const int rc4 = rb && rc3 == CLS_OK ? cls_resident_fetch(x, rb, nullptr, &rv) : CLS_OK;
+                const bool hit = fakecuda::fail_alloc_in().exchange(0) == 0;
+                EXPECT(hit == (rc != CLS_OK || rc2 != CLS_OK || rc3 != CLS_OK || rc4 != CLS_OK));
+                failed_calls += hit;
+                if (rb) cls_resident_destroy(rb);
+                Results again(b.n());
+                cls_result av = again.view();
+                EXPECT(cls_place_batch(x, &bv, &params, &av) == CLS_OK);    // memory is back: the handle works
+                compare(b, again, orc, params, "after a failed allocation");
+                cls_index_destroy(x);
+                if (!hit) break;
+            }
+        }
+        cls_set_pack_mode(0);
+        EXPECT(failed_creates >= 8 && failed_calls >= 10);
+    }
     fakek::oracle_model = nullptr;
     orc_model_destroy(orc);
     cls_built_model_destroy(bm);

@@ -12,6 +12,7 @@
 // The kernels' launch functions are supplied by tests/native/fake_kernels.cpp.  Nothing of this is ever linked into the
 // product.
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -97,6 +98,9 @@ inline std::map<const char *, size_t> &pinned() { static std::map<const char *, 
 inline int device_count() { const char *e = getenv("FAKE_CUDA_DEVICES"); const int n = e ? atoi(e) : 4; return n > 0 ? n : 4; }
 inline int &current() { static thread_local int d = 0; return d; }
 inline long &live_allocs() { static long n = 0; return n; }    // device + pinned allocations not yet freed (leak check of the tests)
+// Fault injection: the N-th allocation from now on (device or pinned) fails, once (0: off).
+inline std::atomic<long> &fail_alloc_in() { static std::atomic<long> n{0}; return n; }
+inline bool alloc_fails() { long n = fail_alloc_in().load(); while (n > 0 && !fail_alloc_in().compare_exchange_weak(n, n - 1)) {} return n == 1; }
 inline bool &skip_copies() { static bool b = false; return b; }   // host-overhead timing (tools/micro/host_floor.cpp): a DMA costs the host nothing
 }  // namespace fakecuda
 
@@ -112,6 +116,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) {
 inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { fakecuda::sync_all_streams(); return cudaSuccess; }
 inline cudaError_t cudaMalloc(void **p, size_t n) {
+    if (fakecuda::alloc_fails()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     *p = malloc(n ? n : 1);
     if (!*p) return cudaErrorMemoryAllocation;
     std::lock_guard<std::mutex> lk(fakecuda::mu());
@@ -125,6 +130,7 @@ inline cudaError_t cudaFree(void *p) {
     return cudaSuccess;
 }
 inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) {
+    if (fakecuda::alloc_fails()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     *p = malloc(n ? n : 1);
     if (!*p) return cudaErrorMemoryAllocation;
     std::lock_guard<std::mutex> lk(fakecuda::mu());
