@@ -437,9 +437,9 @@ int main(int argc, char **argv) {
     }
     // ---- 8. an allocation that fails (device or pinned), at every position in turn: the call reports it, nothing is leaked,
     //      and the same handle places the batch once memory is back -----------------------------------------------------------------
-    if (!threads_only) {
+    if (!threads_only && !fakecuda::async()) {
         STEP("8. failing allocations");
-        const Batch b = make_reads(600, 30, 300, 7);
+        const Batch b = make_reads(40, 30, 300, 7);
         const cls_batch bv = b.view();
         int failed_creates = 0, failed_calls = 0;
         for (long n = 1; n < 200; ++n) {                                    // cls_index_create
