@@ -25,6 +25,7 @@ namespace fakek {
 extern const void *oracle_model;
 extern std::atomic<uint64_t> place_launches, pack_launches, reads_placed, async_errors;
 extern std::atomic<uint32_t> fail_above_len;
+extern std::atomic<bool> null_placement;
 }  // namespace fakek
 extern "C" {
 void *orc_model_create(const void *view);
@@ -481,6 +482,44 @@ int main(int argc, char **argv) {
         }
         cls_set_pack_mode(0);
         EXPECT(failed_creates >= 8 && failed_calls >= 10);
+    }
+    // ---- 9. a CUDA call that reports an error, at every position of a call of several chunks in turn: the call reports it and
+    //      leaves NOTHING in flight on its workspace - the very next call on the handle takes the same workspace and must give
+    //      the same results (with asynchronous streams a copy or a launch that outlived the failed call would race with it).
+    //      The launches write "no match" records here: what is compared is one call against another --------------------------------
+    {
+        STEP("9. failing CUDA calls");
+        fakek::null_placement = true;
+        const Batch b = make_reads(9000, 36, 90, 0);
+        const cls_batch bv = b.view();
+        int failed_calls = 0;
+        for (int mode = 1; mode <= 2; ++mode) {
+            cls_set_pack_mode(mode);
+            cls_index *x = nullptr;
+            EXPECT(cls_index_create(&model, 0, &x) == CLS_OK);
+            if (!x) break;
+            Results ref(b.n());
+            cls_result refv = ref.view();
+            EXPECT(cls_place_batch(x, &bv, &params, &refv) == CLS_OK);
+            for (long n = 1; n < 400; ++n) {
+                Results r(b.n());
+                cls_result rv = r.view();
+                fakecuda::fail_call_in() = n;
+                const int rc = cls_place_batch(x, &bv, &params, &rv);
+                const bool hit = fakecuda::fail_call_in().exchange(0) == 0;
+                EXPECT(hit == (rc != CLS_OK));
+                failed_calls += hit;
+                Results again(b.n());
+                cls_result av = again.view();
+                EXPECT(cls_place_batch(x, &bv, &params, &av) == CLS_OK);
+                EXPECT(again.status == ref.status && again.node == ref.node && again.nq == ref.nq && again.nm == ref.nm);
+                if (!hit) break;
+            }
+            cls_index_destroy(x);
+        }
+        cls_set_pack_mode(0);
+        fakek::null_placement = false;
+        EXPECT(failed_calls >= 40);
     }
     fakek::oracle_model = nullptr;
     orc_model_destroy(orc);

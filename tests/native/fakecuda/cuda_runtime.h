@@ -101,13 +101,17 @@ inline long &live_allocs() { static long n = 0; return n; }    // device + pinne
 // Fault injection: the N-th allocation from now on (device or pinned) fails, once (0: off).
 inline std::atomic<long> &fail_alloc_in() { static std::atomic<long> n{0}; return n; }
 inline bool alloc_fails() { long n = fail_alloc_in().load(); while (n > 0 && !fail_alloc_in().compare_exchange_weak(n, n - 1)) {} return n == 1; }
+// ... and the N-th call of any of the functions below that can report an error (0: off).  A synchronising call that "fails"
+// has still synchronised: what is injected is the error code, not a broken runtime.
+inline std::atomic<long> &fail_call_in() { static std::atomic<long> n{0}; return n; }
+inline bool call_fails() { long n = fail_call_in().load(); while (n > 0 && !fail_call_in().compare_exchange_weak(n, n - 1)) {} return n == 1; }
 inline bool &skip_copies() { static bool b = false; return b; }   // host-overhead timing (tools/micro/host_floor.cpp): a DMA costs the host nothing
 }  // namespace fakecuda
 
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorInvalidConfiguration ? "invalid configuration" : "fake CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = fakecuda::device_count(); return cudaSuccess; }
-inline cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= fakecuda::device_count()) return cudaErrorInvalidDevice; fakecuda::current() = d; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int d) { if (fakecuda::call_fails()) return cudaErrorUnknown; if (d < 0 || d >= fakecuda::device_count()) return cudaErrorInvalidDevice; fakecuda::current() = d; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) {
     if (d < 0 || d >= fakecuda::device_count()) return cudaErrorInvalidDevice;
     p->major = 10; p->minor = 0; p->multiProcessorCount = 148;
@@ -116,7 +120,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d) {
 inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { fakecuda::sync_all_streams(); return cudaSuccess; }
 inline cudaError_t cudaMalloc(void **p, size_t n) {
-    if (fakecuda::alloc_fails()) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    if (fakecuda::call_fails() || fakecuda::alloc_fails()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     *p = malloc(n ? n : 1);
     if (!*p) return cudaErrorMemoryAllocation;
     std::lock_guard<std::mutex> lk(fakecuda::mu());
@@ -130,7 +134,7 @@ inline cudaError_t cudaFree(void *p) {
     return cudaSuccess;
 }
 inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) {
-    if (fakecuda::alloc_fails()) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    if (fakecuda::call_fails() || fakecuda::alloc_fails()) { *p = nullptr; return cudaErrorMemoryAllocation; }
     *p = malloc(n ? n : 1);
     if (!*p) return cudaErrorMemoryAllocation;
     std::lock_guard<std::mutex> lk(fakecuda::mu());
@@ -154,15 +158,17 @@ inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void
     }
     return cudaSuccess;
 }
-inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (fakecuda::call_fails()) return cudaErrorUnknown; if (n) memcpy(d, s, n); return cudaSuccess; }
 // (the blocking calls and the NULL stream run on the calling thread: the library's pipelines use their own non-blocking streams)
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t st) {
+    if (fakecuda::call_fails()) return cudaErrorUnknown;
     if (n && !fakecuda::skip_copies()) fakecuda::enqueue(st, [d, s, n] { memcpy(d, s, n); });
     return cudaSuccess;
 }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { if (n) fakecuda::enqueue(st, [d, v, n] { memset(d, v, n); }); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { if (fakecuda::call_fails()) return cudaErrorUnknown; if (n) fakecuda::enqueue(st, [d, v, n] { memset(d, v, n); }); return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+    if (fakecuda::call_fails()) { *s = nullptr; return cudaErrorUnknown; }
     FakeCudaStream *st = new FakeCudaStream;
     st->device = fakecuda::current();
     if (fakecuda::async()) {
@@ -173,7 +179,7 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
     *s = st;
     return cudaSuccess;
 }
-inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { if (fakecuda::async() && s) s->drain(); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { if (fakecuda::async() && s) s->drain(); return fakecuda::call_fails() ? cudaErrorUnknown : cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
     if (!s) return cudaSuccess;
     if (fakecuda::async()) {
@@ -187,19 +193,21 @@ inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
     delete s;
     return cudaSuccess;
 }
-inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new FakeCudaEvent; return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { if (fakecuda::call_fails()) { *e = nullptr; return cudaErrorUnknown; } *e = new FakeCudaEvent; return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 // The event's fields belong to the host thread that uses it (as in the library: one workspace, one caller at a time);
 // what crosses to the stream threads is the ticket of one record.
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+    if (fakecuda::call_fails()) return cudaErrorUnknown;
     auto t = std::make_shared<fakecuda::Ticket>();
     e->cur = t;
     fakecuda::enqueue(s, [t] { t->signal(); });
     return cudaSuccess;
 }
-inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { if (e->cur) e->cur->wait(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { if (e->cur) e->cur->wait(); return fakecuda::call_fails() ? cudaErrorUnknown : cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    if (fakecuda::call_fails()) return cudaErrorUnknown;
     if (std::shared_ptr<fakecuda::Ticket> t = e->cur) fakecuda::enqueue(s, [t] { t->wait(); });   // the record seen at the time of the call
     return cudaSuccess;
 }
