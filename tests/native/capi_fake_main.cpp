@@ -328,7 +328,7 @@ int main(int argc, char **argv) {
     }
     // ---- 5c. the whole use-case in one call: cls_place_sequences = reader + the REAL cls_place_batch per batch of 3 000 queries
     //      + the writer, which renders and appends batch i on a second thread while batch i + 1 is placed ------------------------------
-    {
+    if (threads_only || fakecuda::async()) {                  // (a scenario about threads: the runs with asynchronous streams take it)
         STEP("5c. cls_place_sequences");
         const uint64_t nn = node_id.size();
         std::vector<int64_t> parent_id(nn, -1);
@@ -454,6 +454,36 @@ int main(int argc, char **argv) {
             EXPECT(fakecuda::live_allocs() == before);
             ++failed_creates;
         }
+        for (long n = 1; n < 200; ++n) {                                    // one handle over three devices: the replicas made so far are released
+            const long before = fakecuda::live_allocs();
+            fakecuda::fail_alloc_in() = n;
+            cls_index *x = nullptr;
+            const int rc = cls_index_create_multi(&model, 0b111, &x);
+            const bool hit = fakecuda::fail_alloc_in().exchange(0) == 0;
+            if (x) cls_index_destroy(x);
+            EXPECT(hit == (rc != CLS_OK) && (rc == CLS_OK) == (x != nullptr) && fakecuda::live_allocs() == before);
+            failed_creates += hit;
+            if (!hit) break;
+        }
+        {                                                                   // cls_fasta_upload: its temporaries and the batch it was building
+            const std::string text = ">a\nACGTTGCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGATCCCCGGGTACCGAGCTCGAATTC\n>b\nACGTTGCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGATCCCC\n";
+            cls_index *x = nullptr;
+            EXPECT(cls_index_create(&model, 0, &x) == CLS_OK);
+            for (long n = 1; n < 200 && x; ++n) {
+                const long before = fakecuda::live_allocs();
+                fakecuda::fail_alloc_in() = n;
+                cls_resident_batch *rb = nullptr;
+                cls_fasta_records dr{};
+                const int rc = cls_fasta_upload(x, reinterpret_cast<const uint8_t *>(text.data()), text.size(), &rb, &dr);
+                const bool hit = fakecuda::fail_alloc_in().exchange(0) == 0;
+                EXPECT(hit == (rc != CLS_OK) && (rc == CLS_OK) == (rb != nullptr));
+                if (rb) { EXPECT(dr.n_records == 2); cls_resident_destroy(rb); }
+                EXPECT(fakecuda::live_allocs() == before);
+                failed_calls += hit;
+                if (!hit) break;
+            }
+            cls_index_destroy(x);
+        }
         for (int mode = 1; mode <= 2; ++mode) {                             // cls_place_batch and the resident calls, host and device packing
             cls_set_pack_mode(mode);
             for (long n = 1; n < 200; ++n) {
@@ -481,7 +511,7 @@ int main(int argc, char **argv) {
             }
         }
         cls_set_pack_mode(0);
-        EXPECT(failed_creates >= 8 && failed_calls >= 10);
+        EXPECT(failed_creates >= 30 && failed_calls >= 20);
     }
     // ---- 9. a CUDA call that reports an error, at every position of a call of several chunks in turn: the call reports it and
     //      leaves NOTHING in flight on its workspace - the very next call on the handle takes the same workspace and must give
