@@ -180,10 +180,10 @@ int main(int argc, char **argv) {
     for (int kind_of = 0; kind_of < 3; ++kind_of)
         for (int mode = 1 + kind_of % 2; mode <= 2; mode += 2) {
             cls_set_pack_mode(mode);
-            Batch b = make_reads(7000, 40, 80, 0);
+            Batch b = make_reads(4500, 40, 80, 0);   // (the first chunk holds 4 096 reads: the odd ones arrive while it is in flight)
             Batch odd = kind_of == 0 ? make_reads(1, 10, 20, 0) : kind_of == 1 ? make_reads(1, 300, 300, 0) : make_reads(8, 60, 60, 4);
             b.bases.insert(b.bases.end(), odd.bases.begin(), odd.bases.begin() + (long)odd.offsets.back());
-            for (uint64_t i = 1; i < odd.offsets.size(); ++i) b.offsets.push_back(b.offsets[7000] + odd.offsets[i]);
+            for (uint64_t i = 1; i < odd.offsets.size(); ++i) b.offsets.push_back(b.offsets[4500] + odd.offsets[i]);
             const Batch tail = make_reads(500, 40, 80, 0);
             const uint64_t base = b.offsets.back();
             b.bases.insert(b.bases.end(), tail.bases.begin(), tail.bases.end());
