@@ -709,12 +709,21 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
         elif str(query_sequence) == "-":
             raw = sys.stdin.buffer.read()
         else:
-            with open(query_sequence, "rb") as f:
-                raw = f.read()
+            try:
+                with open(query_sequence, "rb") as f:
+                    raw = f.read()
+            except OSError:
+                # a query that cannot be opened or read is not an error of the use-case: the reference drops the reader's
+                # Result (`let _ = query_sequence.sequence_content_by_channel(sender)`, mod.rs:119), has created both files
+                # by then (:111-115) and returns Ok with nothing placed - as cls_sequences_open does
+                raw = b""
         headers, host_bases, host_offsets = read_fasta_native(raw)
         records = [(h, None) for h in headers]
     else:
-        records = read_fasta(query_sequence)
+        try:
+            records = read_fasta(query_sequence)
+        except OSError:
+            records = []
     lookup = _TreeLookup(tree) if writer == "python" else None
     rtree = RecordTree(tree) if writer == "native" else None
     params = PlaceParams(max_iterations, min_match_coverage, remove_intersection)

@@ -256,3 +256,31 @@ def test_build_database_mirror_equals_oracle(tmp_path, oracle, col_queries, col_
     except OSError:
         pytest.skip("libzstd not available")
     assert cq.load_database(out).to_obj() == tree.to_obj()
+
+
+def test_a_query_that_cannot_be_read_places_nothing_and_is_not_an_error(tmp_path, col_tree, col_flat):
+    """mod.rs:111-119: both files are created, then the reader's Result is dropped (`let _ = ...`): Ok, nothing placed.
+    The Python driver (both readers) and cls_sequences_open behave alike; a result file that cannot be removed under
+    `overwrite` is the reference's "Could not remove file" error (:103-110)."""
+    import ctypes as C
+    import classeq2_b200 as cq
+    from classeq2_b200 import _lib
+    from test_record_writer import _OracleIndex
+    tree = cq.Tree.from_obj(col_tree.to_obj())
+    index = _OracleIndex(col_flat)
+    for reader in ("native", "python"):
+        out = tmp_path / reader / "r.out"
+        times = cq.place_sequences(tmp_path / "no_such.fasta", tree, out, index=index, reader=reader)
+        assert times == []
+        assert (tmp_path / reader / "r.yaml").read_bytes() == b"" and (tmp_path / reader / "r.error").read_bytes() == b""
+    index.close()
+    h, b = C.c_void_p(), _lib.Batch()
+    out = tmp_path / "c" / "r.out"
+    assert _lib.lib.cls_sequences_open(str(tmp_path / "no_such.fasta").encode(), str(out).encode(), 0, 0, C.byref(h), C.byref(b)) == 0
+    assert int(b.n_queries) == 0
+    _lib.lib.cls_sequences_close(h)
+    assert (tmp_path / "c" / "r.yaml").read_bytes() == b"" and (tmp_path / "c" / "r.error").read_bytes() == b""
+    # overwrite = true, but the "file" in the way is a directory with something in it: remove() fails
+    (tmp_path / "d" / "r.yaml" / "x").mkdir(parents=True)
+    rc = _lib.lib.cls_sequences_open(str(tmp_path / "no_such.fasta").encode(), str(tmp_path / "d" / "r.out").encode(), 0, 1, C.byref(h), C.byref(b))
+    assert rc == _lib.CLS_ERR_INVALID_ARGUMENT and _lib.last_error().startswith("Could not remove file given ")
