@@ -698,8 +698,11 @@ def place_sequences(query_sequence, tree: Tree, out_file: Union[str, os.PathLike
     if ingest == "device":
         if hasattr(query_sequence, "read") or str(query_sequence) == "-":
             raise ValueError("ingest='device' reads a file path")
-        with open(query_sequence, "rb") as f:
-            raw = f.read()
+        try:
+            with open(query_sequence, "rb") as f:
+                raw = f.read()
+        except OSError:
+            raw = b""                                                          # nothing placed, no error (see below)
         device_batch, headers, _ = index.upload_fasta(raw)
         records = [(h, None) for h in headers]
         batch_size = max(len(records), 1)
